@@ -1,0 +1,293 @@
+/*
+ * terrarium_b200.h -- C ABI of the B200-native per-column land time-step.
+ *
+ * This is the drop-in boundary for ONE hot path of Terrarium.jl: everything that runs inside
+ *   timestep!(integrator::ModelIntegrator, ::ForwardEuler | ::Heun, dt)
+ *   (reference: src/timesteppers/forward_euler.jl:19-31, src/timesteppers/heun.jl:37-71),
+ * i.e. update_state! (src/state_variables.jl:72-80), explicit_step!
+ * (src/timesteppers/abstract_timestepper.jl:65-77) and closure! (src/models/soil/soil_model.jl:51-54,
+ * src/models/coupled/land_model.jl:98-102) for SoilModel and (bare-ground) LandModel on a
+ * ColumnGrid / ColumnRingGrid.  The reference has no FFI of its own for this path (it is pure Julia
+ * dispatching KernelAbstractions kernels through Oceananigans' launch!, src/grids/grid_utils.jl:2-6);
+ * the entry points below are what a `ccall` based Julia method of timestep!/run!/initialize would bind
+ * (see INTEGRATION.md and terrarium.jl_b200/julia/TerrariumB200.jl).
+ *
+ * Conventions
+ *  - every function returns an int status (TRM_OK == 0); a human readable message for the last
+ *    failure on the calling thread is available from trm_last_error();
+ *  - no exception, no torch/ATen type, no C++ type crosses this boundary: plain pointers and sizes;
+ *  - a handle owns all of its device memory; pointers handed out by trm_field_ptr are borrowed;
+ *  - calls on one handle must be serialised by the caller; work is stream ordered on the handle's
+ *    stream, trm_sync() blocks until it is complete;
+ *  - one handle drives one GPU and one contiguous column range [col0, col0+ncol) of the domain.
+ *    Columns never exchange data (reference: only d/dz operators, src/Terrarium.jl:27), so a
+ *    multi-GPU run is N handles (one process per GPU) with no halo exchange;
+ *  - memory layout of every 3-D field is SoA [layer][column], column fastest, layer 0 = BOTTOM
+ *    cell (reference convention, docs/src/introduction/numerical_core.md:21-22), leading dimension
+ *    `ld` >= ncol padded to 256 bytes so that rows are 128-bit vector aligned;
+ *  - all floating point parameters are passed as double and converted once to the handle's
+ *    number format NF (float or double), the way Julia constructs `Struct{NF}` from literals.
+ *
+ * The identical ABI (prefix orc_ instead of trm_) is exported by the CPU oracle in oracle/, which
+ * is test infrastructure only and is never loaded by the product path.
+ */
+#ifndef TERRARIUM_B200_H
+#define TERRARIUM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRM_ABI_VERSION 1
+#define TRM_MAX_NZ 128       /* per-column layers supported by the fused kernels            */
+#define TRM_NUM_USER_INPUTS 8
+
+/* ---- status codes ---------------------------------------------------------------------- */
+enum trm_status {
+    TRM_OK = 0,
+    TRM_ERR_INVALID = 1,      /* bad argument / configuration                                */
+    TRM_ERR_CUDA = 2,         /* CUDA runtime failure (message has the CUDA error string)    */
+    TRM_ERR_STATE = 3,        /* call sequence error (e.g. step before initialize)           */
+    TRM_ERR_UNSUPPORTED = 4,  /* valid in the reference but not built here                   */
+    TRM_ERR_NO_DEVICE = 5     /* no usable CUDA device: the product path has NO CPU fallback */
+};
+
+/* ---- enumerations ---------------------------------------------------------------------- */
+enum trm_dtype       { TRM_F32 = 0, TRM_F64 = 1 };
+/* SoilModel (src/models/soil/soil_model.jl:9-59), LandModel with vegetation = nothing
+ * (src/models/coupled/land_model.jl:111-125: BareGroundEvaporation + NoCanopyInterception). */
+enum trm_model       { TRM_MODEL_SOIL = 0, TRM_MODEL_LAND = 1 };
+enum trm_timestepper { TRM_EULER = 0, TRM_HEUN = 1 };
+/* src/processes/soil/hydrology/soil_hydrology.jl:13 (NoFlow), soil_hydrology_rre.jl:18 (RichardsEq) */
+enum trm_hydrology   { TRM_NOFLOW = 0, TRM_RICHARDS = 1 };
+/* FreezeCurves.jl SWRC types used at soil_hydraulic_closures.jl:95-97,115-118 */
+enum trm_swrc        { TRM_SWRC_VANGENUCHTEN = 0, TRM_SWRC_BROOKSCOREY = 1 };
+/* src/processes/soil/hydrology/soil_hydraulic_properties.jl:163-221 */
+enum trm_unsat_k     { TRM_UNSATK_LINEAR = 0, TRM_UNSATK_VANGENUCHTEN = 1 };
+/* What the never-filled z-halo of the auxiliary saturation field holds under NoFlow hydrology
+ * (unpinned Oceananigans `set!` semantics). Richards always copies. */
+enum trm_halo        { TRM_HALO_ZERO = 0, TRM_HALO_COPY = 1 };
+/* Skin temperature scheme, src/processes/surface_energy/skin_temperature.jl:12,52 */
+enum trm_skin        { TRM_SKIN_IMPLICIT = 0, TRM_SKIN_PRESCRIBED = 1 };
+/* Arithmetic contract of the CUDA kernels.
+ *  FAITHFUL: same operations in the same order as the reference/oracle (true divisions,
+ *            pow where the reference calls ^), no FMA contraction.
+ *  FAST:     algebraically identical but uses reciprocal metrics, cbrt/sqrt/rsqrt special cases
+ *            for van Genuchten n = 2 and FMA contraction. Results differ from FAITHFUL by
+ *            rounding only (tests pin the tolerance).                                        */
+enum trm_math        { TRM_MATH_FAITHFUL = 0, TRM_MATH_FAST = 1 };
+
+/* Boundary conditions (Oceananigans Value/Gradient/Flux semantics). */
+enum trm_bc_kind { TRM_BC_DEFAULT = 0 /* zero flux */, TRM_BC_VALUE = 1, TRM_BC_GRADIENT = 2, TRM_BC_FLUX = 3 };
+enum trm_bc_slot {
+    TRM_BC_TEMPERATURE_TOP = 0,   /* PrescribedSurfaceTemperature, src/models/soil/soil_model_bcs.jl:17 */
+    TRM_BC_TEMPERATURE_BOTTOM = 1,/* PrescribedBottomTemperature, :22                                    */
+    TRM_BC_ENERGY_TOP = 2,        /* GroundHeatFlux (Flux on internal_energy), :6                        */
+    TRM_BC_ENERGY_BOTTOM = 3,     /* GeothermalHeatFlux, :12                                             */
+    TRM_BC_SATURATION_TOP = 4,    /* InfiltrationFlux, :29 (value is the flux itself, positive upward)   */
+    TRM_BC_SATURATION_BOTTOM = 5, /* ImpermeableBoundary, :34                                            */
+    TRM_BC_PRESSURE_TOP = 6,
+    TRM_BC_PRESSURE_BOTTOM = 7,   /* FreeDrainage = Gradient(0), :40                                     */
+    TRM_BC_NSLOTS = 8
+};
+
+/* Per-column 2-D input variables (src/input_output/input_sources.jl; atmosphere inputs of
+ * src/processes/atmosphere/prescribed_atmosphere.jl:89-99,147-149,192-195,220-224). */
+enum trm_input_id {
+    TRM_IN_USER0 = 0,  /* .. TRM_IN_USER0 + TRM_NUM_USER_INPUTS-1: BC inputs such as T_ub */
+    TRM_IN_AIR_TEMPERATURE = 8,
+    TRM_IN_AIR_PRESSURE = 9,
+    TRM_IN_WINDSPEED = 10,
+    TRM_IN_SPECIFIC_HUMIDITY = 11,
+    TRM_IN_RAINFALL = 12,
+    TRM_IN_SNOWFALL = 13,
+    TRM_IN_SHORTWAVE_DOWN = 14,
+    TRM_IN_LONGWAVE_DOWN = 15,
+    TRM_IN_DAYTIME_LENGTH = 16,
+    TRM_IN_CO2 = 17,
+    TRM_IN_SKIN_TEMPERATURE = 18, /* only read with TRM_SKIN_PRESCRIBED */
+    TRM_IN_COUNT = 19
+};
+/* How an input is produced at clock time t (device resident, evaluated inside the stage kernel). */
+enum trm_source {
+    TRM_SRC_CONST = 0,     /* one scalar for all columns                                        */
+    TRM_SRC_FIELD = 1,     /* per-column vector owned by the handle, set with trm_set_input_field */
+    TRM_SRC_SINUSOID = 2,  /* clamp(mean[c] + amp[c]*sin(2*pi*t/period - phase[c]), lo, hi)      */
+    TRM_SRC_TABLE = 3      /* snapshots values[nt][ncol] at times[nt]; linear in time, flat outside
+                              (Oceananigans FieldTimeSeries[Time(t)]; ext/TerrariumRastersExt:104-120) */
+};
+
+/* Fields that can be read / written / borrowed. 3-D fields are [nz][ld]; the hydraulic
+ * conductivity is a z-face field [nz+1][ld]; 2-D fields are [ld]. */
+enum trm_field_id {
+    TRM_F_INTERNAL_ENERGY = 0,        /* prognostic, src/processes/soil/energy/soil_energy.jl:47       */
+    TRM_F_TEMPERATURE = 1,            /* closure, soil_energy_closures.jl:22-25                        */
+    TRM_F_LIQUID_WATER_FRACTION = 2,
+    TRM_F_SATURATION_WATER_ICE = 3,   /* auxiliary (NoFlow) / prognostic (Richards)                    */
+    TRM_F_PRESSURE_HEAD = 4,          /* closure, soil_hydraulic_closures.jl:14-16 (Richards only)     */
+    TRM_F_HYDRAULIC_CONDUCTIVITY = 5, /* z-face auxiliary, soil_hydrology.jl:81                        */
+    TRM_F_SURFACE_EXCESS_WATER = 6,   /* prognostic 2-D (Richards)                                     */
+    TRM_F_WATER_TABLE = 7,
+    TRM_F_GROUND_TEMPERATURE = 8,     /* read-only alias of the top temperature layer                  */
+    TRM_F_SKIN_TEMPERATURE = 9,       /* LandModel 2-D fields from here                                */
+    TRM_F_GROUND_HEAT_FLUX = 10,
+    TRM_F_SHORTWAVE_UP = 11,
+    TRM_F_LONGWAVE_UP = 12,
+    TRM_F_NET_RADIATION = 13,
+    TRM_F_SENSIBLE_HEAT_FLUX = 14,
+    TRM_F_LATENT_HEAT_FLUX = 15,
+    TRM_F_EVAPORATION_GROUND = 16,
+    TRM_F_INFILTRATION = 17,
+    TRM_F_SURFACE_RUNOFF = 18,
+    TRM_F_TEND_INTERNAL_ENERGY = 19,  /* materialised only by trm_compute_tendencies (debug/tests)     */
+    TRM_F_TEND_SATURATION = 20,
+    TRM_F_COUNT = 21
+};
+
+/* ---- parameters ---------------------------------------------------------------------------
+ * Defaults (trm_default_params) are the reference's package defaults. */
+typedef struct trm_params {
+    /* ConstantSoilPorosity, src/processes/soil/stratigraphy/soil_porosity.jl:7-13 */
+    double mineral_porosity;      /* 0.49 */
+    double organic_porosity;      /* 0.9  */
+    /* ConstantSoilCarbonDensity, src/processes/soil/biogeochem/constant_soil_carbon.jl:10-16 */
+    double rho_soc;               /* 0.0  */
+    double rho_org;               /* 1300 */
+    /* SoilThermalConductivities / SoilHeatCapacities, soil_thermal_properties.jl:13-45 ;
+       order: water, ice, air, mineral, organic */
+    double kappa[5];              /* 0.57 2.2 0.025 3.8 0.25 */
+    double heatcap[5];            /* 4.2e6 1.9e6 1.25e3 2.0e6 2.5e6 */
+    /* PhysicalConstants, src/processes/physical_constants.jl:9-51 */
+    double rho_w;                 /* 1000  */
+    double Lsl;                   /* 3.34e5 */
+    double Llg;                   /* 2.257e6 */
+    double rho_a;                 /* 1.293 */
+    double c_a;                   /* 1005.7 */
+    double Tref;                  /* 273.15 */
+    double sigma;                 /* 5.6704e-8 */
+    double eps_mw;                /* 0.622 (ratio of molecular weights) */
+    /* Soil hydraulics, soil_hydraulic_properties.jl:62-76 and FreezeCurves SWRC parameters */
+    double K_sat;                 /* 1e-5 */
+    double vg_alpha;              /* VanGenuchten alpha [1/m] (FreezeCurves default 1.0) */
+    double vg_n;                  /* VanGenuchten n (FreezeCurves default 2.0) */
+    double bc_psis;               /* BrooksCorey air entry head [m] (0.01) */
+    double bc_lambda;             /* BrooksCorey pore size index (0.2) */
+    double theta_res;             /* residual water content (0.0) */
+    double impedance;             /* UnsatKVanGenuchten ice impedance Omega (7) */
+    double vwc_forcing;           /* constant user VWC forcing [1/s] added in every cell
+                                     (soil_hydrology.jl:39, test/soil/soil_hydrology_tests.jl:191-233) */
+    /* Surface energy balance */
+    double albedo;                /* ConstantAlbedo 0.3, src/processes/surface_energy/albedo.jl:22 */
+    double emissivity;            /* 0.97 */
+    double kappa_skin;            /* ImplicitSkinTemperature kappa_s 2.0, skin_temperature.jl:54 */
+    double C_h;                   /* ConstantAerodynamics 1.2e-3, atmosphere/aerodynamics.jl:8 */
+    double min_windspeed;         /* 0.01, prescribed_atmosphere.jl:80 */
+    /* Surface hydrology */
+    double tau_r;                 /* DirectSurfaceRunoff 3600 s, runoff/direct_surface_runoff.jl:17 */
+    double evap_beta;             /* ConstantEvaporationResistanceFactor 1.0 */
+} trm_params;
+
+typedef struct trm_bc {
+    int32_t kind;       /* trm_bc_kind */
+    int32_t input;      /* trm_input_id that provides the value / gradient / flux per column */
+} trm_bc;
+
+typedef struct trm_config {
+    int32_t abi_version;      /* must be TRM_ABI_VERSION */
+    int32_t dtype;            /* trm_dtype */
+    int64_t ncol;             /* columns owned by this handle */
+    int64_t col0;             /* global index of the first owned column (informational) */
+    int32_t nz;               /* layers, 1..TRM_MAX_NZ */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t model;            /* trm_model */
+    int32_t timestepper;      /* trm_timestepper */
+    int32_t hydrology;        /* trm_hydrology */
+    int32_t swrc;             /* trm_swrc */
+    int32_t unsat_k;          /* trm_unsat_k */
+    int32_t sat_halo;         /* trm_halo (NoFlow only) */
+    int32_t skin;             /* trm_skin (LandModel only) */
+    int32_t math;             /* trm_math */
+    const double* z_faces;    /* nz+1 face elevations, bottom .. 0 (column_grid.jl:30-31); copied */
+    trm_params params;
+    trm_bc bc[TRM_BC_NSLOTS];
+} trm_config;
+
+/* Local (per handle) diagnostics; a multi-GPU caller reduces them with NCCL:
+ * sums with ncclSum, minima with ncclMin, maxima with ncclMax. */
+typedef struct trm_diag {
+    double energy;        /* sum_c sum_k U*dz                 [J/m^2 summed over columns]  */
+    double water;         /* sum_c (sum_k sat*por*dz + S_excess)  [m summed over columns]   */
+    double t_min, t_max;  /* extrema of temperature */
+    double sat_min, sat_max;
+    double nan_count;     /* non-finite values in U, T, sat */
+    double ncol;          /* columns contributing */
+} trm_diag;
+
+typedef struct trm_handle trm_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+void        trm_default_params(trm_params* p);
+void        trm_default_config(trm_config* c);   /* SoilModel, Euler, NoFlow, f64, defaults */
+int         trm_create(const trm_config* cfg, trm_handle** out);
+int         trm_destroy(trm_handle* h);
+const char* trm_last_error(void);
+int         trm_abi_version(void);
+int         trm_sync(trm_handle* h);
+
+/* ---- layout / zero-copy access ---------------------------------------------------------
+ * devptr: device pointer to element [0][0]; ld: leading dimension in elements;
+ * nrows: nz, nz+1 or 1. The Julia wrapper unsafe_wrap()s these as CuArrays (interior(field)). */
+int trm_field_ptr(trm_handle* h, int field_id, void** devptr, int64_t* ld, int32_t* nrows);
+/* Host <-> device copies of whole fields. Host layout is dense [nrows][ncol] in the handle's
+ * dtype (replaces set!(field, ...) / interior(field), src/initializers.jl:23-27). Writing
+ * TEMPERATURE / SATURATION before trm_initialize sets the initial condition. */
+int trm_set_field(trm_handle* h, int field_id, const void* host, int64_t count);
+int trm_get_field(trm_handle* h, int field_id, void* host, int64_t count);
+
+/* ---- inputs / forcing (device resident; replaces InputSource / FieldTimeSeriesInputSource,
+ *      src/input_output/input_sources.jl:81-171, and function valued BCs) ----------------- */
+int trm_set_input_const(trm_handle* h, int input_id, double value);
+int trm_set_input_field(trm_handle* h, int input_id, const void* host_values /* [ncol] NF */);
+int trm_set_input_sinusoid(trm_handle* h, int input_id, const void* mean, const void* amp,
+                           const void* phase /* each [ncol] NF */, double period,
+                           double lo, double hi /* clamp; use -INFINITY/INFINITY for none */);
+int trm_set_input_table(trm_handle* h, int input_id, int32_t nt, const double* times,
+                        const void* values /* [nt][ncol] NF */);
+/* Borrow the per-column device vector of a TRM_SRC_FIELD input so that a coupled model
+ * (e.g. SpeedyWeather, examples/simulations/speedy_dry_land.jl) can write forcing in place. */
+int trm_input_ptr(trm_handle* h, int input_id, void** devptr);
+
+/* ---- model ------------------------------------------------------------------------------ */
+/* initialize!(state, model) after the user initializers ran: hydrology closure + hydraulics,
+ * then the inverse energy closure T -> U (src/processes/soil/soil_coupled.jl:45-54). */
+int trm_initialize(trm_handle* h);
+/* nsteps x timestep!(integrator, dt; finalize = false) (forward_euler.jl:19-31, heun.jl:37-71):
+ * one fused kernel launch per time step. */
+int trm_step(trm_handle* h, double dt, int64_t nsteps);
+/* compute_auxiliary!(state, model) (soil_model.jl:39-42, land_model.jl:79-88): what
+ * timestep!(...; finalize = true) and run! do after stepping (model_integrator.jl:81-87,125-131). */
+int trm_compute_auxiliary(trm_handle* h);
+/* update_state!(...; compute_tendencies = true) with the tendencies (incl. flux BCs)
+ * materialised in TRM_F_TEND_* (tests / debugging only, not on the hot path). */
+int trm_compute_tendencies(trm_handle* h);
+
+int trm_get_clock(trm_handle* h, double* time, int64_t* iteration);
+int trm_set_clock(trm_handle* h, double time, int64_t iteration);
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+int trm_diagnostics(trm_handle* h, trm_diag* out);
+/* Same numbers left in device memory as 8 doubles in trm_diag order (for ncclAllReduce). */
+int trm_diagnostics_device(trm_handle* h, double** dev_out);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t trm_launch_count(trm_handle* h);
+/* Elapsed device time [ms] of the most recent trm_step call measured with CUDA events on the
+ * handle's stream (the events bracket exactly the fused stage kernels of that call). */
+int trm_last_step_ms(trm_handle* h, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TERRARIUM_B200_H */

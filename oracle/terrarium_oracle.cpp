@@ -1,0 +1,795 @@
+// terrarium_oracle.cpp -- CPU restatement of Terrarium.jl's per-column land time-step.
+//
+// *** TEST INFRASTRUCTURE ONLY. ***  Nothing under oracle/ is part of the product: only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, load or
+// call it, and only as the checker (or as the timed CPU baseline), never as a fallback.
+//
+// PARITY PINNING STATUS: "partially pinned".  The reference is pure Julia and neither `julia` nor
+// its un-vendored dependencies (Oceananigans 0.100-0.106, FreezeCurves 0.9; Project.toml:31-48,
+// there is no Manifest.toml) exist in this environment, so the reference cannot be executed.
+// This file restates the algorithm from the reference sources (file:line cited per function,
+// paths relative to /root/reference) and is pinned against every known-answer test the reference
+// holds for the path (tests/test_oracle_golden.py).  Semantics that live
+// in the absent dependencies are restated from their published behaviour and are marked [OCN]
+// (Oceananigans) or [FC] (FreezeCurves); each is listed in DESIGN.md as "unpinned at rounding
+// level".
+//
+// Structure: "reference-structured" -- one loop nest per reference kernel launch, in the reference
+// order, tendencies / face conductivities / halo planes materialised in memory exactly like the
+// Julia code does (~29 array passes per Euler step).  This is deliberate: the same code is timed as
+// the CPU baseline ("restated reference CPU path (C++/OpenMP, N cores)").
+//
+// Layout: [k][column] (column fastest, like Oceananigans' parent arrays), k = 0 and k = Nz+1 are
+// the z-halo planes of centre fields, faces are k = 1..Nz+1 with halo planes 0 and Nz+2.
+// k = 1 is the BOTTOM cell (docs/src/introduction/numerical_core.md:21-22).
+
+#include "../include/terrarium_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) { g_err = m; return code; }
+
+constexpr int64_t CHUNK = 2048;  // columns per OpenMP work item
+
+// Julia `min` / `max` for floats (NaN propagating).
+template <class T> inline T jmin(T a, T b) { return (a != a || b != b) ? std::numeric_limits<T>::quiet_NaN() : (b < a ? b : a); }
+template <class T> inline T jmax(T a, T b) { return (a != a || b != b) ? std::numeric_limits<T>::quiet_NaN() : (a < b ? b : a); }
+
+// Julia Base.Math.pow_body(x::Float64, n::Integer) for n = 4 (base/math.jl): compensated
+// power-by-squaring.  Float32 goes through Float64 power_by_squaring and rounds once.
+inline double two_mul_hi(double a, double b, double& lo) { double hi = a * b; lo = std::fma(a, b, -hi); return hi; }
+inline double jl_pow4(double x) {
+    double y = 1.0, xnlo = 0.0, ynlo = 0.0;
+    int n = 4;
+    while (n > 1) {
+        if (n & 1) { double err = std::fma(y, xnlo, x * ynlo); double lo; y = two_mul_hi(x, y, lo); ynlo = lo + err; }
+        double err = x * 2 * xnlo; double lo; x = two_mul_hi(x, x, lo); xnlo = lo + err;
+        n >>= 1;
+    }
+    double err = std::fma(y, xnlo, x * ynlo);
+    return (std::isfinite(x) && std::isfinite(err)) ? std::fma(x, y, err) : x * y;
+}
+inline float jl_pow4(float x) { double d = (double)x; double d2 = d * d; return (float)(d2 * d2); }
+
+struct InputSource {
+    int kind = TRM_SRC_CONST;
+    double cval = 0.0;
+    double period = 1.0, lo = -INFINITY, hi = INFINITY;
+    int nt = 0;
+    std::vector<double> times;
+};
+
+template <class NF>
+struct State {  // one StateVariables instance (src/state_variables.jl:16-54)
+    int nz = 0; int64_t nc = 0;
+    // centre fields with z-halos: (nz+2) x nc
+    std::vector<NF> U, T, liq, sat, psi, tendU, tendsat;
+    // z-face field with halos: (nz+3) x nc   (faces 1..nz+1)
+    std::vector<NF> Kf;
+    // 2-D
+    std::vector<NF> Sx, tendSx, wt, Ts, tendTs, G, SWup, LWup, Rnet, Hs, Hl, Egnd, infil, runoff;
+    std::vector<std::vector<NF>> in;  // materialised input fields [TRM_IN_COUNT][nc]
+    NF time = 0; int64_t iteration = 0;
+
+    void alloc(int nz_, int64_t nc_, bool land) {
+        nz = nz_; nc = nc_;
+        size_t c3 = (size_t)(nz + 2) * nc, f3 = (size_t)(nz + 3) * nc;
+        for (auto* v : {&U, &T, &liq, &sat, &psi, &tendU, &tendsat}) v->assign(c3, NF(0));
+        Kf.assign(f3, NF(0));
+        for (auto* v : {&Sx, &tendSx, &wt}) v->assign(nc, NF(0));
+        if (land) for (auto* v : {&Ts, &tendTs, &G, &SWup, &LWup, &Rnet, &Hs, &Hl, &Egnd, &infil, &runoff}) v->assign(nc, NF(0));
+        in.assign(TRM_IN_COUNT, std::vector<NF>());
+    }
+    inline size_t ix(int k, int64_t c) const { return (size_t)k * nc + c; }
+};
+
+template <class NF>
+struct Oracle {
+    trm_config cfg{};
+    int nz = 0; int64_t nc = 0;
+    bool land = false, richards = false, heun = false;
+    // grid metrics in NF  [OCN] generate_coordinate: halo faces extend with the edge spacing,
+    // centres are face midpoints, dzf are centre differences.
+    std::vector<NF> zF, zC, dzc, dzf, rdzc, rdzf;  // indices as in the reference (1-based + halos)
+    // parameters in NF
+    NF por, org, L, sqk[5], hc[5], Ksat, vg_alpha, vg_n, bc_psis, bc_lambda, theta_res, Omega, vwcf;
+    NF rho_a, c_a, Llg, Tref, sigma, eps_mw, albedo, emis, kappa_skin, C_h, Vmin, tau_r, beta;
+    State<NF> st, stage;
+    std::vector<InputSource> src;
+    std::vector<std::vector<NF>> src_field, src_mean, src_amp, src_phase, src_table;
+    bool initialized = false;
+    int64_t passes = 0;  // 3-D array passes executed (reported for the baseline description)
+
+    // ---------------------------------------------------------------- construction
+    int setup(const trm_config& c) {
+        cfg = c; nz = c.nz; nc = c.ncol;
+        land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
+        if (land && !richards) {
+            // reference: LandModel needs surface_excess_water/infiltration coupling which only the
+            // Richards variant defines (land_model.jl:56-62 injects a Flux BC on the *prognostic*
+            // saturation_water_ice, which is only prognostic under RichardsEq).
+            return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
+        }
+        const trm_params& p = c.params;
+        // ---- grid (column_grid.jl:30-31: z_coords converted to NF, then [OCN] metrics in NF)
+        zF.assign(nz + 3, NF(0)); zC.assign(nz + 2, NF(0)); dzc.assign(nz + 2, NF(0)); dzf.assign(nz + 3, NF(0));
+        rdzc.assign(nz + 2, NF(0)); rdzf.assign(nz + 3, NF(0));
+        for (int k = 1; k <= nz + 1; ++k) zF[k] = (NF)c.z_faces[k - 1];
+        zF[0] = zF[1] - (zF[2] - zF[1]);
+        zF[nz + 2] = zF[nz + 1] + (zF[nz + 1] - zF[nz]);
+        for (int k = 0; k <= nz + 1; ++k) { zC[k] = (zF[k + 1] + zF[k]) / 2; dzc[k] = zF[k + 1] - zF[k]; rdzc[k] = 1 / dzc[k]; }
+        for (int k = 1; k <= nz + 1; ++k) { dzf[k] = zC[k] - zC[k - 1]; rdzf[k] = 1 / dzf[k]; }
+        // ---- parameters
+        NF por_m = (NF)p.mineral_porosity, por_o = (NF)p.organic_porosity;
+        // homogeneous_strat.jl:34-45 : organic = rho_soc / ((1 - por_o) * rho_org)
+        org = (NF)p.rho_soc / ((1 - por_o) * (NF)p.rho_org);
+        // homogeneous_strat.jl:52-61 : (1 - organic) * por_m + organic * por_o
+        por = (1 - org) * por_m + org * por_o;
+        L = (NF)p.rho_w * (NF)p.Lsl;                       // soil_energy_closures.jl:76,113
+        for (int i = 0; i < 5; ++i) { sqk[i] = std::sqrt((NF)p.kappa[i]); hc[i] = (NF)p.heatcap[i]; }
+        Ksat = (NF)p.K_sat; vg_alpha = (NF)p.vg_alpha; vg_n = (NF)p.vg_n; bc_psis = (NF)p.bc_psis; bc_lambda = (NF)p.bc_lambda;
+        theta_res = (NF)p.theta_res; Omega = (NF)p.impedance; vwcf = (NF)p.vwc_forcing;
+        rho_a = (NF)p.rho_a; c_a = (NF)p.c_a; Llg = (NF)p.Llg; Tref = (NF)p.Tref; sigma = (NF)p.sigma; eps_mw = (NF)p.eps_mw;
+        albedo = (NF)p.albedo; emis = (NF)p.emissivity; kappa_skin = (NF)p.kappa_skin; C_h = (NF)p.C_h; Vmin = (NF)p.min_windspeed;
+        tau_r = (NF)p.tau_r; beta = (NF)p.evap_beta;
+        st.alloc(nz, nc, land);
+        src.assign(TRM_IN_COUNT, InputSource());
+        src_field.assign(TRM_IN_COUNT, {}); src_mean.assign(TRM_IN_COUNT, {}); src_amp.assign(TRM_IN_COUNT, {});
+        src_phase.assign(TRM_IN_COUNT, {}); src_table.assign(TRM_IN_COUNT, {});
+        // input defaults, prescribed_atmosphere.jl:89-99,147-149,192-195,220-224,10-14
+        src[TRM_IN_AIR_TEMPERATURE].cval = 10; src[TRM_IN_AIR_PRESSURE].cval = 101325; src[TRM_IN_WINDSPEED].cval = 0.1;
+        src[TRM_IN_SPECIFIC_HUMIDITY].cval = 1.0e-3; src[TRM_IN_SHORTWAVE_DOWN].cval = 300; src[TRM_IN_LONGWAVE_DOWN].cval = 50;
+        src[TRM_IN_DAYTIME_LENGTH].cval = 12; src[TRM_IN_CO2].cval = 380;
+        return TRM_OK;
+    }
+
+    // ---------------------------------------------------------------- inputs
+    // update_inputs! (state_variables.jl:154-162, input_sources.jl:165-171) + evaluation of
+    // function-valued boundary conditions at clock time t [OCN getbc(f, x, t)].
+    NF eval_input(int id, int64_t c, NF t) const {
+        const InputSource& s = src[id];
+        switch (s.kind) {
+            case TRM_SRC_CONST: return (NF)s.cval;
+            case TRM_SRC_FIELD: return src_field[id][c];
+            case TRM_SRC_SINUSOID: {
+                // examples/simulations/soil_heat_global.jl:79-88: `2pi * t / period - lon` promotes to
+                // Float64 in Julia whatever NF is; the result is rounded when stored in the NF field.
+                double ph = 6.283185307179586 * (double)t / s.period - (double)src_phase[id][c];
+                double v = (double)src_mean[id][c] + (double)src_amp[id][c] * std::sin(ph);
+                v = std::min(std::max(v, s.lo), s.hi);
+                return (NF)v;
+            }
+            case TRM_SRC_TABLE: {
+                // [OCN] FieldTimeSeries[Time(t)]: v2*n + v1*(1-n), n = (t-t1)/(t2-t1); flat outside
+                // the table (rule of ext/TerrariumRastersExt/TerrariumRastersExt.jl:104-120).
+                const std::vector<double>& tt = s.times; const std::vector<NF>& v = src_table[id];
+                double td = (double)t;
+                if (td <= tt.front()) return v[c];
+                if (td >= tt.back()) return v[(size_t)(s.nt - 1) * nc + c];
+                int n2 = (int)(std::upper_bound(tt.begin(), tt.end(), td) - tt.begin()); int n1 = n2 - 1;
+                NF frac = (NF)((td - tt[n1]) / (tt[n2] - tt[n1]));
+                return v[(size_t)n2 * nc + c] * frac + v[(size_t)n1 * nc + c] * (1 - frac);
+            }
+        }
+        return NF(0);
+    }
+    bool input_used(int id) const {
+        if (land && id >= TRM_IN_AIR_TEMPERATURE) return true;
+        for (int s = 0; s < TRM_BC_NSLOTS; ++s) if (cfg.bc[s].kind != TRM_BC_DEFAULT && cfg.bc[s].input == id) return true;
+        return false;
+    }
+    void update_inputs(State<NF>& s) {
+        for (int id = 0; id < TRM_IN_COUNT; ++id) {
+            if (!input_used(id)) continue;
+            auto& f = s.in[id]; if ((int64_t)f.size() != nc) f.assign(nc, NF(0));
+            NF t = s.time;
+#pragma omp parallel for schedule(static)
+            for (int64_t c = 0; c < nc; ++c) f[c] = eval_input(id, c, t);
+        }
+    }
+
+    // ---------------------------------------------------------------- soil constituents
+    struct Fr { NF water, ice, air, mineral, organic; };
+    // soil_volume.jl:52-67,103-107
+    inline Fr fractions(NF sat, NF liq) const {
+        NF wi = sat * por; Fr f;
+        f.water = wi * liq; f.ice = wi * (1 - liq); f.air = (1 - sat) * por;
+        NF solid = 1 - por; f.organic = solid * org; f.mineral = solid * (1 - org);
+        return f;
+    }
+    // soil_thermal_properties.jl:90-123 (InverseQuadratic; sum order water, ice, air, mineral, organic)
+    inline NF conductivity(NF sat, NF liq) const {
+        Fr f = fractions(sat, liq);
+        NF s = sqk[0] * f.water + sqk[1] * f.ice + sqk[2] * f.air + sqk[3] * f.mineral + sqk[4] * f.organic;
+        return s * s;
+    }
+    inline NF heat_capacity(NF sat, NF liq) const {
+        Fr f = fractions(sat, liq);
+        return hc[0] * f.water + hc[1] * f.ice + hc[2] * f.air + hc[3] * f.mineral + hc[4] * f.organic;
+    }
+    // soil_hydraulic_properties.jl:170-221 (real branch of the complex formula: theta_w/theta_sat in [0,1])
+    inline NF cell_K(NF sat, NF liq) const {
+        Fr f = fractions(sat, liq);
+        if (cfg.unsat_k == TRM_UNSATK_LINEAR) {
+            NF thsat = f.water + f.ice + f.air;
+            return Ksat * f.water / thsat;
+        }
+        NF n = vg_n;
+        NF I_ice = std::pow(NF(10), -Omega * (1 - liq));
+        NF x = f.water / por;
+        NF inner = 1 - std::pow(x, n / (n + 1));
+        NF a = 1 - std::pow(inner, (n - 1) / n);
+        return std::fabs(Ksat * I_ice * std::sqrt(x) * (a * a));
+    }
+    // [FC] inverse soil water retention curve psi_m(theta; theta_sat)
+    inline NF swrc_inv(NF theta, NF thsat) const {
+        if (cfg.swrc == TRM_SWRC_VANGENUCHTEN) {
+            NF n = vg_n, m = 1 - 1 / n;
+            if (!(theta < thsat)) return NF(0);
+            NF se = (theta - theta_res) / (thsat - theta_res);
+            return -1 / vg_alpha * std::pow(std::pow(se, -1 / m) - NF(1), 1 / n);
+        }
+        if (!(theta < thsat)) return -bc_psis;
+        NF se = (theta - theta_res) / (thsat - theta_res);
+        return -bc_psis * std::pow(se, -1 / bc_lambda);
+    }
+
+    // ---------------------------------------------------------------- halos [OCN] (Appendix B.4)
+    NF bc_value(const State<NF>& s, int slot, int64_t c) const { return s.in[cfg.bc[slot].input][c]; }
+    void fill_halo_field(State<NF>& s, std::vector<NF>& f, int slot_top, int slot_bottom) {
+        int kt = slot_top >= 0 ? cfg.bc[slot_top].kind : TRM_BC_DEFAULT;
+        int kb = slot_bottom >= 0 ? cfg.bc[slot_bottom].kind : TRM_BC_DEFAULT;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF ct = f[s.ix(nz, c)], cb = f[s.ix(1, c)];
+            // top: c[N+1] = c[N] + grad * dzf[N+1]; Value: grad = (v - c[N]) / (dzf/2)
+            if (kt == TRM_BC_VALUE) { NF D = dzf[nz + 1]; NF g = (bc_value(s, slot_top, c) - ct) / (D / 2); f[s.ix(nz + 1, c)] = ct + g * D; }
+            else if (kt == TRM_BC_GRADIENT) { NF D = dzf[nz + 1]; f[s.ix(nz + 1, c)] = ct + bc_value(s, slot_top, c) * D; }
+            else f[s.ix(nz + 1, c)] = ct;
+            // bottom: c[0] = c[1] - grad * dzf[1]; Value: grad = (c[1] - v) / (dzf/2)
+            if (kb == TRM_BC_VALUE) { NF D = dzf[1]; NF g = (cb - bc_value(s, slot_bottom, c)) / (D / 2); f[s.ix(0, c)] = cb + g * (-D); }
+            else if (kb == TRM_BC_GRADIENT) { NF D = dzf[1]; f[s.ix(0, c)] = cb + bc_value(s, slot_bottom, c) * (-D); }
+            else f[s.ix(0, c)] = cb;
+        }
+    }
+    // state_variables.jl:85-100: every prognostic field, then every closure field.
+    void fill_halo_regions(State<NF>& s) {
+        fill_halo_field(s, s.U, -1, -1);  // Flux / default BCs on internal_energy: no-gradient halo
+        if (richards) {
+            fill_halo_field(s, s.sat, -1, -1);
+            fill_halo_field(s, s.psi, TRM_BC_PRESSURE_TOP, TRM_BC_PRESSURE_BOTTOM);
+        } else if (cfg.sat_halo == TRM_HALO_COPY) {
+            fill_halo_field(s, s.sat, -1, -1);  // switch B.6: constant initializer filled the halos
+        }
+        fill_halo_field(s, s.T, TRM_BC_TEMPERATURE_TOP, TRM_BC_TEMPERATURE_BOTTOM);
+        fill_halo_field(s, s.liq, -1, -1);
+    }
+
+    // ---------------------------------------------------------------- kernels, reference order
+    void reset_tendencies(State<NF>& s) {  // state_variables.jl:127-136
+        std::fill(s.tendU.begin(), s.tendU.end(), NF(0)); passes++;
+        if (richards) { std::fill(s.tendsat.begin(), s.tendsat.end(), NF(0)); std::fill(s.tendSx.begin(), s.tendSx.end(), NF(0)); passes++; }
+        if (land) std::fill(s.tendTs.begin(), s.tendTs.end(), NF(0));
+    }
+    // compute_hydraulics! soil_hydrology.jl:145-163, kernel :249-276
+    void compute_hydraulics(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c) {
+                    if (k <= 1) s.Kf[s.ix(k, c)] = cell_K(s.sat[s.ix(1, c)], s.liq[s.ix(1, c)]);
+                    else if (k >= nz) { NF K = cell_K(s.sat[s.ix(nz, c)], s.liq[s.ix(nz, c)]); s.Kf[s.ix(k, c)] = K; s.Kf[s.ix(k + 1, c)] = K; }
+                    else s.Kf[s.ix(k, c)] = jmin(cell_K(s.sat[s.ix(k, c)], s.liq[s.ix(k, c)]), cell_K(s.sat[s.ix(k - 1, c)], s.liq[s.ix(k - 1, c)]));
+                }
+        }
+        passes += 3;
+    }
+    // darcy_flux soil_hydrology_rre.jl:119-131
+    inline NF darcy(const State<NF>& s, int k, int64_t c) const {
+        NF g = (s.psi[s.ix(k, c)] - s.psi[s.ix(k - 1, c)]) * rdzf[k];
+        NF Kk = (g < 0 ? jmin(s.Kf[s.ix(k - 1, c)], s.Kf[s.ix(k, c)]) : NF(0)) + (g >= 0 ? jmin(s.Kf[s.ix(k, c)], s.Kf[s.ix(k + 1, c)]) : NF(0));
+        return -Kk * g;
+    }
+    // compute_tendencies! (Richards) soil_hydrology_rre.jl:76-93,150-162; soil_hydrology.jl:222-237
+    void richards_tendency(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c) {
+                    NF div = (darcy(s, k + 1, c) - darcy(s, k, c)) * rdzc[k];
+                    NF dth = -div + NF(0) + vwcf;          // ET forcing is `nothing` -> zero (soil_coupled.jl:86)
+                    s.tendsat[s.ix(k, c)] += dth / por;
+                    if (k == 1) s.tendSx[c] += NF(0);       // runoff is `nothing` -> zero(S)
+                }
+        }
+        passes += 4;
+    }
+    // compute_tendencies! (energy) soil_energy.jl:83-149
+    inline NF heat_flux(const State<NF>& s, int k, int64_t c) const {
+        NF kap = (conductivity(s.sat[s.ix(k, c)], s.liq[s.ix(k, c)]) + conductivity(s.sat[s.ix(k - 1, c)], s.liq[s.ix(k - 1, c)])) / 2;
+        return -kap * ((s.T[s.ix(k, c)] - s.T[s.ix(k - 1, c)]) * rdzf[k]);
+    }
+    void energy_tendency(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c)
+                    s.tendU[s.ix(k, c)] += -((heat_flux(s, k + 1, c) - heat_flux(s, k, c)) * rdzc[k]);
+        }
+        passes += 5;
+    }
+
+    // ---- LandModel auxiliaries --------------------------------------------------------------
+    // aerodynamic_resistance prescribed_atmosphere.jl:110-116,137 ; the literal 1.0e-6 promotes the
+    // expression to Float64 for NF = Float32 -> computed in double here.
+    inline double r_a(const State<NF>& s, int64_t c) const {
+        NF V = jmax(s.in[TRM_IN_WINDSPEED][c], Vmin);
+        double Va = std::max((double)V, 1.0e-6);
+        return 1.0 / ((double)C_h * Va);
+    }
+    // physics_utils.jl:54-73
+    inline NF e_sat(NF T) const {
+        return T <= 0 ? NF(611.0) * std::exp(NF(22.46) * T / (T + NF(272.62))) : NF(611.0) * std::exp(NF(17.62) * T / (T + NF(243.12)));
+    }
+    // compute_humidity_vpd prescribed_atmosphere.jl:160-182 + physical_constants.jl:83-97 + physics_utils.jl:38
+    inline NF humidity_vpd(const State<NF>& s, int64_t c, NF Tsurf) const {
+        NF q = s.in[TRM_IN_SPECIFIC_HUMIDITY][c], p = s.in[TRM_IN_AIR_PRESSURE][c];
+        NF es = e_sat(Tsurf);
+        NF ea = q * p / (eps_mw + (1 - eps_mw) * q);
+        NF vpd = jmax(es - ea, NF(0.1));
+        return eps_mw * vpd / p;
+    }
+    // bare_ground_evaporation.jl:49-62
+    void compute_evaporation(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF Tsurf = cfg.skin == TRM_SKIN_PRESCRIBED ? s.in[TRM_IN_SKIN_TEMPERATURE][c] : s.Ts[c];
+            NF dq = humidity_vpd(s, c, Tsurf);
+            s.Egnd[c] = (NF)((double)(beta * dq) / r_a(s, c));
+        }
+    }
+    // direct_surface_runoff.jl:87-117
+    void compute_runoff(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF rain = s.in[TRM_IN_RAINFALL][c];  // rainfall_ground aliases rainfall (canopy_interception.jl:11-15)
+            NF S = s.Sx[c], Kt = s.Kf[s.ix(nz, c)], sat_top = s.sat[s.ix(nz, c)];
+            NF drain, inf;
+            if (S > 0) { drain = jmax(S, NF(0)) / tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
+            else { drain = 0; inf = (sat_top < 1) ? jmin(rain, Kt) : NF(0); }
+            s.infil[c] = inf;
+            s.runoff[c] = rain + drain - inf;
+        }
+    }
+    // compute_surface_energy_fluxes! surface_energy_balance.jl:119-144 (one evaluation)
+    inline void seb_fluxes(State<NF>& s, int64_t c) const {
+        NF SWd = s.in[TRM_IN_SHORTWAVE_DOWN][c], LWd = s.in[TRM_IN_LONGWAVE_DOWN][c];
+        NF Tsurf = cfg.skin == TRM_SKIN_PRESCRIBED ? s.in[TRM_IN_SKIN_TEMPERATURE][c] : s.Ts[c];
+        NF swu = albedo * SWd;                                   // radiative_fluxes.jl:85-88
+        NF TK = Tsurf + Tref;
+        NF lwu = emis * sigma * jl_pow4(TK) + (1 - emis) * LWd;  // radiative_fluxes.jl:95-100, physical_constants.jl:67
+        s.SWup[c] = swu; s.LWup[c] = lwu;
+        NF rnet = swu - SWd + lwu - LWd;                         // radiative_fluxes.jl:196-209
+        s.Rnet[c] = rnet;
+        double ra = r_a(s, c);
+        NF Ta = s.in[TRM_IN_AIR_TEMPERATURE][c];
+        NF hs = (NF)((double)(c_a * rho_a) * ((double)(Tsurf - Ta) / ra));  // turbulent_fluxes.jl:85-105
+        NF hl = Llg * rho_a * s.Egnd[c];                          // turbulent_fluxes.jl:137-150 (coupled to ET)
+        s.Hs[c] = hs; s.Hl[c] = hl;
+        s.G[c] = rnet - hs - hl;                                  // skin_temperature.jl:76-80
+    }
+    // compute_surface_energy_fluxes_kernel! surface_energy_balance.jl:82-110
+    void compute_seb(State<NF>& s) {
+        bool implicit = cfg.skin == TRM_SKIN_IMPLICIT;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            seb_fluxes(s, c);
+            if (implicit) {
+                NF Tg = s.T[s.ix(nz, c)];  // ground_temperature is a view of T[:, :, Nz] (soil_energy.jl:52-57)
+                s.Ts[c] = Tg - s.G[c] * dzc[nz] / (2 * kappa_skin);  // skin_temperature.jl:62-68,138-150
+                seb_fluxes(s, c);
+            }
+        }
+    }
+    // compute_auxiliary! soil_coupled.jl:62-72 / land_model.jl:79-88
+    void compute_auxiliary(State<NF>& s) {
+        compute_hydraulics(s);
+        if (land) { compute_evaporation(s); compute_runoff(s); compute_seb(s); compute_seb(s); }
+    }
+    // compute_tendencies! soil_coupled.jl:80-90 / land_model.jl:90-96
+    void compute_tendencies(State<NF>& s) {
+        if (richards) richards_tendency(s);
+        energy_tendency(s);
+    }
+    // update_state! state_variables.jl:72-80
+    void update_state(State<NF>& s) {
+        reset_tendencies(s);
+        update_inputs(s);
+        fill_halo_regions(s);
+        compute_auxiliary(s);
+        compute_tendencies(s);
+    }
+    // explicit_step! abstract_timestepper.jl:65-141 with [OCN] compute_z_bcs! (Flux BCs only; Appendix A.8)
+    void explicit_step(State<NF>& s, NF dt) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            if (land) {  // land_model.jl:56-62 : top Flux BCs G and -infiltration
+                s.tendU[s.ix(nz, c)] -= s.G[c] / dzc[nz];
+                s.tendsat[s.ix(nz, c)] -= (-s.infil[c]) / dzc[nz];
+            } else {
+                if (cfg.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) s.tendU[s.ix(nz, c)] -= bc_value(s, TRM_BC_ENERGY_TOP, c) / dzc[nz];
+                if (richards && cfg.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) s.tendsat[s.ix(nz, c)] -= bc_value(s, TRM_BC_SATURATION_TOP, c) / dzc[nz];
+            }
+            if (cfg.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) s.tendU[s.ix(1, c)] += bc_value(s, TRM_BC_ENERGY_BOTTOM, c) / dzc[1];
+            if (richards && cfg.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) s.tendsat[s.ix(1, c)] += bc_value(s, TRM_BC_SATURATION_BOTTOM, c) / dzc[1];
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c) {
+                    s.U[s.ix(k, c)] += s.tendU[s.ix(k, c)] * dt;
+                    if (richards) s.sat[s.ix(k, c)] += s.tendsat[s.ix(k, c)] * dt;
+                }
+            if (richards) for (int64_t c = c0; c < c1; ++c) s.Sx[c] += s.tendSx[c] * dt;
+            if (land && cfg.skin == TRM_SKIN_IMPLICIT) for (int64_t c = c0; c < c1; ++c) s.Ts[c] += s.tendTs[c] * dt;
+        }
+        passes += richards ? 6 : 3;
+    }
+    // adjust_saturation_profile! soil_hydrology.jl:185-219
+    void adjust_saturation(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            for (int k = 1; k <= nz - 1; ++k) {
+                NF e = jmax(s.sat[s.ix(k, c)] - 1, NF(0));
+                s.sat[s.ix(k, c)] -= e;
+                s.sat[s.ix(k + 1, c)] += e * dzc[k] / dzc[k + 1];
+            }
+            for (int k = nz; k >= 2; --k) {
+                NF d = jmax(-s.sat[s.ix(k, c)], NF(0));
+                s.sat[s.ix(k, c)] += d;
+                s.sat[s.ix(k - 1, c)] -= d * dzc[k] / dzc[k - 1];
+            }
+            NF e = jmax(s.sat[s.ix(nz, c)] - 1, NF(0));
+            s.sat[s.ix(nz, c)] -= e;
+            s.Sx[c] += e * dzc[nz];
+            s.sat[s.ix(1, c)] = jmax(s.sat[s.ix(1, c)], NF(0));
+        }
+        passes += 2;
+    }
+    // compute_water_table! soil_hydrology.jl:170-175 + findfirst_z kernel_utils.jl:7-16
+    // (scans k = 1..Nz+1 over the face nodes, i.e. reads the halo cell Nz+1)
+    void compute_water_table(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            int idx = -1;
+            for (int k = 1; k <= nz + 1; ++k) if (idx < 0 && s.sat[s.ix(k, c)] < 1) idx = k;
+            s.wt[c] = idx > 0 ? zF[idx] : zF[nz + 1];
+        }
+        passes += 1;
+    }
+    // saturation_to_pressure! soil_hydraulic_closures.jl:102-129
+    void saturation_to_pressure(State<NF>& s) {
+        NF zref = zF[nz + 1];
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c) {
+                    NF sat = s.sat[s.ix(k, c)], z = zC[k];
+                    NF psim = swrc_inv(sat * por, por);
+                    NF psiz = z - zref;
+                    NF psih = jmax(NF(0), s.wt[c] - z);
+                    s.psi[s.ix(k, c)] = psih + psim + psiz;
+                }
+        }
+        passes += 2;
+    }
+    // energy_to_temperature! soil_energy_closures.jl:99-159 ; safediv utils.jl:25
+    void energy_to_temperature(State<NF>& s) {
+        const NF epsNF = std::numeric_limits<NF>::epsilon();
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c) {
+                    NF U = s.U[s.ix(k, c)], sat = s.sat[s.ix(k, c)];
+                    NF Lt = L * sat * por;
+                    NF liq;
+                    if (U >= 0) liq = 1;
+                    else if (U >= -Lt) { NF y = -Lt; NF sd = (y == 0) ? std::numeric_limits<NF>::infinity() : U / (y + epsNF); liq = 1 - sd; }
+                    else liq = 0;  // Bool * x is a strong zero in Julia
+                    s.liq[s.ix(k, c)] = liq;
+                    NF C = heat_capacity(sat, liq);
+                    NF T;
+                    if (U < -Lt) T = (U + Lt) / C; else if (U >= 0) T = U / C; else T = 0;
+                    s.T[s.ix(k, c)] = T;
+                }
+        }
+        passes += 4;
+    }
+    // temperature_to_energy! soil_energy_closures.jl:64-97 (initialisation only)
+    void temperature_to_energy(State<NF>& s) {
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c) {
+                    NF T = s.T[s.ix(k, c)], sat = s.sat[s.ix(k, c)];
+                    NF liq = T >= 0 ? NF(1) : NF(0);
+                    s.liq[s.ix(k, c)] = liq;
+                    NF C = heat_capacity(sat, liq);
+                    s.U[s.ix(k, c)] = T * C - L * sat * por * (1 - liq);
+                }
+        }
+    }
+    // closure! soil_coupled.jl:99-107 (hydrology closure only exists for Richards)
+    void closure(State<NF>& s) {
+        if (richards) { adjust_saturation(s); compute_water_table(s); saturation_to_pressure(s); }
+        energy_to_temperature(s);
+    }
+    void tick(State<NF>& s, NF dt) { s.time = s.time + dt; s.iteration += 1; }
+
+    // ---------------------------------------------------------------- public operations
+    // initialize!(integrator) tail, model_integrator.jl:96-109 -> soil_model.jl:31-37 / land_model.jl:68-77
+    int initialize() {
+        // reset!(clock) and the reset of every non user-initialised field (model_integrator.jl:96-100)
+        st.time = 0; st.iteration = 0;
+        std::fill(st.liq.begin(), st.liq.end(), NF(0));
+        update_inputs(st);
+        // hydrology: Richards closure! then hydraulics (soil_hydrology_rre.jl:33-47);
+        // NoFlow hydraulics + water table (soil_hydrology.jl:113-117). liquid fraction is still the
+        // freshly reset field (zero) at this point in the reference; hydraulics are recomputed at the
+        // first update_state! so only the ordering of the writes matters.
+        if (richards) { adjust_saturation(st); compute_water_table(st); saturation_to_pressure(st); compute_hydraulics(st); }
+        else { compute_hydraulics(st); compute_water_table(st); }
+        temperature_to_energy(st);  // soil_energy.jl:64-77
+        initialized = true;
+        return TRM_OK;
+    }
+    void copy_state(State<NF>& dst, const State<NF>& src_) { dst = src_; }  // copyto! state_variables.jl:505-523
+    // forward_euler.jl:19-31
+    void step_euler(NF dt) {
+        update_state(st);
+        explicit_step(st, dt);
+        closure(st);
+        tick(st, dt);
+    }
+    // heun.jl:37-71
+    void step_heun(NF dt) {
+        update_state(st);
+        copy_state(stage, st);
+        explicit_step(stage, dt);
+        closure(stage);
+        tick(stage, dt);
+        update_state(stage);
+        // average_tendencies! heun.jl:27-35
+        size_t n3 = st.tendU.size();
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n3; ++i) {
+            st.tendU[i] = (st.tendU[i] + stage.tendU[i]) / 2;
+            if (richards) st.tendsat[i] = (st.tendsat[i] + stage.tendsat[i]) / 2;
+        }
+        if (richards) for (int64_t c = 0; c < nc; ++c) st.tendSx[c] = (st.tendSx[c] + stage.tendSx[c]) / 2;
+        if (land && cfg.skin == TRM_SKIN_IMPLICIT) for (int64_t c = 0; c < nc; ++c) st.tendTs[c] = (st.tendTs[c] + stage.tendTs[c]) / 2;
+        explicit_step(st, dt);
+        closure(st);
+        tick(st, dt);
+    }
+    int step(double dt, int64_t nsteps) {
+        if (!initialized) return fail(TRM_ERR_STATE, "orc_step before orc_initialize");
+        for (int64_t i = 0; i < nsteps; ++i) { if (heun) step_heun((NF)dt); else step_euler((NF)dt); }
+        return TRM_OK;
+    }
+    int aux() { compute_auxiliary(st); return TRM_OK; }
+    int tendencies() {
+        update_state(st);
+        // show what explicit_step! would integrate: add the flux BCs on a scratch copy
+        State<NF> tmp = st; NF zero = 0; explicit_step(tmp, zero);
+        st.tendU = tmp.tendU; st.tendsat = tmp.tendsat;
+        return TRM_OK;
+    }
+
+    // ---------------------------------------------------------------- field access
+    std::vector<NF>* field3(int id) {
+        switch (id) {
+            case TRM_F_INTERNAL_ENERGY: return &st.U; case TRM_F_TEMPERATURE: return &st.T;
+            case TRM_F_LIQUID_WATER_FRACTION: return &st.liq; case TRM_F_SATURATION_WATER_ICE: return &st.sat;
+            case TRM_F_PRESSURE_HEAD: return &st.psi; case TRM_F_TEND_INTERNAL_ENERGY: return &st.tendU;
+            case TRM_F_TEND_SATURATION: return &st.tendsat;
+        }
+        return nullptr;
+    }
+    std::vector<NF>* field2(int id) {
+        switch (id) {
+            case TRM_F_SURFACE_EXCESS_WATER: return &st.Sx; case TRM_F_WATER_TABLE: return &st.wt;
+            case TRM_F_SKIN_TEMPERATURE: return &st.Ts; case TRM_F_GROUND_HEAT_FLUX: return &st.G;
+            case TRM_F_SHORTWAVE_UP: return &st.SWup; case TRM_F_LONGWAVE_UP: return &st.LWup;
+            case TRM_F_NET_RADIATION: return &st.Rnet; case TRM_F_SENSIBLE_HEAT_FLUX: return &st.Hs;
+            case TRM_F_LATENT_HEAT_FLUX: return &st.Hl; case TRM_F_EVAPORATION_GROUND: return &st.Egnd;
+            case TRM_F_INFILTRATION: return &st.infil; case TRM_F_SURFACE_RUNOFF: return &st.runoff;
+        }
+        return nullptr;
+    }
+    int set_field(int id, const void* host, int64_t count) {
+        const NF* h = (const NF*)host;
+        if (auto* f = field3(id)) {
+            if (count != (int64_t)nz * nc) return fail(TRM_ERR_INVALID, "set_field: count != nz*ncol");
+            for (int k = 1; k <= nz; ++k) std::memcpy(&(*f)[st.ix(k, 0)], h + (size_t)(k - 1) * nc, sizeof(NF) * nc);  // set! writes the interior only
+            return TRM_OK;
+        }
+        if (auto* f = field2(id)) {
+            if (f->empty()) return fail(TRM_ERR_INVALID, "field not defined for this model");
+            if (count != nc) return fail(TRM_ERR_INVALID, "set_field: count != ncol");
+            std::memcpy(f->data(), h, sizeof(NF) * nc); return TRM_OK;
+        }
+        return fail(TRM_ERR_INVALID, "set_field: unknown or read-only field");
+    }
+    int get_field(int id, void* host, int64_t count) {
+        NF* h = (NF*)host;
+        if (auto* f = field3(id)) {
+            if (count != (int64_t)nz * nc) return fail(TRM_ERR_INVALID, "get_field: count != nz*ncol");
+            for (int k = 1; k <= nz; ++k) std::memcpy(h + (size_t)(k - 1) * nc, &(*f)[st.ix(k, 0)], sizeof(NF) * nc);
+            return TRM_OK;
+        }
+        if (id == TRM_F_HYDRAULIC_CONDUCTIVITY) {
+            if (count != (int64_t)(nz + 1) * nc) return fail(TRM_ERR_INVALID, "get_field: count != (nz+1)*ncol");
+            for (int k = 1; k <= nz + 1; ++k) std::memcpy(h + (size_t)(k - 1) * nc, &st.Kf[st.ix(k, 0)], sizeof(NF) * nc);
+            return TRM_OK;
+        }
+        if (id == TRM_F_GROUND_TEMPERATURE) {
+            if (count != nc) return fail(TRM_ERR_INVALID, "get_field: count != ncol");
+            std::memcpy(h, &st.T[st.ix(nz, 0)], sizeof(NF) * nc); return TRM_OK;
+        }
+        if (auto* f = field2(id)) {
+            if (f->empty()) return fail(TRM_ERR_INVALID, "field not defined for this model");
+            if (count != nc) return fail(TRM_ERR_INVALID, "get_field: count != ncol");
+            std::memcpy(h, f->data(), sizeof(NF) * nc); return TRM_OK;
+        }
+        return fail(TRM_ERR_INVALID, "get_field: unknown field");
+    }
+    int diagnostics(trm_diag* d) {
+        double e = 0, w = 0, tmin = INFINITY, tmax = -INFINITY, smin = INFINITY, smax = -INFINITY, nan = 0;
+        for (int64_t c = 0; c < nc; ++c) {
+            for (int k = 1; k <= nz; ++k) {
+                double U = st.U[st.ix(k, c)], T = st.T[st.ix(k, c)], s = st.sat[st.ix(k, c)];
+                e += U * (double)dzc[k]; w += s * (double)por * (double)dzc[k];
+                tmin = std::min(tmin, T); tmax = std::max(tmax, T); smin = std::min(smin, s); smax = std::max(smax, s);
+                nan += (!std::isfinite(U)) + (!std::isfinite(T)) + (!std::isfinite(s));
+            }
+            w += (double)st.Sx[c];
+        }
+        d->energy = e; d->water = w; d->t_min = tmin; d->t_max = tmax; d->sat_min = smin; d->sat_max = smax; d->nan_count = nan; d->ncol = (double)nc;
+        return TRM_OK;
+    }
+};
+
+struct Handle {
+    int dtype;
+    Oracle<float>* f32 = nullptr;
+    Oracle<double>* f64 = nullptr;
+    ~Handle() { delete f32; delete f64; }
+};
+
+#define DISPATCH(h, expr) ((h)->dtype == TRM_F32 ? (h)->f32->expr : (h)->f64->expr)
+
+template <class NF>
+int set_sinusoid(Oracle<NF>* o, int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) {
+    o->src[id].kind = TRM_SRC_SINUSOID; o->src[id].period = period; o->src[id].lo = lo; o->src[id].hi = hi;
+    o->src_mean[id].assign((const NF*)mean, (const NF*)mean + o->nc);
+    o->src_amp[id].assign((const NF*)amp, (const NF*)amp + o->nc);
+    o->src_phase[id].assign((const NF*)phase, (const NF*)phase + o->nc);
+    return TRM_OK;
+}
+template <class NF>
+int set_table(Oracle<NF>* o, int id, int nt, const double* times, const void* values) {
+    o->src[id].kind = TRM_SRC_TABLE; o->src[id].nt = nt; o->src[id].times.assign(times, times + nt);
+    o->src_table[id].assign((const NF*)values, (const NF*)values + (size_t)nt * o->nc);
+    return TRM_OK;
+}
+template <class NF>
+int set_infield(Oracle<NF>* o, int id, const void* v) {
+    o->src[id].kind = TRM_SRC_FIELD; o->src_field[id].assign((const NF*)v, (const NF*)v + o->nc);
+    return TRM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void orc_default_params(trm_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->mineral_porosity = 0.49; p->organic_porosity = 0.9; p->rho_soc = 0.0; p->rho_org = 1300.0;
+    const double k[5] = {0.57, 2.2, 0.025, 3.8, 0.25}; const double c[5] = {4.2e6, 1.9e6, 0.00125e6, 2.0e6, 2.5e6};
+    for (int i = 0; i < 5; ++i) { p->kappa[i] = k[i]; p->heatcap[i] = c[i]; }
+    p->rho_w = 1000.0; p->Lsl = 3.34e5; p->Llg = 2.257e6; p->rho_a = 1.293; p->c_a = 1005.7; p->Tref = 273.15;
+    p->sigma = 5.6704e-8; p->eps_mw = 0.622;
+    p->K_sat = 1.0e-5; p->vg_alpha = 1.0; p->vg_n = 2.0; p->bc_psis = 0.01; p->bc_lambda = 0.2; p->theta_res = 0.0;
+    p->impedance = 7.0; p->vwc_forcing = 0.0;
+    p->albedo = 0.3; p->emissivity = 0.97; p->kappa_skin = 2.0; p->C_h = 1.2e-3; p->min_windspeed = 0.01;
+    p->tau_r = 3600.0; p->evap_beta = 1.0;
+}
+void orc_default_config(trm_config* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->abi_version = TRM_ABI_VERSION; c->dtype = TRM_F64; c->model = TRM_MODEL_SOIL; c->timestepper = TRM_EULER;
+    c->hydrology = TRM_NOFLOW; c->swrc = TRM_SWRC_BROOKSCOREY; c->unsat_k = TRM_UNSATK_LINEAR; c->sat_halo = TRM_HALO_ZERO;
+    c->skin = TRM_SKIN_IMPLICIT; c->math = TRM_MATH_FAITHFUL;
+    orc_default_params(&c->params);
+}
+const char* orc_last_error(void) { return g_err.c_str(); }
+int orc_abi_version(void) { return TRM_ABI_VERSION; }
+
+int orc_create(const trm_config* cfg, trm_handle** out) {
+    if (!cfg || !out) return fail(TRM_ERR_INVALID, "null argument");
+    if (cfg->abi_version != TRM_ABI_VERSION) return fail(TRM_ERR_INVALID, "ABI version mismatch");
+    if (cfg->nz < 2 || cfg->nz > TRM_MAX_NZ || cfg->ncol < 1 || !cfg->z_faces) return fail(TRM_ERR_INVALID, "bad nz / ncol / z_faces");
+    for (int k = 0; k < cfg->nz; ++k) if (!(cfg->z_faces[k + 1] > cfg->z_faces[k])) return fail(TRM_ERR_INVALID, "z_faces must increase");
+    Handle* h = new Handle(); h->dtype = cfg->dtype; int rc;
+    if (cfg->dtype == TRM_F32) { h->f32 = new Oracle<float>(); rc = h->f32->setup(*cfg); }
+    else if (cfg->dtype == TRM_F64) { h->f64 = new Oracle<double>(); rc = h->f64->setup(*cfg); }
+    else { delete h; return fail(TRM_ERR_INVALID, "bad dtype"); }
+    if (rc != TRM_OK) { delete h; return rc; }
+    *out = (trm_handle*)h; return TRM_OK;
+}
+int orc_destroy(trm_handle* h) { delete (Handle*)h; return TRM_OK; }
+int orc_sync(trm_handle*) { return TRM_OK; }
+int orc_set_field(trm_handle* h, int id, const void* host, int64_t count) { return DISPATCH((Handle*)h, set_field(id, host, count)); }
+int orc_get_field(trm_handle* h, int id, void* host, int64_t count) { return DISPATCH((Handle*)h, get_field(id, host, count)); }
+int orc_set_input_const(trm_handle* h_, int id, double v) {
+    Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bad input id");
+    if (h->dtype == TRM_F32) { h->f32->src[id].kind = TRM_SRC_CONST; h->f32->src[id].cval = v; } else { h->f64->src[id].kind = TRM_SRC_CONST; h->f64->src[id].cval = v; }
+    return TRM_OK;
+}
+int orc_set_input_field(trm_handle* h_, int id, const void* v) {
+    Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bad input id");
+    return h->dtype == TRM_F32 ? set_infield(h->f32, id, v) : set_infield(h->f64, id, v);
+}
+int orc_set_input_sinusoid(trm_handle* h_, int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) {
+    Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bad input id");
+    return h->dtype == TRM_F32 ? set_sinusoid(h->f32, id, mean, amp, phase, period, lo, hi) : set_sinusoid(h->f64, id, mean, amp, phase, period, lo, hi);
+}
+int orc_set_input_table(trm_handle* h_, int id, int32_t nt, const double* times, const void* values) {
+    Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT || nt < 1) return fail(TRM_ERR_INVALID, "bad input id / nt");
+    return h->dtype == TRM_F32 ? set_table(h->f32, id, nt, times, values) : set_table(h->f64, id, nt, times, values);
+}
+int orc_initialize(trm_handle* h) { return DISPATCH((Handle*)h, initialize()); }
+int orc_step(trm_handle* h, double dt, int64_t n) { return DISPATCH((Handle*)h, step(dt, n)); }
+int orc_compute_auxiliary(trm_handle* h) { return DISPATCH((Handle*)h, aux()); }
+int orc_compute_tendencies(trm_handle* h) { return DISPATCH((Handle*)h, tendencies()); }
+int orc_get_clock(trm_handle* h_, double* t, int64_t* it) {
+    Handle* h = (Handle*)h_;
+    if (h->dtype == TRM_F32) { *t = h->f32->st.time; *it = h->f32->st.iteration; } else { *t = h->f64->st.time; *it = h->f64->st.iteration; }
+    return TRM_OK;
+}
+int orc_set_clock(trm_handle* h_, double t, int64_t it) {
+    Handle* h = (Handle*)h_;
+    if (h->dtype == TRM_F32) { h->f32->st.time = (float)t; h->f32->st.iteration = it; } else { h->f64->st.time = t; h->f64->st.iteration = it; }
+    return TRM_OK;
+}
+int orc_diagnostics(trm_handle* h, trm_diag* d) { return DISPATCH((Handle*)h, diagnostics(d)); }
+int64_t orc_array_passes(trm_handle* h_) { Handle* h = (Handle*)h_; return h->dtype == TRM_F32 ? h->f32->passes : h->f64->passes; }
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,478 @@
+"""Host-side mirror of the reference's model / process configuration types for the hot path.
+
+Same names, keyword arguments and defaults as the Julia constructors they mirror (file:line below,
+relative to the reference root), reduced to what the per-column time-step consumes.  These objects
+hold *configuration only*; all arithmetic runs in the CUDA library behind the C ABI.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _abi as abi
+from .grids import ColumnGrid
+
+
+# ---------------------------------------------------------------------------------------------
+# physical constants and soil parameterisations
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class PhysicalConstants:  # src/processes/physical_constants.jl:9-51
+    rho_w: float = 1000.0
+    rho_i: float = 916.2
+    rho_a: float = 1.293
+    c_a: float = 1005.7
+    Lsl: float = 3.34e5
+    Llg: float = 2.257e6
+    Lsg: float = 2.834e6
+    g: float = 9.80665
+    Tref: float = 273.15
+    sigma: float = 5.6704e-8
+    kappa: float = 0.4
+    eps: float = 0.622
+    R_a: float = 287.058
+    C_mass: float = 12.0
+
+
+@dataclass
+class SoilThermalConductivities:  # soil_thermal_properties.jl:13-24
+    water: float = 0.57
+    ice: float = 2.2
+    air: float = 0.025
+    mineral: float = 3.8
+    organic: float = 0.25
+
+
+@dataclass
+class SoilHeatCapacities:  # soil_thermal_properties.jl:34-45
+    water: float = 4.2e6
+    ice: float = 1.9e6
+    air: float = 0.00125e6
+    mineral: float = 2.0e6
+    organic: float = 2.5e6
+
+
+@dataclass
+class SoilThermalProperties:  # soil_thermal_properties.jl:56-76 (InverseQuadratic + FreeWater only)
+    conductivities: SoilThermalConductivities = field(default_factory=SoilThermalConductivities)
+    heat_capacities: SoilHeatCapacities = field(default_factory=SoilHeatCapacities)
+
+
+@dataclass
+class SoilEnergyBalance:  # soil_energy.jl:23-44 (ExplicitTwoPhaseHeatConduction + SoilEnergyTemperatureClosure)
+    thermal_properties: SoilThermalProperties = field(default_factory=SoilThermalProperties)
+
+
+@dataclass
+class VanGenuchten:  # FreezeCurves.jl SWRC (soil_hydraulic_closures.jl:95-97,115-118)
+    alpha: float = 1.0
+    n: float = 2.0
+    theta_res: float = 0.0
+
+
+@dataclass
+class BrooksCorey:  # FreezeCurves.jl SWRC
+    psi_s: float = 0.01
+    lam: float = 0.2
+    theta_res: float = 0.0
+
+
+@dataclass
+class UnsatKLinear:  # soil_hydraulic_properties.jl:163-182
+    pass
+
+
+@dataclass
+class UnsatKVanGenuchten:  # soil_hydraulic_properties.jl:196-221
+    impedance: float = 7.0
+
+
+@dataclass
+class ConstantSoilHydraulics:  # soil_hydraulic_properties.jl:62-91
+    swrc: Any = field(default_factory=BrooksCorey)
+    unsat_hydraulic_cond: Any = field(default_factory=UnsatKLinear)
+    sat_hydraulic_cond: float = 1.0e-5
+    field_capacity: float = 0.25
+    wilting_point: float = 0.05
+
+
+@dataclass
+class SoilHydraulicsSURFEX(ConstantSoilHydraulics):  # soil_hydraulic_properties.jl:112-140 (same K path)
+    pass
+
+
+class NoFlow:  # soil_hydrology.jl:13
+    pass
+
+
+class RichardsEq:  # soil_hydrology_rre.jl:18
+    pass
+
+
+@dataclass
+class SoilHydrology:  # soil_hydrology.jl:21-51
+    vertical_flow: Any = field(default_factory=NoFlow)
+    hydraulic_properties: Any = field(default_factory=SoilHydraulicsSURFEX)
+    vwc_forcing: Optional[float] = None  # constant source/sink [1/s] (test/soil/soil_hydrology_tests.jl:191-233)
+
+
+@dataclass
+class ConstantSoilPorosity:  # soil_porosity.jl:7-13
+    mineral_porosity: float = 0.49
+    organic_porosity: float = 0.9
+
+
+@dataclass
+class HomogeneousStratigraphy:  # homogeneous_strat.jl:8-23
+    porosity: ConstantSoilPorosity = field(default_factory=ConstantSoilPorosity)
+
+
+@dataclass
+class ConstantSoilCarbonDensity:  # constant_soil_carbon.jl:10-16
+    rho_soc: float = 0.0
+    rho_org: float = 1300.0
+
+
+@dataclass
+class SoilEnergyWaterCarbon:  # soil_coupled.jl:7-35
+    strat: HomogeneousStratigraphy = field(default_factory=HomogeneousStratigraphy)
+    energy: SoilEnergyBalance = field(default_factory=SoilEnergyBalance)
+    hydrology: SoilHydrology = field(default_factory=SoilHydrology)
+    biogeochem: ConstantSoilCarbonDensity = field(default_factory=ConstantSoilCarbonDensity)
+
+
+# ---------------------------------------------------------------------------------------------
+# surface processes (bare ground)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ConstantAlbedo:  # surface_energy/albedo.jl:20-27
+    albedo: float = 0.3
+    emissivity: float = 0.97
+
+
+@dataclass
+class ImplicitSkinTemperature:  # skin_temperature.jl:52-55
+    kappa_s: float = 2.0
+
+
+@dataclass
+class PrescribedSkinTemperature:  # skin_temperature.jl:12-15
+    kappa_s: float = 2.0
+
+
+@dataclass
+class SurfaceEnergyBalance:  # surface_energy_balance.jl:9-38 (diagnosed radiative + turbulent fluxes)
+    skin_temperature: Any = field(default_factory=ImplicitSkinTemperature)
+    albedo: ConstantAlbedo = field(default_factory=ConstantAlbedo)
+
+
+@dataclass
+class DirectSurfaceRunoff:  # runoff/direct_surface_runoff.jl:15-18
+    tau_r: float = 3600.0
+
+
+@dataclass
+class BareGroundEvaporation:  # evapotranspiration/bare_ground_evaporation.jl:12-20
+    ground_resistance_factor: float = 1.0  # ConstantEvaporationResistanceFactor
+
+
+class NoCanopyInterception:  # canopy_interception.jl:7
+    pass
+
+
+@dataclass
+class SurfaceHydrology:  # surface_hydrology.jl:11-34 with the vegetation = nothing defaults (land_model.jl:119-125)
+    canopy_interception: Any = field(default_factory=NoCanopyInterception)
+    evapotranspiration: BareGroundEvaporation = field(default_factory=BareGroundEvaporation)
+    surface_runoff: DirectSurfaceRunoff = field(default_factory=DirectSurfaceRunoff)
+
+
+@dataclass
+class PrescribedAtmosphere:  # prescribed_atmosphere.jl:44-87 (ConstantAerodynamics, aerodynamics.jl:6-9)
+    altitude: float = 10.0
+    min_windspeed: float = 0.01
+    C_h: float = 1.2e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# initializers (src/models/soil/soil_model_init.jl, src/initializers.jl)
+# ---------------------------------------------------------------------------------------------
+class DefaultInitializer:
+    def fields(self, grid) -> Dict[str, Any]:
+        return {}
+
+
+@dataclass
+class ConstantSoilTemperature:
+    T0: float = 0.0
+
+    def fields(self, grid):
+        return {"temperature": self.T0}
+
+
+@dataclass
+class QuasiThermalSteadyState:
+    T0: float = 0.0
+    Qgeo: float = 0.02
+    k_eff: float = 1.0
+
+    def fields(self, grid):
+        return {"temperature": lambda x, z: self.T0 - self.Qgeo / self.k_eff * z}
+
+
+@dataclass
+class ConstantSaturation:
+    sat: float = 1.0
+
+    def fields(self, grid):
+        return {"saturation_water_ice": self.sat}
+
+
+@dataclass
+class SaturationWaterTable:
+    vadose_zone_saturation: float = 0.5
+    water_table_depth: float = 5.0
+
+    def fields(self, grid):
+        # as coded (soil_model_init.jl:150): z <= +depth is always true for z <= 0 -> fully saturated
+        return {"saturation_water_ice": lambda x, z: np.where(z <= self.water_table_depth, 1.0, self.vadose_zone_saturation)}
+
+
+@dataclass
+class SoilInitializer:  # soil_model_init.jl:6-36 ; order hydrology, biogeochem, energy
+    energy: Any = field(default_factory=QuasiThermalSteadyState)
+    hydrology: Any = field(default_factory=SaturationWaterTable)
+
+    def fields(self, grid):
+        out = {}
+        out.update(self.hydrology.fields(grid))
+        out.update(self.energy.fields(grid))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# time-dependent per-column values: what a boundary condition or an input may be made of
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Sinusoid:
+    """``clamp(mean + amp*sin(2*pi*t/period - phase), lo, hi)`` per column, evaluated on the device.
+
+    The device-resident form of the function valued boundary condition of
+    ``examples/simulations/soil_heat_global.jl:72-93``."""
+    mean: Union[float, np.ndarray]
+    amp: Union[float, np.ndarray]
+    phase: Union[float, np.ndarray] = 0.0
+    period: float = 86400.0
+    lo: float = -np.inf
+    hi: float = np.inf
+
+
+@dataclass
+class TimeSeries:
+    """Snapshots ``values[nt, ncol]`` at ``times[nt]`` (FieldTimeSeriesInputSource, input_sources.jl:142-171)."""
+    times: Sequence[float]
+    values: np.ndarray
+
+
+@dataclass
+class BoundaryCondition:
+    kind: int           # abi.TRM_BC_*
+    slot: int           # abi.TRM_BC_<field>_<side>
+    value: Any          # number | per-column array | Sinusoid | TimeSeries | callable (x, t)
+    name: Optional[str] = None
+
+
+def ValueBoundaryCondition(value):
+    return ("value", value)
+
+
+def FluxBoundaryCondition(value):
+    return ("flux", value)
+
+
+def GradientBoundaryCondition(value):
+    return ("gradient", value)
+
+
+# aliases of src/models/soil/soil_model_bcs.jl:6-40 -------------------------------------------
+def PrescribedSurfaceTemperature(name: str, value) -> Dict[str, Dict[str, BoundaryCondition]]:
+    return {"temperature": {"top": BoundaryCondition(abi.TRM_BC_VALUE, abi.TRM_BC_TEMPERATURE_TOP, value, name)}}
+
+
+def PrescribedBottomTemperature(name: str, value):
+    return {"temperature": {"bottom": BoundaryCondition(abi.TRM_BC_VALUE, abi.TRM_BC_TEMPERATURE_BOTTOM, value, name)}}
+
+
+def GroundHeatFlux(value):
+    return {"internal_energy": {"top": BoundaryCondition(abi.TRM_BC_FLUX, abi.TRM_BC_ENERGY_TOP, value, "ground_heat_flux")}}
+
+
+def GeothermalHeatFlux(value):
+    return {"internal_energy": {"bottom": BoundaryCondition(abi.TRM_BC_FLUX, abi.TRM_BC_ENERGY_BOTTOM, value, "geothermal_heat_flux")}}
+
+
+def InfiltrationFlux(value):
+    return {"saturation_water_ice": {"top": BoundaryCondition(abi.TRM_BC_FLUX, abi.TRM_BC_SATURATION_TOP, value, "infiltration")}}
+
+
+def ImpermeableBoundary():
+    return {"saturation_water_ice": {"bottom": BoundaryCondition(abi.TRM_BC_DEFAULT, abi.TRM_BC_SATURATION_BOTTOM, 0.0)}}
+
+
+def FreeDrainage():
+    return {"pressure_head": {"bottom": BoundaryCondition(abi.TRM_BC_GRADIENT, abi.TRM_BC_PRESSURE_BOTTOM, 0.0)}}
+
+
+_SLOTS = {
+    ("temperature", "top"): abi.TRM_BC_TEMPERATURE_TOP, ("temperature", "bottom"): abi.TRM_BC_TEMPERATURE_BOTTOM,
+    ("internal_energy", "top"): abi.TRM_BC_ENERGY_TOP, ("internal_energy", "bottom"): abi.TRM_BC_ENERGY_BOTTOM,
+    ("saturation_water_ice", "top"): abi.TRM_BC_SATURATION_TOP, ("saturation_water_ice", "bottom"): abi.TRM_BC_SATURATION_BOTTOM,
+    ("pressure_head", "top"): abi.TRM_BC_PRESSURE_TOP, ("pressure_head", "bottom"): abi.TRM_BC_PRESSURE_BOTTOM,
+}
+_KINDS = {"value": abi.TRM_BC_VALUE, "flux": abi.TRM_BC_FLUX, "gradient": abi.TRM_BC_GRADIENT}
+
+
+def merge_boundary_conditions(*bcs) -> Dict[str, Dict[str, BoundaryCondition]]:
+    """Recursive merge, later arguments win (boundary_conditions.jl:18)."""
+    out: Dict[str, Dict[str, BoundaryCondition]] = {}
+    for b in bcs:
+        for var, sides in (b or {}).items():
+            for side, bc in sides.items():
+                if isinstance(bc, tuple):  # (kind, value) from Value/Flux/GradientBoundaryCondition
+                    bc = BoundaryCondition(_KINDS[bc[0]], _SLOTS[(var, side)], bc[1])
+                out.setdefault(var, {})[side] = bc
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# models
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class SoilModel:  # src/models/soil/soil_model.jl:9-27
+    grid: ColumnGrid
+    soil: SoilEnergyWaterCarbon = field(default_factory=SoilEnergyWaterCarbon)
+    constants: PhysicalConstants = field(default_factory=PhysicalConstants)
+    initializer: Any = field(default_factory=DefaultInitializer)
+    # unpinned Oceananigans semantics: what the never filled z-halo of the
+    # auxiliary saturation field holds under NoFlow hydrology. "zero" | "copy"
+    sat_halo: str = "zero"
+
+
+@dataclass
+class LandModel:  # src/models/coupled/land_model.jl:10-44 with vegetation = nothing
+    grid: ColumnGrid
+    vegetation: None = None
+    soil: SoilEnergyWaterCarbon = field(default_factory=lambda: SoilEnergyWaterCarbon(hydrology=SoilHydrology(RichardsEq())))
+    surface_energy_balance: SurfaceEnergyBalance = field(default_factory=SurfaceEnergyBalance)
+    surface_hydrology: SurfaceHydrology = field(default_factory=SurfaceHydrology)
+    atmosphere: PrescribedAtmosphere = field(default_factory=PrescribedAtmosphere)
+    constants: PhysicalConstants = field(default_factory=PhysicalConstants)
+    initializer: Any = field(default_factory=DefaultInitializer)
+    sat_halo: str = "zero"
+
+    def __post_init__(self):
+        if self.vegetation is not None:
+            raise NotImplementedError(
+                "LandModel with PALADYN vegetation is outside the built hot path (SURVEY.md 8f row f1); "
+                "use vegetation=None (bare ground)")
+
+
+# ---------------------------------------------------------------------------------------------
+# time steppers (src/timesteppers/forward_euler.jl:6-17, heun.jl:6-20)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ForwardEuler:
+    dt: float = 300.0
+
+
+@dataclass
+class Heun:
+    dt: float = 300.0
+
+
+def default_dt(ts) -> float:
+    return ts.dt
+
+
+def is_adaptive(ts) -> bool:
+    return False
+
+
+# ---------------------------------------------------------------------------------------------
+# model -> trm_config
+# ---------------------------------------------------------------------------------------------
+def build_params(model) -> abi.trm_params:
+    p = abi.trm_params()
+    soil, c = model.soil, model.constants
+    p.mineral_porosity = soil.strat.porosity.mineral_porosity
+    p.organic_porosity = soil.strat.porosity.organic_porosity
+    p.rho_soc, p.rho_org = soil.biogeochem.rho_soc, soil.biogeochem.rho_org
+    k, h = soil.energy.thermal_properties.conductivities, soil.energy.thermal_properties.heat_capacities
+    for i, n in enumerate(("water", "ice", "air", "mineral", "organic")):
+        p.kappa[i] = getattr(k, n)
+        p.heatcap[i] = getattr(h, n)
+    p.rho_w, p.Lsl, p.Llg, p.rho_a, p.c_a = c.rho_w, c.Lsl, c.Llg, c.rho_a, c.c_a
+    p.Tref, p.sigma, p.eps_mw = c.Tref, c.sigma, c.eps
+    hp = soil.hydrology.hydraulic_properties
+    p.K_sat = hp.sat_hydraulic_cond
+    vg, bc = VanGenuchten(), BrooksCorey()
+    if isinstance(hp.swrc, VanGenuchten):
+        vg = hp.swrc
+    elif isinstance(hp.swrc, BrooksCorey):
+        bc = hp.swrc
+    else:
+        raise TypeError(f"unsupported SWRC {type(hp.swrc).__name__}")
+    p.vg_alpha, p.vg_n, p.bc_psis, p.bc_lambda = vg.alpha, vg.n, bc.psi_s, bc.lam
+    p.theta_res = hp.swrc.theta_res
+    p.impedance = getattr(hp.unsat_hydraulic_cond, "impedance", 7.0)
+    p.vwc_forcing = soil.hydrology.vwc_forcing or 0.0
+    # surface defaults; overwritten for LandModel
+    p.albedo, p.emissivity, p.kappa_skin, p.C_h, p.min_windspeed, p.tau_r, p.evap_beta = 0.3, 0.97, 2.0, 1.2e-3, 0.01, 3600.0, 1.0
+    if isinstance(model, LandModel):
+        seb, sh, atm = model.surface_energy_balance, model.surface_hydrology, model.atmosphere
+        p.albedo, p.emissivity = seb.albedo.albedo, seb.albedo.emissivity
+        p.kappa_skin = seb.skin_temperature.kappa_s
+        p.C_h, p.min_windspeed = atm.C_h, atm.min_windspeed
+        p.tau_r = sh.surface_runoff.tau_r
+        p.evap_beta = sh.evapotranspiration.ground_resistance_factor
+    return p
+
+
+def build_config(model, timestepper, ncol: int, col0: int = 0, device: int = 0, math: str = "faithful"):
+    """Translate a model + timestepper into the POD ``trm_config`` (BC slots are filled by the caller).
+
+    Returns ``(config, z_faces_buffer)``; the buffer must stay alive until ``trm_create`` returned."""
+    grid = model.grid
+    cfg = abi.trm_config()
+    cfg.abi_version = abi.TRM_ABI_VERSION
+    cfg.dtype = abi.dtype_code(grid.nf)
+    cfg.ncol, cfg.col0, cfg.nz, cfg.device = int(ncol), int(col0), int(grid.Nz), int(device)
+    cfg.model = abi.TRM_MODEL_LAND if isinstance(model, LandModel) else abi.TRM_MODEL_SOIL
+    if isinstance(timestepper, Heun):
+        cfg.timestepper = abi.TRM_HEUN
+    elif isinstance(timestepper, ForwardEuler):
+        cfg.timestepper = abi.TRM_EULER
+    else:
+        raise TypeError(f"unsupported timestepper {type(timestepper).__name__}")
+    hyd = model.soil.hydrology
+    cfg.hydrology = abi.TRM_RICHARDS if isinstance(hyd.vertical_flow, RichardsEq) else abi.TRM_NOFLOW
+    hp = hyd.hydraulic_properties
+    cfg.swrc = abi.TRM_SWRC_VANGENUCHTEN if isinstance(hp.swrc, VanGenuchten) else abi.TRM_SWRC_BROOKSCOREY
+    if isinstance(hp.unsat_hydraulic_cond, UnsatKVanGenuchten):
+        if not isinstance(hp.swrc, VanGenuchten):
+            raise TypeError("UnsatKVanGenuchten requires a VanGenuchten SWRC (soil_hydraulic_properties.jl:203-206)")
+        cfg.unsat_k = abi.TRM_UNSATK_VANGENUCHTEN
+    else:
+        cfg.unsat_k = abi.TRM_UNSATK_LINEAR
+    cfg.sat_halo = abi.TRM_HALO_COPY if model.sat_halo == "copy" else abi.TRM_HALO_ZERO
+    cfg.skin = abi.TRM_SKIN_IMPLICIT
+    if isinstance(model, LandModel) and isinstance(model.surface_energy_balance.skin_temperature, PrescribedSkinTemperature):
+        cfg.skin = abi.TRM_SKIN_PRESCRIBED
+    cfg.math = abi.TRM_MATH_FAST if math == "fast" else abi.TRM_MATH_FAITHFUL
+    zbuf = np.ascontiguousarray(grid.z_faces, dtype=np.float64)
+    import ctypes as C
+    cfg.z_faces = zbuf.ctypes.data_as(C.POINTER(C.c_double))
+    cfg.params = build_params(model)
+    return cfg, zbuf
