@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the fused per-column land time-step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # restated reference CPU path on the host cores
+
+Workload (BASELINE.json configs[4]): synthetic 10 M-column x 30-layer domain, coupled soil
+energy + Richards hydrology, ForwardEuler, dt = 60 s, Float64, sinusoidal surface temperature forcing
+evaluated on the device.  A "step" is ONE fused stage-kernel launch over every column of the rank's column
+range.  For N > 1 the 10 M columns are split by contiguous column range (strong scaling, no halo, no
+data-path collective); NCCL only reduces the timing and the global budgets.
+
+Prints ONE JSON line (rank 0).  `value` = column-layer-steps/s with the state resident in HBM, timed with
+CUDA events on the library's stream; `e2e` = the same metric when every step also uploads that step's
+surface forcing from pinned host memory and downloads the ground temperature (coupled-model usage, cf.
+examples/simulations/speedy_dry_land.jl) through the public C ABI.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "column-layer-steps/sec"
+UNIT = "column-layer-steps/s"
+NZ = 30
+DT = 60.0
+SEED = 20260101
+
+
+def algorithmic_bytes_per_cell(itemsize: int, nz: int) -> float:
+    """read U, sat; write U, sat, T, liq, psi (7 values per cell) + per column: surface_excess_water
+    R/W, water_table R/W, sinusoid forcing parameters (mean, amp, phase) R = 7 values per column."""
+    return 7.0 * itemsize + 7.0 * itemsize / nz
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(nf_name: str):
+    """dram bytes per launch of the stage kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(nf_name)
+
+
+def synthetic(ncol_global: int, c0: int, c1: int):
+    rng = np.random.default_rng(SEED)
+    lat = rng.uniform(-np.pi / 2, np.pi / 2, ncol_global)[c0:c1]
+    lon = rng.uniform(0.0, 2 * np.pi, ncol_global)[c0:c1]
+    T0 = 20.0 - np.abs(40.0 * np.sin(lat))
+    return lon, T0
+
+
+def build_case(trm, make_integrator, ncol_global, rank, world, device, nf, math, forcing="sinusoid"):
+    from common import richards_soil
+    grid = trm.ColumnGrid(trm.B200(device), nf, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=NZ), ncol_global)
+    c0, c1 = grid.partition(rank, world)
+    lon, T0 = synthetic(ncol_global, c0, c1)
+    model = trm.SoilModel(grid, soil=richards_soil())
+    if forcing == "sinusoid":
+        value = trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0)
+    else:
+        value = T0 + 10.0 * np.sin(-lon)
+    bcs = trm.PrescribedSurfaceTemperature("T_ub", value)
+    zc = grid.znodes_center().astype(np.float64)
+    temp = (T0[None, :] - 0.05 * zc[:, None]).astype(nf)
+    sat = np.ascontiguousarray(np.broadcast_to(np.minimum(1.0, 0.5 - 0.1 * zc)[:, None], temp.shape), dtype=nf)
+    # temp / sat already hold only this rank's columns
+    integ = make_integrator(model, trm.ForwardEuler(dt=DT), None, boundary_conditions=bcs,
+                            initializers={"temperature": temp, "saturation_water_ice": sat},
+                            partition=(rank, world), math=math)
+    return integ, lon, T0
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        power = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_reference(ncol_sample, steps, warmup, nf):
+    """Restated reference CPU path (C++/OpenMP oracle in reference-structured mode) on the host cores."""
+    import oracle_integrator as oi
+    import terrarium_jl_b200 as trm
+    integ, _, _ = build_case(trm, oi.oracle_initialize, ncol_sample, 0, 1, 0, nf, "faithful")
+    cores = int(oi.oracle_library().cdll.orc_num_threads())
+    integ.step(DT, warmup)
+    t0 = time.perf_counter()
+    integ.step(DT, steps)
+    el = time.perf_counter() - t0
+    return ncol_sample * NZ * steps / el, el, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--columns", type=int, default=10_000_000, help="total columns of the synthetic domain")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--math", default="fast", choices=["fast", "faithful"])
+    ap.add_argument("--block", type=int, default=0, help="threads per block of the stage kernel (0 = library default)")
+    ap.add_argument("--cpu-columns", type=int, default=262144, help="columns of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    nf = np.float64 if args.dtype == "f64" else np.float32
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        ncs = args.cpu_columns
+        v, el, cores = cpu_reference(ncs, args.steps, args.warmup, nf)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "soil energy + Richards hydrology, ForwardEuler, dt=60 s, Nz=30 exponential grid, sinusoidal surface "
+                                   "temperature; restated reference CPU path (C++/OpenMP oracle, one loop nest per reference kernel); the "
+                                   "Julia reference cannot run here (no julia in the image)",
+                       "columns_per_step": ncs, "nz": NZ},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{ncs} columns x {NZ} layers x {args.steps} steps of the same workload"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import terrarium_jl_b200 as trm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    integ, lon, T0 = build_case(trm, trm.initialize, args.columns, rank, world, local_rank, nf, args.math)
+    lib, h = integ._lib, integ._h
+    if args.block:
+        lib.check(lib.set_block_size(h, args.block), "set_block_size")
+    ncol_local = integ.ncol
+    itemsize = np.dtype(nf).itemsize
+
+    d0 = integ.diagnostics()
+    integ.step(DT, args.warmup)
+    ms = C.c_float()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = lib.launch_count(h)
+    w0 = time.perf_counter()
+    integ.step(DT, args.steps)   # K fused stage-kernel launches; device time bracketed by CUDA events on the library's stream
+    barrier()
+    wall = time.perf_counter() - w0
+    launches = lib.launch_count(h) - l0
+    lib.check(lib.last_step_ms(h, C.byref(ms)), "last_step_ms")
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(t_ms.item())
+    total_cells = args.columns * NZ
+    value = total_cells * args.steps / (dev_ms * 1e-3)
+
+    # global budgets (NCCL all-reduce of the per-rank diagnostics): the run must conserve water
+    d1 = integ.diagnostics()
+    bud = torch.tensor([d0["water"], d1["water"], d1["nan_count"], d1["energy"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(bud, op=dist.ReduceOp.SUM)
+    bud = bud.tolist()
+
+    # ---- end-to-end: per step upload the surface forcing (pinned host -> device), step, download the ground temperature
+    e2e = None
+    if not args.no_e2e:
+        integ2 = integ
+        tdtype = torch.float64 if nf == np.float64 else torch.float32
+        forc = torch.empty(ncol_local, dtype=tdtype).pin_memory()
+        out = torch.empty(ncol_local, dtype=tdtype).pin_memory()
+        fnp, onp = forc.numpy(), out.numpy()
+        in_id = integ2._bc_inputs["T_ub"]
+        gt_id = trm.abi.FIELD_IDS["ground_temperature"]
+
+        def e2e_step(t):
+            np.sin(2 * np.pi * t / 86400.0 - lon, out=fnp)   # the host-side "atmosphere" produces this step's forcing
+            fnp *= 10.0
+            fnp += T0
+            lib.check(lib.set_input_field(h, in_id, C.c_void_p(forc.data_ptr())), "set_input_field")
+            lib.check(lib.step(h, DT, 1), "step")
+            lib.check(lib.get_field(h, gt_id, C.c_void_p(out.data_ptr()), ncol_local), "get_field")
+
+        t = integ2.clock.time
+        for _ in range(3):
+            e2e_step(t); t += DT
+        k2 = max(3, min(args.steps, 20))
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(k2):
+            e2e_step(t); t += DT
+        barrier()
+        el = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_cells * k2 / float(el.item()), "unit": UNIT, "h2d_bytes_per_step": args.columns * itemsize,
+               "d2h_bytes_per_step": args.columns * itemsize, "steps": k2,
+               "what": "per step: host computes the surface temperature forcing into pinned memory, trm_set_input_field (H2D), "
+                       "trm_step, trm_get_field(ground_temperature) (D2H); wall clock, max over ranks"}
+        assert np.all(np.isfinite(onp))
+
+    peak, peak_src = peaks()
+    bpc = algorithmic_bytes_per_cell(itemsize, NZ)
+    per_launch_ms = dev_ms / args.steps
+    achieved = bpc * (ncol_local * NZ) / (per_launch_ms * 1e-3) / 1e9   # this rank's kernel (ranks are symmetric)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(args.dtype), "peak_source": peak_src,
+                "algorithmic_bytes_per_column_layer_step": bpc, "kernel": "trm::stage_kernel<NF, RICHARDS, EULER, recompute, fast>",
+                "launch_ms": per_launch_ms}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        try:
+            v, el, cores = cpu_reference(args.cpu_columns, 10, 1, nf)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{args.cpu_columns} columns x {NZ} layers x 10 steps of the same workload ({el:.1f} s)"}
+        except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU number
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "configs[4]: synthetic 10M-column soil energy + Richards hydrology (VanGenuchten alpha=2 n=2, "
+                                   "UnsatKVanGenuchten, K_sat=1e-5), ForwardEuler dt=60 s, Nz=30 exponential grid, sinusoidal surface "
+                                   "temperature evaluated on the device",
+                       "columns": args.columns, "nz": NZ, "columns_per_gpu": ncol_local, "math": args.math,
+                       "partition": "contiguous column ranges, no halo, no data-path collective",
+                       "cache": "inputs larger than L2 (state read per step = %.1f GB per GPU)" % (2 * ncol_local * NZ * itemsize / 1e9)},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "wall_s_timed_region": wall,
+            "budgets": {"water_before": bud[0], "water_after": bud[1], "nan_count": bud[2], "energy_after": bud[3]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -54,5 +54,7 @@ class OracleIntegrator(trm.ModelIntegrator):
         return int(self._lib.cdll.orc_array_passes(self._h))
 
 
-def oracle_initialize(model, timestepper, inputs=None, *, boundary_conditions=None, initializers=None, partition=None):
+def oracle_initialize(model, timestepper, inputs=None, *, boundary_conditions=None, initializers=None, partition=None,
+                      math="faithful"):
+    # `math` is accepted for signature parity with trm.initialize and ignored: the oracle has one arithmetic
     return OracleIntegrator(model, timestepper, inputs, boundary_conditions, initializers, partition)

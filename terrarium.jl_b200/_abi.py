@@ -118,9 +118,10 @@ SIGNATURES = {
     "diagnostics_device": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "launch_count": (C.c_int64, [_H]),
     "last_step_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "set_block_size": (C.c_int, [_H, C.c_int]),
 }
 # entry points that only make sense on a device and that the CPU oracle does not export
-DEVICE_ONLY = ("field_ptr", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms")
+DEVICE_ONLY = ("field_ptr", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size")
 
 
 class BoundLibrary:

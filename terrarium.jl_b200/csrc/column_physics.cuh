@@ -1,0 +1,199 @@
+// column_physics.cuh -- per-cell / per-column scalar physics of the land time-step (device code).
+//
+// Every function cites the reference code it computes (paths relative to the reference root).
+// The arithmetic is written in the SAME operation order as the reference kernels so that a
+// translation unit compiled with -fmad=false ("faithful" math) reproduces the reference CPU
+// path rounding for rounding wherever no transcendental is involved.  `FAST` selects
+// algebraically identical shortcuts (van Genuchten n = 2 via cbrt/sqrt, exp10 instead of pow,
+// reciprocal multiplies); that translation unit is additionally compiled with FMA contraction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/terrarium_b200.h"
+
+namespace trm {
+
+// Parameters converted once to the number format NF (like Julia's `Struct{NF}` constructors).
+template <class NF>
+struct DevParams {
+    NF por, org, L;            // homogeneous_strat.jl:34-61 ; rho_w * Lsl (soil_energy_closures.jl:76,113)
+    NF sqk[5], hc[5];          // sqrt(kappa_i) and c_i in the order water, ice, air, mineral, organic
+    NF Ksat, vg_alpha, vg_n, bc_psis, bc_lambda, theta_res, Omega, vwcf;
+    NF rho_a, c_a, Llg, Tref, sigma, eps_mw, albedo, emis, kappa_skin, C_h, Vmin, tau_r, beta;
+    // derived constants used by FAST math only
+    NF rpor, neg_inv_alpha, vg_k_exp1, vg_k_exp2, vg_inv_m_neg, vg_inv_n;
+    int32_t swrc, unsat_k, sat_halo, skin;
+    int32_t vg_n_is_2;
+};
+
+template <class NF> struct Lim;
+template <> struct Lim<float> {
+    __device__ static float eps() { return 1.1920928955078125e-07f; }
+    __device__ static float inf() { return CUDART_INF_F; }
+    __device__ static float nan() { return CUDART_NAN_F; }
+};
+template <> struct Lim<double> {
+    __device__ static double eps() { return 2.220446049250313e-16; }
+    __device__ static double inf() { return CUDART_INF; }
+    __device__ static double nan() { return CUDART_NAN; }
+};
+
+// Julia `min` / `max` on floats propagate NaN (base/math.jl); fmin/fmax would drop it.
+template <class NF> __device__ __forceinline__ NF jmin(NF a, NF b) { return (a != a || b != b) ? Lim<NF>::nan() : (b < a ? b : a); }
+template <class NF> __device__ __forceinline__ NF jmax(NF a, NF b) { return (a != a || b != b) ? Lim<NF>::nan() : (a < b ? b : a); }
+
+__device__ __forceinline__ float  tpow(float a, float b)   { return powf(a, b); }
+__device__ __forceinline__ double tpow(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ float  tsqrt(float a)  { return sqrtf(a); }
+__device__ __forceinline__ double tsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float  tcbrt(float a)  { return cbrtf(a); }
+__device__ __forceinline__ double tcbrt(double a) { return cbrt(a); }
+__device__ __forceinline__ float  texp(float a)   { return expf(a); }
+__device__ __forceinline__ double texp(double a)  { return exp(a); }
+__device__ __forceinline__ float  texp10(float a)  { return exp10f(a); }
+__device__ __forceinline__ double texp10(double a) { return exp10(a); }
+__device__ __forceinline__ float  tabs(float a)   { return fabsf(a); }
+__device__ __forceinline__ double tabs(double a)  { return fabs(a); }
+
+// volumetric fractions, src/processes/soil/stratigraphy/soil_volume.jl:52-67,103-107
+template <class NF>
+struct Fractions { NF water, ice, air, mineral, organic; };
+
+template <class NF>
+__device__ __forceinline__ Fractions<NF> fractions(const DevParams<NF>& p, NF sat, NF liq) {
+    Fractions<NF> f;
+    NF wi = sat * p.por;
+    f.water = wi * liq;
+    f.ice = wi * (1 - liq);
+    f.air = (1 - sat) * p.por;
+    NF solid = 1 - p.por;
+    f.organic = solid * p.org;
+    f.mineral = solid * (1 - p.org);
+    return f;
+}
+
+// InverseQuadratic bulk thermal conductivity, soil_thermal_properties.jl:90-108
+template <class NF>
+__device__ __forceinline__ NF thermal_conductivity(const DevParams<NF>& p, NF sat, NF liq) {
+    Fractions<NF> f = fractions(p, sat, liq);
+    NF s = p.sqk[0] * f.water + p.sqk[1] * f.ice + p.sqk[2] * f.air + p.sqk[3] * f.mineral + p.sqk[4] * f.organic;
+    return s * s;
+}
+
+// volumetric heat capacity, soil_thermal_properties.jl:110-123
+template <class NF>
+__device__ __forceinline__ NF heat_capacity(const DevParams<NF>& p, NF sat, NF liq) {
+    Fractions<NF> f = fractions(p, sat, liq);
+    return p.hc[0] * f.water + p.hc[1] * f.ice + p.hc[2] * f.air + p.hc[3] * f.mineral + p.hc[4] * f.organic;
+}
+
+// energy_to_temperature + liquid_water_fraction (free water freeze curve),
+// soil_energy_closures.jl:99-159 ; safediv utils/utils.jl:25 ; Bool * x is a strong zero.
+template <class NF, bool FAST>
+__device__ __forceinline__ void energy_to_temperature(const DevParams<NF>& p, NF U, NF sat, NF& T, NF& liq) {
+    NF Lt = p.L * sat * p.por;
+    if (U >= 0) {
+        liq = 1;
+    } else if (U >= -Lt) {
+        NF y = -Lt;
+        NF sd = (y == 0) ? Lim<NF>::inf() : U / (y + Lim<NF>::eps());
+        liq = 1 - sd;
+    } else {
+        liq = 0;
+    }
+    NF C = heat_capacity(p, sat, liq);
+    if (U < -Lt) T = (U + Lt) / C;
+    else if (U >= 0) T = U / C;
+    else T = 0;
+}
+
+// temperature_to_energy (initialisation), soil_energy_closures.jl:64-97
+template <class NF>
+__device__ __forceinline__ void temperature_to_energy(const DevParams<NF>& p, NF T, NF sat, NF& U, NF& liq) {
+    liq = T >= 0 ? NF(1) : NF(0);
+    NF C = heat_capacity(p, sat, liq);
+    U = T * C - p.L * sat * p.por * (1 - liq);
+}
+
+// hydraulic conductivity at a cell centre, soil_hydraulic_properties.jl:170-221
+// (real branch of the complex-valued formula; exponent n/(n+1) as coded)
+template <class NF, bool FAST>
+__device__ __forceinline__ NF cell_conductivity(const DevParams<NF>& p, NF sat, NF liq) {
+    Fractions<NF> f = fractions(p, sat, liq);
+    if (p.unsat_k == TRM_UNSATK_LINEAR) {
+        NF thsat = f.water + f.ice + f.air;
+        return p.Ksat * f.water / thsat;
+    }
+    NF n = p.vg_n;
+    NF x = f.water / p.por;
+    if (FAST) {
+        NF I_ice = (liq == NF(1)) ? NF(1) : texp10(-p.Omega * (1 - liq));
+        NF a;
+        if (p.vg_n_is_2) {
+            NF c = tcbrt(x);                 // x^(2/3) = cbrt(x)^2
+            a = 1 - tsqrt(1 - c * c);        // (.)^(1/2)
+        } else {
+            a = 1 - tpow(1 - tpow(x, p.vg_k_exp1), p.vg_k_exp2);
+        }
+        return tabs(p.Ksat * I_ice * tsqrt(x) * (a * a));
+    }
+    NF I_ice = tpow(NF(10), -p.Omega * (1 - liq));
+    NF inner = 1 - tpow(x, n / (n + 1));
+    NF a = 1 - tpow(inner, (n - 1) / n);
+    return tabs(p.Ksat * I_ice * tsqrt(x) * (a * a));
+}
+
+// inverse soil water retention curve psi_m(theta; theta_sat) [FreezeCurves.jl 0.9 VanGenuchten /
+// BrooksCorey], called at soil_hydraulic_closures.jl:115-118
+template <class NF, bool FAST>
+__device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF thsat) {
+    if (p.swrc == TRM_SWRC_VANGENUCHTEN) {
+        if (!(theta < thsat)) return NF(0);
+        NF se = (theta - p.theta_res) / (thsat - p.theta_res);
+        if (FAST) {
+            if (p.vg_n_is_2) return p.neg_inv_alpha * tsqrt(1 / (se * se) - NF(1));   // m = 1/2
+            return p.neg_inv_alpha * tpow(tpow(se, p.vg_inv_m_neg) - NF(1), p.vg_inv_n);
+        }
+        NF n = p.vg_n, m = 1 - 1 / n;
+        return -1 / p.vg_alpha * tpow(tpow(se, -1 / m) - NF(1), 1 / n);
+    }
+    if (!(theta < thsat)) return -p.bc_psis;
+    NF se = (theta - p.theta_res) / (thsat - p.theta_res);
+    return -p.bc_psis * tpow(se, -1 / p.bc_lambda);
+}
+
+// total pressure head, saturation_to_pressure! soil_hydraulic_closures.jl:102-129
+template <class NF, bool FAST>
+__device__ __forceinline__ NF pressure_head(const DevParams<NF>& p, NF sat, NF wt, NF zc, NF zref) {
+    NF psim = swrc_inverse<NF, FAST>(p, sat * p.por, p.por);
+    NF psiz = zc - zref;
+    NF psih = jmax(NF(0), wt - zc);
+    return psih + psim + psiz;
+}
+
+// Julia Base.Math.pow_body(x::Float64, 4) (compensated power by squaring); Float32 `x^4` goes
+// through Float64 and rounds once.  Used for (Ts + Tref)^4, physical_constants.jl:67.
+__device__ __forceinline__ double pow4(double x) {
+    double y = 1.0, xnlo = 0.0, ynlo = 0.0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {   // n = 4 -> 2 -> 1: two squarings, the odd branch is never taken
+        double err = x * 2 * xnlo;
+        double hi = x * x;
+        double lo = fma(x, x, -hi);
+        x = hi; xnlo = lo + err;
+    }
+    double err = fma(y, xnlo, x * ynlo);
+    return (isfinite(x) && isfinite(err)) ? fma(x, y, err) : x * y;
+}
+__device__ __forceinline__ float pow4(float x) { double d = (double)x; double d2 = d * d; return (float)(d2 * d2); }
+
+// saturation vapour pressure (August-Roche-Magnus), physics_utils.jl:54-73
+template <class NF>
+__device__ __forceinline__ NF saturation_vapor_pressure(NF T) {
+    return T <= 0 ? NF(611.0) * texp(NF(22.46) * T / (T + NF(272.62))) : NF(611.0) * texp(NF(17.62) * T / (T + NF(243.12)));
+}
+
+}  // namespace trm

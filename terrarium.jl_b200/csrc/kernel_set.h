@@ -1,0 +1,22 @@
+// kernel_set.h -- launch entry points of one math-mode translation unit (faithful or fast).
+#pragma once
+#include "stage_kernel.cuh"
+
+namespace trm {
+
+// which stage_kernel instantiation to launch
+enum Variant { VAR_EULER_RECOMPUTE = 0, VAR_EULER_LOAD = 1, VAR_GENERIC = 2 };
+
+struct KernelSet {
+    cudaError_t (*stage_f32)(int phys, int variant, const StageArgs<float>& a, int block, cudaStream_t st);
+    cudaError_t (*stage_f64)(int phys, int variant, const StageArgs<double>& a, int block, cudaStream_t st);
+    cudaError_t (*init_f32)(int64_t ncol, int64_t ld, int nz, int richards, const float* metrics, const DevParams<float>& p,
+                            float* U, float* S, float* T, float* L, float* P, float* Wt, float* Sx, cudaStream_t st);
+    cudaError_t (*init_f64)(int64_t ncol, int64_t ld, int nz, int richards, const double* metrics, const DevParams<double>& p,
+                            double* U, double* S, double* T, double* L, double* P, double* Wt, double* Sx, cudaStream_t st);
+};
+
+const KernelSet& kernels_faithful();   // compiled with -fmad=false, reference operation order
+const KernelSet& kernels_fast();       // FMA contraction + algebraic shortcuts
+
+}  // namespace trm

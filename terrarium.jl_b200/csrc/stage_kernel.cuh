@@ -1,0 +1,561 @@
+// stage_kernel.cuh -- the fused per-column stage kernel (one launch per timestepper stage).
+//
+// One thread owns one column and streams it bottom -> top exactly once.  In that single sweep it
+// performs what the reference does in ~25 separate KernelAbstractions launches per Euler step
+// (SURVEY.md 3.2):
+//
+//   update_state!            src/state_variables.jl:72-80
+//     reset_tendencies!        (tendencies never exist in memory here)
+//     update_inputs!           inputs are evaluated in-kernel at clock time t (device resident forcing)
+//     fill_halo_regions!       halo values are formed in registers from the BC descriptors
+//     compute_auxiliary!       hydraulic conductivity at centres/faces, soil_hydrology.jl:145-163,249-276;
+//                              LandModel: evaporation, runoff/infiltration, 2 x surface energy balance
+//                              (land_model.jl:79-88)
+//     compute_tendencies!      Richards/Darcy soil_hydrology_rre.jl:95-131 ; heat conduction soil_energy.jl:112-149
+//   explicit_step!           src/timesteppers/abstract_timestepper.jl:65-141 (+ Flux BCs)
+//   closure!                 adjust_saturation_profile! soil_hydrology.jl:185-219, compute_water_table! :170-175,
+//                            saturation_to_pressure! soil_hydraulic_closures.jl:102-129,
+//                            energy_to_temperature! soil_energy_closures.jl:99-159
+//
+// Memory traffic per column-layer-step (Richards + energy, Euler, LOAD_AUX = false): read U, sat;
+// write U, sat, T, liq, psi = 7 * sizeof(NF).  Temperature, liquid fraction and pressure head of the
+// state at time n are NOT re-read: they are recomputed in registers from (U, sat, water_table) with
+// the same closure code that wrote them at the end of step n-1.  LOAD_AUX = true reads them from
+// HBM instead (first step after initialize / after the user overwrote a field, where the stored
+// closure fields are not a function of the stored prognostic fields).
+//
+// Data layout: [layer][column], column fastest: a warp touches 32 adjacent columns of one layer
+// per load instruction (fully coalesced 256 B for FP64, 128 B for FP32); raw loads are software
+// pipelined PF layers ahead in registers.
+#pragma once
+
+#include "column_physics.cuh"
+
+namespace trm {
+
+enum StageMode { MODE_EULER = 0, MODE_HEUN1 = 1, MODE_HEUN2 = 2, MODE_TEND = 3, MODE_AUX = 4 };
+enum Phys { PHYS_NOFLOW = 0, PHYS_RICHARDS = 1, PHYS_LAND = 2 };
+
+template <class NF>
+struct InputDesc {
+    int32_t kind, nt;
+    NF cval;
+    double period, lo, hi;
+    const NF *a, *b, *c;     // FIELD: a ; SINUSOID: a = mean, b = amp, c = phase ; TABLE: a = values[nt][ld]
+    const double* times;     // TABLE
+    int64_t ld;
+};
+
+template <class NF>
+struct StageArgs {
+    int64_t ncol, ld;
+    int32_t nz, mode, load_aux, pad_;
+    NF dt;
+    NF t_x;   // clock time of the state the tendencies are evaluated on (halo BC inputs, forcing)
+    NF t_b;   // clock time of the base state (Flux BC inputs); differs from t_x only in Heun stage 2
+    // X: state the tendencies are evaluated on
+    const NF *xU, *xS, *xT, *xL, *xP, *xWt;
+    // B: base state the update is applied to
+    const NF *bU, *bS, *bSx;
+    // Y: updated state
+    NF *yU, *yS, *yT, *yL, *yP, *yWt, *ySx;
+    // tendencies: read in Heun stage 2, written in Heun stage 1 (without Flux BCs) and TEND (with)
+    const NF *k1U, *k1S;
+    NF *oTU, *oTS;
+    NF* Kf;   // z-face hydraulic conductivity [nz+1][ld], written in AUX / TEND
+    // LandModel 2-D fields
+    NF *Ts, *G, *SWup, *LWup, *Rnet, *Hs, *Hl, *Egnd, *infil, *runoff;
+    const NF* metrics;   // [6][nz+3]: zF, zC, dzc, rdzc, dzf, rdzf (reference 1-based indices + halos)
+    DevParams<NF> p;
+    trm_bc bc[TRM_BC_NSLOTS];
+    InputDesc<NF> in[TRM_IN_COUNT];
+};
+
+// update_inputs! (input_sources.jl:165-171) and function valued BCs, evaluated at clock time t.
+template <class NF>
+__device__ __forceinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) {
+    switch (s.kind) {
+        case TRM_SRC_CONST: return s.cval;
+        case TRM_SRC_FIELD: return s.a[c];
+        case TRM_SRC_SINUSOID: {
+            // `2pi * t / period - lon` is Float64 arithmetic in Julia whatever NF is
+            // (examples/simulations/soil_heat_global.jl:79-88); rounded when stored in the NF field.
+            double ph = 6.283185307179586 * (double)t / s.period - (double)s.c[c];
+            double v = (double)s.a[c] + (double)s.b[c] * sin(ph);
+            v = fmin(fmax(v, s.lo), s.hi);
+            return (NF)v;
+        }
+        case TRM_SRC_TABLE: {
+            // FieldTimeSeries[Time(t)]: linear between bracketing snapshots, flat outside
+            // (ext/TerrariumRastersExt/TerrariumRastersExt.jl:104-120)
+            double td = (double)t;
+            const double* tt = s.times;
+            int nt = s.nt;
+            if (td <= tt[0]) return s.a[c];
+            if (td >= tt[nt - 1]) return s.a[(int64_t)(nt - 1) * s.ld + c];
+            int lo = 0, hi = nt;   // upper_bound: first index with tt[i] > td
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (tt[mid] > td) hi = mid; else lo = mid + 1; }
+            int n2 = lo, n1 = lo - 1;
+            NF frac = (NF)((td - tt[n1]) / (tt[n2] - tt[n1]));
+            return s.a[(int64_t)n2 * s.ld + c] * frac + s.a[(int64_t)n1 * s.ld + c] * (1 - frac);
+        }
+    }
+    return NF(0);
+}
+
+// Oceananigans halo fill for one side.  `D` is the face spacing at the
+// boundary, `top` selects the sign convention.
+template <class NF>
+__device__ __forceinline__ NF halo_value(int kind, NF edge, NF v, NF D, bool top) {
+    if (kind == TRM_BC_VALUE) {
+        if (top) { NF g = (v - edge) / (D / 2); return edge + g * D; }
+        NF g = (edge - v) / (D / 2); return edge + g * (-D);
+    }
+    if (kind == TRM_BC_GRADIENT) return top ? edge + v * D : edge + v * (-D);
+    return edge;
+}
+
+// ---- LandModel per-column surface processes ---------------------------------------------------
+template <class NF>
+struct Surface {
+    NF SWd, LWd, Ta, pres, q, V, rain, Tskin_in;
+    double ra;
+};
+
+// compute_surface_energy_fluxes! (one evaluation), surface_energy_balance.jl:119-144:
+// radiative_fluxes.jl:85-100,196-209 ; turbulent_fluxes.jl:85-105,137-150 ; skin_temperature.jl:76-80
+template <class NF>
+__device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface<NF>& a, NF Tsurf, NF Egnd,
+                                           NF& swu, NF& lwu, NF& rnet, NF& hs, NF& hl, NF& G) {
+    swu = p.albedo * a.SWd;
+    NF TK = Tsurf + p.Tref;
+    lwu = p.emis * p.sigma * pow4(TK) + (1 - p.emis) * a.LWd;
+    rnet = swu - a.SWd + lwu - a.LWd;
+    hs = (NF)((double)(p.c_a * p.rho_a) * ((double)(Tsurf - a.Ta) / a.ra));
+    hl = p.Llg * p.rho_a * Egnd;
+    G = rnet - hs - hl;
+}
+
+template <class NF, int PHYS, int MODE_CT, int LOAD_CT, bool FAST>
+__global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ StageArgs<NF> A) {
+    constexpr bool RICH = PHYS != PHYS_NOFLOW;
+    constexpr bool LAND = PHYS == PHYS_LAND;
+    constexpr int PF = 4;   // layers of raw loads in flight per thread
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NF* sm = reinterpret_cast<NF*>(smem_raw);
+    const int nz = A.nz, nzp = nz + 3;
+    for (int i = threadIdx.x; i < 6 * nzp; i += blockDim.x) sm[i] = A.metrics[i];
+    __syncthreads();
+    const NF* zF = sm;
+    const NF* zC = sm + nzp;
+    const NF* dzc = sm + 2 * nzp;
+    const NF* rdzc = sm + 3 * nzp;
+    const NF* dzf = sm + 4 * nzp;
+    const NF* rdzf = sm + 5 * nzp;
+
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.ncol) return;
+    const int64_t ld = A.ld;
+    const DevParams<NF>& p = A.p;
+    const int mode = MODE_CT >= 0 ? MODE_CT : A.mode;
+    const bool load_aux = LOAD_CT >= 0 ? (LOAD_CT != 0) : (A.load_aux != 0);
+    const bool need_K = RICH || mode == MODE_AUX || mode == MODE_TEND;   // compute_hydraulics! always runs in the
+                                                                        // reference; only materialised when asked
+    const bool write_K = mode == MODE_AUX || mode == MODE_TEND;
+    const bool do_update = mode == MODE_EULER || mode == MODE_HEUN1 || mode == MODE_HEUN2;
+    const bool full_closure = mode == MODE_EULER || mode == MODE_HEUN2;
+    const NF dt = A.dt;
+    const NF zref = zF[nz + 1];
+
+    // ---- boundary condition inputs at the times the reference evaluates them ----
+    NF bcv[TRM_BC_NSLOTS];
+#pragma unroll
+    for (int s = 0; s < TRM_BC_NSLOTS; ++s) {
+        bcv[s] = NF(0);
+        int kind = A.bc[s].kind;
+        if (kind != TRM_BC_DEFAULT) bcv[s] = eval_input(A.in[A.bc[s].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x);
+    }
+    const NF wtx = RICH && !load_aux ? A.xWt[c] : NF(0);
+
+    struct Raw { NF U, s, T, l, P; };
+    auto load_raw = [&](int k) {
+        Raw r; r.U = r.s = r.T = r.l = r.P = NF(0);
+        if (k <= nz) {
+            int64_t o = (int64_t)(k - 1) * ld + c;
+            r.U = A.xU[o]; r.s = A.xS[o];
+            if (load_aux) { r.T = A.xT[o]; r.l = A.xL[o]; if (RICH) r.P = A.xP[o]; }
+        }
+        return r;
+    };
+    // cell properties of the state at time n: T, liq, psi (closure fields), kappa, Kc
+    struct Cell { NF U, s, T, l, P, kap, Kc; };
+    auto make_cell = [&](const Raw& r, int k) {
+        Cell q; q.U = r.U; q.s = r.s; q.P = NF(0); q.Kc = NF(0);
+        if (load_aux) { q.T = r.T; q.l = r.l; q.P = r.P; }
+        else {
+            energy_to_temperature<NF, FAST>(p, r.U, r.s, q.T, q.l);
+            if (RICH) q.P = pressure_head<NF, FAST>(p, r.s, wtx, zC[k], zref);
+        }
+        q.kap = thermal_conductivity(p, r.s, q.l);
+        if (need_K) q.Kc = cell_conductivity<NF, FAST>(p, r.s, q.l);
+        return q;
+    };
+
+    Raw r1 = load_raw(1), r2 = load_raw(2);
+    Raw ring[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) ring[i] = load_raw(3 + i);
+
+    // ---- prologue: cells 1, 2 and the bottom halo (cell 0) ----
+    Cell ca = make_cell(r1, 1);
+    Cell cb = make_cell(r2, 2);
+    Cell cc = cb;
+    NF T0 = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, ca.T, bcv[TRM_BC_TEMPERATURE_BOTTOM], dzf[1], false);
+    NF s0 = (RICH || p.sat_halo == TRM_HALO_COPY) ? ca.s : NF(0);
+    NF kap0 = thermal_conductivity(p, s0, ca.l);
+    NF qh_lo = -((ca.kap + kap0) / 2) * ((ca.T - T0) * rdzf[1]);          // diffusive_heat_flux, soil_energy.jl:134-149
+    NF Kf_m = NF(0);                                                      // Kf[j-1]; Kf[0] is never written
+    NF Kf_0 = ca.Kc;                                                      // Kf[j]   ; Kf[1] = Kc[1]
+    NF Kf_p = (2 >= nz) ? cb.Kc : jmin(cb.Kc, ca.Kc);                     // Kf[j+1] ; Kf[2]
+    NF qd_lo = NF(0);
+    if (RICH) {
+        NF P0 = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, ca.P, bcv[TRM_BC_PRESSURE_BOTTOM], dzf[1], false);
+        NF g = (ca.P - P0) * rdzf[1];
+        NF Kk = (g < 0 ? jmin(Kf_m, Kf_0) : NF(0)) + (g >= 0 ? jmin(Kf_0, Kf_p) : NF(0));   // darcy_flux, soil_hydrology_rre.jl:119-131
+        qd_lo = -Kk * g;
+    }
+    if (write_K) A.Kf[c] = Kf_0;
+
+    NF carry = NF(0);          // over-saturation handed to the layer above (upward sweep of adjust_saturation_profile!)
+    bool any_neg = false;      // a negative saturation needs the downward sweep -> slow path
+    int idx = 0;               // lowest unsaturated layer (compute_water_table!), 0 = not found yet
+    NF wt_new = NF(0);
+    NF Sx_new = NF(0);
+    if (RICH && do_update) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
+
+    // LandModel: fluxes coupling the surface to the top soil layer
+    NF G_top = NF(0), infil_top = NF(0);
+
+    for (int jb = 1; jb <= nz; jb += PF) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const int j = jb + i;
+            if (j > nz) break;
+            // ---- cell j+2 (or the top halo) enters the window ----
+            Raw rc = ring[i];
+            ring[i] = load_raw(j + 2 + PF);
+            NF T_c = NF(0), kap_c = NF(0), P_c = NF(0);
+            if (j + 2 <= nz) {
+                cc = make_cell(rc, j + 2);
+            } else if (j + 2 == nz + 1) {   // top halo (cell nz + 1) built from cell nz, which is cb right now
+                T_c = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, cb.T, bcv[TRM_BC_TEMPERATURE_TOP], dzf[nz + 1], true);
+                NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? cb.s : NF(0);
+                kap_c = thermal_conductivity(p, sh, cb.l);
+                if (RICH) P_c = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, cb.P, bcv[TRM_BC_PRESSURE_TOP], dzf[nz + 1], true);
+            }
+            // ---- face conductivity Kf[j+2], soil_hydrology.jl:249-276 ----
+            NF Kf_pp = NF(0);
+            if (need_K) {
+                const int kf = j + 2;
+                if (kf < nz) Kf_pp = jmin(cc.Kc, cb.Kc);
+                else if (kf == nz) Kf_pp = cc.Kc;
+                else if (kf == nz + 1) Kf_pp = Kf_p;    // Kf[Nz+1] = Kf[Nz]
+                // kf == nz + 2: halo face, never written (0)
+            }
+            if (write_K) A.Kf[(int64_t)j * ld + c] = Kf_p;   // Kf[j+1] lives in row j (0-based)
+
+            // ---- LandModel surface processes, once the top cell is cell j ----
+            if (LAND && j == nz && mode != MODE_HEUN2) {
+                Surface<NF> a;
+                a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
+                a.LWd = eval_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
+                a.Ta = eval_input(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
+                a.pres = eval_input(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
+                a.q = eval_input(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
+                a.V = eval_input(A.in[TRM_IN_WINDSPEED], c, A.t_x);
+                a.rain = eval_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
+                const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
+                a.Tskin_in = prescribed ? eval_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
+                // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
+                NF Vc = jmax(a.V, p.Vmin);
+                double Va = fmax((double)Vc, 1.0e-6);
+                a.ra = 1.0 / ((double)p.C_h * Va);
+                NF Ts = A.Ts[c];
+                // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
+                // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
+                NF Tsurf = prescribed ? a.Tskin_in : Ts;
+                NF es = saturation_vapor_pressure(Tsurf);
+                NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
+                NF vpd = jmax(es - ea, NF(0.1));
+                NF dq = p.eps_mw * vpd / a.pres;
+                NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
+                // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall)
+                NF S = A.bSx[c], Kt = Kf_0, sat_top = ca.s;
+                NF drain, inf;
+                if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
+                else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, Kt) : NF(0); }
+                NF runoff = a.rain + drain - inf;
+                // surface energy balance kernel, executed twice (land_model.jl:85-86)
+                NF swu, lwu, rnet, hs, hl, G;
+#pragma unroll 1
+                for (int rep = 0; rep < 2; ++rep) {
+                    seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+                    if (!prescribed) {
+                        Ts = ca.T - G * dzc[nz] / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
+                        seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+                    }
+                }
+                A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
+                A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
+                if (!prescribed) A.Ts[c] = Ts;
+                G_top = G; infil_top = inf;
+            }
+            if (LAND && j == nz && mode == MODE_HEUN2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
+
+            if (mode != MODE_AUX) {
+                // ---- fluxes at face j+1 ----
+                // window: a = cell j, b = cell j+1 (for j == nz slot b holds the top halo, see the shift below)
+                NF qh_hi = -((cb.kap + ca.kap) / 2) * ((cb.T - ca.T) * rdzf[j + 1]);
+                NF qd_hi = NF(0);
+                if (RICH) {
+                    NF g = (cb.P - ca.P) * rdzf[j + 1];
+                    NF Kk = (g < 0 ? jmin(Kf_0, Kf_p) : NF(0)) + (g >= 0 ? jmin(Kf_p, Kf_pp) : NF(0));
+                    qd_hi = -Kk * g;
+                }
+                // ---- tendencies of cell j ----
+                NF tU = -((qh_hi - qh_lo) * rdzc[j]);                              // soil_energy.jl:112-131
+                NF tS = NF(0);
+                if (RICH) {
+                    NF dth = -((qd_hi - qd_lo) * rdzc[j]) + NF(0) + p.vwcf;          // soil_hydrology_rre.jl:95-117
+                    tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
+                }
+                qh_lo = qh_hi; qd_lo = qd_hi;
+                const int64_t o = (int64_t)(j - 1) * ld + c;
+                if (mode == MODE_HEUN1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
+                if (mode == MODE_HEUN2) {                                           // average_tendencies! heun.jl:27-35
+                    tU = (A.k1U[o] + tU) / 2;
+                    if (RICH) tS = (A.k1S[o] + tS) / 2;
+                }
+                // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
+                if (j == nz) {
+                    if (LAND) { tU -= G_top / dzc[nz]; tS -= (-infil_top) / dzc[nz]; }           // land_model.jl:56-62
+                    else {
+                        if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bcv[TRM_BC_ENERGY_TOP] / dzc[nz];
+                        if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bcv[TRM_BC_SATURATION_TOP] / dzc[nz];
+                    }
+                }
+                if (j == 1) {
+                    if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bcv[TRM_BC_ENERGY_BOTTOM] / dzc[1];
+                    if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bcv[TRM_BC_SATURATION_BOTTOM] / dzc[1];
+                }
+                if (mode == MODE_TEND) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
+
+                if (do_update) {
+                    // ---- explicit step, abstract_timestepper.jl:113-141 ----
+                    NF Ub = (mode == MODE_HEUN2) ? A.bU[o] : ca.U;
+                    NF Un = Ub + tU * dt;
+                    NF sn = ca.s;
+                    if (RICH) {
+                        NF sb = (mode == MODE_HEUN2) ? A.bS[o] : ca.s;
+                        sn = sb + tS * dt;
+                        // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
+                        sn = sn + carry;
+                        if (j < nz) {
+                            NF e = jmax(sn - 1, NF(0));
+                            sn -= e;
+                            carry = e * dzc[j] / dzc[j + 1];
+                        }
+                        if (sn < 0) any_neg = true;
+                    }
+                    if (RICH && any_neg) {
+                        // raw values for the slow path below (downward sweep needs the whole profile)
+                        A.yU[o] = Un; A.yS[o] = sn;
+                    } else {
+                        if (RICH) {
+                            // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208)
+                            if (j >= 2) sn = sn + jmax(-sn, NF(0));
+                            if (j == nz) {                                   // top excess -> surface_excess_water (:210-214)
+                                NF e = jmax(sn - 1, NF(0));
+                                sn -= e;
+                                Sx_new += e * dzc[nz];
+                            }
+                            if (j == 1) sn = jmax(sn, NF(0));                // :216
+                            A.yS[o] = sn;
+                            if (idx == 0 && sn < 1) { idx = j; wt_new = zF[j]; }   // compute_water_table!, kernel_utils.jl:7-16
+                        }
+                        A.yU[o] = Un;
+                        if (full_closure) {
+                            NF Tn, ln;
+                            energy_to_temperature<NF, FAST>(p, Un, sn, Tn, ln);
+                            A.yT[o] = Tn; A.yL[o] = ln;
+                            // cells below the water table wait for it (written after the sweep)
+                            if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, zC[j], zref);
+                        }
+                    }
+                }
+            }
+            // ---- shift the window ----
+            Kf_m = Kf_0; Kf_0 = Kf_p; Kf_p = Kf_pp;
+            if (j + 1 <= nz) {
+                ca = cb;
+                if (j + 2 <= nz) cb = cc;
+                else { cb.T = T_c; cb.kap = kap_c; cb.P = P_c; }   // top halo now sits in slot b (only T, kap, P are used)
+            }
+        }
+    }
+    if (mode == MODE_AUX || mode == MODE_TEND || !do_update) return;
+    if (!RICH) return;
+
+    if (!any_neg) {
+        if (idx == 0) { idx = nz + 1; wt_new = zF[nz + 1]; }   // all saturated: z of the surface (halo cell / fallback give the same)
+        A.yWt[c] = wt_new;
+        if (A.ySx) A.ySx[c] = Sx_new;
+        if (full_closure) {
+            // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
+            NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
+            for (int k = 1; k < idx && k <= nz; ++k) {
+                NF z = zC[k];
+                A.yP[(int64_t)(k - 1) * ld + c] = jmax(NF(0), wt_new - z) + psat + (z - zref);
+            }
+        }
+        return;
+    }
+    // ---- slow path: a layer went negative. Downward sweep (soil_hydrology.jl:201-216) top -> bottom on the raw
+    //      profile this thread just stored, then water table and closures bottom -> top. ----
+    {
+        NF carry_dn = NF(0);
+        for (int k = nz; k >= 1; --k) {
+            const int64_t o = (int64_t)(k - 1) * ld + c;
+            NF s = A.yS[o];
+            if (k < nz) s -= carry_dn;
+            if (k >= 2) {
+                NF d = jmax(-s, NF(0));
+                s += d;
+                carry_dn = d * dzc[k] / dzc[k - 1];
+            }
+            if (k == nz) {
+                NF e = jmax(s - 1, NF(0));
+                s -= e;
+                Sx_new += e * dzc[nz];
+            }
+            if (k == 1) s = jmax(s, NF(0));
+            A.yS[o] = s;
+        }
+        idx = 0;
+        for (int k = 1; k <= nz; ++k) if (idx == 0 && A.yS[(int64_t)(k - 1) * ld + c] < 1) idx = k;
+        if (idx == 0) idx = nz + 1;
+        wt_new = zF[idx];
+        A.yWt[c] = wt_new;
+        if (A.ySx) A.ySx[c] = Sx_new;
+        if (full_closure) {
+            for (int k = 1; k <= nz; ++k) {
+                const int64_t o = (int64_t)(k - 1) * ld + c;
+                NF s = A.yS[o], U = A.yU[o], Tn, ln;
+                energy_to_temperature<NF, FAST>(p, U, s, Tn, ln);
+                A.yT[o] = Tn; A.yL[o] = ln;
+                A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, zC[k], zref);
+            }
+        }
+    }
+}
+
+// ---- initialisation kernels (not on the hot path) ---------------------------------------------
+// initialize!(state, model): Richards closure! (adjust, water table, psi) then the inverse energy
+// closure T -> U (soil_coupled.jl:45-54, soil_hydrology_rre.jl:33-47, soil_energy.jl:64-77).
+template <class NF, bool FAST>
+__global__ void init_kernel(int64_t ncol, int64_t ld, int nz, int richards, const NF* __restrict__ metrics, DevParams<NF> p,
+                            NF* U, NF* S, NF* T, NF* Lq, NF* P, NF* Wt, NF* Sx) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const int nzp = nz + 3;
+    const NF* zF = metrics;
+    const NF* zC = metrics + nzp;
+    const NF* dzc = metrics + 2 * nzp;
+    if (richards) {
+        for (int k = 1; k <= nz - 1; ++k) {
+            NF s = S[(int64_t)(k - 1) * ld + c];
+            NF e = jmax(s - 1, NF(0));
+            S[(int64_t)(k - 1) * ld + c] = s - e;
+            S[(int64_t)k * ld + c] += e * dzc[k] / dzc[k + 1];
+        }
+        for (int k = nz; k >= 2; --k) {
+            NF s = S[(int64_t)(k - 1) * ld + c];
+            NF d = jmax(-s, NF(0));
+            S[(int64_t)(k - 1) * ld + c] = s + d;
+            S[(int64_t)(k - 2) * ld + c] -= d * dzc[k] / dzc[k - 1];
+        }
+        NF st = S[(int64_t)(nz - 1) * ld + c];
+        NF e = jmax(st - 1, NF(0));
+        S[(int64_t)(nz - 1) * ld + c] = st - e;
+        Sx[c] += e * dzc[nz];
+        S[c] = jmax(S[c], NF(0));
+    }
+    int idx = 0;
+    for (int k = 1; k <= nz; ++k) if (idx == 0 && S[(int64_t)(k - 1) * ld + c] < 1) idx = k;
+    // k = nz + 1 is the halo cell of the saturation field; found or not the result is zF[nz + 1]
+    if (idx == 0) idx = nz + 1;
+    NF wt = zF[idx];
+    Wt[c] = wt;
+    NF zref = zF[nz + 1];
+    for (int k = 1; k <= nz; ++k) {
+        const int64_t o = (int64_t)(k - 1) * ld + c;
+        NF s = S[o];
+        if (richards) P[o] = pressure_head<NF, FAST>(p, s, wt, zC[k], zref);
+        NF Uo, lo;
+        temperature_to_energy(p, T[o], s, Uo, lo);
+        U[o] = Uo; Lq[o] = lo;
+    }
+}
+
+// ---- diagnostics: column budgets and extrema (one partial per block, reduced by finish_diag) ----
+template <class NF>
+__global__ void __launch_bounds__(256) diag_kernel(int64_t ncol, int64_t ld, int nz, const NF* __restrict__ metrics, NF por,
+                                                   const NF* __restrict__ U, const NF* __restrict__ T, const NF* __restrict__ S,
+                                                   const NF* __restrict__ Sx, double* __restrict__ partial) {
+    const int nzp = nz + 3;
+    const NF* dzc = metrics + 2 * nzp;
+    double e = 0, w = 0, tmin = CUDART_INF, tmax = -CUDART_INF, smin = CUDART_INF, smax = -CUDART_INF, nan = 0;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += (int64_t)gridDim.x * blockDim.x) {
+        for (int k = 1; k <= nz; ++k) {
+            const int64_t o = (int64_t)(k - 1) * ld + c;
+            double u = U[o], t = T[o], s = S[o], dz = dzc[k];
+            e += u * dz; w += s * (double)por * dz;
+            tmin = fmin(tmin, t); tmax = fmax(tmax, t); smin = fmin(smin, s); smax = fmax(smax, s);
+            nan += (!isfinite(u)) + (!isfinite(t)) + (!isfinite(s));
+        }
+        if (Sx) w += (double)Sx[c];
+    }
+    __shared__ double red[7][256];
+    double v[7] = {e, w, tmin, tmax, smin, smax, nan};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) red[i][threadIdx.x] = v[i];
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + s];
+            red[1][threadIdx.x] += red[1][threadIdx.x + s];
+            red[2][threadIdx.x] = fmin(red[2][threadIdx.x], red[2][threadIdx.x + s]);
+            red[3][threadIdx.x] = fmax(red[3][threadIdx.x], red[3][threadIdx.x + s]);
+            red[4][threadIdx.x] = fmin(red[4][threadIdx.x], red[4][threadIdx.x + s]);
+            red[5][threadIdx.x] = fmax(red[5][threadIdx.x], red[5][threadIdx.x + s]);
+            red[6][threadIdx.x] += red[6][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 7; ++i) partial[(int64_t)blockIdx.x * 8 + i] = red[i][0];
+}
+
+static __global__ void finish_diag(int nblocks, const double* __restrict__ partial, double ncol, double* __restrict__ out) {
+    // single thread, fixed order: deterministic sums
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double e = 0, w = 0, tmin = CUDART_INF, tmax = -CUDART_INF, smin = CUDART_INF, smax = -CUDART_INF, nan = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        const double* q = partial + (int64_t)b * 8;
+        e += q[0]; w += q[1]; tmin = fmin(tmin, q[2]); tmax = fmax(tmax, q[3]); smin = fmin(smin, q[4]); smax = fmax(smax, q[5]); nan += q[6];
+    }
+    out[0] = e; out[1] = w; out[2] = tmin; out[3] = tmax; out[4] = smin; out[5] = smax; out[6] = nan; out[7] = ncol;
+}
+
+}  // namespace trm

@@ -1,0 +1,502 @@
+// terrarium_b200.cu -- the C ABI of include/terrarium_b200.h on top of the fused stage kernels.
+//
+// Host orchestration only: device buffers in [layer][column] SoA, parameter conversion to the
+// handle's number format, the ForwardEuler / Heun stage sequencing of
+// src/timesteppers/forward_euler.jl:19-31 and heun.jl:37-71, host <-> device field copies.
+// There is NO CPU implementation behind these entry points: without a CUDA device trm_create
+// fails with TRM_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernel_set.h"
+
+namespace {
+
+using namespace trm;
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) { g_err = m; return code; }
+
+#define CU(expr)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(TRM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+struct HandleBase {
+    virtual ~HandleBase() {}
+    virtual int set_field(int id, const void* host, int64_t count) = 0;
+    virtual int get_field(int id, void* host, int64_t count) = 0;
+    virtual int field_ptr(int id, void** p, int64_t* ld, int32_t* nrows) = 0;
+    virtual int set_input_const(int id, double v) = 0;
+    virtual int set_input_field(int id, const void* v) = 0;
+    virtual int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) = 0;
+    virtual int set_input_table(int id, int nt, const double* times, const void* values) = 0;
+    virtual int input_ptr(int id, void** p) = 0;
+    virtual int initialize() = 0;
+    virtual int step(double dt, int64_t n) = 0;
+    virtual int aux() = 0;
+    virtual int tendencies() = 0;
+    virtual int diagnostics(trm_diag* out, double** dev) = 0;
+    virtual int set_block(int b) = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    double time = 0.0;   // holds an NF value
+    int64_t iteration = 0;
+    int64_t launches = 0;
+    float last_ms = 0.f;
+};
+
+template <class NF>
+struct Handle : HandleBase {
+    trm_config cfg{};
+    int nz = 0; int64_t nc = 0, ld = 0;
+    bool land = false, richards = false, heun = false, fast = false;
+    int phys = PHYS_NOFLOW;
+    int block = 128;
+    const KernelSet* ks = nullptr;
+    DevParams<NF> p{};
+    std::vector<void*> allocs;
+    NF* metrics = nullptr;
+    // 3-D [nz][ld]
+    NF *U = nullptr, *T = nullptr, *Lq = nullptr, *S = nullptr, *P = nullptr, *Kf = nullptr;
+    NF *tU = nullptr, *tS = nullptr, *gU = nullptr, *gS = nullptr;   // tendencies, Heun stage state
+    // 2-D [ld]
+    NF *Sx = nullptr, *Wt = nullptr, *gWt = nullptr;
+    NF* land2d[10] = {nullptr};   // Ts, G, SWup, LWup, Rnet, Hs, Hl, Egnd, infil, runoff
+    struct Input { int kind = TRM_SRC_CONST; double cval = 0, period = 1, lo = -INFINITY, hi = INFINITY; int nt = 0;
+                   NF *a = nullptr, *b = nullptr, *c = nullptr; double* times = nullptr; };
+    Input in[TRM_IN_COUNT];
+    bool initialized = false;
+    bool aux_stale = true;   // stored T / liq / psi are not closure(U, sat): the next stage must read them
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double* diag_partial = nullptr; double* diag_out = nullptr; int diag_blocks = 0;
+
+    ~Handle() override {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (void* q : allocs) cudaFree(q);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    template <class X> int dalloc(X** out, size_t count, bool zero = true) {
+        void* q = nullptr;
+        CU(cudaMalloc(&q, count * sizeof(X)));
+        allocs.push_back(q);
+        if (zero) CU(cudaMemsetAsync(q, 0, count * sizeof(X), stream));
+        *out = (X*)q;
+        return TRM_OK;
+    }
+    void dfree(void* q) {
+        for (size_t i = 0; i < allocs.size(); ++i) if (allocs[i] == q) { allocs.erase(allocs.begin() + i); break; }
+        cudaFree(q);
+    }
+
+    int setup(const trm_config& c) {
+        cfg = c; nz = c.nz; nc = c.ncol; device = c.device;
+        land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
+        fast = c.math == TRM_MATH_FAST;
+        if (land && !richards) return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
+        phys = land ? PHYS_LAND : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
+        ks = fast ? &kernels_fast() : &kernels_faithful();
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return fail(TRM_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");
+        }
+        if (device < 0 || device >= ndev) return fail(TRM_ERR_INVALID, "device ordinal out of range");
+        CU(cudaSetDevice(device));
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+        ld = (nc + 63) / 64 * 64;   // rows are 256 B (FP32) / 512 B (FP64) aligned
+
+        // ---- grid metrics in NF, exactly as Oceananigans builds them from the NF faces:
+        //      halo faces extend with the edge spacing, centres are face midpoints.
+        const int nzp = nz + 3;
+        std::vector<NF> m(6 * (size_t)nzp, NF(0));
+        NF *zF = m.data(), *zC = zF + nzp, *dzc = zC + nzp, *rdzc = dzc + nzp, *dzf = rdzc + nzp, *rdzf = dzf + nzp;
+        for (int k = 1; k <= nz + 1; ++k) zF[k] = (NF)c.z_faces[k - 1];
+        zF[0] = zF[1] - (zF[2] - zF[1]);
+        zF[nz + 2] = zF[nz + 1] + (zF[nz + 1] - zF[nz]);
+        for (int k = 0; k <= nz + 1; ++k) { zC[k] = (zF[k + 1] + zF[k]) / 2; dzc[k] = zF[k + 1] - zF[k]; rdzc[k] = 1 / dzc[k]; }
+        for (int k = 1; k <= nz + 1; ++k) { dzf[k] = zC[k] - zC[k - 1]; rdzf[k] = 1 / dzf[k]; }
+        if (int rc = dalloc(&metrics, m.size())) return rc;
+        CU(cudaMemcpyAsync(metrics, m.data(), m.size() * sizeof(NF), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+
+        // ---- parameters in NF (same expression order as the reference constructors / kernels)
+        const trm_params& q = c.params;
+        NF por_m = (NF)q.mineral_porosity, por_o = (NF)q.organic_porosity;
+        p.org = (NF)q.rho_soc / ((1 - por_o) * (NF)q.rho_org);      // homogeneous_strat.jl:34-45
+        p.por = (1 - p.org) * por_m + p.org * por_o;                // homogeneous_strat.jl:52-61
+        p.L = (NF)q.rho_w * (NF)q.Lsl;
+        for (int i = 0; i < 5; ++i) { p.sqk[i] = std::sqrt((NF)q.kappa[i]); p.hc[i] = (NF)q.heatcap[i]; }
+        p.Ksat = (NF)q.K_sat; p.vg_alpha = (NF)q.vg_alpha; p.vg_n = (NF)q.vg_n; p.bc_psis = (NF)q.bc_psis; p.bc_lambda = (NF)q.bc_lambda;
+        p.theta_res = (NF)q.theta_res; p.Omega = (NF)q.impedance; p.vwcf = (NF)q.vwc_forcing;
+        p.rho_a = (NF)q.rho_a; p.c_a = (NF)q.c_a; p.Llg = (NF)q.Llg; p.Tref = (NF)q.Tref; p.sigma = (NF)q.sigma; p.eps_mw = (NF)q.eps_mw;
+        p.albedo = (NF)q.albedo; p.emis = (NF)q.emissivity; p.kappa_skin = (NF)q.kappa_skin; p.C_h = (NF)q.C_h; p.Vmin = (NF)q.min_windspeed;
+        p.tau_r = (NF)q.tau_r; p.beta = (NF)q.evap_beta;
+        p.rpor = 1 / p.por; p.neg_inv_alpha = -1 / p.vg_alpha;
+        p.vg_k_exp1 = p.vg_n / (p.vg_n + 1); p.vg_k_exp2 = (p.vg_n - 1) / p.vg_n;
+        { NF mm = 1 - 1 / p.vg_n; p.vg_inv_m_neg = -1 / mm; p.vg_inv_n = 1 / p.vg_n; }
+        p.swrc = c.swrc; p.unsat_k = c.unsat_k; p.sat_halo = c.sat_halo; p.skin = c.skin;
+        p.vg_n_is_2 = (p.vg_n == NF(2)) ? 1 : 0;
+
+        // ---- fields
+        const size_t n3 = (size_t)nz * ld;
+        for (NF** f : {&U, &T, &Lq, &S}) if (int rc = dalloc(f, n3)) return rc;
+        if (richards) { if (int rc = dalloc(&P, n3)) return rc; }
+        if (int rc = dalloc(&Kf, (size_t)(nz + 1) * ld)) return rc;
+        if (int rc = dalloc(&Sx, ld)) return rc;
+        if (int rc = dalloc(&Wt, ld)) return rc;
+        if (heun) {
+            for (NF** f : {&tU, &gU}) if (int rc = dalloc(f, n3)) return rc;
+            if (richards) { for (NF** f : {&tS, &gS}) if (int rc = dalloc(f, n3)) return rc; if (int rc = dalloc(&gWt, ld)) return rc; }
+        }
+        if (land) for (int i = 0; i < 10; ++i) if (int rc = dalloc(&land2d[i], ld)) return rc;
+        // input defaults, prescribed_atmosphere.jl:89-99,147-149,192-195,220-224,10-14
+        in[TRM_IN_AIR_TEMPERATURE].cval = 10; in[TRM_IN_AIR_PRESSURE].cval = 101325; in[TRM_IN_WINDSPEED].cval = 0.1;
+        in[TRM_IN_SPECIFIC_HUMIDITY].cval = 1.0e-3; in[TRM_IN_SHORTWAVE_DOWN].cval = 300; in[TRM_IN_LONGWAVE_DOWN].cval = 50;
+        in[TRM_IN_DAYTIME_LENGTH].cval = 12; in[TRM_IN_CO2].cval = 380;
+        diag_blocks = (int)std::min<int64_t>((nc + 255) / 256, 148 * 8);
+        if (int rc = dalloc(&diag_partial, (size_t)diag_blocks * 8)) return rc;
+        if (int rc = dalloc(&diag_out, 8)) return rc;
+        CU(cudaStreamSynchronize(stream));
+        return TRM_OK;
+    }
+
+    // ------------------------------------------------------------------ field access
+    struct FieldRef { NF* ptr; int nrows; bool writable; };
+    FieldRef field(int id) {
+        switch (id) {
+            case TRM_F_INTERNAL_ENERGY: return {U, nz, true};
+            case TRM_F_TEMPERATURE: return {T, nz, true};
+            case TRM_F_LIQUID_WATER_FRACTION: return {Lq, nz, true};
+            case TRM_F_SATURATION_WATER_ICE: return {S, nz, true};
+            case TRM_F_PRESSURE_HEAD: return {P, nz, true};
+            case TRM_F_HYDRAULIC_CONDUCTIVITY: return {Kf, nz + 1, false};
+            case TRM_F_SURFACE_EXCESS_WATER: return {Sx, 1, true};
+            case TRM_F_WATER_TABLE: return {Wt, 1, true};
+            case TRM_F_GROUND_TEMPERATURE: return {T ? T + (size_t)(nz - 1) * ld : nullptr, 1, false};
+            case TRM_F_TEND_INTERNAL_ENERGY: return {tU, nz, false};
+            case TRM_F_TEND_SATURATION: return {tS, nz, false};
+        }
+        if (id >= TRM_F_SKIN_TEMPERATURE && id <= TRM_F_SURFACE_RUNOFF) return {land2d[id - TRM_F_SKIN_TEMPERATURE], 1, true};
+        return {nullptr, 0, false};
+    }
+    int set_field(int id, const void* host, int64_t count) override {
+        FieldRef f = field(id);
+        if (!f.ptr && (id == TRM_F_PRESSURE_HEAD || (id >= TRM_F_SKIN_TEMPERATURE && id <= TRM_F_SURFACE_RUNOFF)))
+            return fail(TRM_ERR_INVALID, "field not defined for this model");
+        if (!f.ptr || !f.writable) return fail(TRM_ERR_INVALID, "set_field: unknown or read-only field");
+        if (count != (int64_t)f.nrows * nc) return fail(TRM_ERR_INVALID, f.nrows == 1 ? "set_field: count != ncol" : "set_field: count != nz*ncol");
+        CU(cudaSetDevice(device));
+        CU(cudaMemcpy2DAsync(f.ptr, ld * sizeof(NF), host, nc * sizeof(NF), nc * sizeof(NF), f.nrows, cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        aux_stale = true;
+        return TRM_OK;
+    }
+    int get_field(int id, void* host, int64_t count) override {
+        FieldRef f = field(id);
+        if (!f.ptr) return fail(TRM_ERR_INVALID, "get_field: unknown field or field not defined for this model");
+        if (count != (int64_t)f.nrows * nc) return fail(TRM_ERR_INVALID, "get_field: wrong element count");
+        CU(cudaSetDevice(device));
+        CU(cudaMemcpy2DAsync(host, nc * sizeof(NF), f.ptr, ld * sizeof(NF), nc * sizeof(NF), f.nrows, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return TRM_OK;
+    }
+    int field_ptr(int id, void** q, int64_t* ld_out, int32_t* nrows) override {
+        FieldRef f = field(id);
+        if (!f.ptr) return fail(TRM_ERR_INVALID, "field_ptr: unknown field or field not defined for this model");
+        if (q) *q = f.ptr;
+        if (ld_out) *ld_out = ld;
+        if (nrows) *nrows = f.nrows;
+        // the caller may write through the pointer: treat the closure fields as user data from now on
+        if (f.writable) aux_stale = true;
+        return TRM_OK;
+    }
+
+    // ------------------------------------------------------------------ inputs
+    int ensure(NF** q, size_t count) { if (*q) return TRM_OK; return dalloc(q, count); }
+    int set_input_const(int id, double v) override { in[id].kind = TRM_SRC_CONST; in[id].cval = v; return TRM_OK; }
+    int set_input_field(int id, const void* v) override {
+        CU(cudaSetDevice(device));
+        if (int rc = ensure(&in[id].a, ld)) return rc;
+        CU(cudaMemcpyAsync(in[id].a, v, nc * sizeof(NF), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        in[id].kind = TRM_SRC_FIELD;
+        return TRM_OK;
+    }
+    int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) override {
+        CU(cudaSetDevice(device));
+        Input& s = in[id];
+        if (s.kind == TRM_SRC_TABLE && s.a) { dfree(s.a); s.a = nullptr; }
+        if (int rc = ensure(&s.a, ld)) return rc;
+        if (int rc = ensure(&s.b, ld)) return rc;
+        if (int rc = ensure(&s.c, ld)) return rc;
+        CU(cudaMemcpyAsync(s.a, mean, nc * sizeof(NF), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(s.b, amp, nc * sizeof(NF), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(s.c, phase, nc * sizeof(NF), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        s.kind = TRM_SRC_SINUSOID; s.period = period; s.lo = lo; s.hi = hi;
+        return TRM_OK;
+    }
+    int set_input_table(int id, int nt, const double* times, const void* values) override {
+        CU(cudaSetDevice(device));
+        Input& s = in[id];
+        if (s.a) { dfree(s.a); s.a = nullptr; }
+        if (s.times) { dfree(s.times); s.times = nullptr; }
+        if (int rc = dalloc(&s.a, (size_t)nt * ld)) return rc;
+        if (int rc = dalloc(&s.times, (size_t)nt)) return rc;
+        CU(cudaMemcpy2DAsync(s.a, ld * sizeof(NF), values, nc * sizeof(NF), nc * sizeof(NF), nt, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(s.times, times, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        s.kind = TRM_SRC_TABLE; s.nt = nt;
+        return TRM_OK;
+    }
+    int input_ptr(int id, void** q) override {
+        CU(cudaSetDevice(device));
+        if (in[id].kind == TRM_SRC_TABLE) return fail(TRM_ERR_STATE, "input_ptr: input is a time series table");
+        if (int rc = ensure(&in[id].a, ld)) return rc;
+        if (in[id].kind == TRM_SRC_CONST) {   // materialise the constant so that the borrowed vector is meaningful
+            std::vector<NF> v((size_t)nc, (NF)in[id].cval);
+            CU(cudaMemcpyAsync(in[id].a, v.data(), nc * sizeof(NF), cudaMemcpyHostToDevice, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
+        if (in[id].kind != TRM_SRC_SINUSOID) in[id].kind = TRM_SRC_FIELD;
+        *q = in[id].a;
+        return TRM_OK;
+    }
+
+    // ------------------------------------------------------------------ launches
+    void base_args(StageArgs<NF>& a) {
+        std::memset(&a, 0, sizeof(a));
+        a.ncol = nc; a.ld = ld; a.nz = nz;
+        a.metrics = metrics; a.p = p;
+        for (int s = 0; s < TRM_BC_NSLOTS; ++s) a.bc[s] = cfg.bc[s];
+        for (int i = 0; i < TRM_IN_COUNT; ++i) {
+            InputDesc<NF>& d = a.in[i]; const Input& s = in[i];
+            d.kind = s.kind; d.nt = s.nt; d.cval = (NF)s.cval; d.period = s.period; d.lo = s.lo; d.hi = s.hi;
+            d.a = s.a; d.b = s.b; d.c = s.c; d.times = s.times; d.ld = ld;
+        }
+        a.Kf = Kf;
+        a.Ts = land2d[0]; a.G = land2d[1]; a.SWup = land2d[2]; a.LWup = land2d[3]; a.Rnet = land2d[4];
+        a.Hs = land2d[5]; a.Hl = land2d[6]; a.Egnd = land2d[7]; a.infil = land2d[8]; a.runoff = land2d[9];
+    }
+    void x_state(StageArgs<NF>& a) { a.xU = U; a.xS = S; a.xT = T; a.xL = Lq; a.xP = P; a.xWt = Wt; a.bU = U; a.bS = S; a.bSx = Sx; }
+    void y_state(StageArgs<NF>& a) { a.yU = U; a.yS = S; a.yT = T; a.yL = Lq; a.yP = P; a.yWt = Wt; a.ySx = Sx; }
+    int launch(int variant, const StageArgs<NF>& a);
+
+    int check_bcs() {
+        for (int s = 0; s < TRM_BC_NSLOTS; ++s) {
+            int k = cfg.bc[s].kind;
+            if (k < TRM_BC_DEFAULT || k > TRM_BC_FLUX) return fail(TRM_ERR_INVALID, "bad boundary condition kind");
+            if (k != TRM_BC_DEFAULT && (cfg.bc[s].input < 0 || cfg.bc[s].input >= TRM_IN_COUNT)) return fail(TRM_ERR_INVALID, "bad boundary condition input id");
+        }
+        return TRM_OK;
+    }
+
+    int initialize() override;
+    int step(double dt, int64_t n) override;
+    int aux() override;
+    int tendencies() override;
+    int diagnostics(trm_diag* out, double** dev) override;
+    int set_block(int b) override { if (b < 32 || b > 256 || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 256]"); block = b; return TRM_OK; }
+};
+
+template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
+    cudaError_t e = ks->stage_f32(phys, variant, a, block, stream); ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("stage kernel launch: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+template <> int Handle<double>::launch(int variant, const StageArgs<double>& a) {
+    cudaError_t e = ks->stage_f64(phys, variant, a, block, stream); ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("stage kernel launch: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+
+template <class NF> cudaError_t call_init(const KernelSet* ks, Handle<NF>* h);
+template <> cudaError_t call_init<float>(const KernelSet* ks, Handle<float>* h) {
+    return ks->init_f32(h->nc, h->ld, h->nz, h->richards, h->metrics, h->p, h->U, h->S, h->T, h->Lq, h->P, h->Wt, h->Sx, h->stream);
+}
+template <> cudaError_t call_init<double>(const KernelSet* ks, Handle<double>* h) {
+    return ks->init_f64(h->nc, h->ld, h->nz, h->richards, h->metrics, h->p, h->U, h->S, h->T, h->Lq, h->P, h->Wt, h->Sx, h->stream);
+}
+
+// initialize!(integrator) tail (model_integrator.jl:96-109 -> soil_model.jl:31-37 / land_model.jl:68-77)
+template <class NF> int Handle<NF>::initialize() {
+    CU(cudaSetDevice(device));
+    if (int rc = check_bcs()) return rc;
+    time = 0.0; iteration = 0;   // reset!(clock)
+    cudaError_t e = call_init<NF>(ks, this); ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("init kernel launch: ") + cudaGetErrorString(e));
+    // compute_hydraulics! of initialize! (soil_hydrology.jl:113-117, soil_hydrology_rre.jl:33-47) runs before
+    // the liquid fraction exists (the field is still zero there); it is recomputed by the first
+    // update_state!, so the hydraulic conductivity field is materialised by trm_compute_auxiliary only.
+    CU(cudaStreamSynchronize(stream));
+    initialized = true; aux_stale = true;
+    return TRM_OK;
+}
+
+template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
+    if (!initialized) return fail(TRM_ERR_STATE, "trm_step before trm_initialize");
+    if (n < 0) return fail(TRM_ERR_INVALID, "nsteps < 0");
+    CU(cudaSetDevice(device));
+    const NF dt = (NF)dt_;
+    CU(cudaEventRecord(ev0, stream));
+    for (int64_t i = 0; i < n; ++i) {
+        StageArgs<NF> a; base_args(a);
+        const NF t = (NF)time;
+        const NF t1 = t + dt;   // tick!(clock, dt) in the clock's number format
+        a.dt = dt;
+        if (!heun) {   // forward_euler.jl:19-31
+            a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
+            if (int rc = launch(aux_stale ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a)) return rc;
+        } else {       // heun.jl:37-71
+            a.mode = MODE_HEUN1; a.load_aux = aux_stale ? 1 : 0; a.t_x = t; a.t_b = t; x_state(a);
+            a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
+            if (int rc = launch(VAR_GENERIC, a)) return rc;
+            StageArgs<NF> b; base_args(b);
+            b.dt = dt; b.mode = MODE_HEUN2; b.load_aux = 0; b.t_x = t1; b.t_b = t;
+            b.xU = gU; b.xS = richards ? gS : S; b.xWt = gWt; b.bU = U; b.bS = S; b.bSx = Sx; b.k1U = tU; b.k1S = tS;
+            y_state(b);
+            if (int rc = launch(VAR_GENERIC, b)) return rc;
+        }
+        aux_stale = false;
+        time = (double)t1; iteration += 1;
+    }
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaEventSynchronize(ev1));
+    CU(cudaEventElapsedTime(&last_ms, ev0, ev1));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("trm_step: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+
+// compute_auxiliary!(state, model): soil_coupled.jl:62-72 / land_model.jl:79-88
+template <class NF> int Handle<NF>::aux() {
+    if (!initialized) return fail(TRM_ERR_STATE, "trm_compute_auxiliary before trm_initialize");
+    CU(cudaSetDevice(device));
+    StageArgs<NF> a; base_args(a);
+    a.mode = MODE_AUX; a.load_aux = 1; a.t_x = (NF)time; a.t_b = a.t_x; a.dt = 0; x_state(a);
+    if (int rc = launch(VAR_GENERIC, a)) return rc;
+    CU(cudaStreamSynchronize(stream));
+    return TRM_OK;
+}
+
+// update_state!(...) with the tendencies (incl. Flux BCs) materialised
+template <class NF> int Handle<NF>::tendencies() {
+    if (!initialized) return fail(TRM_ERR_STATE, "trm_compute_tendencies before trm_initialize");
+    CU(cudaSetDevice(device));
+    const size_t n3 = (size_t)nz * ld;
+    if (!tU) { if (int rc = dalloc(&tU, n3)) return rc; }
+    if (richards && !tS) { if (int rc = dalloc(&tS, n3)) return rc; }
+    StageArgs<NF> a; base_args(a);
+    a.mode = MODE_TEND; a.load_aux = 1; a.t_x = (NF)time; a.t_b = a.t_x; a.dt = 0; x_state(a);
+    a.oTU = tU; a.oTS = tS;
+    if (int rc = launch(VAR_GENERIC, a)) return rc;
+    CU(cudaStreamSynchronize(stream));
+    return TRM_OK;
+}
+
+template <class NF> int Handle<NF>::diagnostics(trm_diag* out, double** dev) {
+    CU(cudaSetDevice(device));
+    diag_kernel<NF><<<diag_blocks, 256, 0, stream>>>(nc, ld, nz, metrics, p.por, U, T, S, richards ? Sx : nullptr, diag_partial);
+    finish_diag<<<1, 32, 0, stream>>>(diag_blocks, diag_partial, (double)nc, diag_out);
+    launches += 2;
+    CU(cudaGetLastError());
+    if (dev) *dev = diag_out;
+    if (out) {
+        double v[8];
+        CU(cudaMemcpyAsync(v, diag_out, sizeof(v), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        out->energy = v[0]; out->water = v[1]; out->t_min = v[2]; out->t_max = v[3];
+        out->sat_min = v[4]; out->sat_max = v[5]; out->nan_count = v[6]; out->ncol = v[7];
+    }
+    return TRM_OK;
+}
+
+HandleBase* H(trm_handle* h) { return reinterpret_cast<HandleBase*>(h); }
+bool bad_input(int id) { return id < 0 || id >= TRM_IN_COUNT; }
+
+}  // namespace
+
+extern "C" {
+
+void trm_default_params(trm_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->mineral_porosity = 0.49; p->organic_porosity = 0.9; p->rho_soc = 0.0; p->rho_org = 1300.0;
+    const double k[5] = {0.57, 2.2, 0.025, 3.8, 0.25};
+    const double c[5] = {4.2e6, 1.9e6, 0.00125e6, 2.0e6, 2.5e6};
+    for (int i = 0; i < 5; ++i) { p->kappa[i] = k[i]; p->heatcap[i] = c[i]; }
+    p->rho_w = 1000.0; p->Lsl = 3.34e5; p->Llg = 2.257e6; p->rho_a = 1.293; p->c_a = 1005.7; p->Tref = 273.15;
+    p->sigma = 5.6704e-8; p->eps_mw = 0.622;
+    p->K_sat = 1.0e-5; p->vg_alpha = 1.0; p->vg_n = 2.0; p->bc_psis = 0.01; p->bc_lambda = 0.2; p->theta_res = 0.0;
+    p->impedance = 7.0; p->vwc_forcing = 0.0;
+    p->albedo = 0.3; p->emissivity = 0.97; p->kappa_skin = 2.0; p->C_h = 1.2e-3; p->min_windspeed = 0.01;
+    p->tau_r = 3600.0; p->evap_beta = 1.0;
+}
+
+void trm_default_config(trm_config* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->abi_version = TRM_ABI_VERSION; c->dtype = TRM_F64; c->model = TRM_MODEL_SOIL; c->timestepper = TRM_EULER;
+    c->hydrology = TRM_NOFLOW; c->swrc = TRM_SWRC_BROOKSCOREY; c->unsat_k = TRM_UNSATK_LINEAR; c->sat_halo = TRM_HALO_ZERO;
+    c->skin = TRM_SKIN_IMPLICIT; c->math = TRM_MATH_FAITHFUL;
+    trm_default_params(&c->params);
+}
+
+const char* trm_last_error(void) { return g_err.c_str(); }
+int trm_abi_version(void) { return TRM_ABI_VERSION; }
+
+int trm_create(const trm_config* cfg, trm_handle** out) {
+    if (!cfg || !out) return fail(TRM_ERR_INVALID, "null argument");
+    if (cfg->abi_version != TRM_ABI_VERSION) return fail(TRM_ERR_INVALID, "ABI version mismatch");
+    if (cfg->nz < 2 || cfg->nz > TRM_MAX_NZ || cfg->ncol < 1 || !cfg->z_faces) return fail(TRM_ERR_INVALID, "bad nz / ncol / z_faces");
+    for (int k = 0; k < cfg->nz; ++k) if (!(cfg->z_faces[k + 1] > cfg->z_faces[k])) return fail(TRM_ERR_INVALID, "z_faces must increase");
+    HandleBase* h = nullptr; int rc;
+    if (cfg->dtype == TRM_F32) { auto* q = new Handle<float>(); rc = q->setup(*cfg); h = q; }
+    else if (cfg->dtype == TRM_F64) { auto* q = new Handle<double>(); rc = q->setup(*cfg); h = q; }
+    else return fail(TRM_ERR_INVALID, "bad dtype");
+    if (rc != TRM_OK) { std::string keep = g_err; delete h; g_err = keep; return rc; }
+    *out = reinterpret_cast<trm_handle*>(h);
+    return TRM_OK;
+}
+int trm_destroy(trm_handle* h) { if (h) delete H(h); return TRM_OK; }
+int trm_sync(trm_handle* h) {
+    if (!h) return fail(TRM_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(H(h)->device)); CU(cudaStreamSynchronize(H(h)->stream)); return TRM_OK;
+}
+int trm_field_ptr(trm_handle* h, int id, void** p, int64_t* ld, int32_t* nrows) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->field_ptr(id, p, ld, nrows); }
+int trm_set_field(trm_handle* h, int id, const void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->set_field(id, host, count); }
+int trm_get_field(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field(id, host, count); }
+int trm_set_input_const(trm_handle* h, int id, double v) { if (!h || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_const(id, v); }
+int trm_set_input_field(trm_handle* h, int id, const void* v) { if (!h || !v || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_field(id, v); }
+int trm_set_input_sinusoid(trm_handle* h, int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) {
+    if (!h || !mean || !amp || !phase || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id");
+    return H(h)->set_input_sinusoid(id, mean, amp, phase, period, lo, hi);
+}
+int trm_set_input_table(trm_handle* h, int id, int32_t nt, const double* times, const void* values) {
+    if (!h || !times || !values || bad_input(id) || nt < 1) return fail(TRM_ERR_INVALID, "bad handle / input id / nt");
+    return H(h)->set_input_table(id, nt, times, values);
+}
+int trm_input_ptr(trm_handle* h, int id, void** p) { if (!h || !p || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->input_ptr(id, p); }
+int trm_initialize(trm_handle* h) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->initialize(); }
+int trm_step(trm_handle* h, double dt, int64_t n) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->step(dt, n); }
+int trm_compute_auxiliary(trm_handle* h) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->aux(); }
+int trm_compute_tendencies(trm_handle* h) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->tendencies(); }
+int trm_get_clock(trm_handle* h, double* t, int64_t* it) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); if (t) *t = H(h)->time; if (it) *it = H(h)->iteration; return TRM_OK; }
+int trm_set_clock(trm_handle* h, double t, int64_t it) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); H(h)->time = t; H(h)->iteration = it; return TRM_OK; }
+int trm_diagnostics(trm_handle* h, trm_diag* out) { if (!h || !out) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics(out, nullptr); }
+int trm_diagnostics_device(trm_handle* h, double** dev) { if (!h || !dev) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics(nullptr, dev); }
+int64_t trm_launch_count(trm_handle* h) { return h ? H(h)->launches : 0; }
+int trm_last_step_ms(trm_handle* h, float* ms) { if (!h || !ms) return fail(TRM_ERR_INVALID, "null argument"); *ms = H(h)->last_ms; return TRM_OK; }
+int trm_set_block_size(trm_handle* h, int block) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->set_block(block); }
+
+}  // extern "C"

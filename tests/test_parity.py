@@ -1,0 +1,174 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the BASELINE configurations.
+
+Tolerance (BASELINE.json north_star): Float64, max relative error 1e-9 on temperature, internal energy
+and saturation after 1000 steps, plus conservation of the column energy and water budgets.  Relative
+errors are measured against each field's scale (max |field|): temperature crosses zero (degC), where a
+pointwise relative error is meaningless.  Heat-only runs with a constant surface temperature involve no
+transcendental function and must be BIT-EXACT in the faithful math mode.
+"""
+import numpy as np
+import pytest
+
+from common import (make, max_scaled_err, richards_soil, synthetic_columns, synthetic_land_case,
+                    synthetic_soil_case, trm)
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("temperature", "internal_energy", "saturation_water_ice", "liquid_water_fraction")
+TOL = 1.0e-9
+
+
+def compare(gpu, cpu, fields, tol):
+    worst = {}
+    for name in fields:
+        a, b = getattr(gpu.state, name).numpy(), getattr(cpu.state, name).numpy()
+        assert np.all(np.isfinite(a)), name
+        worst[name] = max_scaled_err(a, b)
+    assert all(v <= tol for v in worst.values()), worst
+    return worst
+
+
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+@pytest.mark.parametrize("stepper", ["euler", "heun"])
+def test_soil_energy_richards_1000_steps(math, stepper):
+    """BASELINE config 3/5 at a size the oracle finishes in seconds."""
+    n = 1536 + 7   # ragged: not a multiple of the block size
+    gpu = synthetic_soil_case("cuda", n, heun=stepper == "heun", math=math)
+    cpu = synthetic_soil_case("oracle", n, heun=stepper == "heun")
+    d0 = gpu.diagnostics()
+    for _ in range(4):
+        gpu.step(60.0, 250)
+        cpu.step(60.0, 250)
+        compare(gpu, cpu, FIELDS + ("pressure_head", "surface_excess_water", "water_table"), TOL)
+    assert gpu.clock.time == cpu.clock.time == 60000.0
+    d1, dc = gpu.diagnostics(), cpu.diagnostics()
+    assert d1["nan_count"] == 0
+    # budgets: identical to the oracle's, and water is conserved (zero-flux boundaries)
+    assert d1["energy"] == pytest.approx(dc["energy"], rel=1e-9)
+    assert d1["water"] == pytest.approx(dc["water"], rel=1e-12)
+    assert d1["water"] == pytest.approx(d0["water"], rel=1e-10)
+
+
+@pytest.mark.parametrize("nf", [np.float64, np.float32])
+def test_heat_only_bit_exact(nf):
+    """NoFlow hydrology, constant per-column surface temperature: no transcendental function on the path,
+    so the faithful build must reproduce the oracle bit for bit (both number formats)."""
+    n = 700
+    lat, lon, T0 = synthetic_columns(n)
+
+    def build(engine):
+        grid = trm.ColumnGrid(trm.B200(), nf, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=30), n)
+        model = trm.SoilModel(grid)
+        bcs = trm.PrescribedSurfaceTemperature("T_ub", T0 + 10.0 * np.sin(-lon))
+        inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z, "saturation_water_ice": 1.0}
+        return make(engine, model, trm.ForwardEuler(dt=300.0), boundary_conditions=bcs, initializers=inits, math="faithful")
+
+    gpu, cpu = build("cuda"), build("oracle")
+    gpu.step(300.0, 1000)
+    cpu.step(300.0, 1000)
+    for name in ("internal_energy", "temperature", "liquid_water_fraction"):
+        a, b = getattr(gpu.state, name).numpy(), getattr(cpu.state, name).numpy()
+        assert np.array_equal(a, b), (name, float(np.max(np.abs(a - b))))
+
+
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+def test_heat_only_sinusoid_1000_steps(math):
+    """BASELINE config 2 (soil_heat_global): heat only with the sinusoidal surface temperature."""
+    gpu = synthetic_soil_case("cuda", 1000, richards=False, math=math)
+    cpu = synthetic_soil_case("oracle", 1000, richards=False)
+    e0 = gpu.diagnostics()["energy"]
+    gpu.step(300.0, 1000)
+    cpu.step(300.0, 1000)
+    compare(gpu, cpu, FIELDS[:2] + FIELDS[3:], TOL)
+    assert gpu.diagnostics()["energy"] == pytest.approx(cpu.diagnostics()["energy"], rel=1e-9)
+    assert np.isfinite(e0)
+
+
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+@pytest.mark.parametrize("stepper", ["euler", "heun"])
+def test_land_model_1000_steps(math, stepper):
+    """BASELINE config 4 (bare ground): surface energy balance + surface hydrology + soil."""
+    n = 600
+    gpu = synthetic_land_case("cuda", n, heun=stepper == "heun", math=math)
+    cpu = synthetic_land_case("oracle", n, heun=stepper == "heun")
+    gpu.step(60.0, 1000)
+    cpu.step(60.0, 1000)
+    compare(gpu, cpu, FIELDS + ("pressure_head", "skin_temperature", "ground_heat_flux", "latent_heat_flux",
+                                "sensible_heat_flux", "infiltration", "surface_runoff"), TOL)
+    gpu.compute_auxiliary()
+    cpu.compute_auxiliary()
+    compare(gpu, cpu, ("hydraulic_conductivity", "skin_temperature", "surface_net_radiation", "evaporation_ground"), TOL)
+
+
+def test_float32_soil_energy_richards():
+    """Float32 (the reference's default for global grids): rounding differences in powf/cbrtf are amplified
+    by the number format; tolerance is a few hundred ulps of the field scale after 200 steps."""
+    n = 512
+    gpu = synthetic_soil_case("cuda", n, nf=np.float32)
+    cpu = synthetic_soil_case("oracle", n, nf=np.float32)
+    gpu.step(60.0, 200)
+    cpu.step(60.0, 200)
+    compare(gpu, cpu, FIELDS, 2.0e-5)
+
+
+def test_negative_saturation_slow_path():
+    """A strong sink drives layers negative: exercises the downward sweep of adjust_saturation_profile!
+    (soil_hydrology.jl:201-216), which the kernel handles on its slow path."""
+    n = 96
+    rng = np.random.default_rng(7)
+
+    def build(engine):
+        grid = trm.ColumnGrid(trm.B200(), np.float64, trm.UniformSpacing(dz=0.1, N=20), n)
+        model = trm.SoilModel(grid, soil=richards_soil(vwc_forcing=-2.0e-4))
+        sat0 = rng.uniform(0.0, 0.05, (20, n))
+        sat0[:, ::3] = 0.9   # every third column stays on the fast path
+        return make(engine, model, trm.ForwardEuler(dt=60.0), initializers={"temperature": 5.0, "saturation_water_ice": sat0})
+
+    rng = np.random.default_rng(7); gpu = build("cuda")
+    rng = np.random.default_rng(7); cpu = build("oracle")
+    for _ in range(5):
+        gpu.step(60.0, 2)
+        cpu.step(60.0, 2)
+        compare(gpu, cpu, FIELDS + ("pressure_head", "water_table", "surface_excess_water"), 1e-12)
+    assert np.min(cpu.state.saturation_water_ice.numpy()) >= 0.0
+
+
+def test_over_saturation_to_surface_excess():
+    """A strong source fills the column: upward sweep and hand-over to surface_excess_water."""
+    n = 64
+
+    def build(engine):
+        grid = trm.ColumnGrid(trm.B200(), np.float64, trm.UniformSpacing(dz=0.1, N=12), n)
+        model = trm.SoilModel(grid, soil=richards_soil(vwc_forcing=+4.0e-4))
+        return make(engine, model, trm.ForwardEuler(dt=60.0), initializers={"temperature": 5.0, "saturation_water_ice": 0.97})
+
+    gpu, cpu = build("cuda"), build("oracle")
+    gpu.step(60.0, 10)
+    cpu.step(60.0, 10)
+    compare(gpu, cpu, FIELDS + ("pressure_head", "water_table", "surface_excess_water"), 1e-12)
+    assert np.all(cpu.state.surface_excess_water.numpy() > 0)
+
+
+def test_full_size_properties():
+    """BASELINE config 5 scale (reduced to 2 M columns to bound test time): properties that do not need the
+    oracle -- finite fields, water conservation, saturation bounds, and agreement of the first 4096 columns
+    with an oracle run of exactly those columns (columns are independent)."""
+    n, sub = 2_000_000, 4096
+    gpu = synthetic_soil_case("cuda", n, math="fast")
+    d0 = gpu.diagnostics()
+    gpu.step(60.0, 50)
+    d1 = gpu.diagnostics()
+    assert d1["nan_count"] == 0 and d1["ncol"] == n
+    assert d1["water"] == pytest.approx(d0["water"], rel=1e-10)
+    assert 0.0 <= d1["sat_min"] and d1["sat_max"] <= 1.0
+    lat, lon, T0 = synthetic_columns(n)
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=30), sub)
+    model = trm.SoilModel(grid, soil=richards_soil())
+    bcs = trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0[:sub], amp=10.0, phase=lon[:sub], period=86400.0))
+    inits = {"temperature": lambda x, z: T0[None, :sub] - 0.05 * z,
+             "saturation_water_ice": lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x}
+    cpu = make("oracle", model, trm.ForwardEuler(dt=60.0), boundary_conditions=bcs, initializers=inits)
+    cpu.step(60.0, 50)
+    for name in FIELDS:
+        a = getattr(gpu.state, name).numpy()[:, :sub]
+        assert max_scaled_err(a, getattr(cpu.state, name).numpy()) <= TOL, name
