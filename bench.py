@@ -253,8 +253,8 @@ def main():
 
         def e2e_step(t):
             np.sin(2 * np.pi * t / 86400.0 - lon, out=fnp)   # the host-side "atmosphere" produces this step's forcing
-            fnp *= 10.0
-            fnp += T0
+            np.multiply(fnp, 10.0, out=fnp)
+            np.add(fnp, T0, out=fnp)
             lib.check(lib.set_input_field(h, in_id, C.c_void_p(forc.data_ptr())), "set_input_field")
             lib.check(lib.step(h, DT, 1), "step")
             lib.check(lib.get_field(h, gt_id, C.c_void_p(out.data_ptr()), ncol_local), "get_field")

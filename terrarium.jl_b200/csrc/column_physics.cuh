@@ -24,7 +24,7 @@ struct DevParams {
     NF Ksat, vg_alpha, vg_n, bc_psis, bc_lambda, theta_res, Omega, vwcf;
     NF rho_a, c_a, Llg, Tref, sigma, eps_mw, albedo, emis, kappa_skin, C_h, Vmin, tau_r, beta;
     // derived constants used by FAST math only
-    NF rpor, neg_inv_alpha, vg_k_exp1, vg_k_exp2, vg_inv_m_neg, vg_inv_n;
+    NF rpor, neg_inv_alpha, vg_k_exp1, vg_k_exp2, vg_inv_m_neg, vg_inv_n, hc_solid, sqk_solid, r_thspan;
     int32_t swrc, unsat_k, sat_halo, skin;
     int32_t vg_n_is_2;
 };
@@ -58,6 +58,61 @@ __device__ __forceinline__ double texp10(double a) { return exp10(a); }
 __device__ __forceinline__ float  tabs(float a)   { return fabsf(a); }
 __device__ __forceinline__ double tabs(double a)  { return fabs(a); }
 
+
+// ---- math policy -------------------------------------------------------------------------------
+// Faithful: IEEE division / sqrt and Julia's NaN-propagating min / max.
+// Fast (FP64): reciprocal / rsqrt seeds (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) refined by two Newton
+// steps on the FP64 FMA pipe (error <= ~2 ulp, no IEEE fix-up branches), fmin / fmax.
+template <class NF, bool FAST>
+struct M {
+    __device__ static __forceinline__ NF div(NF a, NF b) { return a / b; }
+    __device__ static __forceinline__ NF rcp(NF a) { return 1 / a; }
+    __device__ static __forceinline__ NF sqrt_(NF a) { return tsqrt(a); }
+    __device__ static __forceinline__ NF mn(NF a, NF b) { return jmin(a, b); }
+    __device__ static __forceinline__ NF mx(NF a, NF b) { return jmax(a, b); }
+    __device__ static __forceinline__ NF pow23(NF x) { NF c = tcbrt(x); return c * c; }
+};
+template <>
+struct M<double, true> {
+    __device__ static __forceinline__ double rcp(double x) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+        double e = fma(-x, r, 1.0); r = fma(r, e, r);
+        e = fma(-x, r, 1.0); r = fma(r, e, r);
+        return r;
+    }
+    __device__ static __forceinline__ double div(double a, double b) { return a * rcp(b); }
+    __device__ static __forceinline__ double rsqrt_(double x) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        double hx = 0.5 * x;
+        double e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+        e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+        return y;
+    }
+    __device__ static __forceinline__ double sqrt_(double x) { return x == 0.0 ? 0.0 : x * rsqrt_(x); }
+    __device__ static __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    __device__ static __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+    // x^(2/3) for 0 < x <= 1: r ~ x^(-1/3) seeded in FP32 (otherwise idle pipe), two Newton steps
+    // r <- r + r (1 - x r^3) / 3 in FP64; x^(2/3) = x r.
+    __device__ static __forceinline__ double pow23(double x) {
+        if (x < 1.0e-30) { double c = cbrt(x); return c * c; }
+        double r = (double)rcbrtf((float)x);
+        double t = x * r * r; double e = fma(-t, r, 1.0); r = fma(r, e * (1.0 / 3.0), r);
+        t = x * r * r; e = fma(-t, r, 1.0); r = fma(r, e * (1.0 / 3.0), r);
+        return x * r;
+    }
+};
+template <>
+struct M<float, true> {
+    __device__ static __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    __device__ static __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    __device__ static __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    __device__ static __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    __device__ static __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+    __device__ static __forceinline__ float pow23(float x) { float c = cbrtf(x); return c * c; }
+};
+
 // volumetric fractions, src/processes/soil/stratigraphy/soil_volume.jl:52-67,103-107
 template <class NF>
 struct Fractions { NF water, ice, air, mineral, organic; };
@@ -82,6 +137,13 @@ __device__ __forceinline__ NF thermal_conductivity(const DevParams<NF>& p, NF sa
     NF s = p.sqk[0] * f.water + p.sqk[1] * f.ice + p.sqk[2] * f.air + p.sqk[3] * f.mineral + p.sqk[4] * f.organic;
     return s * s;
 }
+// same sum with the constant solid part folded (fast math only)
+template <class NF>
+__device__ __forceinline__ NF thermal_conductivity_fast(const DevParams<NF>& p, NF sat, NF liq) {
+    NF wi = sat * p.por, water = wi * liq;
+    NF s = p.sqk[0] * water + p.sqk[1] * (wi - water) + p.sqk[2] * (p.por - wi) + p.sqk_solid;
+    return s * s;
+}
 
 // volumetric heat capacity, soil_thermal_properties.jl:110-123
 template <class NF>
@@ -94,6 +156,19 @@ __device__ __forceinline__ NF heat_capacity(const DevParams<NF>& p, NF sat, NF l
 // soil_energy_closures.jl:99-159 ; safediv utils/utils.jl:25 ; Bool * x is a strong zero.
 template <class NF, bool FAST>
 __device__ __forceinline__ void energy_to_temperature(const DevParams<NF>& p, NF U, NF sat, NF& T, NF& liq) {
+    if (FAST) {
+        // same branches, one reciprocal: C from the constituent sums with the solid part precomputed
+        NF wi = sat * p.por;
+        NF Lt = p.L * wi;
+        NF num;
+        if (U >= 0) { liq = 1; num = U; }
+        else if (U >= -Lt) { NF y = -Lt; liq = (y == 0) ? -Lim<NF>::inf() : 1 - M<NF, FAST>::div(U, y + Lim<NF>::eps()); num = 0; }
+        else { liq = 0; num = U + Lt; }
+        NF water = wi * liq;
+        NF C = p.hc[0] * water + p.hc[1] * (wi - water) + p.hc[2] * (p.por - wi) + p.hc_solid;
+        T = M<NF, FAST>::div(num, C);
+        return;
+    }
     NF Lt = p.L * sat * p.por;
     if (U >= 0) {
         liq = 1;
@@ -128,18 +203,19 @@ __device__ __forceinline__ NF cell_conductivity(const DevParams<NF>& p, NF sat, 
         return p.Ksat * f.water / thsat;
     }
     NF n = p.vg_n;
-    NF x = f.water / p.por;
     if (FAST) {
-        NF I_ice = (liq == NF(1)) ? NF(1) : texp10(-p.Omega * (1 - liq));
+        // end members are exact in the reference formula too: x = 0 -> K = 0, x = 1 (saturated, thawed) -> K = K_sat
+        NF x = sat * liq;
+        if (x == NF(0)) return NF(0);
+        NF I_ice = NF(1);
+        if (liq != NF(1)) I_ice = texp10(-p.Omega * (1 - liq));
+        if (x == NF(1)) return p.Ksat * I_ice;
         NF a;
-        if (p.vg_n_is_2) {
-            NF c = tcbrt(x);                 // x^(2/3) = cbrt(x)^2
-            a = 1 - tsqrt(1 - c * c);        // (.)^(1/2)
-        } else {
-            a = 1 - tpow(1 - tpow(x, p.vg_k_exp1), p.vg_k_exp2);
-        }
-        return tabs(p.Ksat * I_ice * tsqrt(x) * (a * a));
+        if (p.vg_n_is_2) a = 1 - M<NF, FAST>::sqrt_(M<NF, FAST>::mx(1 - M<NF, FAST>::pow23(x), NF(0)));
+        else a = 1 - tpow(1 - tpow(x, p.vg_k_exp1), p.vg_k_exp2);
+        return tabs(p.Ksat * I_ice * M<NF, FAST>::sqrt_(x) * (a * a));
     }
+    NF x = f.water / p.por;
     NF I_ice = tpow(NF(10), -p.Omega * (1 - liq));
     NF inner = 1 - tpow(x, n / (n + 1));
     NF a = 1 - tpow(inner, (n - 1) / n);
@@ -152,9 +228,9 @@ template <class NF, bool FAST>
 __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF thsat) {
     if (p.swrc == TRM_SWRC_VANGENUCHTEN) {
         if (!(theta < thsat)) return NF(0);
-        NF se = (theta - p.theta_res) / (thsat - p.theta_res);
+        NF se = FAST ? (theta - p.theta_res) * p.r_thspan : (theta - p.theta_res) / (thsat - p.theta_res);
         if (FAST) {
-            if (p.vg_n_is_2) return p.neg_inv_alpha * tsqrt(1 / (se * se) - NF(1));   // m = 1/2
+            if (p.vg_n_is_2) return p.neg_inv_alpha * M<NF, FAST>::sqrt_(M<NF, FAST>::mx(M<NF, FAST>::rcp(se * se) - NF(1), NF(0)));   // m = 1/2
             return p.neg_inv_alpha * tpow(tpow(se, p.vg_inv_m_neg) - NF(1), p.vg_inv_n);
         }
         NF n = p.vg_n, m = 1 - 1 / n;
@@ -170,7 +246,7 @@ template <class NF, bool FAST>
 __device__ __forceinline__ NF pressure_head(const DevParams<NF>& p, NF sat, NF wt, NF zc, NF zref) {
     NF psim = swrc_inverse<NF, FAST>(p, sat * p.por, p.por);
     NF psiz = zc - zref;
-    NF psih = jmax(NF(0), wt - zc);
+    NF psih = M<NF, FAST>::mx(NF(0), wt - zc);
     return psih + psim + psiz;
 }
 

@@ -36,6 +36,13 @@ namespace trm {
 enum StageMode { MODE_EULER = 0, MODE_HEUN1 = 1, MODE_HEUN2 = 2, MODE_TEND = 3, MODE_AUX = 4 };
 enum Phys { PHYS_NOFLOW = 0, PHYS_RICHARDS = 1, PHYS_LAND = 2 };
 
+#ifndef TRM_MAX_BLOCK
+#define TRM_MAX_BLOCK 256   // largest block the stage kernel may be launched with
+#endif
+#ifndef TRM_MIN_BLOCKS
+#define TRM_MIN_BLOCKS 1    // resident blocks per SM the register allocator must allow
+#endif
+
 template <class NF>
 struct InputDesc {
     int32_t kind, nt;
@@ -137,10 +144,10 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
 }
 
 template <class NF, int PHYS, int MODE_CT, int LOAD_CT, bool FAST>
-__global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ StageArgs<NF> A) {
+__global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(const __grid_constant__ StageArgs<NF> A) {
     constexpr bool RICH = PHYS != PHYS_NOFLOW;
     constexpr bool LAND = PHYS == PHYS_LAND;
-    constexpr int PF = 4;   // layers of raw loads in flight per thread
+    using Mx = M<NF, FAST>;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NF* sm = reinterpret_cast<NF*>(smem_raw);
@@ -169,20 +176,19 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
     const NF zref = zF[nz + 1];
 
     // ---- boundary condition inputs at the times the reference evaluates them ----
-    NF bcv[TRM_BC_NSLOTS];
-#pragma unroll
-    for (int s = 0; s < TRM_BC_NSLOTS; ++s) {
-        bcv[s] = NF(0);
-        int kind = A.bc[s].kind;
-        if (kind != TRM_BC_DEFAULT) bcv[s] = eval_input(A.in[A.bc[s].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x);
-    }
+    auto bc_input = [&](int slot) -> NF {
+        const int kind = A.bc[slot].kind;
+        if (kind == TRM_BC_DEFAULT) return NF(0);
+        return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x);
+    };
+    const NF bc_T_top = bc_input(TRM_BC_TEMPERATURE_TOP);
     const NF wtx = RICH && !load_aux ? A.xWt[c] : NF(0);
 
     struct Raw { NF U, s, T, l, P; };
     auto load_raw = [&](int k) {
         Raw r; r.U = r.s = r.T = r.l = r.P = NF(0);
         if (k <= nz) {
-            int64_t o = (int64_t)(k - 1) * ld + c;
+            const int64_t o = (int64_t)(k - 1) * ld + c;
             r.U = A.xU[o]; r.s = A.xS[o];
             if (load_aux) { r.T = A.xT[o]; r.l = A.xL[o]; if (RICH) r.P = A.xP[o]; }
         }
@@ -197,35 +203,20 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
             energy_to_temperature<NF, FAST>(p, r.U, r.s, q.T, q.l);
             if (RICH) q.P = pressure_head<NF, FAST>(p, r.s, wtx, zC[k], zref);
         }
-        q.kap = thermal_conductivity(p, r.s, q.l);
+        q.kap = FAST ? thermal_conductivity_fast(p, r.s, q.l) : thermal_conductivity(p, r.s, q.l);
         if (need_K) q.Kc = cell_conductivity<NF, FAST>(p, r.s, q.l);
         return q;
     };
 
-    Raw r1 = load_raw(1), r2 = load_raw(2);
-    Raw ring[PF];
-#pragma unroll
-    for (int i = 0; i < PF; ++i) ring[i] = load_raw(3 + i);
+    // raw loads run PF = 4 layers ahead of the layer entering the window
+    Raw ring0 = load_raw(1), ring1 = load_raw(2), ring2 = load_raw(3), ring3 = load_raw(4);
 
-    // ---- prologue: cells 1, 2 and the bottom halo (cell 0) ----
-    Cell ca = make_cell(r1, 1);
-    Cell cb = make_cell(r2, 2);
-    Cell cc = cb;
-    NF T0 = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, ca.T, bcv[TRM_BC_TEMPERATURE_BOTTOM], dzf[1], false);
-    NF s0 = (RICH || p.sat_halo == TRM_HALO_COPY) ? ca.s : NF(0);
-    NF kap0 = thermal_conductivity(p, s0, ca.l);
-    NF qh_lo = -((ca.kap + kap0) / 2) * ((ca.T - T0) * rdzf[1]);          // diffusive_heat_flux, soil_energy.jl:134-149
-    NF Kf_m = NF(0);                                                      // Kf[j-1]; Kf[0] is never written
-    NF Kf_0 = ca.Kc;                                                      // Kf[j]   ; Kf[1] = Kc[1]
-    NF Kf_p = (2 >= nz) ? cb.Kc : jmin(cb.Kc, ca.Kc);                     // Kf[j+1] ; Kf[2]
-    NF qd_lo = NF(0);
-    if (RICH) {
-        NF P0 = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, ca.P, bcv[TRM_BC_PRESSURE_BOTTOM], dzf[1], false);
-        NF g = (ca.P - P0) * rdzf[1];
-        NF Kk = (g < 0 ? jmin(Kf_m, Kf_0) : NF(0)) + (g >= 0 ? jmin(Kf_0, Kf_p) : NF(0));   // darcy_flux, soil_hydrology_rre.jl:119-131
-        qd_lo = -Kk * g;
-    }
-    if (write_K) A.Kf[c] = Kf_0;
+    // sliding window over the layers: a = m-2, b = m-1, c = m (m = layer entering the window)
+    Cell ca, cb, cc;
+    ca.U = ca.s = ca.T = ca.l = ca.P = ca.kap = ca.Kc = NF(0);
+    cb = ca; cc = ca;
+    NF Kf_a = NF(0), Kf_b = NF(0);     // Kf[m-2], Kf[m-1] ; Kf[0] is never written by the reference (stays 0)
+    NF qh_lo = NF(0), qd_lo = NF(0);   // fluxes through the lower face of layer a
 
     NF carry = NF(0);          // over-saturation handed to the layer above (upward sweep of adjust_saturation_profile!)
     bool any_neg = false;      // a negative saturation needs the downward sweep -> slow path
@@ -233,40 +224,34 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
     NF wt_new = NF(0);
     NF Sx_new = NF(0);
     if (RICH && do_update) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
+    NF G_top = NF(0), infil_top = NF(0);   // LandModel: fluxes coupling the surface to the top soil layer
 
-    // LandModel: fluxes coupling the surface to the top soil layer
-    NF G_top = NF(0), infil_top = NF(0);
+#pragma unroll 1
+    for (int m = 1; m <= nz + 2; ++m) {
+        const Raw rin = ring0;
+        ring0 = ring1; ring1 = ring2; ring2 = ring3; ring3 = load_raw(m + 4);
+        // ---- layer m (or the top halo, m = nz + 1) enters the window ----
+        if (m <= nz) {
+            cc = make_cell(rin, m);
+        } else if (m == nz + 1) {   // halo above the surface, built from layer nz (slot b)
+            cc.T = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, cb.T, bc_T_top, dzf[nz + 1], true);
+            const NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? cb.s : NF(0);
+            cc.kap = FAST ? thermal_conductivity_fast(p, sh, cb.l) : thermal_conductivity(p, sh, cb.l);
+            if (RICH) cc.P = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, cb.P, bc_input(TRM_BC_PRESSURE_TOP), dzf[nz + 1], true);
+        }
+        // ---- face conductivity Kf[m], soil_hydrology.jl:249-276 ----
+        NF Kf_c = NF(0);
+        if (need_K) {
+            if (m == 1 || m == nz) Kf_c = cc.Kc;            // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
+            else if (m < nz) Kf_c = Mx::mn(cc.Kc, cb.Kc);
+            else if (m == nz + 1) Kf_c = Kf_b;              // Kf[Nz+1] = Kf[Nz] ; Kf[Nz+2] is a halo face (0)
+            if (write_K && m <= nz + 1) A.Kf[(int64_t)(m - 1) * ld + c] = Kf_c;
+        }
 
-    for (int jb = 1; jb <= nz; jb += PF) {
-#pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            const int j = jb + i;
-            if (j > nz) break;
-            // ---- cell j+2 (or the top halo) enters the window ----
-            Raw rc = ring[i];
-            ring[i] = load_raw(j + 2 + PF);
-            NF T_c = NF(0), kap_c = NF(0), P_c = NF(0);
-            if (j + 2 <= nz) {
-                cc = make_cell(rc, j + 2);
-            } else if (j + 2 == nz + 1) {   // top halo (cell nz + 1) built from cell nz, which is cb right now
-                T_c = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, cb.T, bcv[TRM_BC_TEMPERATURE_TOP], dzf[nz + 1], true);
-                NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? cb.s : NF(0);
-                kap_c = thermal_conductivity(p, sh, cb.l);
-                if (RICH) P_c = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, cb.P, bcv[TRM_BC_PRESSURE_TOP], dzf[nz + 1], true);
-            }
-            // ---- face conductivity Kf[j+2], soil_hydrology.jl:249-276 ----
-            NF Kf_pp = NF(0);
-            if (need_K) {
-                const int kf = j + 2;
-                if (kf < nz) Kf_pp = jmin(cc.Kc, cb.Kc);
-                else if (kf == nz) Kf_pp = cc.Kc;
-                else if (kf == nz + 1) Kf_pp = Kf_p;    // Kf[Nz+1] = Kf[Nz]
-                // kf == nz + 2: halo face, never written (0)
-            }
-            if (write_K) A.Kf[(int64_t)j * ld + c] = Kf_p;   // Kf[j+1] lives in row j (0-based)
-
-            // ---- LandModel surface processes, once the top cell is cell j ----
-            if (LAND && j == nz && mode != MODE_HEUN2) {
+        // ---- LandModel surface processes, once the top layer sits in slot a ----
+        if (LAND && m == nz + 2) {
+            if (mode == MODE_HEUN2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
+            else {
                 Surface<NF> a;
                 a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
                 a.LWd = eval_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
@@ -291,7 +276,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
                 NF dq = p.eps_mw * vpd / a.pres;
                 NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
                 // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall)
-                NF S = A.bSx[c], Kt = Kf_0, sat_top = ca.s;
+                NF S = A.bSx[c], Kt = Kf_a, sat_top = ca.s;
                 NF drain, inf;
                 if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
                 else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, Kt) : NF(0); }
@@ -311,27 +296,29 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
                 if (!prescribed) A.Ts[c] = Ts;
                 G_top = G; infil_top = inf;
             }
-            if (LAND && j == nz && mode == MODE_HEUN2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
+        }
 
-            if (mode != MODE_AUX) {
-                // ---- fluxes at face j+1 ----
-                // window: a = cell j, b = cell j+1 (for j == nz slot b holds the top halo, see the shift below)
-                NF qh_hi = -((cb.kap + ca.kap) / 2) * ((cb.T - ca.T) * rdzf[j + 1]);
-                NF qd_hi = NF(0);
-                if (RICH) {
-                    NF g = (cb.P - ca.P) * rdzf[j + 1];
-                    NF Kk = (g < 0 ? jmin(Kf_0, Kf_p) : NF(0)) + (g >= 0 ? jmin(Kf_p, Kf_pp) : NF(0));
-                    qd_hi = -Kk * g;
-                }
-                // ---- tendencies of cell j ----
+        if (m >= 2 && mode != MODE_AUX) {
+            // ---- fluxes through face m-1, between slot a (layer m-2; the bottom halo for m = 2) and slot b ----
+            const NF qh_hi = -((cb.kap + ca.kap) / 2) * ((cb.T - ca.T) * rdzf[m - 1]);   // diffusive_heat_flux, soil_energy.jl:134-149
+            NF qd_hi = NF(0);
+            if (RICH) {                                                                    // darcy_flux, soil_hydrology_rre.jl:119-131
+                const NF g = (cb.P - ca.P) * rdzf[m - 1];
+                NF Kk;
+                if (FAST) Kk = g < 0 ? Mx::mn(Kf_a, Kf_b) : Mx::mn(Kf_b, Kf_c);
+                else Kk = (g < 0 ? jmin(Kf_a, Kf_b) : NF(0)) + (g >= 0 ? jmin(Kf_b, Kf_c) : NF(0));
+                qd_hi = -Kk * g;
+            }
+            if (m >= 3) {
+                // ---- tendencies of layer j = m-2 (slot a) ----
+                const int j = m - 2;
+                const int64_t o = (int64_t)(j - 1) * ld + c;
                 NF tU = -((qh_hi - qh_lo) * rdzc[j]);                              // soil_energy.jl:112-131
                 NF tS = NF(0);
                 if (RICH) {
-                    NF dth = -((qd_hi - qd_lo) * rdzc[j]) + NF(0) + p.vwcf;          // soil_hydrology_rre.jl:95-117
+                    const NF dth = -((qd_hi - qd_lo) * rdzc[j]) + NF(0) + p.vwcf;    // soil_hydrology_rre.jl:95-117
                     tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
                 }
-                qh_lo = qh_hi; qd_lo = qd_hi;
-                const int64_t o = (int64_t)(j - 1) * ld + c;
                 if (mode == MODE_HEUN1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
                 if (mode == MODE_HEUN2) {                                           // average_tendencies! heun.jl:27-35
                     tU = (A.k1U[o] + tU) / 2;
@@ -341,46 +328,46 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
                 if (j == nz) {
                     if (LAND) { tU -= G_top / dzc[nz]; tS -= (-infil_top) / dzc[nz]; }           // land_model.jl:56-62
                     else {
-                        if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bcv[TRM_BC_ENERGY_TOP] / dzc[nz];
-                        if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bcv[TRM_BC_SATURATION_TOP] / dzc[nz];
+                        if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / dzc[nz];
+                        if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / dzc[nz];
                     }
                 }
                 if (j == 1) {
-                    if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bcv[TRM_BC_ENERGY_BOTTOM] / dzc[1];
-                    if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bcv[TRM_BC_SATURATION_BOTTOM] / dzc[1];
+                    if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / dzc[1];
+                    if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / dzc[1];
                 }
                 if (mode == MODE_TEND) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
 
                 if (do_update) {
                     // ---- explicit step, abstract_timestepper.jl:113-141 ----
-                    NF Ub = (mode == MODE_HEUN2) ? A.bU[o] : ca.U;
-                    NF Un = Ub + tU * dt;
+                    const NF Ub = (mode == MODE_HEUN2) ? A.bU[o] : ca.U;
+                    const NF Un = Ub + tU * dt;
                     NF sn = ca.s;
                     if (RICH) {
-                        NF sb = (mode == MODE_HEUN2) ? A.bS[o] : ca.s;
+                        const NF sb = (mode == MODE_HEUN2) ? A.bS[o] : ca.s;
                         sn = sb + tS * dt;
                         // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
                         sn = sn + carry;
                         if (j < nz) {
-                            NF e = jmax(sn - 1, NF(0));
+                            const NF e = Mx::mx(sn - 1, NF(0));
                             sn -= e;
-                            carry = e * dzc[j] / dzc[j + 1];
+                            carry = FAST ? e * dzc[j] * rdzc[j + 1] : e * dzc[j] / dzc[j + 1];
                         }
                         if (sn < 0) any_neg = true;
                     }
                     if (RICH && any_neg) {
-                        // raw values for the slow path below (downward sweep needs the whole profile)
+                        // raw values for the slow path below (the downward sweep needs the whole profile)
                         A.yU[o] = Un; A.yS[o] = sn;
                     } else {
                         if (RICH) {
-                            // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208)
-                            if (j >= 2) sn = sn + jmax(-sn, NF(0));
+                            // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
+                            if (!FAST && j >= 2) sn = sn + jmax(-sn, NF(0));
                             if (j == nz) {                                   // top excess -> surface_excess_water (:210-214)
-                                NF e = jmax(sn - 1, NF(0));
+                                const NF e = Mx::mx(sn - 1, NF(0));
                                 sn -= e;
                                 Sx_new += e * dzc[nz];
                             }
-                            if (j == 1) sn = jmax(sn, NF(0));                // :216
+                            if (!FAST && j == 1) sn = jmax(sn, NF(0));       // :216
                             A.yS[o] = sn;
                             if (idx == 0 && sn < 1) { idx = j; wt_new = zF[j]; }   // compute_water_table!, kernel_utils.jl:7-16
                         }
@@ -389,19 +376,21 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
                             NF Tn, ln;
                             energy_to_temperature<NF, FAST>(p, Un, sn, Tn, ln);
                             A.yT[o] = Tn; A.yL[o] = ln;
-                            // cells below the water table wait for it (written after the sweep)
+                            // layers below the water table wait for it (written after the sweep)
                             if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, zC[j], zref);
                         }
                     }
                 }
             }
-            // ---- shift the window ----
-            Kf_m = Kf_0; Kf_0 = Kf_p; Kf_p = Kf_pp;
-            if (j + 1 <= nz) {
-                ca = cb;
-                if (j + 2 <= nz) cb = cc;
-                else { cb.T = T_c; cb.kap = kap_c; cb.P = P_c; }   // top halo now sits in slot b (only T, kap, P are used)
-            }
+            qh_lo = qh_hi; qd_lo = qd_hi;
+        }
+        // ---- shift the window ----
+        ca = cb; cb = cc; Kf_a = Kf_b; Kf_b = Kf_c;
+        if (m == 1) {   // halo below the bottom layer (cell 0), built from layer 1 (now slot b)
+            ca.T = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, cb.T, bc_input(TRM_BC_TEMPERATURE_BOTTOM), dzf[1], false);
+            const NF s0 = (RICH || p.sat_halo == TRM_HALO_COPY) ? cb.s : NF(0);
+            ca.kap = FAST ? thermal_conductivity_fast(p, s0, cb.l) : thermal_conductivity(p, s0, cb.l);
+            if (RICH) ca.P = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, cb.P, bc_input(TRM_BC_PRESSURE_BOTTOM), dzf[1], false);
         }
     }
     if (mode == MODE_AUX || mode == MODE_TEND || !do_update) return;
@@ -413,10 +402,11 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
         if (A.ySx) A.ySx[c] = Sx_new;
         if (full_closure) {
             // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
-            NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
+            const NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
+#pragma unroll 1
             for (int k = 1; k < idx && k <= nz; ++k) {
-                NF z = zC[k];
-                A.yP[(int64_t)(k - 1) * ld + c] = jmax(NF(0), wt_new - z) + psat + (z - zref);
+                const NF z = zC[k];
+                A.yP[(int64_t)(k - 1) * ld + c] = Mx::mx(NF(0), wt_new - z) + psat + (z - zref);
             }
         }
         return;
@@ -425,17 +415,18 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
     //      profile this thread just stored, then water table and closures bottom -> top. ----
     {
         NF carry_dn = NF(0);
+#pragma unroll 1
         for (int k = nz; k >= 1; --k) {
             const int64_t o = (int64_t)(k - 1) * ld + c;
             NF s = A.yS[o];
             if (k < nz) s -= carry_dn;
             if (k >= 2) {
-                NF d = jmax(-s, NF(0));
+                const NF d = jmax(-s, NF(0));
                 s += d;
                 carry_dn = d * dzc[k] / dzc[k - 1];
             }
             if (k == nz) {
-                NF e = jmax(s - 1, NF(0));
+                const NF e = jmax(s - 1, NF(0));
                 s -= e;
                 Sx_new += e * dzc[nz];
             }
@@ -443,12 +434,14 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ Stag
             A.yS[o] = s;
         }
         idx = 0;
+#pragma unroll 1
         for (int k = 1; k <= nz; ++k) if (idx == 0 && A.yS[(int64_t)(k - 1) * ld + c] < 1) idx = k;
         if (idx == 0) idx = nz + 1;
         wt_new = zF[idx];
         A.yWt[c] = wt_new;
         if (A.ySx) A.ySx[c] = Sx_new;
         if (full_closure) {
+#pragma unroll 1
             for (int k = 1; k <= nz; ++k) {
                 const int64_t o = (int64_t)(k - 1) * ld + c;
                 NF s = A.yS[o], U = A.yU[o], Tn, ln;

@@ -7,6 +7,7 @@
 // fails with TRM_ERR_NO_DEVICE.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -74,6 +75,7 @@ struct Handle : HandleBase {
     Input in[TRM_IN_COUNT];
     bool initialized = false;
     bool aux_stale = true;   // stored T / liq / psi are not closure(U, sat): the next stage must read them
+    bool force_load = false; // tuning knob (env TRM_FORCE_LOAD_AUX=1): always read T / liq / psi instead of recomputing them
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* diag_partial = nullptr; double* diag_out = nullptr; int diag_blocks = 0;
 
@@ -103,6 +105,7 @@ struct Handle : HandleBase {
         cfg = c; nz = c.nz; nc = c.ncol; device = c.device;
         land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
         fast = c.math == TRM_MATH_FAST;
+        { const char* e = std::getenv("TRM_FORCE_LOAD_AUX"); force_load = e && e[0] == '1'; }
         if (land && !richards) return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
         phys = land ? PHYS_LAND : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
         ks = fast ? &kernels_fast() : &kernels_faithful();
@@ -146,6 +149,9 @@ struct Handle : HandleBase {
         p.rpor = 1 / p.por; p.neg_inv_alpha = -1 / p.vg_alpha;
         p.vg_k_exp1 = p.vg_n / (p.vg_n + 1); p.vg_k_exp2 = (p.vg_n - 1) / p.vg_n;
         { NF mm = 1 - 1 / p.vg_n; p.vg_inv_m_neg = -1 / mm; p.vg_inv_n = 1 / p.vg_n; }
+        { NF solid = 1 - p.por, organic = solid * p.org, mineral = solid * (1 - p.org);
+          p.hc_solid = p.hc[3] * mineral + p.hc[4] * organic; p.sqk_solid = p.sqk[3] * mineral + p.sqk[4] * organic; }
+        p.r_thspan = 1 / (p.por - p.theta_res);
         p.swrc = c.swrc; p.unsat_k = c.unsat_k; p.sat_halo = c.sat_halo; p.skin = c.skin;
         p.vg_n_is_2 = (p.vg_n == NF(2)) ? 1 : 0;
 
@@ -308,7 +314,7 @@ struct Handle : HandleBase {
     int aux() override;
     int tendencies() override;
     int diagnostics(trm_diag* out, double** dev) override;
-    int set_block(int b) override { if (b < 32 || b > 256 || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 256]"); block = b; return TRM_OK; }
+    int set_block(int b) override { if (b < 32 || b > TRM_MAX_BLOCK || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, TRM_MAX_BLOCK]"); block = b; return TRM_OK; }
 };
 
 template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
@@ -358,7 +364,7 @@ template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
         a.dt = dt;
         if (!heun) {   // forward_euler.jl:19-31
             a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
-            if (int rc = launch(aux_stale ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a)) return rc;
+            if (int rc = launch((aux_stale || force_load) ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a)) return rc;
         } else {       // heun.jl:37-71
             a.mode = MODE_HEUN1; a.load_aux = aux_stale ? 1 : 0; a.t_x = t; a.t_b = t; x_state(a);
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;

@@ -63,7 +63,7 @@ def synthetic_soil_case(engine, ncol, nf=np.float64, richards=True, heun=False, 
     return make(engine, model, ts, boundary_conditions=bcs, initializers=inits, math=math)
 
 
-def synthetic_land_case(engine, ncol, nf=np.float64, heun=False, nz=30, math="faithful", dt=60.0):
+def synthetic_land_case(engine, ncol, nf=np.float64, heun=False, nz=30, math="faithful", dt=60.0, windspeed=3.0):
     """BASELINE config 4 (bare ground): LandModel with the synthetic atmosphere of BASELINE.md section 5."""
     lat, lon, T0 = synthetic_columns(ncol)
     grid = trm.ColumnGrid(trm.B200(), nf, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=nz), ncol)
@@ -78,7 +78,7 @@ def synthetic_land_case(engine, ncol, nf=np.float64, heun=False, nz=30, math="fa
         "surface_longwave_down": 300.0,
         "specific_humidity": 0.005,
         "air_pressure": 101325.0,
-        "windspeed": 3.0,
+        "windspeed": windspeed,
         "rainfall": trm.TimeSeries(hours * 3600.0, np.repeat(rain[:, None], ncol, axis=1)),
     }
     inits = {

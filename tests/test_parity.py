@@ -84,20 +84,41 @@ def test_heat_only_sinusoid_1000_steps(math):
     assert np.isfinite(e0)
 
 
+LAND_FIELDS = FIELDS + ("pressure_head", "skin_temperature", "ground_heat_flux", "latent_heat_flux", "sensible_heat_flux",
+                        "infiltration", "surface_runoff", "surface_excess_water")
+
+
 @pytest.mark.parametrize("math", ["faithful", "fast"])
 @pytest.mark.parametrize("stepper", ["euler", "heun"])
 def test_land_model_1000_steps(math, stepper):
-    """BASELINE config 4 (bare ground): surface energy balance + surface hydrology + soil."""
+    """BASELINE config 4 (bare ground): surface energy balance + surface hydrology + soil.
+
+    Wind speed 0.5 m/s: with the 3 m/s of BASELINE.md the as-coded sign convention of the ground heat flux
+    (G = Rnet - Hs - Hl used as an upward Flux BC) makes the explicit skin/soil coupling
+    diverge after ~100 steps of 60 s on the 5 cm top layer -- in the oracle exactly as on the GPU (see the
+    60-step test below)."""
     n = 600
-    gpu = synthetic_land_case("cuda", n, heun=stepper == "heun", math=math)
-    cpu = synthetic_land_case("oracle", n, heun=stepper == "heun")
-    gpu.step(60.0, 1000)
-    cpu.step(60.0, 1000)
-    compare(gpu, cpu, FIELDS + ("pressure_head", "skin_temperature", "ground_heat_flux", "latent_heat_flux",
-                                "sensible_heat_flux", "infiltration", "surface_runoff"), TOL)
+    gpu = synthetic_land_case("cuda", n, heun=stepper == "heun", math=math, windspeed=0.5)
+    cpu = synthetic_land_case("oracle", n, heun=stepper == "heun", windspeed=0.5)
+    for _ in range(4):
+        gpu.step(60.0, 250)
+        cpu.step(60.0, 250)
+        compare(gpu, cpu, LAND_FIELDS, TOL)
     gpu.compute_auxiliary()
     cpu.compute_auxiliary()
-    compare(gpu, cpu, ("hydraulic_conductivity", "skin_temperature", "surface_net_radiation", "evaporation_ground"), TOL)
+    compare(gpu, cpu, ("hydraulic_conductivity", "skin_temperature", "surface_net_radiation", "evaporation_ground",
+                       "surface_shortwave_up", "surface_longwave_up"), TOL)
+
+
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+def test_land_model_baseline_forcing_60_steps(math):
+    """The BASELINE.md synthetic atmosphere (V = 3 m/s) for the first simulated hour."""
+    n = 600
+    gpu = synthetic_land_case("cuda", n, math=math)
+    cpu = synthetic_land_case("oracle", n)
+    gpu.step(60.0, 60)
+    cpu.step(60.0, 60)
+    compare(gpu, cpu, LAND_FIELDS, TOL)
 
 
 def test_float32_soil_energy_richards():
