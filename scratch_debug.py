@@ -1,30 +1,21 @@
-import sys, os
+import sys
 sys.path.insert(0, 'tests'); sys.path.insert(0, 'oracle')
 import numpy as np
-from common import synthetic_land_case
-for math in ("faithful", "fast"):
-    gpu = synthetic_land_case("cuda", 600, math=math)
-    cpu = synthetic_land_case("oracle", 600)
-    for step in range(1000):
-        prev = {n: getattr(gpu.state, n).numpy() for n in ("temperature", "internal_energy", "saturation_water_ice", "pressure_head", "liquid_water_fraction", "surface_excess_water", "skin_temperature", "ground_heat_flux", "infiltration")}
-        gpu.step(60.0, 1); cpu.step(60.0, 1)
-        bad = None
-        for n in ("temperature", "internal_energy", "saturation_water_ice", "pressure_head", "skin_temperature", "ground_heat_flux"):
-            a = getattr(gpu.state, n).numpy()
-            if not np.all(np.isfinite(a)):
-                idx = np.argwhere(~np.isfinite(a))
-                print(math, "step", step, "field", n, "first bad idx", idx[:5].tolist(), "count", len(idx))
-                bad = idx[0]
-                break
-        if bad is not None:
-            c = bad[-1]
-            np.set_printoptions(precision=17, linewidth=200)
-            for n, v in prev.items():
-                print("prev", n, v[..., c] if v.ndim > 1 else v[c])
-            for n in prev:
-                a = getattr(gpu.state, n).numpy(); b = getattr(cpu.state, n).numpy()
-                print("now gpu", n, a[..., c] if a.ndim > 1 else a[c])
-                print("now cpu", n, b[..., c] if b.ndim > 1 else b[c])
-            break
-    else:
-        print(math, "no NaN in 1000 steps")
+from common import *
+n = 96
+def build(engine, math):
+    rng = np.random.default_rng(7)
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.UniformSpacing(dz=0.1, N=20), n)
+    model = trm.SoilModel(grid, soil=richards_soil(vwc_forcing=-2.0e-4))
+    sat0 = rng.uniform(0.0, 0.05, (20, n)); sat0[:, ::3] = 0.9
+    return make(engine, model, trm.ForwardEuler(dt=60.0), initializers={"temperature": 5.0, "saturation_water_ice": sat0}, math=math)
+np.set_printoptions(linewidth=220, precision=8)
+cpu = build("oracle", "faithful"); gpu = build("cuda", "faithful")
+print("init sat", gpu.state.saturation_water_ice.numpy()[:, 2])
+print("init psi gpu", gpu.state.pressure_head.numpy()[:, 2])
+print("init psi cpu", cpu.state.pressure_head.numpy()[:, 2])
+cpu.step(60.0, 1); gpu.step(60.0, 1)
+for nme in ("saturation_water_ice", "pressure_head", "temperature"):
+    print(nme, "gpu", getattr(gpu.state, nme).numpy()[:, 2])
+    print(nme, "cpu", getattr(cpu.state, nme).numpy()[:, 2])
+print("wt", gpu.state.water_table.numpy()[2], cpu.state.water_table.numpy()[2])

@@ -230,7 +230,11 @@ __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF 
         if (!(theta < thsat)) return NF(0);
         NF se = FAST ? (theta - p.theta_res) * p.r_thspan : (theta - p.theta_res) / (thsat - p.theta_res);
         if (FAST) {
-            if (p.vg_n_is_2) return p.neg_inv_alpha * M<NF, FAST>::sqrt_(M<NF, FAST>::mx(M<NF, FAST>::rcp(se * se) - NF(1), NF(0)));   // m = 1/2
+            if (p.vg_n_is_2) {   // m = 1/2: psi_m = -(1/alpha) sqrt(se^-2 - 1) ; se = 0 (dry layer) is -Inf as in the reference
+                const NF t = se * se;
+                if (t == NF(0)) return -Lim<NF>::inf();
+                return p.neg_inv_alpha * M<NF, FAST>::sqrt_(M<NF, FAST>::mx(M<NF, FAST>::rcp(t) - NF(1), NF(0)));
+            }
             return p.neg_inv_alpha * tpow(tpow(se, p.vg_inv_m_neg) - NF(1), p.vg_inv_n);
         }
         NF n = p.vg_n, m = 1 - 1 / n;

@@ -48,6 +48,7 @@ struct HandleBase {
     int device = 0;
     cudaStream_t stream = nullptr;
     double time = 0.0;   // holds an NF value
+    double t_inputs = 0.0;   // clock time of the last update_inputs! (state_variables.jl:154-162)
     int64_t iteration = 0;
     int64_t launches = 0;
     float last_ms = 0.f;
@@ -340,7 +341,7 @@ template <> cudaError_t call_init<double>(const KernelSet* ks, Handle<double>* h
 template <class NF> int Handle<NF>::initialize() {
     CU(cudaSetDevice(device));
     if (int rc = check_bcs()) return rc;
-    time = 0.0; iteration = 0;   // reset!(clock)
+    time = 0.0; iteration = 0; t_inputs = 0.0;   // reset!(clock); update_inputs! at t0
     cudaError_t e = call_init<NF>(ks, this); ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("init kernel launch: ") + cudaGetErrorString(e));
     // compute_hydraulics! of initialize! (soil_hydrology.jl:113-117, soil_hydrology_rre.jl:33-47) runs before
@@ -376,6 +377,7 @@ template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
             if (int rc = launch(VAR_GENERIC, b)) return rc;
         }
         aux_stale = false;
+        t_inputs = (double)t;   // the state's inputs were last updated at the start of this step
         time = (double)t1; iteration += 1;
     }
     CU(cudaEventRecord(ev1, stream));
@@ -391,7 +393,9 @@ template <class NF> int Handle<NF>::aux() {
     if (!initialized) return fail(TRM_ERR_STATE, "trm_compute_auxiliary before trm_initialize");
     CU(cudaSetDevice(device));
     StageArgs<NF> a; base_args(a);
-    a.mode = MODE_AUX; a.load_aux = 1; a.t_x = (NF)time; a.t_b = a.t_x; a.dt = 0; x_state(a);
+    // compute_auxiliary! does not call update_inputs!: the input fields still hold the values of the last
+    // update_state! (start of the last step), which is what timestep!(...; finalize = true) / run! see.
+    a.mode = MODE_AUX; a.load_aux = 1; a.t_x = (NF)t_inputs; a.t_b = a.t_x; a.dt = 0; x_state(a);
     if (int rc = launch(VAR_GENERIC, a)) return rc;
     CU(cudaStreamSynchronize(stream));
     return TRM_OK;
@@ -406,6 +410,7 @@ template <class NF> int Handle<NF>::tendencies() {
     if (richards && !tS) { if (int rc = dalloc(&tS, n3)) return rc; }
     StageArgs<NF> a; base_args(a);
     a.mode = MODE_TEND; a.load_aux = 1; a.t_x = (NF)time; a.t_b = a.t_x; a.dt = 0; x_state(a);
+    t_inputs = time;
     a.oTU = tU; a.oTS = tS;
     if (int rc = launch(VAR_GENERIC, a)) return rc;
     CU(cudaStreamSynchronize(stream));
