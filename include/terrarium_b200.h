@@ -287,7 +287,8 @@ int64_t trm_launch_count(trm_handle* h);
  * handle's stream (the events bracket exactly the fused stage kernels of that call). */
 int trm_last_step_ms(trm_handle* h, float* ms);
 
-/* Tuning knob: threads per block of the stage kernel (multiple of 32 in [32, 128], default 128). */
+/* Tuning knob: threads per block of the stage kernels (multiple of 32 in [32, 256]; default 256 for the
+ * shared-memory tile kernel, capped at 128 for the streaming kernel). */
 int trm_set_block_size(trm_handle* h, int block);
 
 #ifdef __cplusplus

@@ -91,8 +91,9 @@ struct M<double, true> {
         return y;
     }
     __device__ static __forceinline__ double sqrt_(double x) { return x == 0.0 ? 0.0 : x * rsqrt_(x); }
-    __device__ static __forceinline__ double mn(double a, double b) { return fmin(a, b); }
-    __device__ static __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+    // compare + select (NaN in `a` falls through to `b`; fast math makes no promise about NaN states)
+    __device__ static __forceinline__ double mn(double a, double b) { return a < b ? a : b; }
+    __device__ static __forceinline__ double mx(double a, double b) { return a > b ? a : b; }
     // x^(2/3) for 0 < x <= 1: r ~ x^(-1/3) seeded in FP32 (otherwise idle pipe), two Newton steps
     // r <- r + r (1 - x r^3) / 3 in FP64; x^(2/3) = x r.
     __device__ static __forceinline__ double pow23(double x) {
@@ -157,15 +158,16 @@ __device__ __forceinline__ NF heat_capacity(const DevParams<NF>& p, NF sat, NF l
 template <class NF, bool FAST>
 __device__ __forceinline__ void energy_to_temperature(const DevParams<NF>& p, NF U, NF sat, NF& T, NF& liq) {
     if (FAST) {
-        // same branches, one reciprocal: C from the constituent sums with the solid part precomputed
-        NF wi = sat * p.por;
-        NF Lt = p.L * wi;
-        NF num;
-        if (U >= 0) { liq = 1; num = U; }
-        else if (U >= -Lt) { NF y = -Lt; liq = (y == 0) ? -Lim<NF>::inf() : 1 - M<NF, FAST>::div(U, y + Lim<NF>::eps()); num = 0; }
-        else { liq = 0; num = U + Lt; }
-        NF water = wi * liq;
-        NF C = p.hc[0] * water + p.hc[1] * (wi - water) + p.hc[2] * (p.por - wi) + p.hc_solid;
+        // same three regimes with selects; only the (rare) phase change zone branches. C from the
+        // constituent sums with the solid part precomputed, one reciprocal.
+        const NF wi = sat * p.por;
+        const NF Lt = p.L * wi;
+        const bool thawed = U >= 0, frozen = U < -Lt;
+        const NF num = thawed ? U : (frozen ? U + Lt : NF(0));
+        liq = thawed ? NF(1) : NF(0);
+        if (!thawed && !frozen) liq = 1 - M<NF, FAST>::div(U, Lim<NF>::eps() - Lt);
+        const NF water = wi * liq;
+        const NF C = p.hc[0] * water + p.hc[1] * (wi - water) + p.hc[2] * (p.por - wi) + p.hc_solid;
         T = M<NF, FAST>::div(num, C);
         return;
     }

@@ -1,6 +1,7 @@
 // kernels.inl -- instantiates the stage kernels for one math mode.  Included by kernels_faithful.cu
 // (TRM_FAST = 0, built with -fmad=false) and kernels_fast.cu (TRM_FAST = 1).
 #include "kernel_set.h"
+#include "tile_kernel.cuh"
 
 namespace trm {
 namespace {
@@ -18,6 +19,34 @@ cudaError_t launch_phys(int variant, const StageArgs<NF>& a, int block, cudaStre
         default:                  stage_kernel<NF, PHYS, -1, -1, kFast><<<grid, blk, smem, st>>>(a); break;
     }
     return cudaGetLastError();
+}
+
+// ForwardEuler stage as a shared-memory tile kernel (tile_kernel.cuh); returns cudaErrorInvalidConfiguration
+// when the column does not fit into shared memory (the caller falls back to the streaming kernel).
+template <class NF, int PHYS, int LOAD>
+cudaError_t launch_tile_variant(const StageArgs<NF>& a, int threads, cudaStream_t st) {
+    const size_t smem = sizeof(NF) * tile_smem_elems(a.nz);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel<NF, PHYS, LOAD, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int64_t nblk = (a.ncol + TILE_COLS - 1) / TILE_COLS;
+    tile_kernel<NF, PHYS, LOAD, kFast><<<(unsigned)nblk, threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <class NF>
+cudaError_t launch_tile(int phys, int load_aux, const StageArgs<NF>& a, int threads, cudaStream_t st) {
+    if (sizeof(NF) * tile_smem_elems(a.nz) > 220 * 1024) return cudaErrorInvalidConfiguration;
+    switch (phys * 2 + (load_aux ? 1 : 0)) {
+        case 0: return launch_tile_variant<NF, PHYS_NOFLOW, 0>(a, threads, st);
+        case 1: return launch_tile_variant<NF, PHYS_NOFLOW, 1>(a, threads, st);
+        case 2: return launch_tile_variant<NF, PHYS_RICHARDS, 0>(a, threads, st);
+        case 3: return launch_tile_variant<NF, PHYS_RICHARDS, 1>(a, threads, st);
+        case 4: return launch_tile_variant<NF, PHYS_LAND, 0>(a, threads, st);
+        default: return launch_tile_variant<NF, PHYS_LAND, 1>(a, threads, st);
+    }
 }
 
 template <class NF>
@@ -44,7 +73,8 @@ const KernelSet& kernels_fast() {
 #else
 const KernelSet& kernels_faithful() {
 #endif
-    static const KernelSet ks = {&launch_stage<float>, &launch_stage<double>, &launch_init<float>, &launch_init<double>};
+    static const KernelSet ks = {&launch_stage<float>, &launch_stage<double>, &launch_init<float>, &launch_init<double>,
+                                 &launch_tile<float>, &launch_tile<double>};
     return ks;
 }
 

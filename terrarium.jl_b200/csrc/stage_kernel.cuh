@@ -143,6 +143,22 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
     G = rnet - hs - hl;
 }
 
+// Values produced while layer m enters the pipeline and consumed one or two iterations later.  Two
+// instances alternate roles (the main loop is unrolled by two), so nothing is ever shifted between
+// registers: "cur" is overwritten by iteration m, "prv" was written by iteration m-1, and the old
+// content of "cur" is what iteration m-2 left behind.
+template <class NF>
+struct Stage {
+    NF U, s;           // prognostic values of layer m (consumed when the layer is updated, at m+2)
+    NF T, l, P;        // closure fields of layer m
+    NF kap, Kc;        // thermal / hydraulic conductivity at the centre of layer m
+    NF Kf;             // hydraulic conductivity at face m
+    NF qh, g;          // heat flux and pressure-head gradient at face m (between layers m-1 and m)
+    NF dqh;            // qh[m] - qh[m-1]   : heat flux divergence numerator of layer m-1
+    NF qd;             // Darcy flux at face m-1
+    NF rU, rS, rT, rL, rP;   // raw loads of layer m+2 (software prefetch, two iterations ahead)
+};
+
 template <class NF, int PHYS, int MODE_CT, int LOAD_CT, bool FAST>
 __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(const __grid_constant__ StageArgs<NF> A) {
     constexpr bool RICH = PHYS != PHYS_NOFLOW;
@@ -184,39 +200,25 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     const NF bc_T_top = bc_input(TRM_BC_TEMPERATURE_TOP);
     const NF wtx = RICH && !load_aux ? A.xWt[c] : NF(0);
 
-    struct Raw { NF U, s, T, l, P; };
-    auto load_raw = [&](int k) {
-        Raw r; r.U = r.s = r.T = r.l = r.P = NF(0);
+    // running element offsets: `oin` addresses the layer being prefetched, `oout` the layer being updated
+    int64_t oin = c;
+    auto prefetch = [&](Stage<NF>& st, int k) {
         if (k <= nz) {
-            const int64_t o = (int64_t)(k - 1) * ld + c;
-            r.U = A.xU[o]; r.s = A.xS[o];
-            if (load_aux) { r.T = A.xT[o]; r.l = A.xL[o]; if (RICH) r.P = A.xP[o]; }
+            st.rU = A.xU[oin]; st.rS = A.xS[oin];
+            if (load_aux) { st.rT = A.xT[oin]; st.rL = A.xL[oin]; if (RICH) st.rP = A.xP[oin]; }
+            oin += ld;
         }
-        return r;
-    };
-    // cell properties of the state at time n: T, liq, psi (closure fields), kappa, Kc
-    struct Cell { NF U, s, T, l, P, kap, Kc; };
-    auto make_cell = [&](const Raw& r, int k) {
-        Cell q; q.U = r.U; q.s = r.s; q.P = NF(0); q.Kc = NF(0);
-        if (load_aux) { q.T = r.T; q.l = r.l; q.P = r.P; }
-        else {
-            energy_to_temperature<NF, FAST>(p, r.U, r.s, q.T, q.l);
-            if (RICH) q.P = pressure_head<NF, FAST>(p, r.s, wtx, zC[k], zref);
-        }
-        q.kap = FAST ? thermal_conductivity_fast(p, r.s, q.l) : thermal_conductivity(p, r.s, q.l);
-        if (need_K) q.Kc = cell_conductivity<NF, FAST>(p, r.s, q.l);
-        return q;
     };
 
-    // raw loads run PF = 4 layers ahead of the layer entering the window
-    Raw ring0 = load_raw(1), ring1 = load_raw(2), ring2 = load_raw(3), ring3 = load_raw(4);
-
-    // sliding window over the layers: a = m-2, b = m-1, c = m (m = layer entering the window)
-    Cell ca, cb, cc;
-    ca.U = ca.s = ca.T = ca.l = ca.P = ca.kap = ca.Kc = NF(0);
-    cb = ca; cc = ca;
-    NF Kf_a = NF(0), Kf_b = NF(0);     // Kf[m-2], Kf[m-1] ; Kf[0] is never written by the reference (stays 0)
-    NF qh_lo = NF(0), qd_lo = NF(0);   // fluxes through the lower face of layer a
+    Stage<NF> s0, s1;
+    {
+        Stage<NF> z;
+        z.U = z.s = z.T = z.l = z.P = z.kap = z.Kc = z.Kf = z.qh = z.g = z.dqh = z.qd = NF(0);
+        z.rU = z.rS = z.rT = z.rL = z.rP = NF(0);
+        s0 = z; s1 = z;
+    }
+    prefetch(s1, 1);   // iteration m reads the raw values parked in slot (m & 1)
+    prefetch(s0, 2);
 
     NF carry = NF(0);          // over-saturation handed to the layer above (upward sweep of adjust_saturation_profile!)
     bool any_neg = false;      // a negative saturation needs the downward sweep -> slow path
@@ -225,30 +227,65 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     NF Sx_new = NF(0);
     if (RICH && do_update) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
     NF G_top = NF(0), infil_top = NF(0);   // LandModel: fluxes coupling the surface to the top soil layer
+    int64_t oout = c;                      // element offset of layer m-2
 
-#pragma unroll 1
-    for (int m = 1; m <= nz + 2; ++m) {
-        const Raw rin = ring0;
-        ring0 = ring1; ring1 = ring2; ring2 = ring3; ring3 = load_raw(m + 4);
-        // ---- layer m (or the top halo, m = nz + 1) enters the window ----
+    // One pipeline iteration: layer m (or the halo above the surface for m = nz+1) enters, the fluxes
+    // through face m (heat) and face m-1 (Darcy, needs Kf[m]) are formed, layer m-2 is updated and closed.
+    auto iterate = [&](const int m, Stage<NF>& cur, const Stage<NF>& prv) {
+        // ---- old content of `cur`: iteration m-2 ----
+        const NF U2 = cur.U, s2 = cur.s, T2 = cur.T, Kf2 = cur.Kf;
+        // ---- layer m ----
+        NF Tn = NF(0), ln = NF(0), Pn = NF(0), kapn = NF(0), Kcn = NF(0);
+        const NF Ur = cur.rU, sr = cur.rS;
         if (m <= nz) {
-            cc = make_cell(rin, m);
-        } else if (m == nz + 1) {   // halo above the surface, built from layer nz (slot b)
-            cc.T = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, cb.T, bc_T_top, dzf[nz + 1], true);
-            const NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? cb.s : NF(0);
-            cc.kap = FAST ? thermal_conductivity_fast(p, sh, cb.l) : thermal_conductivity(p, sh, cb.l);
-            if (RICH) cc.P = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, cb.P, bc_input(TRM_BC_PRESSURE_TOP), dzf[nz + 1], true);
+            if (load_aux) { Tn = cur.rT; ln = cur.rL; Pn = cur.rP; }
+            else {
+                energy_to_temperature<NF, FAST>(p, Ur, sr, Tn, ln);
+                if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, zC[m], zref);
+            }
+            kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
+            if (need_K) Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
+        } else if (m == nz + 1) {   // halo above the surface, built from layer nz (prv)
+            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, prv.T, bc_T_top, dzf[nz + 1], true);
+            const NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? prv.s : NF(0);
+            kapn = FAST ? thermal_conductivity_fast(p, sh, prv.l) : thermal_conductivity(p, sh, prv.l);
+            if (RICH) Pn = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, prv.P, bc_input(TRM_BC_PRESSURE_TOP), dzf[nz + 1], true);
+        }
+        prefetch(cur, m + 2);
+        // ---- lower neighbour of layer m: layer m-1, or the halo below the bottom layer for m = 1 ----
+        NF Tp = prv.T, kapp = prv.kap, Pp = prv.P;
+        if (m == 1) {
+            Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, Tn, bc_input(TRM_BC_TEMPERATURE_BOTTOM), dzf[1], false);
+            const NF sb0 = (RICH || p.sat_halo == TRM_HALO_COPY) ? sr : NF(0);
+            kapp = FAST ? thermal_conductivity_fast(p, sb0, ln) : thermal_conductivity(p, sb0, ln);
+            if (RICH) Pp = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, Pn, bc_input(TRM_BC_PRESSURE_BOTTOM), dzf[1], false);
         }
         // ---- face conductivity Kf[m], soil_hydrology.jl:249-276 ----
-        NF Kf_c = NF(0);
+        NF Kfn = NF(0);
         if (need_K) {
-            if (m == 1 || m == nz) Kf_c = cc.Kc;            // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
-            else if (m < nz) Kf_c = Mx::mn(cc.Kc, cb.Kc);
-            else if (m == nz + 1) Kf_c = Kf_b;              // Kf[Nz+1] = Kf[Nz] ; Kf[Nz+2] is a halo face (0)
-            if (write_K && m <= nz + 1) A.Kf[(int64_t)(m - 1) * ld + c] = Kf_c;
+            if (m == 1 || m == nz) Kfn = Kcn;                   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
+            else if (m < nz) Kfn = Mx::mn(Kcn, prv.Kc);
+            else if (m == nz + 1) Kfn = prv.Kf;                 // Kf[Nz+1] = Kf[Nz] ; Kf[Nz+2] is a halo face (0)
+            if (write_K && m <= nz + 1) A.Kf[(int64_t)(m - 1) * ld + c] = Kfn;
+        }
+        // ---- heat flux and head gradient at face m (diffusive_heat_flux, soil_energy.jl:134-149) ----
+        NF qhn = NF(0), gn = NF(0);
+        if (m <= nz + 1) {
+            qhn = -((kapn + kapp) / 2) * ((Tn - Tp) * rdzf[m]);
+            if (RICH) gn = (Pn - Pp) * rdzf[m];
+        }
+        const NF dqhn = qhn - prv.qh;
+        // ---- Darcy flux at face m-1 (darcy_flux, soil_hydrology_rre.jl:119-131) ----
+        NF qdn = NF(0);
+        if (RICH && m >= 2) {
+            const NF g = prv.g;
+            NF Kk;
+            if (FAST) Kk = Mx::mn(prv.Kf, g < 0 ? Kf2 : Kfn);
+            else Kk = (g < 0 ? jmin(Kf2, prv.Kf) : NF(0)) + (g >= 0 ? jmin(prv.Kf, Kfn) : NF(0));
+            qdn = -Kk * g;
         }
 
-        // ---- LandModel surface processes, once the top layer sits in slot a ----
+        // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         if (LAND && m == nz + 2) {
             if (mode == MODE_HEUN2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
             else {
@@ -276,7 +313,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                 NF dq = p.eps_mw * vpd / a.pres;
                 NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
                 // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall)
-                NF S = A.bSx[c], Kt = Kf_a, sat_top = ca.s;
+                NF S = A.bSx[c], Kt = Kf2, sat_top = s2;
                 NF drain, inf;
                 if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
                 else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, Kt) : NF(0); }
@@ -287,7 +324,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                 for (int rep = 0; rep < 2; ++rep) {
                     seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
                     if (!prescribed) {
-                        Ts = ca.T - G * dzc[nz] / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
+                        Ts = T2 - G * dzc[nz] / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
                         seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
                     }
                 }
@@ -298,100 +335,89 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             }
         }
 
-        if (m >= 2 && mode != MODE_AUX) {
-            // ---- fluxes through face m-1, between slot a (layer m-2; the bottom halo for m = 2) and slot b ----
-            const NF qh_hi = -((cb.kap + ca.kap) / 2) * ((cb.T - ca.T) * rdzf[m - 1]);   // diffusive_heat_flux, soil_energy.jl:134-149
-            NF qd_hi = NF(0);
-            if (RICH) {                                                                    // darcy_flux, soil_hydrology_rre.jl:119-131
-                const NF g = (cb.P - ca.P) * rdzf[m - 1];
-                NF Kk;
-                if (FAST) Kk = g < 0 ? Mx::mn(Kf_a, Kf_b) : Mx::mn(Kf_b, Kf_c);
-                else Kk = (g < 0 ? jmin(Kf_a, Kf_b) : NF(0)) + (g >= 0 ? jmin(Kf_b, Kf_c) : NF(0));
-                qd_hi = -Kk * g;
+        if (m >= 3 && mode != MODE_AUX) {
+            // ---- tendencies of layer j = m-2 ----
+            const int j = m - 2;
+            const int64_t o = oout;
+            oout += ld;
+            NF tU = -(prv.dqh * rdzc[j]);                                      // soil_energy.jl:112-131
+            NF tS = NF(0);
+            if (RICH) {
+                const NF dth = -((qdn - prv.qd) * rdzc[j]) + NF(0) + p.vwcf;     // soil_hydrology_rre.jl:95-117
+                tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
             }
-            if (m >= 3) {
-                // ---- tendencies of layer j = m-2 (slot a) ----
-                const int j = m - 2;
-                const int64_t o = (int64_t)(j - 1) * ld + c;
-                NF tU = -((qh_hi - qh_lo) * rdzc[j]);                              // soil_energy.jl:112-131
-                NF tS = NF(0);
-                if (RICH) {
-                    const NF dth = -((qd_hi - qd_lo) * rdzc[j]) + NF(0) + p.vwcf;    // soil_hydrology_rre.jl:95-117
-                    tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
+            if (mode == MODE_HEUN1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
+            if (mode == MODE_HEUN2) {                                           // average_tendencies! heun.jl:27-35
+                tU = (A.k1U[o] + tU) / 2;
+                if (RICH) tS = (A.k1S[o] + tS) / 2;
+            }
+            // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
+            if (j == nz) {
+                if (LAND) { tU -= G_top / dzc[nz]; tS -= (-infil_top) / dzc[nz]; }           // land_model.jl:56-62
+                else {
+                    if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / dzc[nz];
+                    if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / dzc[nz];
                 }
-                if (mode == MODE_HEUN1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
-                if (mode == MODE_HEUN2) {                                           // average_tendencies! heun.jl:27-35
-                    tU = (A.k1U[o] + tU) / 2;
-                    if (RICH) tS = (A.k1S[o] + tS) / 2;
-                }
-                // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
-                if (j == nz) {
-                    if (LAND) { tU -= G_top / dzc[nz]; tS -= (-infil_top) / dzc[nz]; }           // land_model.jl:56-62
-                    else {
-                        if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / dzc[nz];
-                        if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / dzc[nz];
-                    }
-                }
-                if (j == 1) {
-                    if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / dzc[1];
-                    if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / dzc[1];
-                }
-                if (mode == MODE_TEND) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
+            }
+            if (j == 1) {
+                if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / dzc[1];
+                if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / dzc[1];
+            }
+            if (mode == MODE_TEND) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
 
-                if (do_update) {
-                    // ---- explicit step, abstract_timestepper.jl:113-141 ----
-                    const NF Ub = (mode == MODE_HEUN2) ? A.bU[o] : ca.U;
-                    const NF Un = Ub + tU * dt;
-                    NF sn = ca.s;
+            if (do_update) {
+                // ---- explicit step, abstract_timestepper.jl:113-141 ----
+                const NF Ub = (mode == MODE_HEUN2) ? A.bU[o] : U2;
+                const NF Un = Ub + tU * dt;
+                NF sn = s2;
+                if (RICH) {
+                    const NF sb = (mode == MODE_HEUN2) ? A.bS[o] : s2;
+                    sn = sb + tS * dt;
+                    // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
+                    sn = sn + carry;
+                    if (j < nz) {
+                        const NF e = Mx::mx(sn - 1, NF(0));
+                        sn -= e;
+                        carry = FAST ? e * dzc[j] * rdzc[j + 1] : e * dzc[j] / dzc[j + 1];
+                    }
+                    if (sn < 0) any_neg = true;
+                }
+                if (RICH && any_neg) {
+                    // raw values for the slow path below (the downward sweep needs the whole profile)
+                    A.yU[o] = Un; A.yS[o] = sn;
+                } else {
                     if (RICH) {
-                        const NF sb = (mode == MODE_HEUN2) ? A.bS[o] : ca.s;
-                        sn = sb + tS * dt;
-                        // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
-                        sn = sn + carry;
-                        if (j < nz) {
+                        // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
+                        if (!FAST && j >= 2) sn = sn + jmax(-sn, NF(0));
+                        if (j == nz) {                                   // top excess -> surface_excess_water (:210-214)
                             const NF e = Mx::mx(sn - 1, NF(0));
                             sn -= e;
-                            carry = FAST ? e * dzc[j] * rdzc[j + 1] : e * dzc[j] / dzc[j + 1];
+                            Sx_new += e * dzc[nz];
                         }
-                        if (sn < 0) any_neg = true;
+                        if (!FAST && j == 1) sn = jmax(sn, NF(0));       // :216
+                        A.yS[o] = sn;
+                        if (idx == 0 && sn < 1) { idx = j; wt_new = zF[j]; }   // compute_water_table!, kernel_utils.jl:7-16
                     }
-                    if (RICH && any_neg) {
-                        // raw values for the slow path below (the downward sweep needs the whole profile)
-                        A.yU[o] = Un; A.yS[o] = sn;
-                    } else {
-                        if (RICH) {
-                            // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
-                            if (!FAST && j >= 2) sn = sn + jmax(-sn, NF(0));
-                            if (j == nz) {                                   // top excess -> surface_excess_water (:210-214)
-                                const NF e = Mx::mx(sn - 1, NF(0));
-                                sn -= e;
-                                Sx_new += e * dzc[nz];
-                            }
-                            if (!FAST && j == 1) sn = jmax(sn, NF(0));       // :216
-                            A.yS[o] = sn;
-                            if (idx == 0 && sn < 1) { idx = j; wt_new = zF[j]; }   // compute_water_table!, kernel_utils.jl:7-16
-                        }
-                        A.yU[o] = Un;
-                        if (full_closure) {
-                            NF Tn, ln;
-                            energy_to_temperature<NF, FAST>(p, Un, sn, Tn, ln);
-                            A.yT[o] = Tn; A.yL[o] = ln;
-                            // layers below the water table wait for it (written after the sweep)
-                            if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, zC[j], zref);
-                        }
+                    A.yU[o] = Un;
+                    if (full_closure) {
+                        NF Tc, lc;
+                        energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
+                        A.yT[o] = Tc; A.yL[o] = lc;
+                        // layers below the water table wait for it (written after the sweep)
+                        if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, zC[j], zref);
                     }
                 }
             }
-            qh_lo = qh_hi; qd_lo = qd_hi;
         }
-        // ---- shift the window ----
-        ca = cb; cb = cc; Kf_a = Kf_b; Kf_b = Kf_c;
-        if (m == 1) {   // halo below the bottom layer (cell 0), built from layer 1 (now slot b)
-            ca.T = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, cb.T, bc_input(TRM_BC_TEMPERATURE_BOTTOM), dzf[1], false);
-            const NF s0 = (RICH || p.sat_halo == TRM_HALO_COPY) ? cb.s : NF(0);
-            ca.kap = FAST ? thermal_conductivity_fast(p, s0, cb.l) : thermal_conductivity(p, s0, cb.l);
-            if (RICH) ca.P = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, cb.P, bc_input(TRM_BC_PRESSURE_BOTTOM), dzf[1], false);
-        }
+        // ---- what later iterations need from this one ----
+        cur.U = Ur; cur.s = sr; cur.T = Tn; cur.l = ln; cur.P = Pn; cur.kap = kapn; cur.Kc = Kcn;
+        cur.Kf = Kfn; cur.qh = qhn; cur.g = gn; cur.dqh = dqhn; cur.qd = qdn;
+    };
+
+#pragma unroll 1
+    for (int m = 1; m <= nz + 2; m += 2) {
+        iterate(m, s1, s0);
+        if (m + 1 <= nz + 2) iterate(m + 1, s0, s1);
     }
     if (mode == MODE_AUX || mode == MODE_TEND || !do_update) return;
     if (!RICH) return;
@@ -403,10 +429,11 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
         if (full_closure) {
             // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
             const NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
+            int64_t o = c;
 #pragma unroll 1
-            for (int k = 1; k < idx && k <= nz; ++k) {
+            for (int k = 1; k < idx && k <= nz; ++k, o += ld) {
                 const NF z = zC[k];
-                A.yP[(int64_t)(k - 1) * ld + c] = Mx::mx(NF(0), wt_new - z) + psat + (z - zref);
+                A.yP[o] = Mx::mx(NF(0), wt_new - z) + psat + (z - zref);
             }
         }
         return;
@@ -444,9 +471,9 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
 #pragma unroll 1
             for (int k = 1; k <= nz; ++k) {
                 const int64_t o = (int64_t)(k - 1) * ld + c;
-                NF s = A.yS[o], U = A.yU[o], Tn, ln;
-                energy_to_temperature<NF, FAST>(p, U, s, Tn, ln);
-                A.yT[o] = Tn; A.yL[o] = ln;
+                NF s = A.yS[o], U = A.yU[o], Tc, lc;
+                energy_to_temperature<NF, FAST>(p, U, s, Tc, lc);
+                A.yT[o] = Tc; A.yL[o] = lc;
                 A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, zC[k], zref);
             }
         }

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernel_set.h"
+#include "tile_kernel.cuh"   // TILE_COLS / TRM_TILE_THREADS (no kernel is instantiated in this file)
 
 namespace {
 
@@ -60,7 +61,9 @@ struct Handle : HandleBase {
     int nz = 0; int64_t nc = 0, ld = 0;
     bool land = false, richards = false, heun = false, fast = false;
     int phys = PHYS_NOFLOW;
-    int block = 128;
+    int block = 128;          // threads per block of the streaming stage kernel
+    int tile_threads = 256;   // threads per block of the tile kernel (warps = layers in flight per tile)
+    bool use_tile = true;     // ForwardEuler stages run the shared-memory tile kernel (env TRM_KERNEL=stream disables)
     const KernelSet* ks = nullptr;
     DevParams<NF> p{};
     std::vector<void*> allocs;
@@ -107,6 +110,7 @@ struct Handle : HandleBase {
         land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
         fast = c.math == TRM_MATH_FAST;
         { const char* e = std::getenv("TRM_FORCE_LOAD_AUX"); force_load = e && e[0] == '1'; }
+        { const char* e = std::getenv("TRM_KERNEL"); use_tile = !(e && std::string(e) == "stream"); }
         if (land && !richards) return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
         phys = land ? PHYS_LAND : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
         ks = fast ? &kernels_fast() : &kernels_faithful();
@@ -315,7 +319,12 @@ struct Handle : HandleBase {
     int aux() override;
     int tendencies() override;
     int diagnostics(trm_diag* out, double** dev) override;
-    int set_block(int b) override { if (b < 32 || b > TRM_MAX_BLOCK || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, TRM_MAX_BLOCK]"); block = b; return TRM_OK; }
+    int set_block(int b) override {
+        if (b < 32 || b > TRM_TILE_THREADS || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 256]");
+        tile_threads = b; block = b < TRM_MAX_BLOCK ? b : TRM_MAX_BLOCK;
+        return TRM_OK;
+    }
+    int launch_tile(const StageArgs<NF>& a, int load_aux);
 };
 
 template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
@@ -326,6 +335,22 @@ template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
 template <> int Handle<double>::launch(int variant, const StageArgs<double>& a) {
     cudaError_t e = ks->stage_f64(phys, variant, a, block, stream); ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("stage kernel launch: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+
+// returns TRM_OK, an error, or -1 when the tile kernel cannot hold a column of this depth in shared memory
+template <> int Handle<float>::launch_tile(const StageArgs<float>& a, int load_aux) {
+    cudaError_t e = ks->tile_f32(phys, load_aux, a, tile_threads, stream);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return -1; }
+    ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("tile kernel launch: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+template <> int Handle<double>::launch_tile(const StageArgs<double>& a, int load_aux) {
+    cudaError_t e = ks->tile_f64(phys, load_aux, a, tile_threads, stream);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return -1; }
+    ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("tile kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
 
@@ -365,7 +390,10 @@ template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
         a.dt = dt;
         if (!heun) {   // forward_euler.jl:19-31
             a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
-            if (int rc = launch((aux_stale || force_load) ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a)) return rc;
+            const bool load = aux_stale || force_load;
+            int rc = use_tile ? launch_tile(a, load ? 1 : 0) : -1;
+            if (rc == -1) rc = launch(load ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a);
+            if (rc) return rc;
         } else {       // heun.jl:37-71
             a.mode = MODE_HEUN1; a.load_aux = aux_stale ? 1 : 0; a.t_x = t; a.t_b = t; x_state(a);
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
