@@ -72,6 +72,8 @@ struct M {
     __device__ static __forceinline__ NF mx(NF a, NF b) { return jmax(a, b); }
     __device__ static __forceinline__ NF pow23(NF x) { NF c = tcbrt(x); return c * c; }
 };
+static __device__ __noinline__ double pow23_cold(double x) { double c = cbrt(x); return c * c; }
+
 template <>
 struct M<double, true> {
     __device__ static __forceinline__ double rcp(double x) {
@@ -97,7 +99,7 @@ struct M<double, true> {
     // x^(2/3) for 0 < x <= 1: r ~ x^(-1/3) seeded in FP32 (otherwise idle pipe), two Newton steps
     // r <- r + r (1 - x r^3) / 3 in FP64; x^(2/3) = x r.
     __device__ static __forceinline__ double pow23(double x) {
-        if (x < 1.0e-30) { double c = cbrt(x); return c * c; }
+        if (x < 1.0e-30) return pow23_cold(x);
         double r = (double)rcbrtf((float)x);
         double t = x * r * r; double e = fma(-t, r, 1.0); r = fma(r, e * (1.0 / 3.0), r);
         t = x * r * r; e = fma(-t, r, 1.0); r = fma(r, e * (1.0 / 3.0), r);
@@ -197,54 +199,72 @@ __device__ __forceinline__ void temperature_to_energy(const DevParams<NF>& p, NF
 
 // hydraulic conductivity at a cell centre, soil_hydraulic_properties.jl:170-221
 // (real branch of the complex-valued formula; exponent n/(n+1) as coded)
-template <class NF, bool FAST>
-__device__ __forceinline__ NF cell_conductivity(const DevParams<NF>& p, NF sat, NF liq) {
+template <class NF>
+__device__ __forceinline__ NF cell_conductivity_reference(const DevParams<NF>& p, NF sat, NF liq) {
     Fractions<NF> f = fractions(p, sat, liq);
     if (p.unsat_k == TRM_UNSATK_LINEAR) {
         NF thsat = f.water + f.ice + f.air;
         return p.Ksat * f.water / thsat;
     }
     NF n = p.vg_n;
-    if (FAST) {
-        // end members are exact in the reference formula too: x = 0 -> K = 0, x = 1 (saturated, thawed) -> K = K_sat
-        NF x = sat * liq;
-        if (x == NF(0)) return NF(0);
-        NF I_ice = NF(1);
-        if (liq != NF(1)) I_ice = texp10(-p.Omega * (1 - liq));
-        if (x == NF(1)) return p.Ksat * I_ice;
-        NF a;
-        if (p.vg_n_is_2) a = 1 - M<NF, FAST>::sqrt_(M<NF, FAST>::mx(1 - M<NF, FAST>::pow23(x), NF(0)));
-        else a = 1 - tpow(1 - tpow(x, p.vg_k_exp1), p.vg_k_exp2);
-        return tabs(p.Ksat * I_ice * M<NF, FAST>::sqrt_(x) * (a * a));
-    }
     NF x = f.water / p.por;
     NF I_ice = tpow(NF(10), -p.Omega * (1 - liq));
     NF inner = 1 - tpow(x, n / (n + 1));
     NF a = 1 - tpow(inner, (n - 1) / n);
     return tabs(p.Ksat * I_ice * tsqrt(x) * (a * a));
 }
+// out-of-line copy for the cold branches of the fast path (keeps the hot loop small in the instruction cache)
+template <class NF>
+__device__ __noinline__ NF cell_conductivity_cold(const DevParams<NF>& p, NF sat, NF liq) { return cell_conductivity_reference(p, sat, liq); }
+template <class NF>
+__device__ __noinline__ NF ice_impedance_cold(NF Omega, NF liq) { return texp10(-Omega * (1 - liq)); }
+
+template <class NF, bool FAST>
+__device__ __forceinline__ NF cell_conductivity(const DevParams<NF>& p, NF sat, NF liq) {
+    if (FAST) {
+        if (!p.vg_n_is_2 || p.unsat_k == TRM_UNSATK_LINEAR) return cell_conductivity_cold(p, sat, liq);
+        // van Genuchten n = 2. End members are exact in the reference formula too:
+        // x = 0 -> K = 0, x = 1 (saturated, thawed) -> K = K_sat
+        const NF x = sat * liq;
+        if (x == NF(0)) return NF(0);
+        NF I_ice = NF(1);
+        if (liq != NF(1)) I_ice = ice_impedance_cold(p.Omega, liq);
+        if (x == NF(1)) return p.Ksat * I_ice;
+        const NF a = 1 - M<NF, FAST>::sqrt_(M<NF, FAST>::mx(1 - M<NF, FAST>::pow23(x), NF(0)));
+        return tabs(p.Ksat * I_ice * M<NF, FAST>::sqrt_(x) * (a * a));
+    }
+    return cell_conductivity_reference(p, sat, liq);
+}
 
 // inverse soil water retention curve psi_m(theta; theta_sat) [FreezeCurves.jl 0.9 VanGenuchten /
 // BrooksCorey], called at soil_hydraulic_closures.jl:115-118
-template <class NF, bool FAST>
-__device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF thsat) {
+template <class NF>
+__device__ __forceinline__ NF swrc_inverse_reference(const DevParams<NF>& p, NF theta, NF thsat) {
     if (p.swrc == TRM_SWRC_VANGENUCHTEN) {
         if (!(theta < thsat)) return NF(0);
-        NF se = FAST ? (theta - p.theta_res) * p.r_thspan : (theta - p.theta_res) / (thsat - p.theta_res);
-        if (FAST) {
-            if (p.vg_n_is_2) {   // m = 1/2: psi_m = -(1/alpha) sqrt(se^-2 - 1) ; se = 0 (dry layer) is -Inf as in the reference
-                const NF t = se * se;
-                if (t == NF(0)) return -Lim<NF>::inf();
-                return p.neg_inv_alpha * M<NF, FAST>::sqrt_(M<NF, FAST>::mx(M<NF, FAST>::rcp(t) - NF(1), NF(0)));
-            }
-            return p.neg_inv_alpha * tpow(tpow(se, p.vg_inv_m_neg) - NF(1), p.vg_inv_n);
-        }
+        NF se = (theta - p.theta_res) / (thsat - p.theta_res);
         NF n = p.vg_n, m = 1 - 1 / n;
         return -1 / p.vg_alpha * tpow(tpow(se, -1 / m) - NF(1), 1 / n);
     }
     if (!(theta < thsat)) return -p.bc_psis;
     NF se = (theta - p.theta_res) / (thsat - p.theta_res);
     return -p.bc_psis * tpow(se, -1 / p.bc_lambda);
+}
+template <class NF>
+__device__ __noinline__ NF swrc_inverse_cold(const DevParams<NF>& p, NF theta, NF thsat) { return swrc_inverse_reference(p, theta, thsat); }
+
+template <class NF, bool FAST>
+__device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF thsat) {
+    if (FAST) {
+        if (p.swrc != TRM_SWRC_VANGENUCHTEN || !p.vg_n_is_2) return swrc_inverse_cold(p, theta, thsat);
+        if (!(theta < thsat)) return NF(0);
+        // m = 1/2: psi_m = -(1/alpha) sqrt(se^-2 - 1) ; se = 0 (dry layer) is -Inf as in the reference
+        const NF se = (theta - p.theta_res) * p.r_thspan;
+        const NF t = se * se;
+        if (t == NF(0)) return -Lim<NF>::inf();
+        return p.neg_inv_alpha * M<NF, FAST>::sqrt_(M<NF, FAST>::mx(M<NF, FAST>::rcp(t) - NF(1), NF(0)));
+    }
+    return swrc_inverse_reference(p, theta, thsat);
 }
 
 // total pressure head, saturation_to_pressure! soil_hydraulic_closures.jl:102-129

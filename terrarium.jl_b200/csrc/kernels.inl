@@ -22,30 +22,36 @@ cudaError_t launch_phys(int variant, const StageArgs<NF>& a, int block, cudaStre
 }
 
 // ForwardEuler stage as a shared-memory tile kernel (tile_kernel.cuh); returns cudaErrorInvalidConfiguration
-// when the column does not fit into shared memory (the caller falls back to the streaming kernel).
-template <class NF, int PHYS, int LOAD>
-cudaError_t launch_tile_variant(const StageArgs<NF>& a, int threads, cudaStream_t st) {
-    const size_t smem = sizeof(NF) * tile_smem_elems(a.nz);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel<NF, PHYS, LOAD, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// when nz exceeds the largest compiled layer capacity (the caller falls back to the streaming kernel).
+template <class NF, int PHYS, int LOAD, int NZCAP>
+cudaError_t launch_tile_variant(const StageArgs<NF>& a, cudaStream_t st) {
+    constexpr size_t smem = sizeof(NF) * TileLayout<NZCAP>::TOTAL;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel<NF, PHYS, LOAD, kFast, NZCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured = true;
     }
     const int64_t nblk = (a.ncol + TILE_COLS - 1) / TILE_COLS;
-    tile_kernel<NF, PHYS, LOAD, kFast><<<(unsigned)nblk, threads, smem, st>>>(a);
+    tile_kernel<NF, PHYS, LOAD, kFast, NZCAP><<<(unsigned)nblk, TILE_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
+template <class NF, int PHYS, int LOAD>
+cudaError_t launch_tile_cap(const StageArgs<NF>& a, cudaStream_t st) {
+    if (a.nz <= 32) return launch_tile_variant<NF, PHYS, LOAD, 32>(a, st);
+    if (a.nz <= 64) return launch_tile_variant<NF, PHYS, LOAD, 64>(a, st);
+    if (a.nz <= 128 && sizeof(NF) * TileLayout<128>::TOTAL <= 227 * 1024) return launch_tile_variant<NF, PHYS, LOAD, 128>(a, st);
+    return cudaErrorInvalidConfiguration;
+}
 template <class NF>
-cudaError_t launch_tile(int phys, int load_aux, const StageArgs<NF>& a, int threads, cudaStream_t st) {
-    if (sizeof(NF) * tile_smem_elems(a.nz) > 220 * 1024) return cudaErrorInvalidConfiguration;
+cudaError_t launch_tile(int phys, int load_aux, const StageArgs<NF>& a, int /*threads*/, cudaStream_t st) {
     switch (phys * 2 + (load_aux ? 1 : 0)) {
-        case 0: return launch_tile_variant<NF, PHYS_NOFLOW, 0>(a, threads, st);
-        case 1: return launch_tile_variant<NF, PHYS_NOFLOW, 1>(a, threads, st);
-        case 2: return launch_tile_variant<NF, PHYS_RICHARDS, 0>(a, threads, st);
-        case 3: return launch_tile_variant<NF, PHYS_RICHARDS, 1>(a, threads, st);
-        case 4: return launch_tile_variant<NF, PHYS_LAND, 0>(a, threads, st);
-        default: return launch_tile_variant<NF, PHYS_LAND, 1>(a, threads, st);
+        case 0: return launch_tile_cap<NF, PHYS_NOFLOW, 0>(a, st);
+        case 1: return launch_tile_cap<NF, PHYS_NOFLOW, 1>(a, st);
+        case 2: return launch_tile_cap<NF, PHYS_RICHARDS, 0>(a, st);
+        case 3: return launch_tile_cap<NF, PHYS_RICHARDS, 1>(a, st);
+        case 4: return launch_tile_cap<NF, PHYS_LAND, 0>(a, st);
+        default: return launch_tile_cap<NF, PHYS_LAND, 1>(a, st);
     }
 }
 

@@ -80,7 +80,7 @@ struct StageArgs {
 
 // update_inputs! (input_sources.jl:165-171) and function valued BCs, evaluated at clock time t.
 template <class NF>
-__device__ __forceinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) {
+__device__ __noinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) {
     switch (s.kind) {
         case TRM_SRC_CONST: return s.cval;
         case TRM_SRC_FIELD: return s.a[c];

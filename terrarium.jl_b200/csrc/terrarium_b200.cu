@@ -320,7 +320,7 @@ struct Handle : HandleBase {
     int tendencies() override;
     int diagnostics(trm_diag* out, double** dev) override;
     int set_block(int b) override {
-        if (b < 32 || b > TRM_TILE_THREADS || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 256]");
+        if (b < 32 || b > 256 || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 256]");
         tile_threads = b; block = b < TRM_MAX_BLOCK ? b : TRM_MAX_BLOCK;
         return TRM_OK;
     }

@@ -1,23 +1,27 @@
 // tile_kernel.cuh -- the ForwardEuler stage as a shared-memory tile kernel (the hot path).
 //
-// A block owns a tile of 32 adjacent columns x all nz layers.  Lanes map to columns (every global
-// access of a warp is one fully coalesced row segment of the [layer][column] arrays), warps map to
-// layers (warp w handles layers w+1, w+1+W, ...), so every layer-dependent special case (boundary
-// faces, halos, flux boundary conditions) is warp-uniform.  The column state lives in shared
-// memory for the whole stage:
+// A block of 8 warps owns a tile of 32 adjacent columns x all nz layers.  Lanes map to columns
+// (every global access of a warp is one fully coalesced row segment of the [layer][column]
+// arrays), warps map to layers (warp w handles layers w+1, w+9, w+17, ...), so every layer
+// dependent special case (boundary faces, halos, flux boundary conditions) is warp-uniform and the
+// cells a thread owns are independent of each other (instruction level parallelism instead of a
+// serial walk up the column).  The column state lives in shared memory for the whole stage:
 //
 //   phase 1  (cell parallel)  load U, sat -> closure fields T, liq, psi of the state at time n
-//            (recomputed, or read when LOAD_AUX), thermal / hydraulic conductivities -> smem
+//            (recomputed, or read when LOAD), thermal / hydraulic conductivities -> smem
 //   phase 2  (cell parallel)  face conductivities, Fourier and Darcy fluxes, tendencies, Flux BCs,
 //            explicit update; LandModel surface processes run in the warp that owns the top layer
-//   phase 3  (column serial, one warp, only if some column of the tile needs it)
+//   phase 3  (column serial, one warp, only for tiles in which some layer left [0, 1])
 //            adjust_saturation_profile! sweeps (soil_hydrology.jl:185-219) on the smem profile
 //   phase 4  (cell parallel)  water table, closures of the new state, stores
 //
-// The reference functions computed are the same as in stage_kernel.cuh (which remains the generic
-// streaming implementation used for Heun stages, tendencies and auxiliaries); the per-cell
-// arithmetic is shared through column_physics.cuh.  HBM traffic per column-layer-step is unchanged:
-// read U, sat; write U, sat, T, liq, psi.
+// The reference functions computed are the same as in stage_kernel.cuh (the generic streaming
+// implementation that serves Heun stages, tendencies and auxiliaries); the per-cell arithmetic is
+// shared through column_physics.cuh.  HBM traffic per column-layer-step is unchanged: read U, sat;
+// write U, sat, T, liq, psi.
+//
+// NZCAP (32 / 64 / 128) fixes the shared-memory spacing of the per-field tiles at compile time so
+// that every shared-memory access is `row offset + immediate`; nz <= NZCAP is a runtime value.
 #pragma once
 
 #include "stage_kernel.cuh"
@@ -25,177 +29,202 @@
 namespace trm {
 
 constexpr int TILE_COLS = 32;
+constexpr int TILE_WARPS = 8;
+constexpr int TILE_THREADS = TILE_COLS * TILE_WARPS;
 
-#ifndef TRM_TILE_THREADS
-#define TRM_TILE_THREADS 256     // 8 warps: warp w owns layers w+1, w+9, ...
-#endif
 #ifndef TRM_TILE_MIN_BLOCKS
 #define TRM_TILE_MIN_BLOCKS 4    // resident blocks per SM the register allocator must allow (<= 64 registers)
 #endif
 
-// number of NF elements of dynamic shared memory the tile kernel needs
-__host__ __device__ inline size_t tile_smem_elems(int nz) {
-    // sU, sS, sKc: nz rows ; sT, sKap, sP: nz+2 rows (z-halos) ; 6 metric arrays ; 4 per-column rows
-    return (size_t)(3 * nz + 3 * (nz + 2) + 4) * TILE_COLS + 6 * (size_t)(nz + 3);
-}
+template <int NZCAP>
+struct TileLayout {
+    static constexpr int ROWS_H = NZCAP + 2;                 // rows of a tile with z-halos
+    // element offsets (units of NF) of the tiles; every tile row holds TILE_COLS columns
+    static constexpr int T = 0;
+    static constexpr int KAP = T + ROWS_H * TILE_COLS;
+    static constexpr int P = KAP + ROWS_H * TILE_COLS;
+    static constexpr int KC = P + ROWS_H * TILE_COLS;        // row k = layer k, rows 0 and nz+1.. unused
+    static constexpr int U = KC + ROWS_H * TILE_COLS;        // row k-1 = layer k
+    static constexpr int S = U + NZCAP * TILE_COLS;
+    static constexpr int COL = S + NZCAP * TILE_COLS;        // 4 per-column rows: G_top / excess, infiltration, idx, flags
+    static constexpr int MET = COL + 4 * TILE_COLS;          // 6 metric arrays of NZCAP + 3
+    static constexpr int TOTAL = MET + 6 * (NZCAP + 3);
+};
 
-template <class NF, int PHYS, int LOAD_CT, bool FAST>
-__global__ void __launch_bounds__(TRM_TILE_THREADS, TRM_TILE_MIN_BLOCKS) tile_kernel(const __grid_constant__ StageArgs<NF> A) {
+template <class NF, int PHYS, int LOAD_CT, bool FAST, int NZCAP>
+__global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOCKS : (NZCAP <= 64 ? 2 : 1))) tile_kernel(const __grid_constant__ StageArgs<NF> A) {
     constexpr bool RICH = PHYS != PHYS_NOFLOW;
     constexpr bool LAND = PHYS == PHYS_LAND;
     constexpr bool LOAD = LOAD_CT != 0;
+    constexpr int R = NZCAP / TILE_WARPS;      // layers per thread (upper bound)
+    constexpr int CH = 4;                      // layers whose loads are issued together
     using Mx = M<NF, FAST>;
+    using L = TileLayout<NZCAP>;
+    constexpr int NZP = NZCAP + 3;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NF* sm = reinterpret_cast<NF*>(smem_raw);
-    const int nz = A.nz, nzp = nz + 3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    // metrics
-    NF* zF = sm;
-    NF* zC = zF + nzp;
-    NF* dzc = zC + nzp;
-    NF* rdzc = dzc + nzp;
-    NF* dzf = rdzc + nzp;
-    NF* rdzf = dzf + nzp;
-    // tiles, row stride TILE_COLS
-    NF* sU = rdzf + nzp;                         // [nz]    internal energy (time n, then n+1)
-    NF* sS = sU + (size_t)nz * TILE_COLS;        // [nz]    saturation (time n, then n+1)
-    NF* sKc = sS + (size_t)nz * TILE_COLS;       // [nz]    hydraulic conductivity at centres
-    NF* sT = sKc + (size_t)nz * TILE_COLS;       // [nz+2]  temperature with z-halos (row 0 = below bottom)
-    NF* sKap = sT + (size_t)(nz + 2) * TILE_COLS;   // [nz+2]  thermal conductivity with z-halos
-    NF* sP = sKap + (size_t)(nz + 2) * TILE_COLS;   // [nz+2]  pressure head with z-halos
-    NF* sCol = sP + (size_t)(nz + 2) * TILE_COLS;   // [4]     per column: G_top, infil_top, (int) idx, (int) flags
-    int* sIdx = reinterpret_cast<int*>(sCol + 2 * TILE_COLS);
-    int* sFlag = reinterpret_cast<int*>(sCol + 3 * TILE_COLS);
+    const int nz = A.nz;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    NF* const zF = sm + L::MET;
+    NF* const zC = zF + NZP;
+    NF* const dzc = zC + NZP;
+    NF* const rdzc = dzc + NZP;
+    NF* const dzf = rdzc + NZP;
+    NF* const rdzf = dzf + NZP;
+    NF* const col = sm + lane;                 // this thread's column inside every tile
+    int* const sIdx = reinterpret_cast<int*>(sm + L::COL + 2 * TILE_COLS);
+    int* const sFlag = reinterpret_cast<int*>(sm + L::COL + 3 * TILE_COLS);
 
-    for (int i = threadIdx.x; i < 6 * nzp; i += blockDim.x) sm[i] = A.metrics[i];
-    const int64_t c = (int64_t)blockIdx.x * TILE_COLS + lane;
-    const bool valid = c < A.ncol;
+    {   // metrics: host layout [6][nz+3] -> smem [6][NZCAP+3]
+        const int nzp = nz + 3;
+        for (int i = threadIdx.x; i < 6 * nzp; i += TILE_THREADS) { const int a = i / nzp, j = i - a * nzp; zF[a * NZP + j] = A.metrics[i]; }
+    }
+    const int64_t c0 = (int64_t)blockIdx.x * TILE_COLS + lane;
+    const bool valid = c0 < A.ncol;
+    const int64_t c = valid ? c0 : A.ncol - 1;   // lanes beyond the last column shadow it (loads only, never stored)
     const int64_t ld = A.ld;
     const DevParams<NF>& p = A.p;
     const NF dt = A.dt;
     if (warp == 0) { sIdx[lane] = nz + 1; sFlag[lane] = 0; }
-
-    // ---- phase 1a: stream the tile into shared memory (independent loads, all in flight together) ----
-    for (int k = warp; k < nz; k += nwarp) {
-        const int64_t o = (int64_t)k * ld + c;
-        sU[k * TILE_COLS + lane] = valid ? A.xU[o] : NF(0);
-        sS[k * TILE_COLS + lane] = valid ? A.xS[o] : NF(1);
-        if (LOAD) {
-            sT[(k + 1) * TILE_COLS + lane] = valid ? A.xT[o] : NF(0);
-            sKap[(k + 1) * TILE_COLS + lane] = valid ? A.xL[o] : NF(1);   // liquid fraction parked in the kappa tile
-            if (RICH) sP[(k + 1) * TILE_COLS + lane] = valid ? A.xP[o] : NF(0);
-        }
-    }
-    __syncthreads();   // metrics visible (the tile rows are read back by the thread that wrote them)
+    __syncthreads();
     const NF zref = zF[nz + 1];
-    const NF wtx = (RICH && !LOAD && valid) ? A.xWt[c] : NF(0);
+    const NF wtx = (RICH && !LOAD) ? A.xWt[c] : NF(0);
 
     auto bc_input = [&](int slot) -> NF {
         const int kind = A.bc[slot].kind;
-        if (kind == TRM_BC_DEFAULT || !valid) return NF(0);
+        if (kind == TRM_BC_DEFAULT) return NF(0);
         return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x);
     };
 
-    // ---- phase 1b: closure fields and conductivities of the state at time n ----
-    for (int k = warp + 1; k <= nz; k += nwarp) {
-        const int r = (k - 1) * TILE_COLS + lane, rh = k * TILE_COLS + lane;
-        const NF U = sU[r], s = sS[r];
-        NF T, l, P = NF(0);
-        if (LOAD) { T = sT[rh]; l = sKap[rh]; if (RICH) P = sP[rh]; }
-        else {
-            energy_to_temperature<NF, FAST>(p, U, s, T, l);
-            if (RICH) P = pressure_head<NF, FAST>(p, s, wtx, zC[k], zref);
-            sT[rh] = T;
-            if (RICH) sP[rh] = P;
-        }
-        sKap[rh] = FAST ? thermal_conductivity_fast(p, s, l) : thermal_conductivity(p, s, l);
-        if (RICH) sKc[r] = cell_conductivity<NF, FAST>(p, s, l);
-        if (k == 1) {          // halo below the bottom layer (fill_halo_regions!)
-            sT[lane] = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, T, bc_input(TRM_BC_TEMPERATURE_BOTTOM), dzf[1], false);
-            const NF s0 = (RICH || p.sat_halo == TRM_HALO_COPY) ? s : NF(0);
-            sKap[lane] = FAST ? thermal_conductivity_fast(p, s0, l) : thermal_conductivity(p, s0, l);
-            if (RICH) sP[lane] = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, P, bc_input(TRM_BC_PRESSURE_BOTTOM), dzf[1], false);
-        }
-        if (k == nz) {         // halo above the surface
-            const int rt = (nz + 1) * TILE_COLS + lane;
-            sT[rt] = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, T, bc_input(TRM_BC_TEMPERATURE_TOP), dzf[nz + 1], true);
-            const NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? s : NF(0);
-            sKap[rt] = FAST ? thermal_conductivity_fast(p, sh, l) : thermal_conductivity(p, sh, l);
-            if (RICH) sP[rt] = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, P, bc_input(TRM_BC_PRESSURE_TOP), dzf[nz + 1], true);
-            if (LAND) {
-                // ---- LandModel surface processes (land_model.jl:79-88), per column, in the top layer's warp ----
-                NF G = NF(0), inf = NF(0);
-                if (valid) {
-                    Surface<NF> a;
-                    a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
-                    a.LWd = eval_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
-                    a.Ta = eval_input(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
-                    a.pres = eval_input(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
-                    a.q = eval_input(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
-                    a.V = eval_input(A.in[TRM_IN_WINDSPEED], c, A.t_x);
-                    a.rain = eval_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
-                    const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
-                    a.Tskin_in = prescribed ? eval_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
-                    // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
-                    NF Vc = jmax(a.V, p.Vmin);
-                    double Va = fmax((double)Vc, 1.0e-6);
-                    a.ra = 1.0 / ((double)p.C_h * Va);
-                    NF Ts = A.Ts[c];
-                    // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
-                    // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
-                    NF Tsurf = prescribed ? a.Tskin_in : Ts;
-                    NF es = saturation_vapor_pressure(Tsurf);
-                    NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
-                    NF vpd = jmax(es - ea, NF(0.1));
-                    NF dq = p.eps_mw * vpd / a.pres;
-                    NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
-                    // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 ; Kf[Nz] = Kc[Nz] (soil_hydrology.jl:270-273)
-                    NF S = A.bSx[c], Kt = sKc[r], sat_top = s;
-                    NF drain;
-                    if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
-                    else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, Kt) : NF(0); }
-                    NF runoff = a.rain + drain - inf;
-                    // surface energy balance kernel, executed twice (land_model.jl:85-86)
-                    NF swu, lwu, rnet, hs, hl;
+    // ---- phase 1: closure fields and conductivities of the state at time n ----
 #pragma unroll 1
-                    for (int rep = 0; rep < 2; ++rep) {
-                        seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
-                        if (!prescribed) {
-                            Ts = T - G * dzc[nz] / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
-                            seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
-                        }
-                    }
-                    A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
-                    A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
-                    if (!prescribed) A.Ts[c] = Ts;
-                }
-                sCol[lane] = G; sCol[TILE_COLS + lane] = inf;
+    for (int i0 = 0; i0 < R; i0 += CH) {
+        NF Ur[CH], sr[CH], Tr[CH], lr[CH], Pr[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int k = warp + 1 + TILE_WARPS * (i0 + j);
+            Ur[j] = NF(0); sr[j] = NF(0); Tr[j] = NF(0); lr[j] = NF(0); Pr[j] = NF(0);
+            if (k <= nz) {
+                const int64_t o = (int64_t)(k - 1) * ld + c;
+                Ur[j] = A.xU[o]; sr[j] = A.xS[o];
+                if (LOAD) { Tr[j] = A.xT[o]; lr[j] = A.xL[o]; if (RICH) Pr[j] = A.xP[o]; }
             }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int k = warp + 1 + TILE_WARPS * (i0 + j);
+            if (k > nz) continue;
+            NF* const q = col + k * TILE_COLS;     // row k of the halo tiles; row k-1 of the U / S tiles is q - TILE_COLS
+            const NF U = Ur[j], s = sr[j];
+            NF T = Tr[j], l = lr[j], P = Pr[j];
+            if (!LOAD) {
+                energy_to_temperature<NF, FAST>(p, U, s, T, l);
+                if (RICH) P = pressure_head<NF, FAST>(p, s, wtx, zC[k], zref);
+            }
+            q[L::T] = T;
+            if (RICH) q[L::P] = P;
+            q[L::U - TILE_COLS] = U;
+            q[L::S - TILE_COLS] = s;
+            q[L::KAP] = FAST ? thermal_conductivity_fast(p, s, l) : thermal_conductivity(p, s, l);
+            if (RICH) q[L::KC] = cell_conductivity<NF, FAST>(p, s, l);
+        }
+    }
+    // ---- z-halos (fill_halo_regions!) by the warps that own the boundary layers; they
+    //      re-read their own shared-memory rows, so no barrier is needed before this point ----
+    if (warp == 0) {           // halo below the bottom layer
+        NF* const q = col + TILE_COLS;
+        const NF T = q[L::T], s = q[L::S - TILE_COLS];
+        col[L::T] = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, T, bc_input(TRM_BC_TEMPERATURE_BOTTOM), dzf[1], false);
+        // conductivity of the halo cell: same (sat, liq) as layer 1 when the saturation halo is a copy, else sat = 0
+        // (SURVEY.md Appendix B.6), for which the liquid fraction drops out of the constituent sum
+        const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
+        col[L::KAP] = copy ? q[L::KAP] : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
+        if (RICH) col[L::P] = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, q[L::P], bc_input(TRM_BC_PRESSURE_BOTTOM), dzf[1], false);
+        (void)s;
+    }
+    if (warp == ((nz - 1) & (TILE_WARPS - 1))) {   // halo above the surface (+ LandModel surface processes)
+        NF* const q = col + nz * TILE_COLS;
+        NF* const qt = q + TILE_COLS;
+        const NF T = q[L::T], s = q[L::S - TILE_COLS];
+        qt[L::T] = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, T, bc_input(TRM_BC_TEMPERATURE_TOP), dzf[nz + 1], true);
+        const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
+        qt[L::KAP] = copy ? q[L::KAP] : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
+        if (RICH) qt[L::P] = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, q[L::P], bc_input(TRM_BC_PRESSURE_TOP), dzf[nz + 1], true);
+        if (LAND) {
+            // ---- LandModel surface processes (land_model.jl:79-88), per column ----
+            const NF Kc = q[L::KC];
+            Surface<NF> a;
+            a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
+            a.LWd = eval_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
+            a.Ta = eval_input(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
+            a.pres = eval_input(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
+            a.q = eval_input(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
+            a.V = eval_input(A.in[TRM_IN_WINDSPEED], c, A.t_x);
+            a.rain = eval_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
+            const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
+            a.Tskin_in = prescribed ? eval_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
+            // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
+            NF Vc = jmax(a.V, p.Vmin);
+            double Va = fmax((double)Vc, 1.0e-6);
+            a.ra = 1.0 / ((double)p.C_h * Va);
+            NF Ts = A.Ts[c];
+            // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
+            // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
+            NF Tsurf = prescribed ? a.Tskin_in : Ts;
+            NF es = saturation_vapor_pressure(Tsurf);
+            NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
+            NF vpd = jmax(es - ea, NF(0.1));
+            NF dq = p.eps_mw * vpd / a.pres;
+            NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
+            // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 ; Kf[Nz] = Kc[Nz] (soil_hydrology.jl:270-273)
+            NF S = A.bSx[c], Kt = Kc, sat_top = s;
+            NF drain, inf;
+            if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
+            else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, Kt) : NF(0); }
+            NF runoff = a.rain + drain - inf;
+            // surface energy balance kernel, executed twice (land_model.jl:85-86)
+            NF swu, lwu, rnet, hs, hl, G;
+#pragma unroll 1
+            for (int rep = 0; rep < 2; ++rep) {
+                seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+                if (!prescribed) {
+                    Ts = T - G * dzc[nz] / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
+                    seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+                }
+            }
+            if (valid) {
+                A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
+                A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
+                if (!prescribed) A.Ts[c] = Ts;
+            }
+            col[L::COL] = G; col[L::COL + TILE_COLS] = inf;
         }
     }
     __syncthreads();
 
     // ---- phase 2: fluxes, tendencies, explicit step ----
-    auto kc_at = [&](int k) -> NF { return sKc[(k - 1) * TILE_COLS + lane]; };
     auto kf_at = [&](int k) -> NF {   // face conductivity Kf[k], soil_hydrology.jl:249-276 (k is warp uniform)
         if (k <= 0 || k >= nz + 2) return NF(0);           // halo faces are never written by the reference
-        if (k == 1) return kc_at(1);
-        if (k >= nz) return kc_at(nz);                     // Kf[Nz] = Kc[Nz], Kf[Nz+1] = Kf[Nz]
-        return Mx::mn(kc_at(k), kc_at(k - 1));
+        if (k == 1) return col[L::KC + TILE_COLS];
+        if (k >= nz) return col[L::KC + nz * TILE_COLS];   // Kf[Nz] = Kc[Nz], Kf[Nz+1] = Kf[Nz]
+        return Mx::mn(col[L::KC + k * TILE_COLS], col[L::KC + (k - 1) * TILE_COLS]);
     };
     int flagged = 0;
-    for (int k = warp + 1; k <= nz; k += nwarp) {
-        const int r = (k - 1) * TILE_COLS + lane, rh = k * TILE_COLS + lane;
-        const NF Tm = sT[rh - TILE_COLS], T0 = sT[rh], Tp = sT[rh + TILE_COLS];
-        const NF km = sKap[rh - TILE_COLS], k0 = sKap[rh], kp = sKap[rh + TILE_COLS];
+#pragma unroll 2
+    for (int i = 0; i < R; ++i) {
+        const int k = warp + 1 + TILE_WARPS * i;
+        if (k > nz) break;
+        NF* const q = col + k * TILE_COLS;
+        const NF Tm = q[L::T - TILE_COLS], T0 = q[L::T], Tp = q[L::T + TILE_COLS];
+        const NF km = q[L::KAP - TILE_COLS], k0 = q[L::KAP], kp = q[L::KAP + TILE_COLS];
         // diffusive_heat_flux at faces k and k+1, soil_energy.jl:134-149
         const NF qh_lo = -((k0 + km) / 2) * ((T0 - Tm) * rdzf[k]);
         const NF qh_hi = -((kp + k0) / 2) * ((Tp - T0) * rdzf[k + 1]);
         NF tU = -((qh_hi - qh_lo) * rdzc[k]);                                   // soil_energy.jl:112-131
         NF tS = NF(0);
         if (RICH) {
-            const NF Pm = sP[rh - TILE_COLS], P0 = sP[rh], Pp = sP[rh + TILE_COLS];
+            const NF Pm = q[L::P - TILE_COLS], P0 = q[L::P], Pp = q[L::P + TILE_COLS];
             const NF Kf_m = kf_at(k - 1), Kf_0 = kf_at(k), Kf_p = kf_at(k + 1), Kf_pp = kf_at(k + 2);
             // darcy_flux at faces k and k+1, soil_hydrology_rre.jl:119-131
             const NF g_lo = (P0 - Pm) * rdzf[k], g_hi = (Pp - P0) * rdzf[k + 1];
@@ -213,7 +242,7 @@ __global__ void __launch_bounds__(TRM_TILE_THREADS, TRM_TILE_MIN_BLOCKS) tile_ke
         }
         // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
         if (k == nz) {
-            if (LAND) { tU -= sCol[lane] / dzc[nz]; tS -= (-sCol[TILE_COLS + lane]) / dzc[nz]; }   // land_model.jl:56-62
+            if (LAND) { tU -= col[L::COL] / dzc[nz]; tS -= (-col[L::COL + TILE_COLS]) / dzc[nz]; }   // land_model.jl:56-62
             else {
                 if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / dzc[nz];
                 if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / dzc[nz];
@@ -224,43 +253,63 @@ __global__ void __launch_bounds__(TRM_TILE_THREADS, TRM_TILE_MIN_BLOCKS) tile_ke
             if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / dzc[1];
         }
         // explicit step, abstract_timestepper.jl:113-141
-        sU[r] = sU[r] + tU * dt;
+        q[L::U - TILE_COLS] = q[L::U - TILE_COLS] + tU * dt;
         if (RICH) {
-            const NF sn = sS[r] + tS * dt;
-            sS[r] = sn;
-            if (!(sn <= 1) || sn < 0) flagged = 1;                       // needs adjust_saturation_profile! (also catches NaN)
-            else if (sn < 1) atomicMin(&sIdx[lane], k);                  // compute_water_table!: lowest unsaturated layer
+            const NF sn = q[L::S - TILE_COLS] + tS * dt;
+            q[L::S - TILE_COLS] = sn;
+            if (!(sn >= 0)) flagged |= 2;                                 // negative (or NaN): needs the downward sweep too
+            else if (sn > 1) flagged |= 1;                                // over-saturated: needs the upward sweep
+            else if (sn < 1) atomicMin(&sIdx[lane], k);                   // compute_water_table!: lowest unsaturated layer
         }
     }
     if (RICH) {
-        // ---- phase 3: adjust_saturation_profile! + compute_water_table! for tiles that need it ----
+        // ---- phase 3: adjust_saturation_profile! + compute_water_table! for the columns that need it ----
         const int any = __syncthreads_or(flagged);
         if (any) {
-            if (flagged) sFlag[lane] = 1;   // benign race: every writer stores 1
+            if (flagged) atomicOr(&sFlag[lane], flagged);
             __syncthreads();
-            if (warp == 0 && sFlag[lane]) {
-                // upward sweep, soil_hydrology.jl:192-199
+            const int flag = sFlag[lane];
+            if (warp == 0 && flag) {
+                // upward sweep, soil_hydrology.jl:192-199 ; the excess travels in a register instead of through
+                // sat[k+1] (same additions in the same order)
+                NF* const sS = col + L::S;
+                NF carry = NF(0);
+                int idx = nz + 1;
+#pragma unroll 1
                 for (int k = 1; k <= nz - 1; ++k) {
-                    NF s = sS[(k - 1) * TILE_COLS + lane];
-                    const NF e = jmax(s - 1, NF(0));
-                    sS[(k - 1) * TILE_COLS + lane] = s - e;
-                    sS[k * TILE_COLS + lane] += e * dzc[k] / dzc[k + 1];
+                    NF s = sS[(k - 1) * TILE_COLS] + carry;
+                    const NF e = Mx::mx(s - 1, NF(0));
+                    s -= e;
+                    carry = FAST ? e * dzc[k] * rdzc[k + 1] : e * dzc[k] / dzc[k + 1];
+                    sS[(k - 1) * TILE_COLS] = s;
+                    if (s < 1) idx = min(idx, k);
                 }
-                // downward sweep, :201-208
-                for (int k = nz; k >= 2; --k) {
-                    NF s = sS[(k - 1) * TILE_COLS + lane];
-                    const NF d = jmax(-s, NF(0));
-                    sS[(k - 1) * TILE_COLS + lane] = s + d;
-                    sS[(k - 2) * TILE_COLS + lane] -= d * dzc[k] / dzc[k - 1];
+                NF st = sS[(nz - 1) * TILE_COLS] + carry;
+                if (flag & 2) {
+                    // downward sweep, :201-208 (only when some layer went negative)
+                    sS[(nz - 1) * TILE_COLS] = st;
+#pragma unroll 1
+                    for (int k = nz; k >= 2; --k) {
+                        NF s = sS[(k - 1) * TILE_COLS];
+                        const NF d = jmax(-s, NF(0));
+                        sS[(k - 1) * TILE_COLS] = s + d;
+                        sS[(k - 2) * TILE_COLS] -= d * dzc[k] / dzc[k - 1];
+                    }
+                    st = sS[(nz - 1) * TILE_COLS];
+                } else if (!FAST) {
+                    st = st + jmax(-st, NF(0));   // the downward sweep is the identity (up to the sign of zero)
                 }
                 // top excess -> surface_excess_water, :210-216
-                NF st = sS[(nz - 1) * TILE_COLS + lane];
-                const NF e = jmax(st - 1, NF(0));
-                sS[(nz - 1) * TILE_COLS + lane] = st - e;
-                sCol[lane] = e * dzc[nz];   // G_top is dead by now: reuse the slot for the excess
-                sS[lane] = jmax(sS[lane], NF(0));
-                int idx = nz + 1;
-                for (int k = nz; k >= 1; --k) if (sS[(k - 1) * TILE_COLS + lane] < 1) idx = k;
+                const NF e = Mx::mx(st - 1, NF(0));
+                st -= e;
+                sS[(nz - 1) * TILE_COLS] = st;
+                col[L::COL] = e * dzc[nz];   // G_top is dead by now: the slot carries the excess to phase 4
+                if (flag & 2) {
+                    sS[0] = jmax(sS[0], NF(0));
+                    idx = nz + 1;
+#pragma unroll 1
+                    for (int k = nz; k >= 1; --k) if (sS[(k - 1) * TILE_COLS] < 1) idx = k;
+                } else if (st < 1) idx = min(idx, nz);
                 sIdx[lane] = idx;
             }
             __syncthreads();
@@ -270,24 +319,28 @@ __global__ void __launch_bounds__(TRM_TILE_THREADS, TRM_TILE_MIN_BLOCKS) tile_ke
     // ---- phase 4: water table, closures of the new state, stores ----
     NF wt_new = NF(0);
     if (RICH) {
-        const int idx = sIdx[lane];
-        wt_new = zF[idx];                      // zF[nz+1] when every layer is saturated (halo cell / fallback agree)
+        wt_new = zF[sIdx[lane]];               // zF[nz+1] when every layer is saturated (halo cell / fallback agree)
         if (warp == 0 && valid) {
             A.yWt[c] = wt_new;
             NF Sx = A.bSx[c] + NF(0) * dt;     // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
-            if (sFlag[lane]) Sx += sCol[lane];
+            if (sFlag[lane]) Sx += col[L::COL];
             A.ySx[c] = Sx;
         }
     }
-    for (int k = warp + 1; k <= nz; k += nwarp) {
-        const int r = (k - 1) * TILE_COLS + lane;
-        const NF Un = sU[r], sn = sS[r];
+#pragma unroll 2
+    for (int i = 0; i < R; ++i) {
+        const int k = warp + 1 + TILE_WARPS * i;
+        if (k > nz) break;
+        NF* const q = col + k * TILE_COLS;
+        const NF Un = q[L::U - TILE_COLS], sn = q[L::S - TILE_COLS];
         NF Tn, ln;
         energy_to_temperature<NF, FAST>(p, Un, sn, Tn, ln);
+        NF Pn = NF(0);
+        if (RICH) Pn = pressure_head<NF, FAST>(p, sn, wt_new, zC[k], zref);
         if (valid) {
             const int64_t o = (int64_t)(k - 1) * ld + c;
             A.yU[o] = Un; A.yT[o] = Tn; A.yL[o] = ln;
-            if (RICH) { A.yS[o] = sn; A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, zC[k], zref); }
+            if (RICH) { A.yS[o] = sn; A.yP[o] = Pn; }
         }
     }
 }
