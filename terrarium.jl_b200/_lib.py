@@ -13,7 +13,8 @@ from functools import lru_cache
 from . import _abi as abi
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(CSRC, "libterrarium_b200.so")
+# TRM_LIB selects an alternative build of the same library (kernel tuning experiments); default is the in-tree build
+LIB_PATH = os.environ.get("TRM_LIB") or os.path.join(CSRC, "libterrarium_b200.so")
 
 
 @lru_cache(maxsize=1)

@@ -230,7 +230,8 @@ __device__ __forceinline__ NF cell_conductivity(const DevParams<NF>& p, NF sat, 
         NF I_ice = NF(1);
         if (liq != NF(1)) I_ice = ice_impedance_cold(p.Omega, liq);
         if (x == NF(1)) return p.Ksat * I_ice;
-        const NF a = 1 - M<NF, FAST>::sqrt_(M<NF, FAST>::mx(1 - M<NF, FAST>::pow23(x), NF(0)));
+        // |.| guards the square root against a -1 ulp residue of the approximate power when x -> 1
+        const NF a = 1 - M<NF, FAST>::sqrt_(tabs(1 - M<NF, FAST>::pow23(x)));
         return tabs(p.Ksat * I_ice * M<NF, FAST>::sqrt_(x) * (a * a));
     }
     return cell_conductivity_reference(p, sat, liq);
@@ -262,7 +263,7 @@ __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF 
         const NF se = (theta - p.theta_res) * p.r_thspan;
         const NF t = se * se;
         if (t == NF(0)) return -Lim<NF>::inf();
-        return p.neg_inv_alpha * M<NF, FAST>::sqrt_(M<NF, FAST>::mx(M<NF, FAST>::rcp(t) - NF(1), NF(0)));
+        return p.neg_inv_alpha * M<NF, FAST>::sqrt_(tabs(M<NF, FAST>::rcp(t) - NF(1)));   // |.|: rounding guard as se -> 1
     }
     return swrc_inverse_reference(p, theta, thsat);
 }

@@ -63,7 +63,8 @@ struct Handle : HandleBase {
     int phys = PHYS_NOFLOW;
     int block = 128;          // threads per block of the streaming stage kernel
     int tile_threads = 256;   // threads per block of the tile kernel (warps = layers in flight per tile)
-    bool use_tile = true;     // ForwardEuler stages run the shared-memory tile kernel (env TRM_KERNEL=stream disables)
+    bool use_tile = false;    // env TRM_KERNEL=tile: run ForwardEuler stages on the shared-memory tile kernel instead of the
+                              // streaming kernel (measured slower on B200 so far: 7.0 ms vs 5.4 ms per 10 M-column step)
     const KernelSet* ks = nullptr;
     DevParams<NF> p{};
     std::vector<void*> allocs;
@@ -110,7 +111,7 @@ struct Handle : HandleBase {
         land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
         fast = c.math == TRM_MATH_FAST;
         { const char* e = std::getenv("TRM_FORCE_LOAD_AUX"); force_load = e && e[0] == '1'; }
-        { const char* e = std::getenv("TRM_KERNEL"); use_tile = !(e && std::string(e) == "stream"); }
+        { const char* e = std::getenv("TRM_KERNEL"); use_tile = e && std::string(e) == "tile"; }
         if (land && !richards) return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
         phys = land ? PHYS_LAND : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
         ks = fast ? &kernels_fast() : &kernels_faithful();
