@@ -287,6 +287,18 @@ int64_t trm_launch_count(trm_handle* h);
  * handle's stream (the events bracket exactly the fused stage kernels of that call). */
 int trm_last_step_ms(trm_handle* h, float* ms);
 
+/* ---- asynchronous variants (coupled-model usage: forcing in, surface state out, every step) ------------
+ * All three only enqueue work; trm_sync() waits for everything. Host buffers must be pinned and must stay
+ * valid / untouched until the next trm_sync().
+ *  trm_set_input_field_async: upload of a per-column input on a copy stream into the back half of a double
+ *      buffer; steps enqueued AFTER the call read the new values, steps already enqueued keep the old ones.
+ *  trm_step_async: trm_step without the final synchronisation (trm_last_step_ms is valid after trm_sync).
+ *  trm_get_field_async: snapshot of the field after all steps enqueued so far (device-to-device on the compute
+ *      stream), downloaded on a second copy stream while later steps run.                                  */
+int trm_set_input_field_async(trm_handle* h, int input_id, const void* pinned_host_values /* [ncol] NF */);
+int trm_step_async(trm_handle* h, double dt, int64_t nsteps);
+int trm_get_field_async(trm_handle* h, int field_id, void* pinned_host, int64_t count);
+
 /* Tuning knob: threads per block of the stage kernels (multiple of 32 in [32, 256]; default 256 for the
  * shared-memory tile kernel, capped at 128 for the streaming kernel). */
 int trm_set_block_size(trm_handle* h, int block);

@@ -12,4 +12,6 @@ from .integrator import (Field, ModelIntegrator, StateVariables, current_time, g
                          timestep)
 from ._lib import LIB_PATH, cuda_library
 
+# `terrarium_jl_b200.distributed` (torch.distributed helpers) is imported on demand: it pulls in torch
+
 __version__ = "0.1.0"

@@ -2,8 +2,8 @@
 
 Only declarations live here: struct layouts, enum values and a ``bind`` helper that attaches
 argument/return types to the entry points of a loaded shared library.  The same declarations
-serve the product library (prefix ``trm_``) and -- in tests only -- the CPU oracle (prefix
-``orc_``), because both export the identical ABI.
+serve the product library (prefix ``trm_``) and -- in tests only -- the CPU checker under ``oracle/``, which
+exports the identical ABI under its own prefix.
 """
 from __future__ import annotations
 
@@ -119,9 +119,13 @@ SIGNATURES = {
     "launch_count": (C.c_int64, [_H]),
     "last_step_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "set_block_size": (C.c_int, [_H, C.c_int]),
+    "set_input_field_async": (C.c_int, [_H, C.c_int, C.c_void_p]),
+    "step_async": (C.c_int, [_H, C.c_double, C.c_int64]),
+    "get_field_async": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
 }
 # entry points that only make sense on a device and that the CPU oracle does not export
-DEVICE_ONLY = ("field_ptr", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size")
+DEVICE_ONLY = ("field_ptr", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size",
+               "set_input_field_async", "step_async", "get_field_async")
 
 
 class BoundLibrary:

@@ -46,6 +46,10 @@ struct HandleBase {
     virtual int tendencies() = 0;
     virtual int diagnostics(trm_diag* out, double** dev) = 0;
     virtual int set_block(int b) = 0;
+    virtual int set_input_field_async(int id, const void* v) = 0;
+    virtual int get_field_async(int id, void* host, int64_t count) = 0;
+    virtual int step_async(double dt, int64_t n) = 0;
+    virtual int sync_all() = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     double time = 0.0;   // holds an NF value
@@ -76,21 +80,30 @@ struct Handle : HandleBase {
     NF *Sx = nullptr, *Wt = nullptr, *gWt = nullptr;
     NF* land2d[10] = {nullptr};   // Ts, G, SWup, LWup, Rnet, Hs, Hl, Egnd, infil, runoff
     struct Input { int kind = TRM_SRC_CONST; double cval = 0, period = 1, lo = -INFINITY, hi = INFINITY; int nt = 0;
-                   NF *a = nullptr, *b = nullptr, *c = nullptr; double* times = nullptr; };
+                   NF *a = nullptr, *b = nullptr, *c = nullptr; double* times = nullptr;
+                   // asynchronous per-column field inputs are double buffered: `a` is what enqueued steps read,
+                   // `a2` receives the next upload; ev_free[i] fires when buffer i is no longer read by any step
+                   NF* a2 = nullptr; cudaEvent_t ev_free[2] = {nullptr, nullptr}; cudaEvent_t ev_ready = nullptr; int front = 0; };
     Input in[TRM_IN_COUNT];
     bool initialized = false;
     bool aux_stale = true;   // stored T / liq / psi are not closure(U, sat): the next stage must read them
     bool force_load = false; // tuning knob (env TRM_FORCE_LOAD_AUX=1): always read T / liq / psi instead of recomputing them
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the asynchronous entry points
+    cudaEvent_t ev_staged = nullptr, ev_out_done = nullptr;
+    NF* staging = nullptr; size_t staging_count = 0;
+    bool timing_open = false;
     double* diag_partial = nullptr; double* diag_out = nullptr; int diag_blocks = 0;
 
     ~Handle() override {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         for (void* q : allocs) cudaFree(q);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        if (stream) cudaStreamDestroy(stream);
+        if (s_in) cudaStreamSynchronize(s_in);
+        if (s_out) cudaStreamSynchronize(s_out);
+        for (cudaEvent_t e : {ev0, ev1, ev_staged, ev_out_done}) if (e) cudaEventDestroy(e);
+        for (Input& s : in) for (cudaEvent_t e : {s.ev_free[0], s.ev_free[1], s.ev_ready}) if (e) cudaEventDestroy(e);
+        for (cudaStream_t s : {stream, s_in, s_out}) if (s) cudaStreamDestroy(s);
     }
 
     template <class X> int dalloc(X** out, size_t count, bool zero = true) {
@@ -326,6 +339,11 @@ struct Handle : HandleBase {
         return TRM_OK;
     }
     int launch_tile(const StageArgs<NF>& a, int load_aux);
+    int enqueue_steps(double dt, int64_t n);
+    int set_input_field_async(int id, const void* v) override;
+    int get_field_async(int id, void* host, int64_t count) override;
+    int step_async(double dt, int64_t n) override;
+    int sync_all() override;
 };
 
 template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
@@ -378,7 +396,7 @@ template <class NF> int Handle<NF>::initialize() {
     return TRM_OK;
 }
 
-template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
+template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
     if (!initialized) return fail(TRM_ERR_STATE, "trm_step before trm_initialize");
     if (n < 0) return fail(TRM_ERR_INVALID, "nsteps < 0");
     CU(cudaSetDevice(device));
@@ -410,10 +428,85 @@ template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
         time = (double)t1; iteration += 1;
     }
     CU(cudaEventRecord(ev1, stream));
+    timing_open = true;
+    return TRM_OK;
+}
+
+template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
+    if (int rc = enqueue_steps(dt_, n)) return rc;
     CU(cudaEventSynchronize(ev1));
     CU(cudaEventElapsedTime(&last_ms, ev0, ev1));
+    timing_open = false;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("trm_step: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+
+template <class NF> int Handle<NF>::step_async(double dt_, int64_t n) { return enqueue_steps(dt_, n); }
+
+template <class NF> int Handle<NF>::sync_all() {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamSynchronize(stream));
+    if (s_in) CU(cudaStreamSynchronize(s_in));
+    if (s_out) CU(cudaStreamSynchronize(s_out));
+    if (timing_open) { CU(cudaEventElapsedTime(&last_ms, ev0, ev1)); timing_open = false; }
+    return TRM_OK;
+}
+
+// Upload of a per-column input overlapped with the steps already enqueued: the copy goes to the back buffer on
+// the copy-in stream; steps enqueued after this call wait for it and read the new buffer.
+template <class NF> int Handle<NF>::set_input_field_async(int id, const void* v) {
+    CU(cudaSetDevice(device));
+    Input& s = in[id];
+    if (s.kind == TRM_SRC_TABLE || s.kind == TRM_SRC_SINUSOID) return fail(TRM_ERR_STATE, "set_input_field_async: input is not a per-column field");
+    if (!s_in) CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    if (int rc = ensure(&s.a, ld)) return rc;
+    if (int rc = ensure(&s.a2, ld)) return rc;
+    if (!s.ev_ready) {
+        CU(cudaEventCreateWithFlags(&s.ev_ready, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&s.ev_free[i], cudaEventDisableTiming));
+        CU(cudaStreamSynchronize(stream));   // the ensure() memsets above
+    }
+    // every step that reads the current front buffer has been enqueued: mark the point where it becomes free
+    CU(cudaEventRecord(s.ev_free[s.front], stream));
+    const int back = 1 - s.front;
+    CU(cudaStreamWaitEvent(s_in, s.ev_free[back], 0));   // (never recorded yet == already complete)
+    NF* dst = s.a2;
+    CU(cudaMemcpyAsync(dst, v, nc * sizeof(NF), cudaMemcpyHostToDevice, s_in));
+    CU(cudaEventRecord(s.ev_ready, s_in));
+    CU(cudaStreamWaitEvent(stream, s.ev_ready, 0));
+    std::swap(s.a, s.a2);   // `a` is what base_args hands to the kernels
+    s.front = back;
+    s.kind = TRM_SRC_FIELD;
+    return TRM_OK;
+}
+
+// Download of a field overlapped with later steps: snapshot on the compute stream (device to device), then
+// device to host on the copy-out stream.
+template <class NF> int Handle<NF>::get_field_async(int id, void* host, int64_t count) {
+    FieldRef f = field(id);
+    if (!f.ptr) return fail(TRM_ERR_INVALID, "get_field_async: unknown field or field not defined for this model");
+    if (count != (int64_t)f.nrows * nc) return fail(TRM_ERR_INVALID, "get_field_async: wrong element count");
+    CU(cudaSetDevice(device));
+    if (!s_out) {
+        CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_out_done, cudaEventDisableTiming));
+    }
+    const size_t need = (size_t)f.nrows * ld;
+    if (need > staging_count) {
+        CU(cudaStreamSynchronize(s_out));
+        if (staging) dfree(staging);
+        staging = nullptr;
+        if (int rc = dalloc(&staging, need, false)) return rc;
+        staging_count = need;
+    }
+    CU(cudaStreamWaitEvent(stream, ev_out_done, 0));   // the previous download is done with the staging buffer
+    CU(cudaMemcpyAsync(staging, f.ptr, need * sizeof(NF), cudaMemcpyDeviceToDevice, stream));
+    CU(cudaEventRecord(ev_staged, stream));
+    CU(cudaStreamWaitEvent(s_out, ev_staged, 0));
+    CU(cudaMemcpy2DAsync(host, nc * sizeof(NF), staging, ld * sizeof(NF), nc * sizeof(NF), f.nrows, cudaMemcpyDeviceToHost, s_out));
+    CU(cudaEventRecord(ev_out_done, s_out));
     return TRM_OK;
 }
 
@@ -511,7 +604,7 @@ int trm_create(const trm_config* cfg, trm_handle** out) {
 int trm_destroy(trm_handle* h) { if (h) delete H(h); return TRM_OK; }
 int trm_sync(trm_handle* h) {
     if (!h) return fail(TRM_ERR_INVALID, "null handle");
-    CU(cudaSetDevice(H(h)->device)); CU(cudaStreamSynchronize(H(h)->stream)); return TRM_OK;
+    return H(h)->sync_all();
 }
 int trm_field_ptr(trm_handle* h, int id, void** p, int64_t* ld, int32_t* nrows) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->field_ptr(id, p, ld, nrows); }
 int trm_set_field(trm_handle* h, int id, const void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->set_field(id, host, count); }
@@ -537,6 +630,9 @@ int trm_diagnostics(trm_handle* h, trm_diag* out) { if (!h || !out) return fail(
 int trm_diagnostics_device(trm_handle* h, double** dev) { if (!h || !dev) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics(nullptr, dev); }
 int64_t trm_launch_count(trm_handle* h) { return h ? H(h)->launches : 0; }
 int trm_last_step_ms(trm_handle* h, float* ms) { if (!h || !ms) return fail(TRM_ERR_INVALID, "null argument"); *ms = H(h)->last_ms; return TRM_OK; }
+int trm_set_input_field_async(trm_handle* h, int id, const void* v) { if (!h || !v || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_field_async(id, v); }
+int trm_get_field_async(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field_async(id, host, count); }
+int trm_step_async(trm_handle* h, double dt, int64_t n) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->step_async(dt, n); }
 int trm_set_block_size(trm_handle* h, int block) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->set_block(block); }
 
 }  // extern "C"

@@ -189,13 +189,14 @@ class ModelIntegrator:
             if len(shape) == 2:
                 z = (self.grid.znodes_center() if shape[0] == self.nz else self.grid.znodes_face()).astype(np.float64)
                 try:
-                    v = np.asarray(value(x[None, :], z[:, None]), dtype=np.float64)
+                    # functions may close over per-column arrays of the *global* domain: slice to this rank's range
+                    v = self._local(np.asarray(value(x[None, :], z[:, None]), dtype=np.float64), shape)
                     v = np.broadcast_to(v, shape)
                 except Exception:
                     v = np.array([[value(xi, zi) for xi in x] for zi in z], dtype=np.float64)
             else:
                 try:
-                    v = np.broadcast_to(np.asarray(value(x), dtype=np.float64), shape)
+                    v = np.broadcast_to(self._local(np.asarray(value(x), dtype=np.float64), shape), shape)
                 except Exception:
                     v = np.array([value(xi) for xi in x], dtype=np.float64)
             return np.ascontiguousarray(v, dtype=nf)

@@ -1,0 +1,104 @@
+"""The C ABI: every symbol `include/terrarium_b200.h` declares is exported by the built library, the ctypes
+mirror has the same struct layout as the C header, and the product path fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from common import trm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "terrarium_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(trm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 25
+    lib = C.CDLL(trm.LIB_PATH)   # loading must work without a GPU: no device call at load time
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # ... and the ctypes mirror binds all of them
+    bound = {"trm_" + n for n in trm.abi.SIGNATURES}
+    assert set(names) <= bound, sorted(set(names) - bound)
+    assert lib.trm_abi_version() == trm.abi.TRM_ABI_VERSION
+
+
+def test_ctypes_layout_matches_header():
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "terrarium_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(trm_params), sizeof(trm_bc), sizeof(trm_config), sizeof(trm_diag),
+           offsetof(trm_config, z_faces), offsetof(trm_config, params), offsetof(trm_config, bc));
+    return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "layout.c"), os.path.join(d, "layout")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
+    a = trm.abi
+    want = [C.sizeof(a.trm_params), C.sizeof(a.trm_bc), C.sizeof(a.trm_config), C.sizeof(a.trm_diag),
+            a.trm_config.z_faces.offset, a.trm_config.params.offset, a.trm_config.bc.offset]
+    assert got == want
+
+
+def test_defaults_match_the_reference_package_defaults():
+    lib = trm.cuda_library()
+    p = trm.abi.trm_params()
+    lib.default_params(C.byref(p))
+    assert (p.mineral_porosity, p.K_sat, p.tau_r, p.albedo, p.emissivity) == (0.49, 1.0e-5, 3600.0, 0.3, 0.97)
+    assert list(p.kappa) == [0.57, 2.2, 0.025, 3.8, 0.25]
+    assert list(p.heatcap) == [4.2e6, 1.9e6, 1.25e3, 2.0e6, 2.5e6]
+
+
+def test_argument_validation_needs_no_device():
+    lib = trm.cuda_library()
+    cfg = trm.abi.trm_config()
+    lib.default_config(C.byref(cfg))
+    h = C.c_void_p()
+    cfg.ncol, cfg.nz = 4, 1          # nz < 2
+    assert lib.create(C.byref(cfg), C.byref(h)) == trm.abi.TRM_ERR_INVALID
+    assert b"nz" in lib.last_error()
+    cfg.nz, cfg.abi_version = 4, 99
+    assert lib.create(C.byref(cfg), C.byref(h)) == trm.abi.TRM_ERR_INVALID
+    assert lib.step(None, 1.0, 1) == trm.abi.TRM_ERR_INVALID
+
+
+def _cuda_device_present():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
+    except FileNotFoundError:
+        return False
+
+
+@pytest.mark.skipif(_cuda_device_present(), reason="a GPU is present: the no-device error path cannot be exercised")
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (TRM_ERR_NO_DEVICE), never compute on the CPU."""
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.UniformSpacing(dz=0.1, N=4), 2)
+    with pytest.raises(trm.TerrariumError) as err:
+        trm.initialize(trm.SoilModel(grid), trm.ForwardEuler())
+    assert err.value.status == trm.abi.TRM_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(err.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "terrarium.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".jl")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle_integrator" not in text and "libterrarium_oracle" not in text and "orc_" not in text, f

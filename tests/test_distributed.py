@@ -1,0 +1,55 @@
+"""Multi-rank host logic on CPU: world size 2, gloo backend, one integrator per rank over its column range.
+The engine is the CPU oracle (no GPU here); partitioning, reductions and gathers are the code under test."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NCOL, STEPS = 101, 20   # odd: ranks get 51 and 50 columns
+
+
+def _case(partition):
+    from common import make, richards_soil, synthetic_columns, trm
+    lat, lon, T0 = synthetic_columns(NCOL)
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=12), NCOL)
+    model = trm.SoilModel(grid, soil=richards_soil())
+    bcs = trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0))
+    inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z,
+             "saturation_water_ice": lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x}
+    return make("oracle", model, trm.ForwardEuler(dt=60.0), boundary_conditions=bcs, initializers=inits, partition=partition)
+
+
+def _worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from terrarium_jl_b200 import distributed as td
+    integ = _case((rank, world))
+    assert integ.ncol == (51 if rank == 0 else 50) and integ.col0 == (0 if rank == 0 else 51)
+    integ.step(60.0, STEPS)
+    diag = td.reduce_diagnostics(integ.diagnostics())
+    T = td.gather_field(integ, "temperature")
+    slowest = td.max_over_ranks(float(rank + 1))
+    if rank == 0:
+        np.savez(out, T=T, **{k: np.float64(v) for k, v in diag.items()}, slowest=slowest)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_match_one(tmp_path):
+    out = str(tmp_path / "rank0.npz")
+    mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, out), nprocs=2, join=True)
+    got = np.load(out)
+    single = _case(None)
+    single.step(60.0, STEPS)
+    d = single.diagnostics()
+    assert np.array_equal(got["T"], single.state.temperature.numpy())       # columns are independent: bit-identical
+    assert got["ncol"] == NCOL and got["nan_count"] == 0
+    assert got["water"] == pytest.approx(d["water"], rel=1e-13) and got["energy"] == pytest.approx(d["energy"], rel=1e-13)
+    assert got["t_min"] == d["t_min"] and got["t_max"] == d["t_max"]
+    assert got["slowest"] == 2.0
