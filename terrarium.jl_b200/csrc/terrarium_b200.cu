@@ -458,7 +458,7 @@ template <class NF> int Handle<NF>::sync_all() {
 template <class NF> int Handle<NF>::set_input_field_async(int id, const void* v) {
     CU(cudaSetDevice(device));
     Input& s = in[id];
-    if (s.kind == TRM_SRC_TABLE || s.kind == TRM_SRC_SINUSOID) return fail(TRM_ERR_STATE, "set_input_field_async: input is not a per-column field");
+    if (s.kind == TRM_SRC_TABLE) return fail(TRM_ERR_STATE, "set_input_field_async: input is a time series table");
     if (!s_in) CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     if (int rc = ensure(&s.a, ld)) return rc;
     if (int rc = ensure(&s.a2, ld)) return rc;

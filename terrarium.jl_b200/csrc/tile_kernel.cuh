@@ -28,7 +28,8 @@
 
 namespace trm {
 
-constexpr int TILE_COLS = 32;
+constexpr int TILE_COLS = 32;     // columns per tile = lanes of a warp
+constexpr int TILE_LD = 33;       // padded row stride of the shared-memory tiles: conflict free along columns AND along layers
 constexpr int TILE_WARPS = 8;
 constexpr int TILE_THREADS = TILE_COLS * TILE_WARPS;
 
@@ -41,13 +42,13 @@ struct TileLayout {
     static constexpr int ROWS_H = NZCAP + 2;                 // rows of a tile with z-halos
     // element offsets (units of NF) of the tiles; every tile row holds TILE_COLS columns
     static constexpr int T = 0;
-    static constexpr int KAP = T + ROWS_H * TILE_COLS;
-    static constexpr int P = KAP + ROWS_H * TILE_COLS;
-    static constexpr int KC = P + ROWS_H * TILE_COLS;        // row k = layer k, rows 0 and nz+1.. unused
-    static constexpr int U = KC + ROWS_H * TILE_COLS;        // row k-1 = layer k
-    static constexpr int S = U + NZCAP * TILE_COLS;
-    static constexpr int COL = S + NZCAP * TILE_COLS;        // 4 per-column rows: G_top / excess, infiltration, idx, flags
-    static constexpr int MET = COL + 4 * TILE_COLS;          // 6 metric arrays of NZCAP + 3
+    static constexpr int KAP = T + ROWS_H * TILE_LD;
+    static constexpr int P = KAP + ROWS_H * TILE_LD;
+    static constexpr int KC = P + ROWS_H * TILE_LD;        // row k = layer k, rows 0 and nz+1.. unused
+    static constexpr int U = KC + ROWS_H * TILE_LD;        // row k-1 = layer k
+    static constexpr int S = U + NZCAP * TILE_LD;
+    static constexpr int COL = S + NZCAP * TILE_LD;        // 4 per-column rows: G_top / excess, infiltration, idx, flags
+    static constexpr int MET = COL + 4 * TILE_LD;          // 6 metric arrays of NZCAP + 3
     static constexpr int TOTAL = MET + 6 * (NZCAP + 3);
 };
 
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
     NF* const dzf = rdzc + NZP;
     NF* const rdzf = dzf + NZP;
     NF* const col = sm + lane;                 // this thread's column inside every tile
-    int* const sIdx = reinterpret_cast<int*>(sm + L::COL + 2 * TILE_COLS);
-    int* const sFlag = reinterpret_cast<int*>(sm + L::COL + 3 * TILE_COLS);
+    int* const sIdx = reinterpret_cast<int*>(sm + L::COL + 2 * TILE_LD);
+    int* const sFlag = reinterpret_cast<int*>(sm + L::COL + 3 * TILE_LD);
 
     {   // metrics: host layout [6][nz+3] -> smem [6][NZCAP+3]
         const int nzp = nz + 3;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
         for (int j = 0; j < CH; ++j) {
             const int k = warp + 1 + TILE_WARPS * (i0 + j);
             if (k > nz) continue;
-            NF* const q = col + k * TILE_COLS;     // row k of the halo tiles; row k-1 of the U / S tiles is q - TILE_COLS
+            NF* const q = col + k * TILE_LD;     // row k of the halo tiles; row k-1 of the U / S tiles is q - TILE_LD
             const NF U = Ur[j], s = sr[j];
             NF T = Tr[j], l = lr[j], P = Pr[j];
             if (!LOAD) {
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
             }
             q[L::T] = T;
             if (RICH) q[L::P] = P;
-            q[L::U - TILE_COLS] = U;
-            q[L::S - TILE_COLS] = s;
+            q[L::U - TILE_LD] = U;
+            q[L::S - TILE_LD] = s;
             q[L::KAP] = FAST ? thermal_conductivity_fast(p, s, l) : thermal_conductivity(p, s, l);
             if (RICH) q[L::KC] = cell_conductivity<NF, FAST>(p, s, l);
         }
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
     // ---- z-halos (fill_halo_regions!) by the warps that own the boundary layers; they
     //      re-read their own shared-memory rows, so no barrier is needed before this point ----
     if (warp == 0) {           // halo below the bottom layer
-        NF* const q = col + TILE_COLS;
-        const NF T = q[L::T], s = q[L::S - TILE_COLS];
+        NF* const q = col + TILE_LD;
+        const NF T = q[L::T], s = q[L::S - TILE_LD];
         col[L::T] = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, T, bc_input(TRM_BC_TEMPERATURE_BOTTOM), dzf[1], false);
         // conductivity of the halo cell: same (sat, liq) as layer 1 when the saturation halo is a copy, else sat = 0
         // (SURVEY.md Appendix B.6), for which the liquid fraction drops out of the constituent sum
@@ -144,9 +145,9 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
         (void)s;
     }
     if (warp == ((nz - 1) & (TILE_WARPS - 1))) {   // halo above the surface (+ LandModel surface processes)
-        NF* const q = col + nz * TILE_COLS;
-        NF* const qt = q + TILE_COLS;
-        const NF T = q[L::T], s = q[L::S - TILE_COLS];
+        NF* const q = col + nz * TILE_LD;
+        NF* const qt = q + TILE_LD;
+        const NF T = q[L::T], s = q[L::S - TILE_LD];
         qt[L::T] = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, T, bc_input(TRM_BC_TEMPERATURE_TOP), dzf[nz + 1], true);
         const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
         qt[L::KAP] = copy ? q[L::KAP] : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
                 A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
                 if (!prescribed) A.Ts[c] = Ts;
             }
-            col[L::COL] = G; col[L::COL + TILE_COLS] = inf;
+            col[L::COL] = G; col[L::COL + TILE_LD] = inf;
         }
     }
     __syncthreads();
@@ -206,25 +207,25 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
     // ---- phase 2: fluxes, tendencies, explicit step ----
     auto kf_at = [&](int k) -> NF {   // face conductivity Kf[k], soil_hydrology.jl:249-276 (k is warp uniform)
         if (k <= 0 || k >= nz + 2) return NF(0);           // halo faces are never written by the reference
-        if (k == 1) return col[L::KC + TILE_COLS];
-        if (k >= nz) return col[L::KC + nz * TILE_COLS];   // Kf[Nz] = Kc[Nz], Kf[Nz+1] = Kf[Nz]
-        return Mx::mn(col[L::KC + k * TILE_COLS], col[L::KC + (k - 1) * TILE_COLS]);
+        if (k == 1) return col[L::KC + TILE_LD];
+        if (k >= nz) return col[L::KC + nz * TILE_LD];   // Kf[Nz] = Kc[Nz], Kf[Nz+1] = Kf[Nz]
+        return Mx::mn(col[L::KC + k * TILE_LD], col[L::KC + (k - 1) * TILE_LD]);
     };
     int flagged = 0;
 #pragma unroll 2
     for (int i = 0; i < R; ++i) {
         const int k = warp + 1 + TILE_WARPS * i;
         if (k > nz) break;
-        NF* const q = col + k * TILE_COLS;
-        const NF Tm = q[L::T - TILE_COLS], T0 = q[L::T], Tp = q[L::T + TILE_COLS];
-        const NF km = q[L::KAP - TILE_COLS], k0 = q[L::KAP], kp = q[L::KAP + TILE_COLS];
+        NF* const q = col + k * TILE_LD;
+        const NF Tm = q[L::T - TILE_LD], T0 = q[L::T], Tp = q[L::T + TILE_LD];
+        const NF km = q[L::KAP - TILE_LD], k0 = q[L::KAP], kp = q[L::KAP + TILE_LD];
         // diffusive_heat_flux at faces k and k+1, soil_energy.jl:134-149
         const NF qh_lo = -((k0 + km) / 2) * ((T0 - Tm) * rdzf[k]);
         const NF qh_hi = -((kp + k0) / 2) * ((Tp - T0) * rdzf[k + 1]);
         NF tU = -((qh_hi - qh_lo) * rdzc[k]);                                   // soil_energy.jl:112-131
         NF tS = NF(0);
         if (RICH) {
-            const NF Pm = q[L::P - TILE_COLS], P0 = q[L::P], Pp = q[L::P + TILE_COLS];
+            const NF Pm = q[L::P - TILE_LD], P0 = q[L::P], Pp = q[L::P + TILE_LD];
             const NF Kf_m = kf_at(k - 1), Kf_0 = kf_at(k), Kf_p = kf_at(k + 1), Kf_pp = kf_at(k + 2);
             // darcy_flux at faces k and k+1, soil_hydrology_rre.jl:119-131
             const NF g_lo = (P0 - Pm) * rdzf[k], g_hi = (Pp - P0) * rdzf[k + 1];
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
         }
         // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
         if (k == nz) {
-            if (LAND) { tU -= col[L::COL] / dzc[nz]; tS -= (-col[L::COL + TILE_COLS]) / dzc[nz]; }   // land_model.jl:56-62
+            if (LAND) { tU -= col[L::COL] / dzc[nz]; tS -= (-col[L::COL + TILE_LD]) / dzc[nz]; }   // land_model.jl:56-62
             else {
                 if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / dzc[nz];
                 if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / dzc[nz];
@@ -253,10 +254,10 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
             if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / dzc[1];
         }
         // explicit step, abstract_timestepper.jl:113-141
-        q[L::U - TILE_COLS] = q[L::U - TILE_COLS] + tU * dt;
+        q[L::U - TILE_LD] = q[L::U - TILE_LD] + tU * dt;
         if (RICH) {
-            const NF sn = q[L::S - TILE_COLS] + tS * dt;
-            q[L::S - TILE_COLS] = sn;
+            const NF sn = q[L::S - TILE_LD] + tS * dt;
+            q[L::S - TILE_LD] = sn;
             if (!(sn >= 0)) flagged |= 2;                                 // negative (or NaN): needs the downward sweep too
             else if (sn > 1) flagged |= 1;                                // over-saturated: needs the upward sweep
             else if (sn < 1) atomicMin(&sIdx[lane], k);                   // compute_water_table!: lowest unsaturated layer
@@ -268,49 +269,104 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
         if (any) {
             if (flagged) atomicOr(&sFlag[lane], flagged);
             __syncthreads();
-            const int flag = sFlag[lane];
-            if (warp == 0 && flag) {
-                // upward sweep, soil_hydrology.jl:192-199 ; the excess travels in a register instead of through
-                // sat[k+1] (same additions in the same order)
-                NF* const sS = col + L::S;
-                NF carry = NF(0);
-                int idx = nz + 1;
+            NF* const sS0 = sm + L::S;
+            if (FAST && NZCAP <= 32) {
+                // Warp-cooperative sweep: the warp walks its 4 columns, lanes = layers (the padded row stride makes
+                // the transposed access conflict free).  The upward sweep (soil_hydrology.jl:192-199) becomes a
+                // relaxation -- every over-saturated layer hands its excess to the layer above until none is left --
+                // which reaches the same profile as the serial sweep up to the rounding of regrouped additions.
+                const int k = lane + 1;
+                const NF ratio = (k < nz) ? dzc[k] * rdzc[k + 1] : NF(0);
 #pragma unroll 1
-                for (int k = 1; k <= nz - 1; ++k) {
-                    NF s = sS[(k - 1) * TILE_COLS] + carry;
-                    const NF e = Mx::mx(s - 1, NF(0));
-                    s -= e;
-                    carry = FAST ? e * dzc[k] * rdzc[k + 1] : e * dzc[k] / dzc[k + 1];
-                    sS[(k - 1) * TILE_COLS] = s;
-                    if (s < 1) idx = min(idx, k);
-                }
-                NF st = sS[(nz - 1) * TILE_COLS] + carry;
-                if (flag & 2) {
-                    // downward sweep, :201-208 (only when some layer went negative)
-                    sS[(nz - 1) * TILE_COLS] = st;
-#pragma unroll 1
-                    for (int k = nz; k >= 2; --k) {
-                        NF s = sS[(k - 1) * TILE_COLS];
-                        const NF d = jmax(-s, NF(0));
-                        sS[(k - 1) * TILE_COLS] = s + d;
-                        sS[(k - 2) * TILE_COLS] -= d * dzc[k] / dzc[k - 1];
+                for (int cc = warp * (TILE_COLS / TILE_WARPS); cc < (warp + 1) * (TILE_COLS / TILE_WARPS); ++cc) {
+                    const int flag = sFlag[cc];
+                    if (!flag) continue;
+                    NF* const colS = sS0 + cc;
+                    if (flag & 2) {
+                        // a layer went negative: serial reference sweeps (up, down, top, bottom clamp) by one lane
+                        if (lane == 0) {
+                            NF carry = NF(0);
+                            for (int kk = 1; kk <= nz - 1; ++kk) {
+                                NF v = colS[(kk - 1) * TILE_LD] + carry;
+                                const NF e = jmax(v - 1, NF(0));
+                                v -= e; carry = e * dzc[kk] / dzc[kk + 1];
+                                colS[(kk - 1) * TILE_LD] = v;
+                            }
+                            colS[(nz - 1) * TILE_LD] += carry;
+                            for (int kk = nz; kk >= 2; --kk) {
+                                NF v = colS[(kk - 1) * TILE_LD];
+                                const NF d = jmax(-v, NF(0));
+                                colS[(kk - 1) * TILE_LD] = v + d;
+                                colS[(kk - 2) * TILE_LD] -= d * dzc[kk] / dzc[kk - 1];
+                            }
+                            colS[0] = jmax(colS[0], NF(0));
+                        }
+                        __syncwarp();
                     }
-                    st = sS[(nz - 1) * TILE_COLS];
-                } else if (!FAST) {
-                    st = st + jmax(-st, NF(0));   // the downward sweep is the identity (up to the sign of zero)
-                }
-                // top excess -> surface_excess_water, :210-216
-                const NF e = Mx::mx(st - 1, NF(0));
-                st -= e;
-                sS[(nz - 1) * TILE_COLS] = st;
-                col[L::COL] = e * dzc[nz];   // G_top is dead by now: the slot carries the excess to phase 4
-                if (flag & 2) {
-                    sS[0] = jmax(sS[0], NF(0));
-                    idx = nz + 1;
+                    NF v = (k <= nz) ? colS[lane * TILE_LD] : NF(0);
+                    if (!(flag & 2)) {
 #pragma unroll 1
-                    for (int k = nz; k >= 1; --k) if (sS[(k - 1) * TILE_COLS] < 1) idx = k;
-                } else if (st < 1) idx = min(idx, nz);
-                sIdx[lane] = idx;
+                        for (;;) {
+                            const NF e = (k < nz && v > 1) ? v - 1 : NF(0);
+                            if (!__any_sync(0xffffffffu, e > 0)) break;
+                            v -= e;
+                            NF recv = __shfl_up_sync(0xffffffffu, e * ratio, 1);
+                            if (lane == 0) recv = NF(0);
+                            v += recv;
+                        }
+                    }
+                    // top excess -> surface_excess_water, :210-216
+                    NF ex = NF(0);
+                    if (k == nz) { ex = Mx::mx(v - 1, NF(0)); v -= ex; sm[L::COL + cc] = ex * dzc[nz]; }   // G_top slot is dead by now
+                    if (k <= nz) colS[lane * TILE_LD] = v;
+                    const unsigned below = __ballot_sync(0xffffffffu, k <= nz && v < 1);
+                    if (lane == 0) sIdx[cc] = below ? __ffs(below) : nz + 1;   // compute_water_table!
+                }
+            } else {
+                const int flag = sFlag[lane];
+                if (warp == 0 && flag) {
+                    // serial sweeps, one lane per column ; the excess travels in a register instead of through
+                    // sat[k+1] (same additions in the same order as soil_hydrology.jl:192-199)
+                    NF* const sS = col + L::S;
+                    NF carry = NF(0);
+                    int idx = nz + 1;
+#pragma unroll 1
+                    for (int k = 1; k <= nz - 1; ++k) {
+                        NF v = sS[(k - 1) * TILE_LD] + carry;
+                        const NF e = Mx::mx(v - 1, NF(0));
+                        v -= e;
+                        carry = FAST ? e * dzc[k] * rdzc[k + 1] : e * dzc[k] / dzc[k + 1];
+                        sS[(k - 1) * TILE_LD] = v;
+                        if (v < 1) idx = min(idx, k);
+                    }
+                    NF st = sS[(nz - 1) * TILE_LD] + carry;
+                    if (flag & 2) {
+                        // downward sweep, :201-208 (only when some layer went negative)
+                        sS[(nz - 1) * TILE_LD] = st;
+#pragma unroll 1
+                        for (int k = nz; k >= 2; --k) {
+                            NF v = sS[(k - 1) * TILE_LD];
+                            const NF d = jmax(-v, NF(0));
+                            sS[(k - 1) * TILE_LD] = v + d;
+                            sS[(k - 2) * TILE_LD] -= d * dzc[k] / dzc[k - 1];
+                        }
+                        st = sS[(nz - 1) * TILE_LD];
+                    } else if (!FAST) {
+                        st = st + jmax(-st, NF(0));   // the downward sweep is the identity (up to the sign of zero)
+                    }
+                    // top excess -> surface_excess_water, :210-216
+                    const NF e = Mx::mx(st - 1, NF(0));
+                    st -= e;
+                    sS[(nz - 1) * TILE_LD] = st;
+                    col[L::COL] = e * dzc[nz];   // G_top is dead by now: the slot carries the excess to phase 4
+                    if (flag & 2) {
+                        sS[0] = jmax(sS[0], NF(0));
+                        idx = nz + 1;
+#pragma unroll 1
+                        for (int k = nz; k >= 1; --k) if (sS[(k - 1) * TILE_LD] < 1) idx = k;
+                    } else if (st < 1) idx = min(idx, nz);
+                    sIdx[lane] = idx;
+                }
             }
             __syncthreads();
         }
@@ -331,8 +387,8 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
     for (int i = 0; i < R; ++i) {
         const int k = warp + 1 + TILE_WARPS * i;
         if (k > nz) break;
-        NF* const q = col + k * TILE_COLS;
-        const NF Un = q[L::U - TILE_COLS], sn = q[L::S - TILE_COLS];
+        NF* const q = col + k * TILE_LD;
+        const NF Un = q[L::U - TILE_LD], sn = q[L::S - TILE_LD];
         NF Tn, ln;
         energy_to_temperature<NF, FAST>(p, Un, sn, Tn, ln);
         NF Pn = NF(0);
