@@ -135,17 +135,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def cpu_reference(ncol_sample, steps, warmup, nf):
-    """Restated reference CPU path (C++/OpenMP oracle in reference-structured mode) on the host cores."""
+def cpu_reference(ncol_sample, steps, warmup, nf, budget_s=None):
+    """Restated reference CPU path (C++/OpenMP oracle in reference-structured mode) on the host cores.
+    With `budget_s` the step count is chosen from a 2-step probe so that the timed sample takes about that long."""
     import oracle_integrator as oi
     import terrarium_jl_b200 as trm
     integ, _, _ = build_case(trm, oi.oracle_initialize, ncol_sample, 0, 1, 0, nf, "faithful")
     cores = int(oi.oracle_library().cdll.orc_num_threads())
-    integ.step(DT, warmup)
+    integ.step(DT, max(warmup, 1))
+    if budget_s is not None:
+        t0 = time.perf_counter()
+        integ.step(DT, 2)
+        per_step = (time.perf_counter() - t0) / 2
+        steps = int(min(max(budget_s / max(per_step, 1e-6), 3), 400))
     t0 = time.perf_counter()
     integ.step(DT, steps)
     el = time.perf_counter() - t0
-    return ncol_sample * NZ * steps / el, el, cores
+    return ncol_sample * NZ * steps / el, el, cores, steps
 
 
 def main():
@@ -158,7 +164,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--math", default="fast", choices=["fast", "faithful"])
     ap.add_argument("--block", type=int, default=0, help="threads per block of the stage kernel (0 = library default)")
-    ap.add_argument("--cpu-columns", type=int, default=262144, help="columns of the bounded CPU sample")
+    ap.add_argument("--cpu-columns", type=int, default=1048576, help="columns of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -173,7 +179,7 @@ def main():
             return 0
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         ncs = args.cpu_columns
-        v, el, cores = cpu_reference(ncs, args.steps, args.warmup, nf)
+        v, el, cores, _ = cpu_reference(ncs, args.steps, args.warmup, nf)
         line = {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -286,9 +292,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         try:
-            v, el, cores = cpu_reference(args.cpu_columns, 10, 1, nf)
+            v, el, cores, nst = cpu_reference(args.cpu_columns, 10, 1, nf, budget_s=12.0)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{args.cpu_columns} columns x {NZ} layers x 10 steps of the same workload ({el:.1f} s)"}
+                            "sample": f"{args.cpu_columns} columns x {NZ} layers x {nst} steps of the same workload ({el:.1f} s); restated "
+                                      "reference CPU path (C++/OpenMP oracle, one loop nest per reference kernel), all host cores"}
         except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU number
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
 
