@@ -24,7 +24,8 @@ struct DevParams {
     NF Ksat, vg_alpha, vg_n, bc_psis, bc_lambda, theta_res, Omega, vwcf;
     NF rho_a, c_a, Llg, Tref, sigma, eps_mw, albedo, emis, kappa_skin, C_h, Vmin, tau_r, beta;
     // derived constants used by FAST math only
-    NF rpor, neg_inv_alpha, vg_k_exp1, vg_k_exp2, vg_inv_m_neg, vg_inv_n, hc_solid, sqk_solid, r_thspan;
+    NF rpor, neg_inv_alpha, vg_k_exp1, vg_k_exp2, vg_inv_m_neg, vg_inv_n, r_thspan, se_off;
+    NF hc_wi, hc_ia, hc_base, sqk_wi, sqk_ia, sqk_base;   // regrouped constituent sums (see energy_to_temperature)
     int32_t swrc, unsat_k, sat_halo, skin;
     int32_t vg_n_is_2;
 };
@@ -57,6 +58,8 @@ __device__ __forceinline__ float  texp10(float a)  { return exp10f(a); }
 __device__ __forceinline__ double texp10(double a) { return exp10(a); }
 __device__ __forceinline__ float  tabs(float a)   { return fabsf(a); }
 __device__ __forceinline__ double tabs(double a)  { return fabs(a); }
+__device__ __forceinline__ float  fma_(float a, float b, float c)    { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 
 
 // ---- math policy -------------------------------------------------------------------------------
@@ -141,11 +144,10 @@ __device__ __forceinline__ NF thermal_conductivity(const DevParams<NF>& p, NF sa
     NF s = p.sqk[0] * f.water + p.sqk[1] * f.ice + p.sqk[2] * f.air + p.sqk[3] * f.mineral + p.sqk[4] * f.organic;
     return s * s;
 }
-// same sum with the constant solid part folded (fast math only)
+// same sum regrouped as wi (liq (k_w - k_i) + (k_i - k_a)) + (k_a por + solid part), k = sqrt(kappa) (fast math only)
 template <class NF>
 __device__ __forceinline__ NF thermal_conductivity_fast(const DevParams<NF>& p, NF sat, NF liq) {
-    NF wi = sat * p.por, water = wi * liq;
-    NF s = p.sqk[0] * water + p.sqk[1] * (wi - water) + p.sqk[2] * (p.por - wi) + p.sqk_solid;
+    const NF s = fma_(sat * p.por, fma_(liq, p.sqk_wi, p.sqk_ia), p.sqk_base);
     return s * s;
 }
 
@@ -156,22 +158,26 @@ __device__ __forceinline__ NF heat_capacity(const DevParams<NF>& p, NF sat, NF l
     return p.hc[0] * f.water + p.hc[1] * f.ice + p.hc[2] * f.air + p.hc[3] * f.mineral + p.hc[4] * f.organic;
 }
 
+// liquid fraction inside the phase change zone -L theta <= U < 0 (soil_energy_closures.jl:139-159); out of line:
+// it is rare, and inlined it would be if-converted into predicated instructions that every cell pays for
+template <class NF>
+__device__ __noinline__ NF partial_liquid_fraction_cold(NF U, NF Lt) { return 1 - U / (Lim<NF>::eps() - Lt); }
+
 // energy_to_temperature + liquid_water_fraction (free water freeze curve),
 // soil_energy_closures.jl:99-159 ; safediv utils/utils.jl:25 ; Bool * x is a strong zero.
 template <class NF, bool FAST>
 __device__ __forceinline__ void energy_to_temperature(const DevParams<NF>& p, NF U, NF sat, NF& T, NF& liq) {
     if (FAST) {
-        // same three regimes with selects; only the (rare) phase change zone branches. C from the
-        // constituent sums with the solid part precomputed, one reciprocal.
+        // same three regimes with selects; only the (rare) phase change zone takes a branch (out of line).
+        // C = sum_i c_i theta_i regrouped as wi (liq (c_w - c_i) + (c_i - c_a)) + (c_a por + solid part).
         const NF wi = sat * p.por;
         const NF Lt = p.L * wi;
         const bool thawed = U >= 0, frozen = U < -Lt;
         const NF num = thawed ? U : (frozen ? U + Lt : NF(0));
         liq = thawed ? NF(1) : NF(0);
-        if (!thawed && !frozen) liq = 1 - M<NF, FAST>::div(U, Lim<NF>::eps() - Lt);
-        const NF water = wi * liq;
-        const NF C = p.hc[0] * water + p.hc[1] * (wi - water) + p.hc[2] * (p.por - wi) + p.hc_solid;
-        T = M<NF, FAST>::div(num, C);
+        if (!thawed && !frozen) liq = partial_liquid_fraction_cold(U, Lt);
+        const NF C = fma_(wi, fma_(liq, p.hc_wi, p.hc_ia), p.hc_base);
+        T = num * M<NF, FAST>::rcp(C);
         return;
     }
     NF Lt = p.L * sat * p.por;
@@ -261,7 +267,7 @@ __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF 
         if (p.swrc != TRM_SWRC_VANGENUCHTEN || !p.vg_n_is_2) return swrc_inverse_cold(p, theta, thsat);
         if (!(theta < thsat)) return NF(0);
         // m = 1/2: psi_m = -(1/alpha) sqrt(se^-2 - 1) ; se = 0 (dry layer) is -Inf as in the reference
-        const NF se = (theta - p.theta_res) * p.r_thspan;
+        const NF se = fma_(theta, p.r_thspan, p.se_off);   // (theta - theta_res) / (theta_sat - theta_res)
         const NF t = se * se;
         if (t == NF(0)) return -Lim<NF>::inf();
         return p.neg_inv_alpha * M<NF, FAST>::sqrt_(tabs(M<NF, FAST>::rcp(t) - NF(1)));   // |.|: rounding guard as se -> 1
@@ -269,11 +275,10 @@ __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF 
     return swrc_inverse_reference(p, theta, thsat);
 }
 
-// total pressure head, saturation_to_pressure! soil_hydraulic_closures.jl:102-129
+// total pressure head, saturation_to_pressure! soil_hydraulic_closures.jl:102-129 ; psiz = zc - zref
 template <class NF, bool FAST>
-__device__ __forceinline__ NF pressure_head(const DevParams<NF>& p, NF sat, NF wt, NF zc, NF zref) {
+__device__ __forceinline__ NF pressure_head(const DevParams<NF>& p, NF sat, NF wt, NF zc, NF psiz) {
     NF psim = swrc_inverse<NF, FAST>(p, sat * p.por, p.por);
-    NF psiz = zc - zref;
     NF psih = M<NF, FAST>::mx(NF(0), wt - zc);
     return psih + psim + psiz;
 }

@@ -12,7 +12,7 @@ template <class NF, int PHYS>
 cudaError_t launch_phys(int variant, const StageArgs<NF>& a, int block, cudaStream_t st) {
     const int64_t nblk = (a.ncol + block - 1) / block;
     dim3 grid((unsigned)nblk), blk((unsigned)block);
-    size_t smem = sizeof(NF) * 6 * (size_t)(a.nz + 3);
+    size_t smem = sizeof(NF) * MET_COUNT * MET_STRIDE;
     switch (variant) {
         case VAR_EULER_RECOMPUTE: stage_kernel<NF, PHYS, MODE_EULER, 0, kFast><<<grid, blk, smem, st>>>(a); break;
         case VAR_EULER_LOAD:      stage_kernel<NF, PHYS, MODE_EULER, 1, kFast><<<grid, blk, smem, st>>>(a); break;

@@ -36,6 +36,28 @@ namespace trm {
 enum StageMode { MODE_EULER = 0, MODE_HEUN1 = 1, MODE_HEUN2 = 2, MODE_TEND = 3, MODE_AUX = 4 };
 enum Phys { PHYS_NOFLOW = 0, PHYS_RICHARDS = 1, PHYS_LAND = 2 };
 
+// Grid metrics (reference 1-based layer / face indices + halos), one row of MET_STRIDE values per quantity.
+// The fixed stride lets the kernels address `quantity[k]` as (k-dependent register) + immediate.
+constexpr int MET_STRIDE = TRM_MAX_NZ + 3;
+enum Metric { MET_ZF = 0, MET_ZC = 1, MET_DZC = 2, MET_RDZC = 3, MET_DZF = 4, MET_RDZF = 5, MET_PSIZ = 6 /* zC - zF[nz+1] */, MET_COUNT = 7 };
+
+// Shared-memory reads through an explicit 32-bit shared address: the generic-pointer form makes the compiler
+// rebuild the shared window base (S2R SR_CgaCtaId + LEA) in front of every access when registers are tight.
+__device__ __forceinline__ float  lds(uint32_t a, float*)  { float v;  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds(uint32_t a, double*) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+template <class NF>
+struct Metrics {
+    uint32_t base;   // shared address of the metric table
+    __device__ __forceinline__ NF get(int q, int k) const { return lds(base + (uint32_t)((q * MET_STRIDE + k) * (int)sizeof(NF)), (NF*)nullptr); }
+    __device__ __forceinline__ NF zF(int k) const { return get(MET_ZF, k); }
+    __device__ __forceinline__ NF zC(int k) const { return get(MET_ZC, k); }
+    __device__ __forceinline__ NF dzc(int k) const { return get(MET_DZC, k); }
+    __device__ __forceinline__ NF rdzc(int k) const { return get(MET_RDZC, k); }
+    __device__ __forceinline__ NF dzf(int k) const { return get(MET_DZF, k); }
+    __device__ __forceinline__ NF rdzf(int k) const { return get(MET_RDZF, k); }
+    __device__ __forceinline__ NF psiz(int k) const { return get(MET_PSIZ, k); }
+};
+
 #ifndef TRM_MAX_BLOCK
 #define TRM_MAX_BLOCK 256   // largest block the stage kernel may be launched with
 #endif
@@ -72,7 +94,7 @@ struct StageArgs {
     NF* Kf;   // z-face hydraulic conductivity [nz+1][ld], written in AUX / TEND
     // LandModel 2-D fields
     NF *Ts, *G, *SWup, *LWup, *Rnet, *Hs, *Hl, *Egnd, *infil, *runoff;
-    const NF* metrics;   // [6][nz+3]: zF, zC, dzc, rdzc, dzf, rdzf (reference 1-based indices + halos)
+    const NF* metrics;   // [MET_COUNT][MET_STRIDE], see enum Metric
     DevParams<NF> p;
     trm_bc bc[TRM_BC_NSLOTS];
     InputDesc<NF> in[TRM_IN_COUNT];
@@ -166,16 +188,15 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     using Mx = M<NF, FAST>;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NF* sm = reinterpret_cast<NF*>(smem_raw);
-    const int nz = A.nz, nzp = nz + 3;
-    for (int i = threadIdx.x; i < 6 * nzp; i += blockDim.x) sm[i] = A.metrics[i];
+    const int nz = A.nz;
+    {
+        NF* sm = reinterpret_cast<NF*>(smem_raw);
+        for (int q = 0; q < MET_COUNT; ++q)
+            for (int i = threadIdx.x; i < nz + 3; i += blockDim.x) sm[q * MET_STRIDE + i] = A.metrics[q * MET_STRIDE + i];
+    }
     __syncthreads();
-    const NF* zF = sm;
-    const NF* zC = sm + nzp;
-    const NF* dzc = sm + 2 * nzp;
-    const NF* rdzc = sm + 3 * nzp;
-    const NF* dzf = sm + 4 * nzp;
-    const NF* rdzf = sm + 5 * nzp;
+    Metrics<NF> met;
+    met.base = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= A.ncol) return;
@@ -189,7 +210,6 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     const bool do_update = mode == MODE_EULER || mode == MODE_HEUN1 || mode == MODE_HEUN2;
     const bool full_closure = mode == MODE_EULER || mode == MODE_HEUN2;
     const NF dt = A.dt;
-    const NF zref = zF[nz + 1];
 
     // ---- boundary condition inputs at the times the reference evaluates them ----
     auto bc_input = [&](int slot) -> NF {
@@ -235,30 +255,31 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
         // ---- old content of `cur`: iteration m-2 ----
         const NF U2 = cur.U, s2 = cur.s, T2 = cur.T, Kf2 = cur.Kf;
         // ---- layer m ----
-        NF Tn = NF(0), ln = NF(0), Pn = NF(0), kapn = NF(0), Kcn = NF(0);
+        // (for m = nz + 2 nothing enters the window: the slots keep their old values, which nobody reads)
+        NF Tn = cur.T, ln = cur.l, Pn = cur.P, kapn = cur.kap, Kcn = cur.Kc;
         const NF Ur = cur.rU, sr = cur.rS;
         if (m <= nz) {
             if (load_aux) { Tn = cur.rT; ln = cur.rL; Pn = cur.rP; }
             else {
                 energy_to_temperature<NF, FAST>(p, Ur, sr, Tn, ln);
-                if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, zC[m], zref);
+                if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
             }
             kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
             if (need_K) Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
         } else if (m == nz + 1) {   // halo above the surface, built from layer nz (prv)
-            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, prv.T, bc_T_top, dzf[nz + 1], true);
+            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, prv.T, bc_T_top, met.dzf(nz + 1), true);
             const NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? prv.s : NF(0);
             kapn = FAST ? thermal_conductivity_fast(p, sh, prv.l) : thermal_conductivity(p, sh, prv.l);
-            if (RICH) Pn = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, prv.P, bc_input(TRM_BC_PRESSURE_TOP), dzf[nz + 1], true);
+            if (RICH) Pn = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, prv.P, bc_input(TRM_BC_PRESSURE_TOP), met.dzf(nz + 1), true);
         }
         prefetch(cur, m + 2);
         // ---- lower neighbour of layer m: layer m-1, or the halo below the bottom layer for m = 1 ----
         NF Tp = prv.T, kapp = prv.kap, Pp = prv.P;
         if (m == 1) {
-            Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, Tn, bc_input(TRM_BC_TEMPERATURE_BOTTOM), dzf[1], false);
+            Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, Tn, bc_input(TRM_BC_TEMPERATURE_BOTTOM), met.dzf(1), false);
             const NF sb0 = (RICH || p.sat_halo == TRM_HALO_COPY) ? sr : NF(0);
             kapp = FAST ? thermal_conductivity_fast(p, sb0, ln) : thermal_conductivity(p, sb0, ln);
-            if (RICH) Pp = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, Pn, bc_input(TRM_BC_PRESSURE_BOTTOM), dzf[1], false);
+            if (RICH) Pp = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, Pn, bc_input(TRM_BC_PRESSURE_BOTTOM), met.dzf(1), false);
         }
         // ---- face conductivity Kf[m], soil_hydrology.jl:249-276 ----
         NF Kfn = NF(0);
@@ -271,8 +292,8 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
         // ---- heat flux and head gradient at face m (diffusive_heat_flux, soil_energy.jl:134-149) ----
         NF qhn = NF(0), gn = NF(0);
         if (m <= nz + 1) {
-            qhn = -((kapn + kapp) / 2) * ((Tn - Tp) * rdzf[m]);
-            if (RICH) gn = (Pn - Pp) * rdzf[m];
+            qhn = -((kapn + kapp) / 2) * ((Tn - Tp) * met.rdzf(m));
+            if (RICH) gn = (Pn - Pp) * met.rdzf(m);
         }
         const NF dqhn = qhn - prv.qh;
         // ---- Darcy flux at face m-1 (darcy_flux, soil_hydrology_rre.jl:119-131) ----
@@ -324,7 +345,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                 for (int rep = 0; rep < 2; ++rep) {
                     seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
                     if (!prescribed) {
-                        Ts = T2 - G * dzc[nz] / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
+                        Ts = T2 - G * met.dzc(nz) / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
                         seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
                     }
                 }
@@ -340,10 +361,10 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             const int j = m - 2;
             const int64_t o = oout;
             oout += ld;
-            NF tU = -(prv.dqh * rdzc[j]);                                      // soil_energy.jl:112-131
+            NF tU = -(prv.dqh * met.rdzc(j));                                      // soil_energy.jl:112-131
             NF tS = NF(0);
             if (RICH) {
-                const NF dth = -((qdn - prv.qd) * rdzc[j]) + NF(0) + p.vwcf;     // soil_hydrology_rre.jl:95-117
+                const NF dth = -((qdn - prv.qd) * met.rdzc(j)) + NF(0) + p.vwcf;     // soil_hydrology_rre.jl:95-117
                 tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
             }
             if (mode == MODE_HEUN1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
@@ -353,15 +374,15 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             }
             // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
             if (j == nz) {
-                if (LAND) { tU -= G_top / dzc[nz]; tS -= (-infil_top) / dzc[nz]; }           // land_model.jl:56-62
+                if (LAND) { tU -= G_top / met.dzc(nz); tS -= (-infil_top) / met.dzc(nz); }           // land_model.jl:56-62
                 else {
-                    if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / dzc[nz];
-                    if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / dzc[nz];
+                    if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / met.dzc(nz);
+                    if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / met.dzc(nz);
                 }
             }
             if (j == 1) {
-                if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / dzc[1];
-                if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / dzc[1];
+                if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / met.dzc(1);
+                if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
             }
             if (mode == MODE_TEND) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }
 
@@ -378,7 +399,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                     if (j < nz) {
                         const NF e = Mx::mx(sn - 1, NF(0));
                         sn -= e;
-                        carry = FAST ? e * dzc[j] * rdzc[j + 1] : e * dzc[j] / dzc[j + 1];
+                        carry = FAST ? e * met.dzc(j) * met.rdzc(j + 1) : e * met.dzc(j) / met.dzc(j + 1);
                     }
                     if (sn < 0) any_neg = true;
                 }
@@ -392,11 +413,11 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                         if (j == nz) {                                   // top excess -> surface_excess_water (:210-214)
                             const NF e = Mx::mx(sn - 1, NF(0));
                             sn -= e;
-                            Sx_new += e * dzc[nz];
+                            Sx_new += e * met.dzc(nz);
                         }
                         if (!FAST && j == 1) sn = jmax(sn, NF(0));       // :216
                         A.yS[o] = sn;
-                        if (idx == 0 && sn < 1) { idx = j; wt_new = zF[j]; }   // compute_water_table!, kernel_utils.jl:7-16
+                        if (idx == 0 && sn < 1) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                     }
                     A.yU[o] = Un;
                     if (full_closure) {
@@ -404,7 +425,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                         energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
                         A.yT[o] = Tc; A.yL[o] = lc;
                         // layers below the water table wait for it (written after the sweep)
-                        if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, zC[j], zref);
+                        if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j));
                     }
                 }
             }
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     if (!RICH) return;
 
     if (!any_neg) {
-        if (idx == 0) { idx = nz + 1; wt_new = zF[nz + 1]; }   // all saturated: z of the surface (halo cell / fallback give the same)
+        if (idx == 0) { idx = nz + 1; wt_new = met.zF(nz + 1); }   // all saturated: z of the surface (halo cell / fallback give the same)
         A.yWt[c] = wt_new;
         if (A.ySx) A.ySx[c] = Sx_new;
         if (full_closure) {
@@ -432,8 +453,8 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             int64_t o = c;
 #pragma unroll 1
             for (int k = 1; k < idx && k <= nz; ++k, o += ld) {
-                const NF z = zC[k];
-                A.yP[o] = Mx::mx(NF(0), wt_new - z) + psat + (z - zref);
+                const NF z = met.zC(k);
+                A.yP[o] = Mx::mx(NF(0), wt_new - z) + psat + met.psiz(k);
             }
         }
         return;
@@ -450,12 +471,12 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             if (k >= 2) {
                 const NF d = jmax(-s, NF(0));
                 s += d;
-                carry_dn = d * dzc[k] / dzc[k - 1];
+                carry_dn = d * met.dzc(k) / met.dzc(k - 1);
             }
             if (k == nz) {
                 const NF e = jmax(s - 1, NF(0));
                 s -= e;
-                Sx_new += e * dzc[nz];
+                Sx_new += e * met.dzc(nz);
             }
             if (k == 1) s = jmax(s, NF(0));
             A.yS[o] = s;
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
 #pragma unroll 1
         for (int k = 1; k <= nz; ++k) if (idx == 0 && A.yS[(int64_t)(k - 1) * ld + c] < 1) idx = k;
         if (idx == 0) idx = nz + 1;
-        wt_new = zF[idx];
+        wt_new = met.zF(idx);
         A.yWt[c] = wt_new;
         if (A.ySx) A.ySx[c] = Sx_new;
         if (full_closure) {
@@ -474,7 +495,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                 NF s = A.yS[o], U = A.yU[o], Tc, lc;
                 energy_to_temperature<NF, FAST>(p, U, s, Tc, lc);
                 A.yT[o] = Tc; A.yL[o] = lc;
-                A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, zC[k], zref);
+                A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, met.zC(k), met.psiz(k));
             }
         }
     }
@@ -488,10 +509,10 @@ __global__ void init_kernel(int64_t ncol, int64_t ld, int nz, int richards, cons
                             NF* U, NF* S, NF* T, NF* Lq, NF* P, NF* Wt, NF* Sx) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
-    const int nzp = nz + 3;
-    const NF* zF = metrics;
-    const NF* zC = metrics + nzp;
-    const NF* dzc = metrics + 2 * nzp;
+    const NF* zF = metrics + MET_ZF * MET_STRIDE;
+    const NF* zC = metrics + MET_ZC * MET_STRIDE;
+    const NF* dzc = metrics + MET_DZC * MET_STRIDE;
+    const NF* psiz = metrics + MET_PSIZ * MET_STRIDE;
     if (richards) {
         for (int k = 1; k <= nz - 1; ++k) {
             NF s = S[(int64_t)(k - 1) * ld + c];
@@ -517,11 +538,10 @@ __global__ void init_kernel(int64_t ncol, int64_t ld, int nz, int richards, cons
     if (idx == 0) idx = nz + 1;
     NF wt = zF[idx];
     Wt[c] = wt;
-    NF zref = zF[nz + 1];
     for (int k = 1; k <= nz; ++k) {
         const int64_t o = (int64_t)(k - 1) * ld + c;
         NF s = S[o];
-        if (richards) P[o] = pressure_head<NF, FAST>(p, s, wt, zC[k], zref);
+        if (richards) P[o] = pressure_head<NF, FAST>(p, s, wt, zC[k], psiz[k]);
         NF Uo, lo;
         temperature_to_energy(p, T[o], s, Uo, lo);
         U[o] = Uo; Lq[o] = lo;
@@ -533,8 +553,7 @@ template <class NF>
 __global__ void __launch_bounds__(256) diag_kernel(int64_t ncol, int64_t ld, int nz, const NF* __restrict__ metrics, NF por,
                                                    const NF* __restrict__ U, const NF* __restrict__ T, const NF* __restrict__ S,
                                                    const NF* __restrict__ Sx, double* __restrict__ partial) {
-    const int nzp = nz + 3;
-    const NF* dzc = metrics + 2 * nzp;
+    const NF* dzc = metrics + MET_DZC * MET_STRIDE;
     double e = 0, w = 0, tmin = CUDART_INF, tmax = -CUDART_INF, smin = CUDART_INF, smax = -CUDART_INF, nan = 0;
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += (int64_t)gridDim.x * blockDim.x) {
         for (int k = 1; k <= nz; ++k) {

@@ -141,14 +141,16 @@ struct Handle : HandleBase {
 
         // ---- grid metrics in NF, exactly as Oceananigans builds them from the NF faces:
         //      halo faces extend with the edge spacing, centres are face midpoints.
-        const int nzp = nz + 3;
-        std::vector<NF> m(6 * (size_t)nzp, NF(0));
-        NF *zF = m.data(), *zC = zF + nzp, *dzc = zC + nzp, *rdzc = dzc + nzp, *dzf = rdzc + nzp, *rdzf = dzf + nzp;
+        std::vector<NF> m((size_t)MET_COUNT * MET_STRIDE, NF(0));
+        NF *zF = m.data() + MET_ZF * MET_STRIDE, *zC = m.data() + MET_ZC * MET_STRIDE, *dzc = m.data() + MET_DZC * MET_STRIDE,
+           *rdzc = m.data() + MET_RDZC * MET_STRIDE, *dzf = m.data() + MET_DZF * MET_STRIDE, *rdzf = m.data() + MET_RDZF * MET_STRIDE,
+           *psiz = m.data() + MET_PSIZ * MET_STRIDE;
         for (int k = 1; k <= nz + 1; ++k) zF[k] = (NF)c.z_faces[k - 1];
         zF[0] = zF[1] - (zF[2] - zF[1]);
         zF[nz + 2] = zF[nz + 1] + (zF[nz + 1] - zF[nz]);
         for (int k = 0; k <= nz + 1; ++k) { zC[k] = (zF[k + 1] + zF[k]) / 2; dzc[k] = zF[k + 1] - zF[k]; rdzc[k] = 1 / dzc[k]; }
         for (int k = 1; k <= nz + 1; ++k) { dzf[k] = zC[k] - zC[k - 1]; rdzf[k] = 1 / dzf[k]; }
+        for (int k = 0; k <= nz + 1; ++k) psiz[k] = zC[k] - zF[nz + 1];   // elevation head relative to the surface
         if (int rc = dalloc(&metrics, m.size())) return rc;
         CU(cudaMemcpyAsync(metrics, m.data(), m.size() * sizeof(NF), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
@@ -169,8 +171,9 @@ struct Handle : HandleBase {
         p.vg_k_exp1 = p.vg_n / (p.vg_n + 1); p.vg_k_exp2 = (p.vg_n - 1) / p.vg_n;
         { NF mm = 1 - 1 / p.vg_n; p.vg_inv_m_neg = -1 / mm; p.vg_inv_n = 1 / p.vg_n; }
         { NF solid = 1 - p.por, organic = solid * p.org, mineral = solid * (1 - p.org);
-          p.hc_solid = p.hc[3] * mineral + p.hc[4] * organic; p.sqk_solid = p.sqk[3] * mineral + p.sqk[4] * organic; }
-        p.r_thspan = 1 / (p.por - p.theta_res);
+          p.hc_wi = p.hc[0] - p.hc[1]; p.hc_ia = p.hc[1] - p.hc[2]; p.hc_base = p.hc[2] * p.por + (p.hc[3] * mineral + p.hc[4] * organic);
+          p.sqk_wi = p.sqk[0] - p.sqk[1]; p.sqk_ia = p.sqk[1] - p.sqk[2]; p.sqk_base = p.sqk[2] * p.por + (p.sqk[3] * mineral + p.sqk[4] * organic); }
+        p.r_thspan = 1 / (p.por - p.theta_res); p.se_off = -p.theta_res * p.r_thspan;
         p.swrc = c.swrc; p.unsat_k = c.unsat_k; p.sat_halo = c.sat_halo; p.skin = c.skin;
         p.vg_n_is_2 = (p.vg_n == NF(2)) ? 1 : 0;
 

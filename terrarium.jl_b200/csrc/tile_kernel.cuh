@@ -49,7 +49,7 @@ struct TileLayout {
     static constexpr int S = U + NZCAP * TILE_LD;
     static constexpr int COL = S + NZCAP * TILE_LD;        // 4 per-column rows: G_top / excess, infiltration, idx, flags
     static constexpr int MET = COL + 4 * TILE_LD;          // 6 metric arrays of NZCAP + 3
-    static constexpr int TOTAL = MET + 6 * (NZCAP + 3);
+    static constexpr int TOTAL = MET + MET_COUNT * (NZCAP + 3);
 };
 
 template <class NF, int PHYS, int LOAD_CT, bool FAST, int NZCAP>
@@ -73,14 +73,14 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
     NF* const rdzc = dzc + NZP;
     NF* const dzf = rdzc + NZP;
     NF* const rdzf = dzf + NZP;
+    NF* const psiz = rdzf + NZP;
     NF* const col = sm + lane;                 // this thread's column inside every tile
     int* const sIdx = reinterpret_cast<int*>(sm + L::COL + 2 * TILE_LD);
     int* const sFlag = reinterpret_cast<int*>(sm + L::COL + 3 * TILE_LD);
 
-    {   // metrics: host layout [6][nz+3] -> smem [6][NZCAP+3]
-        const int nzp = nz + 3;
-        for (int i = threadIdx.x; i < 6 * nzp; i += TILE_THREADS) { const int a = i / nzp, j = i - a * nzp; zF[a * NZP + j] = A.metrics[i]; }
-    }
+    // metrics: host rows of MET_STRIDE -> compact smem rows of NZCAP + 3
+    for (int a = 0; a < MET_COUNT; ++a)
+        for (int j = threadIdx.x; j < nz + 3; j += TILE_THREADS) zF[a * NZP + j] = A.metrics[a * MET_STRIDE + j];
     const int64_t c0 = (int64_t)blockIdx.x * TILE_COLS + lane;
     const bool valid = c0 < A.ncol;
     const int64_t c = valid ? c0 : A.ncol - 1;   // lanes beyond the last column shadow it (loads only, never stored)
@@ -89,7 +89,6 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
     const NF dt = A.dt;
     if (warp == 0) { sIdx[lane] = nz + 1; sFlag[lane] = 0; }
     __syncthreads();
-    const NF zref = zF[nz + 1];
     const NF wtx = (RICH && !LOAD) ? A.xWt[c] : NF(0);
 
     auto bc_input = [&](int slot) -> NF {
@@ -121,7 +120,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
             NF T = Tr[j], l = lr[j], P = Pr[j];
             if (!LOAD) {
                 energy_to_temperature<NF, FAST>(p, U, s, T, l);
-                if (RICH) P = pressure_head<NF, FAST>(p, s, wtx, zC[k], zref);
+                if (RICH) P = pressure_head<NF, FAST>(p, s, wtx, zC[k], psiz[k]);
             }
             q[L::T] = T;
             if (RICH) q[L::P] = P;
@@ -392,7 +391,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (NZCAP <= 32 ? TRM_TILE_MIN_BLOC
         NF Tn, ln;
         energy_to_temperature<NF, FAST>(p, Un, sn, Tn, ln);
         NF Pn = NF(0);
-        if (RICH) Pn = pressure_head<NF, FAST>(p, sn, wt_new, zC[k], zref);
+        if (RICH) Pn = pressure_head<NF, FAST>(p, sn, wt_new, zC[k], psiz[k]);
         if (valid) {
             const int64_t o = (int64_t)(k - 1) * ld + c;
             A.yU[o] = Un; A.yT[o] = Tn; A.yL[o] = ln;
