@@ -1,0 +1,355 @@
+// euler_kernel.cuh -- ForwardEuler stage, streaming kernel with the pipeline state in shared memory.
+//
+// Same algorithm and the same per-cell arithmetic as stage_kernel (one thread = one column, one sweep
+// bottom -> top, see the header of stage_kernel.cuh for the reference functions), but the values that
+// travel between pipeline iterations (closure fields, conductivities, fluxes of the two most recent
+// layers) live in a per-thread strip of shared memory `[field][slot][thread]` instead of registers,
+// and the raw U / sat loads are prefetched by cp.async (LDGSTS) into a 4-deep shared-memory ring:
+//   * no register rotation (the register version spends ~16 % of its instructions on moves),
+//   * one copy of the loop body instead of two (half the instruction-cache footprint),
+//   * ~half the registers -> more resident warps to hide the FP64 dependency latency.
+// Shared memory is addressed through explicit 32-bit shared addresses (`row register + immediate`).
+#pragma once
+
+#include "stage_kernel.cuh"
+
+namespace trm {
+
+#ifndef TRM_EULER_BLOCK
+#define TRM_EULER_BLOCK 128     // threads per block (compile time: it is the stride of the smem strips)
+#endif
+#ifndef TRM_EULER_MIN_BLOCKS
+#define TRM_EULER_MIN_BLOCKS 6
+#endif
+
+__device__ __forceinline__ void sts(uint32_t a, float v)  { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ float  ldsv(uint32_t a, float*)  { float v;  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ double ldsv(uint32_t a, double*) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// fields of the per-thread pipeline strip (two slots each: written by iteration m, read by m+1 and m+2)
+enum EulerField { EF_U = 0, EF_S, EF_T, EF_P, EF_KAP, EF_KC, EF_KF, EF_QH, EF_G, EF_DQH, EF_QD, EF_COUNT };
+constexpr int EULER_PF = 4;   // depth of the raw prefetch ring (layers in flight: 3)
+
+constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 6 blocks per SM resident)
+
+template <class NF, int LOAD, int MS>
+struct EulerSmem {
+    static constexpr int RAW_FIELDS = LOAD ? 5 : 2;                                    // U, sat (, T, liq, psi)
+    static constexpr int METRICS = MET_COUNT * MS;                                    // elements
+    static constexpr int STRIP = EF_COUNT * 2 * TRM_EULER_BLOCK;
+    static constexpr int RING = RAW_FIELDS * EULER_PF * TRM_EULER_BLOCK;
+    static constexpr size_t BYTES = sizeof(NF) * (size_t)(METRICS + STRIP + RING);
+};
+
+template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS>
+__global__ void __launch_bounds__(TRM_EULER_BLOCK, TRM_EULER_MIN_BLOCKS) euler_kernel(const __grid_constant__ StageArgs<NF> A) {
+    constexpr bool RICH = PHYS != PHYS_NOFLOW;
+    constexpr bool LAND = PHYS == PHYS_LAND;
+    constexpr bool LOAD = LOAD_CT != 0;
+    constexpr int B = TRM_EULER_BLOCK;
+    constexpr int ES = (int)sizeof(NF);
+    using Mx = M<NF, FAST>;
+    using SM = EulerSmem<NF, LOAD_CT, MS>;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nz = A.nz;
+    {
+        NF* sm = reinterpret_cast<NF*>(smem_raw);
+        for (int q = 0; q < MET_COUNT; ++q)
+            for (int i = threadIdx.x; i < nz + 3; i += B) sm[q * MS + i] = A.metrics[q * MET_STRIDE + i];
+    }
+    __syncthreads();
+    Metrics<NF, MS> met;
+    met.base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+
+    const int64_t c = (int64_t)blockIdx.x * B + threadIdx.x;
+    if (c >= A.ncol) return;
+    const int64_t ld = A.ld;
+    const DevParams<NF>& p = A.p;
+    const NF dt = A.dt;
+
+    // shared addresses of this thread's strip: slot(m & 1) of field f is  slot_addr + f * 2 * B * ES
+    const uint32_t strip0 = met.base + (uint32_t)((SM::METRICS + threadIdx.x) * ES);
+    uint32_t a_cur = strip0 + B * ES, a_prv = strip0;   // iteration m = 1 writes slot 1 and reads slot 0 (zeros)
+    const uint32_t ring0 = met.base + (uint32_t)((SM::METRICS + SM::STRIP + threadIdx.x) * ES);
+    auto fld = [](int f) { return (uint32_t)(f * 2 * B * ES); };
+    auto rd = [&](uint32_t slot, int f) { return ldsv(slot + fld(f), (NF*)nullptr); };
+    auto wr = [&](uint32_t slot, int f, NF v) { sts(slot + fld(f), v); };
+#pragma unroll
+    for (int f = 0; f < EF_COUNT; ++f) { wr(a_cur, f, NF(0)); wr(a_prv, f, NF(0)); }
+
+    auto bc_input = [&](int slot) -> NF {
+        const int kind = A.bc[slot].kind;
+        if (kind == TRM_BC_DEFAULT) return NF(0);
+        return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x);
+    };
+    const NF wtx = (RICH && !LOAD) ? A.xWt[c] : NF(0);
+
+    // ---- raw prefetch ring: layer k lives in ring slot (k & 3); one cp.async group per layer ----
+    int64_t oin = c;
+    auto prefetch = [&](int k) {
+        if (k <= nz) {
+            const uint32_t dst = ring0 + (uint32_t)((k & (EULER_PF - 1)) * B * ES);
+            cp_async<ES>(dst, A.xU + oin);
+            cp_async<ES>(dst + EULER_PF * B * ES, A.xS + oin);
+            if (LOAD) {
+                cp_async<ES>(dst + 2 * EULER_PF * B * ES, A.xT + oin);
+                cp_async<ES>(dst + 3 * EULER_PF * B * ES, A.xL + oin);
+                if (RICH) cp_async<ES>(dst + 4 * EULER_PF * B * ES, A.xP + oin);
+            }
+            oin += ld;
+        }
+        cp_async_commit();   // (an empty group when k > nz keeps the group count in step with the iteration count)
+    };
+    prefetch(1); prefetch(2); prefetch(3);
+
+    NF carry = NF(0);          // over-saturation handed to the layer above (upward sweep of adjust_saturation_profile!)
+    bool any_neg = false;      // a negative saturation needs the downward sweep -> slow path
+    int idx = 0;               // lowest unsaturated layer (compute_water_table!), 0 = not found yet
+    NF wt_new = NF(0);
+    NF Sx_new = NF(0);
+    if (RICH) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
+    NF G_top = NF(0), infil_top = NF(0);
+    int64_t oout = c;          // element offset of layer m-2
+
+#pragma unroll 1
+    for (int m = 1; m <= nz + 2; ++m) {
+        prefetch(m + 3);
+        // ---- layer m (or the halo above the surface) enters the pipeline ----
+        NF Ur = NF(0), sr = NF(0), Tn = NF(0), Pn = NF(0), kapn = NF(0), Kcn = NF(0);
+        if (m <= nz) {
+            cp_async_wait<3>();   // all but the 3 most recent groups have landed: layer m is in the ring
+            const uint32_t src = ring0 + (uint32_t)((m & (EULER_PF - 1)) * B * ES);
+            Ur = ldsv(src, (NF*)nullptr);
+            sr = ldsv(src + EULER_PF * B * ES, (NF*)nullptr);
+            NF ln;
+            if (LOAD) {
+                Tn = ldsv(src + 2 * EULER_PF * B * ES, (NF*)nullptr);
+                ln = ldsv(src + 3 * EULER_PF * B * ES, (NF*)nullptr);
+                if (RICH) Pn = ldsv(src + 4 * EULER_PF * B * ES, (NF*)nullptr);
+            } else {
+                energy_to_temperature<NF, FAST>(p, Ur, sr, Tn, ln);
+                if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
+            }
+            kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
+            if (RICH) Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
+        } else if (m == nz + 1) {   // halo above the surface, built from layer nz (prv)
+            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(a_prv, EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
+            // conductivity of the halo cell: same (sat, liq) as layer nz when the saturation halo is a copy, else
+            // sat = 0, for which the liquid fraction drops out of the constituent sum
+            const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
+            kapn = copy ? rd(a_prv, EF_KAP) : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
+            if (RICH) Pn = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, rd(a_prv, EF_P), bc_input(TRM_BC_PRESSURE_TOP), met.dzf(nz + 1), true);
+        }
+        // ---- lower neighbour of layer m: layer m-1, or the halo below the bottom layer for m = 1 ----
+        NF Tp, kapp, Pp = NF(0);
+        if (m == 1) {
+            Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, Tn, bc_input(TRM_BC_TEMPERATURE_BOTTOM), met.dzf(1), false);
+            const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
+            kapp = copy ? kapn : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
+            if (RICH) Pp = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, Pn, bc_input(TRM_BC_PRESSURE_BOTTOM), met.dzf(1), false);
+        } else {
+            Tp = rd(a_prv, EF_T); kapp = rd(a_prv, EF_KAP);
+            if (RICH) Pp = rd(a_prv, EF_P);
+        }
+        // ---- face conductivity Kf[m], soil_hydrology.jl:249-276 ----
+        NF Kfn = NF(0), Kf1 = NF(0);   // Kf[m], Kf[m-1]
+        if (RICH) {
+            Kf1 = rd(a_prv, EF_KF);
+            if (m == 1 || m == nz) Kfn = Kcn;                   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
+            else if (m < nz) Kfn = Mx::mn(Kcn, rd(a_prv, EF_KC));
+            else if (m == nz + 1) Kfn = Kf1;                    // Kf[Nz+1] = Kf[Nz] ; Kf[Nz+2] is a halo face (0)
+        }
+        // ---- heat flux and head gradient at face m (diffusive_heat_flux, soil_energy.jl:134-149) ----
+        NF qhn = NF(0), gn = NF(0);
+        if (m <= nz + 1) {
+            qhn = -((kapn + kapp) / 2) * ((Tn - Tp) * met.rdzf(m));
+            if (RICH) gn = (Pn - Pp) * met.rdzf(m);
+        }
+        const NF dqhn = qhn - rd(a_prv, EF_QH);
+        // ---- Darcy flux at face m-1 (darcy_flux, soil_hydrology_rre.jl:119-131) ----
+        NF qdn = NF(0);
+        if (RICH && m >= 2) {
+            const NF g = rd(a_prv, EF_G);
+            const NF Kf2 = rd(a_cur, EF_KF);   // Kf[m-2] (0 for m = 2: Kf[0] is never written by the reference)
+            NF Kk;
+            if (FAST) Kk = Mx::mn(Kf1, g < 0 ? Kf2 : Kfn);
+            else Kk = (g < 0 ? jmin(Kf2, Kf1) : NF(0)) + (g >= 0 ? jmin(Kf1, Kfn) : NF(0));
+            qdn = -Kk * g;
+        }
+
+        // ---- LandModel surface processes, once the top layer is the one about to be updated ----
+        if (LAND && m == nz + 2) {
+            const NF T2 = rd(a_cur, EF_T), s2 = rd(a_cur, EF_S), Kt = rd(a_cur, EF_KF);
+            Surface<NF> a;
+            a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
+            a.LWd = eval_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
+            a.Ta = eval_input(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
+            a.pres = eval_input(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
+            a.q = eval_input(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
+            a.V = eval_input(A.in[TRM_IN_WINDSPEED], c, A.t_x);
+            a.rain = eval_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
+            const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
+            a.Tskin_in = prescribed ? eval_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
+            // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
+            NF Vc = jmax(a.V, p.Vmin);
+            double Va = fmax((double)Vc, 1.0e-6);
+            a.ra = 1.0 / ((double)p.C_h * Va);
+            NF Ts = A.Ts[c];
+            // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
+            // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
+            NF Tsurf = prescribed ? a.Tskin_in : Ts;
+            NF es = saturation_vapor_pressure(Tsurf);
+            NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
+            NF vpd = jmax(es - ea, NF(0.1));
+            NF dq = p.eps_mw * vpd / a.pres;
+            NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
+            // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall)
+            NF S = A.bSx[c];
+            NF drain, inf;
+            if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (s2 < 1) ? jmin(drain, Kt) : NF(0); }
+            else { drain = 0; inf = (s2 < 1) ? jmin(a.rain, Kt) : NF(0); }
+            NF runoff = a.rain + drain - inf;
+            // surface energy balance kernel, executed twice (land_model.jl:85-86)
+            NF swu, lwu, rnet, hs, hl, G;
+#pragma unroll 1
+            for (int rep = 0; rep < 2; ++rep) {
+                seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+                if (!prescribed) {
+                    Ts = T2 - G * met.dzc(nz) / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
+                    seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+                }
+            }
+            A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
+            A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
+            if (!prescribed) A.Ts[c] = Ts;
+            G_top = G; infil_top = inf;
+        }
+
+        if (m >= 3) {
+            // ---- tendencies of layer j = m-2 ----
+            const int j = m - 2;
+            const int64_t o = oout;
+            oout += ld;
+            NF tU = -(rd(a_prv, EF_DQH) * met.rdzc(j));                          // soil_energy.jl:112-131
+            NF tS = NF(0);
+            if (RICH) {
+                const NF dth = -((qdn - rd(a_prv, EF_QD)) * met.rdzc(j)) + NF(0) + p.vwcf;   // soil_hydrology_rre.jl:95-117
+                tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
+            }
+            // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
+            if (j == nz) {
+                if (LAND) { tU -= G_top / met.dzc(nz); tS -= (-infil_top) / met.dzc(nz); }           // land_model.jl:56-62
+                else {
+                    if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / met.dzc(nz);
+                    if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / met.dzc(nz);
+                }
+            }
+            if (j == 1) {
+                if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / met.dzc(1);
+                if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
+            }
+            // ---- explicit step, abstract_timestepper.jl:113-141 ----
+            const NF Un = rd(a_cur, EF_U) + tU * dt;
+            NF sn = rd(a_cur, EF_S);
+            if (RICH) {
+                sn = sn + tS * dt;
+                // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
+                sn = sn + carry;
+                if (j < nz) {
+                    const NF e = Mx::mx(sn - 1, NF(0));
+                    sn -= e;
+                    carry = FAST ? e * met.dzc(j) * met.rdzc(j + 1) : e * met.dzc(j) / met.dzc(j + 1);
+                }
+                if (sn < 0) any_neg = true;
+            }
+            if (RICH && any_neg) {
+                // raw values for the slow path below (the downward sweep needs the whole profile)
+                A.yU[o] = Un; A.yS[o] = sn;
+            } else {
+                if (RICH) {
+                    // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
+                    if (!FAST && j >= 2) sn = sn + jmax(-sn, NF(0));
+                    if (j == nz) {                                   // top excess -> surface_excess_water (:210-214)
+                        const NF e = Mx::mx(sn - 1, NF(0));
+                        sn -= e;
+                        Sx_new += e * met.dzc(nz);
+                    }
+                    if (!FAST && j == 1) sn = jmax(sn, NF(0));       // :216
+                    A.yS[o] = sn;
+                    if (idx == 0 && sn < 1) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
+                }
+                A.yU[o] = Un;
+                NF Tc, lc;
+                energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
+                A.yT[o] = Tc; A.yL[o] = lc;
+                // layers below the water table wait for it (written after the sweep)
+                if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j));
+            }
+        }
+        // ---- what later iterations need from this one ----
+        wr(a_cur, EF_U, Ur); wr(a_cur, EF_S, sr); wr(a_cur, EF_T, Tn); wr(a_cur, EF_KAP, kapn); wr(a_cur, EF_QH, qhn); wr(a_cur, EF_DQH, dqhn);
+        if (RICH) { wr(a_cur, EF_P, Pn); wr(a_cur, EF_KC, Kcn); wr(a_cur, EF_KF, Kfn); wr(a_cur, EF_G, gn); wr(a_cur, EF_QD, qdn); }
+        const uint32_t t = a_cur; a_cur = a_prv; a_prv = t;
+    }
+    if (!RICH) return;
+
+    if (!any_neg) {
+        if (idx == 0) { idx = nz + 1; wt_new = met.zF(nz + 1); }   // all saturated: z of the surface (halo cell / fallback give the same)
+        A.yWt[c] = wt_new;
+        A.ySx[c] = Sx_new;
+        // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
+        const NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
+        int64_t o = c;
+#pragma unroll 1
+        for (int k = 1; k < idx && k <= nz; ++k, o += ld) A.yP[o] = Mx::mx(NF(0), wt_new - met.zC(k)) + psat + met.psiz(k);
+        return;
+    }
+    // ---- slow path: a layer went negative. Downward sweep (soil_hydrology.jl:201-216) top -> bottom on the raw
+    //      profile this thread just stored, then water table and closures bottom -> top. ----
+    {
+        NF carry_dn = NF(0);
+#pragma unroll 1
+        for (int k = nz; k >= 1; --k) {
+            const int64_t o = (int64_t)(k - 1) * ld + c;
+            NF s = A.yS[o];
+            if (k < nz) s -= carry_dn;
+            if (k >= 2) {
+                const NF d = jmax(-s, NF(0));
+                s += d;
+                carry_dn = d * met.dzc(k) / met.dzc(k - 1);
+            }
+            if (k == nz) {
+                const NF e = jmax(s - 1, NF(0));
+                s -= e;
+                Sx_new += e * met.dzc(nz);
+            }
+            if (k == 1) s = jmax(s, NF(0));
+            A.yS[o] = s;
+        }
+        idx = 0;
+#pragma unroll 1
+        for (int k = 1; k <= nz; ++k) if (idx == 0 && A.yS[(int64_t)(k - 1) * ld + c] < 1) idx = k;
+        if (idx == 0) idx = nz + 1;
+        wt_new = met.zF(idx);
+        A.yWt[c] = wt_new;
+        A.ySx[c] = Sx_new;
+#pragma unroll 1
+        for (int k = 1; k <= nz; ++k) {
+            const int64_t o = (int64_t)(k - 1) * ld + c;
+            NF s = A.yS[o], U = A.yU[o], Tc, lc;
+            energy_to_temperature<NF, FAST>(p, U, s, Tc, lc);
+            A.yT[o] = Tc; A.yL[o] = lc;
+            A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, met.zC(k), met.psiz(k));
+        }
+    }
+}
+
+}  // namespace trm

@@ -16,6 +16,8 @@ struct KernelSet {
                             double* U, double* S, double* T, double* L, double* P, double* Wt, double* Sx, cudaStream_t st);
     cudaError_t (*tile_f32)(int phys, int load_aux, const StageArgs<float>& a, int threads, cudaStream_t st);
     cudaError_t (*tile_f64)(int phys, int load_aux, const StageArgs<double>& a, int threads, cudaStream_t st);
+    cudaError_t (*euler_f32)(int phys, int load_aux, const StageArgs<float>& a, int threads, cudaStream_t st);
+    cudaError_t (*euler_f64)(int phys, int load_aux, const StageArgs<double>& a, int threads, cudaStream_t st);
 };
 
 const KernelSet& kernels_faithful();   // compiled with -fmad=false, reference operation order

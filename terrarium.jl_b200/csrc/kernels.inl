@@ -2,6 +2,7 @@
 // (TRM_FAST = 0, built with -fmad=false) and kernels_fast.cu (TRM_FAST = 1).
 #include "kernel_set.h"
 #include "tile_kernel.cuh"
+#include "euler_kernel.cuh"
 
 namespace trm {
 namespace {
@@ -55,6 +56,37 @@ cudaError_t launch_tile(int phys, int load_aux, const StageArgs<NF>& a, int /*th
     }
 }
 
+// ForwardEuler stage, streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
+template <class NF, int PHYS, int LOAD, int MS>
+cudaError_t launch_euler_variant(const StageArgs<NF>& a, cudaStream_t st) {
+    constexpr size_t smem = EulerSmem<NF, LOAD, MS>::BYTES;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(euler_kernel<NF, PHYS, LOAD, kFast, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int64_t nblk = (a.ncol + TRM_EULER_BLOCK - 1) / TRM_EULER_BLOCK;
+    euler_kernel<NF, PHYS, LOAD, kFast, MS><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <class NF, int PHYS, int LOAD>
+cudaError_t launch_euler_ms(const StageArgs<NF>& a, cudaStream_t st) {
+    if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL>(a, st);
+    return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE>(a, st);
+}
+template <class NF>
+cudaError_t launch_euler(int phys, int load_aux, const StageArgs<NF>& a, int /*threads*/, cudaStream_t st) {
+    switch (phys * 2 + (load_aux ? 1 : 0)) {
+        case 0: return launch_euler_ms<NF, PHYS_NOFLOW, 0>(a, st);
+        case 1: return launch_euler_ms<NF, PHYS_NOFLOW, 1>(a, st);
+        case 2: return launch_euler_ms<NF, PHYS_RICHARDS, 0>(a, st);
+        case 3: return launch_euler_ms<NF, PHYS_RICHARDS, 1>(a, st);
+        case 4: return launch_euler_ms<NF, PHYS_LAND, 0>(a, st);
+        default: return launch_euler_ms<NF, PHYS_LAND, 1>(a, st);
+    }
+}
+
 template <class NF>
 cudaError_t launch_stage(int phys, int variant, const StageArgs<NF>& a, int block, cudaStream_t st) {
     switch (phys) {
@@ -80,7 +112,7 @@ const KernelSet& kernels_fast() {
 const KernelSet& kernels_faithful() {
 #endif
     static const KernelSet ks = {&launch_stage<float>, &launch_stage<double>, &launch_init<float>, &launch_init<double>,
-                                 &launch_tile<float>, &launch_tile<double>};
+                                 &launch_tile<float>, &launch_tile<double>, &launch_euler<float>, &launch_euler<double>};
     return ks;
 }
 

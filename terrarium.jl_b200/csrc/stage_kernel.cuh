@@ -45,10 +45,10 @@ enum Metric { MET_ZF = 0, MET_ZC = 1, MET_DZC = 2, MET_RDZC = 3, MET_DZF = 4, ME
 // rebuild the shared window base (S2R SR_CgaCtaId + LEA) in front of every access when registers are tight.
 __device__ __forceinline__ float  lds(uint32_t a, float*)  { float v;  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double lds(uint32_t a, double*) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
-template <class NF>
+template <class NF, int STRIDE = MET_STRIDE>
 struct Metrics {
-    uint32_t base;   // shared address of the metric table
-    __device__ __forceinline__ NF get(int q, int k) const { return lds(base + (uint32_t)((q * MET_STRIDE + k) * (int)sizeof(NF)), (NF*)nullptr); }
+    uint32_t base;   // shared address of the metric table (rows of STRIDE values)
+    __device__ __forceinline__ NF get(int q, int k) const { return lds(base + (uint32_t)((q * STRIDE + k) * (int)sizeof(NF)), (NF*)nullptr); }
     __device__ __forceinline__ NF zF(int k) const { return get(MET_ZF, k); }
     __device__ __forceinline__ NF zC(int k) const { return get(MET_ZC, k); }
     __device__ __forceinline__ NF dzc(int k) const { return get(MET_DZC, k); }
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
         const NF dqhn = qhn - prv.qh;
         // ---- Darcy flux at face m-1 (darcy_flux, soil_hydrology_rre.jl:119-131) ----
         NF qdn = NF(0);
-        if (RICH && m >= 2) {
+        if (RICH && m >= 2 && m <= nz + 2) {
             const NF g = prv.g;
             NF Kk;
             if (FAST) Kk = Mx::mn(prv.Kf, g < 0 ? Kf2 : Kfn);
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             }
         }
 
-        if (m >= 3 && mode != MODE_AUX) {
+        if (m >= 3 && m <= nz + 2 && mode != MODE_AUX) {
             // ---- tendencies of layer j = m-2 ----
             const int j = m - 2;
             const int64_t o = oout;

@@ -67,8 +67,11 @@ struct Handle : HandleBase {
     int phys = PHYS_NOFLOW;
     int block = 128;          // threads per block of the streaming stage kernel
     int tile_threads = 256;   // threads per block of the tile kernel (warps = layers in flight per tile)
-    bool use_tile = false;    // env TRM_KERNEL=tile: run ForwardEuler stages on the shared-memory tile kernel instead of the
-                              // streaming kernel (measured slower on B200 so far: 7.0 ms vs 5.4 ms per 10 M-column step)
+    // which implementation runs ForwardEuler stages (env TRM_KERNEL = stream | smem | tile):
+    //   0 stream: register-resident streaming kernel (stage_kernel.cuh)
+    //   1 smem:   streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
+    //   2 tile:   32-column shared-memory tiles (tile_kernel.cuh)
+    int euler_impl = 0;
     const KernelSet* ks = nullptr;
     DevParams<NF> p{};
     std::vector<void*> allocs;
@@ -124,7 +127,11 @@ struct Handle : HandleBase {
         land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
         fast = c.math == TRM_MATH_FAST;
         { const char* e = std::getenv("TRM_FORCE_LOAD_AUX"); force_load = e && e[0] == '1'; }
-        { const char* e = std::getenv("TRM_KERNEL"); use_tile = e && std::string(e) == "tile"; }
+        if (const char* e = std::getenv("TRM_KERNEL")) {
+            const std::string k(e);
+            if (k == "stream") euler_impl = 0; else if (k == "smem") euler_impl = 1; else if (k == "tile") euler_impl = 2;
+            else return fail(TRM_ERR_INVALID, "TRM_KERNEL must be stream, smem or tile");
+        }
         if (land && !richards) return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
         phys = land ? PHYS_LAND : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
         ks = fast ? &kernels_fast() : &kernels_faithful();
@@ -362,14 +369,14 @@ template <> int Handle<double>::launch(int variant, const StageArgs<double>& a) 
 
 // returns TRM_OK, an error, or -1 when the tile kernel cannot hold a column of this depth in shared memory
 template <> int Handle<float>::launch_tile(const StageArgs<float>& a, int load_aux) {
-    cudaError_t e = ks->tile_f32(phys, load_aux, a, tile_threads, stream);
+    cudaError_t e = euler_impl == 1 ? ks->euler_f32(phys, load_aux, a, 0, stream) : ks->tile_f32(phys, load_aux, a, tile_threads, stream);
     if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return -1; }
     ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("tile kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
 template <> int Handle<double>::launch_tile(const StageArgs<double>& a, int load_aux) {
-    cudaError_t e = ks->tile_f64(phys, load_aux, a, tile_threads, stream);
+    cudaError_t e = euler_impl == 1 ? ks->euler_f64(phys, load_aux, a, 0, stream) : ks->tile_f64(phys, load_aux, a, tile_threads, stream);
     if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return -1; }
     ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("tile kernel launch: ") + cudaGetErrorString(e));
@@ -413,7 +420,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
         if (!heun) {   // forward_euler.jl:19-31
             a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
             const bool load = aux_stale || force_load;
-            int rc = use_tile ? launch_tile(a, load ? 1 : 0) : -1;
+            int rc = euler_impl != 0 ? launch_tile(a, load ? 1 : 0) : -1;
             if (rc == -1) rc = launch(load ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a);
             if (rc) return rc;
         } else {       // heun.jl:37-71
