@@ -19,19 +19,22 @@ namespace trm {
 #define TRM_EULER_BLOCK 128     // threads per block (compile time: it is the stride of the smem strips)
 #endif
 #ifndef TRM_EULER_MIN_BLOCKS
-#define TRM_EULER_MIN_BLOCKS 6
+#define TRM_EULER_MIN_BLOCKS 6   // <= 80 registers per thread, 24 resident warps per SM (measured: 4 blocks 5.08 ms, 5: 4.52, 6: 4.16 per 10 M-column step)
 #endif
 
-__device__ __forceinline__ void sts(uint32_t a, float v)  { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ void sts(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ float  ldsv(uint32_t a, float*)  { float v;  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ double ldsv(uint32_t a, double*) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+// volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
+// themselves (every strip / ring location is private to one thread), while ordinary loads, stores and arithmetic
+// may be scheduled across them
+__device__ __forceinline__ void sts(uint32_t a, float v)  { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v)); }
+__device__ __forceinline__ void sts(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v)); }
+__device__ __forceinline__ float  ldsv(uint32_t a, float*)  { float v;  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double ldsv(uint32_t a, double*) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 template <int BYTES>
 __device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(dst), "l"(src), "n"(BYTES) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(dst), "l"(src), "n"(BYTES));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 
 // fields of the per-thread pipeline strip (two slots each: written by iteration m, read by m+1 and m+2)
 enum EulerField { EF_U = 0, EF_S, EF_T, EF_P, EF_KAP, EF_KC, EF_KF, EF_QH, EF_G, EF_DQH, EF_QD, EF_COUNT };
@@ -123,12 +126,13 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, TRM_EULER_MIN_BLOCKS) euler_k
     for (int m = 1; m <= nz + 2; ++m) {
         prefetch(m + 3);
         // ---- layer m (or the halo above the surface) enters the pipeline ----
-        NF Ur = NF(0), sr = NF(0), Tn = NF(0), Pn = NF(0), kapn = NF(0), Kcn = NF(0);
+        NF Tn, Pn = NF(0), kapn, Kfn = NF(0);     // T, psi, kappa of layer m ; Kf[m]
+        const NF Kf1 = RICH ? rd(a_prv, EF_KF) : NF(0);   // Kf[m-1]
         if (m <= nz) {
             cp_async_wait<3>();   // all but the 3 most recent groups have landed: layer m is in the ring
             const uint32_t src = ring0 + (uint32_t)((m & (EULER_PF - 1)) * B * ES);
-            Ur = ldsv(src, (NF*)nullptr);
-            sr = ldsv(src + EULER_PF * B * ES, (NF*)nullptr);
+            const NF Ur = ldsv(src, (NF*)nullptr);
+            const NF sr = ldsv(src + EULER_PF * B * ES, (NF*)nullptr);
             NF ln;
             if (LOAD) {
                 Tn = ldsv(src + 2 * EULER_PF * B * ES, (NF*)nullptr);
@@ -139,7 +143,12 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, TRM_EULER_MIN_BLOCKS) euler_k
                 if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
             }
             kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
-            if (RICH) Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
+            if (RICH) {
+                // cell conductivity and face conductivity Kf[m], soil_hydrology.jl:249-276
+                const NF Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
+                Kfn = (m == 1 || m == nz) ? Kcn : Mx::mn(Kcn, rd(a_prv, EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
+                wr(a_cur, EF_KC, Kcn);
+            }
         } else if (m == nz + 1) {   // halo above the surface, built from layer nz (prv)
             Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(a_prv, EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
             // conductivity of the halo cell: same (sat, liq) as layer nz when the saturation halo is a copy, else
@@ -147,6 +156,9 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, TRM_EULER_MIN_BLOCKS) euler_k
             const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
             kapn = copy ? rd(a_prv, EF_KAP) : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
             if (RICH) Pn = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, rd(a_prv, EF_P), bc_input(TRM_BC_PRESSURE_TOP), met.dzf(nz + 1), true);
+            Kfn = Kf1;              // Kf[Nz+1] = Kf[Nz] ; Kf[Nz+2] is a halo face (0)
+        } else {
+            Tn = NF(0); kapn = NF(0);
         }
         // ---- lower neighbour of layer m: layer m-1, or the halo below the bottom layer for m = 1 ----
         NF Tp, kapp, Pp = NF(0);
@@ -158,14 +170,6 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, TRM_EULER_MIN_BLOCKS) euler_k
         } else {
             Tp = rd(a_prv, EF_T); kapp = rd(a_prv, EF_KAP);
             if (RICH) Pp = rd(a_prv, EF_P);
-        }
-        // ---- face conductivity Kf[m], soil_hydrology.jl:249-276 ----
-        NF Kfn = NF(0), Kf1 = NF(0);   // Kf[m], Kf[m-1]
-        if (RICH) {
-            Kf1 = rd(a_prv, EF_KF);
-            if (m == 1 || m == nz) Kfn = Kcn;                   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
-            else if (m < nz) Kfn = Mx::mn(Kcn, rd(a_prv, EF_KC));
-            else if (m == nz + 1) Kfn = Kf1;                    // Kf[Nz+1] = Kf[Nz] ; Kf[Nz+2] is a halo face (0)
         }
         // ---- heat flux and head gradient at face m (diffusive_heat_flux, soil_energy.jl:134-149) ----
         NF qhn = NF(0), gn = NF(0);
@@ -295,8 +299,13 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, TRM_EULER_MIN_BLOCKS) euler_k
             }
         }
         // ---- what later iterations need from this one ----
-        wr(a_cur, EF_U, Ur); wr(a_cur, EF_S, sr); wr(a_cur, EF_T, Tn); wr(a_cur, EF_KAP, kapn); wr(a_cur, EF_QH, qhn); wr(a_cur, EF_DQH, dqhn);
-        if (RICH) { wr(a_cur, EF_P, Pn); wr(a_cur, EF_KC, Kcn); wr(a_cur, EF_KF, Kfn); wr(a_cur, EF_G, gn); wr(a_cur, EF_QD, qdn); }
+        if (m <= nz) {   // U and sat of layer m wait in the strip until the layer is updated (iteration m + 2)
+            const uint32_t src = ring0 + (uint32_t)((m & (EULER_PF - 1)) * B * ES);
+            wr(a_cur, EF_U, ldsv(src, (NF*)nullptr));
+            wr(a_cur, EF_S, ldsv(src + EULER_PF * B * ES, (NF*)nullptr));
+        }
+        wr(a_cur, EF_T, Tn); wr(a_cur, EF_KAP, kapn); wr(a_cur, EF_QH, qhn); wr(a_cur, EF_DQH, dqhn);
+        if (RICH) { wr(a_cur, EF_P, Pn); wr(a_cur, EF_KF, Kfn); wr(a_cur, EF_G, gn); wr(a_cur, EF_QD, qdn); }
         const uint32_t t = a_cur; a_cur = a_prv; a_prv = t;
     }
     if (!RICH) return;

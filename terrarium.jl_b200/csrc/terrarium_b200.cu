@@ -71,7 +71,7 @@ struct Handle : HandleBase {
     //   0 stream: register-resident streaming kernel (stage_kernel.cuh)
     //   1 smem:   streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
     //   2 tile:   32-column shared-memory tiles (tile_kernel.cuh)
-    int euler_impl = 0;
+    int euler_impl = 1;
     const KernelSet* ks = nullptr;
     DevParams<NF> p{};
     std::vector<void*> allocs;
