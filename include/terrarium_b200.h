@@ -299,8 +299,8 @@ int trm_set_input_field_async(trm_handle* h, int input_id, const void* pinned_ho
 int trm_step_async(trm_handle* h, double dt, int64_t nsteps);
 int trm_get_field_async(trm_handle* h, int field_id, void* pinned_host, int64_t count);
 
-/* Tuning knob: threads per block of the stage kernels (multiple of 32 in [32, 256]; default 256 for the
- * shared-memory tile kernel, capped at 128 for the streaming kernel). */
+/* Tuning knob: threads per block of the register-streaming stage kernel (multiple of 32 in [32, 128], default
+ * 128). The shared-memory staged ForwardEuler kernel has a compile-time block size. */
 int trm_set_block_size(trm_handle* h, int block);
 
 #ifdef __cplusplus

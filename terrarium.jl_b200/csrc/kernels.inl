@@ -1,7 +1,6 @@
 // kernels.inl -- instantiates the stage kernels for one math mode.  Included by kernels_faithful.cu
 // (TRM_FAST = 0, built with -fmad=false) and kernels_fast.cu (TRM_FAST = 1).
 #include "kernel_set.h"
-#include "tile_kernel.cuh"
 #include "euler_kernel.cuh"
 
 namespace trm {
@@ -20,40 +19,6 @@ cudaError_t launch_phys(int variant, const StageArgs<NF>& a, int block, cudaStre
         default:                  stage_kernel<NF, PHYS, -1, -1, kFast><<<grid, blk, smem, st>>>(a); break;
     }
     return cudaGetLastError();
-}
-
-// ForwardEuler stage as a shared-memory tile kernel (tile_kernel.cuh); returns cudaErrorInvalidConfiguration
-// when nz exceeds the largest compiled layer capacity (the caller falls back to the streaming kernel).
-template <class NF, int PHYS, int LOAD, int NZCAP>
-cudaError_t launch_tile_variant(const StageArgs<NF>& a, cudaStream_t st) {
-    constexpr size_t smem = sizeof(NF) * TileLayout<NZCAP>::TOTAL;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel<NF, PHYS, LOAD, kFast, NZCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    const int64_t nblk = (a.ncol + TILE_COLS - 1) / TILE_COLS;
-    tile_kernel<NF, PHYS, LOAD, kFast, NZCAP><<<(unsigned)nblk, TILE_THREADS, smem, st>>>(a);
-    return cudaGetLastError();
-}
-template <class NF, int PHYS, int LOAD>
-cudaError_t launch_tile_cap(const StageArgs<NF>& a, cudaStream_t st) {
-    if (a.nz <= 32) return launch_tile_variant<NF, PHYS, LOAD, 32>(a, st);
-    if (a.nz <= 64) return launch_tile_variant<NF, PHYS, LOAD, 64>(a, st);
-    if (a.nz <= 128 && sizeof(NF) * TileLayout<128>::TOTAL <= 227 * 1024) return launch_tile_variant<NF, PHYS, LOAD, 128>(a, st);
-    return cudaErrorInvalidConfiguration;
-}
-template <class NF>
-cudaError_t launch_tile(int phys, int load_aux, const StageArgs<NF>& a, int /*threads*/, cudaStream_t st) {
-    switch (phys * 2 + (load_aux ? 1 : 0)) {
-        case 0: return launch_tile_cap<NF, PHYS_NOFLOW, 0>(a, st);
-        case 1: return launch_tile_cap<NF, PHYS_NOFLOW, 1>(a, st);
-        case 2: return launch_tile_cap<NF, PHYS_RICHARDS, 0>(a, st);
-        case 3: return launch_tile_cap<NF, PHYS_RICHARDS, 1>(a, st);
-        case 4: return launch_tile_cap<NF, PHYS_LAND, 0>(a, st);
-        default: return launch_tile_cap<NF, PHYS_LAND, 1>(a, st);
-    }
 }
 
 // ForwardEuler stage, streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
@@ -76,7 +41,7 @@ cudaError_t launch_euler_ms(const StageArgs<NF>& a, cudaStream_t st) {
     return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE>(a, st);
 }
 template <class NF>
-cudaError_t launch_euler(int phys, int load_aux, const StageArgs<NF>& a, int /*threads*/, cudaStream_t st) {
+cudaError_t launch_euler(int phys, int load_aux, const StageArgs<NF>& a, cudaStream_t st) {
     switch (phys * 2 + (load_aux ? 1 : 0)) {
         case 0: return launch_euler_ms<NF, PHYS_NOFLOW, 0>(a, st);
         case 1: return launch_euler_ms<NF, PHYS_NOFLOW, 1>(a, st);
@@ -112,7 +77,7 @@ const KernelSet& kernels_fast() {
 const KernelSet& kernels_faithful() {
 #endif
     static const KernelSet ks = {&launch_stage<float>, &launch_stage<double>, &launch_init<float>, &launch_init<double>,
-                                 &launch_tile<float>, &launch_tile<double>, &launch_euler<float>, &launch_euler<double>};
+                                 &launch_euler<float>, &launch_euler<double>};
     return ks;
 }
 

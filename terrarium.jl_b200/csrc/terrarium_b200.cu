@@ -14,7 +14,6 @@
 #include <vector>
 
 #include "kernel_set.h"
-#include "tile_kernel.cuh"   // TILE_COLS / TRM_TILE_THREADS (no kernel is instantiated in this file)
 
 namespace {
 
@@ -65,12 +64,10 @@ struct Handle : HandleBase {
     int nz = 0; int64_t nc = 0, ld = 0;
     bool land = false, richards = false, heun = false, fast = false;
     int phys = PHYS_NOFLOW;
-    int block = 128;          // threads per block of the streaming stage kernel
-    int tile_threads = 256;   // threads per block of the tile kernel (warps = layers in flight per tile)
-    // which implementation runs ForwardEuler stages (env TRM_KERNEL = stream | smem | tile):
-    //   0 stream: register-resident streaming kernel (stage_kernel.cuh)
-    //   1 smem:   streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
-    //   2 tile:   32-column shared-memory tiles (tile_kernel.cuh)
+    int block = 128;          // threads per block of the register-streaming stage kernel
+    // which implementation runs ForwardEuler stages (env TRM_KERNEL = smem | stream):
+    //   1 smem:   streaming kernel with the pipeline state in shared memory (euler_kernel.cuh), the default
+    //   0 stream: register-resident streaming kernel (stage_kernel.cuh), which also serves every other mode
     int euler_impl = 1;
     const KernelSet* ks = nullptr;
     DevParams<NF> p{};
@@ -129,12 +126,9 @@ struct Handle : HandleBase {
         { const char* e = std::getenv("TRM_FORCE_LOAD_AUX"); force_load = e && e[0] == '1'; }
         if (const char* e = std::getenv("TRM_KERNEL")) {
             const std::string k(e);
-            if (k == "stream") euler_impl = 0; else if (k == "smem") euler_impl = 1; else if (k == "tile") euler_impl = 2;
-            else return fail(TRM_ERR_INVALID, "TRM_KERNEL must be stream, smem or tile");
+            if (k == "stream") euler_impl = 0; else if (k == "smem") euler_impl = 1;
+            else return fail(TRM_ERR_INVALID, "TRM_KERNEL must be smem or stream");
         }
-        if (land && !richards) return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
-        phys = land ? PHYS_LAND : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
-        ks = fast ? &kernels_fast() : &kernels_faithful();
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
             cudaGetLastError();
@@ -344,11 +338,11 @@ struct Handle : HandleBase {
     int tendencies() override;
     int diagnostics(trm_diag* out, double** dev) override;
     int set_block(int b) override {
-        if (b < 32 || b > 256 || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 256]");
-        tile_threads = b; block = b < TRM_MAX_BLOCK ? b : TRM_MAX_BLOCK;
+        if (b < 32 || b > TRM_MAX_BLOCK || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 128]");
+        block = b;
         return TRM_OK;
     }
-    int launch_tile(const StageArgs<NF>& a, int load_aux);
+    int launch_euler(const StageArgs<NF>& a, int load_aux);
     int enqueue_steps(double dt, int64_t n);
     int set_input_field_async(int id, const void* v) override;
     int get_field_async(int id, void* host, int64_t count) override;
@@ -367,19 +361,14 @@ template <> int Handle<double>::launch(int variant, const StageArgs<double>& a) 
     return TRM_OK;
 }
 
-// returns TRM_OK, an error, or -1 when the tile kernel cannot hold a column of this depth in shared memory
-template <> int Handle<float>::launch_tile(const StageArgs<float>& a, int load_aux) {
-    cudaError_t e = euler_impl == 1 ? ks->euler_f32(phys, load_aux, a, 0, stream) : ks->tile_f32(phys, load_aux, a, tile_threads, stream);
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return -1; }
-    ++launches;
-    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("tile kernel launch: ") + cudaGetErrorString(e));
+template <> int Handle<float>::launch_euler(const StageArgs<float>& a, int load_aux) {
+    cudaError_t e = ks->euler_f32(phys, load_aux, a, stream); ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
-template <> int Handle<double>::launch_tile(const StageArgs<double>& a, int load_aux) {
-    cudaError_t e = euler_impl == 1 ? ks->euler_f64(phys, load_aux, a, 0, stream) : ks->tile_f64(phys, load_aux, a, tile_threads, stream);
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return -1; }
-    ++launches;
-    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("tile kernel launch: ") + cudaGetErrorString(e));
+template <> int Handle<double>::launch_euler(const StageArgs<double>& a, int load_aux) {
+    cudaError_t e = ks->euler_f64(phys, load_aux, a, stream); ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
 
@@ -420,9 +409,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
         if (!heun) {   // forward_euler.jl:19-31
             a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
             const bool load = aux_stale || force_load;
-            int rc = euler_impl != 0 ? launch_tile(a, load ? 1 : 0) : -1;
-            if (rc == -1) rc = launch(load ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a);
-            if (rc) return rc;
+            if (int rc = euler_impl == 1 ? launch_euler(a, load ? 1 : 0) : launch(load ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a)) return rc;
         } else {       // heun.jl:37-71
             a.mode = MODE_HEUN1; a.load_aux = aux_stale ? 1 : 0; a.t_x = t; a.t_b = t; x_state(a);
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
