@@ -21,6 +21,11 @@ namespace trm {
 #ifndef TRM_EULER_MIN_BLOCKS
 #define TRM_EULER_MIN_BLOCKS 6   // <= 80 registers per thread, 24 resident warps per SM (measured: 4 blocks 5.08 ms, 5: 4.52, 6: 4.16 per 10 M-column step)
 #endif
+// Resident blocks per SM the register allocator must allow. Register spills are ruinous here (shared memory
+// leaves little L1 for local memory), so the variants that need more registers -- the LandModel surface block
+// and the faithful math mode with its inlined pow / IEEE division sequences -- get a looser bound.
+template <class NF, int PHYS, bool FAST>
+constexpr int euler_min_blocks() { return (!FAST || PHYS == PHYS_LAND) ? (sizeof(NF) == 8 ? 3 : 4) : TRM_EULER_MIN_BLOCKS; }
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
 // themselves (every strip / ring location is private to one thread), while ordinary loads, stores and arithmetic
@@ -52,7 +57,7 @@ struct EulerSmem {
 };
 
 template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS>
-__global__ void __launch_bounds__(TRM_EULER_BLOCK, TRM_EULER_MIN_BLOCKS) euler_kernel(const __grid_constant__ StageArgs<NF> A) {
+__global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, FAST>())) euler_kernel(const __grid_constant__ StageArgs<NF> A) {
     constexpr bool RICH = PHYS != PHYS_NOFLOW;
     constexpr bool LAND = PHYS == PHYS_LAND;
     constexpr bool LOAD = LOAD_CT != 0;
