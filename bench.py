@@ -285,7 +285,8 @@ def main():
     achieved = bpc * (ncol_local * NZ) / (per_launch_ms * 1e-3) / 1e9   # this rank's kernel (ranks are symmetric)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": profiled_traffic(args.dtype), "peak_source": peak_src,
-                "algorithmic_bytes_per_column_layer_step": bpc, "kernel": "trm::stage_kernel<NF, RICHARDS, EULER, recompute, fast>",
+                "algorithmic_bytes_per_column_layer_step": bpc,
+                "kernel": ("trm::stage_kernel" if os.environ.get("TRM_KERNEL") == "stream" else "trm::euler_kernel") + f"<{args.dtype}, RICHARDS, recompute, {args.math}>",
                 "launch_ms": per_launch_ms}
 
     cpu_baseline = None
