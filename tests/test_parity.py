@@ -240,3 +240,65 @@ def test_async_pipeline_matches_blocking_calls():
         assert np.array_equal(r, o.numpy())
     assert np.array_equal(a.state.internal_energy.numpy(), b.state.internal_energy.numpy())
     assert a.clock.time == b.clock.time == steps * 60.0
+
+
+# ---------------------------------------------------------------------------------------------
+# configuration coverage: every process variant / boundary condition kind / size limit of the C ABI
+# ---------------------------------------------------------------------------------------------
+def _variant_case(engine, math, *, nz, ncol, nf=np.float64, swrc="vg", unsat="vg", n=2.0, heun=False, bcs="value", kernel_dt=60.0):
+    rng = np.random.default_rng(11)
+    T0 = rng.uniform(-8.0, 12.0, ncol)
+    spacing = trm.ExponentialSpacing(dz_min=0.05, dz_max=20.0, N=nz) if nz > 2 else trm.PrescribedSpacing([0.1, 0.2])
+    grid = trm.ColumnGrid(trm.B200(), nf, spacing, ncol)
+    hp = trm.ConstantSoilHydraulics(
+        swrc=trm.VanGenuchten(alpha=2.0, n=n) if swrc == "vg" else trm.BrooksCorey(psi_s=0.05, lam=0.4),
+        unsat_hydraulic_cond=trm.UnsatKVanGenuchten() if unsat == "vg" else trm.UnsatKLinear(), sat_hydraulic_cond=2.0e-6)
+    soil = trm.SoilEnergyWaterCarbon(hydrology=trm.SoilHydrology(trm.RichardsEq(), hydraulic_properties=hp))
+    model = trm.SoilModel(grid, soil=soil)
+    if bcs == "value":
+        bc = trm.merge_boundary_conditions(trm.PrescribedSurfaceTemperature("T_ub", T0 + 3.0), trm.PrescribedBottomTemperature("T_lb", T0 - 1.0))
+    elif bcs == "flux":
+        bc = trm.merge_boundary_conditions(trm.GroundHeatFlux(-15.0 + 0 * T0), trm.GeothermalHeatFlux(0.05), trm.InfiltrationFlux(-1.0e-8))
+    else:   # gradient on the pressure head at the bottom (FreeDrainage), default elsewhere
+        bc = trm.merge_boundary_conditions(trm.FreeDrainage())
+    zc = grid.znodes_center().astype(np.float64)
+    sat0 = np.clip(0.35 + 0.5 * (zc[:, None] / zc[0]) + 0.1 * rng.uniform(-1, 1, (nz, ncol)), 0.05, 1.0)
+    inits = {"temperature": T0[None, :] - 0.02 * zc[:, None], "saturation_water_ice": sat0}
+    ts = (trm.Heun if heun else trm.ForwardEuler)(dt=kernel_dt)
+    return make(engine, model, ts, boundary_conditions=bc, initializers=inits, math=math)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nz=2, ncol=1), dict(nz=3, ncol=33), dict(nz=128, ncol=257, kernel_dt=20.0), dict(nz=64, ncol=100, heun=True, kernel_dt=20.0),
+    dict(nz=30, ncol=300, swrc="bc", unsat="lin"), dict(nz=30, ncol=300, n=1.6), dict(nz=30, ncol=300, n=3.0, heun=True),
+    dict(nz=30, ncol=300, bcs="flux"), dict(nz=30, ncol=300, bcs="flux", heun=True), dict(nz=30, ncol=300, bcs="gradient"),
+    dict(nz=30, ncol=300, nf=np.float32),
+], ids=lambda k: "-".join(f"{a}{getattr(b, '__name__', b)}" for a, b in k.items()))
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+def test_configuration_variants(math, kw):
+    """Layer counts 2 ... TRM_MAX_NZ, single / ragged column counts, Brooks-Corey + linear K, general van Genuchten n,
+    Value / Flux / Gradient boundary conditions, Heun, Float32: 200 steps against the oracle."""
+    gpu, cpu = _variant_case("cuda", math, **kw), _variant_case("oracle", math, **kw)
+    dt = kw.get("kernel_dt", 60.0)
+    gpu.step(dt, 200)
+    cpu.step(dt, 200)
+    tol = 5.0e-5 if kw.get("nf") is np.float32 else TOL
+    compare(gpu, cpu, FIELDS + ("pressure_head", "water_table", "surface_excess_water"), tol)
+    gpu.compute_auxiliary(); cpu.compute_auxiliary()
+    compare(gpu, cpu, ("hydraulic_conductivity",), tol)
+
+
+def test_handles_are_independent_and_reusable():
+    """Several handles on one device, interleaved stepping, destroy and recreate: results do not depend on it."""
+    a = synthetic_soil_case("cuda", 300, math="fast")
+    b = synthetic_soil_case("cuda", 300, math="fast")
+    c = synthetic_soil_case("cuda", 300, math="fast", heun=True)
+    for _ in range(5):
+        a.step(60.0, 3); c.step(60.0, 2); b.step(60.0, 3)
+    assert np.array_equal(a.state.internal_energy.numpy(), b.state.internal_energy.numpy())
+    a.close()
+    d = synthetic_soil_case("cuda", 300, math="fast")
+    d.step(60.0, 15)
+    assert np.array_equal(d.state.saturation_water_ice.numpy(), b.state.saturation_water_ice.numpy())
+    with pytest.raises(trm.TerrariumError):
+        d._lib.check(d._lib.step(d._h, 60.0, -1), "step")
