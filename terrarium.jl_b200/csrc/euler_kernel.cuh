@@ -11,6 +11,8 @@
 // Shared memory is addressed through explicit 32-bit shared addresses (`row register + immediate`).
 #pragma once
 
+#include <type_traits>
+
 #include "stage_kernel.cuh"
 
 namespace trm {
@@ -101,9 +103,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     const NF wtx = (RICH && !LOAD) ? A.xWt[c] : NF(0);
 
     // ---- raw prefetch ring: layer k lives in ring slot (k & 3); one cp.async group per layer ----
-    int64_t oin = c;
-    auto prefetch = [&](int k) {
-        if (k <= nz) {
+    // element offsets fit 32 bits (the launcher checks nz * ld < 2^32): one IMAD.WIDE.U32 per address
+    uint32_t oin = (uint32_t)c;
+    auto prefetch = [&](int k, bool always = false) {
+        if (always || k <= nz) {
             const uint32_t dst = ring0 + (uint32_t)((k & (EULER_PF - 1)) * B * ES);
             cp_async<ES>(dst, A.xU + oin);
             cp_async<ES>(dst + EULER_PF * B * ES, A.xS + oin);
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 cp_async<ES>(dst + 3 * EULER_PF * B * ES, A.xL + oin);
                 if (RICH) cp_async<ES>(dst + 4 * EULER_PF * B * ES, A.xP + oin);
             }
-            oin += ld;
+            oin += (uint32_t)ld;
         }
         cp_async_commit();   // (an empty group when k > nz keeps the group count in step with the iteration count)
     };
@@ -125,15 +128,18 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     NF Sx_new = NF(0);
     if (RICH) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
     NF G_top = NF(0), infil_top = NF(0);
-    int64_t oout = c;          // element offset of layer m-2
+    uint32_t oout = (uint32_t)c;   // element offset of layer m-2
 
-#pragma unroll 1
-    for (int m = 1; m <= nz + 2; ++m) {
-        prefetch(m + 3);
+    // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-3, for which every
+    // layer-index special case below is statically false / true: no halo, no boundary face, no Flux BC, the
+    // prefetched layer exists. The two instantiations share the source; the loop picks the cheap one whenever it can.
+    auto iterate = [&](const int m, auto inner_tag) {
+        constexpr bool inner = decltype(inner_tag)::value;
+        prefetch(m + 3, inner);
         // ---- layer m (or the halo above the surface) enters the pipeline ----
         NF Tn, Pn = NF(0), kapn, Kfn = NF(0);     // T, psi, kappa of layer m ; Kf[m]
         const NF Kf1 = RICH ? rd(a_prv, EF_KF) : NF(0);   // Kf[m-1]
-        if (m <= nz) {
+        if (inner || m <= nz) {
             cp_async_wait<3>();   // all but the 3 most recent groups have landed: layer m is in the ring
             const uint32_t src = ring0 + (uint32_t)((m & (EULER_PF - 1)) * B * ES);
             const NF Ur = ldsv(src, (NF*)nullptr);
@@ -151,10 +157,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             if (RICH) {
                 // cell conductivity and face conductivity Kf[m], soil_hydrology.jl:249-276
                 const NF Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
-                Kfn = (m == 1 || m == nz) ? Kcn : Mx::mn(Kcn, rd(a_prv, EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
+                Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : Mx::mn(Kcn, rd(a_prv, EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
                 wr(a_cur, EF_KC, Kcn);
             }
-        } else if (m == nz + 1) {   // halo above the surface, built from layer nz (prv)
+        } else if (!inner && m == nz + 1) {   // halo above the surface, built from layer nz (prv)
             Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(a_prv, EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
             // conductivity of the halo cell: same (sat, liq) as layer nz when the saturation halo is a copy, else
             // sat = 0, for which the liquid fraction drops out of the constituent sum
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
         // ---- lower neighbour of layer m: layer m-1, or the halo below the bottom layer for m = 1 ----
         NF Tp, kapp, Pp = NF(0);
-        if (m == 1) {
+        if (!inner && m == 1) {
             Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, Tn, bc_input(TRM_BC_TEMPERATURE_BOTTOM), met.dzf(1), false);
             const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
             kapp = copy ? kapn : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
@@ -178,14 +184,14 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
         // ---- heat flux and head gradient at face m (diffusive_heat_flux, soil_energy.jl:134-149) ----
         NF qhn = NF(0), gn = NF(0);
-        if (m <= nz + 1) {
+        if (inner || m <= nz + 1) {
             qhn = -((kapn + kapp) / 2) * ((Tn - Tp) * met.rdzf(m));
             if (RICH) gn = (Pn - Pp) * met.rdzf(m);
         }
         const NF dqhn = qhn - rd(a_prv, EF_QH);
         // ---- Darcy flux at face m-1 (darcy_flux, soil_hydrology_rre.jl:119-131) ----
         NF qdn = NF(0);
-        if (RICH && m >= 2) {
+        if (RICH && (inner || m >= 2)) {
             const NF g = rd(a_prv, EF_G);
             const NF Kf2 = rd(a_cur, EF_KF);   // Kf[m-2] (0 for m = 2: Kf[0] is never written by the reference)
             NF Kk;
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
 
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
-        if (LAND && m == nz + 2) {
+        if (LAND && !inner && m == nz + 2) {
             const NF T2 = rd(a_cur, EF_T), s2 = rd(a_cur, EF_S), Kt = rd(a_cur, EF_KF);
             Surface<NF> a;
             a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
@@ -242,11 +248,11 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             G_top = G; infil_top = inf;
         }
 
-        if (m >= 3) {
+        if (inner || m >= 3) {
             // ---- tendencies of layer j = m-2 ----
             const int j = m - 2;
-            const int64_t o = oout;
-            oout += ld;
+            const uint32_t o = oout;
+            oout += (uint32_t)ld;
             NF tU = -(rd(a_prv, EF_DQH) * met.rdzc(j));                          // soil_energy.jl:112-131
             NF tS = NF(0);
             if (RICH) {
@@ -254,14 +260,14 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
             }
             // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
-            if (j == nz) {
+            if (!inner && j == nz) {
                 if (LAND) { tU -= G_top / met.dzc(nz); tS -= (-infil_top) / met.dzc(nz); }           // land_model.jl:56-62
                 else {
                     if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / met.dzc(nz);
                     if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / met.dzc(nz);
                 }
             }
-            if (j == 1) {
+            if (!inner && j == 1) {
                 if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / met.dzc(1);
                 if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
             }
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 sn = sn + tS * dt;
                 // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
                 sn = sn + carry;
-                if (j < nz) {
+                if (inner || j < nz) {
                     const NF e = Mx::mx(sn - 1, NF(0));
                     sn -= e;
                     carry = FAST ? e * met.dzc(j) * met.rdzc(j + 1) : e * met.dzc(j) / met.dzc(j + 1);
@@ -286,12 +292,12 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (RICH) {
                     // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
                     if (!FAST && j >= 2) sn = sn + jmax(-sn, NF(0));
-                    if (j == nz) {                                   // top excess -> surface_excess_water (:210-214)
+                    if (!inner && j == nz) {                         // top excess -> surface_excess_water (:210-214)
                         const NF e = Mx::mx(sn - 1, NF(0));
                         sn -= e;
                         Sx_new += e * met.dzc(nz);
                     }
-                    if (!FAST && j == 1) sn = jmax(sn, NF(0));       // :216
+                    if (!FAST && !inner && j == 1) sn = jmax(sn, NF(0));       // :216
                     A.yS[o] = sn;
                     if (idx == 0 && sn < 1) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                 }
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             }
         }
         // ---- what later iterations need from this one ----
-        if (m <= nz) {   // U and sat of layer m wait in the strip until the layer is updated (iteration m + 2)
+        if (inner || m <= nz) {   // U and sat of layer m wait in the strip until the layer is updated (iteration m + 2)
             const uint32_t src = ring0 + (uint32_t)((m & (EULER_PF - 1)) * B * ES);
             wr(a_cur, EF_U, ldsv(src, (NF*)nullptr));
             wr(a_cur, EF_S, ldsv(src + EULER_PF * B * ES, (NF*)nullptr));
@@ -312,6 +318,19 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         wr(a_cur, EF_T, Tn); wr(a_cur, EF_KAP, kapn); wr(a_cur, EF_QH, qhn); wr(a_cur, EF_DQH, dqhn);
         if (RICH) { wr(a_cur, EF_P, Pn); wr(a_cur, EF_KF, Kfn); wr(a_cur, EF_G, gn); wr(a_cur, EF_QD, qdn); }
         const uint32_t t = a_cur; a_cur = a_prv; a_prv = t;
+    };
+    {
+        int m = 1;
+#pragma unroll 1
+        while (m <= nz + 2) {
+            if (m >= 4 && m <= nz - 3) {
+#pragma unroll 1
+                do { iterate(m, std::true_type{}); ++m; } while (m <= nz - 3);
+            } else {
+                iterate(m, std::false_type{});
+                ++m;
+            }
+        }
     }
     if (!RICH) return;
 

@@ -42,6 +42,8 @@ cudaError_t launch_euler_ms(const StageArgs<NF>& a, cudaStream_t st) {
 }
 template <class NF>
 cudaError_t launch_euler(int phys, int load_aux, const StageArgs<NF>& a, cudaStream_t st) {
+    // the kernel addresses layers with 32-bit element offsets; larger fields run the generic streaming kernel
+    if ((uint64_t)a.nz * (uint64_t)a.ld >= (1ull << 32)) return cudaErrorInvalidConfiguration;
     switch (phys * 2 + (load_aux ? 1 : 0)) {
         case 0: return launch_euler_ms<NF, PHYS_NOFLOW, 0>(a, st);
         case 1: return launch_euler_ms<NF, PHYS_NOFLOW, 1>(a, st);

@@ -365,12 +365,16 @@ template <> int Handle<double>::launch(int variant, const StageArgs<double>& a) 
 }
 
 template <> int Handle<float>::launch_euler(const StageArgs<float>& a, int load_aux) {
-    cudaError_t e = ks->euler_f32(phys, load_aux, a, stream); ++launches;
+    cudaError_t e = ks->euler_f32(phys, load_aux, a, stream);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a); }
+    ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
 template <> int Handle<double>::launch_euler(const StageArgs<double>& a, int load_aux) {
-    cudaError_t e = ks->euler_f64(phys, load_aux, a, stream); ++launches;
+    cudaError_t e = ks->euler_f64(phys, load_aux, a, stream);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a); }
+    ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
