@@ -71,11 +71,29 @@ def synthetic(ncol_global: int, c0: int, c1: int):
     return lon, T0
 
 
-def build_case(trm, make_integrator, ncol_global, rank, world, device, nf, math, forcing="sinusoid"):
+def build_case(trm, make_integrator, ncol_global, rank, world, device, nf, math, forcing="sinusoid", model_kind="soil", heun=False):
     from common import richards_soil
     grid = trm.ColumnGrid(trm.B200(device), nf, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=NZ), ncol_global)
     c0, c1 = grid.partition(rank, world)
     lon, T0 = synthetic(ncol_global, c0, c1)
+    if model_kind == "land":
+        # secondary workload (BASELINE configs[3], bare ground): synthetic atmosphere of BASELINE.md section 5 with a
+        # calm wind (see tests/test_parity.py on the stability of the as-coded skin / soil coupling at 3 m/s)
+        model = trm.LandModel(grid, soil=richards_soil())
+        day = 86400.0
+        hours = np.arange(0, 73, dtype=np.float64)
+        rain = np.where((hours % 24) < 6, 2.0e-8, 0.0)
+        inputs = {"air_temperature": trm.Sinusoid(mean=T0, amp=8.0, phase=lon, period=day),
+                  "surface_shortwave_down": trm.Sinusoid(mean=0.0, amp=600.0, phase=lon, period=day, lo=0.0),
+                  "surface_longwave_down": 300.0, "specific_humidity": 0.005, "air_pressure": 101325.0, "windspeed": 0.5,
+                  "rainfall": trm.TimeSeries(hours * 3600.0, np.repeat(rain[:, None], c1 - c0, axis=1))}
+        zc = grid.znodes_center().astype(np.float64)
+        temp = (T0[None, :] - 0.05 * zc[:, None]).astype(nf)
+        sat = np.ascontiguousarray(np.broadcast_to(np.minimum(1.0, 0.5 - 0.1 * zc)[:, None], temp.shape), dtype=nf)
+        ts = (trm.Heun if heun else trm.ForwardEuler)(dt=DT)
+        integ = make_integrator(model, ts, inputs, initializers={"temperature": temp, "saturation_water_ice": sat, "skin_temperature": T0},
+                                partition=(rank, world), math=math)
+        return integ, lon, T0
     model = trm.SoilModel(grid, soil=richards_soil())
     if forcing == "sinusoid":
         value = trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0)
@@ -86,7 +104,7 @@ def build_case(trm, make_integrator, ncol_global, rank, world, device, nf, math,
     temp = (T0[None, :] - 0.05 * zc[:, None]).astype(nf)
     sat = np.ascontiguousarray(np.broadcast_to(np.minimum(1.0, 0.5 - 0.1 * zc)[:, None], temp.shape), dtype=nf)
     # temp / sat already hold only this rank's columns
-    integ = make_integrator(model, trm.ForwardEuler(dt=DT), None, boundary_conditions=bcs,
+    integ = make_integrator(model, (trm.Heun if heun else trm.ForwardEuler)(dt=DT), None, boundary_conditions=bcs,
                             initializers={"temperature": temp, "saturation_water_ice": sat},
                             partition=(rank, world), math=math)
     return integ, lon, T0
@@ -167,6 +185,8 @@ def main():
     ap.add_argument("--cpu-columns", type=int, default=1048576, help="columns of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--model", default="soil", choices=["soil", "land"], help="secondary workloads (not the headline): bare-ground LandModel")
+    ap.add_argument("--timestepper", default="euler", choices=["euler", "heun"], help="secondary workloads: Heun (two stage launches per step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     nf = np.float64 if args.dtype == "f64" else np.float32
@@ -211,7 +231,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    integ, lon, T0 = build_case(trm, trm.initialize, args.columns, rank, world, local_rank, nf, args.math)
+    secondary = args.model != "soil" or args.timestepper != "euler"
+    if secondary:
+        args.no_e2e = True   # the end-to-end leg drives the soil model's surface temperature input
+    integ, lon, T0 = build_case(trm, trm.initialize, args.columns, rank, world, local_rank, nf, args.math,
+                                model_kind=args.model, heun=args.timestepper == "heun")
     lib, h = integ._lib, integ._h
     if args.block:
         lib.check(lib.set_block_size(h, args.block), "set_block_size")
@@ -309,6 +333,7 @@ def main():
                                    "UnsatKVanGenuchten, K_sat=1e-5), ForwardEuler dt=60 s, Nz=30 exponential grid, sinusoidal surface "
                                    "temperature evaluated on the device",
                        "columns": args.columns, "nz": NZ, "columns_per_gpu": ncol_local, "math": args.math,
+                       "model": args.model, "timestepper": args.timestepper,
                        "partition": "contiguous column ranges, no halo, no data-path collective",
                        "cache": "inputs larger than L2 (state read per step = %.1f GB per GPU)" % (2 * ncol_local * NZ * itemsize / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
