@@ -24,10 +24,10 @@ namespace trm {
 #define TRM_EULER_MIN_BLOCKS 6   // <= 80 registers per thread, 24 resident warps per SM (measured: 4 blocks 5.08 ms, 5: 4.52, 6: 4.16 per 10 M-column step)
 #endif
 // Resident blocks per SM the register allocator must allow. Register spills are ruinous here (shared memory
-// leaves little L1 for local memory), so the variants that need more registers -- the LandModel surface block
-// and the faithful math mode with its inlined pow / IEEE division sequences -- get a looser bound.
+// leaves little L1 for local memory), so the faithful math mode with its inlined pow / IEEE division sequences
+// gets a looser bound; the LandModel variant runs best with 5 blocks (measured 4: 5.9 ms, 5: 5.1 ms, 6: 6.7 ms).
 template <class NF, int PHYS, bool FAST>
-constexpr int euler_min_blocks() { return (!FAST || PHYS == PHYS_LAND) ? (sizeof(NF) == 8 ? 3 : 4) : TRM_EULER_MIN_BLOCKS; }
+constexpr int euler_min_blocks() { return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (PHYS == PHYS_LAND ? 5 : TRM_EULER_MIN_BLOCKS); }
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
 // themselves (every strip / ring location is private to one thread), while ordinary loads, stores and arithmetic
@@ -127,7 +127,6 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     NF wt_new = NF(0);
     NF Sx_new = NF(0);
     if (RICH) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
-    NF G_top = NF(0), infil_top = NF(0);
     uint32_t oout = (uint32_t)c;   // element offset of layer m-2
 
     // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-3, for which every
@@ -201,51 +200,9 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
 
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
+        NF G_top = NF(0), infil_top = NF(0);   // fluxes coupling the surface to the top soil layer (same iteration)
         if (LAND && !inner && m == nz + 2) {
-            const NF T2 = rd(a_cur, EF_T), s2 = rd(a_cur, EF_S), Kt = rd(a_cur, EF_KF);
-            Surface<NF> a;
-            a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
-            a.LWd = eval_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
-            a.Ta = eval_input(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
-            a.pres = eval_input(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
-            a.q = eval_input(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
-            a.V = eval_input(A.in[TRM_IN_WINDSPEED], c, A.t_x);
-            a.rain = eval_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
-            const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
-            a.Tskin_in = prescribed ? eval_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
-            // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
-            NF Vc = jmax(a.V, p.Vmin);
-            double Va = fmax((double)Vc, 1.0e-6);
-            a.ra = 1.0 / ((double)p.C_h * Va);
-            NF Ts = A.Ts[c];
-            // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
-            // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
-            NF Tsurf = prescribed ? a.Tskin_in : Ts;
-            NF es = saturation_vapor_pressure(Tsurf);
-            NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
-            NF vpd = jmax(es - ea, NF(0.1));
-            NF dq = p.eps_mw * vpd / a.pres;
-            NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
-            // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall)
-            NF S = A.bSx[c];
-            NF drain, inf;
-            if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (s2 < 1) ? jmin(drain, Kt) : NF(0); }
-            else { drain = 0; inf = (s2 < 1) ? jmin(a.rain, Kt) : NF(0); }
-            NF runoff = a.rain + drain - inf;
-            // surface energy balance kernel, executed twice (land_model.jl:85-86)
-            NF swu, lwu, rnet, hs, hl, G;
-#pragma unroll 1
-            for (int rep = 0; rep < 2; ++rep) {
-                seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
-                if (!prescribed) {
-                    Ts = T2 - G * met.dzc(nz) / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
-                    seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
-                }
-            }
-            A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
-            A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
-            if (!prescribed) A.Ts[c] = Ts;
-            G_top = G; infil_top = inf;
+            land_surface(A, c, rd(a_cur, EF_T), rd(a_cur, EF_S), rd(a_cur, EF_KF), met.dzc(nz), G_top, infil_top);
         }
 
         if (inner || m >= 3) {

@@ -102,7 +102,7 @@ struct StageArgs {
 
 // update_inputs! (input_sources.jl:165-171) and function valued BCs, evaluated at clock time t.
 template <class NF>
-__device__ __noinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) {
+__device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t c, NF t) {
     switch (s.kind) {
         case TRM_SRC_CONST: return s.cval;
         case TRM_SRC_FIELD: return s.a[c];
@@ -131,6 +131,9 @@ __device__ __noinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) {
     }
     return NF(0);
 }
+// out-of-line copy for the layer loop (boundary condition inputs: rare, and inlined they would bloat the loop)
+template <class NF>
+__device__ __noinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) { return eval_input_inline(s, c, t); }
 
 // Oceananigans halo fill for one side.  `D` is the face spacing at the
 // boundary, `top` selects the sign convention.
@@ -163,6 +166,60 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
     hs = (NF)((double)(p.c_a * p.rho_a) * ((double)(Tsurf - a.Ta) / a.ra));
     hl = p.Llg * p.rho_a * Egnd;
     G = rnet - hs - hl;
+}
+
+// LandModel per-column surface processes for one update_state! (land_model.jl:79-88): bare-ground evaporation,
+// runoff / infiltration, then the surface energy balance kernel twice. Reads the atmospheric inputs at clock time
+// t, the skin temperature and the surface excess water; writes every 2-D surface field; returns the two fluxes
+// that couple to the top soil layer. Out of line: it runs once per column and step, and inlined it would set the
+// register budget of the whole layer loop.
+template <class NF>
+__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, NF T_top, NF sat_top, NF K_top, NF dz_top, NF& G_out, NF& inf_out) {
+    const DevParams<NF>& p = A.p;
+    // (inputs evaluated inline: their loads are independent and overlap; through eval_input() they would serialise)
+    Surface<NF> a;
+    const NF Ts0 = A.Ts[c], S = A.bSx[c];
+    a.SWd = eval_input_inline(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
+    a.LWd = eval_input_inline(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
+    a.Ta = eval_input_inline(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
+    a.pres = eval_input_inline(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
+    a.q = eval_input_inline(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
+    a.V = eval_input_inline(A.in[TRM_IN_WINDSPEED], c, A.t_x);
+    a.rain = eval_input_inline(A.in[TRM_IN_RAINFALL], c, A.t_x);
+    const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
+    a.Tskin_in = prescribed ? eval_input_inline(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
+    // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
+    NF Vc = jmax(a.V, p.Vmin);
+    double Va = fmax((double)Vc, 1.0e-6);
+    a.ra = 1.0 / ((double)p.C_h * Va);
+    NF Ts = Ts0;
+    // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
+    // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
+    NF Tsurf = prescribed ? a.Tskin_in : Ts;
+    NF es = saturation_vapor_pressure(Tsurf);
+    NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
+    NF vpd = jmax(es - ea, NF(0.1));
+    NF dq = p.eps_mw * vpd / a.pres;
+    NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
+    // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall) ; K_top = Kf[Nz]
+    NF drain, inf;
+    if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, K_top) : NF(0); }
+    else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, K_top) : NF(0); }
+    NF runoff = a.rain + drain - inf;
+    // surface energy balance kernel, executed twice (land_model.jl:85-86)
+    NF swu, lwu, rnet, hs, hl, G;
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+        seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+        if (!prescribed) {
+            Ts = T_top - G * dz_top / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
+            seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+        }
+    }
+    A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
+    A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
+    if (!prescribed) A.Ts[c] = Ts;
+    G_out = G; inf_out = inf;
 }
 
 // Values produced while layer m enters the pipeline and consumed one or two iterations later.  Two
@@ -309,51 +366,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         if (LAND && m == nz + 2) {
             if (mode == MODE_HEUN2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
-            else {
-                Surface<NF> a;
-                a.SWd = eval_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
-                a.LWd = eval_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
-                a.Ta = eval_input(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
-                a.pres = eval_input(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
-                a.q = eval_input(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
-                a.V = eval_input(A.in[TRM_IN_WINDSPEED], c, A.t_x);
-                a.rain = eval_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
-                const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
-                a.Tskin_in = prescribed ? eval_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
-                // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
-                NF Vc = jmax(a.V, p.Vmin);
-                double Va = fmax((double)Vc, 1.0e-6);
-                a.ra = 1.0 / ((double)p.C_h * Va);
-                NF Ts = A.Ts[c];
-                // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
-                // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
-                NF Tsurf = prescribed ? a.Tskin_in : Ts;
-                NF es = saturation_vapor_pressure(Tsurf);
-                NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
-                NF vpd = jmax(es - ea, NF(0.1));
-                NF dq = p.eps_mw * vpd / a.pres;
-                NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
-                // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall)
-                NF S = A.bSx[c], Kt = Kf2, sat_top = s2;
-                NF drain, inf;
-                if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
-                else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, Kt) : NF(0); }
-                NF runoff = a.rain + drain - inf;
-                // surface energy balance kernel, executed twice (land_model.jl:85-86)
-                NF swu, lwu, rnet, hs, hl, G;
-#pragma unroll 1
-                for (int rep = 0; rep < 2; ++rep) {
-                    seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
-                    if (!prescribed) {
-                        Ts = T2 - G * met.dzc(nz) / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
-                        seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
-                    }
-                }
-                A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
-                A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
-                if (!prescribed) A.Ts[c] = Ts;
-                G_top = G; infil_top = inf;
-            }
+            else land_surface(A, c, T2, s2, Kf2, met.dzc(nz), G_top, infil_top);
         }
 
         if (m >= 3 && m <= nz + 2 && mode != MODE_AUX) {
