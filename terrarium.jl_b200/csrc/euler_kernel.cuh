@@ -1,4 +1,4 @@
-// euler_kernel.cuh -- ForwardEuler stage, streaming kernel with the pipeline state in shared memory.
+// euler_kernel.cuh -- ForwardEuler / Heun stages, streaming kernel with the pipeline state in shared memory.
 //
 // Same algorithm and the same per-cell arithmetic as stage_kernel (one thread = one column, one sweep
 // bottom -> top, see the header of stage_kernel.cuh for the reference functions), but the values that
@@ -26,8 +26,10 @@ namespace trm {
 // Resident blocks per SM the register allocator must allow. Register spills are ruinous here (shared memory
 // leaves little L1 for local memory), so the faithful math mode with its inlined pow / IEEE division sequences
 // gets a looser bound; the LandModel variant runs best with 5 blocks (measured 4: 5.9 ms, 5: 5.1 ms, 6: 6.7 ms).
-template <class NF, int PHYS, bool FAST>
-constexpr int euler_min_blocks() { return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (PHYS == PHYS_LAND ? 5 : TRM_EULER_MIN_BLOCKS); }
+template <class NF, int PHYS, bool FAST, int MODE = MODE_EULER>
+constexpr int euler_min_blocks() {
+    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (PHYS == PHYS_LAND ? 5 : TRM_EULER_MIN_BLOCKS));
+}
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
 // themselves (every strip / ring location is private to one thread), while ordinary loads, stores and arithmetic
@@ -49,24 +51,30 @@ constexpr int EULER_PF = 4;   // depth of the raw prefetch ring (layers in fligh
 
 constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 6 blocks per SM resident)
 
-template <class NF, int LOAD, int MS>
+// MODE: which timestepper stage the launch is (subset of StageMode): MODE_EULER, MODE_HEUN1 (stage state and k1 out,
+// no closure fields), MODE_HEUN2 (tendencies evaluated on the stage state, averaged with k1, applied to the base state:
+// k1 and the base U / sat of a layer are prefetched into a second cp.async ring two iterations before its update).
+template <class NF, int LOAD, int MS, int MODE = MODE_EULER>
 struct EulerSmem {
     static constexpr int RAW_FIELDS = LOAD ? 5 : 2;                                    // U, sat (, T, liq, psi)
     static constexpr int METRICS = MET_COUNT * MS;                                    // elements
     static constexpr int STRIP = EF_COUNT * 2 * TRM_EULER_BLOCK;
     static constexpr int RING = RAW_FIELDS * EULER_PF * TRM_EULER_BLOCK;
-    static constexpr size_t BYTES = sizeof(NF) * (size_t)(METRICS + STRIP + RING);
+    static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * EULER_PF * TRM_EULER_BLOCK;   // k1U, k1S, bU, bS
+    static constexpr size_t BYTES = sizeof(NF) * (size_t)(METRICS + STRIP + RING + XRING);
 };
 
-template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS>
-__global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, FAST>())) euler_kernel(const __grid_constant__ StageArgs<NF> A) {
+template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS, int MODE = MODE_EULER>
+__global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, FAST, MODE>())) euler_kernel(const __grid_constant__ StageArgs<NF> A) {
     constexpr bool RICH = PHYS != PHYS_NOFLOW;
     constexpr bool LAND = PHYS == PHYS_LAND;
     constexpr bool LOAD = LOAD_CT != 0;
     constexpr int B = TRM_EULER_BLOCK;
     constexpr int ES = (int)sizeof(NF);
     using Mx = M<NF, FAST>;
-    using SM = EulerSmem<NF, LOAD_CT, MS>;
+    using SM = EulerSmem<NF, LOAD_CT, MS, MODE>;
+    constexpr bool H1 = MODE == MODE_HEUN1, H2 = MODE == MODE_HEUN2;
+    constexpr bool CLOSE = !H1;    // Heun stage 1 leaves the closure fields of the stage state to stage 2 (recomputed there)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nz = A.nz;
@@ -105,6 +113,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     // ---- raw prefetch ring: layer k lives in ring slot (k & 3); one cp.async group per layer ----
     // element offsets fit 32 bits (the launcher checks nz * ld < 2^32): one IMAD.WIDE.U32 per address
     uint32_t oin = (uint32_t)c;
+    const uint32_t xring0 = ring0 + (uint32_t)(SM::RING * ES);
+    uint32_t oext = (uint32_t)c;   // (Heun stage 2) element offset of the next layer of the extra ring
     auto prefetch = [&](int k, bool always = false) {
         if (always || k <= nz) {
             const uint32_t dst = ring0 + (uint32_t)((k & (EULER_PF - 1)) * B * ES);
@@ -117,7 +127,18 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             }
             oin += (uint32_t)ld;
         }
-        cp_async_commit();   // (an empty group when k > nz keeps the group count in step with the iteration count)
+        if (H2) {
+            // Heun stage 2: k1 and the base state of layer k-2, needed when that layer is updated (iteration k)
+            const int kk = k - 2;
+            if (kk >= 1 && kk <= nz) {
+                const uint32_t dst = xring0 + (uint32_t)((kk & (EULER_PF - 1)) * B * ES);
+                cp_async<ES>(dst, A.k1U + oext);
+                cp_async<ES>(dst + 2 * EULER_PF * B * ES, A.bU + oext);
+                if (RICH) { cp_async<ES>(dst + EULER_PF * B * ES, A.k1S + oext); cp_async<ES>(dst + 3 * EULER_PF * B * ES, A.bS + oext); }
+                oext += (uint32_t)ld;
+            }
+        }
+        cp_async_commit();   // (an empty group when nothing is left keeps the group count in step with the iteration count)
     };
     prefetch(1); prefetch(2); prefetch(3);
 
@@ -126,7 +147,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     int idx = 0;               // lowest unsaturated layer (compute_water_table!), 0 = not found yet
     NF wt_new = NF(0);
     NF Sx_new = NF(0);
-    if (RICH) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
+    if (RICH && !H1) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
     uint32_t oout = (uint32_t)c;   // element offset of layer m-2
 
     // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-3, for which every
@@ -202,7 +223,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         NF G_top = NF(0), infil_top = NF(0);   // fluxes coupling the surface to the top soil layer (same iteration)
         if (LAND && !inner && m == nz + 2) {
-            land_surface(A, c, rd(a_cur, EF_T), rd(a_cur, EF_S), rd(a_cur, EF_KF), met.dzc(nz), G_top, infil_top);
+            if (H2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
+            else land_surface(A, c, rd(a_cur, EF_T), rd(a_cur, EF_S), rd(a_cur, EF_KF), met.dzc(nz), G_top, infil_top);
         }
 
         if (inner || m >= 3) {
@@ -215,6 +237,17 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             if (RICH) {
                 const NF dth = -((qdn - rd(a_prv, EF_QD)) * met.rdzc(j)) + NF(0) + p.vwcf;   // soil_hydrology_rre.jl:95-117
                 tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
+            }
+            NF Ub, sb;   // base state the update is applied to
+            if (H2) {   // average_tendencies! (heun.jl:27-35) with k1 of stage 1 ; the base is the state at time n
+                const uint32_t x = xring0 + (uint32_t)((j & (EULER_PF - 1)) * B * ES);
+                tU = (ldsv(x, (NF*)nullptr) + tU) / 2;
+                Ub = ldsv(x + 2 * EULER_PF * B * ES, (NF*)nullptr);
+                if (RICH) { tS = (ldsv(x + EULER_PF * B * ES, (NF*)nullptr) + tS) / 2; sb = ldsv(x + 3 * EULER_PF * B * ES, (NF*)nullptr); }
+                else sb = rd(a_cur, EF_S);   // NoFlow: the saturation is not a prognostic variable
+            } else {
+                if (H1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }   // k1, before the Flux BCs
+                Ub = rd(a_cur, EF_U); sb = rd(a_cur, EF_S);
             }
             // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
             if (!inner && j == nz) {
@@ -229,8 +262,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
             }
             // ---- explicit step, abstract_timestepper.jl:113-141 ----
-            const NF Un = rd(a_cur, EF_U) + tU * dt;
-            NF sn = rd(a_cur, EF_S);
+            const NF Un = Ub + tU * dt;
+            NF sn = sb;
             if (RICH) {
                 sn = sn + tS * dt;
                 // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
@@ -259,11 +292,13 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                     if (idx == 0 && sn < 1) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                 }
                 A.yU[o] = Un;
-                NF Tc, lc;
-                energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
-                A.yT[o] = Tc; A.yL[o] = lc;
-                // layers below the water table wait for it (written after the sweep)
-                if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j));
+                if (CLOSE) {
+                    NF Tc, lc;
+                    energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
+                    A.yT[o] = Tc; A.yL[o] = lc;
+                    // layers below the water table wait for it (written after the sweep)
+                    if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j));
+                }
             }
         }
         // ---- what later iterations need from this one ----
@@ -294,6 +329,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     if (!any_neg) {
         if (idx == 0) { idx = nz + 1; wt_new = met.zF(nz + 1); }   // all saturated: z of the surface (halo cell / fallback give the same)
         A.yWt[c] = wt_new;
+        if (H1) return;            // the stage state needs no surface excess water and no closure fields
         A.ySx[c] = Sx_new;
         // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
         const NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
@@ -330,6 +366,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         if (idx == 0) idx = nz + 1;
         wt_new = met.zF(idx);
         A.yWt[c] = wt_new;
+        if (H1) return;
         A.ySx[c] = Sx_new;
 #pragma unroll 1
         for (int k = 1; k <= nz; ++k) {

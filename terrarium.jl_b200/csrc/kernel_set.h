@@ -14,9 +14,10 @@ struct KernelSet {
                             float* U, float* S, float* T, float* L, float* P, float* Wt, float* Sx, cudaStream_t st);
     cudaError_t (*init_f64)(int64_t ncol, int64_t ld, int nz, int richards, const double* metrics, const DevParams<double>& p,
                             double* U, double* S, double* T, double* L, double* P, double* Wt, double* Sx, cudaStream_t st);
-    // ForwardEuler stage with the pipeline state in shared memory (euler_kernel.cuh)
-    cudaError_t (*euler_f32)(int phys, int load_aux, const StageArgs<float>& a, cudaStream_t st);
-    cudaError_t (*euler_f64)(int phys, int load_aux, const StageArgs<double>& a, cudaStream_t st);
+    // ForwardEuler / Heun stage (mode = MODE_EULER | MODE_HEUN1 | MODE_HEUN2) with the pipeline state in shared
+    // memory (euler_kernel.cuh); cudaErrorInvalidConfiguration = not applicable, use the generic kernel
+    cudaError_t (*euler_f32)(int phys, int mode, int load_aux, const StageArgs<float>& a, cudaStream_t st);
+    cudaError_t (*euler_f64)(int phys, int mode, int load_aux, const StageArgs<double>& a, cudaStream_t st);
 };
 
 const KernelSet& kernels_faithful();   // compiled with -fmad=false, reference operation order

@@ -21,36 +21,38 @@ cudaError_t launch_phys(int variant, const StageArgs<NF>& a, int block, cudaStre
     return cudaGetLastError();
 }
 
-// ForwardEuler stage, streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
-template <class NF, int PHYS, int LOAD, int MS>
+// ForwardEuler / Heun stages, streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
+template <class NF, int PHYS, int LOAD, int MS, int MODE>
 cudaError_t launch_euler_variant(const StageArgs<NF>& a, cudaStream_t st) {
-    constexpr size_t smem = EulerSmem<NF, LOAD, MS>::BYTES;
+    constexpr size_t smem = EulerSmem<NF, LOAD, MS, MODE>::BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(euler_kernel<NF, PHYS, LOAD, kFast, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int64_t nblk = (a.ncol + TRM_EULER_BLOCK - 1) / TRM_EULER_BLOCK;
-    euler_kernel<NF, PHYS, LOAD, kFast, MS><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
+    euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <class NF, int PHYS, int LOAD>
-cudaError_t launch_euler_ms(const StageArgs<NF>& a, cudaStream_t st) {
-    if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL>(a, st);
-    return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE>(a, st);
+cudaError_t launch_euler_mode(int mode, const StageArgs<NF>& a, cudaStream_t st) {
+    if (mode == MODE_HEUN1) return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_HEUN1>(a, st);
+    if (mode == MODE_HEUN2) return launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2>(a, st);   // stage state: always recomputed
+    if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER>(a, st);
+    return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER>(a, st);
 }
 template <class NF>
-cudaError_t launch_euler(int phys, int load_aux, const StageArgs<NF>& a, cudaStream_t st) {
+cudaError_t launch_euler(int phys, int mode, int load_aux, const StageArgs<NF>& a, cudaStream_t st) {
     // the kernel addresses layers with 32-bit element offsets; larger fields run the generic streaming kernel
     if ((uint64_t)a.nz * (uint64_t)a.ld >= (1ull << 32)) return cudaErrorInvalidConfiguration;
     switch (phys * 2 + (load_aux ? 1 : 0)) {
-        case 0: return launch_euler_ms<NF, PHYS_NOFLOW, 0>(a, st);
-        case 1: return launch_euler_ms<NF, PHYS_NOFLOW, 1>(a, st);
-        case 2: return launch_euler_ms<NF, PHYS_RICHARDS, 0>(a, st);
-        case 3: return launch_euler_ms<NF, PHYS_RICHARDS, 1>(a, st);
-        case 4: return launch_euler_ms<NF, PHYS_LAND, 0>(a, st);
-        default: return launch_euler_ms<NF, PHYS_LAND, 1>(a, st);
+        case 0: return launch_euler_mode<NF, PHYS_NOFLOW, 0>(mode, a, st);
+        case 1: return launch_euler_mode<NF, PHYS_NOFLOW, 1>(mode, a, st);
+        case 2: return launch_euler_mode<NF, PHYS_RICHARDS, 0>(mode, a, st);
+        case 3: return launch_euler_mode<NF, PHYS_RICHARDS, 1>(mode, a, st);
+        case 4: return launch_euler_mode<NF, PHYS_LAND, 0>(mode, a, st);
+        default: return launch_euler_mode<NF, PHYS_LAND, 1>(mode, a, st);
     }
 }
 

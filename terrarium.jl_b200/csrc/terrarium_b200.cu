@@ -364,16 +364,22 @@ template <> int Handle<double>::launch(int variant, const StageArgs<double>& a) 
     return TRM_OK;
 }
 
+// stage launch on the shared-memory staged kernel; falls back to the generic streaming kernel when that one does
+// not apply (fields of 2^32 elements or more) or when TRM_KERNEL=stream asks for it
 template <> int Handle<float>::launch_euler(const StageArgs<float>& a, int load_aux) {
-    cudaError_t e = ks->euler_f32(phys, load_aux, a, stream);
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a); }
+    const int generic = a.mode == MODE_EULER ? (load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE) : VAR_GENERIC;
+    if (euler_impl != 1) return launch(generic, a);
+    cudaError_t e = ks->euler_f32(phys, a.mode, load_aux, a, stream);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(generic, a); }
     ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
 template <> int Handle<double>::launch_euler(const StageArgs<double>& a, int load_aux) {
-    cudaError_t e = ks->euler_f64(phys, load_aux, a, stream);
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a); }
+    const int generic = a.mode == MODE_EULER ? (load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE) : VAR_GENERIC;
+    if (euler_impl != 1) return launch(generic, a);
+    cudaError_t e = ks->euler_f64(phys, a.mode, load_aux, a, stream);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(generic, a); }
     ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
@@ -416,16 +422,16 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
         if (!heun) {   // forward_euler.jl:19-31
             a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
             const bool load = aux_stale || force_load;
-            if (int rc = euler_impl == 1 ? launch_euler(a, load ? 1 : 0) : launch(load ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE, a)) return rc;
+            if (int rc = launch_euler(a, load ? 1 : 0)) return rc;
         } else {       // heun.jl:37-71
             a.mode = MODE_HEUN1; a.load_aux = aux_stale ? 1 : 0; a.t_x = t; a.t_b = t; x_state(a);
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
-            if (int rc = launch(VAR_GENERIC, a)) return rc;
+            if (int rc = launch_euler(a, a.load_aux)) return rc;
             StageArgs<NF> b; base_args(b);
             b.dt = dt; b.mode = MODE_HEUN2; b.load_aux = 0; b.t_x = t1; b.t_b = t;
             b.xU = gU; b.xS = richards ? gS : S; b.xWt = gWt; b.bU = U; b.bS = S; b.bSx = Sx; b.k1U = tU; b.k1S = tS;
             y_state(b);
-            if (int rc = launch(VAR_GENERIC, b)) return rc;
+            if (int rc = launch_euler(b, 0)) return rc;
         }
         aux_stale = false;
         t_inputs = (double)t;   // the state's inputs were last updated at the start of this step
