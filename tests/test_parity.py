@@ -302,3 +302,23 @@ def test_handles_are_independent_and_reusable():
     assert np.array_equal(d.state.saturation_water_ice.numpy(), b.state.saturation_water_ice.numpy())
     with pytest.raises(trm.TerrariumError):
         d._lib.check(d._lib.step(d._h, 60.0, -1), "step")
+
+
+@pytest.mark.parametrize("case", ["soil-euler", "soil-heun", "land-euler", "land-heun", "heat-euler"])
+def test_generic_streaming_kernel(case, monkeypatch):
+    """TRM_KERNEL=stream routes every stage through the generic register-streaming kernel (the fallback for fields of
+    2^32 elements or more): same parity bar as the default shared-memory staged kernel."""
+    monkeypatch.setenv("TRM_KERNEL", "stream")
+    kind, stepper = case.split("-")
+    heun = stepper == "heun"
+    if kind == "land":
+        gpu, cpu = synthetic_land_case("cuda", 333, heun=heun, math="fast", windspeed=0.5), synthetic_land_case("oracle", 333, heun=heun, windspeed=0.5)
+        fields = LAND_FIELDS
+    else:
+        rich = kind == "soil"
+        gpu, cpu = synthetic_soil_case("cuda", 333, richards=rich, heun=heun, math="fast"), synthetic_soil_case("oracle", 333, richards=rich, heun=heun)
+        fields = FIELDS + (("pressure_head", "water_table") if rich else ())
+    dt = 60.0 if kind != "heat" else 300.0
+    gpu.step(dt, 300)
+    cpu.step(dt, 300)
+    compare(gpu, cpu, fields, TOL)
