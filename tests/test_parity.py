@@ -178,10 +178,10 @@ def test_over_saturation_to_surface_excess():
 
 
 def test_full_size_properties():
-    """BASELINE config 5 scale (reduced to 2 M columns to bound test time): properties that do not need the
-    oracle -- finite fields, water conservation, saturation bounds, and agreement of the first 4096 columns
-    with an oracle run of exactly those columns (columns are independent)."""
-    n, sub = 2_000_000, 4096
+    """BASELINE config 5 at its full size (10 M columns x 30 layers): properties that do not need the oracle --
+    finite fields, water conservation, saturation bounds -- and agreement of the first 4096 columns with an
+    oracle run of exactly those columns (columns are independent)."""
+    n, sub = 10_000_000, 4096
     gpu = synthetic_soil_case("cuda", n, math="fast")
     d0 = gpu.diagnostics()
     gpu.step(60.0, 50)
