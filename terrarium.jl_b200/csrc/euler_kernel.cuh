@@ -28,7 +28,7 @@ namespace trm {
 // gets a looser bound; the LandModel variant runs best with 5 blocks (measured 4: 5.9 ms, 5: 5.1 ms, 6: 6.7 ms).
 template <class NF, int PHYS, bool FAST, int MODE = MODE_EULER>
 constexpr int euler_min_blocks() {
-    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (PHYS == PHYS_LAND ? 5 : TRM_EULER_MIN_BLOCKS));
+    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (PHYS == PHYS_LAND ? 5 : (sizeof(NF) == 4 ? 8 : TRM_EULER_MIN_BLOCKS)));
 }
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
