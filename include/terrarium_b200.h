@@ -299,6 +299,16 @@ int trm_set_input_field_async(trm_handle* h, int input_id, const void* pinned_ho
 int trm_step_async(trm_handle* h, double dt, int64_t nsteps);
 int trm_get_field_async(trm_handle* h, int field_id, void* pinned_host, int64_t count);
 
+/* ---- ColumnRingGrid conversions (src/grids/column_ring_grid.jl:102-149) --------------------------------
+ * The columns of a ColumnRingGrid are the `true` points of a mask over a ring grid of `nring` points, in ring
+ * order. trm_set_ring_index hands over, for every owned column, its position in the ring grid (host array of
+ * ncol int64). trm_get_field_ring scatters a field into a dense host array [nrows][nring] with `fill_value` at
+ * the unmasked points (RingGrids.Field(field, grid; fill_value)); trm_set_field_ring gathers the masked points
+ * of such an array into the field (Field(ring_field, grid)). Scatter / gather run on the device.           */
+int trm_set_ring_index(trm_handle* h, const int64_t* ring_index, int64_t nring);
+int trm_get_field_ring(trm_handle* h, int field_id, void* host_ring, int64_t count, double fill_value);
+int trm_set_field_ring(trm_handle* h, int field_id, const void* host_ring, int64_t count);
+
 /* Tuning knob: threads per block of the register-streaming stage kernel (multiple of 32 in [32, 128], default
  * 128). The shared-memory staged ForwardEuler kernel has a compile-time block size. */
 int trm_set_block_size(trm_handle* h, int block);

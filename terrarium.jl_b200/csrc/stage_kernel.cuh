@@ -561,6 +561,29 @@ __global__ void init_kernel(int64_t ncol, int64_t ld, int nz, int richards, cons
     }
 }
 
+// ---- masked columns <-> full ring grid (RingGrids.Field(field, grid) / Field(ring_field, grid),
+//      src/grids/column_ring_grid.jl:102-149): scatter / gather by the ring position of every column ----
+template <class NF>
+__global__ void ring_fill_kernel(int64_t n, NF* __restrict__ out, NF fill) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = fill;
+}
+template <class NF>
+__global__ void ring_scatter_kernel(int64_t ncol, int64_t ld, int nrows, int64_t nring, const int64_t* __restrict__ ring_index,
+                                    const NF* __restrict__ field, NF* __restrict__ ring) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const int64_t r = ring_index[c];
+    for (int k = 0; k < nrows; ++k) ring[(int64_t)k * nring + r] = field[(int64_t)k * ld + c];
+}
+template <class NF>
+__global__ void ring_gather_kernel(int64_t ncol, int64_t ld, int nrows, int64_t nring, const int64_t* __restrict__ ring_index,
+                                   const NF* __restrict__ ring, NF* __restrict__ field) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const int64_t r = ring_index[c];
+    for (int k = 0; k < nrows; ++k) field[(int64_t)k * ld + c] = ring[(int64_t)k * nring + r];
+}
+
 // ---- diagnostics: column budgets and extrema (one partial per block, reduced by finish_diag) ----
 template <class NF>
 __global__ void __launch_bounds__(256) diag_kernel(int64_t ncol, int64_t ld, int nz, const NF* __restrict__ metrics, NF por,

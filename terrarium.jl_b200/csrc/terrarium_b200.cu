@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -49,6 +50,9 @@ struct HandleBase {
     virtual int get_field_async(int id, void* host, int64_t count) = 0;
     virtual int step_async(double dt, int64_t n) = 0;
     virtual int sync_all() = 0;
+    virtual int set_ring_index(const int64_t* idx, int64_t nring) = 0;
+    virtual int get_field_ring(int id, void* host, int64_t count, double fill) = 0;
+    virtual int set_field_ring(int id, const void* host, int64_t count) = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     double time = 0.0;   // holds an NF value
@@ -92,6 +96,8 @@ struct Handle : HandleBase {
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the asynchronous entry points
     cudaEvent_t ev_staged = nullptr, ev_out_done = nullptr;
     NF* staging = nullptr; size_t staging_count = 0;
+    int64_t* ring_index = nullptr; int64_t nring = 0;   // ring-grid position of every owned column (ColumnRingGrid mask)
+    NF* ring_buf = nullptr; size_t ring_count = 0;
     bool timing_open = false;
     double* diag_partial = nullptr; double* diag_out = nullptr; int diag_blocks = 0;
 
@@ -351,6 +357,10 @@ struct Handle : HandleBase {
     int get_field_async(int id, void* host, int64_t count) override;
     int step_async(double dt, int64_t n) override;
     int sync_all() override;
+    int set_ring_index(const int64_t* idx, int64_t nring_) override;
+    int get_field_ring(int id, void* host, int64_t count, double fill) override;
+    int set_field_ring(int id, const void* host, int64_t count) override;
+    int ring_buffer(size_t need);
 };
 
 template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
@@ -460,6 +470,56 @@ template <class NF> int Handle<NF>::sync_all() {
     if (s_in) CU(cudaStreamSynchronize(s_in));
     if (s_out) CU(cudaStreamSynchronize(s_out));
     if (timing_open) { CU(cudaEventElapsedTime(&last_ms, ev0, ev1)); timing_open = false; }
+    return TRM_OK;
+}
+
+// ---- ColumnRingGrid conversions (src/grids/column_ring_grid.jl:102-149) on the device ----
+template <class NF> int Handle<NF>::set_ring_index(const int64_t* idx, int64_t nring_) {
+    if (nring_ < nc) return fail(TRM_ERR_INVALID, "set_ring_index: ring grid smaller than the column count");
+    for (int64_t i = 0; i < nc; ++i) if (idx[i] < 0 || idx[i] >= nring_) return fail(TRM_ERR_INVALID, "set_ring_index: index outside the ring grid");
+    CU(cudaSetDevice(device));
+    if (!ring_index) { if (int rc = dalloc(&ring_index, (size_t)ld)) return rc; }
+    CU(cudaMemcpyAsync(ring_index, idx, nc * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));
+    nring = nring_;
+    return TRM_OK;
+}
+template <class NF> int Handle<NF>::ring_buffer(size_t need) {
+    if (need <= ring_count) return TRM_OK;
+    if (ring_buf) dfree(ring_buf);
+    ring_buf = nullptr; ring_count = 0;
+    if (int rc = dalloc(&ring_buf, need, false)) return rc;
+    ring_count = need;
+    return TRM_OK;
+}
+template <class NF> int Handle<NF>::get_field_ring(int id, void* host, int64_t count, double fill) {
+    if (!ring_index) return fail(TRM_ERR_STATE, "get_field_ring before trm_set_ring_index");
+    FieldRef f = field(id);
+    if (!f.ptr) return fail(TRM_ERR_INVALID, "get_field_ring: unknown field or field not defined for this model");
+    if (count != (int64_t)f.nrows * nring) return fail(TRM_ERR_INVALID, "get_field_ring: count != nrows * nring");
+    CU(cudaSetDevice(device));
+    if (int rc = ring_buffer((size_t)count)) return rc;
+    ring_fill_kernel<NF><<<(unsigned)std::min<int64_t>((count + 255) / 256, 148 * 16), 256, 0, stream>>>(count, ring_buf, (NF)fill);
+    ring_scatter_kernel<NF><<<(unsigned)((nc + 127) / 128), 128, 0, stream>>>(nc, ld, f.nrows, nring, ring_index, f.ptr, ring_buf);
+    launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, ring_buf, (size_t)count * sizeof(NF), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return TRM_OK;
+}
+template <class NF> int Handle<NF>::set_field_ring(int id, const void* host, int64_t count) {
+    if (!ring_index) return fail(TRM_ERR_STATE, "set_field_ring before trm_set_ring_index");
+    FieldRef f = field(id);
+    if (!f.ptr || !f.writable) return fail(TRM_ERR_INVALID, "set_field_ring: unknown or read-only field");
+    if (count != (int64_t)f.nrows * nring) return fail(TRM_ERR_INVALID, "set_field_ring: count != nrows * nring");
+    CU(cudaSetDevice(device));
+    if (int rc = ring_buffer((size_t)count)) return rc;
+    CU(cudaMemcpyAsync(ring_buf, host, (size_t)count * sizeof(NF), cudaMemcpyHostToDevice, stream));
+    ring_gather_kernel<NF><<<(unsigned)((nc + 127) / 128), 128, 0, stream>>>(nc, ld, f.nrows, nring, ring_index, ring_buf, f.ptr);
+    ++launches;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(stream));
+    aux_stale = true;
     return TRM_OK;
 }
 
@@ -643,6 +703,9 @@ int trm_last_step_ms(trm_handle* h, float* ms) { if (!h || !ms) return fail(TRM_
 int trm_set_input_field_async(trm_handle* h, int id, const void* v) { if (!h || !v || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_field_async(id, v); }
 int trm_get_field_async(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field_async(id, host, count); }
 int trm_step_async(trm_handle* h, double dt, int64_t n) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->step_async(dt, n); }
+int trm_set_ring_index(trm_handle* h, const int64_t* ring_index, int64_t nring) { if (!h || !ring_index) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->set_ring_index(ring_index, nring); }
+int trm_get_field_ring(trm_handle* h, int id, void* host, int64_t count, double fill) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field_ring(id, host, count, fill); }
+int trm_set_field_ring(trm_handle* h, int id, const void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->set_field_ring(id, host, count); }
 int trm_set_block_size(trm_handle* h, int block) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->set_block(block); }
 
 }  // extern "C"

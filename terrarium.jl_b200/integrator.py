@@ -73,6 +73,27 @@ class Field:
         lib = self._i._lib
         lib.check(lib.set_field(self._i._h, self.id, arr.ctypes.data_as(C.c_void_p), arr.size), f"set_field({self.name})")
 
+    # -- ColumnRingGrid conversions (src/grids/column_ring_grid.jl:102-149), scatter / gather on the device ------
+    def to_ring(self, fill_value=np.nan) -> np.ndarray:
+        """``RingGrids.Field(field, grid; fill_value)``: the field on the full ring grid, ``fill_value`` off the mask.
+        On a multi-rank partition every rank fills the points of its own column range."""
+        integ = self._i
+        nring = integ._ensure_ring_index()
+        rows = 1 if len(self.shape) == 1 else self.shape[0]
+        out = np.empty((rows, nring), dtype=integ.nf)
+        lib = integ._lib
+        lib.check(lib.get_field_ring(integ._h, self.id, out.ctypes.data_as(C.c_void_p), out.size, float(fill_value)), f"get_field_ring({self.name})")
+        return out[0] if len(self.shape) == 1 else out
+
+    def set_from_ring(self, ring_field) -> None:
+        """``Field(ring_field, grid)``: copy the masked points of a ring-grid array ``[nring]`` / ``[rows, nring]``."""
+        integ = self._i
+        nring = integ._ensure_ring_index()
+        rows = 1 if len(self.shape) == 1 else self.shape[0]
+        arr = np.ascontiguousarray(np.broadcast_to(np.asarray(ring_field, dtype=integ.nf).reshape(rows, -1), (rows, nring)), dtype=integ.nf)
+        lib = integ._lib
+        lib.check(lib.set_field_ring(integ._h, self.id, arr.ctypes.data_as(C.c_void_p), arr.size), f"set_field_ring({self.name})")
+
     def __repr__(self):
         return f"Field({self.name}, shape={self.shape}, {np.dtype(self._i.nf).name}) on device"
 
@@ -174,6 +195,16 @@ class ModelIntegrator:
             Field(self, name).set(value)
         self._lib.check(self._lib.initialize(self._h), "initialize")
         return self
+
+    def _ensure_ring_index(self) -> int:
+        """Hand the ring positions of this rank's columns to the library once (ColumnRingGrid only)."""
+        if not hasattr(self.grid, "mask"):
+            raise TypeError("ring-grid conversions need a ColumnRingGrid")
+        if not getattr(self, "_ring_ready", False):
+            idx = np.ascontiguousarray(np.flatnonzero(self.grid.mask)[self.col0:self.col1], dtype=np.int64)
+            self._lib.check(self._lib.set_ring_index(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), int(self.grid.npoints)), "set_ring_index")
+            self._ring_ready = True
+        return int(self.grid.npoints)
 
     def _local(self, a, shape):
         """Slice a per-column array given for the global domain down to this rank's column range."""

@@ -458,3 +458,34 @@ def test_run_on_ring_grid(engine, stepper):
         trm.run(integ, steps=2, period=3600)
     with pytest.raises(ValueError):
         trm.run(integ)
+
+
+# ---------------------------------------------------------------------------------------------
+# function valued boundary conditions (x, t) -> value, as in examples/simulations/soil_heat_global.jl:72-93:
+# evaluated on the host before every step (ForwardEuler only); must agree with the device resident Sinusoid form
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+def test_function_valued_boundary_condition(engine):
+    n, P = 7, 86400.0
+    grid = trm.ColumnRingGrid(trm.B200(), F64, trm.ExponentialSpacing(dz_min=0.05, dz_max=10.0, N=12), mask=np.array([1, 0, 1, 1, 1, 0, 1, 1, 1], bool))
+    assert grid.Nc == n
+    T0 = np.linspace(-3.0, 6.0, n)
+    lon = np.linspace(0.0, 5.0, n)
+
+    def surface_temperature(x, t):   # x = x-node of the column: round(x) is the 1-based column index (column_ring_grid.jl:54)
+        i = np.rint(x).astype(int) - 1
+        return T0[i] + 10.0 * np.sin(2 * np.pi * t / P - lon[i])
+
+    inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z, "saturation_water_ice": 0.8}
+    a = make(engine, trm.SoilModel(grid), trm.ForwardEuler(dt=300.0), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", surface_temperature), initializers=inits)
+    b = make(engine, trm.SoilModel(grid), trm.ForwardEuler(dt=300.0), initializers=inits,
+             boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=P)))
+    a.step(300.0, 100)
+    b.step(300.0, 100)
+    Ta, Tb = a.state.temperature.numpy(), b.state.temperature.numpy()
+    assert np.max(np.abs(Ta - Tb)) <= 1e-11 * np.max(np.abs(Tb))
+    assert a.clock.time == b.clock.time == 30000.0
+    # with Heun the stage at t + dt would need a second host evaluation inside the step: refused, not silently wrong
+    h = make(engine, trm.SoilModel(grid), trm.Heun(dt=300.0), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", surface_temperature), initializers=inits)
+    with pytest.raises(NotImplementedError):
+        h.step(300.0, 1)

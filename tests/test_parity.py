@@ -322,3 +322,28 @@ def test_generic_streaming_kernel(case, monkeypatch):
     gpu.step(dt, 300)
     cpu.step(dt, 300)
     compare(gpu, cpu, fields, TOL)
+
+
+def test_ring_grid_scatter_gather():
+    """ColumnRingGrid <-> ring grid conversions on the device (column_ring_grid.jl:102-149; reference test
+    test/grids.jl:33-139) against the host mirror ColumnRingGrid.to_ring / from_ring, for 3-D, z-face and 2-D fields."""
+    rng = np.random.default_rng(3)
+    mask = rng.random(4000) > 0.6
+    grid = trm.ColumnRingGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_min=0.05, dz_max=10.0, N=9), mask=mask)
+    model = trm.SoilModel(grid, soil=richards_soil())
+    T0 = rng.uniform(-5, 15, grid.Nc)
+    integ = make("cuda", model, trm.ForwardEuler(dt=60.0), initializers={"temperature": T0[None, :] + np.zeros((9, 1)), "saturation_water_ice": 0.6})
+    integ.step(60.0, 5)
+    integ.compute_auxiliary()
+    for name in ("temperature", "hydraulic_conductivity", "water_table"):
+        f = getattr(integ.state, name)
+        ring = f.to_ring(fill_value=-999.0)
+        assert np.array_equal(ring, grid.to_ring(f.numpy(), fill_value=-999.0))
+        assert np.all(ring[..., ~mask] == -999.0)
+    assert np.all(np.isnan(integ.state.temperature.to_ring()[:, ~mask]))
+    # ring -> masked columns
+    new_sat = rng.uniform(0.2, 0.9, (9, mask.size))
+    integ.state.saturation_water_ice.set_from_ring(new_sat)
+    assert np.array_equal(integ.state.saturation_water_ice.numpy(), grid.from_ring(new_sat))
+    with pytest.raises(trm.TerrariumError):
+        integ._lib.check(integ._lib.get_field_ring(integ._h, 1, new_sat.ctypes.data, 5, 0.0), "get_field_ring")
