@@ -117,12 +117,6 @@ struct Oracle {
     int setup(const trm_config& c) {
         cfg = c; nz = c.nz; nc = c.ncol;
         land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
-        if (land && !richards) {
-            // reference: LandModel needs surface_excess_water/infiltration coupling which only the
-            // Richards variant defines (land_model.jl:56-62 injects a Flux BC on the *prognostic*
-            // saturation_water_ice, which is only prognostic under RichardsEq).
-            return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
-        }
         const trm_params& p = c.params;
         // ---- grid (column_grid.jl:30-31: z_coords converted to NF, then [OCN] metrics in NF)
         zF.assign(nz + 3, NF(0)); zC.assign(nz + 2, NF(0)); dzc.assign(nz + 2, NF(0)); dzf.assign(nz + 3, NF(0));
@@ -369,7 +363,9 @@ struct Oracle {
 #pragma omp parallel for schedule(static)
         for (int64_t c = 0; c < nc; ++c) {
             NF rain = s.in[TRM_IN_RAINFALL][c];  // rainfall_ground aliases rainfall (canopy_interception.jl:11-15)
-            NF S = s.Sx[c], Kt = s.Kf[s.ix(nz, c)], sat_top = s.sat[s.ix(nz, c)];
+            // surface_excess_water(i, j, grid, fields, hydrology): the prognostic field under RichardsEq
+            // (soil_hydrology_rre.jl:28), identically zero for immobile soil water (soil_hydrology.jl:138)
+            NF S = richards ? s.Sx[c] : NF(0), Kt = s.Kf[s.ix(nz, c)], sat_top = s.sat[s.ix(nz, c)];
             NF drain, inf;
             if (S > 0) { drain = jmax(S, NF(0)) / tau_r; inf = (sat_top < 1) ? jmin(drain, Kt) : NF(0); }
             else { drain = 0; inf = (sat_top < 1) ? jmin(rain, Kt) : NF(0); }
@@ -431,7 +427,8 @@ struct Oracle {
         for (int64_t c = 0; c < nc; ++c) {
             if (land) {  // land_model.jl:56-62 : top Flux BCs G and -infiltration
                 s.tendU[s.ix(nz, c)] -= s.G[c] / dzc[nz];
-                s.tendsat[s.ix(nz, c)] -= (-s.infil[c]) / dzc[nz];
+                // the infiltration Flux BC sits on saturation_water_ice, which is only stepped when it is prognostic (RichardsEq)
+                if (richards) s.tendsat[s.ix(nz, c)] -= (-s.infil[c]) / dzc[nz];
             } else {
                 if (cfg.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) s.tendU[s.ix(nz, c)] -= bc_value(s, TRM_BC_ENERGY_TOP, c) / dzc[nz];
                 if (richards && cfg.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) s.tendsat[s.ix(nz, c)] -= bc_value(s, TRM_BC_SATURATION_TOP, c) / dzc[nz];

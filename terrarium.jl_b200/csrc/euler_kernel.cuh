@@ -28,7 +28,7 @@ namespace trm {
 // gets a looser bound; the LandModel variant runs best with 5 blocks (measured 4: 5.9 ms, 5: 5.1 ms, 6: 6.7 ms).
 template <class NF, int PHYS, bool FAST, int MODE = MODE_EULER>
 constexpr int euler_min_blocks() {
-    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (PHYS == PHYS_LAND ? 5 : (sizeof(NF) == 4 ? 8 : TRM_EULER_MIN_BLOCKS)));
+    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (phys_land(PHYS) ? 5 : (sizeof(NF) == 4 ? 8 : TRM_EULER_MIN_BLOCKS)));
 }
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
@@ -66,8 +66,8 @@ struct EulerSmem {
 
 template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS, int MODE = MODE_EULER>
 __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, FAST, MODE>())) euler_kernel(const __grid_constant__ StageArgs<NF> A) {
-    constexpr bool RICH = PHYS != PHYS_NOFLOW;
-    constexpr bool LAND = PHYS == PHYS_LAND;
+    constexpr bool RICH = phys_richards(PHYS);
+    constexpr bool LAND = phys_land(PHYS);
     constexpr bool LOAD = LOAD_CT != 0;
     constexpr int B = TRM_EULER_BLOCK;
     constexpr int ES = (int)sizeof(NF);
@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 const NF Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
                 Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : Mx::mn(Kcn, rd(a_prv, EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
                 wr(a_cur, EF_KC, Kcn);
+            } else if (LAND && !inner && m == nz) {
+                Kfn = cell_conductivity<NF, FAST>(p, sr, ln);   // compute_hydraulics! (soil_hydrology.jl:145-163): the runoff scheme reads Kf[Nz] = Kc[Nz]
             }
         } else if (!inner && m == nz + 1) {   // halo above the surface, built from layer nz (prv)
             Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(a_prv, EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         NF G_top = NF(0), infil_top = NF(0);   // fluxes coupling the surface to the top soil layer (same iteration)
         if (LAND && !inner && m == nz + 2) {
             if (H2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
-            else land_surface(A, c, rd(a_cur, EF_T), rd(a_cur, EF_S), rd(a_cur, EF_KF), met.dzc(nz), G_top, infil_top);
+            else land_surface(A, c, RICH, rd(a_cur, EF_T), rd(a_cur, EF_S), rd(a_cur, EF_KF), met.dzc(nz), G_top, infil_top);
         }
 
         if (inner || m >= 3) {
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             }
             // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
             if (!inner && j == nz) {
-                if (LAND) { tU -= G_top / met.dzc(nz); tS -= (-infil_top) / met.dzc(nz); }           // land_model.jl:56-62
+                if (LAND) { tU -= G_top / met.dzc(nz); if (RICH) tS -= (-infil_top) / met.dzc(nz); }   // land_model.jl:56-62
                 else {
                     if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / met.dzc(nz);
                     if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / met.dzc(nz);
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
         wr(a_cur, EF_T, Tn); wr(a_cur, EF_KAP, kapn); wr(a_cur, EF_QH, qhn); wr(a_cur, EF_DQH, dqhn);
         if (RICH) { wr(a_cur, EF_P, Pn); wr(a_cur, EF_KF, Kfn); wr(a_cur, EF_G, gn); wr(a_cur, EF_QD, qdn); }
+        else if (LAND) wr(a_cur, EF_KF, Kfn);
         const uint32_t t = a_cur; a_cur = a_prv; a_prv = t;
     };
     {

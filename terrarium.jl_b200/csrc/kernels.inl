@@ -52,7 +52,9 @@ cudaError_t launch_euler(int phys, int mode, int load_aux, const StageArgs<NF>& 
         case 2: return launch_euler_mode<NF, PHYS_RICHARDS, 0>(mode, a, st);
         case 3: return launch_euler_mode<NF, PHYS_RICHARDS, 1>(mode, a, st);
         case 4: return launch_euler_mode<NF, PHYS_LAND, 0>(mode, a, st);
-        default: return launch_euler_mode<NF, PHYS_LAND, 1>(mode, a, st);
+        case 5: return launch_euler_mode<NF, PHYS_LAND, 1>(mode, a, st);
+        case 6: return launch_euler_mode<NF, PHYS_LAND_NOFLOW, 0>(mode, a, st);
+        default: return launch_euler_mode<NF, PHYS_LAND_NOFLOW, 1>(mode, a, st);
     }
 }
 
@@ -61,7 +63,8 @@ cudaError_t launch_stage(int phys, int variant, const StageArgs<NF>& a, int bloc
     switch (phys) {
         case PHYS_NOFLOW:   return launch_phys<NF, PHYS_NOFLOW>(variant, a, block, st);
         case PHYS_RICHARDS: return launch_phys<NF, PHYS_RICHARDS>(variant, a, block, st);
-        default:            return launch_phys<NF, PHYS_LAND>(variant, a, block, st);
+        case PHYS_LAND:     return launch_phys<NF, PHYS_LAND>(variant, a, block, st);
+        default:            return launch_phys<NF, PHYS_LAND_NOFLOW>(variant, a, block, st);
     }
 }
 

@@ -34,7 +34,11 @@
 namespace trm {
 
 enum StageMode { MODE_EULER = 0, MODE_HEUN1 = 1, MODE_HEUN2 = 2, MODE_TEND = 3, MODE_AUX = 4 };
-enum Phys { PHYS_NOFLOW = 0, PHYS_RICHARDS = 1, PHYS_LAND = 2 };
+// soil hydrology / model combination a kernel is compiled for: SoilModel with immobile water or Richards flow,
+// LandModel (bare ground) on top of either (default_soil(grid, nothing) is the immobile variant, land_model.jl:111)
+enum Phys { PHYS_NOFLOW = 0, PHYS_RICHARDS = 1, PHYS_LAND = 2 /* LandModel + Richards */, PHYS_LAND_NOFLOW = 3, PHYS_COUNT = 4 };
+__host__ __device__ constexpr bool phys_richards(int phys) { return phys == PHYS_RICHARDS || phys == PHYS_LAND; }
+__host__ __device__ constexpr bool phys_land(int phys) { return phys == PHYS_LAND || phys == PHYS_LAND_NOFLOW; }
 
 // Grid metrics (reference 1-based layer / face indices + halos), one row of MET_STRIDE values per quantity.
 // The fixed stride lets the kernels address `quantity[k]` as (k-dependent register) + immediate.
@@ -174,11 +178,13 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
 // that couple to the top soil layer. Out of line: it runs once per column and step, and inlined it would set the
 // register budget of the whole layer loop.
 template <class NF>
-__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, NF T_top, NF sat_top, NF K_top, NF dz_top, NF& G_out, NF& inf_out) {
+__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF K_top, NF dz_top, NF& G_out, NF& inf_out) {
     const DevParams<NF>& p = A.p;
     // (inputs evaluated inline: their loads are independent and overlap; through eval_input() they would serialise)
     Surface<NF> a;
-    const NF Ts0 = A.Ts[c], S = A.bSx[c];
+    // surface_excess_water(...) is the prognostic field under RichardsEq (soil_hydrology_rre.jl:28) and identically
+    // zero for immobile soil water (soil_hydrology.jl:138)
+    const NF Ts0 = A.Ts[c], S = richards ? A.bSx[c] : NF(0);
     a.SWd = eval_input_inline(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
     a.LWd = eval_input_inline(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
     a.Ta = eval_input_inline(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
@@ -240,8 +246,8 @@ struct Stage {
 
 template <class NF, int PHYS, int MODE_CT, int LOAD_CT, bool FAST>
 __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(const __grid_constant__ StageArgs<NF> A) {
-    constexpr bool RICH = PHYS != PHYS_NOFLOW;
-    constexpr bool LAND = PHYS == PHYS_LAND;
+    constexpr bool RICH = phys_richards(PHYS);
+    constexpr bool LAND = phys_land(PHYS);
     using Mx = M<NF, FAST>;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     const DevParams<NF>& p = A.p;
     const int mode = MODE_CT >= 0 ? MODE_CT : A.mode;
     const bool load_aux = LOAD_CT >= 0 ? (LOAD_CT != 0) : (A.load_aux != 0);
-    const bool need_K = RICH || mode == MODE_AUX || mode == MODE_TEND;   // compute_hydraulics! always runs in the
+    const bool need_K = RICH || LAND || mode == MODE_AUX || mode == MODE_TEND;   // compute_hydraulics! always runs in the
                                                                         // reference; only materialised when asked
     const bool write_K = mode == MODE_AUX || mode == MODE_TEND;
     const bool do_update = mode == MODE_EULER || mode == MODE_HEUN1 || mode == MODE_HEUN2;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         if (LAND && m == nz + 2) {
             if (mode == MODE_HEUN2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
-            else land_surface(A, c, T2, s2, Kf2, met.dzc(nz), G_top, infil_top);
+            else land_surface(A, c, RICH, T2, s2, Kf2, met.dzc(nz), G_top, infil_top);
         }
 
         if (m >= 3 && m <= nz + 2 && mode != MODE_AUX) {

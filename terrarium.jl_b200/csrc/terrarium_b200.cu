@@ -135,8 +135,7 @@ struct Handle : HandleBase {
             if (k == "stream") euler_impl = 0; else if (k == "smem") euler_impl = 1;
             else return fail(TRM_ERR_INVALID, "TRM_KERNEL must be smem or stream");
         }
-        if (land && !richards) return fail(TRM_ERR_UNSUPPORTED, "LandModel requires hydrology = RICHARDS");
-        phys = land ? PHYS_LAND : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
+        phys = land ? (richards ? PHYS_LAND : PHYS_LAND_NOFLOW) : (richards ? PHYS_RICHARDS : PHYS_NOFLOW);
         ks = fast ? &kernels_fast() : &kernels_faithful();
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

@@ -364,7 +364,8 @@ class SoilModel:  # src/models/soil/soil_model.jl:9-27
 class LandModel:  # src/models/coupled/land_model.jl:10-44 with vegetation = nothing
     grid: ColumnGrid
     vegetation: None = None
-    soil: SoilEnergyWaterCarbon = field(default_factory=lambda: SoilEnergyWaterCarbon(hydrology=SoilHydrology(RichardsEq())))
+    # default_soil(grid, ::Nothing) = SoilEnergyWaterCarbon(NF): immobile soil water (land_model.jl:111-112)
+    soil: SoilEnergyWaterCarbon = field(default_factory=SoilEnergyWaterCarbon)
     surface_energy_balance: SurfaceEnergyBalance = field(default_factory=SurfaceEnergyBalance)
     surface_hydrology: SurfaceHydrology = field(default_factory=SurfaceHydrology)
     atmosphere: PrescribedAtmosphere = field(default_factory=PrescribedAtmosphere)

@@ -489,3 +489,33 @@ def test_function_valued_boundary_condition(engine):
     h = make(engine, trm.SoilModel(grid), trm.Heun(dt=300.0), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", surface_temperature), initializers=inits)
     with pytest.raises(NotImplementedError):
         h.step(300.0, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# LandModel(grid; vegetation = nothing) with its DEFAULT soil: default_soil(grid, ::Nothing) is immobile soil water
+# (land_model.jl:111-112). The surface excess water seen by the runoff scheme is then identically zero
+# (soil_hydrology.jl:138), infiltration is diagnosed but never applied (saturation is not prognostic), the ground
+# heat flux still drives the soil energy.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("stepper", ["euler", "heun"])
+def test_land_model_default_soil_is_immobile_water(engine, stepper):
+    grid = column(trm.ExponentialSpacing(dz_max=1.0, N=20), n=3)
+    land = trm.LandModel(grid)
+    assert isinstance(land.soil.hydrology.vertical_flow, trm.NoFlow)
+    ts = trm.ForwardEuler(dt=60.0) if stepper == "euler" else trm.Heun(dt=60.0)
+    integ = make(engine, land, ts, {"rainfall": 1.0e-7, "windspeed": 0.5},
+                 initializers={"temperature": lambda x, z: 5.0 - 0.02 * z, "saturation_water_ice": 0.5, "skin_temperature": 5.0})
+    sat0 = integ.state.saturation_water_ice.numpy().copy()
+    U0 = integ.state.internal_energy.numpy().copy()
+    integ.step(60.0, 10)
+    integ.compute_auxiliary()
+    assert np.array_equal(integ.state.saturation_water_ice.numpy(), sat0)       # not prognostic: untouched
+    inf = integ.state.infiltration.numpy()
+    K_top = integ.state.hydraulic_conductivity.numpy()[-1]
+    assert np.all(inf == np.minimum(1.0e-7, K_top)) and np.all(inf > 0)          # min(rain, Kf[Nz]) * (sat_top < 1)
+    assert np.all(integ.state.surface_runoff.numpy() == 1.0e-7 - inf)
+    G = integ.state.ground_heat_flux.numpy()
+    assert np.all(np.isfinite(G)) and np.all(G != 0)
+    dU = integ.state.internal_energy.numpy() - U0
+    assert np.all(np.sign(dU[-1]) == -np.sign(G))                                # G > 0 (upward) cools the top layer

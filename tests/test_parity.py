@@ -347,3 +347,19 @@ def test_ring_grid_scatter_gather():
     assert np.array_equal(integ.state.saturation_water_ice.numpy(), grid.from_ring(new_sat))
     with pytest.raises(trm.TerrariumError):
         integ._lib.check(integ._lib.get_field_ring(integ._h, 1, new_sat.ctypes.data, 5, 0.0), "get_field_ring")
+
+
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+@pytest.mark.parametrize("stepper", ["euler", "heun"])
+def test_land_model_immobile_water_1000_steps(math, stepper):
+    """LandModel on its default soil (NoFlow hydrology): surface energy balance driving heat conduction with freeze-thaw."""
+    n = 500
+    gpu = synthetic_land_case("cuda", n, heun=stepper == "heun", math=math, windspeed=0.5, richards=False)
+    cpu = synthetic_land_case("oracle", n, heun=stepper == "heun", windspeed=0.5, richards=False)
+    fields = FIELDS[:2] + FIELDS[3:] + ("skin_temperature", "ground_heat_flux", "latent_heat_flux", "sensible_heat_flux", "infiltration", "surface_runoff")
+    for _ in range(4):
+        gpu.step(60.0, 250)
+        cpu.step(60.0, 250)
+        compare(gpu, cpu, fields, TOL)
+    gpu.compute_auxiliary(); cpu.compute_auxiliary()
+    compare(gpu, cpu, ("hydraulic_conductivity", "surface_net_radiation", "evaporation_ground"), TOL)
