@@ -57,7 +57,8 @@ enum trm_status {
 /* ---- enumerations ---------------------------------------------------------------------- */
 enum trm_dtype       { TRM_F32 = 0, TRM_F64 = 1 };
 /* SoilModel (src/models/soil/soil_model.jl:9-59), LandModel with vegetation = nothing
- * (src/models/coupled/land_model.jl:111-125: BareGroundEvaporation + NoCanopyInterception). */
+ * (src/models/coupled/land_model.jl:111-125: BareGroundEvaporation + NoCanopyInterception) on either soil
+ * hydrology (its default soil has immobile water, land_model.jl:111-112). */
 enum trm_model       { TRM_MODEL_SOIL = 0, TRM_MODEL_LAND = 1 };
 enum trm_timestepper { TRM_EULER = 0, TRM_HEUN = 1 };
 /* src/processes/soil/hydrology/soil_hydrology.jl:13 (NoFlow), soil_hydrology_rre.jl:18 (RichardsEq) */
@@ -264,7 +265,7 @@ int trm_input_ptr(trm_handle* h, int input_id, void** devptr);
  * then the inverse energy closure T -> U (src/processes/soil/soil_coupled.jl:45-54). */
 int trm_initialize(trm_handle* h);
 /* nsteps x timestep!(integrator, dt; finalize = false) (forward_euler.jl:19-31, heun.jl:37-71):
- * one fused kernel launch per time step. */
+ * one fused kernel launch per timestepper stage (ForwardEuler: one per step, Heun: two per step). */
 int trm_step(trm_handle* h, double dt, int64_t nsteps);
 /* compute_auxiliary!(state, model) (soil_model.jl:39-42, land_model.jl:79-88): what
  * timestep!(...; finalize = true) and run! do after stepping (model_integrator.jl:81-87,125-131). */
