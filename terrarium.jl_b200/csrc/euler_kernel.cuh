@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     auto fld = [](int f) { return (uint32_t)(f * 2 * B * ES); };
     auto rd = [&](uint32_t slot, int f) { return ldsv(slot + fld(f), (NF*)nullptr); };
     auto wr = [&](uint32_t slot, int f, NF v) { sts(slot + fld(f), v); };
-#pragma unroll
-    for (int f = 0; f < EF_COUNT; ++f) { wr(a_cur, f, NF(0)); wr(a_prv, f, NF(0)); }
+    // the only strip values read before the pipeline has written them: Kf[0] = 0 (never written by the reference)
+    // and the (unused) differences formed against the not yet existing layer 0
+    wr(a_cur, EF_KF, NF(0)); wr(a_prv, EF_KF, NF(0)); wr(a_prv, EF_QH, NF(0)); wr(a_prv, EF_G, NF(0)); wr(a_prv, EF_KC, NF(0));
 
     auto bc_input = [&](int slot) -> NF {
         const int kind = A.bc[slot].kind;
