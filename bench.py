@@ -306,9 +306,13 @@ def main():
     peak, peak_src = peaks()
     bpc = algorithmic_bytes_per_cell(itemsize, NZ)
     per_launch_ms = dev_ms / args.steps
+    # ncu dram bytes of one launch over 10 M columns (profiles/traffic.json), scaled to this rank's column count
+    traffic = profiled_traffic(args.dtype)
+    if traffic is not None:
+        traffic = traffic * ncol_local / 10_000_000 if not secondary else None
     achieved = bpc * (ncol_local * NZ) / (per_launch_ms * 1e-3) / 1e9   # this rank's kernel (ranks are symmetric)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(args.dtype), "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_column_layer_step": bpc,
                 "kernel": ("trm::stage_kernel" if os.environ.get("TRM_KERNEL") == "stream" else "trm::euler_kernel") + f"<{args.dtype}, RICHARDS, recompute, {args.math}>",
                 "launch_ms": per_launch_ms}
