@@ -71,9 +71,12 @@ struct M {
     __device__ static __forceinline__ NF div(NF a, NF b) { return a / b; }
     __device__ static __forceinline__ NF rcp(NF a) { return 1 / a; }
     __device__ static __forceinline__ NF sqrt_(NF a) { return tsqrt(a); }
+    __device__ static __forceinline__ NF rsqrt_(NF a) { return 1 / tsqrt(a); }
     __device__ static __forceinline__ NF mn(NF a, NF b) { return jmin(a, b); }
     __device__ static __forceinline__ NF mx(NF a, NF b) { return jmax(a, b); }
     __device__ static __forceinline__ NF pow23(NF x) { NF c = tcbrt(x); return c * c; }
+    __device__ static __forceinline__ NF pos(NF e) { return jmax(e, NF(0)); }
+    __device__ static __forceinline__ void roots(NF x, NF& x23, NF& x12) { x23 = pow23(x); x12 = sqrt_(x); }
 };
 static __device__ __noinline__ double pow23_cold(double x) { double c = cbrt(x); return c * c; }
 
@@ -87,15 +90,32 @@ struct M<double, true> {
         return fma(r, fma(e, e, e), r);
     }
     __device__ static __forceinline__ double div(double a, double b) { return a * rcp(b); }
-    __device__ static __forceinline__ double rsqrt_(double x) {
+    // seed of 1/sqrt(x) (MUFU.RSQ64H), clamped to 2^512 so that x = 0 gives finite products (0 * seed = 0)
+    __device__ static __forceinline__ double rsqrt_seed(double x) {
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-        double hx = 0.5 * x;
-        // one third-order step: y (1 + h + 3/2 h^2), h = 1/2 - 1/2 x y^2
-        const double h = fma(-hx * y, y, 0.5);
-        return fma(y, h * fma(1.5, h, 1.0), y);
+        return __hiloint2double(min(__double2hiint(y), 0x5FF00000), 0);
     }
-    __device__ static __forceinline__ double sqrt_(double x) { return x == 0.0 ? 0.0 : x * rsqrt_(x); }
+    // one third-order step: y (1 + h + 3/2 h^2), h = 1/2 - 1/2 x y^2 ; rsqrt_(0) = 1.875 * 2^512 (finite)
+    __device__ static __forceinline__ double rsqrt_(double x) {
+        const double y = rsqrt_seed(x);
+        const double h = fma((-0.5 * x) * y, y, 0.5);
+        const double w = fma(1.5, h * h, h);
+        return fma(y, w, y);
+    }
+    // same step in Goldschmidt form: g = x y ~ sqrt(x), sqrt(x) = g (1 + h + 3/2 h^2) ; sqrt_(0) = 0 without a branch
+    __device__ static __forceinline__ double sqrt_(double x) {
+        const double y = rsqrt_seed(x);
+        const double g = x * y;
+        const double h = fma(-g, 0.5 * y, 0.5);
+        const double w = fma(1.5, h * h, h);
+        return fma(g, w, g);
+    }
+    // max(e, 0) on the integer pipe: clear the value when its sign bit is set (-0 -> +0, NaN passes)
+    __device__ static __forceinline__ double pos(double e) {
+        const int hi = __double2hiint(e), keep = ~(hi >> 31);
+        return __hiloint2double(hi & keep, __double2loint(e) & keep);
+    }
     // compare + select (NaN in `a` falls through to `b`; fast math makes no promise about NaN states)
     __device__ static __forceinline__ double mn(double a, double b) { return a < b ? a : b; }
     __device__ static __forceinline__ double mx(double a, double b) { return a > b ? a : b; }
@@ -109,15 +129,33 @@ struct M<double, true> {
         r = fma(r, e * fma(2.0 / 9.0, e, 1.0 / 3.0), r);
         return x * r;
     }
+    // x^(2/3) and x^(1/2) for 0 < x <= 1 from ONE root: r ~ x^(-1/6) seeded in FP32 (lg2 / ex2 on the MUFU pipe,
+    // relative error < 2^-19 for x >= 1e-30), one third-order step r (1 + e/6 + 7/72 e^2), e = 1 - x r^6, in FP64;
+    // x^(2/3) = x r^2, x^(1/2) = x r^3.
+    __device__ static __forceinline__ void roots(double x, double& x23, double& x12) {
+        if (x < 1.0e-30) { x23 = pow23_cold(x); x12 = sqrt_(x); return; }
+        float l, s;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"((float)x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(l * (-1.0f / 6.0f)));
+        double r = (double)s;
+        const double r3 = (r * r) * r;
+        const double e = fma(-x * r3, r3, 1.0);
+        r = fma(r, e * fma(7.0 / 72.0, e, 1.0 / 6.0), r);
+        x23 = x * (r * r);
+        x12 = x23 * r;
+    }
 };
 template <>
 struct M<float, true> {
     __device__ static __forceinline__ float rcp(float x) { return __frcp_rn(x); }
     __device__ static __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
     __device__ static __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    __device__ static __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
     __device__ static __forceinline__ float mn(float a, float b) { return fminf(a, b); }
     __device__ static __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
     __device__ static __forceinline__ float pow23(float x) { float c = cbrtf(x); return c * c; }
+    __device__ static __forceinline__ float pos(float e) { return fmaxf(e, 0.0f); }
+    __device__ static __forceinline__ void roots(float x, float& x23, float& x12) { x23 = pow23(x); x12 = sqrtf(x); }
 };
 
 // volumetric fractions, src/processes/soil/stratigraphy/soil_volume.jl:52-67,103-107
@@ -238,8 +276,10 @@ __device__ __forceinline__ NF cell_conductivity(const DevParams<NF>& p, NF sat, 
         if (liq != NF(1)) I_ice = ice_impedance_cold(p.Omega, liq);
         if (x == NF(1)) return p.Ksat * I_ice;
         // |.| guards the square root against a -1 ulp residue of the approximate power when x -> 1
-        const NF a = 1 - M<NF, FAST>::sqrt_(tabs(1 - M<NF, FAST>::pow23(x)));
-        return tabs(p.Ksat * I_ice * M<NF, FAST>::sqrt_(x) * (a * a));
+        NF x23, x12;
+        M<NF, FAST>::roots(x, x23, x12);
+        const NF a = 1 - M<NF, FAST>::sqrt_(tabs(1 - x23));
+        return tabs(p.Ksat * I_ice * x12 * (a * a));
     }
     return cell_conductivity_reference(p, sat, liq);
 }
@@ -265,12 +305,20 @@ template <class NF, bool FAST>
 __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF thsat) {
     if (FAST) {
         if (p.swrc != TRM_SWRC_VANGENUCHTEN || !p.vg_n_is_2) return swrc_inverse_cold(p, theta, thsat);
-        if (!(theta < thsat)) return NF(0);
         // m = 1/2: psi_m = -(1/alpha) sqrt(se^-2 - 1) ; se = 0 (dry layer) is -Inf as in the reference
         const NF se = fma_(theta, p.r_thspan, p.se_off);   // (theta - theta_res) / (theta_sat - theta_res)
         const NF t = se * se;
-        if (t == NF(0)) return -Lim<NF>::inf();
-        return p.neg_inv_alpha * M<NF, FAST>::sqrt_(tabs(M<NF, FAST>::rcp(t) - NF(1)));   // |.|: rounding guard as se -> 1
+        NF r;
+        if (sizeof(NF) == 8) {
+            // sqrt((1 - t) / t) = a / sqrt(a t), a = 1 - se^2 from one FMA (no cancellation as se -> 1), one
+            // reciprocal square root and no branch: a = 0 gives 0 * (finite seed) = 0 ; |.|: rounding guard as se -> 1
+            const NF a = tabs(fma_(-se, se, NF(1)));
+            r = (p.neg_inv_alpha * a) * M<NF, FAST>::rsqrt_(a * t);
+        } else {
+            r = p.neg_inv_alpha * M<NF, FAST>::sqrt_(tabs(M<NF, FAST>::rcp(t) - NF(1)));
+        }
+        r = t == NF(0) ? -Lim<NF>::inf() : r;
+        return theta < thsat ? r : NF(0);
     }
     return swrc_inverse_reference(p, theta, thsat);
 }
@@ -279,7 +327,7 @@ __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF 
 template <class NF, bool FAST>
 __device__ __forceinline__ NF pressure_head(const DevParams<NF>& p, NF sat, NF wt, NF zc, NF psiz) {
     NF psim = swrc_inverse<NF, FAST>(p, sat * p.por, p.por);
-    NF psih = M<NF, FAST>::mx(NF(0), wt - zc);
+    NF psih = M<NF, FAST>::pos(wt - zc);
     return psih + psim + psiz;
 }
 

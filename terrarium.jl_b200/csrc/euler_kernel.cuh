@@ -44,10 +44,19 @@ __device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
+// integer views used by the fast-math control flow: sign word of a value ; v < 1 for v >= 0 or v < 0 (not NaN)
+__device__ __forceinline__ int sign_word(double v) { return __double2hiint(v); }
+__device__ __forceinline__ int sign_word(float v)  { return __float_as_int(v); }
+__device__ __forceinline__ bool below_one(double v) { return __double2hiint(v) < 0x3FF00000; }
+__device__ __forceinline__ bool below_one(float v)  { return __float_as_int(v) < 0x3F800000; }
 
-// fields of the per-thread pipeline strip (two slots each: written by iteration m, read by m+1 and m+2)
-enum EulerField { EF_U = 0, EF_S, EF_T, EF_P, EF_KAP, EF_KC, EF_KF, EF_QH, EF_G, EF_DQH, EF_QD, EF_COUNT };
-constexpr int EULER_PF = 4;   // depth of the raw prefetch ring (layers in flight: 3)
+// fields of the per-thread pipeline strip. One slot each (written at the end of iteration m, read by iteration
+// m+1 before it is overwritten), except Kf which iteration m+2 still needs (two alternating slots, EF_KF and
+// EF_KF + 1) and, for the LandModel, a copy of the top layer's temperature (EF_TTOP) that outlives the halo iteration.
+enum EulerField { EF_KF = 0, EF_T = 2, EF_P, EF_KAP, EF_KC, EF_QH, EF_G, EF_DQH, EF_QD, EF_TTOP, EF_COUNT };
+constexpr int EULER_PF = 4;   // depth of the prefetch rings consumed when a layer enters (layers in flight: 3)
+constexpr int EULER_RD = 8;   // depth of the U / sat ring: layer k stays in slot (k & 7) from its prefetch (iteration
+                              // k-3) until it is updated (iteration k+2), so the raw values are never copied
 
 constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 6 blocks per SM resident)
 
@@ -56,10 +65,9 @@ constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 
 // k1 and the base U / sat of a layer are prefetched into a second cp.async ring two iterations before its update).
 template <class NF, int LOAD, int MS, int MODE = MODE_EULER>
 struct EulerSmem {
-    static constexpr int RAW_FIELDS = LOAD ? 5 : 2;                                    // U, sat (, T, liq, psi)
     static constexpr int METRICS = MET_COUNT * MS;                                    // elements
-    static constexpr int STRIP = EF_COUNT * 2 * TRM_EULER_BLOCK;
-    static constexpr int RING = RAW_FIELDS * EULER_PF * TRM_EULER_BLOCK;
+    static constexpr int STRIP = EF_COUNT * TRM_EULER_BLOCK;
+    static constexpr int RING = (2 * EULER_RD + (LOAD ? 3 : 0) * EULER_PF) * TRM_EULER_BLOCK;   // U, sat (, T, liq, psi)
     static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * EULER_PF * TRM_EULER_BLOCK;   // k1U, k1S, bU, bS
     static constexpr size_t BYTES = sizeof(NF) * (size_t)(METRICS + STRIP + RING + XRING);
 };
@@ -93,16 +101,18 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     const DevParams<NF>& p = A.p;
     const NF dt = A.dt;
 
-    // shared addresses of this thread's strip: slot(m & 1) of field f is  slot_addr + f * 2 * B * ES
+    // shared addresses of this thread's strip: field f is  strip0 + f * B * ES ; the two Kf slots alternate
     const uint32_t strip0 = met.base + (uint32_t)((SM::METRICS + threadIdx.x) * ES);
-    uint32_t a_cur = strip0 + B * ES, a_prv = strip0;   // iteration m = 1 writes slot 1 and reads slot 0 (zeros)
+    uint32_t kf_cur = strip0 + B * ES, kf_prv = strip0;   // Kf[m] is written to kf_cur, which still holds Kf[m-2] ; kf_prv holds Kf[m-1]
     const uint32_t ring0 = met.base + (uint32_t)((SM::METRICS + SM::STRIP + threadIdx.x) * ES);
-    auto fld = [](int f) { return (uint32_t)(f * 2 * B * ES); };
-    auto rd = [&](uint32_t slot, int f) { return ldsv(slot + fld(f), (NF*)nullptr); };
-    auto wr = [&](uint32_t slot, int f, NF v) { sts(slot + fld(f), v); };
+    auto rd = [&](int f) { return ldsv(strip0 + (uint32_t)(f * B * ES), (NF*)nullptr); };
+    auto wr = [&](int f, NF v) { sts(strip0 + (uint32_t)(f * B * ES), v); };
+    // U and sat of layer k while it is in flight (iterations k-3 .. k+2)
+    auto ringU = [&](int k) { return ring0 + (uint32_t)((k & (EULER_RD - 1)) * B * ES); };
+    auto ringS = [&](int k) { return ring0 + (uint32_t)(((k & (EULER_RD - 1)) + EULER_RD) * B * ES); };
     // the only strip values read before the pipeline has written them: Kf[0] = 0 (never written by the reference)
     // and the (unused) differences formed against the not yet existing layer 0
-    wr(a_cur, EF_KF, NF(0)); wr(a_prv, EF_KF, NF(0)); wr(a_prv, EF_QH, NF(0)); wr(a_prv, EF_G, NF(0)); wr(a_prv, EF_KC, NF(0));
+    sts(kf_cur, NF(0)); sts(kf_prv, NF(0)); wr(EF_QH, NF(0)); wr(EF_G, NF(0)); wr(EF_KC, NF(0));
 
     auto bc_input = [&](int slot) -> NF {
         const int kind = A.bc[slot].kind;
@@ -118,13 +128,13 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     uint32_t oext = (uint32_t)c;   // (Heun stage 2) element offset of the next layer of the extra ring
     auto prefetch = [&](int k, bool always = false) {
         if (always || k <= nz) {
-            const uint32_t dst = ring0 + (uint32_t)((k & (EULER_PF - 1)) * B * ES);
-            cp_async<ES>(dst, A.xU + oin);
-            cp_async<ES>(dst + EULER_PF * B * ES, A.xS + oin);
+            cp_async<ES>(ringU(k), A.xU + oin);
+            cp_async<ES>(ringS(k), A.xS + oin);
             if (LOAD) {
-                cp_async<ES>(dst + 2 * EULER_PF * B * ES, A.xT + oin);
-                cp_async<ES>(dst + 3 * EULER_PF * B * ES, A.xL + oin);
-                if (RICH) cp_async<ES>(dst + 4 * EULER_PF * B * ES, A.xP + oin);
+                const uint32_t dst = ring0 + (uint32_t)((2 * EULER_RD + (k & (EULER_PF - 1))) * B * ES);
+                cp_async<ES>(dst, A.xT + oin);
+                cp_async<ES>(dst + EULER_PF * B * ES, A.xL + oin);
+                if (RICH) cp_async<ES>(dst + 2 * EULER_PF * B * ES, A.xP + oin);
             }
             oin += (uint32_t)ld;
         }
@@ -144,7 +154,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     prefetch(1); prefetch(2); prefetch(3);
 
     NF carry = NF(0);          // over-saturation handed to the layer above (upward sweep of adjust_saturation_profile!)
-    bool any_neg = false;      // a negative saturation needs the downward sweep -> slow path
+    // a negative saturation needs the downward sweep -> slow path. Fast math ORs the sign words of the updated
+    // saturations (one integer instruction per layer; -0 takes the slow path too, which gives the same result)
+    int neg_acc = 0;
+    auto any_neg = [&]() { return neg_acc < 0; };
     int idx = 0;               // lowest unsaturated layer (compute_water_table!), 0 = not found yet
     NF wt_new = NF(0);
     NF Sx_new = NF(0);
@@ -159,17 +172,17 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         prefetch(m + 3, inner);
         // ---- layer m (or the halo above the surface) enters the pipeline ----
         NF Tn, Pn = NF(0), kapn, Kfn = NF(0);     // T, psi, kappa of layer m ; Kf[m]
-        const NF Kf1 = RICH ? rd(a_prv, EF_KF) : NF(0);   // Kf[m-1]
+        const NF Kf1 = RICH ? ldsv(kf_prv, (NF*)nullptr) : NF(0);   // Kf[m-1]
         if (inner || m <= nz) {
             cp_async_wait<3>();   // all but the 3 most recent groups have landed: layer m is in the ring
-            const uint32_t src = ring0 + (uint32_t)((m & (EULER_PF - 1)) * B * ES);
-            const NF Ur = ldsv(src, (NF*)nullptr);
-            const NF sr = ldsv(src + EULER_PF * B * ES, (NF*)nullptr);
+            const NF Ur = ldsv(ringU(m), (NF*)nullptr);
+            const NF sr = ldsv(ringS(m), (NF*)nullptr);
             NF ln;
             if (LOAD) {
-                Tn = ldsv(src + 2 * EULER_PF * B * ES, (NF*)nullptr);
-                ln = ldsv(src + 3 * EULER_PF * B * ES, (NF*)nullptr);
-                if (RICH) Pn = ldsv(src + 4 * EULER_PF * B * ES, (NF*)nullptr);
+                const uint32_t src = ring0 + (uint32_t)((2 * EULER_RD + (m & (EULER_PF - 1))) * B * ES);
+                Tn = ldsv(src, (NF*)nullptr);
+                ln = ldsv(src + EULER_PF * B * ES, (NF*)nullptr);
+                if (RICH) Pn = ldsv(src + 2 * EULER_PF * B * ES, (NF*)nullptr);
             } else {
                 energy_to_temperature<NF, FAST>(p, Ur, sr, Tn, ln);
                 if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
@@ -178,18 +191,18 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             if (RICH) {
                 // cell conductivity and face conductivity Kf[m], soil_hydrology.jl:249-276
                 const NF Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
-                Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : Mx::mn(Kcn, rd(a_prv, EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
-                wr(a_cur, EF_KC, Kcn);
+                Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : Mx::mn(Kcn, rd(EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
+                wr(EF_KC, Kcn);
             } else if (LAND && !inner && m == nz) {
                 Kfn = cell_conductivity<NF, FAST>(p, sr, ln);   // compute_hydraulics! (soil_hydrology.jl:145-163): the runoff scheme reads Kf[Nz] = Kc[Nz]
             }
         } else if (!inner && m == nz + 1) {   // halo above the surface, built from layer nz (prv)
-            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(a_prv, EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
+            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
             // conductivity of the halo cell: same (sat, liq) as layer nz when the saturation halo is a copy, else
             // sat = 0, for which the liquid fraction drops out of the constituent sum
             const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
-            kapn = copy ? rd(a_prv, EF_KAP) : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
-            if (RICH) Pn = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, rd(a_prv, EF_P), bc_input(TRM_BC_PRESSURE_TOP), met.dzf(nz + 1), true);
+            kapn = copy ? rd(EF_KAP) : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
+            if (RICH) Pn = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, rd(EF_P), bc_input(TRM_BC_PRESSURE_TOP), met.dzf(nz + 1), true);
             Kfn = Kf1;              // Kf[Nz+1] = Kf[Nz] ; Kf[Nz+2] is a halo face (0)
         } else {
             Tn = NF(0); kapn = NF(0);
@@ -202,8 +215,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             kapp = copy ? kapn : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
             if (RICH) Pp = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, Pn, bc_input(TRM_BC_PRESSURE_BOTTOM), met.dzf(1), false);
         } else {
-            Tp = rd(a_prv, EF_T); kapp = rd(a_prv, EF_KAP);
-            if (RICH) Pp = rd(a_prv, EF_P);
+            Tp = rd(EF_T); kapp = rd(EF_KAP);
+            if (RICH) Pp = rd(EF_P);
         }
         // ---- heat flux and head gradient at face m (diffusive_heat_flux, soil_energy.jl:134-149) ----
         NF qhn = NF(0), gn = NF(0);
@@ -211,12 +224,12 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             qhn = -((kapn + kapp) / 2) * ((Tn - Tp) * met.rdzf(m));
             if (RICH) gn = (Pn - Pp) * met.rdzf(m);
         }
-        const NF dqhn = qhn - rd(a_prv, EF_QH);
+        const NF dqhn = qhn - rd(EF_QH);
         // ---- Darcy flux at face m-1 (darcy_flux, soil_hydrology_rre.jl:119-131) ----
         NF qdn = NF(0);
         if (RICH && (inner || m >= 2)) {
-            const NF g = rd(a_prv, EF_G);
-            const NF Kf2 = rd(a_cur, EF_KF);   // Kf[m-2] (0 for m = 2: Kf[0] is never written by the reference)
+            const NF g = rd(EF_G);
+            const NF Kf2 = ldsv(kf_cur, (NF*)nullptr);   // Kf[m-2] (0 for m = 2: Kf[0] is never written by the reference)
             NF Kk;
             if (FAST) Kk = Mx::mn(Kf1, g < 0 ? Kf2 : Kfn);
             else Kk = (g < 0 ? jmin(Kf2, Kf1) : NF(0)) + (g >= 0 ? jmin(Kf1, Kfn) : NF(0));
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         NF G_top = NF(0), infil_top = NF(0);   // fluxes coupling the surface to the top soil layer (same iteration)
         if (LAND && !inner && m == nz + 2) {
             if (H2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
-            else land_surface(A, c, RICH, rd(a_cur, EF_T), rd(a_cur, EF_S), rd(a_cur, EF_KF), met.dzc(nz), G_top, infil_top);
+            else land_surface(A, c, RICH, rd(EF_TTOP), ldsv(ringS(nz), (NF*)nullptr), ldsv(kf_cur, (NF*)nullptr), met.dzc(nz), G_top, infil_top);
         }
 
         if (inner || m >= 3) {
@@ -235,10 +248,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             const int j = m - 2;
             const uint32_t o = oout;
             oout += (uint32_t)ld;
-            NF tU = -(rd(a_prv, EF_DQH) * met.rdzc(j));                          // soil_energy.jl:112-131
+            NF tU = -(rd(EF_DQH) * met.rdzc(j));                          // soil_energy.jl:112-131
             NF tS = NF(0);
             if (RICH) {
-                const NF dth = -((qdn - rd(a_prv, EF_QD)) * met.rdzc(j)) + NF(0) + p.vwcf;   // soil_hydrology_rre.jl:95-117
+                const NF dth = -((qdn - rd(EF_QD)) * met.rdzc(j)) + NF(0) + p.vwcf;   // soil_hydrology_rre.jl:95-117
                 tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
             }
             NF Ub, sb;   // base state the update is applied to
@@ -247,10 +260,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 tU = (ldsv(x, (NF*)nullptr) + tU) / 2;
                 Ub = ldsv(x + 2 * EULER_PF * B * ES, (NF*)nullptr);
                 if (RICH) { tS = (ldsv(x + EULER_PF * B * ES, (NF*)nullptr) + tS) / 2; sb = ldsv(x + 3 * EULER_PF * B * ES, (NF*)nullptr); }
-                else sb = rd(a_cur, EF_S);   // NoFlow: the saturation is not a prognostic variable
+                else sb = ldsv(ringS(j), (NF*)nullptr);   // NoFlow: the saturation is not a prognostic variable
             } else {
                 if (H1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }   // k1, before the Flux BCs
-                Ub = rd(a_cur, EF_U); sb = rd(a_cur, EF_S);
+                Ub = ldsv(ringU(j), (NF*)nullptr); sb = ldsv(ringS(j), (NF*)nullptr);
             }
             // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
             if (!inner && j == nz) {
@@ -272,13 +285,15 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
                 sn = sn + carry;
                 if (inner || j < nz) {
-                    const NF e = Mx::mx(sn - 1, NF(0));
+                    const NF e = Mx::pos(sn - 1);
                     sn -= e;
                     carry = FAST ? e * met.dzc(j) * met.rdzc(j + 1) : e * met.dzc(j) / met.dzc(j + 1);
                 }
-                if (sn < 0) any_neg = true;
+                if (FAST) neg_acc |= sign_word(sn); else if (sn < 0) neg_acc = -1;
             }
-            if (RICH && any_neg) {
+            // (fast math, inner layers: the regular stores below ARE the raw values the slow path re-reads -- no
+            //  surface excess, no clamp -- so the flag needs no branch here; the closure stores are overwritten later)
+            if (RICH && !(inner && FAST) && any_neg()) {
                 // raw values for the slow path below (the downward sweep needs the whole profile)
                 A.yU[o] = Un; A.yS[o] = sn;
             } else {
@@ -286,13 +301,13 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                     // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
                     if (!FAST && j >= 2) sn = sn + jmax(-sn, NF(0));
                     if (!inner && j == nz) {                         // top excess -> surface_excess_water (:210-214)
-                        const NF e = Mx::mx(sn - 1, NF(0));
+                        const NF e = Mx::pos(sn - 1);
                         sn -= e;
                         Sx_new += e * met.dzc(nz);
                     }
                     if (!FAST && !inner && j == 1) sn = jmax(sn, NF(0));       // :216
                     A.yS[o] = sn;
-                    if (idx == 0 && sn < 1) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
+                    if (idx == 0 && (FAST ? below_one(sn) : sn < 1)) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                 }
                 A.yU[o] = Un;
                 if (CLOSE) {
@@ -305,15 +320,11 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             }
         }
         // ---- what later iterations need from this one ----
-        if (inner || m <= nz) {   // U and sat of layer m wait in the strip until the layer is updated (iteration m + 2)
-            const uint32_t src = ring0 + (uint32_t)((m & (EULER_PF - 1)) * B * ES);
-            wr(a_cur, EF_U, ldsv(src, (NF*)nullptr));
-            wr(a_cur, EF_S, ldsv(src + EULER_PF * B * ES, (NF*)nullptr));
-        }
-        wr(a_cur, EF_T, Tn); wr(a_cur, EF_KAP, kapn); wr(a_cur, EF_QH, qhn); wr(a_cur, EF_DQH, dqhn);
-        if (RICH) { wr(a_cur, EF_P, Pn); wr(a_cur, EF_KF, Kfn); wr(a_cur, EF_G, gn); wr(a_cur, EF_QD, qdn); }
-        else if (LAND) wr(a_cur, EF_KF, Kfn);
-        const uint32_t t = a_cur; a_cur = a_prv; a_prv = t;
+        wr(EF_T, Tn); wr(EF_KAP, kapn); wr(EF_QH, qhn); wr(EF_DQH, dqhn);
+        if (LAND && !inner && m == nz) wr(EF_TTOP, Tn);
+        if (RICH) { wr(EF_P, Pn); sts(kf_cur, Kfn); wr(EF_G, gn); wr(EF_QD, qdn); }
+        else if (LAND) sts(kf_cur, Kfn);
+        const uint32_t t = kf_cur; kf_cur = kf_prv; kf_prv = t;
     };
     {
         int m = 1;
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     }
     if (!RICH) return;
 
-    if (!any_neg) {
+    if (!any_neg()) {
         if (idx == 0) { idx = nz + 1; wt_new = met.zF(nz + 1); }   // all saturated: z of the surface (halo cell / fallback give the same)
         A.yWt[c] = wt_new;
         if (H1) return;            // the stage state needs no surface excess water and no closure fields
