@@ -79,7 +79,7 @@ def build_case(trm, make_integrator, ncol_global, rank, world, device, nf, math,
     if model_kind == "land":
         # secondary workload (BASELINE configs[3], bare ground): synthetic atmosphere of BASELINE.md section 5 with a
         # calm wind (see tests/test_parity.py on the stability of the as-coded skin / soil coupling at 3 m/s)
-        model = trm.LandModel(grid, soil=richards_soil())
+        model = trm.LandModel(grid, soil=richards_soil(), vegetation=None)
         day = 86400.0
         hours = np.arange(0, 73, dtype=np.float64)
         rain = np.where((hours % 24) < 6, 2.0e-8, 0.0)

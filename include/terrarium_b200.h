@@ -6,8 +6,8 @@
  *   (reference: src/timesteppers/forward_euler.jl:19-31, src/timesteppers/heun.jl:37-71),
  * i.e. update_state! (src/state_variables.jl:72-80), explicit_step!
  * (src/timesteppers/abstract_timestepper.jl:65-77) and closure! (src/models/soil/soil_model.jl:51-54,
- * src/models/coupled/land_model.jl:98-102) for SoilModel and (bare-ground) LandModel on a
- * ColumnGrid / ColumnRingGrid.  The reference has no FFI of its own for this path (it is pure Julia
+ * src/models/coupled/land_model.jl:98-102) for SoilModel and LandModel (bare ground, or with the PALADYN
+ * vegetation / canopy processes of VegetationCarbon) on a ColumnGrid / ColumnRingGrid.  The reference has no FFI of its own for this path (it is pure Julia
  * dispatching KernelAbstractions kernels through Oceananigans' launch!, src/grids/grid_utils.jl:2-6);
  * the entry points below are what a `ccall` based Julia method of timestep!/run!/initialize would bind
  * (see INTEGRATION.md and terrarium.jl_b200/julia/TerrariumB200.jl).
@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TRM_ABI_VERSION 1
+#define TRM_ABI_VERSION 2
 #define TRM_MAX_NZ 128       /* per-column layers supported by the fused kernels            */
 #define TRM_NUM_USER_INPUTS 8
 
@@ -72,6 +72,12 @@ enum trm_unsat_k     { TRM_UNSATK_LINEAR = 0, TRM_UNSATK_VANGENUCHTEN = 1 };
 enum trm_halo        { TRM_HALO_ZERO = 0, TRM_HALO_COPY = 1 };
 /* Skin temperature scheme, src/processes/surface_energy/skin_temperature.jl:12,52 */
 enum trm_skin        { TRM_SKIN_IMPLICIT = 0, TRM_SKIN_PRESCRIBED = 1 };
+/* LandModel(vegetation = ...): nothing -> BareGroundEvaporation + NoCanopyInterception (land_model.jl:114-125);
+ * VegetationCarbon (src/processes/vegetation/vegetation_carbon.jl:6-66: LUEPhotosynthesis, MedlynStomatalConductance,
+ * PALADYNAutotrophicRespiration, PALADYNPhenology, PALADYNCarbonDynamics, PALADYNVegetationDynamics,
+ * StaticExponentialRootDistribution, FieldCapacityLimitedPAW) with the default SurfaceHydrology
+ * (PALADYNCanopyInterception + PALADYNCanopyEvapotranspiration + DirectSurfaceRunoff, surface_hydrology.jl:22-29). */
+enum trm_vegetation  { TRM_VEG_NONE = 0, TRM_VEG_CARBON = 1 };
 /* Arithmetic contract of the CUDA kernels.
  *  FAITHFUL: same operations in the same order as the reference/oracle (true divisions,
  *            pow where the reference calls ^), no FMA contraction.
@@ -109,7 +115,9 @@ enum trm_input_id {
     TRM_IN_DAYTIME_LENGTH = 16,
     TRM_IN_CO2 = 17,
     TRM_IN_SKIN_TEMPERATURE = 18, /* only read with TRM_SKIN_PRESCRIBED */
-    TRM_IN_COUNT = 19
+    TRM_IN_SAI = 19,                    /* stem area index, canopy_interception.jl:54 (no default: 0)          */
+    TRM_IN_DAILY_LEAF_RESPIRATION = 20, /* autotrophic_respiration.jl:33 (no default: 0)                       */
+    TRM_IN_COUNT = 21
 };
 /* How an input is produced at clock time t (device resident, evaluated inside the stage kernel). */
 enum trm_source {
@@ -144,7 +152,30 @@ enum trm_field_id {
     TRM_F_SURFACE_RUNOFF = 18,
     TRM_F_TEND_INTERNAL_ENERGY = 19,  /* materialised only by trm_compute_tendencies (debug/tests)     */
     TRM_F_TEND_SATURATION = 20,
-    TRM_F_COUNT = 21
+    /* vegetated LandModel (TRM_VEG_CARBON) ; all 2-D unless noted */
+    TRM_F_CARBON_VEGETATION = 21,         /* prognostic, carbon_dynamics.jl:43                                 */
+    TRM_F_VEGETATION_AREA_FRACTION = 22,  /* prognostic, vegetation_dynamics.jl:23                             */
+    TRM_F_CANOPY_WATER = 23,              /* prognostic, canopy_interception.jl:48                             */
+    TRM_F_BALANCED_LEAF_AREA_INDEX = 24,  /* auxiliaries from here */
+    TRM_F_LEAF_AREA_INDEX = 25,
+    TRM_F_PHENOLOGY_FACTOR = 26,
+    TRM_F_CANOPY_WATER_CONDUCTANCE = 27,
+    TRM_F_LEAF_TO_AIR_CO2_RATIO = 28,
+    TRM_F_NET_ASSIMILATION = 29,          /* read back by the next evaluation of the stomatal conductance       */
+    TRM_F_LEAF_RESPIRATION = 30,
+    TRM_F_GROSS_PRIMARY_PRODUCTION = 31,
+    TRM_F_AUTOTROPHIC_RESPIRATION = 32,
+    TRM_F_NET_PRIMARY_PRODUCTION = 33,
+    TRM_F_SOIL_MOISTURE_LIMITING_FACTOR = 34,
+    TRM_F_CANOPY_WATER_INTERCEPTION = 35,
+    TRM_F_CANOPY_WATER_REMOVAL = 36,
+    TRM_F_SATURATION_CANOPY_WATER = 37,
+    TRM_F_RAINFALL_GROUND = 38,
+    TRM_F_EVAPORATION_CANOPY = 39,
+    TRM_F_TRANSPIRATION = 40,
+    TRM_F_PLANT_AVAILABLE_WATER = 41,     /* 3-D [nz][ld], materialised by trm_compute_auxiliary                */
+    TRM_F_ROOT_FRACTION = 42,             /* 3-D static function of depth (root_distribution.jl:47-56): get only */
+    TRM_F_COUNT = 43
 };
 
 /* ---- parameters ---------------------------------------------------------------------------
@@ -188,6 +219,28 @@ typedef struct trm_params {
     /* Surface hydrology */
     double tau_r;                 /* DirectSurfaceRunoff 3600 s, runoff/direct_surface_runoff.jl:17 */
     double evap_beta;             /* ConstantEvaporationResistanceFactor 1.0 */
+    /* ---- vegetated LandModel (TRM_VEG_CARBON) ---- */
+    double field_capacity;        /* ConstantSoilHydraulics 0.25, soil_hydraulic_properties.jl:77 */
+    double wilting_point;         /* 0.05, :80 */
+    double C_mass;                /* PhysicalConstants 12.0 gC/mol, physical_constants.jl:50 */
+    /* LUEPhotosynthesis, src/processes/vegetation/photosynthesis.jl:19-67 */
+    double tau25, Kc25, Ko25, q10_tau, q10_Kc, q10_Ko;       /* 2600 30 3e4 0.57 2.1 1.2 */
+    double alpha_leaf, alpha_a, alpha_C3, cq, k_ext;         /* 0.17 0.5 0.08 4.6e-6 0.5 */
+    double T_CO2_high, T_CO2_low, T_photos_high, T_photos_low, theta_r;   /* 42 -4 30 15 0.7 */
+    /* MedlynStomatalConductance, stomatal_conductance.jl:18-25 */
+    double g1, g_min;             /* 2.3 0.5 */
+    /* PALADYNAutotrophicRespiration, autotrophic_respiration.jl:16-25 */
+    double cn_sapwood, cn_root, aws;                         /* 330 29 10 */
+    /* PALADYNCarbonDynamics, carbon_dynamics.jl:18-39 */
+    double SLA, awl, LAI_min, LAI_max, gamma_L, gamma_R, gamma_S;   /* 10 2 1 6 0.3 0.3 0.05 */
+    /* PALADYNVegetationDynamics, vegetation_dynamics.jl:14-20 */
+    double nu_seed, gamma_v_min;  /* 0.001 0.002 */
+    /* StaticExponentialRootDistribution, root_distribution.jl:25-31 */
+    double root_a, root_b;        /* 7 2 */
+    /* PALADYNCanopyInterception, canopy_interception.jl:33-45 */
+    double alpha_int, k_ext_can, w_can_max, tau_w;           /* 0.2 0.5 2e-4 86400 */
+    /* PALADYNCanopyEvapotranspiration, canopy_evapotranspiration.jl:32-44 */
+    double C_can;                 /* 0.006 */
 } trm_params;
 
 typedef struct trm_bc {
@@ -210,6 +263,7 @@ typedef struct trm_config {
     int32_t sat_halo;         /* trm_halo (NoFlow only) */
     int32_t skin;             /* trm_skin (LandModel only) */
     int32_t math;             /* trm_math */
+    int32_t vegetation;       /* trm_vegetation (LandModel only) */
     const double* z_faces;    /* nz+1 face elevations, bottom .. 0 (column_grid.jl:30-31); copied */
     trm_params params;
     trm_bc bc[TRM_BC_NSLOTS];

@@ -81,16 +81,25 @@ struct State {  // one StateVariables instance (src/state_variables.jl:16-54)
     std::vector<NF> Kf;
     // 2-D
     std::vector<NF> Sx, tendSx, wt, Ts, tendTs, G, SWup, LWup, Rnet, Hs, Hl, Egnd, infil, runoff;
+    // vegetated LandModel: prognostic 2-D (+ tendencies), auxiliary 2-D, plant available water (nz+2) x nc
+    std::vector<NF> Cveg, nu, wcan, tendCveg, tendnu, tendwcan;
+    std::vector<NF> LAIb, LAI, phen, gwcan, lamc, An, Rd, GPP, Ra, NPP, betasm, Ican, Rcan, fcan, raing, Ecan, transp;
+    std::vector<NF> PAW;
     std::vector<std::vector<NF>> in;  // materialised input fields [TRM_IN_COUNT][nc]
     NF time = 0; int64_t iteration = 0;
 
-    void alloc(int nz_, int64_t nc_, bool land) {
+    void alloc(int nz_, int64_t nc_, bool land, bool veg = false) {
         nz = nz_; nc = nc_;
         size_t c3 = (size_t)(nz + 2) * nc, f3 = (size_t)(nz + 3) * nc;
         for (auto* v : {&U, &T, &liq, &sat, &psi, &tendU, &tendsat}) v->assign(c3, NF(0));
         Kf.assign(f3, NF(0));
         for (auto* v : {&Sx, &tendSx, &wt}) v->assign(nc, NF(0));
         if (land) for (auto* v : {&Ts, &tendTs, &G, &SWup, &LWup, &Rnet, &Hs, &Hl, &Egnd, &infil, &runoff}) v->assign(nc, NF(0));
+        if (veg) {
+            for (auto* v : {&Cveg, &nu, &wcan, &tendCveg, &tendnu, &tendwcan, &LAIb, &LAI, &phen, &gwcan, &lamc, &An, &Rd, &GPP, &Ra, &NPP,
+                            &betasm, &Ican, &Rcan, &fcan, &raing, &Ecan, &transp}) v->assign(nc, NF(0));
+            PAW.assign(c3, NF(0));
+        }
         in.assign(TRM_IN_COUNT, std::vector<NF>());
     }
     inline size_t ix(int k, int64_t c) const { return (size_t)k * nc + c; }
@@ -100,7 +109,9 @@ template <class NF>
 struct Oracle {
     trm_config cfg{};
     int nz = 0; int64_t nc = 0;
-    bool land = false, richards = false, heun = false;
+    bool land = false, richards = false, heun = false, veg = false;
+    trm_params vp{};          // vegetation parameters are converted to NF where they are used (Struct{NF} fields)
+    std::vector<NF> rootf;    // static root fraction per layer (root_distribution.jl:47-56), index 1..nz
     // grid metrics in NF  [OCN] generate_coordinate: halo faces extend with the edge spacing,
     // centres are face midpoints, dzf are centre differences.
     std::vector<NF> zF, zC, dzc, dzf, rdzc, rdzf;  // indices as in the reference (1-based + halos)
@@ -117,7 +128,9 @@ struct Oracle {
     int setup(const trm_config& c) {
         cfg = c; nz = c.nz; nc = c.ncol;
         land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
+        veg = land && c.vegetation == TRM_VEG_CARBON;
         const trm_params& p = c.params;
+        vp = p;
         // ---- grid (column_grid.jl:30-31: z_coords converted to NF, then [OCN] metrics in NF)
         zF.assign(nz + 3, NF(0)); zC.assign(nz + 2, NF(0)); dzc.assign(nz + 2, NF(0)); dzf.assign(nz + 3, NF(0));
         rdzc.assign(nz + 2, NF(0)); rdzf.assign(nz + 3, NF(0));
@@ -139,7 +152,15 @@ struct Oracle {
         rho_a = (NF)p.rho_a; c_a = (NF)p.c_a; Llg = (NF)p.Llg; Tref = (NF)p.Tref; sigma = (NF)p.sigma; eps_mw = (NF)p.eps_mw;
         albedo = (NF)p.albedo; emis = (NF)p.emissivity; kappa_skin = (NF)p.kappa_skin; C_h = (NF)p.C_h; Vmin = (NF)p.min_windspeed;
         tau_r = (NF)p.tau_r; beta = (NF)p.evap_beta;
-        st.alloc(nz, nc, land);
+        st.alloc(nz, nc, land, veg);
+        if (veg) {
+            // root_fraction(rootdist, grid, ...), root_distribution.jl:47-56: density at the cell centres times the
+            // layer thickness, normalised by its sum over the column
+            rootf.assign(nz + 2, NF(0));
+            NF a = (NF)p.root_a, b = (NF)p.root_b, sum = 0;
+            for (int k = 1; k <= nz; ++k) { rootf[k] = NF(0.5) * (a * std::exp(a * zC[k]) + b * std::exp(b * zC[k])) * dzc[k]; sum += rootf[k]; }
+            for (int k = 1; k <= nz; ++k) rootf[k] = rootf[k] / sum;
+        }
         src.assign(TRM_IN_COUNT, InputSource());
         src_field.assign(TRM_IN_COUNT, {}); src_mean.assign(TRM_IN_COUNT, {}); src_amp.assign(TRM_IN_COUNT, {});
         src_phase.assign(TRM_IN_COUNT, {}); src_table.assign(TRM_IN_COUNT, {});
@@ -362,7 +383,7 @@ struct Oracle {
     void compute_runoff(State<NF>& s) {
 #pragma omp parallel for schedule(static)
         for (int64_t c = 0; c < nc; ++c) {
-            NF rain = s.in[TRM_IN_RAINFALL][c];  // rainfall_ground aliases rainfall (canopy_interception.jl:11-15)
+            NF rain = veg ? s.raing[c] : s.in[TRM_IN_RAINFALL][c];  // rainfall_ground aliases rainfall without canopy (canopy_interception.jl:11-15)
             // surface_excess_water(i, j, grid, fields, hydrology): the prognostic field under RichardsEq
             // (soil_hydrology_rre.jl:28), identically zero for immobile soil water (soil_hydrology.jl:138)
             NF S = richards ? s.Sx[c] : NF(0), Kt = s.Kf[s.ix(nz, c)], sat_top = s.sat[s.ix(nz, c)];
@@ -386,7 +407,9 @@ struct Oracle {
         double ra = r_a(s, c);
         NF Ta = s.in[TRM_IN_AIR_TEMPERATURE][c];
         NF hs = (NF)((double)(c_a * rho_a) * ((double)(Tsurf - Ta) / ra));  // turbulent_fluxes.jl:85-105
-        NF hl = Llg * rho_a * s.Egnd[c];                          // turbulent_fluxes.jl:137-150 (coupled to ET)
+        // turbulent_fluxes.jl:137-150 (coupled to ET): surface_humidity_flux = E_gnd (+ E_can + T_can, canopy_evapotranspiration.jl:75-80)
+        NF Qh = veg ? s.Egnd[c] + s.Ecan[c] + s.transp[c] : s.Egnd[c];
+        NF hl = Llg * rho_a * Qh;
         s.Hs[c] = hs; s.Hl[c] = hl;
         s.G[c] = rnet - hs - hl;                                  // skin_temperature.jl:76-80
     }
@@ -403,15 +426,185 @@ struct Oracle {
             }
         }
     }
+    // ---- vegetated LandModel (VegetationCarbon + PALADYN canopy hydrology) ---------------------------------
+    inline NF skin_T(const State<NF>& s, int64_t c) const { return cfg.skin == TRM_SKIN_PRESCRIBED ? s.in[TRM_IN_SKIN_TEMPERATURE][c] : s.Ts[c]; }
+    // compute_vpd physical_constants.jl:83-97 [Pa]
+    inline NF vpd_pa(const State<NF>& s, int64_t c, NF Tsurf) const {
+        NF q = s.in[TRM_IN_SPECIFIC_HUMIDITY][c], p = s.in[TRM_IN_AIR_PRESSURE][c];
+        NF ea = q * p / (eps_mw + (1 - eps_mw) * q);
+        return jmax(e_sat(Tsurf) - ea, NF(0.1));
+    }
+    // compute_auxiliary!(state, grid, veg::VegetationCarbon, ...), vegetation_carbon.jl:71-104 : one loop per launch
+    void compute_vegetation(State<NF>& s) {
+        const NF th_fc = (NF)vp.field_capacity, th_wp = (NF)vp.wilting_point;
+        // FieldCapacityLimitedPAW: XYZ kernel (plant_available_water.jl:64-89) ...
+#pragma omp parallel for schedule(static)
+        for (int64_t c0 = 0; c0 < nc; c0 += CHUNK) {
+            int64_t c1 = std::min(nc, c0 + CHUNK);
+            for (int k = 1; k <= nz; ++k)
+                for (int64_t c = c0; c < c1; ++c) {
+                    Fr f = fractions(s.sat[s.ix(k, c)], s.liq[s.ix(k, c)]);
+                    s.PAW[s.ix(k, c)] = jmax(jmin(NF(1), (f.water - th_wp) / (th_fc - th_wp)), NF(0));
+                }
+        }
+        // ... then compute!(soil_moisture_limiting_factor) = Integral(PAW * root_fraction / dz, dims = 3) (:31-35)
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF b = 0;
+            for (int k = 1; k <= nz; ++k) b += s.PAW[s.ix(k, c)] * rootf[k] / dzc[k] * dzc[k];
+            s.betasm[c] = b;
+        }
+        passes += 3;
+        const NF SLA = (NF)vp.SLA, awl = (NF)vp.awl;
+        // PALADYNCarbonDynamics auxiliary: LAI_b (carbon_dynamics.jl:82-85,167-170)
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) s.LAIb[c] = s.Cveg[c] / ((NF(2.0) / SLA) + awl);
+        // PALADYNPhenology (phenology.jl:33-70): f_deciduous = 0, phen = 1
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF fdec = 0, ph = NF(1.0);
+            s.phen[c] = ph;
+            s.LAI[c] = (fdec * ph + (NF(1.0) - fdec)) * s.LAIb[c];
+        }
+        // MedlynStomatalConductance (stomatal_conductance.jl:45-82,106-118): reads the net assimilation of the
+        // PREVIOUS evaluation (the circular dependency noted at vegetation_carbon.jl:89-91)
+        const NF g1 = (NF)vp.g1, g_min = (NF)vp.g_min / 1000, k_ext = (NF)vp.k_ext;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF vpd = vpd_pa(s, c, s.in[TRM_IN_AIR_TEMPERATURE][c]);
+            NF co2 = s.in[TRM_IN_CO2][c];
+            NF g0 = g_min * (1 - std::exp(-k_ext * s.LAI[c])) * s.betasm[c];
+            s.gwcan[c] = g0 + NF(1.6) * (1 + g1 / std::sqrt(vpd)) * s.An[c] / co2 * NF(1.0e6);
+            s.lamc[c] = NF(1.0) - NF(1.0) / (NF(1.0) + g1 / std::sqrt(vpd * NF(1.0e-3)));
+        }
+        // LUEPhotosynthesis (photosynthesis.jl:284-344)
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF Rd, An;
+            photosynthesis(s.in[TRM_IN_AIR_TEMPERATURE][c], s.in[TRM_IN_SHORTWAVE_DOWN][c], s.in[TRM_IN_AIR_PRESSURE][c],
+                           s.in[TRM_IN_CO2][c], s.LAI[c], s.lamc[c], s.betasm[c], Rd, An);
+            s.Rd[c] = Rd; s.An[c] = An; s.GPP[c] = An * NF(1.0e-3);
+        }
+        // PALADYNAutotrophicRespiration (autotrophic_respiration.jl:46-154)
+        const NF cn_sap = (NF)vp.cn_sapwood, cn_root = (NF)vp.cn_root, aws = (NF)vp.aws;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF Ta = s.in[TRM_IN_AIR_TEMPERATURE][c], Tsoil = s.T[s.ix(nz, c)];
+            NF Rdl = s.in[TRM_IN_DAILY_LEAF_RESPIRATION][c], ph = s.phen[c], Cv = s.Cveg[c], GPP = s.GPP[c];
+            auto f_temp = [](NF T) { return std::exp(NF(308.56) * (NF(1.0) / NF(56.02) - NF(1.0) / (NF(46.02) + T))); };
+            NF f_soil = (Tsoil > 7) ? f_temp(Tsoil) : NF(0);
+            NF f_air = f_temp(Ta);
+            NF resp10 = NF(0.066);
+            NF R_leaf = Rdl / NF(1000.0);
+            NF R_stem = resp10 * f_air * (awl * ((NF(2.0) / SLA) + awl)) / (Cv * aws * cn_sap);
+            NF R_root = resp10 * f_soil * ph * (NF(2.0) / SLA) / (SLA * Cv * cn_root);
+            NF Rm = R_leaf + R_stem + R_root;
+            NF Rg = NF(0.25) * (GPP - Rm);
+            NF Ra = Rm + Rg;
+            s.Ra[c] = Ra; s.NPP[c] = GPP - Ra;
+        }
+    }
+    // compute_respiration_assimilation, photosynthesis.jl:212-275
+    void photosynthesis(NF T_air, NF swdown, NF pres, NF co2, NF LAI, NF lamc, NF beta_sm, NF& Rd, NF& An) const {
+        NF pres_O2 = NF(0.209) * pres;               // physics_utils.jl:16-20
+        NF pres_a = co2 * NF(1.0e-6) * pres;         // physics_utils.jl:27-30
+        Rd = 0; An = 0;
+        if (!(swdown > 0 && T_air > NF(-3.0))) return;
+        NF ex = (T_air - NF(25.0)) * NF(0.1);
+        NF tau = (NF)vp.tau25 * std::pow((NF)vp.q10_tau, ex);
+        NF Kc = (NF)vp.Kc25 * std::pow((NF)vp.q10_Kc, ex);
+        NF Ko = (NF)vp.Ko25 * std::pow((NF)vp.q10_Ko, ex);
+        NF Gs = pres_O2 / (NF(2.0) * tau);
+        if (!(LAI > 0)) return;
+        NF PAR = NF(0.5) * swdown * (NF(1.0) - (NF)vp.alpha_leaf) * (NF)vp.cq;
+        NF APAR = (NF)vp.alpha_a * PAR * (NF(1.0) - std::exp(-(NF)vp.k_ext * LAI));
+        NF pres_i = lamc * pres_a;
+        // compute_temperature_stress :143-169
+        NF Tl = (NF)vp.T_CO2_low, Th = (NF)vp.T_CO2_high, Pl = (NF)vp.T_photos_low, Ph = (NF)vp.T_photos_high;
+        NF k1 = NF(2.0) * std::log(NF(1.0) / NF(0.99) - NF(1.0)) / (Tl - Pl);
+        NF k2 = NF(0.5) * (Tl + Pl);
+        NF k3 = std::log(NF(0.99) / NF(0.01)) / (Th - Ph);
+        NF T_stress = 0;
+        if (Tl < T_air && T_air < Th) {
+            NF low = NF(1.0) / (NF(1.0) + std::exp(k1 * (k2 - T_air)));
+            NF high = NF(1.0) - NF(0.01) * std::exp(k3 * (T_air - Ph));
+            T_stress = low * high;
+        }
+        // compute_assimilation_factors :185-194, compute_Vc_max :208-211 (called with APAR), compute_Rd, compute_Ag
+        NF aC3 = (NF)vp.alpha_C3, th = (NF)vp.theta_r;
+        NF c_1 = aC3 * T_stress * (NF)vp.C_mass * (pres_i - Gs) / (pres_i + NF(2.0) * Gs);
+        NF c_2 = (pres_i - Gs) / (pres_i + Kc * (NF(1.0) + pres_O2 / Ko));
+        NF Vc_max = c_1 * APAR * (pres_i + Kc * (NF(1.0) + pres_O2 / Ko)) / (pres_i - Gs);
+        Rd = aC3 * Vc_max * beta_sm;
+        NF JE = c_1 * APAR, JC = c_2 * Vc_max;
+        NF sJ = JE + JC;
+        NF Ag = (sJ - std::sqrt(sJ * sJ - NF(4) * th * JE * JC)) / (NF(2) * th) * beta_sm;
+        An = Ag - Rd;
+    }
+    // PALADYNCanopyInterception auxiliary, canopy_interception.jl:161-187
+    void compute_canopy_interception(State<NF>& s) {
+        const NF a_int = (NF)vp.alpha_int, k_ext = (NF)vp.k_ext_can, wmax0 = (NF)vp.w_can_max, tau_w = (NF)vp.tau_w;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF rain = s.in[TRM_IN_RAINFALL][c], LAI = s.LAI[c], SAI = s.in[TRM_IN_SAI][c], w = s.wcan[c];
+            NF wmax = wmax0 * (LAI + SAI);
+            NF f_can = wmax > 0 ? w / wmax : NF(0);
+            NF I_can = a_int * rain * (NF(1) - std::exp(-k_ext * (LAI + SAI)));
+            NF R_can = jmax(w, NF(0)) / tau_w;
+            s.Ican[c] = I_can; s.Rcan[c] = R_can; s.fcan[c] = f_can;
+            s.raing[c] = rain - I_can + R_can;
+        }
+    }
+    // PALADYNCanopyEvapotranspiration, canopy_evapotranspiration.jl:51-177
+    void compute_evapotranspiration(State<NF>& s) {
+        const NF C_can = (NF)vp.C_can;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF Tsk = s.Ts[c];   // fields.skin_temperature: the state variable (the prescribed variant reads its input field)
+            if (cfg.skin == TRM_SKIN_PRESCRIBED) Tsk = s.in[TRM_IN_SKIN_TEMPERATURE][c];
+            NF Tg = s.T[s.ix(nz, c)];
+            NF dqs = humidity_vpd(s, c, Tsk), dqg = humidity_vpd(s, c, Tg);
+            double ra = r_a(s, c);
+            NF V = jmax(s.in[TRM_IN_WINDSPEED][c], Vmin);
+            NF re = (1 - std::exp(-s.LAI[c] - s.in[TRM_IN_SAI][c])) / (C_can * V);
+            NF rs = 1 / jmax(s.gwcan[c], std::sqrt(std::numeric_limits<NF>::epsilon()));
+            s.transp[c] = (NF)((double)dqs / (ra + (double)rs));
+            s.Egnd[c] = (NF)((double)(beta * dqg) / (ra + (double)re));
+            s.Ecan[c] = (NF)((double)(s.fcan[c] * dqs) / ra);
+        }
+    }
+    // compute_tendencies!: canopy water (canopy_interception.jl:189-200), vegetation carbon (carbon_dynamics.jl:107-112,
+    // 152-158), vegetation fraction (vegetation_dynamics.jl:60-75,110-120)
+    void vegetation_tendencies(State<NF>& s) {
+        const NF SLA = (NF)vp.SLA, awl = (NF)vp.awl, Lmin = (NF)vp.LAI_min, Lmax = (NF)vp.LAI_max;
+        const NF gL = (NF)vp.gamma_L, gR = (NF)vp.gamma_R, gS = (NF)vp.gamma_S, nu_seed = (NF)vp.nu_seed, gv = (NF)vp.gamma_v_min;
+        auto lambda_NPP = [&](NF LAI_b) { return LAI_b < Lmin ? NF(0) : (LAI_b <= Lmax ? (LAI_b - Lmin) / (Lmax - Lmin) : NF(1.0)); };
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) s.tendwcan[c] = s.Ican[c] - s.Ecan[c] - s.Rcan[c];
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF lam = lambda_NPP(s.LAIb[c]);
+            NF Lloc = (gL / SLA + gR / SLA + gS * awl) * s.LAIb[c];
+            s.tendCveg[c] = (NF(1.0) - lam) * s.NPP[c] - Lloc;
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nc; ++c) {
+            NF lam = lambda_NPP(s.LAIb[c]);
+            NF nus = jmax(s.nu[c], nu_seed);
+            s.tendnu[c] = (lam * s.NPP[c] / s.Cveg[c]) * nus * (NF(1.0) - s.nu[c]) - gv * nus;
+        }
+    }
     // compute_auxiliary! soil_coupled.jl:62-72 / land_model.jl:79-88
     void compute_auxiliary(State<NF>& s) {
         compute_hydraulics(s);
-        if (land) { compute_evaporation(s); compute_runoff(s); compute_seb(s); compute_seb(s); }
+        if (veg) { compute_vegetation(s); compute_canopy_interception(s); compute_evapotranspiration(s); compute_runoff(s); compute_seb(s); compute_seb(s); }
+        else if (land) { compute_evaporation(s); compute_runoff(s); compute_seb(s); compute_seb(s); }
     }
     // compute_tendencies! soil_coupled.jl:80-90 / land_model.jl:90-96
     void compute_tendencies(State<NF>& s) {
         if (richards) richards_tendency(s);
         energy_tendency(s);
+        if (veg) vegetation_tendencies(s);
     }
     // update_state! state_variables.jl:72-80
     void update_state(State<NF>& s) {
@@ -446,6 +639,9 @@ struct Oracle {
                 }
             if (richards) for (int64_t c = c0; c < c1; ++c) s.Sx[c] += s.tendSx[c] * dt;
             if (land && cfg.skin == TRM_SKIN_IMPLICIT) for (int64_t c = c0; c < c1; ++c) s.Ts[c] += s.tendTs[c] * dt;
+            if (veg) for (int64_t c = c0; c < c1; ++c) {
+                s.wcan[c] += s.tendwcan[c] * dt; s.Cveg[c] += s.tendCveg[c] * dt; s.nu[c] += s.tendnu[c] * dt;
+            }
         }
         passes += richards ? 6 : 3;
     }
@@ -585,6 +781,11 @@ struct Oracle {
         }
         if (richards) for (int64_t c = 0; c < nc; ++c) st.tendSx[c] = (st.tendSx[c] + stage.tendSx[c]) / 2;
         if (land && cfg.skin == TRM_SKIN_IMPLICIT) for (int64_t c = 0; c < nc; ++c) st.tendTs[c] = (st.tendTs[c] + stage.tendTs[c]) / 2;
+        if (veg) for (int64_t c = 0; c < nc; ++c) {
+            st.tendwcan[c] = (st.tendwcan[c] + stage.tendwcan[c]) / 2;
+            st.tendCveg[c] = (st.tendCveg[c] + stage.tendCveg[c]) / 2;
+            st.tendnu[c] = (st.tendnu[c] + stage.tendnu[c]) / 2;
+        }
         explicit_step(st, dt);
         closure(st);
         tick(st, dt);
@@ -610,6 +811,7 @@ struct Oracle {
             case TRM_F_LIQUID_WATER_FRACTION: return &st.liq; case TRM_F_SATURATION_WATER_ICE: return &st.sat;
             case TRM_F_PRESSURE_HEAD: return &st.psi; case TRM_F_TEND_INTERNAL_ENERGY: return &st.tendU;
             case TRM_F_TEND_SATURATION: return &st.tendsat;
+            case TRM_F_PLANT_AVAILABLE_WATER: return veg ? &st.PAW : nullptr;
         }
         return nullptr;
     }
@@ -621,6 +823,16 @@ struct Oracle {
             case TRM_F_NET_RADIATION: return &st.Rnet; case TRM_F_SENSIBLE_HEAT_FLUX: return &st.Hs;
             case TRM_F_LATENT_HEAT_FLUX: return &st.Hl; case TRM_F_EVAPORATION_GROUND: return &st.Egnd;
             case TRM_F_INFILTRATION: return &st.infil; case TRM_F_SURFACE_RUNOFF: return &st.runoff;
+            case TRM_F_CARBON_VEGETATION: return &st.Cveg; case TRM_F_VEGETATION_AREA_FRACTION: return &st.nu;
+            case TRM_F_CANOPY_WATER: return &st.wcan; case TRM_F_BALANCED_LEAF_AREA_INDEX: return &st.LAIb;
+            case TRM_F_LEAF_AREA_INDEX: return &st.LAI; case TRM_F_PHENOLOGY_FACTOR: return &st.phen;
+            case TRM_F_CANOPY_WATER_CONDUCTANCE: return &st.gwcan; case TRM_F_LEAF_TO_AIR_CO2_RATIO: return &st.lamc;
+            case TRM_F_NET_ASSIMILATION: return &st.An; case TRM_F_LEAF_RESPIRATION: return &st.Rd;
+            case TRM_F_GROSS_PRIMARY_PRODUCTION: return &st.GPP; case TRM_F_AUTOTROPHIC_RESPIRATION: return &st.Ra;
+            case TRM_F_NET_PRIMARY_PRODUCTION: return &st.NPP; case TRM_F_SOIL_MOISTURE_LIMITING_FACTOR: return &st.betasm;
+            case TRM_F_CANOPY_WATER_INTERCEPTION: return &st.Ican; case TRM_F_CANOPY_WATER_REMOVAL: return &st.Rcan;
+            case TRM_F_SATURATION_CANOPY_WATER: return &st.fcan; case TRM_F_RAINFALL_GROUND: return &st.raing;
+            case TRM_F_EVAPORATION_CANOPY: return &st.Ecan; case TRM_F_TRANSPIRATION: return &st.transp;
         }
         return nullptr;
     }
@@ -648,6 +860,11 @@ struct Oracle {
         if (id == TRM_F_HYDRAULIC_CONDUCTIVITY) {
             if (count != (int64_t)(nz + 1) * nc) return fail(TRM_ERR_INVALID, "get_field: count != (nz+1)*ncol");
             for (int k = 1; k <= nz + 1; ++k) std::memcpy(h + (size_t)(k - 1) * nc, &st.Kf[st.ix(k, 0)], sizeof(NF) * nc);
+            return TRM_OK;
+        }
+        if (id == TRM_F_ROOT_FRACTION && veg) {
+            if (count != (int64_t)nz * nc) return fail(TRM_ERR_INVALID, "get_field: count != nz*ncol");
+            for (int k = 1; k <= nz; ++k) for (int64_t c = 0; c < nc; ++c) h[(size_t)(k - 1) * nc + c] = rootf[k];
             return TRM_OK;
         }
         if (id == TRM_F_GROUND_TEMPERATURE) {
@@ -721,6 +938,14 @@ void orc_default_params(trm_params* p) {
     p->impedance = 7.0; p->vwc_forcing = 0.0;
     p->albedo = 0.3; p->emissivity = 0.97; p->kappa_skin = 2.0; p->C_h = 1.2e-3; p->min_windspeed = 0.01;
     p->tau_r = 3600.0; p->evap_beta = 1.0;
+    p->field_capacity = 0.25; p->wilting_point = 0.05; p->C_mass = 12.0;
+    p->tau25 = 2600.0; p->Kc25 = 30.0; p->Ko25 = 3.0e4; p->q10_tau = 0.57; p->q10_Kc = 2.1; p->q10_Ko = 1.2;
+    p->alpha_leaf = 0.17; p->alpha_a = 0.5; p->alpha_C3 = 0.08; p->cq = 4.6e-6; p->k_ext = 0.5;
+    p->T_CO2_high = 42.0; p->T_CO2_low = -4.0; p->T_photos_high = 30.0; p->T_photos_low = 15.0; p->theta_r = 0.7;
+    p->g1 = 2.3; p->g_min = 0.5; p->cn_sapwood = 330.0; p->cn_root = 29.0; p->aws = 10.0;
+    p->SLA = 10.0; p->awl = 2.0; p->LAI_min = 1.0; p->LAI_max = 6.0; p->gamma_L = 0.3; p->gamma_R = 0.3; p->gamma_S = 0.05;
+    p->nu_seed = 0.001; p->gamma_v_min = 0.002; p->root_a = 7.0; p->root_b = 2.0;
+    p->alpha_int = 0.2; p->k_ext_can = 0.5; p->w_can_max = 2.0e-4; p->tau_w = 86400.0; p->C_can = 0.006;
 }
 void orc_default_config(trm_config* c) {
     std::memset(c, 0, sizeof(*c));

@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-TRM_ABI_VERSION = 1
+TRM_ABI_VERSION = 2
 TRM_MAX_NZ = 128
 TRM_NUM_USER_INPUTS = 8
 
@@ -27,6 +27,7 @@ TRM_UNSATK_LINEAR, TRM_UNSATK_VANGENUCHTEN = 0, 1
 TRM_HALO_ZERO, TRM_HALO_COPY = 0, 1
 TRM_SKIN_IMPLICIT, TRM_SKIN_PRESCRIBED = 0, 1
 TRM_MATH_FAITHFUL, TRM_MATH_FAST = 0, 1
+TRM_VEG_NONE, TRM_VEG_CARBON = 0, 1
 TRM_BC_DEFAULT, TRM_BC_VALUE, TRM_BC_GRADIENT, TRM_BC_FLUX = 0, 1, 2, 3
 (TRM_BC_TEMPERATURE_TOP, TRM_BC_TEMPERATURE_BOTTOM, TRM_BC_ENERGY_TOP, TRM_BC_ENERGY_BOTTOM,
  TRM_BC_SATURATION_TOP, TRM_BC_SATURATION_BOTTOM, TRM_BC_PRESSURE_TOP, TRM_BC_PRESSURE_BOTTOM) = range(8)
@@ -34,8 +35,8 @@ TRM_BC_NSLOTS = 8
 TRM_IN_USER0 = 0
 (TRM_IN_AIR_TEMPERATURE, TRM_IN_AIR_PRESSURE, TRM_IN_WINDSPEED, TRM_IN_SPECIFIC_HUMIDITY, TRM_IN_RAINFALL,
  TRM_IN_SNOWFALL, TRM_IN_SHORTWAVE_DOWN, TRM_IN_LONGWAVE_DOWN, TRM_IN_DAYTIME_LENGTH, TRM_IN_CO2,
- TRM_IN_SKIN_TEMPERATURE) = range(8, 19)
-TRM_IN_COUNT = 19
+ TRM_IN_SKIN_TEMPERATURE, TRM_IN_SAI, TRM_IN_DAILY_LEAF_RESPIRATION) = range(8, 21)
+TRM_IN_COUNT = 21
 TRM_SRC_CONST, TRM_SRC_FIELD, TRM_SRC_SINUSOID, TRM_SRC_TABLE = 0, 1, 2, 3
 
 FIELD_IDS = {
@@ -45,16 +46,37 @@ FIELD_IDS = {
     "surface_longwave_up": 12, "surface_net_radiation": 13, "sensible_heat_flux": 14, "latent_heat_flux": 15,
     "evaporation_ground": 16, "infiltration": 17, "surface_runoff": 18,
     "tendency_internal_energy": 19, "tendency_saturation_water_ice": 20,
+    # vegetated LandModel
+    "carbon_vegetation": 21, "vegetation_area_fraction": 22, "canopy_water": 23, "balanced_leaf_area_index": 24,
+    "leaf_area_index": 25, "phenology_factor": 26, "canopy_water_conductance": 27, "leaf_to_air_co2_ratio": 28,
+    "net_assimilation": 29, "leaf_respiration": 30, "gross_primary_production": 31, "autotrophic_respiration": 32,
+    "net_primary_production": 33, "soil_moisture_limiting_factor": 34, "canopy_water_interception": 35,
+    "canopy_water_removal": 36, "saturation_canopy_water": 37, "rainfall_ground": 38, "evaporation_canopy": 39,
+    "transpiration": 40, "plant_available_water": 41, "root_fraction": 42,
 }
+VEGETATION_FIELDS = tuple(n for n, i in FIELD_IDS.items() if i >= 21)
 FIELDS_3D = ("internal_energy", "temperature", "liquid_water_fraction", "saturation_water_ice", "pressure_head",
-             "tendency_internal_energy", "tendency_saturation_water_ice")
+             "tendency_internal_energy", "tendency_saturation_water_ice", "plant_available_water", "root_fraction")
 FIELDS_FACE = ("hydraulic_conductivity",)
 INPUT_IDS = {
     "air_temperature": TRM_IN_AIR_TEMPERATURE, "air_pressure": TRM_IN_AIR_PRESSURE, "windspeed": TRM_IN_WINDSPEED,
     "specific_humidity": TRM_IN_SPECIFIC_HUMIDITY, "rainfall": TRM_IN_RAINFALL, "snowfall": TRM_IN_SNOWFALL,
     "surface_shortwave_down": TRM_IN_SHORTWAVE_DOWN, "surface_longwave_down": TRM_IN_LONGWAVE_DOWN,
     "daytime_length": TRM_IN_DAYTIME_LENGTH, "CO2": TRM_IN_CO2, "skin_temperature": TRM_IN_SKIN_TEMPERATURE,
+    "SAI": TRM_IN_SAI, "daily_leaf_respiration": TRM_IN_DAILY_LEAF_RESPIRATION,
 }
+
+
+# vegetated LandModel parameters, in header order
+VEGETATION_PARAMS = (
+    "field_capacity", "wilting_point", "C_mass",
+    "tau25", "Kc25", "Ko25", "q10_tau", "q10_Kc", "q10_Ko", "alpha_leaf", "alpha_a", "alpha_C3", "cq", "k_ext",
+    "T_CO2_high", "T_CO2_low", "T_photos_high", "T_photos_low", "theta_r",
+    "g1", "g_min", "cn_sapwood", "cn_root", "aws",
+    "SLA", "awl", "LAI_min", "LAI_max", "gamma_L", "gamma_R", "gamma_S",
+    "nu_seed", "gamma_v_min", "root_a", "root_b",
+    "alpha_int", "k_ext_can", "w_can_max", "tau_w", "C_can",
+)
 
 
 class trm_params(C.Structure):
@@ -67,7 +89,7 @@ class trm_params(C.Structure):
         ("bc_lambda", C.c_double), ("theta_res", C.c_double), ("impedance", C.c_double), ("vwc_forcing", C.c_double),
         ("albedo", C.c_double), ("emissivity", C.c_double), ("kappa_skin", C.c_double), ("C_h", C.c_double),
         ("min_windspeed", C.c_double), ("tau_r", C.c_double), ("evap_beta", C.c_double),
-    ]
+    ] + [(n, C.c_double) for n in VEGETATION_PARAMS]
 
 
 class trm_bc(C.Structure):
@@ -79,7 +101,7 @@ class trm_config(C.Structure):
         ("abi_version", C.c_int32), ("dtype", C.c_int32), ("ncol", C.c_int64), ("col0", C.c_int64),
         ("nz", C.c_int32), ("device", C.c_int32), ("model", C.c_int32), ("timestepper", C.c_int32),
         ("hydrology", C.c_int32), ("swrc", C.c_int32), ("unsat_k", C.c_int32), ("sat_halo", C.c_int32),
-        ("skin", C.c_int32), ("math", C.c_int32),
+        ("skin", C.c_int32), ("math", C.c_int32), ("vegetation", C.c_int32),
         ("z_faces", C.POINTER(C.c_double)),
         ("params", trm_params),
         ("bc", trm_bc * TRM_BC_NSLOTS),

@@ -65,7 +65,7 @@ constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 
 // k1 and the base U / sat of a layer are prefetched into a second cp.async ring two iterations before its update).
 template <class NF, int LOAD, int MS, int MODE = MODE_EULER>
 struct EulerSmem {
-    static constexpr int METRICS = MET_COUNT * MS;                                    // elements
+    static constexpr int METRICS = MET_COUNT * MS;                                    // elements (the root fraction row is only filled by LandModel kernels)
     static constexpr int STRIP = EF_COUNT * TRM_EULER_BLOCK;
     static constexpr int RING = (2 * EULER_RD + (LOAD ? 3 : 0) * EULER_PF) * TRM_EULER_BLOCK;   // U, sat (, T, liq, psi)
     static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * EULER_PF * TRM_EULER_BLOCK;   // k1U, k1S, bU, bS
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     const int nz = A.nz;
     {
         NF* sm = reinterpret_cast<NF*>(smem_raw);
-        for (int q = 0; q < MET_COUNT; ++q)
+        for (int q = 0; q < met_rows(LAND); ++q)
             for (int i = threadIdx.x; i < nz + 3; i += B) sm[q * MS + i] = A.metrics[q * MET_STRIDE + i];
     }
     __syncthreads();
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     NF Sx_new = NF(0);
     if (RICH && !H1) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
     uint32_t oout = (uint32_t)c;   // element offset of layer m-2
+    NF beta_sm = NF(0);            // vegetated LandModel: soil moisture limiting factor (plant_available_water.jl:31-35)
 
     // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-3, for which every
     // layer-index special case below is statically false / true: no halo, no boundary face, no Flux BC, the
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
             }
             kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
+            if (LAND && A.veg) beta_sm += plant_available_water(A.vp, p, sr, ln) * met.root(m) / met.dzc(m) * met.dzc(m);
             if (RICH) {
                 // cell conductivity and face conductivity Kf[m], soil_hydrology.jl:249-276
                 const NF Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
@@ -239,8 +241,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         NF G_top = NF(0), infil_top = NF(0);   // fluxes coupling the surface to the top soil layer (same iteration)
         if (LAND && !inner && m == nz + 2) {
-            if (H2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
-            else land_surface(A, c, RICH, rd(EF_TTOP), ldsv(ringS(nz), (NF*)nullptr), ldsv(kf_cur, (NF*)nullptr), met.dzc(nz), G_top, infil_top);
+            if (H2 && !A.veg) { G_top = A.G[c]; infil_top = A.infil[c]; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
+            else land_surface(A, c, RICH, rd(EF_TTOP), ldsv(ringS(nz), (NF*)nullptr), ldsv(kf_cur, (NF*)nullptr), met.dzc(nz), beta_sm, H2, G_top, infil_top);
         }
 
         if (inner || m >= 3) {

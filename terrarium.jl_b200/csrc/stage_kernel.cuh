@@ -30,6 +30,7 @@
 #pragma once
 
 #include "column_physics.cuh"
+#include "vegetation.cuh"
 
 namespace trm {
 
@@ -43,7 +44,10 @@ __host__ __device__ constexpr bool phys_land(int phys) { return phys == PHYS_LAN
 // Grid metrics (reference 1-based layer / face indices + halos), one row of MET_STRIDE values per quantity.
 // The fixed stride lets the kernels address `quantity[k]` as (k-dependent register) + immediate.
 constexpr int MET_STRIDE = TRM_MAX_NZ + 3;
-enum Metric { MET_ZF = 0, MET_ZC = 1, MET_DZC = 2, MET_RDZC = 3, MET_DZF = 4, MET_RDZF = 5, MET_PSIZ = 6 /* zC - zF[nz+1] */, MET_COUNT = 7 };
+enum Metric { MET_ZF = 0, MET_ZC = 1, MET_DZC = 2, MET_RDZC = 3, MET_DZF = 4, MET_RDZF = 5, MET_PSIZ = 6 /* zC - zF[nz+1] */,
+              MET_ROOT = 7 /* static root fraction, root_distribution.jl:47-56 ; only staged by the LandModel kernels */, MET_COUNT = 8 };
+// rows a kernel stages in shared memory
+__host__ __device__ constexpr int met_rows(bool land) { return land ? MET_COUNT : MET_COUNT - 1; }
 
 // Shared-memory reads through an explicit 32-bit shared address: the generic-pointer form makes the compiler
 // rebuild the shared window base (S2R SR_CgaCtaId + LEA) in front of every access when registers are tight.
@@ -60,6 +64,7 @@ struct Metrics {
     __device__ __forceinline__ NF dzf(int k) const { return get(MET_DZF, k); }
     __device__ __forceinline__ NF rdzf(int k) const { return get(MET_RDZF, k); }
     __device__ __forceinline__ NF psiz(int k) const { return get(MET_PSIZ, k); }
+    __device__ __forceinline__ NF root(int k) const { return get(MET_ROOT, k); }
 };
 
 #ifndef TRM_MAX_BLOCK
@@ -98,6 +103,15 @@ struct StageArgs {
     NF* Kf;   // z-face hydraulic conductivity [nz+1][ld], written in AUX / TEND
     // LandModel 2-D fields
     NF *Ts, *G, *SWup, *LWup, *Rnet, *Hs, *Hl, *Egnd, *infil, *runoff;
+    // vegetated LandModel: 2-D fields (VegField order; auxiliaries are written by every evaluation on the model
+    // state), the prognostic triple (C_veg, nu, w_can) of the state the tendencies are evaluated on (vx), of the base
+    // state (vb) and of the updated state (vy), Heun k1 in / out, plant available water [nz][ld] (MODE_AUX only)
+    int32_t veg, pad2_;
+    NF* veg2d[VF_COUNT];
+    const NF *vx[3], *vb[3], *vk1[3];
+    NF *vy[3], *vok1[3];
+    NF* paw;
+    VegParams<NF> vp;
     const NF* metrics;   // [MET_COUNT][MET_STRIDE], see enum Metric
     DevParams<NF> p;
     trm_bc bc[TRM_BC_NSLOTS];
@@ -177,9 +191,16 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
 // t, the skin temperature and the surface excess water; writes every 2-D surface field; returns the two fluxes
 // that couple to the top soil layer. Out of line: it runs once per column and step, and inlined it would set the
 // register budget of the whole layer loop.
+// Vegetated LandModel (A.veg): beta_sm is the soil moisture limiting factor accumulated over the column by the caller;
+// the block additionally evaluates the vegetation auxiliaries (vegetation_carbon.jl:71-104), canopy interception and
+// evapotranspiration (surface_hydrology.jl:36-50) and advances canopy water, vegetation carbon and area fraction.
+// `stage2` (Heun stage 2): only what feeds the k2 tendencies of those three variables is evaluated -- on the stage
+// state, at t + dt -- and no auxiliary field is written (they belong to the stage copy in the reference, heun.jl:45-58).
 template <class NF>
-__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF K_top, NF dz_top, NF& G_out, NF& inf_out) {
+__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF K_top, NF dz_top, NF beta_sm,
+                                          bool stage2, NF& G_out, NF& inf_out) {
     const DevParams<NF>& p = A.p;
+    const bool veg = A.veg != 0;
     // (inputs evaluated inline: their loads are independent and overlap; through eval_input() they would serialise)
     Surface<NF> a;
     // surface_excess_water(...) is the prognostic field under RichardsEq (soil_hydrology_rre.jl:28) and identically
@@ -207,19 +228,94 @@ __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, boo
     NF vpd = jmax(es - ea, NF(0.1));
     NF dq = p.eps_mw * vpd / a.pres;
     NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
-    // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 (rainfall_ground aliases rainfall) ; K_top = Kf[Nz]
+    NF rain_ground = a.rain;   // NoCanopyInterception: rainfall_ground aliases rainfall (canopy_interception.jl:11-15)
+    NF Qh = Egnd;              // surface_humidity_flux of the evapotranspiration scheme
+    if (veg) {
+        const VegParams<NF>& v = A.vp;
+        const NF co2 = eval_input_inline(A.in[TRM_IN_CO2], c, A.t_x);
+        const NF SAI = eval_input_inline(A.in[TRM_IN_SAI], c, A.t_x);
+        const NF Rdl = eval_input_inline(A.in[TRM_IN_DAILY_LEAF_RESPIRATION], c, A.t_x);
+        const NF Cv = A.vx[0][c], nu = A.vx[1][c], wcan = A.vx[2][c];
+        const NF An_prev = A.veg2d[VF_AN][c];
+        // PALADYNCarbonDynamics / PALADYNPhenology auxiliaries (carbon_dynamics.jl:82-85, phenology.jl:33-70)
+        const NF LAIb = Cv / ((NF(2.0) / v.SLA) + v.awl);
+        const NF fdec = NF(0), phen = NF(1.0);
+        const NF LAI = (fdec * phen + (NF(1.0) - fdec)) * LAIb;
+        // MedlynStomatalConductance (stomatal_conductance.jl:45-82): vapour pressure deficit at the air temperature,
+        // net assimilation of the PREVIOUS evaluation (vegetation_carbon.jl:89-91)
+        const NF vpd_air = jmax(saturation_vapor_pressure(a.Ta) - ea, NF(0.1));
+        const NF g0 = (v.g_min / 1000) * (1 - texp(-v.k_ext * LAI)) * beta_sm;
+        const NF gw = g0 + NF(1.6) * (1 + v.g1 / tsqrt(vpd_air)) * An_prev / co2 * NF(1.0e6);
+        const NF lamc = NF(1.0) - NF(1.0) / (NF(1.0) + v.g1 / tsqrt(vpd_air * NF(1.0e-3)));
+        // LUEPhotosynthesis (photosynthesis.jl:284-344)
+        NF Rd, An;
+        photosynthesis(v, a.Ta, a.SWd, a.pres, co2, LAI, lamc, beta_sm, Rd, An);
+        const NF GPP = An * NF(1.0e-3);
+        // PALADYNAutotrophicRespiration (autotrophic_respiration.jl:46-154) ; T_soil = ground temperature
+        const NF f_soil = (T_top > 7) ? texp(NF(308.56) * (NF(1.0) / NF(56.02) - NF(1.0) / (NF(46.02) + T_top))) : NF(0);
+        const NF f_air = texp(NF(308.56) * (NF(1.0) / NF(56.02) - NF(1.0) / (NF(46.02) + a.Ta)));
+        const NF resp10 = NF(0.066);
+        const NF R_leaf = Rdl / NF(1000.0);
+        const NF R_stem = resp10 * f_air * (v.awl * ((NF(2.0) / v.SLA) + v.awl)) / (Cv * v.aws * v.cn_sapwood);
+        const NF R_root = resp10 * f_soil * phen * (NF(2.0) / v.SLA) / (v.SLA * Cv * v.cn_root);
+        const NF Rm = R_leaf + R_stem + R_root;
+        const NF Rg = NF(0.25) * (GPP - Rm);
+        const NF Ra = Rm + Rg;
+        const NF NPP = GPP - Ra;
+        // PALADYNCanopyInterception (canopy_interception.jl:79-187)
+        const NF wmax = v.w_can_max * (LAI + SAI);
+        const NF f_can = wmax > 0 ? wcan / wmax : NF(0);
+        const NF I_can = v.alpha_int * a.rain * (NF(1) - texp(-v.k_ext_can * (LAI + SAI)));
+        const NF R_can = jmax(wcan, NF(0)) / v.tau_w;
+        rain_ground = a.rain - I_can + R_can;
+        // PALADYNCanopyEvapotranspiration (canopy_evapotranspiration.jl:51-177): humidity gradients at the skin and at
+        // the ground temperature, resistance between ground and canopy, stomatal resistance
+        const NF esg = saturation_vapor_pressure(T_top);
+        const NF dqg = p.eps_mw * jmax(esg - ea, NF(0.1)) / a.pres;
+        const NF re = (1 - texp(-LAI - SAI)) / (v.C_can * Vc);
+        const NF rs = 1 / jmax(gw, tsqrt(Lim<NF>::eps()));
+        const NF transp = (NF)((double)dq / (a.ra + (double)rs));
+        Egnd = (NF)((double)(p.beta * dqg) / (a.ra + (double)re));
+        const NF E_can = (NF)((double)(f_can * dq) / a.ra);
+        Qh = Egnd + E_can + transp;
+        // tendencies: canopy water (canopy_interception.jl:121-127), vegetation carbon (carbon_dynamics.jl:107-112),
+        // vegetation area fraction (vegetation_dynamics.jl:60-75)
+        const NF lam = lambda_NPP(v, LAIb);
+        NF k[3];
+        k[2] = I_can - E_can - R_can;
+        k[0] = (NF(1.0) - lam) * NPP - (v.gamma_L / v.SLA + v.gamma_R / v.SLA + v.gamma_S * v.awl) * LAIb;
+        const NF nus = jmax(nu, v.nu_seed);
+        k[1] = (lam * NPP / Cv) * nus * (NF(1.0) - nu) - v.gamma_v * nus;
+        if (A.mode == MODE_EULER || A.mode == MODE_HEUN1 || A.mode == MODE_HEUN2) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                NF ki = k[i];
+                if (A.mode == MODE_HEUN1) A.vok1[i][c] = ki;
+                if (A.mode == MODE_HEUN2) ki = (A.vk1[i][c] + ki) / 2;   // average_tendencies!, heun.jl:27-35
+                A.vy[i][c] = A.vb[i][c] + ki * A.dt;
+            }
+        }
+        if (stage2) { G_out = A.G[c]; inf_out = A.infil[c]; return; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
+        NF* const* o = A.veg2d;
+        o[VF_LAIB][c] = LAIb; o[VF_LAI][c] = LAI; o[VF_PHEN][c] = phen; o[VF_GWCAN][c] = gw; o[VF_LAMC][c] = lamc;
+        o[VF_AN][c] = An; o[VF_RD][c] = Rd; o[VF_GPP][c] = GPP; o[VF_RA][c] = Ra; o[VF_NPP][c] = NPP; o[VF_BETASM][c] = beta_sm;
+        o[VF_ICAN][c] = I_can; o[VF_RCAN][c] = R_can; o[VF_FCAN][c] = f_can; o[VF_RAING][c] = rain_ground;
+        o[VF_ECAN][c] = E_can; o[VF_TRANSP][c] = transp;
+    }
+    // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 ; K_top = Kf[Nz]
     NF drain, inf;
     if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, K_top) : NF(0); }
-    else { drain = 0; inf = (sat_top < 1) ? jmin(a.rain, K_top) : NF(0); }
-    NF runoff = a.rain + drain - inf;
-    // surface energy balance kernel, executed twice (land_model.jl:85-86)
+    else { drain = 0; inf = (sat_top < 1) ? jmin(rain_ground, K_top) : NF(0); }
+    NF runoff = rain_ground + drain - inf;
+    // surface energy balance kernel, executed twice (land_model.jl:85-86) ; the latent heat flux follows the humidity
+    // flux of the evapotranspiration scheme (turbulent_fluxes.jl:137-150)
     NF swu, lwu, rnet, hs, hl, G;
 #pragma unroll 1
     for (int rep = 0; rep < 2; ++rep) {
-        seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+        seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Qh, swu, lwu, rnet, hs, hl, G);
         if (!prescribed) {
             Ts = T_top - G * dz_top / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
-            seb_fluxes(p, a, Ts, Egnd, swu, lwu, rnet, hs, hl, G);
+            seb_fluxes(p, a, Ts, Qh, swu, lwu, rnet, hs, hl, G);
         }
     }
     A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
@@ -254,7 +350,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     const int nz = A.nz;
     {
         NF* sm = reinterpret_cast<NF*>(smem_raw);
-        for (int q = 0; q < MET_COUNT; ++q)
+        for (int q = 0; q < met_rows(LAND); ++q)
             for (int i = threadIdx.x; i < nz + 3; i += blockDim.x) sm[q * MET_STRIDE + i] = A.metrics[q * MET_STRIDE + i];
     }
     __syncthreads();
@@ -310,6 +406,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     NF Sx_new = NF(0);
     if (RICH && do_update) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
     NF G_top = NF(0), infil_top = NF(0);   // LandModel: fluxes coupling the surface to the top soil layer
+    NF beta_sm = NF(0);                    // vegetated LandModel: soil moisture limiting factor (plant_available_water.jl:31-35)
     int64_t oout = c;                      // element offset of layer m-2
 
     // One pipeline iteration: layer m (or the halo above the surface for m = nz+1) enters, the fluxes
@@ -329,6 +426,11 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             }
             kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
             if (need_K) Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
+            if (LAND && A.veg) {   // Integral(PAW * root_fraction / dz, dims = 3), accumulated bottom -> top
+                const NF paw = plant_available_water(A.vp, p, sr, ln);
+                beta_sm += paw * met.root(m) / met.dzc(m) * met.dzc(m);
+                if (mode == MODE_AUX) A.paw[(int64_t)(m - 1) * ld + c] = paw;
+            }
         } else if (m == nz + 1) {   // halo above the surface, built from layer nz (prv)
             Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, prv.T, bc_T_top, met.dzf(nz + 1), true);
             const NF sh = (RICH || p.sat_halo == TRM_HALO_COPY) ? prv.s : NF(0);
@@ -371,8 +473,8 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
 
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         if (LAND && m == nz + 2) {
-            if (mode == MODE_HEUN2) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
-            else land_surface(A, c, RICH, T2, s2, Kf2, met.dzc(nz), G_top, infil_top);
+            if (mode == MODE_HEUN2 && !A.veg) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
+            else land_surface(A, c, RICH, T2, s2, Kf2, met.dzc(nz), beta_sm, mode == MODE_HEUN2, G_top, infil_top);
         }
 
         if (m >= 3 && m <= nz + 2 && mode != MODE_AUX) {

@@ -66,7 +66,7 @@ template <class NF>
 struct Handle : HandleBase {
     trm_config cfg{};
     int nz = 0; int64_t nc = 0, ld = 0;
-    bool land = false, richards = false, heun = false, fast = false;
+    bool land = false, richards = false, heun = false, fast = false, veg = false;
     int phys = PHYS_NOFLOW;
     int block = 128;          // threads per block of the register-streaming stage kernel
     // which implementation runs ForwardEuler stages (env TRM_KERNEL = smem | stream):
@@ -83,6 +83,13 @@ struct Handle : HandleBase {
     // 2-D [ld]
     NF *Sx = nullptr, *Wt = nullptr, *gWt = nullptr;
     NF* land2d[10] = {nullptr};   // Ts, G, SWup, LWup, Rnet, Hs, Hl, Egnd, infil, runoff
+    // vegetated LandModel: 2-D fields in VegField order (first three prognostic), Heun stage values and k1 of the
+    // prognostic triple, plant available water [nz][ld], host copy of the static root fraction per layer
+    NF* veg2d[VF_COUNT] = {nullptr};
+    NF *gveg[3] = {nullptr}, *tveg[3] = {nullptr};
+    NF* paw = nullptr;
+    VegParams<NF> vp{};
+    std::vector<NF> rootf;
     struct Input { int kind = TRM_SRC_CONST; double cval = 0, period = 1, lo = -INFINITY, hi = INFINITY; int nt = 0;
                    NF *a = nullptr, *b = nullptr, *c = nullptr; double* times = nullptr;
                    // asynchronous per-column field inputs are double buffered: `a` is what enqueued steps read,
@@ -129,6 +136,8 @@ struct Handle : HandleBase {
         cfg = c; nz = c.nz; nc = c.ncol; device = c.device;
         land = c.model == TRM_MODEL_LAND; richards = c.hydrology == TRM_RICHARDS; heun = c.timestepper == TRM_HEUN;
         fast = c.math == TRM_MATH_FAST;
+        if (c.vegetation != TRM_VEG_NONE && c.vegetation != TRM_VEG_CARBON) return fail(TRM_ERR_INVALID, "bad vegetation code");
+        veg = land && c.vegetation == TRM_VEG_CARBON;   // (the field is ignored for a SoilModel)
         { const char* e = std::getenv("TRM_FORCE_LOAD_AUX"); force_load = e && e[0] == '1'; }
         if (const char* e = std::getenv("TRM_KERNEL")) {
             const std::string k(e);
@@ -160,6 +169,16 @@ struct Handle : HandleBase {
         for (int k = 0; k <= nz + 1; ++k) { zC[k] = (zF[k + 1] + zF[k]) / 2; dzc[k] = zF[k + 1] - zF[k]; rdzc[k] = 1 / dzc[k]; }
         for (int k = 1; k <= nz + 1; ++k) { dzf[k] = zC[k] - zC[k - 1]; rdzf[k] = 1 / dzf[k]; }
         for (int k = 0; k <= nz + 1; ++k) psiz[k] = zC[k] - zF[nz + 1];   // elevation head relative to the surface
+        if (veg) {
+            // root_fraction(rootdist, grid, ...), root_distribution.jl:47-56: density at the cell centres times the layer
+            // thickness, normalised by its sum over the column
+            NF* root = m.data() + MET_ROOT * MET_STRIDE;
+            const NF a = (NF)c.params.root_a, b = (NF)c.params.root_b;
+            NF sum = 0;
+            for (int k = 1; k <= nz; ++k) { root[k] = NF(0.5) * (a * std::exp(a * zC[k]) + b * std::exp(b * zC[k])) * dzc[k]; sum += root[k]; }
+            for (int k = 1; k <= nz; ++k) root[k] = root[k] / sum;
+            rootf.assign(root + 1, root + nz + 1);
+        }
         if (int rc = dalloc(&metrics, m.size())) return rc;
         CU(cudaMemcpyAsync(metrics, m.data(), m.size() * sizeof(NF), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
@@ -185,6 +204,14 @@ struct Handle : HandleBase {
         p.r_thspan = 1 / (p.por - p.theta_res); p.se_off = -p.theta_res * p.r_thspan;
         p.swrc = c.swrc; p.unsat_k = c.unsat_k; p.sat_halo = c.sat_halo; p.skin = c.skin;
         p.vg_n_is_2 = (p.vg_n == NF(2)) ? 1 : 0;
+        vp.th_fc = (NF)q.field_capacity; vp.th_wp = (NF)q.wilting_point; vp.C_mass = (NF)q.C_mass;
+        vp.tau25 = (NF)q.tau25; vp.Kc25 = (NF)q.Kc25; vp.Ko25 = (NF)q.Ko25; vp.q10_tau = (NF)q.q10_tau; vp.q10_Kc = (NF)q.q10_Kc; vp.q10_Ko = (NF)q.q10_Ko;
+        vp.alpha_leaf = (NF)q.alpha_leaf; vp.alpha_a = (NF)q.alpha_a; vp.alpha_C3 = (NF)q.alpha_C3; vp.cq = (NF)q.cq; vp.k_ext = (NF)q.k_ext;
+        vp.T_CO2_high = (NF)q.T_CO2_high; vp.T_CO2_low = (NF)q.T_CO2_low; vp.T_photos_high = (NF)q.T_photos_high; vp.T_photos_low = (NF)q.T_photos_low;
+        vp.theta_r = (NF)q.theta_r; vp.g1 = (NF)q.g1; vp.g_min = (NF)q.g_min; vp.cn_sapwood = (NF)q.cn_sapwood; vp.cn_root = (NF)q.cn_root; vp.aws = (NF)q.aws;
+        vp.SLA = (NF)q.SLA; vp.awl = (NF)q.awl; vp.LAI_min = (NF)q.LAI_min; vp.LAI_max = (NF)q.LAI_max;
+        vp.gamma_L = (NF)q.gamma_L; vp.gamma_R = (NF)q.gamma_R; vp.gamma_S = (NF)q.gamma_S; vp.nu_seed = (NF)q.nu_seed; vp.gamma_v = (NF)q.gamma_v_min;
+        vp.alpha_int = (NF)q.alpha_int; vp.k_ext_can = (NF)q.k_ext_can; vp.w_can_max = (NF)q.w_can_max; vp.tau_w = (NF)q.tau_w; vp.C_can = (NF)q.C_can;
 
         // ---- fields
         const size_t n3 = (size_t)nz * ld;
@@ -198,6 +225,11 @@ struct Handle : HandleBase {
             if (richards) { for (NF** f : {&tS, &gS}) if (int rc = dalloc(f, n3)) return rc; if (int rc = dalloc(&gWt, ld)) return rc; }
         }
         if (land) for (int i = 0; i < 10; ++i) if (int rc = dalloc(&land2d[i], ld)) return rc;
+        if (veg) {
+            for (int i = 0; i < VF_COUNT; ++i) if (int rc = dalloc(&veg2d[i], ld)) return rc;
+            if (heun) for (int i = 0; i < 3; ++i) { if (int rc = dalloc(&gveg[i], ld)) return rc; if (int rc = dalloc(&tveg[i], ld)) return rc; }
+            if (int rc = dalloc(&paw, n3)) return rc;
+        }
         // input defaults, prescribed_atmosphere.jl:89-99,147-149,192-195,220-224,10-14
         in[TRM_IN_AIR_TEMPERATURE].cval = 10; in[TRM_IN_AIR_PRESSURE].cval = 101325; in[TRM_IN_WINDSPEED].cval = 0.1;
         in[TRM_IN_SPECIFIC_HUMIDITY].cval = 1.0e-3; in[TRM_IN_SHORTWAVE_DOWN].cval = 300; in[TRM_IN_LONGWAVE_DOWN].cval = 50;
@@ -226,6 +258,8 @@ struct Handle : HandleBase {
             case TRM_F_TEND_SATURATION: return {tS, nz, false};
         }
         if (id >= TRM_F_SKIN_TEMPERATURE && id <= TRM_F_SURFACE_RUNOFF) return {land2d[id - TRM_F_SKIN_TEMPERATURE], 1, true};
+        if (id >= TRM_F_CARBON_VEGETATION && id <= TRM_F_TRANSPIRATION) return {veg2d[id - TRM_F_CARBON_VEGETATION], 1, true};
+        if (id == TRM_F_PLANT_AVAILABLE_WATER) return {paw, nz, false};
         return {nullptr, 0, false};
     }
     int set_field(int id, const void* host, int64_t count) override {
@@ -241,6 +275,12 @@ struct Handle : HandleBase {
         return TRM_OK;
     }
     int get_field(int id, void* host, int64_t count) override {
+        if (id == TRM_F_ROOT_FRACTION && veg) {   // static function of depth: the same profile in every column
+            if (count != (int64_t)nz * nc) return fail(TRM_ERR_INVALID, "get_field: wrong element count");
+            NF* h = (NF*)host;
+            for (int k = 0; k < nz; ++k) std::fill(h + (size_t)k * nc, h + (size_t)(k + 1) * nc, rootf[k]);
+            return TRM_OK;
+        }
         FieldRef f = field(id);
         if (!f.ptr) return fail(TRM_ERR_INVALID, "get_field: unknown field or field not defined for this model");
         if (count != (int64_t)f.nrows * nc) return fail(TRM_ERR_INVALID, "get_field: wrong element count");
@@ -326,6 +366,10 @@ struct Handle : HandleBase {
         a.Kf = Kf;
         a.Ts = land2d[0]; a.G = land2d[1]; a.SWup = land2d[2]; a.LWup = land2d[3]; a.Rnet = land2d[4];
         a.Hs = land2d[5]; a.Hl = land2d[6]; a.Egnd = land2d[7]; a.infil = land2d[8]; a.runoff = land2d[9];
+        a.veg = veg ? 1 : 0; a.vp = vp; a.paw = paw;
+        for (int i = 0; i < VF_COUNT; ++i) a.veg2d[i] = veg2d[i];
+        // ForwardEuler / auxiliary evaluations: evaluate on, and update, the model state in place
+        for (int i = 0; i < 3; ++i) { a.vx[i] = veg2d[i]; a.vb[i] = veg2d[i]; a.vy[i] = veg2d[i]; a.vk1[i] = nullptr; a.vok1[i] = nullptr; }
     }
     void x_state(StageArgs<NF>& a) { a.xU = U; a.xS = S; a.xT = T; a.xL = Lq; a.xP = P; a.xWt = Wt; a.bU = U; a.bS = S; a.bSx = Sx; }
     void y_state(StageArgs<NF>& a) { a.yU = U; a.yS = S; a.yT = T; a.yL = Lq; a.yP = P; a.yWt = Wt; a.ySx = Sx; }
@@ -435,10 +479,12 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
         } else {       // heun.jl:37-71
             a.mode = MODE_HEUN1; a.load_aux = aux_stale ? 1 : 0; a.t_x = t; a.t_b = t; x_state(a);
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
+            for (int i = 0; i < 3; ++i) { a.vy[i] = gveg[i]; a.vok1[i] = tveg[i]; }
             if (int rc = launch_euler(a, a.load_aux)) return rc;
             StageArgs<NF> b; base_args(b);
             b.dt = dt; b.mode = MODE_HEUN2; b.load_aux = 0; b.t_x = t1; b.t_b = t;
             b.xU = gU; b.xS = richards ? gS : S; b.xWt = gWt; b.bU = U; b.bS = S; b.bSx = Sx; b.k1U = tU; b.k1S = tS;
+            for (int i = 0; i < 3; ++i) { b.vx[i] = gveg[i]; b.vk1[i] = tveg[i]; }
             y_state(b);
             if (int rc = launch_euler(b, 0)) return rc;
         }
@@ -644,6 +690,14 @@ void trm_default_params(trm_params* p) {
     p->impedance = 7.0; p->vwc_forcing = 0.0;
     p->albedo = 0.3; p->emissivity = 0.97; p->kappa_skin = 2.0; p->C_h = 1.2e-3; p->min_windspeed = 0.01;
     p->tau_r = 3600.0; p->evap_beta = 1.0;
+    p->field_capacity = 0.25; p->wilting_point = 0.05; p->C_mass = 12.0;
+    p->tau25 = 2600.0; p->Kc25 = 30.0; p->Ko25 = 3.0e4; p->q10_tau = 0.57; p->q10_Kc = 2.1; p->q10_Ko = 1.2;
+    p->alpha_leaf = 0.17; p->alpha_a = 0.5; p->alpha_C3 = 0.08; p->cq = 4.6e-6; p->k_ext = 0.5;
+    p->T_CO2_high = 42.0; p->T_CO2_low = -4.0; p->T_photos_high = 30.0; p->T_photos_low = 15.0; p->theta_r = 0.7;
+    p->g1 = 2.3; p->g_min = 0.5; p->cn_sapwood = 330.0; p->cn_root = 29.0; p->aws = 10.0;
+    p->SLA = 10.0; p->awl = 2.0; p->LAI_min = 1.0; p->LAI_max = 6.0; p->gamma_L = 0.3; p->gamma_R = 0.3; p->gamma_S = 0.05;
+    p->nu_seed = 0.001; p->gamma_v_min = 0.002; p->root_a = 7.0; p->root_b = 2.0;
+    p->alpha_int = 0.2; p->k_ext_can = 0.5; p->w_can_max = 2.0e-4; p->tau_w = 86400.0; p->C_can = 0.006;
 }
 
 void trm_default_config(trm_config* c) {

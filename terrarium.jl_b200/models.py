@@ -183,10 +183,101 @@ class NoCanopyInterception:  # canopy_interception.jl:7
 
 
 @dataclass
-class SurfaceHydrology:  # surface_hydrology.jl:11-34 with the vegetation = nothing defaults (land_model.jl:119-125)
-    canopy_interception: Any = field(default_factory=NoCanopyInterception)
-    evapotranspiration: BareGroundEvaporation = field(default_factory=BareGroundEvaporation)
+class PALADYNCanopyInterception:  # canopy_interception.jl:33-45
+    alpha_int: float = 0.2
+    k_ext: float = 0.5
+    w_can_max: float = 2.0e-4
+    tau_w: float = 86400.0
+
+
+@dataclass
+class PALADYNCanopyEvapotranspiration:  # canopy_evapotranspiration.jl:28-44
+    C_can: float = 0.006
+    ground_resistance_factor: float = 1.0  # ConstantEvaporationResistanceFactor
+
+
+@dataclass
+class SurfaceHydrology:  # surface_hydrology.jl:11-34 ; defaults are filled by LandModel (land_model.jl:114-125)
+    canopy_interception: Any = None
+    evapotranspiration: Any = None
     surface_runoff: DirectSurfaceRunoff = field(default_factory=DirectSurfaceRunoff)
+
+
+# ---- vegetation processes (src/processes/vegetation/*.jl), one PFT (needleleaf tree defaults) ----
+@dataclass
+class LUEPhotosynthesis:  # photosynthesis.jl:19-67
+    tau25: float = 2600.0
+    Kc25: float = 30.0
+    Ko25: float = 3.0e4
+    q10_tau: float = 0.57
+    q10_Kc: float = 2.1
+    q10_Ko: float = 1.2
+    alpha_leaf: float = 0.17
+    alpha_a: float = 0.5
+    alpha_C3: float = 0.08
+    cq: float = 4.6e-6
+    k_ext: float = 0.5
+    T_CO2_high: float = 42.0
+    T_CO2_low: float = -4.0
+    T_photos_high: float = 30.0
+    T_photos_low: float = 15.0
+    theta_r: float = 0.7
+
+
+@dataclass
+class MedlynStomatalConductance:  # stomatal_conductance.jl:18-25
+    g1: float = 2.3
+    g_min: float = 0.5
+
+
+@dataclass
+class PALADYNAutotrophicRespiration:  # autotrophic_respiration.jl:16-25
+    cn_sapwood: float = 330.0
+    cn_root: float = 29.0
+    aws: float = 10.0
+
+
+class PALADYNPhenology:  # phenology.jl:14-15
+    pass
+
+
+@dataclass
+class PALADYNCarbonDynamics:  # carbon_dynamics.jl:18-39
+    SLA: float = 10.0
+    awl: float = 2.0
+    LAI_min: float = 1.0
+    LAI_max: float = 6.0
+    gamma_L: float = 0.3
+    gamma_R: float = 0.3
+    gamma_S: float = 0.05
+
+
+@dataclass
+class PALADYNVegetationDynamics:  # vegetation_dynamics.jl:14-20
+    nu_seed: float = 0.001
+    gamma_v_min: float = 0.002
+
+
+@dataclass
+class StaticExponentialRootDistribution:  # root_distribution.jl:25-31
+    a: float = 7.0
+    b: float = 2.0
+
+
+class FieldCapacityLimitedPAW:  # plant_available_water.jl:17
+    pass
+
+
+@dataclass
+class VegetationCarbon:  # vegetation_carbon.jl:6-66
+    photosynthesis: LUEPhotosynthesis = field(default_factory=LUEPhotosynthesis)
+    stomatal_conductance: MedlynStomatalConductance = field(default_factory=MedlynStomatalConductance)
+    autotrophic_respiration: PALADYNAutotrophicRespiration = field(default_factory=PALADYNAutotrophicRespiration)
+    phenology: PALADYNPhenology = field(default_factory=PALADYNPhenology)
+    carbon_dynamics: PALADYNCarbonDynamics = field(default_factory=PALADYNCarbonDynamics)
+    vegetation_dynamics: PALADYNVegetationDynamics = field(default_factory=PALADYNVegetationDynamics)
+    root_distribution: StaticExponentialRootDistribution = field(default_factory=StaticExponentialRootDistribution)
+    plant_available_water: FieldCapacityLimitedPAW = field(default_factory=FieldCapacityLimitedPAW)
 
 
 @dataclass
@@ -360,24 +451,43 @@ class SoilModel:  # src/models/soil/soil_model.jl:9-27
     sat_halo: str = "zero"
 
 
+_DEFAULT_VEGETATION = object()
+
+
 @dataclass
-class LandModel:  # src/models/coupled/land_model.jl:10-44 with vegetation = nothing
+class LandModel:  # src/models/coupled/land_model.jl:10-44
     grid: ColumnGrid
-    vegetation: None = None
-    # default_soil(grid, ::Nothing) = SoilEnergyWaterCarbon(NF): immobile soil water (land_model.jl:111-112)
-    soil: SoilEnergyWaterCarbon = field(default_factory=SoilEnergyWaterCarbon)
+    # reference default: VegetationCarbon(NF) (land_model.jl:26) ; vegetation=None is the bare-ground LandModel
+    vegetation: Any = _DEFAULT_VEGETATION
+    # default_soil: immobile soil water without vegetation, RichardsEq with (land_model.jl:111-112)
+    soil: Any = None
     surface_energy_balance: SurfaceEnergyBalance = field(default_factory=SurfaceEnergyBalance)
-    surface_hydrology: SurfaceHydrology = field(default_factory=SurfaceHydrology)
+    # default_surface_hydrology (land_model.jl:118-125)
+    surface_hydrology: Any = None
     atmosphere: PrescribedAtmosphere = field(default_factory=PrescribedAtmosphere)
     constants: PhysicalConstants = field(default_factory=PhysicalConstants)
     initializer: Any = field(default_factory=DefaultInitializer)
     sat_halo: str = "zero"
 
     def __post_init__(self):
-        if self.vegetation is not None:
-            raise NotImplementedError(
-                "LandModel with PALADYN vegetation is outside the built hot path (SURVEY.md 8f row f1); "
-                "use vegetation=None (bare ground)")
+        if self.vegetation is _DEFAULT_VEGETATION:
+            self.vegetation = VegetationCarbon()
+        veg = self.vegetation is not None
+        if veg and not isinstance(self.vegetation, VegetationCarbon):
+            raise TypeError(f"unsupported vegetation {type(self.vegetation).__name__}")
+        if self.soil is None:
+            self.soil = SoilEnergyWaterCarbon(hydrology=SoilHydrology(vertical_flow=RichardsEq())) if veg else SoilEnergyWaterCarbon()
+        if self.surface_hydrology is None:
+            self.surface_hydrology = SurfaceHydrology()
+        sh = self.surface_hydrology
+        if sh.canopy_interception is None:
+            sh.canopy_interception = PALADYNCanopyInterception() if veg else NoCanopyInterception()
+        if sh.evapotranspiration is None:
+            sh.evapotranspiration = PALADYNCanopyEvapotranspiration() if veg else BareGroundEvaporation()
+        canopy = isinstance(sh.canopy_interception, PALADYNCanopyInterception), isinstance(sh.evapotranspiration, PALADYNCanopyEvapotranspiration)
+        if veg != canopy[0] or veg != canopy[1]:
+            raise NotImplementedError("built combinations: vegetation=None with BareGroundEvaporation + NoCanopyInterception, "
+                                      "VegetationCarbon with PALADYNCanopyInterception + PALADYNCanopyEvapotranspiration")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -438,6 +548,23 @@ def build_params(model) -> abi.trm_params:
         p.C_h, p.min_windspeed = atm.C_h, atm.min_windspeed
         p.tau_r = sh.surface_runoff.tau_r
         p.evap_beta = sh.evapotranspiration.ground_resistance_factor
+    # vegetated LandModel
+    d = dict(field_capacity=hp.field_capacity, wilting_point=hp.wilting_point, C_mass=c.C_mass)
+    veg = getattr(model, "vegetation", None) or VegetationCarbon()
+    ph, sc, ar, cd, vd, rd = (veg.photosynthesis, veg.stomatal_conductance, veg.autotrophic_respiration, veg.carbon_dynamics,
+                              veg.vegetation_dynamics, veg.root_distribution)
+    for n in ("tau25", "Kc25", "Ko25", "q10_tau", "q10_Kc", "q10_Ko", "alpha_leaf", "alpha_a", "alpha_C3", "cq", "k_ext",
+              "T_CO2_high", "T_CO2_low", "T_photos_high", "T_photos_low", "theta_r"):
+        d[n] = getattr(ph, n)
+    d.update(g1=sc.g1, g_min=sc.g_min, cn_sapwood=ar.cn_sapwood, cn_root=ar.cn_root, aws=ar.aws,
+             SLA=cd.SLA, awl=cd.awl, LAI_min=cd.LAI_min, LAI_max=cd.LAI_max, gamma_L=cd.gamma_L, gamma_R=cd.gamma_R, gamma_S=cd.gamma_S,
+             nu_seed=vd.nu_seed, gamma_v_min=vd.gamma_v_min, root_a=rd.a, root_b=rd.b)
+    ci, et = PALADYNCanopyInterception(), PALADYNCanopyEvapotranspiration()
+    if isinstance(model, LandModel) and model.vegetation is not None:
+        ci, et = model.surface_hydrology.canopy_interception, model.surface_hydrology.evapotranspiration
+    d.update(alpha_int=ci.alpha_int, k_ext_can=ci.k_ext, w_can_max=ci.w_can_max, tau_w=ci.tau_w, C_can=et.C_can)
+    for n in abi.VEGETATION_PARAMS:
+        setattr(p, n, float(d[n]))
     return p
 
 
@@ -472,6 +599,7 @@ def build_config(model, timestepper, ncol: int, col0: int = 0, device: int = 0, 
     if isinstance(model, LandModel) and isinstance(model.surface_energy_balance.skin_temperature, PrescribedSkinTemperature):
         cfg.skin = abi.TRM_SKIN_PRESCRIBED
     cfg.math = abi.TRM_MATH_FAST if math == "fast" else abi.TRM_MATH_FAITHFUL
+    cfg.vegetation = abi.TRM_VEG_CARBON if isinstance(model, LandModel) and model.vegetation is not None else abi.TRM_VEG_NONE
     zbuf = np.ascontiguousarray(grid.z_faces, dtype=np.float64)
     import ctypes as C
     cfg.z_faces = zbuf.ctypes.data_as(C.POINTER(C.c_double))

@@ -68,7 +68,7 @@ def synthetic_land_case(engine, ncol, nf=np.float64, heun=False, nz=30, math="fa
     lat, lon, T0 = synthetic_columns(ncol)
     grid = trm.ColumnGrid(trm.B200(), nf, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=nz), ncol)
     # richards=False: the reference's default soil of LandModel(grid; vegetation = nothing), immobile soil water
-    model = trm.LandModel(grid, soil=richards_soil()) if richards else trm.LandModel(grid)
+    model = trm.LandModel(grid, soil=richards_soil(), vegetation=None) if richards else trm.LandModel(grid, vegetation=None)
     day = 86400.0
     # rain: 2e-8 m/s during the first 6 h of each day, as an hourly table over 3 days (flat outside)
     hours = np.arange(0, 73, dtype=np.float64)

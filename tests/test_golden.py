@@ -321,7 +321,7 @@ def test_euler_and_heun_stage_algebra(engine):
 # 10. surface energy balance -- test/surface_energy/{radiative_fluxes,turbulent_fluxes,skin_temperature}.jl
 # ---------------------------------------------------------------------------------------------
 def _land(grid, **kw):
-    return trm.LandModel(grid, soil=richards_soil(), **kw)
+    return trm.LandModel(grid, soil=richards_soil(), vegetation=None, **kw)
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -501,7 +501,7 @@ def test_function_valued_boundary_condition(engine):
 @pytest.mark.parametrize("stepper", ["euler", "heun"])
 def test_land_model_default_soil_is_immobile_water(engine, stepper):
     grid = column(trm.ExponentialSpacing(dz_max=1.0, N=20), n=3)
-    land = trm.LandModel(grid)
+    land = trm.LandModel(grid, vegetation=None)
     assert isinstance(land.soil.hydrology.vertical_flow, trm.NoFlow)
     ts = trm.ForwardEuler(dt=60.0) if stepper == "euler" else trm.Heun(dt=60.0)
     integ = make(engine, land, ts, {"rainfall": 1.0e-7, "windspeed": 0.5},
