@@ -76,10 +76,15 @@ def build_case(trm, make_integrator, ncol_global, rank, world, device, nf, math,
     grid = trm.ColumnGrid(trm.B200(device), nf, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=NZ), ncol_global)
     c0, c1 = grid.partition(rank, world)
     lon, T0 = synthetic(ncol_global, c0, c1)
-    if model_kind == "land":
-        # secondary workload (BASELINE configs[3], bare ground): synthetic atmosphere of BASELINE.md section 5 with a
-        # calm wind (see tests/test_parity.py on the stability of the as-coded skin / soil coupling at 3 m/s)
-        model = trm.LandModel(grid, soil=richards_soil(), vegetation=None)
+    if model_kind in ("land", "land-veg"):
+        # secondary workloads (BASELINE configs[3]): bare-ground LandModel, or the full LandModel with the PALADYN vegetation
+        # and canopy hydrology, under the synthetic atmosphere of BASELINE.md section 5 with a calm wind (see
+        # tests/test_parity.py on the stability of the as-coded skin / soil coupling at 3 m/s)
+        veg = None
+        if model_kind == "land-veg":   # turnover rates per second that keep the carbon pool in range (tests/test_vegetation.py)
+            veg = trm.VegetationCarbon(carbon_dynamics=trm.PALADYNCarbonDynamics(gamma_L=1e-9, gamma_R=1e-9, gamma_S=1e-10),
+                                       vegetation_dynamics=trm.PALADYNVegetationDynamics(gamma_v_min=1e-8))
+        model = trm.LandModel(grid, soil=richards_soil(), vegetation=veg)
         day = 86400.0
         hours = np.arange(0, 73, dtype=np.float64)
         rain = np.where((hours % 24) < 6, 2.0e-8, 0.0)
@@ -91,8 +96,11 @@ def build_case(trm, make_integrator, ncol_global, rank, world, device, nf, math,
         temp = (T0[None, :] - 0.05 * zc[:, None]).astype(nf)
         sat = np.ascontiguousarray(np.broadcast_to(np.minimum(1.0, 0.5 - 0.1 * zc)[:, None], temp.shape), dtype=nf)
         ts = (trm.Heun if heun else trm.ForwardEuler)(dt=DT)
-        integ = make_integrator(model, ts, inputs, initializers={"temperature": temp, "saturation_water_ice": sat, "skin_temperature": T0},
-                                partition=(rank, world), math=math)
+        inits = {"temperature": temp, "saturation_water_ice": sat, "skin_temperature": T0}
+        if veg is not None:
+            inputs.update(SAI=0.5, CO2=400.0)
+            inits.update(carbon_vegetation=10.0, vegetation_area_fraction=0.5)
+        integ = make_integrator(model, ts, inputs, initializers=inits, partition=(rank, world), math=math)
         return integ, lon, T0
     model = trm.SoilModel(grid, soil=richards_soil())
     if forcing == "sinusoid":
@@ -185,7 +193,8 @@ def main():
     ap.add_argument("--cpu-columns", type=int, default=1048576, help="columns of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--model", default="soil", choices=["soil", "land"], help="secondary workloads (not the headline): bare-ground LandModel")
+    ap.add_argument("--model", default="soil", choices=["soil", "land", "land-veg"],
+                    help="secondary workloads (not the headline): bare-ground LandModel, LandModel with PALADYN vegetation")
     ap.add_argument("--timestepper", default="euler", choices=["euler", "heun"], help="secondary workloads: Heun (two stage launches per step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -4,7 +4,7 @@
 # STATUS: UNTESTED SOURCE.  Neither `julia` nor Terrarium's dependencies exist in the build image or
 # on the GPU boxes, so this file has never been executed; the tested caller of the same C ABI is
 # the Python ctypes mirror (terrarium.jl_b200/integrator.py).  The struct layouts below must match
-# include/terrarium_b200.h field for field (TRM_ABI_VERSION = 1).
+# include/terrarium_b200.h field for field (TRM_ABI_VERSION = 2).
 #
 # What it replaces in the reference (paths relative to the Terrarium.jl root):
 #   initialize(model, timestepper, inputs...)            src/timesteppers/model_integrator.jl:145-161
@@ -20,9 +20,9 @@ import FreezeCurves: VanGenuchten, BrooksCorey
 
 const LIB = get(ENV, "TERRARIUM_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libterrarium_b200.so"))
 
-const TRM_ABI_VERSION = Int32(1)
+const TRM_ABI_VERSION = Int32(2)
 const TRM_BC_NSLOTS = 8
-@enum FieldId::Cint internal_energy=0 temperature=1 liquid_water_fraction=2 saturation_water_ice=3 pressure_head=4 hydraulic_conductivity=5 surface_excess_water=6 water_table=7 ground_temperature=8 skin_temperature=9 ground_heat_flux=10 surface_shortwave_up=11 surface_longwave_up=12 surface_net_radiation=13 sensible_heat_flux=14 latent_heat_flux=15 evaporation_ground=16 infiltration=17 surface_runoff=18
+@enum FieldId::Cint internal_energy=0 temperature=1 liquid_water_fraction=2 saturation_water_ice=3 pressure_head=4 hydraulic_conductivity=5 surface_excess_water=6 water_table=7 ground_temperature=8 skin_temperature=9 ground_heat_flux=10 surface_shortwave_up=11 surface_longwave_up=12 surface_net_radiation=13 sensible_heat_flux=14 latent_heat_flux=15 evaporation_ground=16 infiltration=17 surface_runoff=18 carbon_vegetation=21 vegetation_area_fraction=22 canopy_water=23 balanced_leaf_area_index=24 leaf_area_index=25 phenology_factor=26 canopy_water_conductance=27 leaf_to_air_co2_ratio=28 net_assimilation=29 leaf_respiration=30 gross_primary_production=31 autotrophic_respiration=32 net_primary_production=33 soil_moisture_limiting_factor=34 canopy_water_interception=35 canopy_water_removal=36 saturation_canopy_water=37 rainfall_ground=38 evaporation_canopy=39 transpiration=40 plant_available_water=41 root_fraction=42
 
 struct TrmParams                      # trm_params
     mineral_porosity::Cdouble; organic_porosity::Cdouble; rho_soc::Cdouble; rho_org::Cdouble
@@ -31,11 +31,14 @@ struct TrmParams                      # trm_params
     K_sat::Cdouble; vg_alpha::Cdouble; vg_n::Cdouble; bc_psis::Cdouble; bc_lambda::Cdouble; theta_res::Cdouble
     impedance::Cdouble; vwc_forcing::Cdouble
     albedo::Cdouble; emissivity::Cdouble; kappa_skin::Cdouble; C_h::Cdouble; min_windspeed::Cdouble; tau_r::Cdouble; evap_beta::Cdouble
+    # vegetated LandModel (40 doubles, header order: field_capacity .. C_can)
+    vegetation::NTuple{40, Cdouble}
 end
 struct TrmBC; kind::Int32; input::Int32; end       # trm_bc
 struct TrmConfig                      # trm_config
     abi_version::Int32; dtype::Int32; ncol::Int64; col0::Int64; nz::Int32; device::Int32
     model::Int32; timestepper::Int32; hydrology::Int32; swrc::Int32; unsat_k::Int32; sat_halo::Int32; skin::Int32; math::Int32
+    vegetation::Int32                 # trm_vegetation: 0 = nothing (bare ground), 1 = VegetationCarbon
     z_faces::Ptr{Cdouble}
     params::TrmParams
     bc::NTuple{TRM_BC_NSLOTS, TrmBC}
@@ -76,7 +79,25 @@ function params_of(model)
         hp.unsat_hydraulic_cond isa UnsatKVanGenuchten ? hp.unsat_hydraulic_cond.impedance : 7.0, 0.0,
         land ? seb.albedo.albedo : 0.3, land ? seb.albedo.emissivity : 0.97, land ? seb.skin_temperature.κₛ : 2.0,
         land ? model.atmosphere.aerodynamics.C_h : 1.2e-3, land ? model.atmosphere.min_windspeed : 0.01,
-        land ? model.surface_hydrology.surface_runoff.τ_r : 3600.0, 1.0)
+        land ? model.surface_hydrology.surface_runoff.τ_r : 3600.0, 1.0,
+        vegetation_params(model, hp, c))
+end
+
+# parameters of VegetationCarbon + PALADYN canopy hydrology in the order of trm_params (reference defaults when absent)
+function vegetation_params(model, hp, c)
+    veg = model isa LandModel && !isnothing(model.vegetation) ? model.vegetation : Terrarium.VegetationCarbon(Float64)
+    ph, sc, ar, cd, vd, rd = veg.photosynthesis, veg.stomatal_conductance, veg.autotrophic_respiration, veg.carbon_dynamics,
+                             veg.vegetation_dynamics, veg.root_distribution
+    vegetated = model isa LandModel && !isnothing(model.vegetation)
+    ci = vegetated ? model.surface_hydrology.canopy_interception : Terrarium.PALADYNCanopyInterception(Float64)
+    et = vegetated ? model.surface_hydrology.evapotranspiration : Terrarium.PALADYNCanopyEvapotranspiration(Float64)
+    Cdouble.((hp.field_capacity, hp.wilting_point, c.C_mass,
+              ph.τ25, ph.Kc25, ph.Ko25, ph.q10_τ, ph.q10_Kc, ph.q10_Ko, ph.α_leaf, ph.α_a, ph.α_C3, ph.cq, ph.k_ext,
+              ph.T_CO2_high, ph.T_CO2_low, ph.T_photos_high, ph.T_photos_low, ph.θ_r,
+              sc.g₁, sc.g_min, ar.cn_sapwood, ar.cn_root, ar.aws,
+              cd.SLA, cd.awl, cd.LAI_min, cd.LAI_max, cd.γL, cd.γR, cd.γS,
+              vd.ν_seed, vd.γv_min, rd.a, rd.b,
+              ci.α_int, ci.k_ext, ci.w_can_max, ci.τ_w, et.C_can))
 end
 
 """
@@ -96,12 +117,14 @@ function initialize_b200(model::Union{SoilModel{NF}, LandModel{NF}}, timestepper
     cfg = Ref(TrmConfig(TRM_ABI_VERSION, dtype_code(NF), ncol, 0, nz, device,
         model isa LandModel ? 1 : 0, timestepper isa Heun ? 1 : 0, hyd.vertical_flow isa RichardsEq ? 1 : 0,
         hyd.hydraulic_properties.swrc isa VanGenuchten ? 0 : 1, hyd.hydraulic_properties.unsat_hydraulic_cond isa UnsatKVanGenuchten ? 1 : 0,
-        0, 0, math === :fast ? 1 : 0, pointer(zf), params_of(model), bcs))
+        0, 0, math === :fast ? 1 : 0, (model isa LandModel && !isnothing(model.vegetation)) ? 1 : 0, pointer(zf), params_of(model), bcs))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve zf check(ccall((:trm_create, LIB), Cint, (Ref{TrmConfig}, Ref{Ptr{Cvoid}}), cfg, h), "create")
     integ = B200Integrator{NF, typeof(model), typeof(timestepper)}(h[], model, timestepper, ncol, nz)
     finalizer(i -> ccall((:trm_destroy, LIB), Cint, (Ptr{Cvoid},), i.handle), integ)
-    for name in (:temperature, :saturation_water_ice)
+    names = (model isa LandModel && !isnothing(model.vegetation)) ?
+        (:temperature, :saturation_water_ice, :carbon_vegetation, :vegetation_area_fraction, :canopy_water) : (:temperature, :saturation_water_ice)
+    for name in names
         set_field!(integ, name, permutedims(Array(Terrarium.interior(getproperty(ref.state, name)))[:, 1, :]))   # [layer, column]
     end
     check(ccall((:trm_initialize, LIB), Cint, (Ptr{Cvoid},), integ.handle), "initialize")
@@ -116,7 +139,8 @@ end
 
 """`interior(field)` as a host array `[layer, column]` (layer 1 = bottom cell) or `[column]` for 2-D fields."""
 function get_field(integ::B200Integrator{NF}, name::Symbol) where {NF}
-    rows = name in (:internal_energy, :temperature, :liquid_water_fraction, :saturation_water_ice, :pressure_head) ? integ.nz :
+    rows = name in (:internal_energy, :temperature, :liquid_water_fraction, :saturation_water_ice, :pressure_head,
+                    :plant_available_water, :root_fraction) ? integ.nz :
            name === :hydraulic_conductivity ? integ.nz + 1 : 1
     out = Array{NF}(undef, integ.ncol, rows)
     check(ccall((:trm_get_field, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), integ.handle,

@@ -18,6 +18,12 @@ for p in (os.path.dirname(HERE), os.path.join(os.path.dirname(os.path.dirname(HE
 
 from common import synthetic_land_case, synthetic_soil_case  # noqa: E402
 
+
+def synthetic_vegetated_case(*a, **kw):
+    from test_vegetation import synthetic_vegetated_case as f
+    return f(*a, **kw)
+
+
 NCOL = 16
 CASES = {
     # name: (builder kwargs, dt, steps, fields)
@@ -32,6 +38,11 @@ CASES = {
                                 "latent_heat_flux", "sensible_heat_flux", "infiltration", "surface_runoff", "surface_excess_water")),
     "land_default_soil_heun": (lambda e: synthetic_land_case(e, NCOL, windspeed=0.5, richards=False, heun=True), 60.0, 200,
                                ("internal_energy", "temperature", "liquid_water_fraction", "skin_temperature", "ground_heat_flux")),
+    "land_vegetation_heun": (lambda e: synthetic_vegetated_case(e, NCOL, heun=True), 60.0, 200,
+                             ("internal_energy", "temperature", "saturation_water_ice", "skin_temperature", "ground_heat_flux", "latent_heat_flux",
+                              "carbon_vegetation", "vegetation_area_fraction", "canopy_water", "net_assimilation", "net_primary_production",
+                              "canopy_water_conductance", "transpiration", "evaporation_canopy", "evaporation_ground", "rainfall_ground",
+                              "soil_moisture_limiting_factor")),
 }
 
 
@@ -43,7 +54,7 @@ def run(name, engine):
 
 
 if __name__ == "__main__":
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):   # optional: only the named cases
         out = run(name, "oracle")
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items()})
