@@ -158,6 +158,10 @@ struct M<float, true> {
     __device__ static __forceinline__ void roots(float x, float& x23, float& x12) { x23 = pow23(x); x12 = sqrtf(x); }
 };
 
+// a / b: IEEE division in the faithful build, reciprocal seed + one third-order step (<= 2 ulp) in the fast build
+template <class NF, bool FAST>
+__device__ __forceinline__ NF dv(NF a, NF b) { return FAST ? M<NF, FAST>::div(a, b) : a / b; }
+
 // volumetric fractions, src/processes/soil/stratigraphy/soil_volume.jl:52-67,103-107
 template <class NF>
 struct Fractions { NF water, ice, air, mineral, organic; };

@@ -23,12 +23,15 @@ namespace trm {
 #ifndef TRM_EULER_MIN_BLOCKS
 #define TRM_EULER_MIN_BLOCKS 6   // <= 80 registers per thread, 24 resident warps per SM (measured: 4 blocks 5.08 ms, 5: 4.52, 6: 4.16 per 10 M-column step)
 #endif
+#ifndef TRM_EULER_LAND_BLOCKS
+#define TRM_EULER_LAND_BLOCKS 6   // the LandModel variants no longer contain the surface block (surface_kernel): same budget as the soil kernel
+#endif
 // Resident blocks per SM the register allocator must allow. Register spills are ruinous here (shared memory
 // leaves little L1 for local memory), so the faithful math mode with its inlined pow / IEEE division sequences
-// gets a looser bound; the LandModel variant runs best with 5 blocks (measured 4: 5.9 ms, 5: 5.1 ms, 6: 6.7 ms).
+// gets a looser bound.
 template <class NF, int PHYS, bool FAST, int MODE = MODE_EULER>
 constexpr int euler_min_blocks() {
-    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (phys_land(PHYS) ? 5 : (sizeof(NF) == 4 ? 8 : TRM_EULER_MIN_BLOCKS)));
+    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (phys_land(PHYS) ? TRM_EULER_LAND_BLOCKS : (sizeof(NF) == 4 ? 8 : TRM_EULER_MIN_BLOCKS)));
 }
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
@@ -52,8 +55,10 @@ __device__ __forceinline__ bool below_one(float v)  { return __float_as_int(v) <
 
 // fields of the per-thread pipeline strip. One slot each (written at the end of iteration m, read by iteration
 // m+1 before it is overwritten), except Kf which iteration m+2 still needs (two alternating slots, EF_KF and
-// EF_KF + 1) and, for the LandModel, a copy of the top layer's temperature (EF_TTOP) that outlives the halo iteration.
-enum EulerField { EF_KF = 0, EF_T = 2, EF_P, EF_KAP, EF_KC, EF_QH, EF_G, EF_DQH, EF_QD, EF_TTOP, EF_COUNT };
+// EF_KF + 1) and, for the vegetated LandModel, the running soil moisture limiting factor of the state being written
+// (EF_BETA). The LandModel variants do not evaluate the surface block: surface_kernel (stage_kernel.cuh) has run before
+// and left the ground heat flux and the infiltration in their 2-D fields.
+enum EulerField { EF_KF = 0, EF_T = 2, EF_P, EF_KAP, EF_KC, EF_QH, EF_G, EF_DQH, EF_QD, EF_BETA, EF_COUNT };
 constexpr int EULER_PF = 4;   // depth of the prefetch rings consumed when a layer enters (layers in flight: 3)
 constexpr int EULER_RD = 8;   // depth of the U / sat ring: layer k stays in slot (k & 7) from its prefetch (iteration
                               // k-3) until it is updated (iteration k+2), so the raw values are never copied
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     NF Sx_new = NF(0);
     if (RICH && !H1) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
     uint32_t oout = (uint32_t)c;   // element offset of layer m-2
-    NF beta_sm = NF(0);            // vegetated LandModel: soil moisture limiting factor (plant_available_water.jl:31-35)
+    if (LAND && has_veg(A)) wr(EF_BETA, NF(0));   // vegetated LandModel: soil moisture limiting factor (plant_available_water.jl:31-35)
 
     // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-3, for which every
     // layer-index special case below is statically false / true: no halo, no boundary face, no Flux BC, the
@@ -189,14 +194,11 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
             }
             kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
-            if (LAND && A.veg) beta_sm += plant_available_water(A.vp, p, sr, ln) * met.root(m) / met.dzc(m) * met.dzc(m);
             if (RICH) {
                 // cell conductivity and face conductivity Kf[m], soil_hydrology.jl:249-276
                 const NF Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
                 Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : Mx::mn(Kcn, rd(EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
                 wr(EF_KC, Kcn);
-            } else if (LAND && !inner && m == nz) {
-                Kfn = cell_conductivity<NF, FAST>(p, sr, ln);   // compute_hydraulics! (soil_hydrology.jl:145-163): the runoff scheme reads Kf[Nz] = Kc[Nz]
             }
         } else if (!inner && m == nz + 1) {   // halo above the surface, built from layer nz (prv)
             Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
@@ -240,10 +242,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
 
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         NF G_top = NF(0), infil_top = NF(0);   // fluxes coupling the surface to the top soil layer (same iteration)
-        if (LAND && !inner && m == nz + 2) {
-            if (H2 && !A.veg) { G_top = A.G[c]; infil_top = A.infil[c]; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
-            else land_surface(A, c, RICH, rd(EF_TTOP), ldsv(ringS(nz), (NF*)nullptr), ldsv(kf_cur, (NF*)nullptr), met.dzc(nz), beta_sm, H2, G_top, infil_top);
-        }
+        // (evaluated by surface_kernel on the time-n state; Heun stage 2 applies the same time-n fluxes, heun.jl:63-66)
+        if (LAND && !inner && m == nz + 2) { G_top = A.G[c]; infil_top = A.infil[c]; }
 
         if (inner || m >= 3) {
             // ---- tendencies of layer j = m-2 ----
@@ -312,20 +312,25 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                     if (idx == 0 && (FAST ? below_one(sn) : sn < 1)) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                 }
                 A.yU[o] = Un;
-                if (CLOSE) {
+                if (CLOSE || (LAND && has_veg(A))) {
                     NF Tc, lc;
                     energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
-                    A.yT[o] = Tc; A.yL[o] = lc;
-                    // layers below the water table wait for it (written after the sweep)
-                    if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j));
+                    // vegetated LandModel: soil moisture limiting factor of the NEW state, for the surface block of the
+                    // next evaluation (Integral(PAW * root_fraction / dz, dims = 3), accumulated bottom -> top)
+                    if (LAND && has_veg(A))
+                        wr(EF_BETA, rd(EF_BETA) + (FAST ? plant_available_water_fast(A.vp, p, sn, lc) * met.root(j)
+                                                        : plant_available_water(A.vp, p, sn, lc) * met.root(j) / met.dzc(j) * met.dzc(j)));
+                    if (CLOSE) {
+                        A.yT[o] = Tc; A.yL[o] = lc;
+                        // layers below the water table wait for it (written after the sweep)
+                        if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j));
+                    }
                 }
             }
         }
         // ---- what later iterations need from this one ----
         wr(EF_T, Tn); wr(EF_KAP, kapn); wr(EF_QH, qhn); wr(EF_DQH, dqhn);
-        if (LAND && !inner && m == nz) wr(EF_TTOP, Tn);
         if (RICH) { wr(EF_P, Pn); sts(kf_cur, Kfn); wr(EF_G, gn); wr(EF_QD, qdn); }
-        else if (LAND) sts(kf_cur, Kfn);
         const uint32_t t = kf_cur; kf_cur = kf_prv; kf_prv = t;
     };
     {
@@ -341,6 +346,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             }
         }
     }
+    if (LAND && has_veg(A) && !(RICH && any_neg())) A.ybeta[c] = rd(EF_BETA);
     if (!RICH) return;
 
     if (!any_neg()) {
@@ -383,16 +389,21 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         if (idx == 0) idx = nz + 1;
         wt_new = met.zF(idx);
         A.yWt[c] = wt_new;
-        if (H1) return;
-        A.ySx[c] = Sx_new;
+        if (H1 && !(LAND && has_veg(A))) return;
+        if (!H1) A.ySx[c] = Sx_new;
+        NF beta = NF(0);
 #pragma unroll 1
         for (int k = 1; k <= nz; ++k) {
             const int64_t o = (int64_t)(k - 1) * ld + c;
             NF s = A.yS[o], U = A.yU[o], Tc, lc;
             energy_to_temperature<NF, FAST>(p, U, s, Tc, lc);
+            if (LAND && has_veg(A))
+                beta += FAST ? plant_available_water_fast(A.vp, p, s, lc) * met.root(k) : plant_available_water(A.vp, p, s, lc) * met.root(k) / met.dzc(k) * met.dzc(k);
+            if (H1) continue;   // the stage state keeps no closure fields
             A.yT[o] = Tc; A.yL[o] = lc;
             A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, met.zC(k), met.psiz(k));
         }
+        if (LAND && has_veg(A)) A.ybeta[c] = beta;
     }
 }
 

@@ -18,6 +18,9 @@ struct KernelSet {
     // memory (euler_kernel.cuh); cudaErrorInvalidConfiguration = not applicable, use the generic kernel
     cudaError_t (*euler_f32)(int phys, int mode, int load_aux, const StageArgs<float>& a, cudaStream_t st);
     cudaError_t (*euler_f64)(int phys, int mode, int load_aux, const StageArgs<double>& a, cudaStream_t st);
+    // LandModel surface block as its own launch (what = 0) / soil moisture limiting factor from stored fields (what = 1)
+    cudaError_t (*surface_f32)(int what, const StageArgs<float>& a, cudaStream_t st);
+    cudaError_t (*surface_f64)(int what, const StageArgs<double>& a, cudaStream_t st);
 };
 
 const KernelSet& kernels_faithful();   // compiled with -fmad=false, reference operation order

@@ -69,6 +69,14 @@ cudaError_t launch_stage(int phys, int variant, const StageArgs<NF>& a, int bloc
 }
 
 template <class NF>
+cudaError_t launch_surface(int what, const StageArgs<NF>& a, cudaStream_t st) {
+    const unsigned nblk = (unsigned)((a.ncol + 127) / 128);
+    if (what == 0) surface_kernel<NF, kFast><<<nblk, 128, 0, st>>>(a);
+    else beta_kernel<NF, kFast><<<nblk, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <class NF>
 cudaError_t launch_init(int64_t ncol, int64_t ld, int nz, int richards, const NF* metrics, const DevParams<NF>& p,
                         NF* U, NF* S, NF* T, NF* L, NF* P, NF* Wt, NF* Sx, cudaStream_t st) {
     const int block = 128;
@@ -84,7 +92,7 @@ const KernelSet& kernels_fast() {
 const KernelSet& kernels_faithful() {
 #endif
     static const KernelSet ks = {&launch_stage<float>, &launch_stage<double>, &launch_init<float>, &launch_init<double>,
-                                 &launch_euler<float>, &launch_euler<double>};
+                                 &launch_euler<float>, &launch_euler<double>, &launch_surface<float>, &launch_surface<double>};
     return ks;
 }
 

@@ -87,7 +87,7 @@ struct InputDesc {
 template <class NF>
 struct StageArgs {
     int64_t ncol, ld;
-    int32_t nz, mode, load_aux, pad_;
+    int32_t nz, mode, load_aux, richards;
     NF dt;
     NF t_x;   // clock time of the state the tendencies are evaluated on (halo BC inputs, forcing)
     NF t_b;   // clock time of the base state (Flux BC inputs); differs from t_x only in Heun stage 2
@@ -111,12 +111,26 @@ struct StageArgs {
     const NF *vx[3], *vb[3], *vk1[3];
     NF *vy[3], *vok1[3];
     NF* paw;
+    // soil moisture limiting factor of the state the surface block is evaluated on (read by surface_kernel) and of the
+    // state a stage kernel writes (accumulated there while the closure fields of the new state are formed)
+    const NF* xbeta;
+    NF* ybeta;
     VegParams<NF> vp;
     const NF* metrics;   // [MET_COUNT][MET_STRIDE], see enum Metric
     DevParams<NF> p;
     trm_bc bc[TRM_BC_NSLOTS];
     InputDesc<NF> in[TRM_IN_COUNT];
 };
+
+// vegetated LandModel? (TRM_NO_VEG: tuning builds that compile the vegetation code out)
+template <class NF>
+__device__ __forceinline__ bool has_veg(const StageArgs<NF>& A) {
+#ifdef TRM_NO_VEG
+    return false;
+#else
+    return A.veg != 0;
+#endif
+}
 
 // update_inputs! (input_sources.jl:165-171) and function valued BCs, evaluated at clock time t.
 template <class NF>
@@ -153,6 +167,17 @@ __device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t 
 template <class NF>
 __device__ __noinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) { return eval_input_inline(s, c, t); }
 
+// input evaluation of the surface block: inlined (independent loads overlap; measured 1.5 % faster than one shared
+// out-of-line copy, TRM_SURFACE_SHARED_INPUTS)
+template <class NF>
+__device__ __forceinline__ NF surface_input(const InputDesc<NF>& s, int64_t c, NF t) {
+#ifdef TRM_SURFACE_SHARED_INPUTS
+    return eval_input(s, c, t);
+#else
+    return eval_input_inline(s, c, t);
+#endif
+}
+
 // Oceananigans halo fill for one side.  `D` is the face spacing at the
 // boundary, `top` selects the sign convention.
 template <class NF>
@@ -174,16 +199,95 @@ struct Surface {
 
 // compute_surface_energy_fluxes! (one evaluation), surface_energy_balance.jl:119-144:
 // radiative_fluxes.jl:85-100,196-209 ; turbulent_fluxes.jl:85-105,137-150 ; skin_temperature.jl:76-80
-template <class NF>
+template <class NF, bool FAST>
 __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface<NF>& a, NF Tsurf, NF Egnd,
                                            NF& swu, NF& lwu, NF& rnet, NF& hs, NF& hl, NF& G) {
     swu = p.albedo * a.SWd;
     NF TK = Tsurf + p.Tref;
     lwu = p.emis * p.sigma * pow4(TK) + (1 - p.emis) * a.LWd;
     rnet = swu - a.SWd + lwu - a.LWd;
-    hs = (NF)((double)(p.c_a * p.rho_a) * ((double)(Tsurf - a.Ta) / a.ra));
+    hs = (NF)((double)(p.c_a * p.rho_a) * dv<double, FAST>((double)(Tsurf - a.Ta), a.ra));
     hl = p.Llg * p.rho_a * Egnd;
     G = rnet - hs - hl;
+}
+
+// Vegetation and canopy block of the vegetated LandModel for one column (see land_surface). Its own out-of-line
+// function: the bare-ground LandModel must not pay for the registers this block needs around the call. Scalars come
+// in by value; the results land_surface needs (ground / canopy evaporation, transpiration, rain reaching the ground)
+// are read back from the auxiliary fields this function writes.
+template <class NF, bool FAST>
+__device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t c, NF Ta, NF SWd, NF pres, NF ea, NF rain, NF Vc, double ra,
+                                                NF dq, NF T_top, NF beta_sm, bool stage2) {
+    const DevParams<NF>& p = A.p;
+    const VegParams<NF>& v = A.vp;
+    const NF co2 = surface_input(A.in[TRM_IN_CO2], c, A.t_x);
+    const NF SAI = surface_input(A.in[TRM_IN_SAI], c, A.t_x);
+    const NF Rdl = surface_input(A.in[TRM_IN_DAILY_LEAF_RESPIRATION], c, A.t_x);
+    const NF Cv = A.vx[0][c], nu = A.vx[1][c], wcan = A.vx[2][c];
+    const NF An_prev = A.veg2d[VF_AN][c];
+    // PALADYNCarbonDynamics / PALADYNPhenology auxiliaries (carbon_dynamics.jl:82-85, phenology.jl:33-70)
+    const NF LAIb = dv<NF, FAST>(Cv, (NF(2.0) / v.SLA) + v.awl);
+    const NF fdec = NF(0), phen = NF(1.0);
+    const NF LAI = (fdec * phen + (NF(1.0) - fdec)) * LAIb;
+    // MedlynStomatalConductance (stomatal_conductance.jl:45-82): vapour pressure deficit at the air temperature,
+    // net assimilation of the PREVIOUS evaluation (vegetation_carbon.jl:89-91)
+    const NF vpd_air = jmax(saturation_vapor_pressure(Ta) - ea, NF(0.1));
+    const NF g0 = (v.g_min / 1000) * (1 - texp(-v.k_ext * LAI)) * beta_sm;
+    const NF gw = g0 + dv<NF, FAST>(NF(1.6) * (1 + dv<NF, FAST>(v.g1, tsqrt(vpd_air))) * An_prev, co2) * NF(1.0e6);
+    const NF lamc = NF(1.0) - dv<NF, FAST>(NF(1.0), NF(1.0) + dv<NF, FAST>(v.g1, tsqrt(vpd_air * NF(1.0e-3))));
+    // LUEPhotosynthesis (photosynthesis.jl:284-344)
+    NF Rd, An;
+    photosynthesis<NF, FAST>(v, Ta, SWd, pres, co2, LAI, lamc, beta_sm, Rd, An);
+    const NF GPP = An * NF(1.0e-3);
+    // PALADYNAutotrophicRespiration (autotrophic_respiration.jl:46-154) ; T_soil = ground temperature
+    const NF f_soil = (T_top > 7) ? texp(NF(308.56) * (NF(1.0) / NF(56.02) - dv<NF, FAST>(NF(1.0), NF(46.02) + T_top))) : NF(0);
+    const NF f_air = texp(NF(308.56) * (NF(1.0) / NF(56.02) - dv<NF, FAST>(NF(1.0), NF(46.02) + Ta)));
+    const NF resp10 = NF(0.066);
+    const NF R_leaf = Rdl / NF(1000.0);
+    const NF R_stem = dv<NF, FAST>(resp10 * f_air * (v.awl * ((NF(2.0) / v.SLA) + v.awl)), Cv * v.aws * v.cn_sapwood);
+    const NF R_root = dv<NF, FAST>(resp10 * f_soil * phen * (NF(2.0) / v.SLA), v.SLA * Cv * v.cn_root);
+    const NF Rm = R_leaf + R_stem + R_root;
+    const NF Rg = NF(0.25) * (GPP - Rm);
+    const NF Ra = Rm + Rg;
+    const NF NPP = GPP - Ra;
+    // PALADYNCanopyInterception (canopy_interception.jl:79-187)
+    const NF wmax = v.w_can_max * (LAI + SAI);
+    const NF f_can = wmax > 0 ? dv<NF, FAST>(wcan, wmax) : NF(0);
+    const NF I_can = v.alpha_int * rain * (NF(1) - texp(-v.k_ext_can * (LAI + SAI)));
+    const NF R_can = jmax(wcan, NF(0)) / v.tau_w;
+    const NF rain_ground = rain - I_can + R_can;
+    // PALADYNCanopyEvapotranspiration (canopy_evapotranspiration.jl:51-177): humidity gradients at the skin and at
+    // the ground temperature, resistance between ground and canopy, stomatal resistance
+    const NF esg = saturation_vapor_pressure(T_top);
+    const NF dqg = dv<NF, FAST>(p.eps_mw * jmax(esg - ea, NF(0.1)), pres);
+    const NF re = dv<NF, FAST>(1 - texp(-LAI - SAI), v.C_can * Vc);
+    const NF rs = dv<NF, FAST>(NF(1), jmax(gw, tsqrt(Lim<NF>::eps())));
+    const NF transp = (NF)dv<double, FAST>((double)dq, ra + (double)rs);
+    const NF Egnd = (NF)dv<double, FAST>((double)(p.beta * dqg), ra + (double)re);
+    const NF E_can = (NF)dv<double, FAST>((double)(f_can * dq), ra);
+    // tendencies: canopy water (canopy_interception.jl:121-127), vegetation carbon (carbon_dynamics.jl:107-112),
+    // vegetation area fraction (vegetation_dynamics.jl:60-75)
+    const NF lam = lambda_NPP(v, LAIb);
+    NF k[3];
+    k[2] = I_can - E_can - R_can;
+    k[0] = (NF(1.0) - lam) * NPP - (v.gamma_L / v.SLA + v.gamma_R / v.SLA + v.gamma_S * v.awl) * LAIb;
+    const NF nus = jmax(nu, v.nu_seed);
+    k[1] = dv<NF, FAST>(lam * NPP, Cv) * nus * (NF(1.0) - nu) - v.gamma_v * nus;
+    if (A.mode == MODE_EULER || A.mode == MODE_HEUN1 || A.mode == MODE_HEUN2) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            NF ki = k[i];
+            if (A.mode == MODE_HEUN1) A.vok1[i][c] = ki;
+            if (A.mode == MODE_HEUN2) ki = (A.vk1[i][c] + ki) / 2;   // average_tendencies!, heun.jl:27-35
+            A.vy[i][c] = A.vb[i][c] + ki * A.dt;
+        }
+    }
+    if (stage2) return;   // the auxiliaries of a stage-2 evaluation belong to the stage copy (heun.jl:45-58)
+    NF* const* o = A.veg2d;
+    o[VF_LAIB][c] = LAIb; o[VF_LAI][c] = LAI; o[VF_PHEN][c] = phen; o[VF_GWCAN][c] = gw; o[VF_LAMC][c] = lamc;
+    o[VF_AN][c] = An; o[VF_RD][c] = Rd; o[VF_GPP][c] = GPP; o[VF_RA][c] = Ra; o[VF_NPP][c] = NPP; o[VF_BETASM][c] = beta_sm;
+    o[VF_ICAN][c] = I_can; o[VF_RCAN][c] = R_can; o[VF_FCAN][c] = f_can; o[VF_RAING][c] = rain_ground;
+    o[VF_ECAN][c] = E_can; o[VF_TRANSP][c] = transp; A.Egnd[c] = Egnd;
 }
 
 // LandModel per-column surface processes for one update_state! (land_model.jl:79-88): bare-ground evaporation,
@@ -196,115 +300,50 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
 // evapotranspiration (surface_hydrology.jl:36-50) and advances canopy water, vegetation carbon and area fraction.
 // `stage2` (Heun stage 2): only what feeds the k2 tendencies of those three variables is evaluated -- on the stage
 // state, at t + dt -- and no auxiliary field is written (they belong to the stage copy in the reference, heun.jl:45-58).
-template <class NF>
+template <class NF, bool FAST>
 __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF K_top, NF dz_top, NF beta_sm,
                                           bool stage2, NF& G_out, NF& inf_out) {
     const DevParams<NF>& p = A.p;
-    const bool veg = A.veg != 0;
-    // (inputs evaluated inline: their loads are independent and overlap; through eval_input() they would serialise)
+    const bool veg = has_veg(A);
+    // (inputs: see surface_input)
     Surface<NF> a;
     // surface_excess_water(...) is the prognostic field under RichardsEq (soil_hydrology_rre.jl:28) and identically
     // zero for immobile soil water (soil_hydrology.jl:138)
     const NF Ts0 = A.Ts[c], S = richards ? A.bSx[c] : NF(0);
-    a.SWd = eval_input_inline(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
-    a.LWd = eval_input_inline(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
-    a.Ta = eval_input_inline(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
-    a.pres = eval_input_inline(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
-    a.q = eval_input_inline(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
-    a.V = eval_input_inline(A.in[TRM_IN_WINDSPEED], c, A.t_x);
-    a.rain = eval_input_inline(A.in[TRM_IN_RAINFALL], c, A.t_x);
+    a.SWd = surface_input(A.in[TRM_IN_SHORTWAVE_DOWN], c, A.t_x);
+    a.LWd = surface_input(A.in[TRM_IN_LONGWAVE_DOWN], c, A.t_x);
+    a.Ta = surface_input(A.in[TRM_IN_AIR_TEMPERATURE], c, A.t_x);
+    a.pres = surface_input(A.in[TRM_IN_AIR_PRESSURE], c, A.t_x);
+    a.q = surface_input(A.in[TRM_IN_SPECIFIC_HUMIDITY], c, A.t_x);
+    a.V = surface_input(A.in[TRM_IN_WINDSPEED], c, A.t_x);
+    a.rain = surface_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
     const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
-    a.Tskin_in = prescribed ? eval_input_inline(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
+    a.Tskin_in = prescribed ? surface_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
     // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
     NF Vc = jmax(a.V, p.Vmin);
     double Va = fmax((double)Vc, 1.0e-6);
-    a.ra = 1.0 / ((double)p.C_h * Va);
+    a.ra = dv<double, FAST>(1.0, (double)p.C_h * Va);
     NF Ts = Ts0;
     // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
     // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
     NF Tsurf = prescribed ? a.Tskin_in : Ts;
     NF es = saturation_vapor_pressure(Tsurf);
-    NF ea = a.q * a.pres / (p.eps_mw + (1 - p.eps_mw) * a.q);
+    NF ea = dv<NF, FAST>(a.q * a.pres, p.eps_mw + (1 - p.eps_mw) * a.q);
     NF vpd = jmax(es - ea, NF(0.1));
-    NF dq = p.eps_mw * vpd / a.pres;
-    NF Egnd = (NF)((double)(p.beta * dq) / a.ra);
+    NF dq = dv<NF, FAST>(p.eps_mw * vpd, a.pres);
+    NF Egnd = (NF)dv<double, FAST>((double)(p.beta * dq), a.ra);
     NF rain_ground = a.rain;   // NoCanopyInterception: rainfall_ground aliases rainfall (canopy_interception.jl:11-15)
     NF Qh = Egnd;              // surface_humidity_flux of the evapotranspiration scheme
     if (veg) {
-        const VegParams<NF>& v = A.vp;
-        const NF co2 = eval_input_inline(A.in[TRM_IN_CO2], c, A.t_x);
-        const NF SAI = eval_input_inline(A.in[TRM_IN_SAI], c, A.t_x);
-        const NF Rdl = eval_input_inline(A.in[TRM_IN_DAILY_LEAF_RESPIRATION], c, A.t_x);
-        const NF Cv = A.vx[0][c], nu = A.vx[1][c], wcan = A.vx[2][c];
-        const NF An_prev = A.veg2d[VF_AN][c];
-        // PALADYNCarbonDynamics / PALADYNPhenology auxiliaries (carbon_dynamics.jl:82-85, phenology.jl:33-70)
-        const NF LAIb = Cv / ((NF(2.0) / v.SLA) + v.awl);
-        const NF fdec = NF(0), phen = NF(1.0);
-        const NF LAI = (fdec * phen + (NF(1.0) - fdec)) * LAIb;
-        // MedlynStomatalConductance (stomatal_conductance.jl:45-82): vapour pressure deficit at the air temperature,
-        // net assimilation of the PREVIOUS evaluation (vegetation_carbon.jl:89-91)
-        const NF vpd_air = jmax(saturation_vapor_pressure(a.Ta) - ea, NF(0.1));
-        const NF g0 = (v.g_min / 1000) * (1 - texp(-v.k_ext * LAI)) * beta_sm;
-        const NF gw = g0 + NF(1.6) * (1 + v.g1 / tsqrt(vpd_air)) * An_prev / co2 * NF(1.0e6);
-        const NF lamc = NF(1.0) - NF(1.0) / (NF(1.0) + v.g1 / tsqrt(vpd_air * NF(1.0e-3)));
-        // LUEPhotosynthesis (photosynthesis.jl:284-344)
-        NF Rd, An;
-        photosynthesis(v, a.Ta, a.SWd, a.pres, co2, LAI, lamc, beta_sm, Rd, An);
-        const NF GPP = An * NF(1.0e-3);
-        // PALADYNAutotrophicRespiration (autotrophic_respiration.jl:46-154) ; T_soil = ground temperature
-        const NF f_soil = (T_top > 7) ? texp(NF(308.56) * (NF(1.0) / NF(56.02) - NF(1.0) / (NF(46.02) + T_top))) : NF(0);
-        const NF f_air = texp(NF(308.56) * (NF(1.0) / NF(56.02) - NF(1.0) / (NF(46.02) + a.Ta)));
-        const NF resp10 = NF(0.066);
-        const NF R_leaf = Rdl / NF(1000.0);
-        const NF R_stem = resp10 * f_air * (v.awl * ((NF(2.0) / v.SLA) + v.awl)) / (Cv * v.aws * v.cn_sapwood);
-        const NF R_root = resp10 * f_soil * phen * (NF(2.0) / v.SLA) / (v.SLA * Cv * v.cn_root);
-        const NF Rm = R_leaf + R_stem + R_root;
-        const NF Rg = NF(0.25) * (GPP - Rm);
-        const NF Ra = Rm + Rg;
-        const NF NPP = GPP - Ra;
-        // PALADYNCanopyInterception (canopy_interception.jl:79-187)
-        const NF wmax = v.w_can_max * (LAI + SAI);
-        const NF f_can = wmax > 0 ? wcan / wmax : NF(0);
-        const NF I_can = v.alpha_int * a.rain * (NF(1) - texp(-v.k_ext_can * (LAI + SAI)));
-        const NF R_can = jmax(wcan, NF(0)) / v.tau_w;
-        rain_ground = a.rain - I_can + R_can;
-        // PALADYNCanopyEvapotranspiration (canopy_evapotranspiration.jl:51-177): humidity gradients at the skin and at
-        // the ground temperature, resistance between ground and canopy, stomatal resistance
-        const NF esg = saturation_vapor_pressure(T_top);
-        const NF dqg = p.eps_mw * jmax(esg - ea, NF(0.1)) / a.pres;
-        const NF re = (1 - texp(-LAI - SAI)) / (v.C_can * Vc);
-        const NF rs = 1 / jmax(gw, tsqrt(Lim<NF>::eps()));
-        const NF transp = (NF)((double)dq / (a.ra + (double)rs));
-        Egnd = (NF)((double)(p.beta * dqg) / (a.ra + (double)re));
-        const NF E_can = (NF)((double)(f_can * dq) / a.ra);
-        Qh = Egnd + E_can + transp;
-        // tendencies: canopy water (canopy_interception.jl:121-127), vegetation carbon (carbon_dynamics.jl:107-112),
-        // vegetation area fraction (vegetation_dynamics.jl:60-75)
-        const NF lam = lambda_NPP(v, LAIb);
-        NF k[3];
-        k[2] = I_can - E_can - R_can;
-        k[0] = (NF(1.0) - lam) * NPP - (v.gamma_L / v.SLA + v.gamma_R / v.SLA + v.gamma_S * v.awl) * LAIb;
-        const NF nus = jmax(nu, v.nu_seed);
-        k[1] = (lam * NPP / Cv) * nus * (NF(1.0) - nu) - v.gamma_v * nus;
-        if (A.mode == MODE_EULER || A.mode == MODE_HEUN1 || A.mode == MODE_HEUN2) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                NF ki = k[i];
-                if (A.mode == MODE_HEUN1) A.vok1[i][c] = ki;
-                if (A.mode == MODE_HEUN2) ki = (A.vk1[i][c] + ki) / 2;   // average_tendencies!, heun.jl:27-35
-                A.vy[i][c] = A.vb[i][c] + ki * A.dt;
-            }
-        }
+        vegetation_surface<NF, FAST>(A, c, a.Ta, a.SWd, a.pres, ea, a.rain, Vc, a.ra, dq, T_top, beta_sm, stage2);
         if (stage2) { G_out = A.G[c]; inf_out = A.infil[c]; return; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
-        NF* const* o = A.veg2d;
-        o[VF_LAIB][c] = LAIb; o[VF_LAI][c] = LAI; o[VF_PHEN][c] = phen; o[VF_GWCAN][c] = gw; o[VF_LAMC][c] = lamc;
-        o[VF_AN][c] = An; o[VF_RD][c] = Rd; o[VF_GPP][c] = GPP; o[VF_RA][c] = Ra; o[VF_NPP][c] = NPP; o[VF_BETASM][c] = beta_sm;
-        o[VF_ICAN][c] = I_can; o[VF_RCAN][c] = R_can; o[VF_FCAN][c] = f_can; o[VF_RAING][c] = rain_ground;
-        o[VF_ECAN][c] = E_can; o[VF_TRANSP][c] = transp;
+        Egnd = A.Egnd[c];
+        rain_ground = A.veg2d[VF_RAING][c];
+        Qh = Egnd + A.veg2d[VF_ECAN][c] + A.veg2d[VF_TRANSP][c];   // surface_humidity_flux, canopy_evapotranspiration.jl:75-80
     }
     // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 ; K_top = Kf[Nz]
     NF drain, inf;
-    if (S > 0) { drain = jmax(S, NF(0)) / p.tau_r; inf = (sat_top < 1) ? jmin(drain, K_top) : NF(0); }
+    if (S > 0) { drain = dv<NF, FAST>(jmax(S, NF(0)), p.tau_r); inf = (sat_top < 1) ? jmin(drain, K_top) : NF(0); }
     else { drain = 0; inf = (sat_top < 1) ? jmin(rain_ground, K_top) : NF(0); }
     NF runoff = rain_ground + drain - inf;
     // surface energy balance kernel, executed twice (land_model.jl:85-86) ; the latent heat flux follows the humidity
@@ -312,16 +351,61 @@ __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, boo
     NF swu, lwu, rnet, hs, hl, G;
 #pragma unroll 1
     for (int rep = 0; rep < 2; ++rep) {
-        seb_fluxes(p, a, prescribed ? a.Tskin_in : Ts, Qh, swu, lwu, rnet, hs, hl, G);
+        seb_fluxes<NF, FAST>(p, a, prescribed ? a.Tskin_in : Ts, Qh, swu, lwu, rnet, hs, hl, G);
         if (!prescribed) {
-            Ts = T_top - G * dz_top / (2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
-            seb_fluxes(p, a, Ts, Qh, swu, lwu, rnet, hs, hl, G);
+            Ts = T_top - dv<NF, FAST>(G * dz_top, 2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
+            seb_fluxes<NF, FAST>(p, a, Ts, Qh, swu, lwu, rnet, hs, hl, G);
         }
     }
     A.Egnd[c] = Egnd; A.infil[c] = inf; A.runoff[c] = runoff;
     A.SWup[c] = swu; A.LWup[c] = lwu; A.Rnet[c] = rnet; A.Hs[c] = hs; A.Hl[c] = hl; A.G[c] = G;
     if (!prescribed) A.Ts[c] = Ts;
     G_out = G; inf_out = inf;
+}
+
+// ---- surface block as its own launch (staged ForwardEuler / Heun kernels, euler_kernel.cuh) ----------------------
+// The surface processes of one update_state! only need the top soil layer of the state they are evaluated on, the
+// per-column 2-D fields and (vegetated model) the soil moisture limiting factor, which the stage kernel that produced
+// that state has left in `xbeta`. Running them as a separate one-thread-per-column launch keeps the layer loop of
+// the stage kernel free of the call (and of its register demand); the stage kernel then reads G and the infiltration
+// like any other Flux boundary condition.
+#ifndef TRM_SURFACE_BLOCKS
+#define TRM_SURFACE_BLOCKS 8   // resident blocks of 128 threads the register allocator must allow (64 registers: measured 4 blocks
+                               // 2.19 ms, 8 blocks 1.60 ms per 10 M vegetated columns -- the block is a long FP64 dependency chain)
+#endif
+template <class NF, bool FAST>
+__global__ void __launch_bounds__(128, TRM_SURFACE_BLOCKS) surface_kernel(const __grid_constant__ StageArgs<NF> A) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.ncol) return;
+    const DevParams<NF>& p = A.p;
+    const int nz = A.nz;
+    const int64_t o = (int64_t)(nz - 1) * A.ld + c;
+    const NF sat_top = A.xS[o];
+    NF T_top, liq_top;
+    if (A.load_aux) { T_top = A.xT[o]; liq_top = A.xL[o]; }
+    else energy_to_temperature<NF, FAST>(p, A.xU[o], sat_top, T_top, liq_top);
+    const NF K_top = cell_conductivity<NF, FAST>(p, sat_top, liq_top);   // Kf[Nz] = Kc[Nz], soil_hydrology.jl:249-276
+    const NF dz_top = A.metrics[MET_DZC * MET_STRIDE + nz];
+    NF G, inf;
+    land_surface<NF, FAST>(A, c, A.richards != 0, T_top, sat_top, K_top, dz_top, has_veg(A) ? A.xbeta[c] : NF(0), A.mode == MODE_HEUN2, G, inf);
+}
+
+// soil moisture limiting factor from the stored saturation / liquid fraction (first step after initialize or after the
+// user overwrote a field; afterwards the stage kernels keep it current)
+template <class NF, bool FAST>
+__global__ void __launch_bounds__(128) beta_kernel(const __grid_constant__ StageArgs<NF> A) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.ncol) return;
+    const NF* root = A.metrics + MET_ROOT * MET_STRIDE;
+    const NF* dzc = A.metrics + MET_DZC * MET_STRIDE;
+    NF b = 0;
+    int64_t o = c;
+#pragma unroll 1
+    for (int k = 1; k <= A.nz; ++k, o += A.ld) {
+        const NF s = A.xS[o], l = A.xL[o];
+        b += FAST ? plant_available_water_fast(A.vp, A.p, s, l) * root[k] : plant_available_water(A.vp, A.p, s, l) * root[k] / dzc[k] * dzc[k];
+    }
+    A.ybeta[c] = b;
 }
 
 // Values produced while layer m enters the pipeline and consumed one or two iterations later.  Two
@@ -426,9 +510,9 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
             }
             kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
             if (need_K) Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
-            if (LAND && A.veg) {   // Integral(PAW * root_fraction / dz, dims = 3), accumulated bottom -> top
-                const NF paw = plant_available_water(A.vp, p, sr, ln);
-                beta_sm += paw * met.root(m) / met.dzc(m) * met.dzc(m);
+            if (LAND && has_veg(A)) {   // Integral(PAW * root_fraction / dz, dims = 3), accumulated bottom -> top
+                const NF paw = FAST ? plant_available_water_fast(A.vp, p, sr, ln) : plant_available_water(A.vp, p, sr, ln);
+                beta_sm += FAST ? paw * met.root(m) : paw * met.root(m) / met.dzc(m) * met.dzc(m);
                 if (mode == MODE_AUX) A.paw[(int64_t)(m - 1) * ld + c] = paw;
             }
         } else if (m == nz + 1) {   // halo above the surface, built from layer nz (prv)
@@ -473,8 +557,8 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
 
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         if (LAND && m == nz + 2) {
-            if (mode == MODE_HEUN2 && !A.veg) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
-            else land_surface(A, c, RICH, T2, s2, Kf2, met.dzc(nz), beta_sm, mode == MODE_HEUN2, G_top, infil_top);
+            if (mode == MODE_HEUN2 && !has_veg(A)) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
+            else land_surface<NF, FAST>(A, c, RICH, T2, s2, Kf2, met.dzc(nz), beta_sm, mode == MODE_HEUN2, G_top, infil_top);
         }
 
         if (m >= 3 && m <= nz + 2 && mode != MODE_AUX) {

@@ -88,6 +88,8 @@ struct Handle : HandleBase {
     NF* veg2d[VF_COUNT] = {nullptr};
     NF *gveg[3] = {nullptr}, *tveg[3] = {nullptr};
     NF* paw = nullptr;
+    NF *beta = nullptr, *gbeta = nullptr;   // soil moisture limiting factor of the model state / of the Heun stage state
+    bool beta_stale = true;                  // `beta` does not belong to the stored state: recompute it before the next surface launch
     VegParams<NF> vp{};
     std::vector<NF> rootf;
     struct Input { int kind = TRM_SRC_CONST; double cval = 0, period = 1, lo = -INFINITY, hi = INFINITY; int nt = 0;
@@ -211,6 +213,11 @@ struct Handle : HandleBase {
         vp.theta_r = (NF)q.theta_r; vp.g1 = (NF)q.g1; vp.g_min = (NF)q.g_min; vp.cn_sapwood = (NF)q.cn_sapwood; vp.cn_root = (NF)q.cn_root; vp.aws = (NF)q.aws;
         vp.SLA = (NF)q.SLA; vp.awl = (NF)q.awl; vp.LAI_min = (NF)q.LAI_min; vp.LAI_max = (NF)q.LAI_max;
         vp.gamma_L = (NF)q.gamma_L; vp.gamma_R = (NF)q.gamma_R; vp.gamma_S = (NF)q.gamma_S; vp.nu_seed = (NF)q.nu_seed; vp.gamma_v = (NF)q.gamma_v_min;
+        vp.r_paw_span = 1 / (vp.th_fc - vp.th_wp);
+        vp.ln_q10_tau = std::log(vp.q10_tau); vp.ln_q10_Kc = std::log(vp.q10_Kc); vp.ln_q10_Ko = std::log(vp.q10_Ko);
+        vp.ts_k1 = NF(2.0) * std::log(NF(1.0) / NF(0.99) - NF(1.0)) / (vp.T_CO2_low - vp.T_photos_low);
+        vp.ts_k2 = NF(0.5) * (vp.T_CO2_low + vp.T_photos_low);
+        vp.ts_k3 = std::log(NF(0.99) / NF(0.01)) / (vp.T_CO2_high - vp.T_photos_high);
         vp.alpha_int = (NF)q.alpha_int; vp.k_ext_can = (NF)q.k_ext_can; vp.w_can_max = (NF)q.w_can_max; vp.tau_w = (NF)q.tau_w; vp.C_can = (NF)q.C_can;
 
         // ---- fields
@@ -229,6 +236,8 @@ struct Handle : HandleBase {
             for (int i = 0; i < VF_COUNT; ++i) if (int rc = dalloc(&veg2d[i], ld)) return rc;
             if (heun) for (int i = 0; i < 3; ++i) { if (int rc = dalloc(&gveg[i], ld)) return rc; if (int rc = dalloc(&tveg[i], ld)) return rc; }
             if (int rc = dalloc(&paw, n3)) return rc;
+            if (int rc = dalloc(&beta, ld)) return rc;
+            if (heun) { if (int rc = dalloc(&gbeta, ld)) return rc; }
         }
         // input defaults, prescribed_atmosphere.jl:89-99,147-149,192-195,220-224,10-14
         in[TRM_IN_AIR_TEMPERATURE].cval = 10; in[TRM_IN_AIR_PRESSURE].cval = 101325; in[TRM_IN_WINDSPEED].cval = 0.1;
@@ -271,7 +280,7 @@ struct Handle : HandleBase {
         CU(cudaSetDevice(device));
         CU(cudaMemcpy2DAsync(f.ptr, ld * sizeof(NF), host, nc * sizeof(NF), nc * sizeof(NF), f.nrows, cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
-        aux_stale = true;
+        aux_stale = true; beta_stale = true;
         return TRM_OK;
     }
     int get_field(int id, void* host, int64_t count) override {
@@ -296,7 +305,7 @@ struct Handle : HandleBase {
         if (ld_out) *ld_out = ld;
         if (nrows) *nrows = f.nrows;
         // the caller may write through the pointer: treat the closure fields as user data from now on
-        if (f.writable) aux_stale = true;
+        if (f.writable) { aux_stale = true; beta_stale = true; }
         return TRM_OK;
     }
 
@@ -355,7 +364,7 @@ struct Handle : HandleBase {
     // ------------------------------------------------------------------ launches
     void base_args(StageArgs<NF>& a) {
         std::memset(&a, 0, sizeof(a));
-        a.ncol = nc; a.ld = ld; a.nz = nz;
+        a.ncol = nc; a.ld = ld; a.nz = nz; a.richards = richards ? 1 : 0;
         a.metrics = metrics; a.p = p;
         for (int s = 0; s < TRM_BC_NSLOTS; ++s) a.bc[s] = cfg.bc[s];
         for (int i = 0; i < TRM_IN_COUNT; ++i) {
@@ -366,7 +375,7 @@ struct Handle : HandleBase {
         a.Kf = Kf;
         a.Ts = land2d[0]; a.G = land2d[1]; a.SWup = land2d[2]; a.LWup = land2d[3]; a.Rnet = land2d[4];
         a.Hs = land2d[5]; a.Hl = land2d[6]; a.Egnd = land2d[7]; a.infil = land2d[8]; a.runoff = land2d[9];
-        a.veg = veg ? 1 : 0; a.vp = vp; a.paw = paw;
+        a.veg = veg ? 1 : 0; a.vp = vp; a.paw = paw; a.xbeta = beta; a.ybeta = beta;
         for (int i = 0; i < VF_COUNT; ++i) a.veg2d[i] = veg2d[i];
         // ForwardEuler / auxiliary evaluations: evaluate on, and update, the model state in place
         for (int i = 0; i < 3; ++i) { a.vx[i] = veg2d[i]; a.vb[i] = veg2d[i]; a.vy[i] = veg2d[i]; a.vk1[i] = nullptr; a.vok1[i] = nullptr; }
@@ -395,6 +404,10 @@ struct Handle : HandleBase {
         return TRM_OK;
     }
     int launch_euler(const StageArgs<NF>& a, int load_aux);
+    int launch_surface(int what, const StageArgs<NF>& a);
+    // the staged kernels (euler_kernel.cuh) leave the LandModel surface block to surface_kernel; the generic streaming
+    // kernel evaluates it inline
+    bool split_surface() const { return land && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     int enqueue_steps(double dt, int64_t n);
     int set_input_field_async(int id, const void* v) override;
     int get_field_async(int id, void* host, int64_t count) override;
@@ -414,6 +427,17 @@ template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
 template <> int Handle<double>::launch(int variant, const StageArgs<double>& a) {
     cudaError_t e = ks->stage_f64(phys, variant, a, block, stream); ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("stage kernel launch: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+
+template <> int Handle<float>::launch_surface(int what, const StageArgs<float>& a) {
+    cudaError_t e = ks->surface_f32(what, a, stream); ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("surface kernel launch: ") + cudaGetErrorString(e));
+    return TRM_OK;
+}
+template <> int Handle<double>::launch_surface(int what, const StageArgs<double>& a) {
+    cudaError_t e = ks->surface_f64(what, a, stream); ++launches;
+    if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("surface kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
 }
 
@@ -457,7 +481,7 @@ template <class NF> int Handle<NF>::initialize() {
     // the liquid fraction exists (the field is still zero there); it is recomputed by the first
     // update_state!, so the hydraulic conductivity field is materialised by trm_compute_auxiliary only.
     CU(cudaStreamSynchronize(stream));
-    initialized = true; aux_stale = true;
+    initialized = true; aux_stale = true; beta_stale = true;
     return TRM_OK;
 }
 
@@ -472,22 +496,36 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
         const NF t = (NF)time;
         const NF t1 = t + dt;   // tick!(clock, dt) in the clock's number format
         a.dt = dt;
+        const bool split = split_surface();
+        if (split && veg && beta_stale) {   // soil moisture limiting factor of the stored state (first step / after a user write)
+            StageArgs<NF> g; base_args(g); x_state(g);
+            if (int rc = launch_surface(1, g)) return rc;
+        }
         if (!heun) {   // forward_euler.jl:19-31
             a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
             const bool load = aux_stale || force_load;
+            a.load_aux = load ? 1 : 0;
+            if (split) { if (int rc = launch_surface(0, a)) return rc; }
             if (int rc = launch_euler(a, load ? 1 : 0)) return rc;
         } else {       // heun.jl:37-71
             a.mode = MODE_HEUN1; a.load_aux = aux_stale ? 1 : 0; a.t_x = t; a.t_b = t; x_state(a);
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
             for (int i = 0; i < 3; ++i) { a.vy[i] = gveg[i]; a.vok1[i] = tveg[i]; }
+            a.ybeta = gbeta;
+            if (split) { if (int rc = launch_surface(0, a)) return rc; }
             if (int rc = launch_euler(a, a.load_aux)) return rc;
             StageArgs<NF> b; base_args(b);
             b.dt = dt; b.mode = MODE_HEUN2; b.load_aux = 0; b.t_x = t1; b.t_b = t;
             b.xU = gU; b.xS = richards ? gS : S; b.xWt = gWt; b.bU = U; b.bS = S; b.bSx = Sx; b.k1U = tU; b.k1S = tS;
             for (int i = 0; i < 3; ++i) { b.vx[i] = gveg[i]; b.vk1[i] = tveg[i]; }
+            b.xbeta = gbeta;
             y_state(b);
+            // stage 2 only re-evaluates the vegetation block (k2 of canopy water, vegetation carbon and area fraction);
+            // the bare-ground surface block of the stage state has no effect on the step (heun.jl:63-66)
+            if (split && veg) { if (int rc = launch_surface(0, b)) return rc; }
             if (int rc = launch_euler(b, 0)) return rc;
         }
+        beta_stale = !split;   // the staged kernels leave the factor of the new state behind; the generic kernel does not
         aux_stale = false;
         t_inputs = (double)t;   // the state's inputs were last updated at the start of this step
         time = (double)t1; iteration += 1;
@@ -564,7 +602,7 @@ template <class NF> int Handle<NF>::set_field_ring(int id, const void* host, int
     ++launches;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(stream));
-    aux_stale = true;
+    aux_stale = true; beta_stale = true;
     return TRM_OK;
 }
 
