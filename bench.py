@@ -40,10 +40,21 @@ DT = 60.0
 SEED = 20260101
 
 
-def algorithmic_bytes_per_cell(itemsize: int, nz: int) -> float:
+def algorithmic_bytes_per_cell(itemsize: int, nz: int, model: str = "soil", heun: bool = False) -> float:
     """read U, sat; write U, sat, T, liq, psi (7 values per cell) + per column: surface_excess_water
-    R/W, water_table R/W, sinusoid forcing parameters (mean, amp, phase) R = 7 values per column."""
-    return 7.0 * itemsize + 7.0 * itemsize / nz
+    R/W, water_table R/W, sinusoid forcing parameters (mean, amp, phase) R = 7 values per column.
+
+    Secondary workloads: Heun = stage 1 (read U, sat; write stage U, sat and k1 of both) + stage 2 (read
+    stage U, sat, both k1, base U, sat; write U, sat, T, liq, psi) = 17 values per cell. Per column, the bare-ground
+    LandModel moves 22 values (skin temperature and surface excess water, 8 forcing parameters / table rows in; 10 surface
+    fields out; G and infiltration read back by the stage kernel), the vegetated one 49 (adds 3 prognostic variables R/W,
+    the previous net assimilation, the soil moisture factor R/W, SAI, 17 auxiliaries out); a Heun step re-reads G and the
+    infiltration in stage 2 (+2) and, vegetated, evaluates the vegetation block again on the stage state (+27)."""
+    per_cell = 17.0 if heun else 7.0
+    per_col = {"soil": 7.0, "land": 22.0, "land-veg": 49.0}[model]
+    if heun:
+        per_col += {"soil": 4.0, "land": 2.0, "land-veg": 27.0}[model]
+    return per_cell * itemsize + per_col * itemsize / nz
 
 
 def peaks():
@@ -281,19 +292,20 @@ def main():
     e2e = None
     if not args.no_e2e:
         tdtype = torch.float64 if nf == np.float64 else torch.float32
-        k2 = max(3, min(args.steps, 20))
+        k2 = max(3, args.steps)   # same step count as the kernel-only measurement
+        NBUF = 4                  # pinned host buffers are reused round robin (a fresh upload / download every step)
         in_id = integ._bc_inputs["T_ub"]
         gt_id = trm.abi.FIELD_IDS["ground_temperature"]
         t = integ.clock.time
-        forc = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(k2 + 3)]
-        outs = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(k2 + 3)]
+        forc = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(NBUF)]
+        outs = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(NBUF)]
         for i, f in enumerate(forc):   # the host-side "atmosphere": this step's surface temperature per column
             f.copy_(torch.from_numpy((T0 + 10.0 * np.sin(2 * np.pi * (t + i * DT) / 86400.0 - lon)).astype(nf)))
 
         def e2e_step(i):
-            lib.check(lib.set_input_field_async(h, in_id, C.c_void_p(forc[i].data_ptr())), "set_input_field_async")
+            lib.check(lib.set_input_field_async(h, in_id, C.c_void_p(forc[i % NBUF].data_ptr())), "set_input_field_async")
             lib.check(lib.step_async(h, DT, 1), "step_async")
-            lib.check(lib.get_field_async(h, gt_id, C.c_void_p(outs[i].data_ptr()), ncol_local), "get_field_async")
+            lib.check(lib.get_field_async(h, gt_id, C.c_void_p(outs[i % NBUF].data_ptr()), ncol_local), "get_field_async")
 
         for i in range(3):
             e2e_step(i)
@@ -313,7 +325,7 @@ def main():
         assert all(bool(torch.isfinite(o).all()) for o in outs[3:3 + k2])
 
     peak, peak_src = peaks()
-    bpc = algorithmic_bytes_per_cell(itemsize, NZ)
+    bpc = algorithmic_bytes_per_cell(itemsize, NZ, args.model, args.timestepper == "heun")
     per_launch_ms = dev_ms / args.steps
     # ncu dram bytes of one launch over 10 M columns (profiles/traffic.json), scaled to this rank's column count
     traffic = profiled_traffic(args.dtype)
@@ -323,7 +335,10 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_column_layer_step": bpc,
-                "kernel": ("trm::stage_kernel" if os.environ.get("TRM_KERNEL") == "stream" else "trm::euler_kernel") + f"<{args.dtype}, RICHARDS, recompute, {args.math}>",
+                "kernel": ("trm::stage_kernel" if os.environ.get("TRM_KERNEL") == "stream" else "trm::euler_kernel")
+                          + f"<{args.dtype}, {'RICHARDS' if args.model == 'soil' else 'LAND'}, recompute, {args.math}>"
+                          + (" (two stage launches per step)" if args.timestepper == "heun" else "")
+                          + (" + trm::surface_kernel" if args.model != "soil" else ""),
                 "launch_ms": per_launch_ms}
 
     cpu_baseline = None
