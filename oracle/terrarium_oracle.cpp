@@ -9,7 +9,9 @@
 // there is no Manifest.toml) exist in this environment, so the reference cannot be executed.
 // This file restates the algorithm from the reference sources (file:line cited per function,
 // paths relative to /root/reference) and is pinned against every known-answer test the reference
-// holds for the path (tests/test_oracle_golden.py).  Semantics that live
+// holds for the path (tests/test_golden.py; vegetation / canopy: test/vegetation/*.jl,
+// test/surface_hydrology/canopy_*_tests.jl, tests/test_vegetation.py, which also holds an independent numpy
+// restatement of the per-column vegetation formulas).  Semantics that live
 // in the absent dependencies are restated from their published behaviour and are marked [OCN]
 // (Oceananigans) or [FC] (FreezeCurves); each is listed in DESIGN.md as "unpinned at rounding
 // level".
