@@ -243,6 +243,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    # one process per GPU, on the cores of the GPU's NUMA node (pinned forcing / result buffers live next to its PCIe root)
+    numa_cpus = td.bind_to_gpu_numa(local_rank) if world > 1 else []
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -321,7 +323,8 @@ def main():
                "d2h_bytes_per_step": args.columns * itemsize, "steps": k2, "ms_per_step": 1e3 * el / k2,
                "what": "per step: trm_set_input_field_async(surface temperature forcing, pinned host) + trm_step_async + "
                        "trm_get_field_async(ground_temperature -> pinned host); copies overlap the stage kernel on copy "
-                       "streams; wall clock around the loop incl. final trm_sync, max over ranks"}
+                       "streams; wall clock around the loop incl. final trm_sync, max over ranks",
+               "host_cpus_of_rank0": len(numa_cpus) if numa_cpus else None}
         assert all(bool(torch.isfinite(o).all()) for o in outs[3:3 + k2])
 
     peak, peak_src = peaks()

@@ -295,6 +295,9 @@ int         trm_sync(trm_handle* h);
  * devptr: device pointer to element [0][0]; ld: leading dimension in elements;
  * nrows: nz, nz+1 or 1. The Julia wrapper unsafe_wrap()s these as CuArrays (interior(field)). */
 int trm_field_ptr(trm_handle* h, int field_id, void** devptr, int64_t* ld, int32_t* nrows);
+/* Same borrow for READING only (output gathers over NCCL, plotting): the library keeps treating its stored closure
+ * fields as current, so the next step does not pay for re-reading them. Valid after trm_sync / a synchronous call. */
+int trm_field_view(trm_handle* h, int field_id, const void** devptr, int64_t* ld, int32_t* nrows);
 /* Host <-> device copies of whole fields. Host layout is dense [nrows][ncol] in the handle's
  * dtype (replaces set!(field, ...) / interior(field), src/initializers.jl:23-27). Writing
  * TEMPERATURE / SATURATION before trm_initialize sets the initial condition. */

@@ -123,6 +123,7 @@ SIGNATURES = {
     "abi_version": (C.c_int, []),
     "sync": (C.c_int, [_H]),
     "field_ptr": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "field_view": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "set_field": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "get_field": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "set_input_const": (C.c_int, [_H, C.c_int, C.c_double]),
@@ -149,7 +150,7 @@ SIGNATURES = {
     "set_field_ring": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
 }
 # entry points that only make sense on a device and that the CPU oracle does not export
-DEVICE_ONLY = ("field_ptr", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size",
+DEVICE_ONLY = ("field_ptr", "field_view", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size",
                "set_input_field_async", "step_async", "get_field_async", "set_ring_index", "get_field_ring",
                "set_field_ring")
 

@@ -35,6 +35,7 @@ struct HandleBase {
     virtual int set_field(int id, const void* host, int64_t count) = 0;
     virtual int get_field(int id, void* host, int64_t count) = 0;
     virtual int field_ptr(int id, void** p, int64_t* ld, int32_t* nrows) = 0;
+    virtual int field_view(int id, const void** p, int64_t* ld, int32_t* nrows) = 0;
     virtual int set_input_const(int id, double v) = 0;
     virtual int set_input_field(int id, const void* v) = 0;
     virtual int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) = 0;
@@ -298,14 +299,21 @@ struct Handle : HandleBase {
         CU(cudaStreamSynchronize(stream));
         return TRM_OK;
     }
-    int field_ptr(int id, void** q, int64_t* ld_out, int32_t* nrows) override {
+    int field_ptr(int id, void** q, int64_t* ld_out, int32_t* nrows) override { return field_borrow(id, q, ld_out, nrows, true); }
+    int field_view(int id, const void** q, int64_t* ld_out, int32_t* nrows) override {
+        void* w = nullptr;
+        int rc = field_borrow(id, &w, ld_out, nrows, false);
+        if (q) *q = w;
+        return rc;
+    }
+    int field_borrow(int id, void** q, int64_t* ld_out, int32_t* nrows, bool may_write) {
         FieldRef f = field(id);
         if (!f.ptr) return fail(TRM_ERR_INVALID, "field_ptr: unknown field or field not defined for this model");
         if (q) *q = f.ptr;
         if (ld_out) *ld_out = ld;
         if (nrows) *nrows = f.nrows;
         // the caller may write through the pointer: treat the closure fields as user data from now on
-        if (f.writable) { aux_stale = true; beta_stale = true; }
+        if (may_write && f.writable) { aux_stale = true; beta_stale = true; }
         return TRM_OK;
     }
 
@@ -768,6 +776,7 @@ int trm_sync(trm_handle* h) {
     return H(h)->sync_all();
 }
 int trm_field_ptr(trm_handle* h, int id, void** p, int64_t* ld, int32_t* nrows) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->field_ptr(id, p, ld, nrows); }
+int trm_field_view(trm_handle* h, int id, const void** p, int64_t* ld, int32_t* nrows) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->field_view(id, p, ld, nrows); }
 int trm_set_field(trm_handle* h, int id, const void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->set_field(id, host, count); }
 int trm_get_field(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field(id, host, count); }
 int trm_set_input_const(trm_handle* h, int id, double v) { if (!h || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_const(id, v); }

@@ -53,3 +53,77 @@ def test_two_ranks_match_one(tmp_path):
     assert got["water"] == pytest.approx(d["water"], rel=1e-13) and got["energy"] == pytest.approx(d["energy"], rel=1e-13)
     assert got["t_min"] == d["t_min"] and got["t_max"] == d["t_max"]
     assert got["slowest"] == 2.0
+
+
+# ---------------------------------------------------------------------------------------------
+# device side: zero-copy views of the library's buffers and the NCCL output gather
+def _cuda_case(partition, ncol=NCOL):
+    from common import make, richards_soil, synthetic_columns, trm
+    lat, lon, T0 = synthetic_columns(ncol)
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=12), ncol)
+    model = trm.SoilModel(grid, soil=richards_soil())
+    bcs = trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0))
+    inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z,
+             "saturation_water_ice": lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x}
+    return make("cuda", model, trm.ForwardEuler(dt=60.0), boundary_conditions=bcs, initializers=inits, partition=partition)
+
+
+@pytest.mark.gpu
+def test_field_tensor_is_a_zero_copy_view():
+    import torch
+    from terrarium_jl_b200 import distributed as td
+    integ = _cuda_case(None)
+    integ.step(60.0, 5)
+    for name in ("temperature", "saturation_water_ice", "hydraulic_conductivity", "water_table"):
+        t = td.field_tensor(integ, name)
+        want = getattr(integ.state, name).numpy()
+        assert t.is_cuda and tuple(t.shape) == (want.shape if want.ndim == 2 else (1,) + want.shape)
+        assert np.array_equal(t.cpu().numpy().reshape(want.shape), want)
+    # a read-only view does not invalidate the stored closure fields: the next step launches the recompute variant
+    # (one launch), and the result equals an undisturbed run
+    ref = _cuda_case(None)
+    ref.step(60.0, 10)
+    integ.step(60.0, 5)
+    assert np.array_equal(integ.state.temperature.numpy(), ref.state.temperature.numpy())
+    full = td.gather_field_device(integ, "temperature")   # world size 1: a copy of the local field
+    assert np.array_equal(full.cpu().numpy(), ref.state.temperature.numpy())
+
+
+def nccl_gather_worker():
+    """Run under torchrun on >= 2 GPUs (tests/test_distributed.py is the entry point): every rank gathers the
+    temperature over NCCL from the library's device buffers and compares it with a single-rank run of the whole domain."""
+    import torch
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from terrarium_jl_b200 import distributed as td
+    import terrarium_jl_b200 as trm_
+    ncol = 1003
+    from common import make, richards_soil, synthetic_columns
+    lat, lon, T0 = synthetic_columns(ncol)
+    grid = trm_.ColumnGrid(trm_.B200(local), np.float64, trm_.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=12), ncol)
+
+    def build(partition):
+        model = trm_.SoilModel(grid, soil=richards_soil())
+        bcs = trm_.PrescribedSurfaceTemperature("T_ub", trm_.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0))
+        inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z, "saturation_water_ice": lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x}
+        return make("cuda", model, trm_.ForwardEuler(dt=60.0), boundary_conditions=bcs, initializers=inits, partition=partition)
+
+    part, whole = build((rank, world)), build(None)
+    part.step(60.0, STEPS); whole.step(60.0, STEPS)
+    for name in ("temperature", "water_table"):
+        got = td.gather_field_device(part, name).cpu().numpy()
+        want = getattr(whole.state, name).numpy()
+        assert np.array_equal(got.reshape(want.shape), want), name
+    d = td.reduce_diagnostics(part.diagnostics())
+    assert d["ncol"] == ncol and d["nan_count"] == 0
+    dist.barrier()
+    if rank == 0:
+        print(f"nccl gather over {world} ranks: OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    nccl_gather_worker()
