@@ -124,8 +124,11 @@ enum trm_source {
     TRM_SRC_CONST = 0,     /* one scalar for all columns                                        */
     TRM_SRC_FIELD = 1,     /* per-column vector owned by the handle, set with trm_set_input_field */
     TRM_SRC_SINUSOID = 2,  /* clamp(mean[c] + amp[c]*sin(2*pi*t/period - phase[c]), lo, hi)      */
-    TRM_SRC_TABLE = 3      /* snapshots values[nt][ncol] at times[nt]; linear in time, flat outside
-                              (Oceananigans FieldTimeSeries[Time(t)]; ext/TerrariumRastersExt:104-120) */
+    TRM_SRC_TABLE = 3,     /* snapshots values[nt][ncol] at times[nt]; linear in time, flat outside
+                              (Oceananigans FieldTimeSeries[Time(t)]: v2*n + v1*(1-n))                  */
+    TRM_SRC_RASTER = 4     /* same data, update rule of RasterInputSource (ext/TerrariumRastersExt/
+                              TerrariumRastersExt.jl:96-121): x1 + eps*(x2-x1)/dt in Float64, the node value
+                              on a node, flat outside the time axis                                      */
 };
 
 /* Fields that can be read / written / borrowed. 3-D fields are [nz][ld]; the hydraulic
@@ -313,9 +316,16 @@ int trm_set_input_sinusoid(trm_handle* h, int input_id, const void* mean, const 
                            double lo, double hi /* clamp; use -INFINITY/INFINITY for none */);
 int trm_set_input_table(trm_handle* h, int input_id, int32_t nt, const double* times,
                         const void* values /* [nt][ncol] NF */);
+/* Time-varying raster already gathered to the owned columns (idxmap = findall(mask), TerrariumRastersExt.jl:44):
+ * same arguments as trm_set_input_table, evaluated with the RasterInputSource rule (TRM_SRC_RASTER). */
+int trm_set_input_raster(trm_handle* h, int input_id, int32_t nt, const double* times,
+                         const void* values /* [nt][ncol] NF */);
 /* Borrow the per-column device vector of a TRM_SRC_FIELD input so that a coupled model
  * (e.g. SpeedyWeather, examples/simulations/speedy_dry_land.jl) can write forcing in place. */
 int trm_input_ptr(trm_handle* h, int input_id, void** devptr);
+/* Values of an input variable as of the last update_inputs! (start of the last step / trm_initialize): what reading the
+ * input Field `state.<name>` returns in the reference (state_variables.jl:154-162). host: [ncol] NF. */
+int trm_get_input(trm_handle* h, int input_id, void* host, int64_t count);
 
 /* ---- model ------------------------------------------------------------------------------ */
 /* initialize!(state, model) after the user initializers ran: hydrology closure + hydraulics,

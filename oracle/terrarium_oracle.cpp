@@ -200,6 +200,21 @@ struct Oracle {
                 NF frac = (NF)((td - tt[n1]) / (tt[n2] - tt[n1]));
                 return v[(size_t)n2 * nc + c] * frac + v[(size_t)n1 * nc + c] * (1 - frac);
             }
+            case TRM_SRC_RASTER: {
+                // update_from_raster!, ext/TerrariumRastersExt/TerrariumRastersExt.jl:96-121: searchsorted on the time
+                // axis; between nodes x1 + eps * (x2 - x1) / dt (eps, dt Float64 seconds), the node value on a node,
+                // flat beyond either end
+                const std::vector<double>& tt = s.times; const std::vector<NF>& v = src_table[id];
+                double td = (double)t;
+                int right = (int)(std::lower_bound(tt.begin(), tt.end(), td) - tt.begin()) + 1;   // first(searchsorted), 1-based
+                int left = (int)(std::upper_bound(tt.begin(), tt.end(), td) - tt.begin());        // last(searchsorted), 1-based
+                if (left >= 1 && right <= s.nt) {
+                    NF x1 = v[(size_t)(left - 1) * nc + c], x2 = v[(size_t)(right - 1) * nc + c];
+                    double dtt = tt[right - 1] - tt[left - 1], e = td - tt[left - 1];
+                    return dtt > 0 ? (NF)((double)x1 + e * (double)(x2 - x1) / dtt) : x2;
+                }
+                return v[(size_t)(std::min(right, s.nt) - 1) * nc + c];
+            }
         }
         return NF(0);
     }
@@ -208,7 +223,15 @@ struct Oracle {
         for (int s = 0; s < TRM_BC_NSLOTS; ++s) if (cfg.bc[s].kind != TRM_BC_DEFAULT && cfg.bc[s].input == id) return true;
         return false;
     }
+    NF t_inputs = 0;   // clock time of the last update_inputs! on the model state
+    int get_input(int id, void* host, int64_t count) {
+        if (count != nc) return fail(TRM_ERR_INVALID, "get_input: count != ncol");
+        NF* h = (NF*)host;
+        for (int64_t c = 0; c < nc; ++c) h[c] = eval_input(id, c, t_inputs);
+        return TRM_OK;
+    }
     void update_inputs(State<NF>& s) {
+        if (&s == &st) t_inputs = s.time;
         for (int id = 0; id < TRM_IN_COUNT; ++id) {
             if (!input_used(id)) continue;
             auto& f = s.in[id]; if ((int64_t)f.size() != nc) f.assign(nc, NF(0));
@@ -920,6 +943,12 @@ int set_table(Oracle<NF>* o, int id, int nt, const double* times, const void* va
     return TRM_OK;
 }
 template <class NF>
+int set_raster(Oracle<NF>* o, int id, int nt, const double* times, const void* values) {
+    int rc = set_table(o, id, nt, times, values);
+    o->src[id].kind = TRM_SRC_RASTER;
+    return rc;
+}
+template <class NF>
 int set_infield(Oracle<NF>* o, int id, const void* v) {
     o->src[id].kind = TRM_SRC_FIELD; o->src_field[id].assign((const NF*)v, (const NF*)v + o->nc);
     return TRM_OK;
@@ -991,6 +1020,14 @@ int orc_set_input_sinusoid(trm_handle* h_, int id, const void* mean, const void*
 int orc_set_input_table(trm_handle* h_, int id, int32_t nt, const double* times, const void* values) {
     Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT || nt < 1) return fail(TRM_ERR_INVALID, "bad input id / nt");
     return h->dtype == TRM_F32 ? set_table(h->f32, id, nt, times, values) : set_table(h->f64, id, nt, times, values);
+}
+int orc_set_input_raster(trm_handle* h_, int id, int32_t nt, const double* times, const void* values) {
+    Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT || nt < 1) return fail(TRM_ERR_INVALID, "bad input id / nt");
+    return h->dtype == TRM_F32 ? set_raster(h->f32, id, nt, times, values) : set_raster(h->f64, id, nt, times, values);
+}
+int orc_get_input(trm_handle* h, int id, void* host, int64_t count) {
+    if (id < 0 || id >= TRM_IN_COUNT || !host) return fail(TRM_ERR_INVALID, "bad input id");
+    return DISPATCH((Handle*)h, get_input(id, host, count));
 }
 int orc_initialize(trm_handle* h) { return DISPATCH((Handle*)h, initialize()); }
 int orc_step(trm_handle* h, double dt, int64_t n) { return DISPATCH((Handle*)h, step(dt, n)); }

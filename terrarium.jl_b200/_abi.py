@@ -37,7 +37,7 @@ TRM_IN_USER0 = 0
  TRM_IN_SNOWFALL, TRM_IN_SHORTWAVE_DOWN, TRM_IN_LONGWAVE_DOWN, TRM_IN_DAYTIME_LENGTH, TRM_IN_CO2,
  TRM_IN_SKIN_TEMPERATURE, TRM_IN_SAI, TRM_IN_DAILY_LEAF_RESPIRATION) = range(8, 21)
 TRM_IN_COUNT = 21
-TRM_SRC_CONST, TRM_SRC_FIELD, TRM_SRC_SINUSOID, TRM_SRC_TABLE = 0, 1, 2, 3
+TRM_SRC_CONST, TRM_SRC_FIELD, TRM_SRC_SINUSOID, TRM_SRC_TABLE, TRM_SRC_RASTER = 0, 1, 2, 3, 4
 
 FIELD_IDS = {
     "internal_energy": 0, "temperature": 1, "liquid_water_fraction": 2, "saturation_water_ice": 3,
@@ -130,6 +130,8 @@ SIGNATURES = {
     "set_input_field": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "set_input_sinusoid": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "set_input_table": (C.c_int, [_H, C.c_int, C.c_int32, C.POINTER(C.c_double), C.c_void_p]),
+    "set_input_raster": (C.c_int, [_H, C.c_int, C.c_int32, C.POINTER(C.c_double), C.c_void_p]),
+    "get_input": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "input_ptr": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p)]),
     "initialize": (C.c_int, [_H]),
     "step": (C.c_int, [_H, C.c_double, C.c_int64]),

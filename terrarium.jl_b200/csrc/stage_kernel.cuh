@@ -160,6 +160,23 @@ __device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t 
             NF frac = (NF)((td - tt[n1]) / (tt[n2] - tt[n1]));
             return s.a[(int64_t)n2 * s.ld + c] * frac + s.a[(int64_t)n1 * s.ld + c] * (1 - frac);
         }
+        case TRM_SRC_RASTER: {
+            // update_from_raster! (ext/TerrariumRastersExt/TerrariumRastersExt.jl:96-121): x1 + eps (x2 - x1) / dt in
+            // Float64 between nodes, the node value on a node, flat beyond either end of the time axis
+            const double td = (double)t;
+            const double* tt = s.times;
+            const int nt = s.nt;
+            int lo = 0, hi = nt;   // lower_bound: first index with tt[i] >= td
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (tt[mid] < td) lo = mid + 1; else hi = mid; }
+            const int right = lo + 1;                                  // first(searchsorted), 1-based
+            const int left = (lo < nt && tt[lo] == td) ? lo + 1 : lo;   // last(searchsorted) (time axes are strictly increasing)
+            if (left >= 1 && right <= nt) {
+                const NF x1 = s.a[(int64_t)(left - 1) * s.ld + c], x2 = s.a[(int64_t)(right - 1) * s.ld + c];
+                const double dtt = tt[right - 1] - tt[left - 1], e = td - tt[left - 1];
+                return dtt > 0 ? (NF)((double)x1 + e * (double)(x2 - x1) / dtt) : x2;
+            }
+            return s.a[(int64_t)((right < nt ? right : nt) - 1) * s.ld + c];
+        }
     }
     return NF(0);
 }

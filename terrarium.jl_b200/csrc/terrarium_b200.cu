@@ -39,7 +39,8 @@ struct HandleBase {
     virtual int set_input_const(int id, double v) = 0;
     virtual int set_input_field(int id, const void* v) = 0;
     virtual int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) = 0;
-    virtual int set_input_table(int id, int nt, const double* times, const void* values) = 0;
+    virtual int get_input(int id, void* host, int64_t count) = 0;
+    virtual int set_input_table(int id, int nt, const double* times, const void* values, int kind = TRM_SRC_TABLE) = 0;
     virtual int input_ptr(int id, void** p) = 0;
     virtual int initialize() = 0;
     virtual int step(double dt, int64_t n) = 0;
@@ -331,7 +332,7 @@ struct Handle : HandleBase {
     int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) override {
         CU(cudaSetDevice(device));
         Input& s = in[id];
-        if (s.kind == TRM_SRC_TABLE && s.a) { dfree(s.a); s.a = nullptr; }
+        if ((s.kind == TRM_SRC_TABLE || s.kind == TRM_SRC_RASTER) && s.a) { dfree(s.a); s.a = nullptr; }
         if (int rc = ensure(&s.a, ld)) return rc;
         if (int rc = ensure(&s.b, ld)) return rc;
         if (int rc = ensure(&s.c, ld)) return rc;
@@ -342,7 +343,7 @@ struct Handle : HandleBase {
         s.kind = TRM_SRC_SINUSOID; s.period = period; s.lo = lo; s.hi = hi;
         return TRM_OK;
     }
-    int set_input_table(int id, int nt, const double* times, const void* values) override {
+    int set_input_table(int id, int nt, const double* times, const void* values, int kind = TRM_SRC_TABLE) override {
         CU(cudaSetDevice(device));
         Input& s = in[id];
         if (s.a) { dfree(s.a); s.a = nullptr; }
@@ -352,12 +353,13 @@ struct Handle : HandleBase {
         CU(cudaMemcpy2DAsync(s.a, ld * sizeof(NF), values, nc * sizeof(NF), nc * sizeof(NF), nt, cudaMemcpyHostToDevice, stream));
         CU(cudaMemcpyAsync(s.times, times, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
-        s.kind = TRM_SRC_TABLE; s.nt = nt;
+        s.kind = kind; s.nt = nt;
         return TRM_OK;
     }
+    int get_input(int id, void* host, int64_t count) override;
     int input_ptr(int id, void** q) override {
         CU(cudaSetDevice(device));
-        if (in[id].kind == TRM_SRC_TABLE) return fail(TRM_ERR_STATE, "input_ptr: input is a time series table");
+        if (in[id].kind == TRM_SRC_TABLE || in[id].kind == TRM_SRC_RASTER) return fail(TRM_ERR_STATE, "input_ptr: input is a time series table");
         if (int rc = ensure(&in[id].a, ld)) return rc;
         if (in[id].kind == TRM_SRC_CONST) {   // materialise the constant so that the borrowed vector is meaningful
             std::vector<NF> v((size_t)nc, (NF)in[id].cval);
@@ -619,7 +621,7 @@ template <class NF> int Handle<NF>::set_field_ring(int id, const void* host, int
 template <class NF> int Handle<NF>::set_input_field_async(int id, const void* v) {
     CU(cudaSetDevice(device));
     Input& s = in[id];
-    if (s.kind == TRM_SRC_TABLE) return fail(TRM_ERR_STATE, "set_input_field_async: input is a time series table");
+    if (s.kind == TRM_SRC_TABLE || s.kind == TRM_SRC_RASTER) return fail(TRM_ERR_STATE, "set_input_field_async: input is a time series table");
     if (!s_in) CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     if (int rc = ensure(&s.a, ld)) return rc;
     if (int rc = ensure(&s.a2, ld)) return rc;
@@ -672,6 +674,25 @@ template <class NF> int Handle<NF>::get_field_async(int id, void* host, int64_t 
 }
 
 // compute_auxiliary!(state, model): soil_coupled.jl:62-72 / land_model.jl:79-88
+// input values as of the last update_inputs! (evaluated on the device with the same code the stage kernels use)
+template <class NF>
+__global__ void eval_input_kernel(int64_t ncol, InputDesc<NF> d, NF t, NF* out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncol) out[c] = eval_input_inline(d, c, t);
+}
+template <class NF> int Handle<NF>::get_input(int id, void* host, int64_t count) {
+    if (count != nc) return fail(TRM_ERR_INVALID, "get_input: count != ncol");
+    CU(cudaSetDevice(device));
+    StageArgs<NF> a; base_args(a);
+    if (int rc = ring_buffer((size_t)nc)) return rc;
+    eval_input_kernel<NF><<<(unsigned)((nc + 127) / 128), 128, 0, stream>>>(nc, a.in[id], (NF)t_inputs, ring_buf);
+    ++launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, ring_buf, nc * sizeof(NF), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return TRM_OK;
+}
+
 template <class NF> int Handle<NF>::aux() {
     if (!initialized) return fail(TRM_ERR_STATE, "trm_compute_auxiliary before trm_initialize");
     CU(cudaSetDevice(device));
@@ -789,6 +810,12 @@ int trm_set_input_table(trm_handle* h, int id, int32_t nt, const double* times, 
     if (!h || !times || !values || bad_input(id) || nt < 1) return fail(TRM_ERR_INVALID, "bad handle / input id / nt");
     return H(h)->set_input_table(id, nt, times, values);
 }
+int trm_set_input_raster(trm_handle* h, int id, int32_t nt, const double* times, const void* values) {
+    if (!h || !times || !values || bad_input(id) || nt < 1) return fail(TRM_ERR_INVALID, "bad handle / input id / table");
+    for (int i = 1; i < nt; ++i) if (!(times[i] > times[i - 1])) return fail(TRM_ERR_INVALID, "raster time axis must increase strictly");
+    return H(h)->set_input_table(id, nt, times, values, TRM_SRC_RASTER);
+}
+int trm_get_input(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->get_input(id, host, count); }
 int trm_input_ptr(trm_handle* h, int id, void** p) { if (!h || !p || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->input_ptr(id, p); }
 int trm_initialize(trm_handle* h) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->initialize(); }
 int trm_step(trm_handle* h, double dt, int64_t n) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->step(dt, n); }

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _abi as abi
 from ._lib import cuda_library
-from .models import (BoundaryCondition, ForwardEuler, Heun, LandModel, Sinusoid, SoilModel, TimeSeries, build_config,
+from .models import (BoundaryCondition, ForwardEuler, Heun, LandModel, RasterInputSource, Sinusoid, SoilModel, TimeSeries, build_config,
                      default_dt, merge_boundary_conditions)
 
 
@@ -129,6 +129,13 @@ class InputField:
 
     def set(self, value):
         self._i._set_input(self.id, value)
+
+    def numpy(self) -> np.ndarray:
+        """The input field as of the last ``update_inputs!`` (start of the last step)."""
+        out = np.empty(self._i.ncol, dtype=self._i.nf)
+        lib = self._i._lib
+        lib.check(lib.get_input(self._i._h, self.id, out.ctypes.data_as(C.c_void_p), out.size), "get_input")
+        return out
 
 
 class ModelIntegrator:
@@ -252,6 +259,19 @@ class ModelIntegrator:
             vals = np.ascontiguousarray(np.broadcast_to(np.asarray(vals, dtype=self.nf), (times.size, self.ncol)), dtype=self.nf)
             lib.check(lib.set_input_table(h, input_id, int(times.size), times.ctypes.data_as(C.POINTER(C.c_double)),
                                           vals.ctypes.data_as(C.c_void_p)), "set_input_table")
+        elif isinstance(value, RasterInputSource):
+            if not hasattr(self.grid, "mask"):
+                raise TypeError("RasterInputSource needs a ColumnRingGrid (the raster lives on its ring grid)")
+            idx = np.flatnonzero(self.grid.mask)[self.col0:self.col1]   # idxmap = findall(mask), this rank's columns
+            vals = np.asarray(value.values)
+            if value.times is None:   # static raster: copied once (initialize_from_raster!, TerrariumRastersExt.jl:70-73)
+                v = np.ascontiguousarray(vals.reshape(-1)[idx], dtype=self.nf)
+                lib.check(lib.set_input_field(h, input_id, v.ctypes.data_as(C.c_void_p)), "set_input_field")
+            else:
+                times = np.ascontiguousarray(np.asarray(value.times, dtype=np.float64) - float(value.reftime))
+                tab = np.ascontiguousarray(vals.reshape(times.size, -1)[:, idx], dtype=self.nf)
+                lib.check(lib.set_input_raster(h, input_id, int(times.size), times.ctypes.data_as(C.POINTER(C.c_double)),
+                                               tab.ctypes.data_as(C.c_void_p)), "set_input_raster")
         elif callable(value):
             # function valued BC (x, t): evaluated on the host before every step (slow path, kept for
             # API compatibility with e.g. examples/simulations/soil_heat_global.jl:72-93)

@@ -368,6 +368,32 @@ class TimeSeries:
 
 
 @dataclass
+class RasterInputSource:
+    """Time-varying (or static) raster on the ring grid of a ``ColumnRingGrid`` (``InputSource(grid, raster)``,
+    ext/TerrariumRastersExt/TerrariumRastersExt.jl:22-56): ``values[nt, nring]`` at ``times[nt]`` seconds relative to
+    ``reftime`` (or ``values[nring]`` without a time axis). The masked points are gathered to the columns
+    (``idxmap = findall(mask)``, :44) and evaluated on the device with the extension's update rule (:96-121)."""
+    values: np.ndarray
+    times: Optional[Sequence[float]] = None
+    reftime: float = 0.0
+
+    @classmethod
+    def from_netcdf(cls, path: str, variable: str, time: str = "time", reftime: float = 0.0):
+        """Read ``variable[time, ...]`` from a NetCDF-3 (classic / 64-bit offset) file; the trailing dimensions are
+        flattened in storage order to the ring-grid points. NetCDF-4 / HDF5 files need a library this image lacks."""
+        from scipy.io import netcdf_file
+        with netcdf_file(path, "r", mmap=False) as f:
+            var = f.variables[variable]
+            data = np.array(var[:], dtype=np.float64)
+            scale, offset = getattr(var, "scale_factor", 1.0), getattr(var, "add_offset", 0.0)
+            data = data * scale + offset
+            has_time = time in f.variables and var.dimensions and var.dimensions[0] == time
+            times = np.array(f.variables[time][:], dtype=np.float64) if has_time else None
+        data = data.reshape(data.shape[0], -1) if has_time else data.reshape(-1)
+        return cls(values=data, times=times, reftime=reftime)
+
+
+@dataclass
 class BoundaryCondition:
     kind: int           # abi.TRM_BC_*
     slot: int           # abi.TRM_BC_<field>_<side>
