@@ -59,7 +59,15 @@ __device__ __forceinline__ bool below_one(float v)  { return __float_as_int(v) <
 // (EF_BETA). The LandModel variants do not evaluate the surface block: surface_kernel (stage_kernel.cuh) has run before
 // and left the ground heat flux and the infiltration in their 2-D fields.
 enum EulerField { EF_KF = 0, EF_T = 2, EF_P, EF_KAP, EF_KC, EF_QH, EF_G, EF_DQH, EF_QD, EF_BETA, EF_COUNT };
-constexpr int EULER_PF = 4;   // depth of the prefetch rings consumed when a layer enters (layers in flight: 3)
+#ifndef TRM_EULER_DIST
+#define TRM_EULER_DIST 4   // measured on the 10 M-column step: 3 layers ahead 3.675 ms, 4: 3.638, 5: 3.646
+#endif
+// layers the cp.async prefetch runs ahead of the layer entering the pipeline. Heun stage 2 keeps 3: its second ring
+// (k1 and the base state) would need 8 instead of 4 slots per field and cost a resident block.
+__host__ __device__ constexpr int euler_dist(int mode) { return mode == MODE_HEUN2 ? 3 : TRM_EULER_DIST; }
+// depth of the prefetch rings that are consumed when a layer enters (T, liq, psi of the LOAD variant; Heun stage 2 ring)
+__host__ __device__ constexpr int euler_pf(int mode) { return euler_dist(mode) < 4 ? 4 : 8; }
+static_assert(TRM_EULER_DIST >= 1 && TRM_EULER_DIST <= 5, "the U / sat ring holds layers m-2 .. m+DIST in 8 slots");
 constexpr int EULER_RD = 8;   // depth of the U / sat ring: layer k stays in slot (k & 7) from its prefetch (iteration
                               // k-3) until it is updated (iteration k+2), so the raw values are never copied
 
@@ -70,10 +78,11 @@ constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 
 // k1 and the base U / sat of a layer are prefetched into a second cp.async ring two iterations before its update).
 template <class NF, int LOAD, int MS, int MODE = MODE_EULER>
 struct EulerSmem {
+    static constexpr int PF_ = euler_pf(MODE);
     static constexpr int METRICS = MET_COUNT * MS;                                    // elements (the root fraction row is only filled by LandModel kernels)
     static constexpr int STRIP = EF_COUNT * TRM_EULER_BLOCK;
-    static constexpr int RING = (2 * EULER_RD + (LOAD ? 3 : 0) * EULER_PF) * TRM_EULER_BLOCK;   // U, sat (, T, liq, psi)
-    static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * EULER_PF * TRM_EULER_BLOCK;   // k1U, k1S, bU, bS
+    static constexpr int RING = (2 * EULER_RD + (LOAD ? 3 : 0) * PF_) * TRM_EULER_BLOCK;   // U, sat (, T, liq, psi)
+    static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * PF_ * TRM_EULER_BLOCK;   // k1U, k1S, bU, bS
     static constexpr size_t BYTES = sizeof(NF) * (size_t)(METRICS + STRIP + RING + XRING);
 };
 
@@ -87,6 +96,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     using Mx = M<NF, FAST>;
     using SM = EulerSmem<NF, LOAD_CT, MS, MODE>;
     constexpr bool H1 = MODE == MODE_HEUN1, H2 = MODE == MODE_HEUN2;
+    constexpr int DIST_ = euler_dist(MODE), PF_ = euler_pf(MODE);
     constexpr bool CLOSE = !H1;    // Heun stage 1 leaves the closure fields of the stage state to stage 2 (recomputed there)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,10 +146,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             cp_async<ES>(ringU(k), A.xU + oin);
             cp_async<ES>(ringS(k), A.xS + oin);
             if (LOAD) {
-                const uint32_t dst = ring0 + (uint32_t)((2 * EULER_RD + (k & (EULER_PF - 1))) * B * ES);
+                const uint32_t dst = ring0 + (uint32_t)((2 * EULER_RD + (k & (PF_ - 1))) * B * ES);
                 cp_async<ES>(dst, A.xT + oin);
-                cp_async<ES>(dst + EULER_PF * B * ES, A.xL + oin);
-                if (RICH) cp_async<ES>(dst + 2 * EULER_PF * B * ES, A.xP + oin);
+                cp_async<ES>(dst + PF_ * B * ES, A.xL + oin);
+                if (RICH) cp_async<ES>(dst + 2 * PF_ * B * ES, A.xP + oin);
             }
             oin += (uint32_t)ld;
         }
@@ -147,16 +157,17 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             // Heun stage 2: k1 and the base state of layer k-2, needed when that layer is updated (iteration k)
             const int kk = k - 2;
             if (kk >= 1 && kk <= nz) {
-                const uint32_t dst = xring0 + (uint32_t)((kk & (EULER_PF - 1)) * B * ES);
+                const uint32_t dst = xring0 + (uint32_t)((kk & (PF_ - 1)) * B * ES);
                 cp_async<ES>(dst, A.k1U + oext);
-                cp_async<ES>(dst + 2 * EULER_PF * B * ES, A.bU + oext);
-                if (RICH) { cp_async<ES>(dst + EULER_PF * B * ES, A.k1S + oext); cp_async<ES>(dst + 3 * EULER_PF * B * ES, A.bS + oext); }
+                cp_async<ES>(dst + 2 * PF_ * B * ES, A.bU + oext);
+                if (RICH) { cp_async<ES>(dst + PF_ * B * ES, A.k1S + oext); cp_async<ES>(dst + 3 * PF_ * B * ES, A.bS + oext); }
                 oext += (uint32_t)ld;
             }
         }
         cp_async_commit();   // (an empty group when nothing is left keeps the group count in step with the iteration count)
     };
-    prefetch(1); prefetch(2); prefetch(3);
+#pragma unroll
+    for (int k = 1; k <= DIST_; ++k) prefetch(k);
 
     NF carry = NF(0);          // over-saturation handed to the layer above (upward sweep of adjust_saturation_profile!)
     // a negative saturation needs the downward sweep -> slow path. Fast math ORs the sign words of the updated
@@ -170,25 +181,25 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     uint32_t oout = (uint32_t)c;   // element offset of layer m-2
     if (LAND && has_veg(A)) wr(EF_BETA, NF(0));   // vegetated LandModel: soil moisture limiting factor (plant_available_water.jl:31-35)
 
-    // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-3, for which every
+    // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-DIST, for which every
     // layer-index special case below is statically false / true: no halo, no boundary face, no Flux BC, the
     // prefetched layer exists. The two instantiations share the source; the loop picks the cheap one whenever it can.
     auto iterate = [&](const int m, auto inner_tag) {
         constexpr bool inner = decltype(inner_tag)::value;
-        prefetch(m + 3, inner);
+        prefetch(m + DIST_, inner);
         // ---- layer m (or the halo above the surface) enters the pipeline ----
         NF Tn, Pn = NF(0), kapn, Kfn = NF(0);     // T, psi, kappa of layer m ; Kf[m]
         const NF Kf1 = RICH ? ldsv(kf_prv, (NF*)nullptr) : NF(0);   // Kf[m-1]
         if (inner || m <= nz) {
-            cp_async_wait<3>();   // all but the 3 most recent groups have landed: layer m is in the ring
+            cp_async_wait<DIST_>();   // all but the DIST most recent groups have landed: layer m is in the ring
             const NF Ur = ldsv(ringU(m), (NF*)nullptr);
             const NF sr = ldsv(ringS(m), (NF*)nullptr);
             NF ln;
             if (LOAD) {
-                const uint32_t src = ring0 + (uint32_t)((2 * EULER_RD + (m & (EULER_PF - 1))) * B * ES);
+                const uint32_t src = ring0 + (uint32_t)((2 * EULER_RD + (m & (PF_ - 1))) * B * ES);
                 Tn = ldsv(src, (NF*)nullptr);
-                ln = ldsv(src + EULER_PF * B * ES, (NF*)nullptr);
-                if (RICH) Pn = ldsv(src + 2 * EULER_PF * B * ES, (NF*)nullptr);
+                ln = ldsv(src + PF_ * B * ES, (NF*)nullptr);
+                if (RICH) Pn = ldsv(src + 2 * PF_ * B * ES, (NF*)nullptr);
             } else {
                 energy_to_temperature<NF, FAST>(p, Ur, sr, Tn, ln);
                 if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
@@ -258,10 +269,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             }
             NF Ub, sb;   // base state the update is applied to
             if (H2) {   // average_tendencies! (heun.jl:27-35) with k1 of stage 1 ; the base is the state at time n
-                const uint32_t x = xring0 + (uint32_t)((j & (EULER_PF - 1)) * B * ES);
+                const uint32_t x = xring0 + (uint32_t)((j & (PF_ - 1)) * B * ES);
                 tU = (ldsv(x, (NF*)nullptr) + tU) / 2;
-                Ub = ldsv(x + 2 * EULER_PF * B * ES, (NF*)nullptr);
-                if (RICH) { tS = (ldsv(x + EULER_PF * B * ES, (NF*)nullptr) + tS) / 2; sb = ldsv(x + 3 * EULER_PF * B * ES, (NF*)nullptr); }
+                Ub = ldsv(x + 2 * PF_ * B * ES, (NF*)nullptr);
+                if (RICH) { tS = (ldsv(x + PF_ * B * ES, (NF*)nullptr) + tS) / 2; sb = ldsv(x + 3 * PF_ * B * ES, (NF*)nullptr); }
                 else sb = ldsv(ringS(j), (NF*)nullptr);   // NoFlow: the saturation is not a prognostic variable
             } else {
                 if (H1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }   // k1, before the Flux BCs
@@ -337,9 +348,9 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         int m = 1;
 #pragma unroll 1
         while (m <= nz + 2) {
-            if (m >= 4 && m <= nz - 3) {
+            if (m >= 4 && m <= nz - DIST_) {
 #pragma unroll 1
-                do { iterate(m, std::true_type{}); ++m; } while (m <= nz - 3);
+                do { iterate(m, std::true_type{}); ++m; } while (m <= nz - DIST_);
             } else {
                 iterate(m, std::false_type{});
                 ++m;
@@ -357,8 +368,16 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
         const NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
         int64_t o = c;
+        if (FAST) {
+            // (wt - zC) + psat + (zC - zref) below the water table: one value for the whole saturated zone (the layer
+            // centres cancel; the two forms differ by rounding only)
+            const NF pconst = (wt_new - met.zF(nz + 1)) + psat;
 #pragma unroll 1
-        for (int k = 1; k < idx && k <= nz; ++k, o += ld) A.yP[o] = Mx::mx(NF(0), wt_new - met.zC(k)) + psat + met.psiz(k);
+            for (int k = 1; k < idx && k <= nz; ++k, o += ld) A.yP[o] = pconst;
+        } else {
+#pragma unroll 1
+            for (int k = 1; k < idx && k <= nz; ++k, o += ld) A.yP[o] = Mx::mx(NF(0), wt_new - met.zC(k)) + psat + met.psiz(k);
+        }
         return;
     }
     // ---- slow path: a layer went negative. Downward sweep (soil_hydrology.jl:201-216) top -> bottom on the raw
