@@ -278,3 +278,37 @@ def test_vegetated_land_f32_and_noflow_soil():
     for it in pair:
         it.step(60.0, 100)
     _compare(pair[0], pair[1], names3=("temperature", "internal_energy"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nz,ncol", [(2, 1), (7, 129), (64, 333), (128, 40)])
+def test_vegetated_land_layer_counts_and_ragged_columns(nz, ncol):
+    """Column counts that do not fill a block / a warp, 2 .. 128 layers (metric rows in the large shared-memory layout),
+    Heun + finalize in the middle of the run, the generic streaming kernel (TRM_KERNEL is read at handle creation)."""
+    import os
+    for kernel in ("smem", "stream"):
+        os.environ["TRM_KERNEL"] = kernel
+        try:
+            cu = synthetic_vegetated_case("cuda", ncol, heun=True, nz=nz, math="fast")
+        finally:
+            os.environ.pop("TRM_KERNEL", None)
+        orc = synthetic_vegetated_case("oracle", ncol, heun=True, nz=nz)
+        for it in (cu, orc):
+            it.step(60.0, 30)
+            it.compute_auxiliary()
+            it.step(60.0, 30)
+        _compare(cu, orc)
+
+
+@pytest.mark.gpu
+def test_user_write_between_steps_refreshes_the_soil_moisture_factor():
+    """set!(saturation_water_ice, ...) between steps: the carried soil moisture limiting factor is recomputed from the
+    stored fields before the next surface launch (beta_kernel), like the oracle's full re-evaluation."""
+    cu = synthetic_vegetated_case("cuda", 50, math="fast")
+    orc = synthetic_vegetated_case("oracle", 50)
+    for it in (cu, orc):
+        it.step(60.0, 10)
+        it.state.saturation_water_ice.set(lambda x, z: np.minimum(1.0, 0.3 - 0.02 * z) + 0 * x)
+        it.step(60.0, 10)
+    _compare(cu, orc)
+    assert np.all(cu.state.soil_moisture_limiting_factor.numpy() < 1.0)
