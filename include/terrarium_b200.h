@@ -78,6 +78,10 @@ enum trm_skin        { TRM_SKIN_IMPLICIT = 0, TRM_SKIN_PRESCRIBED = 1 };
  * StaticExponentialRootDistribution, FieldCapacityLimitedPAW) with the default SurfaceHydrology
  * (PALADYNCanopyInterception + PALADYNCanopyEvapotranspiration + DirectSurfaceRunoff, surface_hydrology.jl:22-29). */
 enum trm_vegetation  { TRM_VEG_NONE = 0, TRM_VEG_CARBON = 1 };
+/* Ground evaporation resistance factor, src/processes/surface_hydrology/evapotranspiration/ground_resistance_factor.jl:
+ * ConstantEvaporationResistanceFactor (params.evap_beta, :6-11) or SoilMoistureResistanceFactor (Lee & Pielke 1992, :32-57:
+ * (1 - cos(pi theta_w / theta_fc))^2 / 4 below field capacity, 1 above; theta_w of the top soil layer). */
+enum trm_ground_resistance { TRM_GROUND_RES_CONSTANT = 0, TRM_GROUND_RES_SOIL_MOISTURE = 1 };
 /* Arithmetic contract of the CUDA kernels.
  *  FAITHFUL: same operations in the same order as the reference/oracle (true divisions,
  *            pow where the reference calls ^), no FMA contraction.
@@ -267,6 +271,7 @@ typedef struct trm_config {
     int32_t skin;             /* trm_skin (LandModel only) */
     int32_t math;             /* trm_math */
     int32_t vegetation;       /* trm_vegetation (LandModel only) */
+    int32_t ground_resistance;/* trm_ground_resistance (LandModel only) */
     const double* z_faces;    /* nz+1 face elevations, bottom .. 0 (column_grid.jl:30-31); copied */
     trm_params params;
     trm_bc bc[TRM_BC_NSLOTS];

@@ -395,13 +395,21 @@ struct Oracle {
         NF vpd = jmax(es - ea, NF(0.1));
         return eps_mw * vpd / p;
     }
+    // ground_evaporation_resistance_factor, ground_resistance_factor.jl:6-11 (constant) / :32-57 (Lee & Pielke 1992)
+    inline NF ground_resistance(const State<NF>& s, int64_t c) const {
+        if (cfg.ground_resistance != TRM_GROUND_RES_SOIL_MOISTURE) return beta;
+        Fr f = fractions(s.sat[s.ix(nz, c)], s.liq[s.ix(nz, c)]);
+        NF fc = (NF)vp.field_capacity;
+        if (f.water < fc) { NF d = 1 - std::cos(NF(3.141592653589793) * f.water / fc); return d * d / 4; }
+        return NF(1);
+    }
     // bare_ground_evaporation.jl:49-62
     void compute_evaporation(State<NF>& s) {
 #pragma omp parallel for schedule(static)
         for (int64_t c = 0; c < nc; ++c) {
             NF Tsurf = cfg.skin == TRM_SKIN_PRESCRIBED ? s.in[TRM_IN_SKIN_TEMPERATURE][c] : s.Ts[c];
             NF dq = humidity_vpd(s, c, Tsurf);
-            s.Egnd[c] = (NF)((double)(beta * dq) / r_a(s, c));
+            s.Egnd[c] = (NF)((double)(ground_resistance(s, c) * dq) / r_a(s, c));
         }
     }
     // direct_surface_runoff.jl:87-117
@@ -594,7 +602,7 @@ struct Oracle {
             NF re = (1 - std::exp(-s.LAI[c] - s.in[TRM_IN_SAI][c])) / (C_can * V);
             NF rs = 1 / jmax(s.gwcan[c], std::sqrt(std::numeric_limits<NF>::epsilon()));
             s.transp[c] = (NF)((double)dqs / (ra + (double)rs));
-            s.Egnd[c] = (NF)((double)(beta * dqg) / (ra + (double)re));
+            s.Egnd[c] = (NF)((double)(ground_resistance(s, c) * dqg) / (ra + (double)re));
             s.Ecan[c] = (NF)((double)(s.fcan[c] * dqs) / ra);
         }
     }

@@ -28,6 +28,7 @@ TRM_HALO_ZERO, TRM_HALO_COPY = 0, 1
 TRM_SKIN_IMPLICIT, TRM_SKIN_PRESCRIBED = 0, 1
 TRM_MATH_FAITHFUL, TRM_MATH_FAST = 0, 1
 TRM_VEG_NONE, TRM_VEG_CARBON = 0, 1
+TRM_GROUND_RES_CONSTANT, TRM_GROUND_RES_SOIL_MOISTURE = 0, 1
 TRM_BC_DEFAULT, TRM_BC_VALUE, TRM_BC_GRADIENT, TRM_BC_FLUX = 0, 1, 2, 3
 (TRM_BC_TEMPERATURE_TOP, TRM_BC_TEMPERATURE_BOTTOM, TRM_BC_ENERGY_TOP, TRM_BC_ENERGY_BOTTOM,
  TRM_BC_SATURATION_TOP, TRM_BC_SATURATION_BOTTOM, TRM_BC_PRESSURE_TOP, TRM_BC_PRESSURE_BOTTOM) = range(8)
@@ -101,7 +102,7 @@ class trm_config(C.Structure):
         ("abi_version", C.c_int32), ("dtype", C.c_int32), ("ncol", C.c_int64), ("col0", C.c_int64),
         ("nz", C.c_int32), ("device", C.c_int32), ("model", C.c_int32), ("timestepper", C.c_int32),
         ("hydrology", C.c_int32), ("swrc", C.c_int32), ("unsat_k", C.c_int32), ("sat_halo", C.c_int32),
-        ("skin", C.c_int32), ("math", C.c_int32), ("vegetation", C.c_int32),
+        ("skin", C.c_int32), ("math", C.c_int32), ("vegetation", C.c_int32), ("ground_resistance", C.c_int32),
         ("z_faces", C.POINTER(C.c_double)),
         ("params", trm_params),
         ("bc", trm_bc * TRM_BC_NSLOTS),

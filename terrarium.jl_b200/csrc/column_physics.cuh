@@ -26,7 +26,8 @@ struct DevParams {
     // derived constants used by FAST math only
     NF rpor, neg_inv_alpha, vg_k_exp1, vg_k_exp2, vg_inv_m_neg, vg_inv_n, r_thspan, se_off;
     NF hc_wi, hc_ia, hc_base, sqk_wi, sqk_ia, sqk_base;   // regrouped constituent sums (see energy_to_temperature)
-    int32_t swrc, unsat_k, sat_halo, skin;
+    int32_t swrc, unsat_k, sat_halo, skin, ground_res;
+    NF th_fc;                  // field capacity (ground evaporation resistance, plant available water)
     int32_t vg_n_is_2;
 };
 
@@ -58,6 +59,8 @@ __device__ __forceinline__ float  texp10(float a)  { return exp10f(a); }
 __device__ __forceinline__ double texp10(double a) { return exp10(a); }
 __device__ __forceinline__ float  tabs(float a)   { return fabsf(a); }
 __device__ __forceinline__ double tabs(double a)  { return fabs(a); }
+__device__ __forceinline__ float  tcos(float a)   { return cosf(a); }
+__device__ __forceinline__ double tcos(double a)  { return cos(a); }
 __device__ __forceinline__ float  fma_(float a, float b, float c)    { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 

@@ -234,7 +234,7 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
 // are read back from the auxiliary fields this function writes.
 template <class NF, bool FAST>
 __device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t c, NF Ta, NF SWd, NF pres, NF ea, NF rain, NF Vc, double ra,
-                                                NF dq, NF T_top, NF beta_sm, bool stage2) {
+                                                NF dq, NF T_top, NF beta_sm, NF beta_g, bool stage2) {
     const DevParams<NF>& p = A.p;
     const VegParams<NF>& v = A.vp;
     const NF co2 = surface_input(A.in[TRM_IN_CO2], c, A.t_x);
@@ -280,7 +280,7 @@ __device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t 
     const NF re = dv<NF, FAST>(1 - texp(-LAI - SAI), v.C_can * Vc);
     const NF rs = dv<NF, FAST>(NF(1), jmax(gw, tsqrt(Lim<NF>::eps())));
     const NF transp = (NF)dv<double, FAST>((double)dq, ra + (double)rs);
-    const NF Egnd = (NF)dv<double, FAST>((double)(p.beta * dqg), ra + (double)re);
+    const NF Egnd = (NF)dv<double, FAST>((double)(beta_g * dqg), ra + (double)re);
     const NF E_can = (NF)dv<double, FAST>((double)(f_can * dq), ra);
     // tendencies: canopy water (canopy_interception.jl:121-127), vegetation carbon (carbon_dynamics.jl:107-112),
     // vegetation area fraction (vegetation_dynamics.jl:60-75)
@@ -318,8 +318,8 @@ __device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t 
 // `stage2` (Heun stage 2): only what feeds the k2 tendencies of those three variables is evaluated -- on the stage
 // state, at t + dt -- and no auxiliary field is written (they belong to the stage copy in the reference, heun.jl:45-58).
 template <class NF, bool FAST>
-__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF K_top, NF dz_top, NF beta_sm,
-                                          bool stage2, NF& G_out, NF& inf_out) {
+__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF liq_top, NF K_top, NF dz_top,
+                                          NF beta_sm, bool stage2, NF& G_out, NF& inf_out) {
     const DevParams<NF>& p = A.p;
     const bool veg = has_veg(A);
     // (inputs: see surface_input)
@@ -348,11 +348,18 @@ __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, boo
     NF ea = dv<NF, FAST>(a.q * a.pres, p.eps_mw + (1 - p.eps_mw) * a.q);
     NF vpd = jmax(es - ea, NF(0.1));
     NF dq = dv<NF, FAST>(p.eps_mw * vpd, a.pres);
-    NF Egnd = (NF)dv<double, FAST>((double)(p.beta * dq), a.ra);
+    // ground evaporation resistance factor, ground_resistance_factor.jl:6-11 (constant) / :32-57 (soil moisture limited)
+    NF beta_g = p.beta;
+    if (p.ground_res == TRM_GROUND_RES_SOIL_MOISTURE) {
+        const NF thw = sat_top * p.por * liq_top;
+        beta_g = NF(1);
+        if (thw < p.th_fc) { const NF d = 1 - tcos(NF(3.141592653589793) * thw / p.th_fc); beta_g = d * d / 4; }
+    }
+    NF Egnd = (NF)dv<double, FAST>((double)(beta_g * dq), a.ra);
     NF rain_ground = a.rain;   // NoCanopyInterception: rainfall_ground aliases rainfall (canopy_interception.jl:11-15)
     NF Qh = Egnd;              // surface_humidity_flux of the evapotranspiration scheme
     if (veg) {
-        vegetation_surface<NF, FAST>(A, c, a.Ta, a.SWd, a.pres, ea, a.rain, Vc, a.ra, dq, T_top, beta_sm, stage2);
+        vegetation_surface<NF, FAST>(A, c, a.Ta, a.SWd, a.pres, ea, a.rain, Vc, a.ra, dq, T_top, beta_sm, beta_g, stage2);
         if (stage2) { G_out = A.G[c]; inf_out = A.infil[c]; return; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
         Egnd = A.Egnd[c];
         rain_ground = A.veg2d[VF_RAING][c];
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(128, TRM_SURFACE_BLOCKS) surface_kernel(const 
     const NF K_top = cell_conductivity<NF, FAST>(p, sat_top, liq_top);   // Kf[Nz] = Kc[Nz], soil_hydrology.jl:249-276
     const NF dz_top = A.metrics[MET_DZC * MET_STRIDE + nz];
     NF G, inf;
-    land_surface<NF, FAST>(A, c, A.richards != 0, T_top, sat_top, K_top, dz_top, has_veg(A) ? A.xbeta[c] : NF(0), A.mode == MODE_HEUN2, G, inf);
+    land_surface<NF, FAST>(A, c, A.richards != 0, T_top, sat_top, liq_top, K_top, dz_top, has_veg(A) ? A.xbeta[c] : NF(0), A.mode == MODE_HEUN2, G, inf);
 }
 
 // soil moisture limiting factor from the stored saturation / liquid fraction (first step after initialize or after the
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     // through face m (heat) and face m-1 (Darcy, needs Kf[m]) are formed, layer m-2 is updated and closed.
     auto iterate = [&](const int m, Stage<NF>& cur, const Stage<NF>& prv) {
         // ---- old content of `cur`: iteration m-2 ----
-        const NF U2 = cur.U, s2 = cur.s, T2 = cur.T, Kf2 = cur.Kf;
+        const NF U2 = cur.U, s2 = cur.s, T2 = cur.T, l2 = cur.l, Kf2 = cur.Kf;
         // ---- layer m ----
         // (for m = nz + 2 nothing enters the window: the slots keep their old values, which nobody reads)
         NF Tn = cur.T, ln = cur.l, Pn = cur.P, kapn = cur.kap, Kcn = cur.Kc;
@@ -575,7 +582,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
         if (LAND && m == nz + 2) {
             if (mode == MODE_HEUN2 && !has_veg(A)) { G_top = A.G[c]; infil_top = A.infil[c]; }   // time-n fluxes (heun.jl:63-66)
-            else land_surface<NF, FAST>(A, c, RICH, T2, s2, Kf2, met.dzc(nz), beta_sm, mode == MODE_HEUN2, G_top, infil_top);
+            else land_surface<NF, FAST>(A, c, RICH, T2, s2, l2, Kf2, met.dzc(nz), beta_sm, mode == MODE_HEUN2, G_top, infil_top);
         }
 
         if (m >= 3 && m <= nz + 2 && mode != MODE_AUX) {

@@ -39,6 +39,7 @@ struct TrmConfig                      # trm_config
     abi_version::Int32; dtype::Int32; ncol::Int64; col0::Int64; nz::Int32; device::Int32
     model::Int32; timestepper::Int32; hydrology::Int32; swrc::Int32; unsat_k::Int32; sat_halo::Int32; skin::Int32; math::Int32
     vegetation::Int32                 # trm_vegetation: 0 = nothing (bare ground), 1 = VegetationCarbon
+    ground_resistance::Int32          # trm_ground_resistance: 0 = constant factor, 1 = SoilMoistureResistanceFactor
     z_faces::Ptr{Cdouble}
     params::TrmParams
     bc::NTuple{TRM_BC_NSLOTS, TrmBC}
@@ -117,7 +118,9 @@ function initialize_b200(model::Union{SoilModel{NF}, LandModel{NF}}, timestepper
     cfg = Ref(TrmConfig(TRM_ABI_VERSION, dtype_code(NF), ncol, 0, nz, device,
         model isa LandModel ? 1 : 0, timestepper isa Heun ? 1 : 0, hyd.vertical_flow isa RichardsEq ? 1 : 0,
         hyd.hydraulic_properties.swrc isa VanGenuchten ? 0 : 1, hyd.hydraulic_properties.unsat_hydraulic_cond isa UnsatKVanGenuchten ? 1 : 0,
-        0, 0, math === :fast ? 1 : 0, (model isa LandModel && !isnothing(model.vegetation)) ? 1 : 0, pointer(zf), params_of(model), bcs))
+        0, 0, math === :fast ? 1 : 0, (model isa LandModel && !isnothing(model.vegetation)) ? 1 : 0,
+        (model isa LandModel && model.surface_hydrology.evapotranspiration.ground_resistance isa Terrarium.SoilMoistureResistanceFactor) ? 1 : 0,
+        pointer(zf), params_of(model), bcs))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve zf check(ccall((:trm_create, LIB), Cint, (Ref{TrmConfig}, Ref{Ptr{Cvoid}}), cfg, h), "create")
     integ = B200Integrator{NF, typeof(model), typeof(timestepper)}(h[], model, timestepper, ncol, nz)

@@ -173,9 +173,19 @@ class DirectSurfaceRunoff:  # runoff/direct_surface_runoff.jl:15-18
     tau_r: float = 3600.0
 
 
+class SoilMoistureResistanceFactor:  # evapotranspiration/ground_resistance_factor.jl:32-57 (Lee & Pielke 1992)
+    pass
+
+
+@dataclass
+class ConstantEvaporationResistanceFactor:  # ground_resistance_factor.jl:6-11
+    factor: float = 1.0
+
+
 @dataclass
 class BareGroundEvaporation:  # evapotranspiration/bare_ground_evaporation.jl:12-20
-    ground_resistance_factor: float = 1.0  # ConstantEvaporationResistanceFactor
+    # a number / ConstantEvaporationResistanceFactor, or SoilMoistureResistanceFactor()
+    ground_resistance_factor: Any = 1.0
 
 
 class NoCanopyInterception:  # canopy_interception.jl:7
@@ -193,7 +203,7 @@ class PALADYNCanopyInterception:  # canopy_interception.jl:33-45
 @dataclass
 class PALADYNCanopyEvapotranspiration:  # canopy_evapotranspiration.jl:28-44
     C_can: float = 0.006
-    ground_resistance_factor: float = 1.0  # ConstantEvaporationResistanceFactor
+    ground_resistance_factor: Any = 1.0  # number / ConstantEvaporationResistanceFactor / SoilMoistureResistanceFactor()
 
 
 @dataclass
@@ -573,7 +583,8 @@ def build_params(model) -> abi.trm_params:
         p.kappa_skin = seb.skin_temperature.kappa_s
         p.C_h, p.min_windspeed = atm.C_h, atm.min_windspeed
         p.tau_r = sh.surface_runoff.tau_r
-        p.evap_beta = sh.evapotranspiration.ground_resistance_factor
+        gr = sh.evapotranspiration.ground_resistance_factor
+        p.evap_beta = 1.0 if isinstance(gr, SoilMoistureResistanceFactor) else float(getattr(gr, "factor", gr))
     # vegetated LandModel
     d = dict(field_capacity=hp.field_capacity, wilting_point=hp.wilting_point, C_mass=c.C_mass)
     veg = getattr(model, "vegetation", None) or VegetationCarbon()
@@ -625,6 +636,8 @@ def build_config(model, timestepper, ncol: int, col0: int = 0, device: int = 0, 
     if isinstance(model, LandModel) and isinstance(model.surface_energy_balance.skin_temperature, PrescribedSkinTemperature):
         cfg.skin = abi.TRM_SKIN_PRESCRIBED
     cfg.math = abi.TRM_MATH_FAST if math == "fast" else abi.TRM_MATH_FAITHFUL
+    if isinstance(model, LandModel) and isinstance(model.surface_hydrology.evapotranspiration.ground_resistance_factor, SoilMoistureResistanceFactor):
+        cfg.ground_resistance = abi.TRM_GROUND_RES_SOIL_MOISTURE
     cfg.vegetation = abi.TRM_VEG_CARBON if isinstance(model, LandModel) and model.vegetation is not None else abi.TRM_VEG_NONE
     zbuf = np.ascontiguousarray(grid.z_faces, dtype=np.float64)
     import ctypes as C

@@ -312,3 +312,32 @@ def test_user_write_between_steps_refreshes_the_soil_moisture_factor():
         it.step(60.0, 10)
     _compare(cu, orc)
     assert np.all(cu.state.soil_moisture_limiting_factor.numpy() < 1.0)
+
+
+# ground_resistance_factor.jl:32-57 (Lee & Pielke 1992): (1 - cos(pi theta_w / theta_fc))^2 / 4 below field capacity
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("vegetated", [False, True], ids=["bare", "vegetated"])
+def test_soil_moisture_resistance_factor(engine, vegetated):
+    n = 6
+    sat_top = np.array([0.05, 0.2, 0.4, 0.5, 0.6, 1.0])   # theta_w = 0.49 sat: below field capacity (0.25) up to sat = 0.51
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_max=1.0, N=12), n)
+
+    def run(factor):
+        if vegetated:
+            sh = trm.SurfaceHydrology(evapotranspiration=trm.PALADYNCanopyEvapotranspiration(ground_resistance_factor=factor))
+            land = trm.LandModel(grid, soil=richards_soil(), surface_hydrology=sh)
+        else:
+            sh = trm.SurfaceHydrology(evapotranspiration=trm.BareGroundEvaporation(ground_resistance_factor=factor))
+            land = trm.LandModel(grid, soil=richards_soil(), vegetation=None, surface_hydrology=sh)
+        inits = {"temperature": 8.0, "saturation_water_ice": lambda x, z: sat_top[None, :] + 0 * z, "carbon_vegetation": 5.0, "skin_temperature": 9.0}
+        integ = make(engine, land, trm.ForwardEuler(dt=60.0), {"windspeed": 2.0}, initializers={k: v for k, v in inits.items() if vegetated or k != "carbon_vegetation"})
+        integ.step(60.0, 1)
+        return integ.state.evaporation_ground.numpy()
+
+    E1, Esm, Ehalf = run(1.0), run(trm.SoilMoistureResistanceFactor()), run(trm.ConstantEvaporationResistanceFactor(0.5))
+    thw = 0.49 * sat_top
+    beta = np.where(thw < 0.25, (1 - np.cos(np.pi * thw / 0.25)) ** 2 / 4, 1.0)
+    assert np.all(E1 > 0)
+    np.testing.assert_allclose(Esm, beta * E1, rtol=1e-12)
+    np.testing.assert_allclose(Ehalf, 0.5 * E1, rtol=1e-12)
+    assert beta[0] < 0.1 and 0.9 < beta[3] < 1.0 and np.all(beta[4:] == 1.0)
