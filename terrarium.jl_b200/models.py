@@ -99,8 +99,17 @@ class ConstantSoilHydraulics:  # soil_hydraulic_properties.jl:62-91
 
 
 @dataclass
-class SoilHydraulicsSURFEX(ConstantSoilHydraulics):  # soil_hydraulic_properties.jl:112-140 (same K path)
-    pass
+class SoilHydraulicsSURFEX(ConstantSoilHydraulics):  # soil_hydraulic_properties.jl:112-156 (same K path)
+    # field capacity and wilting point follow the clay content of the (homogeneous) soil texture
+    wilting_point_coef: float = 37.13e-3
+    field_capacity_coef: float = 89.0e-3
+    field_capacity_exp: float = 0.35
+
+    def capacities(self, texture, nf):
+        """``(field_capacity, wilting_point)`` evaluated in the number format ``nf`` like the reference kernels (:145-156)."""
+        clay100 = nf(texture.clay) * nf(100)
+        return (float(nf(self.field_capacity_coef) * clay100 ** nf(self.field_capacity_exp)),
+                float(nf(self.wilting_point_coef) * np.sqrt(clay100)))
 
 
 class NoFlow:  # soil_hydrology.jl:13
@@ -125,8 +134,31 @@ class ConstantSoilPorosity:  # soil_porosity.jl:7-13
 
 
 @dataclass
+class SoilTexture:  # stratigraphy/soil_texture.jl:6-20 (named textures: :35-39)
+    sand: float = 1.0
+    clay: float = 0.0
+    silt: Optional[float] = None
+
+    def __post_init__(self):
+        if self.silt is None:
+            self.silt = 1.0 - self.sand - self.clay
+        for v in (self.sand, self.silt, self.clay):
+            if not -1e-12 <= v <= 1.0 + 1e-12:
+                raise ValueError("sand, silt and clay fractions must lie in [0, 1]")
+        if abs(self.sand + self.silt + self.clay - 1.0) > 1e-8:
+            raise ValueError("sand, silt, and clay fractions must sum to unity")
+
+    @classmethod
+    def named(cls, name: str):
+        return cls(**{"sand": dict(sand=1.0, silt=0.0, clay=0.0), "silt": dict(sand=0.0, silt=1.0, clay=0.0),
+                      "clay": dict(sand=0.0, silt=0.0, clay=1.0), "sandyclay": dict(sand=0.5, silt=0.0, clay=0.5),
+                      "siltyclay": dict(sand=0.0, silt=0.5, clay=0.5)}[name])
+
+
+@dataclass
 class HomogeneousStratigraphy:  # homogeneous_strat.jl:8-23
     porosity: ConstantSoilPorosity = field(default_factory=ConstantSoilPorosity)
+    texture: SoilTexture = field(default_factory=SoilTexture)
 
 
 @dataclass
@@ -586,7 +618,10 @@ def build_params(model) -> abi.trm_params:
         gr = sh.evapotranspiration.ground_resistance_factor
         p.evap_beta = 1.0 if isinstance(gr, SoilMoistureResistanceFactor) else float(getattr(gr, "factor", gr))
     # vegetated LandModel
-    d = dict(field_capacity=hp.field_capacity, wilting_point=hp.wilting_point, C_mass=c.C_mass)
+    fc, wp = hp.field_capacity, hp.wilting_point
+    if isinstance(hp, SoilHydraulicsSURFEX):
+        fc, wp = hp.capacities(soil.strat.texture, np.dtype(model.grid.nf).type)
+    d = dict(field_capacity=fc, wilting_point=wp, C_mass=c.C_mass)
     veg = getattr(model, "vegetation", None) or VegetationCarbon()
     ph, sc, ar, cd, vd, rd = (veg.photosynthesis, veg.stomatal_conductance, veg.autotrophic_respiration, veg.carbon_dynamics,
                               veg.vegetation_dynamics, veg.root_distribution)

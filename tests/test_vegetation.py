@@ -341,3 +341,21 @@ def test_soil_moisture_resistance_factor(engine, vegetated):
     np.testing.assert_allclose(Esm, beta * E1, rtol=1e-12)
     np.testing.assert_allclose(Ehalf, 0.5 * E1, rtol=1e-12)
     assert beta[0] < 0.1 and 0.9 < beta[3] < 1.0 and np.all(beta[4:] == 1.0)
+
+
+# SoilHydraulicsSURFEX (soil_hydraulic_properties.jl:112-156): field capacity / wilting point from the clay content
+@pytest.mark.parametrize("engine", ENGINES)
+def test_surfex_field_capacity_and_wilting_point(engine):
+    clay = 0.3
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.UniformSpacing(dz=0.2, N=10), 2)
+    hp = trm.SoilHydraulicsSURFEX(swrc=trm.VanGenuchten(alpha=2.0, n=2.0), unsat_hydraulic_cond=trm.UnsatKVanGenuchten())
+    soil = trm.SoilEnergyWaterCarbon(hydrology=trm.SoilHydrology(trm.RichardsEq(), hydraulic_properties=hp),
+                                     strat=trm.HomogeneousStratigraphy(texture=trm.SoilTexture(sand=0.5, clay=clay)))
+    fc, wp = 89.0e-3 * (clay * 100) ** 0.35, 37.13e-3 * np.sqrt(clay * 100)
+    assert trm.build_params(trm.LandModel(grid, soil=soil)).field_capacity == pytest.approx(fc, rel=1e-15)
+    integ = veg_land(engine, grid=grid, soil=soil, inits={"temperature": 10.0, "saturation_water_ice": 0.5, "carbon_vegetation": 5.0})
+    integ.compute_auxiliary()
+    want = min(1.0, max(0.0, (0.49 * 0.5 - wp) / (fc - wp)))
+    np.testing.assert_allclose(integ.state.plant_available_water.numpy(), want, rtol=1e-12)
+    with pytest.raises(ValueError):
+        trm.SoilTexture(sand=0.8, clay=0.5)
