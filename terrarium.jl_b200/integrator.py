@@ -180,6 +180,9 @@ class ModelIntegrator:
         self._cfg = cfg
         for input_id, value in pending:
             self._set_input(input_id, value)
+        if inputs is not None and not isinstance(inputs, dict):   # initialize(model, ts, InputSource(...), ...) style
+            sources = [inputs] if hasattr(inputs, "name") else list(inputs)
+            inputs = {src.name: src.value for src in sources}
         for name, value in (inputs or {}).items():
             if name not in abi.INPUT_IDS:
                 raise KeyError(f"unknown input variable {name!r}")

@@ -435,6 +435,23 @@ class RasterInputSource:
         return cls(values=data, times=times, reftime=reftime)
 
 
+def InputSource(grid, data, name: Optional[str] = None, times=None, reftime: float = 0.0):
+    """``InputSource(grid, field_or_raster; name = ...)`` (input_sources.jl:81-171, TerrariumRastersExt.jl:39-56): a named
+    input for ``initialize(model, timestepper, inputs...)``. ``data`` is a number / per-column array / ``Sinusoid`` /
+    ``TimeSeries`` (field sources), or an array on the ring grid of a ``ColumnRingGrid`` (optionally with ``times``)."""
+    if name is None:
+        raise ValueError("InputSource needs the name of the input variable it provides")
+    ring = hasattr(grid, "mask") and isinstance(data, np.ndarray) and data.shape[-1] == grid.npoints and grid.npoints != grid.Nc
+    value = RasterInputSource(values=data, times=times, reftime=reftime) if ring else (TimeSeries(times, data) if times is not None else data)
+    return NamedInput(name, value)
+
+
+@dataclass
+class NamedInput:
+    name: str
+    value: Any
+
+
 @dataclass
 class BoundaryCondition:
     kind: int           # abi.TRM_BC_*

@@ -92,3 +92,21 @@ def test_raster_forcing_parity_with_oracle():
             runs.append(integ.state.temperature.numpy())
     assert np.max(np.abs(runs[0] - runs[2])) <= 1e-11 * np.max(np.abs(runs[2]))
     assert np.max(np.abs(runs[1] - runs[3])) <= 2e-5 * np.max(np.abs(runs[3]))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_input_source_constructor(engine):
+    """initialize(model, timestepper, InputSource(grid, data; name)...) -- field sources and ring-grid rasters."""
+    rng = np.random.default_rng(8)
+    mask = rng.uniform(size=30) > 0.3
+    grid = trm.ColumnRingGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_max=1.0, N=8), mask)
+    land = trm.LandModel(grid, vegetation=None)
+    Ta_ring = rng.uniform(-5.0, 20.0, (3, 30))
+    srcs = [trm.InputSource(grid, Ta_ring, name="air_temperature", times=[0.0, 600.0, 1200.0]),
+            trm.InputSource(grid, 2.5, name="windspeed"),
+            trm.InputSource(grid, rng.uniform(100.0, 400.0, int(mask.sum())), name="surface_shortwave_down")]
+    integ = make(engine, land, trm.ForwardEuler(dt=300.0), srcs, initializers={"temperature": 3.0})
+    integ.step(300.0, 2)   # last update_inputs! at t = 300: halfway between the first two snapshots
+    np.testing.assert_allclose(integ.state.air_temperature.numpy(), 0.5 * (Ta_ring[0] + Ta_ring[1])[mask], rtol=1e-14)
+    assert np.all(integ.state.windspeed.numpy() == 2.5)
+    assert np.all(np.isfinite(integ.state.ground_heat_flux.numpy()))
