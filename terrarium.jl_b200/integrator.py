@@ -112,8 +112,22 @@ class StateVariables:
         object.__setattr__(self, "clock", Clock(integ))
 
     def __getattr__(self, name):
+        if name == "inputs":   # state.inputs.<name> (state_variables.jl:38-41)
+            return _Inputs(self._i)
         if name in abi.FIELD_IDS:
             return Field(self._i, name)
+        if name in self._i._bc_inputs:
+            return InputField(self._i, self._i._bc_inputs[name])
+        if name in abi.INPUT_IDS:
+            return InputField(self._i, abi.INPUT_IDS[name])
+        raise AttributeError(name)
+
+
+class _Inputs:
+    def __init__(self, integ):
+        self._i = integ
+
+    def __getattr__(self, name):
         if name in self._i._bc_inputs:
             return InputField(self._i, self._i._bc_inputs[name])
         if name in abi.INPUT_IDS:
