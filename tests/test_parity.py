@@ -363,3 +363,48 @@ def test_land_model_immobile_water_1000_steps(math, stepper):
         compare(gpu, cpu, fields, TOL)
     gpu.compute_auxiliary(); cpu.compute_auxiliary()
     compare(gpu, cpu, ("hydraulic_conductivity", "surface_net_radiation", "evaporation_ground"), TOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# fast-math formulas across regimes: the one-root conductivity, the reciprocal-square-root retention curve, clamped seeds
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(6))
+def test_fast_math_regimes_randomised(seed):
+    """Random columns spanning frozen / thawing / thawed soil, nearly dry to exactly saturated layers, residual water
+    content, van Genuchten alpha from 0.3 to 5 per metre and ice impedance 0 .. 9: 150 steps of the fast build against
+    the oracle, per-step ulp-level formula differences must stay below the parity bar."""
+    rng = np.random.default_rng(100 + seed)
+    ncol, nz = 257, int(rng.integers(5, 40))
+    alpha, theta_res, omega = float(rng.uniform(0.3, 5.0)), float(rng.choice([0.0, 0.03, 0.08])), float(rng.uniform(0.0, 9.0))
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_min=0.05, dz_max=10.0, N=nz), ncol)
+    hp = trm.ConstantSoilHydraulics(swrc=trm.VanGenuchten(alpha=alpha, n=2.0, theta_res=theta_res),
+                                    unsat_hydraulic_cond=trm.UnsatKVanGenuchten(impedance=omega), sat_hydraulic_cond=float(rng.uniform(1e-7, 5e-6)))
+    soil = trm.SoilEnergyWaterCarbon(hydrology=trm.SoilHydrology(trm.RichardsEq(), hydraulic_properties=hp))
+    T0 = rng.uniform(-12.0, 12.0, ncol)
+    zc = grid.znodes_center().astype(np.float64)
+    sat0 = rng.uniform(0.02, 1.3, (nz, ncol)).clip(max=1.0)           # about a quarter of the cells exactly saturated
+    T_init = T0[None, :] + rng.uniform(-2.0, 2.0, (nz, ncol))
+    T_ub = T0 + (4.0 if seed % 2 else -4.0)
+    pair = []
+    for engine in ("cuda", "oracle"):
+        model = trm.SoilModel(grid, soil=soil)
+        integ = make(engine, model, trm.ForwardEuler(dt=20.0), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", T_ub),
+                     initializers={"temperature": T_init, "saturation_water_ice": sat0}, math="fast")
+        pair.append(integ)
+    for integ in pair:
+        integ.step(20.0, 150)
+    compare(pair[0], pair[1], FIELDS + ("pressure_head", "water_table"), TOL)
+    # (the surface excess is zero or rounding noise of a top layer sitting at saturation here: absolute comparison)
+    assert np.max(np.abs(pair[0].state.surface_excess_water.numpy() - pair[1].state.surface_excess_water.numpy())) <= 1.0e-13
+    pair[0].compute_auxiliary(); pair[1].compute_auxiliary()
+    # K(x) = K_sat sqrt(x) (1 - sqrt(1 - x^(2/3)))^2 has an unbounded derivative at saturation: one ulp in x^(2/3) next to
+    # x = 1 moves K by 1.5e-8 K_sat in the reference formula itself (1 - sqrt(1.1e-16) vs 1 - 0), whatever computes the
+    # power. Cells whose liquid saturation sits within a few ulp of 1 are therefore compared at 1e-7; all others at the bar.
+    Kc, Ko = pair[0].state.hydraulic_conductivity.numpy(), pair[1].state.hydraulic_conductivity.numpy()
+    assert np.max(np.abs(Kc - Ko)) <= 1.0e-7 * np.max(np.abs(Ko))
+    x = (pair[1].state.saturation_water_ice.numpy() * pair[1].state.liquid_water_fraction.numpy())
+    near = (x > 1.0 - 1.0e-12) & (x < 1.0)
+    face_near = np.zeros(Ko.shape, dtype=bool)
+    face_near[:-1] |= near; face_near[1:] |= near          # a face takes the smaller of the two adjacent cell values
+    ok = ~face_near
+    assert np.max(np.abs(Kc - Ko)[ok]) <= TOL * np.max(np.abs(Ko))
