@@ -359,3 +359,37 @@ def test_surfex_field_capacity_and_wilting_point(engine):
     np.testing.assert_allclose(integ.state.plant_available_water.numpy(), want, rtol=1e-12)
     with pytest.raises(ValueError):
         trm.SoilTexture(sand=0.8, clay=0.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# column budgets of the coupled model: what enters through the surface is what the column gains
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("vegetated", [False, True], ids=["bare", "vegetated"])
+def test_land_model_energy_and_water_budgets_close(engine, vegetated):
+    """ForwardEuler: the column energy changes by -G dt per step (G: ground heat flux, positive upward, Flux BC on the
+    internal energy, land_model.jl:56-62) and the column water (soil + surface excess) by porosity * infiltration dt -- as
+    coded the infiltration is a Flux BC on the SATURATION (land_model.jl:59-61, soil_model_bcs.jl:29), so a layer's water
+    content gains porosity times the flux; the bottom boundary is closed. Evaluated step by step from the fields the
+    surface block leaves behind."""
+    ncol = 24
+    if vegetated:
+        integ = synthetic_vegetated_case(engine, ncol, dt=60.0)
+    else:
+        from common import synthetic_land_case
+        integ = synthetic_land_case(engine, ncol, windspeed=0.5)
+    dz = np.diff(integ.grid.znodes_face().astype(np.float64))[:, None]
+
+    def budgets():
+        U, s = integ.state.internal_energy.numpy(), integ.state.saturation_water_ice.numpy()
+        return (U * dz).sum(axis=0), (s * 0.49 * dz).sum(axis=0) + integ.state.surface_excess_water.numpy()
+
+    E0, W0 = budgets()
+    dE, dW = np.zeros(ncol), np.zeros(ncol)
+    for _ in range(120):   # two hours: rain on, infiltration active
+        integ.step(60.0, 1)
+        dE -= 60.0 * integ.state.ground_heat_flux.numpy()     # fluxes of the evaluation at the start of the step
+        dW += 0.49 * 60.0 * integ.state.infiltration.numpy()
+    E1, W1 = budgets()
+    assert np.any(np.abs(dW) > 0) and np.all(np.abs(dE) > 0)
+    np.testing.assert_allclose(E1 - E0, dE, rtol=1e-9, atol=1e-9 * np.max(np.abs(dE)))
+    np.testing.assert_allclose(W1 - W0, dW, rtol=1e-9, atol=1e-9 * np.max(np.abs(dW)))
