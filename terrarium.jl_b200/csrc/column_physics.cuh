@@ -161,6 +161,35 @@ struct M<float, true> {
     __device__ static __forceinline__ void roots(float x, float& x23, float& x12) { x23 = pow23(x); x12 = sqrtf(x); }
 };
 
+// exp for the fast build (per-column surface / vegetation block: thirteen of them per column). Argument reduction
+// x = n ln2 + r with the round-to-nearest magic constant, degree-13 Taylor polynomial on |r| <= ln2 / 2 (truncation
+// 4e-18), scaling through the exponent field; arguments are clamped to +-700 (no overflow / denormal handling).
+__device__ __forceinline__ double exp_fast(double x) {
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -6.93147180369123816490e-01, x);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+template <class NF, bool FAST> __device__ __forceinline__ NF xexp(NF a) { return texp(a); }
+template <> __device__ __forceinline__ double xexp<double, true>(double a) { return exp_fast(a); }
+
 // a / b: IEEE division in the faithful build, reciprocal seed + one third-order step (<= 2 ulp) in the fast build
 template <class NF, bool FAST>
 __device__ __forceinline__ NF dv(NF a, NF b) { return FAST ? M<NF, FAST>::div(a, b) : a / b; }
@@ -355,9 +384,9 @@ __device__ __forceinline__ double pow4(double x) {
 __device__ __forceinline__ float pow4(float x) { double d = (double)x; double d2 = d * d; return (float)(d2 * d2); }
 
 // saturation vapour pressure (August-Roche-Magnus), physics_utils.jl:54-73
-template <class NF>
+template <class NF, bool FAST = false>
 __device__ __forceinline__ NF saturation_vapor_pressure(NF T) {
-    return T <= 0 ? NF(611.0) * texp(NF(22.46) * T / (T + NF(272.62))) : NF(611.0) * texp(NF(17.62) * T / (T + NF(243.12)));
+    return T <= 0 ? NF(611.0) * xexp<NF, FAST>(dv<NF, FAST>(NF(22.46) * T, T + NF(272.62))) : NF(611.0) * xexp<NF, FAST>(dv<NF, FAST>(NF(17.62) * T, T + NF(243.12)));
 }
 
 }  // namespace trm

@@ -248,17 +248,18 @@ __device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t 
     const NF LAI = (fdec * phen + (NF(1.0) - fdec)) * LAIb;
     // MedlynStomatalConductance (stomatal_conductance.jl:45-82): vapour pressure deficit at the air temperature,
     // net assimilation of the PREVIOUS evaluation (vegetation_carbon.jl:89-91)
-    const NF vpd_air = jmax(saturation_vapor_pressure(Ta) - ea, NF(0.1));
-    const NF g0 = (v.g_min / 1000) * (1 - texp(-v.k_ext * LAI)) * beta_sm;
+    const NF vpd_air = jmax(saturation_vapor_pressure<NF, FAST>(Ta) - ea, NF(0.1));
+    const NF fapar = 1 - xexp<NF, FAST>(-v.k_ext * LAI);   // also the absorbed fraction of PAR (photosynthesis.jl:124-128)
+    const NF g0 = (v.g_min / 1000) * fapar * beta_sm;
     const NF gw = g0 + dv<NF, FAST>(NF(1.6) * (1 + dv<NF, FAST>(v.g1, tsqrt(vpd_air))) * An_prev, co2) * NF(1.0e6);
     const NF lamc = NF(1.0) - dv<NF, FAST>(NF(1.0), NF(1.0) + dv<NF, FAST>(v.g1, tsqrt(vpd_air * NF(1.0e-3))));
     // LUEPhotosynthesis (photosynthesis.jl:284-344)
     NF Rd, An;
-    photosynthesis<NF, FAST>(v, Ta, SWd, pres, co2, LAI, lamc, beta_sm, Rd, An);
+    photosynthesis<NF, FAST>(v, Ta, SWd, pres, co2, LAI, fapar, lamc, beta_sm, Rd, An);
     const NF GPP = An * NF(1.0e-3);
     // PALADYNAutotrophicRespiration (autotrophic_respiration.jl:46-154) ; T_soil = ground temperature
-    const NF f_soil = (T_top > 7) ? texp(NF(308.56) * (NF(1.0) / NF(56.02) - dv<NF, FAST>(NF(1.0), NF(46.02) + T_top))) : NF(0);
-    const NF f_air = texp(NF(308.56) * (NF(1.0) / NF(56.02) - dv<NF, FAST>(NF(1.0), NF(46.02) + Ta)));
+    const NF f_soil = (T_top > 7) ? xexp<NF, FAST>(NF(308.56) * (NF(1.0) / NF(56.02) - dv<NF, FAST>(NF(1.0), NF(46.02) + T_top))) : NF(0);
+    const NF f_air = xexp<NF, FAST>(NF(308.56) * (NF(1.0) / NF(56.02) - dv<NF, FAST>(NF(1.0), NF(46.02) + Ta)));
     const NF resp10 = NF(0.066);
     const NF R_leaf = Rdl / NF(1000.0);
     const NF R_stem = dv<NF, FAST>(resp10 * f_air * (v.awl * ((NF(2.0) / v.SLA) + v.awl)), Cv * v.aws * v.cn_sapwood);
@@ -270,14 +271,14 @@ __device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t 
     // PALADYNCanopyInterception (canopy_interception.jl:79-187)
     const NF wmax = v.w_can_max * (LAI + SAI);
     const NF f_can = wmax > 0 ? dv<NF, FAST>(wcan, wmax) : NF(0);
-    const NF I_can = v.alpha_int * rain * (NF(1) - texp(-v.k_ext_can * (LAI + SAI)));
+    const NF I_can = v.alpha_int * rain * (NF(1) - xexp<NF, FAST>(-v.k_ext_can * (LAI + SAI)));
     const NF R_can = jmax(wcan, NF(0)) / v.tau_w;
     const NF rain_ground = rain - I_can + R_can;
     // PALADYNCanopyEvapotranspiration (canopy_evapotranspiration.jl:51-177): humidity gradients at the skin and at
     // the ground temperature, resistance between ground and canopy, stomatal resistance
-    const NF esg = saturation_vapor_pressure(T_top);
+    const NF esg = saturation_vapor_pressure<NF, FAST>(T_top);
     const NF dqg = dv<NF, FAST>(p.eps_mw * jmax(esg - ea, NF(0.1)), pres);
-    const NF re = dv<NF, FAST>(1 - texp(-LAI - SAI), v.C_can * Vc);
+    const NF re = dv<NF, FAST>(1 - xexp<NF, FAST>(-LAI - SAI), v.C_can * Vc);
     const NF rs = dv<NF, FAST>(NF(1), jmax(gw, tsqrt(Lim<NF>::eps())));
     const NF transp = (NF)dv<double, FAST>((double)dq, ra + (double)rs);
     const NF Egnd = (NF)dv<double, FAST>((double)(beta_g * dqg), ra + (double)re);
@@ -344,7 +345,7 @@ __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, boo
     // BareGroundEvaporation, bare_ground_evaporation.jl:49-62 ; compute_humidity_vpd
     // prescribed_atmosphere.jl:160-182, physical_constants.jl:83-97, physics_utils.jl:38
     NF Tsurf = prescribed ? a.Tskin_in : Ts;
-    NF es = saturation_vapor_pressure(Tsurf);
+    NF es = saturation_vapor_pressure<NF, FAST>(Tsurf);
     NF ea = dv<NF, FAST>(a.q * a.pres, p.eps_mw + (1 - p.eps_mw) * a.q);
     NF vpd = jmax(es - ea, NF(0.1));
     NF dq = dv<NF, FAST>(p.eps_mw * vpd, a.pres);

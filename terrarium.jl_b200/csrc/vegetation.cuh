@@ -51,7 +51,7 @@ __device__ __forceinline__ NF plant_available_water_fast(const VegParams<NF>& v,
 // :110-113, compute_APAR :124-128, compute_temperature_stress :143-169, compute_assimilation_factors :185-194,
 // compute_Vc_max :208-211 -- called with APAR --, compute_Rd :225-228, compute_Ag :241-248)
 template <class NF, bool FAST>
-__device__ __forceinline__ void photosynthesis(const VegParams<NF>& v, NF T_air, NF swdown, NF pres, NF co2, NF LAI, NF lamc, NF beta_sm,
+__device__ __forceinline__ void photosynthesis(const VegParams<NF>& v, NF T_air, NF swdown, NF pres, NF co2, NF LAI, NF fapar /* 1 - exp(-k_ext LAI) */, NF lamc, NF beta_sm,
                                                NF& Rd, NF& An) {
     const NF pres_O2 = NF(0.209) * pres;          // physics_utils.jl:16-20
     const NF pres_a = co2 * NF(1.0e-6) * pres;    // physics_utils.jl:27-30
@@ -59,21 +59,21 @@ __device__ __forceinline__ void photosynthesis(const VegParams<NF>& v, NF T_air,
     if (!(swdown > 0 && T_air > NF(-3.0))) return;
     const NF ex = (T_air - NF(25.0)) * NF(0.1);
     // fast math: q10^ex = exp(ex ln q10) with the logarithms taken once on the host
-    const NF tau = v.tau25 * (FAST ? texp(ex * v.ln_q10_tau) : tpow(v.q10_tau, ex));
-    const NF Kc = v.Kc25 * (FAST ? texp(ex * v.ln_q10_Kc) : tpow(v.q10_Kc, ex));
-    const NF Ko = v.Ko25 * (FAST ? texp(ex * v.ln_q10_Ko) : tpow(v.q10_Ko, ex));
+    const NF tau = v.tau25 * (FAST ? xexp<NF, FAST>(ex * v.ln_q10_tau) : tpow(v.q10_tau, ex));
+    const NF Kc = v.Kc25 * (FAST ? xexp<NF, FAST>(ex * v.ln_q10_Kc) : tpow(v.q10_Kc, ex));
+    const NF Ko = v.Ko25 * (FAST ? xexp<NF, FAST>(ex * v.ln_q10_Ko) : tpow(v.q10_Ko, ex));
     const NF Gs = dv<NF, FAST>(pres_O2, NF(2.0) * tau);
     if (!(LAI > 0)) return;
     const NF PAR = NF(0.5) * swdown * (NF(1.0) - v.alpha_leaf) * v.cq;
-    const NF APAR = v.alpha_a * PAR * (NF(1.0) - texp(-v.k_ext * LAI));
+    const NF APAR = v.alpha_a * PAR * fapar;
     const NF pres_i = lamc * pres_a;
     const NF k1 = FAST ? v.ts_k1 : NF(2.0) * tlog(NF(1.0) / NF(0.99) - NF(1.0)) / (v.T_CO2_low - v.T_photos_low);
     const NF k2 = FAST ? v.ts_k2 : NF(0.5) * (v.T_CO2_low + v.T_photos_low);
     const NF k3 = FAST ? v.ts_k3 : tlog(NF(0.99) / NF(0.01)) / (v.T_CO2_high - v.T_photos_high);
     NF T_stress = 0;
     if (v.T_CO2_low < T_air && T_air < v.T_CO2_high) {
-        const NF low = dv<NF, FAST>(NF(1.0), NF(1.0) + texp(k1 * (k2 - T_air)));
-        const NF high = NF(1.0) - NF(0.01) * texp(k3 * (T_air - v.T_photos_high));
+        const NF low = dv<NF, FAST>(NF(1.0), NF(1.0) + xexp<NF, FAST>(k1 * (k2 - T_air)));
+        const NF high = NF(1.0) - NF(0.01) * xexp<NF, FAST>(k3 * (T_air - v.T_photos_high));
         T_stress = low * high;
     }
     const NF c_1 = dv<NF, FAST>(v.alpha_C3 * T_stress * v.C_mass * (pres_i - Gs), pres_i + NF(2.0) * Gs);
