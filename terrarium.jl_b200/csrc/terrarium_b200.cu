@@ -5,6 +5,7 @@
 // src/timesteppers/forward_euler.jl:19-31 and heun.jl:37-71, host <-> device field copies.
 // There is NO CPU implementation behind these entry points: without a CUDA device trm_create
 // fails with TRM_ERR_NO_DEVICE.
+#include <nvtx3/nvToolsExt.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -102,6 +103,7 @@ struct Handle : HandleBase {
     Input in[TRM_IN_COUNT];
     bool initialized = false;
     bool aux_stale = true;   // stored T / liq / psi are not closure(U, sat): the next stage must read them
+    bool debug_nancheck = false;   // env TERRARIUM_DEBUG=true, the reference's debug switch (src/diagnostics/debugging.jl:1)
     bool force_load = false; // tuning knob (env TRM_FORCE_LOAD_AUX=1): always read T / liq / psi instead of recomputing them
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the asynchronous entry points
@@ -143,6 +145,7 @@ struct Handle : HandleBase {
         if (c.vegetation != TRM_VEG_NONE && c.vegetation != TRM_VEG_CARBON) return fail(TRM_ERR_INVALID, "bad vegetation code");
         veg = land && c.vegetation == TRM_VEG_CARBON;   // (the field is ignored for a SoilModel)
         { const char* e = std::getenv("TRM_FORCE_LOAD_AUX"); force_load = e && e[0] == '1'; }
+        { const char* e = std::getenv("TERRARIUM_DEBUG"); debug_nancheck = e && std::string(e) == "true"; }
         if (const char* e = std::getenv("TRM_KERNEL")) {
             const std::string k(e);
             if (k == "stream") euler_impl = 0; else if (k == "smem") euler_impl = 1;
@@ -548,12 +551,22 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
 }
 
 template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
-    if (int rc = enqueue_steps(dt_, n)) return rc;
+    nvtxRangePushA("trm_step");   // visible in nsys / ncu timelines around the stage launches of this call
+    int rc = enqueue_steps(dt_, n);
+    nvtxRangePop();
+    if (rc) return rc;
     CU(cudaEventSynchronize(ev1));
     CU(cudaEventElapsedTime(&last_ms, ev0, ev1));
     timing_open = false;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("trm_step: ") + cudaGetErrorString(e));
+    if (debug_nancheck) {
+        // TERRARIUM_DEBUG=true (src/diagnostics/debugging.jl:1-47): the reference checks every kernel output for NaN;
+        // here the state is checked once per trm_step call with the diagnostics reduction
+        trm_diag d;
+        if (int rc2 = diagnostics(&d, nullptr)) return rc2;
+        if (d.nan_count > 0) return fail(TRM_ERR_STATE, "TERRARIUM_DEBUG: found " + std::to_string((long long)d.nan_count) + " non-finite values in internal_energy / temperature / saturation_water_ice after trm_step");
+    }
     return TRM_OK;
 }
 

@@ -408,3 +408,15 @@ def test_fast_math_regimes_randomised(seed):
     face_near[:-1] |= near; face_near[1:] |= near          # a face takes the smaller of the two adjacent cell values
     ok = ~face_near
     assert np.max(np.abs(Kc - Ko)[ok]) <= TOL * np.max(np.abs(Ko))
+
+
+def test_debug_nancheck(monkeypatch):
+    """TERRARIUM_DEBUG=true (src/diagnostics/debugging.jl): a NaN in the state makes trm_step fail instead of continuing."""
+    monkeypatch.setenv("TERRARIUM_DEBUG", "true")
+    integ = synthetic_soil_case("cuda", 40, math="fast")
+    integ.step(60.0, 2)
+    U = integ.state.internal_energy.numpy()
+    U[3, 5] = np.nan
+    integ.state.internal_energy.set(U)
+    with pytest.raises(trm.TerrariumError, match="TERRARIUM_DEBUG"):
+        integ.step(60.0, 1)
