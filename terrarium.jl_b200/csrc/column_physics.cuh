@@ -150,15 +150,32 @@ struct M<double, true> {
 };
 template <>
 struct M<float, true> {
-    __device__ static __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    // MUFU seeds are within ~1 ulp of FP32 already: no refinement, no IEEE fix-up paths (no calls in the layer loop)
+    __device__ static __forceinline__ float rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
     __device__ static __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
-    __device__ static __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-    __device__ static __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+    // seed of 1/sqrt(x), clamped to 2^64 so that x = 0 gives finite products (0 * seed = 0)
+    __device__ static __forceinline__ float rsqrt_(float x) {
+        float y;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return fminf(y, 1.8446744e19f);
+    }
+    __device__ static __forceinline__ float sqrt_(float x) { return x * rsqrt_(x); }
     __device__ static __forceinline__ float mn(float a, float b) { return fminf(a, b); }
     __device__ static __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
     __device__ static __forceinline__ float pow23(float x) { float c = cbrtf(x); return c * c; }
     __device__ static __forceinline__ float pos(float e) { return fmaxf(e, 0.0f); }
-    __device__ static __forceinline__ void roots(float x, float& x23, float& x12) { x23 = pow23(x); x12 = sqrtf(x); }
+    // x^(2/3) and x^(1/2) from r ~ x^(-1/6) (lg2 / ex2 seed, one Newton step), like the FP64 variant
+    __device__ static __forceinline__ void roots(float x, float& x23, float& x12) {
+        if (x < 1.0e-30f) { x23 = pow23(x); x12 = sqrtf(x); return; }
+        float l, r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * (-1.0f / 6.0f)));
+        const float r3 = (r * r) * r;
+        const float e = fmaf(-x * r3, r3, 1.0f);
+        r = fmaf(r, e * (1.0f / 6.0f), r);
+        x23 = x * (r * r);
+        x12 = x23 * r;
+    }
 };
 
 // exp for the fast build (per-column surface / vegetation block: thirteen of them per column). Argument reduction
@@ -344,15 +361,10 @@ __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF 
         // m = 1/2: psi_m = -(1/alpha) sqrt(se^-2 - 1) ; se = 0 (dry layer) is -Inf as in the reference
         const NF se = fma_(theta, p.r_thspan, p.se_off);   // (theta - theta_res) / (theta_sat - theta_res)
         const NF t = se * se;
-        NF r;
-        if (sizeof(NF) == 8) {
-            // sqrt((1 - t) / t) = a / sqrt(a t), a = 1 - se^2 from one FMA (no cancellation as se -> 1), one
-            // reciprocal square root and no branch: a = 0 gives 0 * (finite seed) = 0 ; |.|: rounding guard as se -> 1
-            const NF a = tabs(fma_(-se, se, NF(1)));
-            r = (p.neg_inv_alpha * a) * M<NF, FAST>::rsqrt_(a * t);
-        } else {
-            r = p.neg_inv_alpha * M<NF, FAST>::sqrt_(tabs(M<NF, FAST>::rcp(t) - NF(1)));
-        }
+        // sqrt((1 - t) / t) = a / sqrt(a t), a = 1 - se^2 from one FMA (no cancellation as se -> 1), one
+        // reciprocal square root and no branch: a = 0 gives 0 * (finite seed) = 0 ; |.|: rounding guard as se -> 1
+        const NF a = tabs(fma_(-se, se, NF(1)));
+        NF r = (p.neg_inv_alpha * a) * M<NF, FAST>::rsqrt_(a * t);
         r = t == NF(0) ? -Lim<NF>::inf() : r;
         return theta < thsat ? r : NF(0);
     }
