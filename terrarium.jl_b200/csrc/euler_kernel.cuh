@@ -23,6 +23,9 @@ namespace trm {
 #ifndef TRM_EULER_MIN_BLOCKS
 #define TRM_EULER_MIN_BLOCKS 6   // <= 80 registers per thread, 24 resident warps per SM (measured: 4 blocks 5.08 ms, 5: 4.52, 6: 4.16 per 10 M-column step)
 #endif
+#ifndef TRM_EULER_F32_BLOCKS
+#define TRM_EULER_F32_BLOCKS 8
+#endif
 #ifndef TRM_EULER_LAND_BLOCKS
 #define TRM_EULER_LAND_BLOCKS 6   // the LandModel variants no longer contain the surface block (surface_kernel): same budget as the soil kernel
 #endif
@@ -31,7 +34,7 @@ namespace trm {
 // gets a looser bound.
 template <class NF, int PHYS, bool FAST, int MODE = MODE_EULER>
 constexpr int euler_min_blocks() {
-    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (phys_land(PHYS) ? TRM_EULER_LAND_BLOCKS : (sizeof(NF) == 4 ? 8 : TRM_EULER_MIN_BLOCKS)));
+    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (phys_land(PHYS) ? TRM_EULER_LAND_BLOCKS : (sizeof(NF) == 4 ? TRM_EULER_F32_BLOCKS : TRM_EULER_MIN_BLOCKS)));
 }
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
