@@ -317,10 +317,12 @@ __device__ __noinline__ NF cell_conductivity_cold(const DevParams<NF>& p, NF sat
 template <class NF>
 __device__ __noinline__ NF ice_impedance_cold(NF Omega, NF liq) { return texp10(-Omega * (1 - liq)); }
 
-template <class NF, bool FAST>
+// VG2 (compile time): the caller has checked on the host that the soil is van Genuchten with n = 2 for both the
+// retention curve and the conductivity, so the run-time tests for the general (cold) formulas drop out of the loop
+template <class NF, bool FAST, bool VG2 = false>
 __device__ __forceinline__ NF cell_conductivity(const DevParams<NF>& p, NF sat, NF liq) {
     if (FAST) {
-        if (!p.vg_n_is_2 || p.unsat_k == TRM_UNSATK_LINEAR) return cell_conductivity_cold(p, sat, liq);
+        if (!VG2 && (!p.vg_n_is_2 || p.unsat_k == TRM_UNSATK_LINEAR)) return cell_conductivity_cold(p, sat, liq);
         // van Genuchten n = 2. End members are exact in the reference formula too:
         // x = 0 -> K = 0, x = 1 (saturated, thawed) -> K = K_sat
         const NF x = sat * liq;
@@ -354,10 +356,10 @@ __device__ __forceinline__ NF swrc_inverse_reference(const DevParams<NF>& p, NF 
 template <class NF>
 __device__ __noinline__ NF swrc_inverse_cold(const DevParams<NF>& p, NF theta, NF thsat) { return swrc_inverse_reference(p, theta, thsat); }
 
-template <class NF, bool FAST>
+template <class NF, bool FAST, bool VG2 = false>
 __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF thsat) {
     if (FAST) {
-        if (p.swrc != TRM_SWRC_VANGENUCHTEN || !p.vg_n_is_2) return swrc_inverse_cold(p, theta, thsat);
+        if (!VG2 && (p.swrc != TRM_SWRC_VANGENUCHTEN || !p.vg_n_is_2)) return swrc_inverse_cold(p, theta, thsat);
         // m = 1/2: psi_m = -(1/alpha) sqrt(se^-2 - 1) ; se = 0 (dry layer) is -Inf as in the reference
         const NF se = fma_(theta, p.r_thspan, p.se_off);   // (theta - theta_res) / (theta_sat - theta_res)
         const NF t = se * se;
@@ -372,9 +374,9 @@ __device__ __forceinline__ NF swrc_inverse(const DevParams<NF>& p, NF theta, NF 
 }
 
 // total pressure head, saturation_to_pressure! soil_hydraulic_closures.jl:102-129 ; psiz = zc - zref
-template <class NF, bool FAST>
+template <class NF, bool FAST, bool VG2 = false>
 __device__ __forceinline__ NF pressure_head(const DevParams<NF>& p, NF sat, NF wt, NF zc, NF psiz) {
-    NF psim = swrc_inverse<NF, FAST>(p, sat * p.por, p.por);
+    NF psim = swrc_inverse<NF, FAST, VG2>(p, sat * p.por, p.por);
     NF psih = M<NF, FAST>::pos(wt - zc);
     return psih + psim + psiz;
 }

@@ -98,7 +98,8 @@ struct EulerSmem {
     static constexpr size_t BYTES = sizeof(NF) * (size_t)(METRICS + STRIP + RING + XRING);
 };
 
-template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS, int MODE = MODE_EULER>
+// VG2: van Genuchten n = 2 for retention curve and conductivity, checked on the host (see cell_conductivity)
+template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS, int MODE = MODE_EULER, bool VG2 = false>
 __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, FAST, MODE>())) euler_kernel(const __grid_constant__ StageArgs<NF> A) {
     constexpr bool RICH = phys_richards(PHYS);
     constexpr bool LAND = phys_land(PHYS);
@@ -214,12 +215,12 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (RICH) Pn = ldsv(src + 2 * PF_ * B * ES, (NF*)nullptr);
             } else {
                 energy_to_temperature<NF, FAST>(p, Ur, sr, Tn, ln);
-                if (RICH) Pn = pressure_head<NF, FAST>(p, sr, wtx, met.zC(m), met.psiz(m));
+                if (RICH) Pn = pressure_head<NF, FAST, VG2>(p, sr, wtx, met.zC(m), met.psiz(m));
             }
             kapn = FAST ? thermal_conductivity_fast(p, sr, ln) : thermal_conductivity(p, sr, ln);
             if (RICH) {
                 // cell conductivity and face conductivity Kf[m], soil_hydrology.jl:249-276
-                const NF Kcn = cell_conductivity<NF, FAST>(p, sr, ln);
+                const NF Kcn = cell_conductivity<NF, FAST, VG2>(p, sr, ln);
                 Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : Mx::mn(Kcn, rd(EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
                 wr(EF_KC, Kcn);
             }
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                     if (CLOSE) {
                         stg(A.yT + o, Tc); stg(A.yL + o, lc);
                         // layers below the water table wait for it (written after the sweep)
-                        if (RICH && idx != 0) stg(A.yP + o, pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j)));
+                        if (RICH && idx != 0) stg(A.yP + o, pressure_head<NF, FAST, VG2>(p, sn, wt_new, met.zC(j), met.psiz(j)));
                     }
                 }
             }
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         if (H1) return;            // the stage state needs no surface excess water and no closure fields
         A.ySx[c] = Sx_new;
         // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
-        const NF psat = swrc_inverse<NF, FAST>(p, p.por, p.por);
+        const NF psat = swrc_inverse<NF, FAST, VG2>(p, p.por, p.por);
         int64_t o = c;
         if (FAST) {
             // (wt - zC) + psat + (zC - zref) below the water table: one value for the whole saturated zone (the layer
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 beta += FAST ? plant_available_water_fast(A.vp, p, s, lc) * met.root(k) : plant_available_water(A.vp, p, s, lc) * met.root(k) / met.dzc(k) * met.dzc(k);
             if (H1) continue;   // the stage state keeps no closure fields
             A.yT[o] = Tc; A.yL[o] = lc;
-            A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, met.zC(k), met.psiz(k));
+            A.yP[o] = pressure_head<NF, FAST, VG2>(p, s, wt_new, met.zC(k), met.psiz(k));
         }
         if (LAND && has_veg(A)) A.ybeta[c] = beta;
     }

@@ -22,17 +22,17 @@ cudaError_t launch_phys(int variant, const StageArgs<NF>& a, int block, cudaStre
 }
 
 // ForwardEuler / Heun stages, streaming kernel with the pipeline state in shared memory (euler_kernel.cuh)
-template <class NF, int PHYS, int LOAD, int MS, int MODE>
+template <class NF, int PHYS, int LOAD, int MS, int MODE, bool VG2 = false>
 cudaError_t launch_euler_variant(const StageArgs<NF>& a, cudaStream_t st) {
     constexpr size_t smem = EulerSmem<NF, LOAD, MS, MODE>::BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE, VG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int64_t nblk = (a.ncol + TRM_EULER_BLOCK - 1) / TRM_EULER_BLOCK;
-    euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
+    euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE, VG2><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <class NF, int PHYS, int LOAD>
@@ -42,6 +42,12 @@ cudaError_t launch_euler_mode(int mode, const StageArgs<NF>& a, cudaStream_t st)
         return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_HEUN1>(a, st);
     }
     if (mode == MODE_HEUN2) return launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2>(a, st);   // stage state: always recomputed
+    // fast math, steady-state ForwardEuler stage of a van Genuchten n = 2 soil: the instantiation without the run-time
+    // tests for the general retention / conductivity formulas (the hot configuration of the benchmark)
+    if (kFast && LOAD == 0 && phys_richards(PHYS) && a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN) {
+        if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER, kFast && LOAD == 0 && phys_richards(PHYS)>(a, st);
+        return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER, kFast && LOAD == 0 && phys_richards(PHYS)>(a, st);
+    }
     if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER>(a, st);
     return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER>(a, st);
 }
