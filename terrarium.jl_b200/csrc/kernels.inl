@@ -37,19 +37,27 @@ cudaError_t launch_euler_variant(const StageArgs<NF>& a, cudaStream_t st) {
 }
 template <class NF, int PHYS, int LOAD>
 cudaError_t launch_euler_mode(int mode, const StageArgs<NF>& a, cudaStream_t st) {
-    if (mode == MODE_HEUN1) {   // compact metric rows keep a sixth block resident (37 -> 31.5 KB of shared memory per block)
-        if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_HEUN1>(a, st);
-        return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_HEUN1>(a, st);
+    // fast math, van Genuchten n = 2 soil, closure fields recomputed: the instantiations without the run-time tests for
+    // the general retention / conductivity formulas (the hot configuration of the benchmark)
+    constexpr bool CAN_VG2 = kFast && LOAD == 0 && phys_richards(PHYS);
+    const bool vg2 = CAN_VG2 && a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN;
+    const bool compact = a.nz + 3 <= EULER_MS_SMALL;   // compact metric rows keep one more block resident
+    if (mode == MODE_HEUN1) {
+        if (vg2) return compact ? launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_HEUN1, CAN_VG2>(a, st)
+                                : launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_HEUN1, CAN_VG2>(a, st);
+        return compact ? launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_HEUN1>(a, st)
+                       : launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_HEUN1>(a, st);
     }
-    if (mode == MODE_HEUN2) return launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2>(a, st);   // stage state: always recomputed
-    // fast math, steady-state ForwardEuler stage of a van Genuchten n = 2 soil: the instantiation without the run-time
-    // tests for the general retention / conductivity formulas (the hot configuration of the benchmark)
-    if (kFast && LOAD == 0 && phys_richards(PHYS) && a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN) {
-        if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER, kFast && LOAD == 0 && phys_richards(PHYS)>(a, st);
-        return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER, kFast && LOAD == 0 && phys_richards(PHYS)>(a, st);
+    if (mode == MODE_HEUN2) {   // stage state: always recomputed
+        constexpr bool H2_VG2 = kFast && phys_richards(PHYS);
+        if (H2_VG2 && a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN)
+            return launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2, H2_VG2>(a, st);
+        return launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2>(a, st);
     }
-    if (a.nz + 3 <= EULER_MS_SMALL) return launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER>(a, st);
-    return launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER>(a, st);
+    if (vg2) return compact ? launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER, CAN_VG2>(a, st)
+                            : launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER, CAN_VG2>(a, st);
+    return compact ? launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER>(a, st)
+                   : launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER>(a, st);
 }
 template <class NF>
 cudaError_t launch_euler(int phys, int mode, int load_aux, const StageArgs<NF>& a, cudaStream_t st) {
