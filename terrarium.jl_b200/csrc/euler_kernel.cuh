@@ -1,14 +1,22 @@
 // euler_kernel.cuh -- ForwardEuler / Heun stages, streaming kernel with the pipeline state in shared memory.
 //
 // Same algorithm and the same per-cell arithmetic as stage_kernel (one thread = one column, one sweep
-// bottom -> top, see the header of stage_kernel.cuh for the reference functions), but the values that
-// travel between pipeline iterations (closure fields, conductivities, fluxes of the two most recent
-// layers) live in a per-thread strip of shared memory `[field][slot][thread]` instead of registers,
-// and the raw U / sat loads are prefetched by cp.async (LDGSTS) into a 4-deep shared-memory ring:
-//   * no register rotation (the register version spends ~16 % of its instructions on moves),
-//   * one copy of the loop body instead of two (half the instruction-cache footprint),
-//   * ~half the registers -> more resident warps to hide the FP64 dependency latency.
-// Shared memory is addressed through explicit 32-bit shared addresses (`row register + immediate`).
+// bottom -> top, see the header of stage_kernel.cuh for the reference functions), but
+//   * the values that travel between pipeline iterations (closure fields, conductivities, fluxes) live in a
+//     per-thread strip of shared memory `[field][thread]` -- one slot per field, read by the next iteration before it
+//     is overwritten; only Kf, which the iteration after next still needs, alternates between two slots -- instead of
+//     registers: no register rotation, one copy of the loop body, 80 registers -> 6 resident blocks (24 warps) per SM;
+//   * the raw U / sat loads are prefetched by cp.async (LDGSTS) four layers ahead into an 8-deep shared-memory ring in
+//     which a layer stays from its prefetch until its update (never copied); T / liq / psi of the LOAD variant and the
+//     k1 / base state of Heun stage 2 come through rings of their own;
+//   * inner iterations (no halo, boundary face, Flux BC) run a second instantiation of the loop body without the
+//     layer-index tests; a third axis (VG2) removes the run-time tests for the general retention / conductivity formulas
+//     when the host has checked that the soil is van Genuchten with n = 2;
+//   * output stores are evict-first (st.global.cs);
+//   * the LandModel variants do not evaluate the surface block: surface_kernel (stage_kernel.cuh) runs before the stage
+//     and leaves the ground heat flux / infiltration in their 2-D fields; for the vegetated model the stage accumulates
+//     the soil moisture limiting factor of the state it WRITES for the next surface launch.
+// Shared memory is addressed through explicit 32-bit shared addresses (`thread register + immediate`).
 #pragma once
 
 #include <type_traits>
