@@ -371,6 +371,10 @@ int trm_last_step_ms(trm_handle* h, float* ms);
 int trm_set_input_field_async(trm_handle* h, int input_id, const void* pinned_host_values /* [ncol] NF */);
 int trm_step_async(trm_handle* h, double dt, int64_t nsteps);
 int trm_get_field_async(trm_handle* h, int field_id, void* pinned_host, int64_t count);
+/* Page-locked host memory for the asynchronous entry points (cudaHostAlloc / cudaFreeHost), so that a caller without
+ * a CUDA binding of its own (the Julia / Python host side) can own pinned buffers. */
+int trm_host_alloc(int64_t bytes, void** host);
+int trm_host_free(void* host);
 
 /* ---- ColumnRingGrid conversions (src/grids/column_ring_grid.jl:102-149) --------------------------------
  * The columns of a ColumnRingGrid are the `true` points of a mask over a ring grid of `nring` points, in ring

@@ -844,6 +844,18 @@ int64_t trm_launch_count(trm_handle* h) { return h ? H(h)->launches : 0; }
 int trm_last_step_ms(trm_handle* h, float* ms) { if (!h || !ms) return fail(TRM_ERR_INVALID, "null argument"); *ms = H(h)->last_ms; return TRM_OK; }
 int trm_set_input_field_async(trm_handle* h, int id, const void* v) { if (!h || !v || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_field_async(id, v); }
 int trm_get_field_async(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field_async(id, host, count); }
+int trm_host_alloc(int64_t bytes, void** host) {
+    if (!host || bytes <= 0) return fail(TRM_ERR_INVALID, "trm_host_alloc: bad arguments");
+    cudaError_t e = cudaHostAlloc(host, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TRM_ERR_NO_DEVICE : TRM_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    return TRM_OK;
+}
+int trm_host_free(void* host) {
+    if (!host) return TRM_OK;
+    cudaError_t e = cudaFreeHost(host);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(TRM_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e)); }
+    return TRM_OK;
+}
 int trm_step_async(trm_handle* h, double dt, int64_t n) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->step_async(dt, n); }
 int trm_set_ring_index(trm_handle* h, const int64_t* ring_index, int64_t nring) { if (!h || !ring_index) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->set_ring_index(ring_index, nring); }
 int trm_get_field_ring(trm_handle* h, int id, void* host, int64_t count, double fill) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field_ring(id, host, count, fill); }

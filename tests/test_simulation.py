@@ -1,0 +1,82 @@
+"""Simulation / output writers / callbacks (docs/src/running/time_stepping.md:86-180 of the reference):
+scheduled NetCDF output with asynchronous snapshots, callbacks, time-step alignment, FieldTimeSeries read-back."""
+import numpy as np
+import pytest
+
+from common import ENGINES, make, synthetic_soil_case, trm
+from test_vegetation import synthetic_vegetated_case
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_simulation_with_output_writer_and_callbacks(engine, tmp_path):
+    integ = synthetic_soil_case(engine, 37, dt=300.0)
+    ref = synthetic_soil_case(engine, 37, dt=300.0)
+    sim = trm.Simulation(integ, stop_time=6 * 3600.0, dt=300.0)
+    path = str(tmp_path / "soil.nc")
+    sim.output_writers["soil"] = trm.NetCDFWriter(integ, {"temperature": integ.state.temperature, "saturation": integ.state.saturation_water_ice,
+                                                           "water_table": "water_table", "K": "hydraulic_conductivity"},
+                                                  filename=path, schedule=trm.TimeInterval(2 * 3600.0), overwrite_existing=True)
+    seen = []
+    sim.callbacks["progress"] = trm.Callback(lambda s: seen.append((s.model.clock.iteration, s.model.clock.time)), trm.IterationInterval(30))
+    trm.run_simulation(sim)
+    sim.close()
+    assert integ.clock.time == 6 * 3600.0 and integ.clock.iteration == 72 and sim.steps_taken == 72
+    assert seen == [(0, 0.0), (30, 9000.0), (60, 18000.0)]
+    T = trm.FieldTimeSeries(path, "temperature")
+    S = trm.FieldTimeSeries(path, "saturation")
+    K = trm.FieldTimeSeries(path, "K")
+    assert list(T.times) == [0.0, 7200.0, 14400.0, 21600.0] and T.data.shape == (4, 30, 37) and K.data.shape == (4, 31, 37)
+    np.testing.assert_array_equal(T.z, integ.grid.znodes_center())
+    # every record equals the state of an undisturbed run at that time (run! semantics: auxiliaries current at output)
+    ref.compute_auxiliary()
+    for i in range(4):
+        assert np.array_equal(T[i], ref.state.temperature.numpy()), i
+        assert np.array_equal(S[i], ref.state.saturation_water_ice.numpy()), i
+        assert np.array_equal(K[i], ref.state.hydraulic_conductivity.numpy()), i
+        if i < 3:
+            trm.run(ref, steps=24, dt=300.0)
+    assert np.array_equal(T[-1], integ.state.temperature.numpy())
+    # a finished simulation does not run again until the integrator is re-initialised (time_stepping.md:131-133)
+    trm.run_simulation(sim)
+    assert sim.steps_taken == 72
+    with pytest.raises(FileExistsError):
+        trm.NetCDFWriter(integ, ["temperature"], filename=path, schedule=trm.IterationInterval(1))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_time_step_alignment_and_stop_iteration(engine, tmp_path):
+    integ = synthetic_soil_case(engine, 5, dt=300.0)
+    sim = trm.Simulation(integ, stop_time=2500.0, dt=300.0)
+    sim.output_writers["o"] = trm.NetCDFWriter(integ, ["temperature"], filename=str(tmp_path / "a.nc"), schedule=trm.TimeInterval(1000.0))
+    sim.run(); sim.close()
+    T = trm.FieldTimeSeries(str(tmp_path / "a.nc"), "temperature")
+    # 3 x 300 + 100 to land on 1000, 3 x 300 + 100 to land on 2000, 300 + 200 to land on the stop time
+    assert list(T.times) == [0.0, 1000.0, 2000.0] and integ.clock.time == 2500.0 and sim.steps_taken == 10
+    ref = synthetic_soil_case(engine, 5, dt=300.0)
+    for dt in (300.0, 300.0, 300.0, 100.0):
+        ref.step(dt, 1)
+    assert np.array_equal(T[1], ref.state.temperature.numpy())
+    integ2 = synthetic_soil_case(engine, 5, dt=300.0)
+    sim2 = trm.Simulation(integ2, stop_iteration=7, dt=300.0)
+    sim2.run()
+    assert integ2.clock.iteration == 7 and integ2.clock.time == 2100.0
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_vegetated_simulation_equals_timestep_loop(engine, tmp_path):
+    """The vegetated LandModel finalizes every step (timestep! semantics): identical to a timestep! loop that starts, like
+    the simulation, with an evaluation of the auxiliaries."""
+    a = synthetic_vegetated_case(engine, 11)
+    b = synthetic_vegetated_case(engine, 11)
+    sim = trm.Simulation(a, stop_iteration=12, dt=60.0)
+    assert sim.finalize_every_step
+    sim.output_writers["veg"] = trm.NetCDFWriter(a, ["carbon_vegetation", "canopy_water_conductance", "temperature"], filename=str(tmp_path / "v.nc"),
+                                                 schedule=trm.IterationInterval(4))
+    sim.run(); sim.close()
+    b.compute_auxiliary()   # run!(sim) starts with update_state! (Oceananigans initialises the simulation): one more evaluation
+    for _ in range(12):
+        trm.timestep(b, 60.0)
+    for name in ("temperature", "carbon_vegetation", "canopy_water_conductance", "net_assimilation", "ground_heat_flux"):
+        assert np.array_equal(getattr(a.state, name).numpy(), getattr(b.state, name).numpy()), name
+    g = trm.FieldTimeSeries(str(tmp_path / "v.nc"), "canopy_water_conductance")
+    assert len(g) == 4 and np.array_equal(g[-1], b.state.canopy_water_conductance.numpy())
