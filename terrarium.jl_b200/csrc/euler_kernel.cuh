@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     auto bc_input = [&](int slot) -> NF {
         const int kind = A.bc[slot].kind;
         if (kind == TRM_BC_DEFAULT) return NF(0);
-        return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x);
+        return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x, kind == TRM_BC_FLUX ? 1 : 0);
     };
     const NF wtx = (RICH && !LOAD) ? A.xWt[c] : NF(0);
 

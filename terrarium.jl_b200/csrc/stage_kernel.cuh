@@ -74,14 +74,21 @@ struct Metrics {
 #define TRM_MIN_BLOCKS 1    // resident blocks per SM the register allocator must allow
 #endif
 
+// where a clock time falls on the time axis of a table input (searched once per launch on the host)
+struct TimeBracket {
+    int32_t i1, i2;      // rows of the two bracketing snapshots (i1 only when flat)
+    int32_t flat, pad_;  // 1: before / after the axis or exactly on a node of a raster -> the value of row i1
+    double e, dtt;       // t - times[i1], times[i2] - times[i1]
+};
+
 template <class NF>
 struct InputDesc {
     int32_t kind, nt;
     NF cval;
     double period, lo, hi;
-    const NF *a, *b, *c;     // FIELD: a ; SINUSOID: a = mean, b = amp, c = phase ; TABLE: a = values[nt][ld]
-    const double* times;     // TABLE
+    const NF *a, *b, *c;     // FIELD: a ; SINUSOID: a = mean, b = amp, c = phase ; TABLE / RASTER: a = values[nt][ld]
     int64_t ld;
+    TimeBracket br[2];       // TABLE / RASTER: bracket of t_x (0) and of t_b (1)
 };
 
 template <class NF>
@@ -133,8 +140,9 @@ __device__ __forceinline__ bool has_veg(const StageArgs<NF>& A) {
 }
 
 // update_inputs! (input_sources.jl:165-171) and function valued BCs, evaluated at clock time t.
+// `which`: 0 when t is the time the tendencies are evaluated at (t_x), 1 for the time of the base state (t_b, Flux BCs)
 template <class NF>
-__device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t c, NF t) {
+__device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t c, NF t, int which = 0) {
     switch (s.kind) {
         case TRM_SRC_CONST: return s.cval;
         case TRM_SRC_FIELD: return s.a[c];
@@ -147,42 +155,28 @@ __device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t 
             return (NF)v;
         }
         case TRM_SRC_TABLE: {
-            // FieldTimeSeries[Time(t)]: linear between bracketing snapshots, flat outside
-            // (ext/TerrariumRastersExt/TerrariumRastersExt.jl:104-120)
-            double td = (double)t;
-            const double* tt = s.times;
-            int nt = s.nt;
-            if (td <= tt[0]) return s.a[c];
-            if (td >= tt[nt - 1]) return s.a[(int64_t)(nt - 1) * s.ld + c];
-            int lo = 0, hi = nt;   // upper_bound: first index with tt[i] > td
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (tt[mid] > td) hi = mid; else lo = mid + 1; }
-            int n2 = lo, n1 = lo - 1;
-            NF frac = (NF)((td - tt[n1]) / (tt[n2] - tt[n1]));
-            return s.a[(int64_t)n2 * s.ld + c] * frac + s.a[(int64_t)n1 * s.ld + c] * (1 - frac);
+            // FieldTimeSeries[Time(t)]: linear between bracketing snapshots, flat outside. The bracket of the clock
+            // time is the same for every column: the host has searched the time axis (Handle::bracket) and passes
+            // the two rows, e = t - t1 and dt = t2 - t1 ; frac = (NF)(e / dt) exactly as input_sources.jl:165-171 would
+            const TimeBracket& k = s.br[which];
+            if (k.flat) return s.a[(int64_t)k.i1 * s.ld + c];
+            const NF frac = (NF)(k.e / k.dtt);
+            return s.a[(int64_t)k.i2 * s.ld + c] * frac + s.a[(int64_t)k.i1 * s.ld + c] * (1 - frac);
         }
         case TRM_SRC_RASTER: {
             // update_from_raster! (ext/TerrariumRastersExt/TerrariumRastersExt.jl:96-121): x1 + eps (x2 - x1) / dt in
             // Float64 between nodes, the node value on a node, flat beyond either end of the time axis
-            const double td = (double)t;
-            const double* tt = s.times;
-            const int nt = s.nt;
-            int lo = 0, hi = nt;   // lower_bound: first index with tt[i] >= td
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (tt[mid] < td) lo = mid + 1; else hi = mid; }
-            const int right = lo + 1;                                  // first(searchsorted), 1-based
-            const int left = (lo < nt && tt[lo] == td) ? lo + 1 : lo;   // last(searchsorted) (time axes are strictly increasing)
-            if (left >= 1 && right <= nt) {
-                const NF x1 = s.a[(int64_t)(left - 1) * s.ld + c], x2 = s.a[(int64_t)(right - 1) * s.ld + c];
-                const double dtt = tt[right - 1] - tt[left - 1], e = td - tt[left - 1];
-                return dtt > 0 ? (NF)((double)x1 + e * (double)(x2 - x1) / dtt) : x2;
-            }
-            return s.a[(int64_t)((right < nt ? right : nt) - 1) * s.ld + c];
+            const TimeBracket& k = s.br[which];
+            if (k.flat) return s.a[(int64_t)k.i1 * s.ld + c];
+            const NF x1 = s.a[(int64_t)k.i1 * s.ld + c], x2 = s.a[(int64_t)k.i2 * s.ld + c];
+            return (NF)((double)x1 + k.e * (double)(x2 - x1) / k.dtt);
         }
     }
     return NF(0);
 }
 // out-of-line copy for the layer loop (boundary condition inputs: rare, and inlined they would bloat the loop)
 template <class NF>
-__device__ __noinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t) { return eval_input_inline(s, c, t); }
+__device__ __noinline__ NF eval_input(const InputDesc<NF>& s, int64_t c, NF t, int which = 0) { return eval_input_inline(s, c, t, which); }
 
 // input evaluation of the surface block: inlined (independent loads overlap; measured 1.5 % faster than one shared
 // out-of-line copy, TRM_SURFACE_SHARED_INPUTS)
@@ -483,7 +477,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
     auto bc_input = [&](int slot) -> NF {
         const int kind = A.bc[slot].kind;
         if (kind == TRM_BC_DEFAULT) return NF(0);
-        return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x);
+        return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x, kind == TRM_BC_FLUX ? 1 : 0);
     };
     const NF bc_T_top = bc_input(TRM_BC_TEMPERATURE_TOP);
     const NF wtx = RICH && !load_aux ? A.xWt[c] : NF(0);

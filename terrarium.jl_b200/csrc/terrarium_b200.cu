@@ -96,7 +96,7 @@ struct Handle : HandleBase {
     VegParams<NF> vp{};
     std::vector<NF> rootf;
     struct Input { int kind = TRM_SRC_CONST; double cval = 0, period = 1, lo = -INFINITY, hi = INFINITY; int nt = 0;
-                   NF *a = nullptr, *b = nullptr, *c = nullptr; double* times = nullptr;
+                   NF *a = nullptr, *b = nullptr, *c = nullptr; std::vector<double> times;   // (time axis of a table: host side only)
                    // asynchronous per-column field inputs are double buffered: `a` is what enqueued steps read,
                    // `a2` receives the next upload; ev_free[i] fires when buffer i is no longer read by any step
                    NF* a2 = nullptr; cudaEvent_t ev_free[2] = {nullptr, nullptr}; cudaEvent_t ev_ready = nullptr; int front = 0; };
@@ -352,11 +352,9 @@ struct Handle : HandleBase {
         CU(cudaSetDevice(device));
         Input& s = in[id];
         if (s.a) { dfree(s.a); s.a = nullptr; }
-        if (s.times) { dfree(s.times); s.times = nullptr; }
         if (int rc = dalloc(&s.a, (size_t)nt * ld)) return rc;
-        if (int rc = dalloc(&s.times, (size_t)nt)) return rc;
+        s.times.assign(times, times + nt);
         CU(cudaMemcpy2DAsync(s.a, ld * sizeof(NF), values, nc * sizeof(NF), nc * sizeof(NF), nt, cudaMemcpyHostToDevice, stream));
-        CU(cudaMemcpyAsync(s.times, times, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
         s.kind = kind; s.nt = nt;
         return TRM_OK;
@@ -385,7 +383,7 @@ struct Handle : HandleBase {
         for (int i = 0; i < TRM_IN_COUNT; ++i) {
             InputDesc<NF>& d = a.in[i]; const Input& s = in[i];
             d.kind = s.kind; d.nt = s.nt; d.cval = (NF)s.cval; d.period = s.period; d.lo = s.lo; d.hi = s.hi;
-            d.a = s.a; d.b = s.b; d.c = s.c; d.times = s.times; d.ld = ld;
+            d.a = s.a; d.b = s.b; d.c = s.c; d.ld = ld;
         }
         a.Kf = Kf;
         a.Ts = land2d[0]; a.G = land2d[1]; a.SWup = land2d[2]; a.LWup = land2d[3]; a.Rnet = land2d[4];
@@ -394,6 +392,41 @@ struct Handle : HandleBase {
         for (int i = 0; i < VF_COUNT; ++i) a.veg2d[i] = veg2d[i];
         // ForwardEuler / auxiliary evaluations: evaluate on, and update, the model state in place
         for (int i = 0; i < 3; ++i) { a.vx[i] = veg2d[i]; a.vb[i] = veg2d[i]; a.vy[i] = veg2d[i]; a.vk1[i] = nullptr; a.vok1[i] = nullptr; }
+    }
+    // Position of clock time t on the time axis of a table input, with the reference's two update rules:
+    // TABLE  = FieldTimeSeries[Time(t)] (input_sources.jl:165-171): flat up to the first / from the last node, else the
+    //          bracket [n1, n2) with n2 = first node after t ;
+    // RASTER = update_from_raster! (TerrariumRastersExt.jl:96-121): searchsorted ; on a node the node itself, beyond the
+    //          axis the nearest end.
+    static void bracket(const Input& s, double t, TimeBracket& k) {
+        const std::vector<double>& tt = s.times;
+        const int nt = (int)tt.size();
+        k = TimeBracket{0, 0, 1, 0, 0.0, 1.0};
+        if (nt == 0) return;
+        if (s.kind == TRM_SRC_TABLE) {
+            if (t <= tt.front()) { k.i1 = 0; return; }
+            if (t >= tt.back()) { k.i1 = nt - 1; return; }
+            const int n2 = (int)(std::upper_bound(tt.begin(), tt.end(), t) - tt.begin()), n1 = n2 - 1;
+            k.i1 = n1; k.i2 = n2; k.flat = 0; k.e = t - tt[n1]; k.dtt = tt[n2] - tt[n1];
+        } else {
+            const int right = (int)(std::lower_bound(tt.begin(), tt.end(), t) - tt.begin()) + 1;   // first(searchsorted), 1-based
+            const int left = (int)(std::upper_bound(tt.begin(), tt.end(), t) - tt.begin());        // last(searchsorted), 1-based
+            if (left >= 1 && right <= nt && right > left) {
+                k.i1 = left - 1; k.i2 = right - 1; k.flat = 0; k.e = t - tt[left - 1]; k.dtt = tt[right - 1] - tt[left - 1];
+            } else if (left >= 1 && right <= nt) {
+                k.i1 = right - 1;                       // exactly on a node (dt = 0 in the reference: the node value)
+            } else {
+                k.i1 = std::min(right, nt) - 1;          // beyond either end: flat
+            }
+        }
+    }
+    // call after t_x / t_b are set: table inputs get the brackets of both clock times
+    void set_times(StageArgs<NF>& a) {
+        for (int i = 0; i < TRM_IN_COUNT; ++i) {
+            if (in[i].kind != TRM_SRC_TABLE && in[i].kind != TRM_SRC_RASTER) continue;
+            bracket(in[i], (double)a.t_x, a.in[i].br[0]);
+            bracket(in[i], (double)a.t_b, a.in[i].br[1]);
+        }
     }
     void x_state(StageArgs<NF>& a) { a.xU = U; a.xS = S; a.xT = T; a.xL = Lq; a.xP = P; a.xWt = Wt; a.bU = U; a.bS = S; a.bSx = Sx; }
     void y_state(StageArgs<NF>& a) { a.yU = U; a.yS = S; a.yT = T; a.yL = Lq; a.yP = P; a.yWt = Wt; a.ySx = Sx; }
@@ -520,6 +553,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             a.mode = MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
             const bool load = aux_stale || force_load;
             a.load_aux = load ? 1 : 0;
+            set_times(a);
             if (split) { if (int rc = launch_surface(0, a)) return rc; }
             if (int rc = launch_euler(a, load ? 1 : 0)) return rc;
         } else {       // heun.jl:37-71
@@ -527,6 +561,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
             for (int i = 0; i < 3; ++i) { a.vy[i] = gveg[i]; a.vok1[i] = tveg[i]; }
             a.ybeta = gbeta;
+            set_times(a);
             if (split) { if (int rc = launch_surface(0, a)) return rc; }
             if (int rc = launch_euler(a, a.load_aux)) return rc;
             StageArgs<NF> b; base_args(b);
@@ -535,6 +570,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             for (int i = 0; i < 3; ++i) { b.vx[i] = gveg[i]; b.vk1[i] = tveg[i]; }
             b.xbeta = gbeta;
             y_state(b);
+            set_times(b);
             // stage 2 only re-evaluates the vegetation block (k2 of canopy water, vegetation carbon and area fraction);
             // the bare-ground surface block of the stage state has no effect on the step (heun.jl:63-66)
             if (split && veg) { if (int rc = launch_surface(0, b)) return rc; }
@@ -700,6 +736,8 @@ template <class NF> int Handle<NF>::get_input(int id, void* host, int64_t count)
     CU(cudaSetDevice(device));
     StageArgs<NF> a; base_args(a);
     if (int rc = ring_buffer((size_t)nc)) return rc;
+    a.t_x = a.t_b = (NF)t_inputs;
+    set_times(a);
     eval_input_kernel<NF><<<(unsigned)((nc + 127) / 128), 128, 0, stream>>>(nc, a.in[id], (NF)t_inputs, ring_buf);
     ++launches;
     CU(cudaGetLastError());
@@ -715,6 +753,7 @@ template <class NF> int Handle<NF>::aux() {
     // compute_auxiliary! does not call update_inputs!: the input fields still hold the values of the last
     // update_state! (start of the last step), which is what timestep!(...; finalize = true) / run! see.
     a.mode = MODE_AUX; a.load_aux = 1; a.t_x = (NF)t_inputs; a.t_b = a.t_x; a.dt = 0; x_state(a);
+    set_times(a);
     if (int rc = launch(VAR_GENERIC, a)) return rc;
     CU(cudaStreamSynchronize(stream));
     return TRM_OK;
@@ -729,6 +768,7 @@ template <class NF> int Handle<NF>::tendencies() {
     if (richards && !tS) { if (int rc = dalloc(&tS, n3)) return rc; }
     StageArgs<NF> a; base_args(a);
     a.mode = MODE_TEND; a.load_aux = 1; a.t_x = (NF)time; a.t_b = a.t_x; a.dt = 0; x_state(a);
+    set_times(a);
     t_inputs = time;
     a.oTU = tU; a.oTS = tS;
     if (int rc = launch(VAR_GENERIC, a)) return rc;
