@@ -102,3 +102,31 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".jl")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_integrator" not in text and "libterrarium_oracle" not in text and "orc_" not in text, f
+
+
+def test_enum_values_match_header():
+    """Field / input / source / option codes of the ctypes mirror equal the header's enumerators (compiled, not parsed)."""
+    a = trm.abi
+    pairs = {
+        "TRM_F_INTERNAL_ENERGY": a.FIELD_IDS["internal_energy"], "TRM_F_SURFACE_RUNOFF": a.FIELD_IDS["surface_runoff"],
+        "TRM_F_TEND_SATURATION": a.FIELD_IDS["tendency_saturation_water_ice"], "TRM_F_CARBON_VEGETATION": a.FIELD_IDS["carbon_vegetation"],
+        "TRM_F_NET_ASSIMILATION": a.FIELD_IDS["net_assimilation"], "TRM_F_TRANSPIRATION": a.FIELD_IDS["transpiration"],
+        "TRM_F_PLANT_AVAILABLE_WATER": a.FIELD_IDS["plant_available_water"], "TRM_F_ROOT_FRACTION": a.FIELD_IDS["root_fraction"],
+        "TRM_F_COUNT": max(a.FIELD_IDS.values()) + 1,
+        "TRM_IN_AIR_TEMPERATURE": a.TRM_IN_AIR_TEMPERATURE, "TRM_IN_CO2": a.TRM_IN_CO2, "TRM_IN_SKIN_TEMPERATURE": a.TRM_IN_SKIN_TEMPERATURE,
+        "TRM_IN_SAI": a.TRM_IN_SAI, "TRM_IN_DAILY_LEAF_RESPIRATION": a.TRM_IN_DAILY_LEAF_RESPIRATION, "TRM_IN_COUNT": a.TRM_IN_COUNT,
+        "TRM_SRC_TABLE": a.TRM_SRC_TABLE, "TRM_SRC_RASTER": a.TRM_SRC_RASTER, "TRM_BC_FLUX": a.TRM_BC_FLUX, "TRM_BC_NSLOTS": a.TRM_BC_NSLOTS,
+        "TRM_VEG_CARBON": a.TRM_VEG_CARBON, "TRM_GROUND_RES_SOIL_MOISTURE": a.TRM_GROUND_RES_SOIL_MOISTURE, "TRM_MATH_FAST": a.TRM_MATH_FAST,
+        "TRM_SKIN_PRESCRIBED": a.TRM_SKIN_PRESCRIBED, "TRM_ABI_VERSION": a.TRM_ABI_VERSION, "TRM_MAX_NZ": a.TRM_MAX_NZ,
+    }
+    names = sorted(pairs)
+    prog = '#include <stdio.h>\n#include "terrarium_b200.h"\nint main(void) {\n' + "".join(f'    printf("%d\\n", (int){n});\n' for n in names) + "    return 0;\n}\n"
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "enums.c"), os.path.join(d, "enums")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
+    assert dict(zip(names, got)) == pairs
+    # the field-id table is dense and in header order for the vegetation block
+    veg = [a.FIELD_IDS[n] for n in a.VEGETATION_FIELDS]
+    assert veg == list(range(21, 43))
