@@ -63,6 +63,12 @@ def test_defaults_match_the_reference_package_defaults():
     assert (p.mineral_porosity, p.K_sat, p.tau_r, p.albedo, p.emissivity) == (0.49, 1.0e-5, 3600.0, 0.3, 0.97)
     assert list(p.kappa) == [0.57, 2.2, 0.025, 3.8, 0.25]
     assert list(p.heatcap) == [4.2e6, 1.9e6, 1.25e3, 2.0e6, 2.5e6]
+    # vegetation / canopy defaults of the library equal the host mirror's dataclass defaults (= the reference's)
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_max=1.0, N=4), 1)
+    q = trm.build_params(trm.LandModel(grid))
+    for name in trm.abi.VEGETATION_PARAMS:
+        assert getattr(p, name) == getattr(q, name), name
+    assert (p.tau25, p.g1, p.SLA, p.w_can_max, p.C_can, p.field_capacity) == (2600.0, 2.3, 10.0, 2.0e-4, 0.006, 0.25)
 
 
 def test_argument_validation_needs_no_device():
