@@ -67,7 +67,10 @@ def test_defaults_match_the_reference_package_defaults():
     grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_max=1.0, N=4), 1)
     q = trm.build_params(trm.LandModel(grid))
     for name in trm.abi.VEGETATION_PARAMS:
+        if name in ("field_capacity", "wilting_point"):
+            continue   # the library default is ConstantSoilHydraulics'; LandModel(grid) has SoilHydraulicsSURFEX (clay = 0 -> 0)
         assert getattr(p, name) == getattr(q, name), name
+    assert (q.field_capacity, q.wilting_point) == (0.0, 0.0)
     assert (p.tau25, p.g1, p.SLA, p.w_can_max, p.C_can, p.field_capacity) == (2600.0, 2.3, 10.0, 2.0e-4, 0.006, 0.25)
 
 
