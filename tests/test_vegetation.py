@@ -437,3 +437,32 @@ def test_vegetated_land_large_domain_properties():
     for name in ("temperature", "saturation_water_ice", "carbon_vegetation", "ground_heat_flux", "transpiration", "net_assimilation"):
         a, b_ = getattr(cu.state, name).numpy()[..., :sub], getattr(orc.state, name).numpy()
         assert max_scaled_err(a, b_) <= 1e-9, name
+
+
+# test/surface_hydrology/canopy_interception_tests.jl, canopy_evapotranspiration_tests.jl: edge properties of the scalar rules
+@pytest.mark.parametrize("engine", ENGINES)
+def test_canopy_edge_properties(engine):
+    n = 6
+    #            no rain   no leaves   wet canopy   negative store   dense canopy   open stomata
+    rain = np.array([0.0,   1.0e-8,     1.0e-8,      1.0e-8,          1.0e-8,        1.0e-8])
+    Cv   = np.array([2.2,   0.0,        2.2,         2.2,             8.8,           2.2])      # LAI = C_veg / 2.2
+    SAI  = np.array([0.5,   0.0,        0.5,         0.5,             1.0,           0.5])
+    w    = np.array([0.0,   1.0e-4,     1.0e-4,      -1.0,            1.0e-4,        0.0])
+    An0  = np.array([0.0,   0.0,        0.0,         0.0,             0.0,           5.0e-4])
+    integ = veg_land(engine, ncol=n, inputs={"rainfall": rain, "SAI": SAI, "windspeed": 1.0, "surface_shortwave_down": 0.0},
+                     inits={"carbon_vegetation": Cv, "canopy_water": w, "net_assimilation": An0, "temperature": 8.0, "skin_temperature": 9.0})
+    integ.step(60.0, 1)
+    st = integ.state
+    I, R, f, rg = (st.canopy_water_interception.numpy(), st.canopy_water_removal.numpy(), st.saturation_canopy_water.numpy(),
+                   st.rainfall_ground.numpy())
+    assert I[0] == 0 and I[1] == 0 and np.all((I[2:] > 0) & (I[2:] < rain[2:]))          # no rain / no canopy -> no interception
+    assert f[0] == 0 and f[1] == 0 and 0 < f[2] < 1 and f[4] < f[2]                      # a denser canopy is less saturated
+    assert R[0] == 0 and R[3] == 0 and R[2] > 0                                          # removal of a non-positive store is zero
+    np.testing.assert_array_equal(rg, rain - I + R)
+    tr = st.transpiration.numpy()
+    assert np.all(np.isfinite(tr)) and np.all(tr > 0) and tr[5] > 5 * tr[0]
+    assert 0 < tr[1] < 1.0e-8   # no conductance at all (no leaves): r_s = 1 / sqrt(eps), tiny but positive (canopy_evapotranspiration.jl:51-56)
+    Ec, Eg = st.evaporation_canopy.numpy(), st.evaporation_ground.numpy()
+    assert Ec[0] == 0 and Ec[2] > 0 and np.all(Eg > 0) and Eg[4] < Eg[2]                 # more leaves -> larger ground-canopy resistance
+    # the canopy store tendency: interception - evaporation - removal
+    np.testing.assert_allclose(st.canopy_water.numpy(), w + 60.0 * (I - Ec - R), rtol=1e-12, atol=1e-20)
