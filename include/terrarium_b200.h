@@ -371,6 +371,12 @@ int trm_last_step_ms(trm_handle* h, float* ms);
 int trm_set_input_field_async(trm_handle* h, int input_id, const void* pinned_host_values /* [ncol] NF */);
 int trm_step_async(trm_handle* h, double dt, int64_t nsteps);
 int trm_get_field_async(trm_handle* h, int field_id, void* pinned_host, int64_t count);
+/* Time-averaged output (Oceananigans AveragedTimeInterval / WindowedTimeAverage): trm_accumulate adds weight * field to
+ * a per-field accumulator owned by the handle (allocated and zeroed on first use; weight = the step's dt);
+ * trm_get_accumulated returns scale * accumulator (scale = 1 / window length) in the layout of trm_get_field and, if
+ * `reset` is non-zero, zeroes it for the next window. */
+int trm_accumulate(trm_handle* h, int field_id, double weight);
+int trm_get_accumulated(trm_handle* h, int field_id, void* host, int64_t count, double scale, int32_t reset);
 /* Page-locked host memory for the asynchronous entry points (cudaHostAlloc / cudaFreeHost), so that a caller without
  * a CUDA binding of its own (the Julia / Python host side) can own pinned buffers. */
 int trm_host_alloc(int64_t bytes, void** host);

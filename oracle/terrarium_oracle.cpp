@@ -911,6 +911,25 @@ struct Oracle {
         }
         return fail(TRM_ERR_INVALID, "get_field: unknown field");
     }
+    // time-averaged output: per-field accumulators in the host layout of get_field
+    std::vector<std::vector<double>> acc = std::vector<std::vector<double>>(TRM_F_COUNT);
+    int accumulate(int id, double w) {
+        if (id < 0 || id >= TRM_F_COUNT) return fail(TRM_ERR_INVALID, "accumulate: bad field id");
+        int64_t count = field3(id) ? (int64_t)nz * nc : (id == TRM_F_HYDRAULIC_CONDUCTIVITY ? (int64_t)(nz + 1) * nc : nc);
+        std::vector<NF> tmp((size_t)count);
+        if (int rc = get_field(id, tmp.data(), count)) return rc;
+        auto& a = acc[id];
+        if ((int64_t)a.size() != count) a.assign((size_t)count, 0.0);
+        for (int64_t i = 0; i < count; ++i) a[(size_t)i] = (double)(NF)((NF)a[(size_t)i] + (NF)w * tmp[(size_t)i]);
+        return TRM_OK;
+    }
+    int get_accumulated(int id, void* host, int64_t count, double scale, int reset) {
+        if (id < 0 || id >= TRM_F_COUNT || (int64_t)acc[id].size() != count) return fail(TRM_ERR_INVALID, "get_accumulated: nothing accumulated for this field / wrong count");
+        NF* h = (NF*)host;
+        for (int64_t i = 0; i < count; ++i) h[i] = (NF)scale * (NF)acc[id][(size_t)i];
+        if (reset) std::fill(acc[id].begin(), acc[id].end(), 0.0);
+        return TRM_OK;
+    }
     int diagnostics(trm_diag* d) {
         double e = 0, w = 0, tmin = INFINITY, tmax = -INFINITY, smin = INFINITY, smax = -INFINITY, nan = 0;
         for (int64_t c = 0; c < nc; ++c) {
@@ -1036,6 +1055,11 @@ int orc_set_input_raster(trm_handle* h_, int id, int32_t nt, const double* times
 int orc_get_input(trm_handle* h, int id, void* host, int64_t count) {
     if (id < 0 || id >= TRM_IN_COUNT || !host) return fail(TRM_ERR_INVALID, "bad input id");
     return DISPATCH((Handle*)h, get_input(id, host, count));
+}
+int orc_accumulate(trm_handle* h, int id, double w) { return DISPATCH((Handle*)h, accumulate(id, w)); }
+int orc_get_accumulated(trm_handle* h, int id, void* host, int64_t count, double scale, int32_t reset) {
+    if (!host) return fail(TRM_ERR_INVALID, "null argument");
+    return DISPATCH((Handle*)h, get_accumulated(id, host, count, scale, reset));
 }
 int orc_initialize(trm_handle* h) { return DISPATCH((Handle*)h, initialize()); }
 int orc_step(trm_handle* h, double dt, int64_t n) { return DISPATCH((Handle*)h, step(dt, n)); }

@@ -10,7 +10,7 @@ from .grids import (B200, ColumnGrid, ColumnRingGrid, ExponentialSpacing, Prescr
 from .models import *  # noqa: F401,F403  (configuration types mirror the reference's exported names)
 from .integrator import (Field, ModelIntegrator, StateVariables, current_time, get_steps, initialize, interior, run, set_,
                          timestep)
-from .simulation import (Callback, FieldTimeSeries, IterationInterval, NetCDFWriter, Simulation, TimeInterval,
+from .simulation import (AveragedTimeInterval, Callback, FieldTimeSeries, IterationInterval, NetCDFWriter, Simulation, TimeInterval,
                          run_simulation)
 from ._lib import LIB_PATH, cuda_library
 

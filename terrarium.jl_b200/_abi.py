@@ -148,6 +148,8 @@ SIGNATURES = {
     "set_input_field_async": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "step_async": (C.c_int, [_H, C.c_double, C.c_int64]),
     "get_field_async": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
+    "accumulate": (C.c_int, [_H, C.c_int, C.c_double]),
+    "get_accumulated": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int32]),
     "host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "host_free": (C.c_int, [C.c_void_p]),
     "set_ring_index": (C.c_int, [_H, C.POINTER(C.c_int64), C.c_int64]),

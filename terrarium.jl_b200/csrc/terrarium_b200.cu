@@ -41,6 +41,8 @@ struct HandleBase {
     virtual int set_input_field(int id, const void* v) = 0;
     virtual int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) = 0;
     virtual int get_input(int id, void* host, int64_t count) = 0;
+    virtual int accumulate(int id, double w) = 0;
+    virtual int get_accumulated(int id, void* host, int64_t count, double scale, int reset) = 0;
     virtual int set_input_table(int id, int nt, const double* times, const void* values, int kind = TRM_SRC_TABLE) = 0;
     virtual int input_ptr(int id, void** p) = 0;
     virtual int initialize() = 0;
@@ -360,6 +362,9 @@ struct Handle : HandleBase {
         return TRM_OK;
     }
     int get_input(int id, void* host, int64_t count) override;
+    int accumulate(int id, double w) override;
+    int get_accumulated(int id, void* host, int64_t count, double scale, int reset) override;
+    NF* acc[TRM_F_COUNT] = {nullptr};   // time-average accumulators [rows][ld], allocated on first use
     int input_ptr(int id, void** q) override {
         CU(cudaSetDevice(device));
         if (in[id].kind == TRM_SRC_TABLE || in[id].kind == TRM_SRC_RASTER) return fail(TRM_ERR_STATE, "input_ptr: input is a time series table");
@@ -746,6 +751,39 @@ template <class NF> int Handle<NF>::get_input(int id, void* host, int64_t count)
     return TRM_OK;
 }
 
+// time-averaged output: acc += w * field (one element per thread over the padded rows), scaled read-back
+template <class NF>
+__global__ void axpy_kernel(int64_t n, NF w, const NF* __restrict__ x, NF* __restrict__ y, int overwrite) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = overwrite ? w * x[i] : y[i] + w * x[i];
+}
+template <class NF> int Handle<NF>::accumulate(int id, double w) {
+    FieldRef f = field(id);
+    if (!f.ptr) return fail(TRM_ERR_INVALID, "accumulate: unknown field or field not defined for this model");
+    CU(cudaSetDevice(device));
+    const int64_t n = (int64_t)f.nrows * ld;
+    if (!acc[id]) { if (int rc = dalloc(&acc[id], (size_t)n)) return rc; }
+    axpy_kernel<NF><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, (NF)w, f.ptr, acc[id], 0);
+    ++launches;
+    CU(cudaGetLastError());
+    return TRM_OK;
+}
+template <class NF> int Handle<NF>::get_accumulated(int id, void* host, int64_t count, double scale, int reset) {
+    FieldRef f = field(id);
+    if (!f.ptr || !acc[id]) return fail(TRM_ERR_INVALID, "get_accumulated: nothing accumulated for this field");
+    if (count != (int64_t)f.nrows * nc) return fail(TRM_ERR_INVALID, "get_accumulated: wrong element count");
+    CU(cudaSetDevice(device));
+    const int64_t n = (int64_t)f.nrows * ld;
+    if (int rc = ring_buffer((size_t)n)) return rc;
+    axpy_kernel<NF><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, (NF)scale, acc[id], ring_buf, 1);
+    ++launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2DAsync(host, nc * sizeof(NF), ring_buf, ld * sizeof(NF), nc * sizeof(NF), f.nrows, cudaMemcpyDeviceToHost, stream));
+    if (reset) CU(cudaMemsetAsync(acc[id], 0, (size_t)n * sizeof(NF), stream));
+    CU(cudaStreamSynchronize(stream));
+    return TRM_OK;
+}
+
 template <class NF> int Handle<NF>::aux() {
     if (!initialized) return fail(TRM_ERR_STATE, "trm_compute_auxiliary before trm_initialize");
     CU(cudaSetDevice(device));
@@ -884,6 +922,11 @@ int64_t trm_launch_count(trm_handle* h) { return h ? H(h)->launches : 0; }
 int trm_last_step_ms(trm_handle* h, float* ms) { if (!h || !ms) return fail(TRM_ERR_INVALID, "null argument"); *ms = H(h)->last_ms; return TRM_OK; }
 int trm_set_input_field_async(trm_handle* h, int id, const void* v) { if (!h || !v || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_field_async(id, v); }
 int trm_get_field_async(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field_async(id, host, count); }
+int trm_accumulate(trm_handle* h, int id, double w) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->accumulate(id, w); }
+int trm_get_accumulated(trm_handle* h, int id, void* host, int64_t count, double scale, int32_t reset) {
+    if (!h || !host) return fail(TRM_ERR_INVALID, "null argument");
+    return H(h)->get_accumulated(id, host, count, scale, reset);
+}
 int trm_host_alloc(int64_t bytes, void** host) {
     if (!host || bytes <= 0) return fail(TRM_ERR_INVALID, "trm_host_alloc: bad arguments");
     cudaError_t e = cudaHostAlloc(host, (size_t)bytes, cudaHostAllocPortable);

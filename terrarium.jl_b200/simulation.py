@@ -56,6 +56,14 @@ class TimeInterval:
         return False
 
 
+class AveragedTimeInterval(TimeInterval):
+    """``AveragedTimeInterval(interval)`` (window = interval, stride = 1): the writer stores the time average over the
+    window that ends at each output time, ``sum_k field(t_k) dt_k / sum_k dt_k`` with the field after every step
+    (Oceananigans' ``WindowedTimeAverage`` accumulates the same right-endpoint sum). The sum lives on the device
+    (``trm_accumulate``); the record written at the start of the run is the instantaneous field."""
+    averaged = True
+
+
 @dataclass
 class IterationInterval:
     interval: int
@@ -140,10 +148,29 @@ class NetCDFWriter:
         self._pending = None       # (time, {name: pinned buffer}) downloaded asynchronously, not yet written
         self._buffers = []         # two sets of pinned buffers, used alternately
         self._async = hasattr(integrator._lib, "get_field_async") and hasattr(integrator._lib, "host_alloc")
+        self.averaged = bool(getattr(schedule, "averaged", False))
+        self._elapsed = 0.0        # length of the averaging window accumulated so far
+
+    def accumulate(self, dt: float):
+        """Add ``dt * field`` of every output to its device-side accumulator (time-averaged writers, after each step)."""
+        lib, h = self.integrator._lib, self.integrator._h
+        for n, f in self.fields.items():
+            lib.check(lib.accumulate(h, f.id, float(dt)), f"accumulate({n})")
+        self._elapsed += float(dt)
 
     # -- snapshot now (enqueue), write later -------------------------------------------------
     def snapshot(self, time: float):
         integ, lib = self.integrator, self.integrator._lib
+        if self.averaged and self._elapsed > 0:
+            self.flush()   # (the instantaneous first record may still be in flight)
+            arrays = {}
+            for n, f in self.fields.items():
+                out = np.empty(f.shape, dtype=integ.nf)
+                lib.check(lib.get_accumulated(integ._h, f.id, out.ctypes.data_as(C.c_void_p), out.size, 1.0 / self._elapsed, 1), f"get_accumulated({n})")
+                arrays[n] = out
+            self._elapsed = 0.0
+            self._write(time, arrays)
+            return
         if not self._async:   # engine without the asynchronous entry points (the CPU checker in tests)
             self._write(time, {n: f.numpy() for n, f in self.fields.items()})
             return
@@ -246,7 +273,7 @@ class Simulation:
     def _observe(self, t: float, it: int, first: bool = False):
         due_w = [w for w in self.output_writers.values() if first or w.schedule.actuate(t, it)]
         due_c = [c for c in self.callbacks.values() if first or c.schedule.actuate(t, it)]
-        if (due_w or due_c) and not self.finalize_every_step:
+        if (due_w or due_c) and not self.finalize_every_step and not any(w.averaged for w in self.output_writers.values()):
             self.integrator.compute_auxiliary()
         for w in due_w:
             w.snapshot(t)
@@ -263,16 +290,25 @@ class Simulation:
         integ.compute_auxiliary()
         self._observe(t, it, first=True)
         lib = integ._lib
-        use_async = hasattr(lib, "step_async") and not integ._host_callbacks and not self.finalize_every_step
+        averaging = [w for w in self.output_writers.values() if w.averaged]
+        single = self.finalize_every_step or bool(averaging)   # one step at a time, auxiliaries current after each
+
+        def after_step(dt_step):
+            if single:
+                integ.compute_auxiliary()
+            for w in averaging:
+                w.accumulate(dt_step)
+
+        use_async = hasattr(lib, "step_async") and not integ._host_callbacks and not single
         while not self._done(t, it):
             n_max, t_next = self._chunk(t, it)
             n_time = math.floor((t_next - t) / self.dt + 1e-9) if math.isfinite(t_next) else math.inf
             n_full = int(min(n_max, n_time))   # (one of the two is finite: the simulation has a stop criterion)
             if n_full >= 1:
-                if self.finalize_every_step:
+                if single:
                     for _ in range(n_full):
                         integ.step(self.dt, 1)
-                        integ.compute_auxiliary()
+                        after_step(self.dt)
                 elif use_async:
                     lib.check(lib.step_async(integ._h, float(self.dt), n_full), "step_async")
                 else:
@@ -280,20 +316,18 @@ class Simulation:
                 self.steps_taken += n_full
             elif self.align_time_step and math.isfinite(t_next) and t_next - t > 1e-9 * max(1.0, abs(t_next)):
                 integ.step(t_next - t, 1)   # shortened step that lands on the scheduled time
-                if self.finalize_every_step:
-                    integ.compute_auxiliary()
+                after_step(t_next - t)
                 self.steps_taken += 1
             else:   # an unaligned event time with alignment switched off: step over it
                 integ.step(self.dt, 1)
-                if self.finalize_every_step:
-                    integ.compute_auxiliary()
+                after_step(self.dt)
                 self.steps_taken += 1
             t, it = integ.clock.time, integ.clock.iteration
             self._observe(t, it)
         integ.synchronize()
         for w in self.output_writers.values():
             w.flush()
-        if not self.finalize_every_step:
+        if not single:
             integ.compute_auxiliary()
         return self
 

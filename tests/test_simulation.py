@@ -80,3 +80,31 @@ def test_vegetated_simulation_equals_timestep_loop(engine, tmp_path):
         assert np.array_equal(getattr(a.state, name).numpy(), getattr(b.state, name).numpy()), name
     g = trm.FieldTimeSeries(str(tmp_path / "v.nc"), "canopy_water_conductance")
     assert len(g) == 4 and np.array_equal(g[-1], b.state.canopy_water_conductance.numpy())
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_averaged_time_interval(engine, tmp_path):
+    """AveragedTimeInterval: every record is the time average of the fields after each step of the window that ends at
+    the output time (device-side accumulator), the first record the instantaneous initial field."""
+    integ = synthetic_soil_case(engine, 9, dt=300.0)
+    ref = synthetic_soil_case(engine, 9, dt=300.0)
+    sim = trm.Simulation(integ, stop_time=3600.0, dt=300.0)
+    path = str(tmp_path / "avg.nc")
+    sim.output_writers["avg"] = trm.NetCDFWriter(integ, ["temperature", "ground_temperature", "hydraulic_conductivity"], filename=path,
+                                                 schedule=trm.AveragedTimeInterval(1800.0))
+    sim.run(); sim.close()
+    T, Tg, K = (trm.FieldTimeSeries(path, n) for n in ("temperature", "ground_temperature", "hydraulic_conductivity"))
+    assert list(T.times) == [0.0, 1800.0, 3600.0]
+    ref.compute_auxiliary()
+    assert np.array_equal(T[0], ref.state.temperature.numpy()) and np.array_equal(K[0], ref.state.hydraulic_conductivity.numpy())
+    for rec in (1, 2):
+        accT, accG, accK = 0.0, 0.0, 0.0
+        for _ in range(6):
+            trm.timestep(ref, 300.0)
+            accT = accT + 300.0 * ref.state.temperature.numpy()
+            accG = accG + 300.0 * ref.state.ground_temperature.numpy()
+            accK = accK + 300.0 * ref.state.hydraulic_conductivity.numpy()
+        np.testing.assert_allclose(T[rec], accT / 1800.0, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(Tg[rec], accG / 1800.0, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(K[rec], accK / 1800.0, rtol=1e-13)
+    assert np.array_equal(integ.state.temperature.numpy(), ref.state.temperature.numpy())
