@@ -4,6 +4,7 @@ The directory name contains a dot, so the package is imported through the ``terr
 shim at the repository root (``import terrarium_jl_b200 as trm``).
 """
 from . import _abi as abi
+from . import netcdf4
 from ._abi import TerrariumError
 from .grids import (B200, ColumnGrid, ColumnRingGrid, ExponentialSpacing, PrescribedSpacing, UniformSpacing,
                     get_spacing, num_layers)

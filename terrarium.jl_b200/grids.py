@@ -170,6 +170,36 @@ class ColumnRingGrid(ColumnGrid):
         self.lon = None if lon is None else np.asarray(lon, dtype=np.float64).ravel()
         self.lat = None if lat is None else np.asarray(lat, dtype=np.float64).ravel()
 
+    @classmethod
+    def from_land_sea_mask(cls, *args, path: str, variable: str = "lsm", threshold: float = 0.5):
+        """``ColumnRingGrid(arch, NF, spacing, rings, land_sea_frac .> 0.5)`` from a land fraction raster file as in
+        ``examples/simulations/soil_heat_global.jl:29-38``: the raster (``[time = 1,] lat, lon``, north to south) is
+        converted to the grid's number format first, its storage order is the ring order of a full grid
+        (``FullGaussianGrid(Matrix(raster), input_as = Matrix)``), points with a land fraction above ``threshold``
+        become columns; ``lon`` / ``lat`` of the ring points are kept in radians as ``RingGrids.get_lonlats`` gives them
+        (:39). ``args`` = ``([arch,] [NF,] spacing)``; reads NetCDF-3 and NetCDF-4 files."""
+        from .models import RasterInputSource
+        nf = next((a for a in args if not isinstance(a, B200) and not hasattr(a, "thicknesses")), np.float32)
+        import warnings
+        from . import netcdf4
+        lon = lat = None
+        src = RasterInputSource.from_netcdf(path, variable)
+        frac = np.asarray(src.values, dtype=np.float64)
+        if frac.ndim == 2:
+            if frac.shape[0] != 1:
+                raise ValueError(f"{path}:{variable} has {frac.shape[0]} time slices; a land-sea mask has one (dropdims over Ti)")
+            frac = frac[0]
+        if netcdf4.is_hdf5(path):
+            with netcdf4.File(path) as f:
+                dims = f.variables[variable].dimensions[-2:]
+                if all(d in f.variables for d in dims):
+                    la, lo = (np.asarray(f.variables[d].read(), dtype=np.float64) for d in dims)
+                    lat, lon = np.deg2rad(np.repeat(la, lo.size)), np.deg2rad(np.tile(lo, la.size))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mask = frac.astype(nf) > nf(threshold)
+        return cls(*args, mask=mask, lon=lon, lat=lat)
+
     def xnodes(self) -> np.ndarray:
         """x in (1, Nh): x_i = 1 + (i - 1/2)(Nh - 1)/Nh so that round(x_i) == i (column_ring_grid.jl:54)."""
         n = self.Nc

@@ -420,19 +420,52 @@ class RasterInputSource:
     reftime: float = 0.0
 
     @classmethod
-    def from_netcdf(cls, path: str, variable: str, time: str = "time", reftime: float = 0.0):
-        """Read ``variable[time, ...]`` from a NetCDF-3 (classic / 64-bit offset) file; the trailing dimensions are
-        flattened in storage order to the ring-grid points. NetCDF-4 / HDF5 files need a library this image lacks."""
-        from scipy.io import netcdf_file
-        with netcdf_file(path, "r", mmap=False) as f:
-            var = f.variables[variable]
-            data = np.array(var[:], dtype=np.float64)
-            scale, offset = getattr(var, "scale_factor", 1.0), getattr(var, "add_offset", 0.0)
-            data = data * scale + offset
-            has_time = time in f.variables and var.dimensions and var.dimensions[0] == time
-            times = np.array(f.variables[time][:], dtype=np.float64) if has_time else None
+    def from_netcdf(cls, path: str, variable: str, time: str = "time", reftime: Optional[float] = 0.0, decode_times: bool = False):
+        """Read ``variable[time, ...]`` from a NetCDF file; the trailing dimensions are flattened in storage order to the
+        ring-grid points (a full Gaussian / lon-lat raster stored ``[lat, lon]`` north to south is in RingGrids order).
+        NetCDF-3 (classic / 64-bit offset) goes through ``scipy.io.netcdf_file``, NetCDF-4 / HDF5 through the decoder in
+        ``netcdf4.py``. ``_FillValue`` / ``missing_value`` become NaN, ``scale_factor`` / ``add_offset`` are applied.
+        ``decode_times`` converts the time axis to seconds with the CF ``units`` attribute (``"hours since ..."``);
+        ``reftime = None`` takes the first time of the axis (``default_reftime``, TerrariumRastersExt.jl:130-133)."""
+        from . import netcdf4
+        if netcdf4.is_hdf5(path):
+            with netcdf4.File(path) as f:
+                var = f.variables[variable]
+                data = var.scaled(np.float64)
+                has_time = bool(var.dimensions) and var.dimensions[0] == time and time in f.variables
+                times = np.array(f.variables[time].read(), dtype=np.float64) if has_time else None
+                units = f.variables[time].attrs.get("units") if has_time else None
+        else:
+            from scipy.io import netcdf_file
+            with netcdf_file(path, "r", mmap=False) as f:
+                var = f.variables[variable]
+                raw = np.array(var[:])
+                data = raw.astype(np.float64)
+                for key in ("_FillValue", "missing_value"):
+                    if hasattr(var, key):
+                        data[raw == np.asarray(getattr(var, key)).reshape(-1)[0]] = np.nan
+                scale, offset = getattr(var, "scale_factor", 1.0), getattr(var, "add_offset", 0.0)
+                data = data * scale + offset
+                has_time = time in f.variables and var.dimensions and var.dimensions[0] == time
+                times = np.array(f.variables[time][:], dtype=np.float64) if has_time else None
+                units = getattr(f.variables[time], "units", None) if has_time else None
+                units = units.decode() if isinstance(units, bytes) else units
+        if has_time and decode_times:
+            times = times * cf_time_unit_seconds(units)
+        if has_time and reftime is None:
+            reftime = float(times[0])
         data = data.reshape(data.shape[0], -1) if has_time else data.reshape(-1)
-        return cls(values=data, times=times, reftime=reftime)
+        return cls(values=data, times=times, reftime=0.0 if reftime is None else reftime)
+
+
+def cf_time_unit_seconds(units: Optional[str]) -> float:
+    """Seconds per unit of a CF time axis (``"<unit> since <epoch>"``)."""
+    unit = (units or "seconds").split()[0].lower()
+    table = {"s": 1.0, "sec": 1.0, "secs": 1.0, "second": 1.0, "seconds": 1.0, "min": 60.0, "minute": 60.0, "minutes": 60.0,
+             "h": 3600.0, "hr": 3600.0, "hour": 3600.0, "hours": 3600.0, "d": 86400.0, "day": 86400.0, "days": 86400.0}
+    if unit not in table:
+        raise ValueError(f"unsupported CF time unit {units!r}")
+    return table[unit]
 
 
 def InputSource(grid, data, name: Optional[str] = None, times=None, reftime: float = 0.0):
