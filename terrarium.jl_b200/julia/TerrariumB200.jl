@@ -114,7 +114,7 @@ function initialize_b200(model::Union{SoilModel{NF}, LandModel{NF}}, timestepper
     zf = collect(Float64, Terrarium.znodes(grid, Terrarium.Face()))
     nz, ncol = length(zf) - 1, size(grid, 1)
     hyd = model.soil.hydrology
-    bcs = ntuple(_ -> TrmBC(0, 0), TRM_BC_NSLOTS)   # TODO(julia side): translate `boundary_conditions` into slots + inputs
+    bcs, bc_sources = translate_bcs(boundary_conditions)
     cfg = Ref(TrmConfig(TRM_ABI_VERSION, dtype_code(NF), ncol, 0, nz, device,
         model isa LandModel ? 1 : 0, timestepper isa Heun ? 1 : 0, hyd.vertical_flow isa RichardsEq ? 1 : 0,
         hyd.hydraulic_properties.swrc isa VanGenuchten ? 0 : 1, hyd.hydraulic_properties.unsat_hydraulic_cond isa UnsatKVanGenuchten ? 1 : 0,
@@ -125,6 +125,9 @@ function initialize_b200(model::Union{SoilModel{NF}, LandModel{NF}}, timestepper
     GC.@preserve zf check(ccall((:trm_create, LIB), Cint, (Ref{TrmConfig}, Ref{Ptr{Cvoid}}), cfg, h), "create")
     integ = B200Integrator{NF, typeof(model), typeof(timestepper)}(h[], model, timestepper, ncol, nz)
     finalizer(i -> ccall((:trm_destroy, LIB), Cint, (Ptr{Cvoid},), i.handle), integ)
+    for (input, source) in bc_sources                       # device-resident boundary values (user input slots 0..7)
+        set_input!(integ, input, source)
+    end
     names = (model isa LandModel && !isnothing(model.vegetation)) ?
         (:temperature, :saturation_water_ice, :carbon_vegetation, :vegetation_area_fraction, :canopy_water) : (:temperature, :saturation_water_ice)
     for name in names
@@ -177,6 +180,172 @@ function Terrarium.current_time(integ::B200Integrator)
     t, it = Ref{Cdouble}(0), Ref{Int64}(0)
     check(ccall((:trm_get_clock, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Int64}), integ.handle, t, it), "get_clock")
     return t[]
+end
+
+# ---- boundary conditions --------------------------------------------------------------------------------------------
+# The reference passes `boundary_conditions = (temperature = (top = ValueBoundaryCondition(v),), ...)`
+# (src/models/soil/soil_model_bcs.jl:6-40). A closure cannot run inside the library's kernels, so `v` must be one of the
+# device-resident sources below (or a number / per-column vector); a Julia function is rejected with an explanation.
+
+"""`clamp(mean[c] + amp[c] * sin(2π t / period - phase[c]), lo, hi)`: the device form of the periodic boundary
+condition of examples/simulations/soil_heat_global.jl:72-93."""
+Base.@kwdef struct Sinusoid{M, A, P}
+    mean::M
+    amp::A
+    phase::P = 0.0
+    period::Float64 = 86400.0
+    lo::Float64 = -Inf
+    hi::Float64 = Inf
+end
+
+"""Snapshots `values[column, it]` at `times[it]` (seconds), interpolated like `FieldTimeSeries[Time(t)]`
+(src/input_output/input_sources.jl:165-171); `raster = true` selects the update rule of `RasterInputSource`
+(ext/TerrariumRastersExt/TerrariumRastersExt.jl:96-121)."""
+struct TimeSeries{V <: AbstractMatrix}
+    times::Vector{Float64}
+    values::V
+    raster::Bool
+end
+TimeSeries(times, values; raster = false) = TimeSeries(collect(Float64, times), values, raster)
+
+const BC_SLOT = Dict((:temperature, :top) => 0, (:temperature, :bottom) => 1, (:internal_energy, :top) => 2,
+                     (:internal_energy, :bottom) => 3, (:saturation_water_ice, :top) => 4, (:saturation_water_ice, :bottom) => 5,
+                     (:pressure_head, :top) => 6, (:pressure_head, :bottom) => 7)
+
+bc_kind(bc) = bc_kind(bc.classification)
+bc_kind(::Terrarium.Oceananigans.BoundaryConditions.Value) = Int32(1)
+bc_kind(::Terrarium.Oceananigans.BoundaryConditions.Gradient) = Int32(2)
+bc_kind(::Terrarium.Oceananigans.BoundaryConditions.Flux) = Int32(3)
+
+function translate_bcs(boundary_conditions)
+    slots = [TrmBC(0, 0) for _ in 1:TRM_BC_NSLOTS]
+    sources = Pair{Int, Any}[]
+    for (field, sides) in pairs(boundary_conditions), (side, bc) in pairs(sides)
+        slot = get(BC_SLOT, (field, side)) do
+            throw(ArgumentError("no boundary condition slot for $field / $side in the B200 library"))
+        end
+        isnothing(bc.condition) && continue                  # NoFluxBoundaryCondition: the default
+        bc.condition isa Function && throw(ArgumentError(
+            "function valued boundary conditions cannot run inside the CUDA kernels: pass a number, a per-column vector, " *
+            "a TerrariumB200.Sinusoid or a TerrariumB200.TimeSeries for $field / $side"))
+        input = length(sources)                              # TRM_IN_USER0 + k
+        input < 8 || throw(ArgumentError("at most 8 user boundary inputs"))
+        slots[slot + 1] = TrmBC(bc_kind(bc), Int32(input))
+        push!(sources, input => bc.condition)
+    end
+    return Tuple(slots), sources
+end
+
+# ---- inputs / forcing -----------------------------------------------------------------------------------------------
+const INPUT_ID = Dict(:air_temperature => 8, :air_pressure => 9, :windspeed => 10, :specific_humidity => 11, :rainfall => 12,
+                      :snowfall => 13, :surface_shortwave_down => 14, :surface_longwave_down => 15, :daytime_length => 16,
+                      :CO2 => 17, :skin_temperature => 18, :SAI => 19, :daily_leaf_respiration => 20)
+input_id(id::Integer) = Cint(id)
+input_id(name::Symbol) = Cint(INPUT_ID[name])
+
+percolumn(::Type{NF}, v::Number, n) where {NF} = fill(NF(v), n)
+percolumn(::Type{NF}, v::AbstractVector, n) where {NF} = (length(v) == n || throw(DimensionMismatch("expected $n columns")); Array{NF}(v))
+
+"""`set_input!(integ, name_or_slot, source)`: number, per-column vector, `Sinusoid` or `TimeSeries`
+(replaces `InputSource`s, src/input_output/input_sources.jl:81-171)."""
+function set_input!(integ::B200Integrator, id, v::Number)
+    check(ccall((:trm_set_input_const, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble), integ.handle, input_id(id), v), "set_input_const")
+end
+function set_input!(integ::B200Integrator{NF}, id, v::AbstractVector) where {NF}
+    a = percolumn(NF, v, integ.ncol)
+    GC.@preserve a check(ccall((:trm_set_input_field, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), integ.handle, input_id(id), pointer(a)), "set_input_field")
+end
+function set_input!(integ::B200Integrator{NF}, id, s::Sinusoid) where {NF}
+    m, a, p = percolumn(NF, s.mean, integ.ncol), percolumn(NF, s.amp, integ.ncol), percolumn(NF, s.phase, integ.ncol)
+    GC.@preserve m a p check(ccall((:trm_set_input_sinusoid, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cdouble),
+        integ.handle, input_id(id), pointer(m), pointer(a), pointer(p), s.period, s.lo, s.hi), "set_input_sinusoid")
+end
+function set_input!(integ::B200Integrator{NF}, id, ts::TimeSeries) where {NF}
+    size(ts.values) == (integ.ncol, length(ts.times)) || throw(DimensionMismatch("values must be [column, time]"))
+    v, t = Array{NF}(ts.values), ts.times                     # column fastest = the library's [nt][ncol]
+    GC.@preserve v t if ts.raster
+        check(ccall((:trm_set_input_raster, LIB), Cint, (Ptr{Cvoid}, Cint, Int32, Ptr{Cdouble}, Ptr{Cvoid}),
+                    integ.handle, input_id(id), length(t), pointer(t), pointer(v)), "set_input_raster")
+    else
+        check(ccall((:trm_set_input_table, LIB), Cint, (Ptr{Cvoid}, Cint, Int32, Ptr{Cdouble}, Ptr{Cvoid}),
+                    integ.handle, input_id(id), length(t), pointer(t), pointer(v)), "set_input_table")
+    end
+end
+
+"""Input variable as of the last `update_inputs!` (reading `state.<input>` in the reference)."""
+function get_input(integ::B200Integrator{NF}, id) where {NF}
+    out = Vector{NF}(undef, integ.ncol)
+    check(ccall((:trm_get_input, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), integ.handle, input_id(id), out, length(out)), "get_input")
+    return out
+end
+
+"""Device pointer of a per-column input for in-place coupling (examples/simulations/speedy_dry_land.jl:45-68)."""
+function input_ptr(integ::B200Integrator, id)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:trm_input_ptr, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), integ.handle, input_id(id), p), "input_ptr")
+    return p[]
+end
+
+# ---- ColumnRingGrid conversions (src/grids/column_ring_grid.jl:102-149) ------------------------------------------------
+"""Hand the mask of a `ColumnRingGrid` to the library: `ring_index = findall(mask)` (0-based on the C side)."""
+function set_ring_mask!(integ::B200Integrator, mask::AbstractVector{Bool})
+    idx = Int64.(findall(mask) .- 1)
+    length(idx) == integ.ncol || throw(DimensionMismatch("mask selects $(length(idx)) points, the integrator has $(integ.ncol) columns"))
+    GC.@preserve idx check(ccall((:trm_set_ring_index, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), integ.handle, pointer(idx), length(mask)), "set_ring_index")
+    return length(mask)
+end
+
+field_rows(integ::B200Integrator, name::Symbol) =
+    name in (:internal_energy, :temperature, :liquid_water_fraction, :saturation_water_ice, :pressure_head,
+             :plant_available_water, :root_fraction) ? integ.nz : name === :hydraulic_conductivity ? integ.nz + 1 : 1
+
+"""`RingGrids.Field(field, grid; fill_value)` data: `[ring point, layer]` with `fill_value` at the ocean points."""
+function get_field_ring(integ::B200Integrator{NF}, name::Symbol, nring::Integer; fill_value = NaN) where {NF}
+    out = Array{NF}(undef, nring, field_rows(integ, name))
+    check(ccall((:trm_get_field_ring, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64, Cdouble), integ.handle,
+                Cint(getproperty(TerrariumB200, name)), out, length(out), fill_value), "get_field_ring")
+    return out
+end
+function set_field_ring!(integ::B200Integrator{NF}, name::Symbol, ring::AbstractArray) where {NF}
+    v = Array{NF}(ring)
+    GC.@preserve v check(ccall((:trm_set_field_ring, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), integ.handle,
+                               Cint(getproperty(TerrariumB200, name)), pointer(v), length(v)), "set_field_ring")
+end
+
+# ---- diagnostics, clock, synchronisation ---------------------------------------------------------------------------------
+struct TrmDiag                        # trm_diag
+    energy::Cdouble; water::Cdouble; t_min::Cdouble; t_max::Cdouble; sat_min::Cdouble; sat_max::Cdouble; nan_count::Cdouble; ncol::Cdouble
+end
+"""Budgets and extrema of the columns owned by this handle (a multi-GPU caller reduces them, e.g. with NCCL.jl)."""
+function diagnostics(integ::B200Integrator)
+    d = Ref(TrmDiag(0, 0, 0, 0, 0, 0, 0, 0))
+    check(ccall((:trm_diagnostics, LIB), Cint, (Ptr{Cvoid}, Ref{TrmDiag}), integ.handle, d), "diagnostics")
+    return d[]
+end
+synchronize(integ::B200Integrator) = check(ccall((:trm_sync, LIB), Cint, (Ptr{Cvoid},), integ.handle), "sync")
+set_clock!(integ::B200Integrator, time, iteration = 0) =
+    check(ccall((:trm_set_clock, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, time, iteration), "set_clock")
+compute_tendencies!(integ::B200Integrator) = check(ccall((:trm_compute_tendencies, LIB), Cint, (Ptr{Cvoid},), integ.handle), "compute_tendencies")
+
+"""Stream-ordered stepping without a host synchronisation (`Simulation` between two scheduled events)."""
+step_async!(integ::B200Integrator, Δt, n) =
+    check(ccall((:trm_step_async, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, convert_dt(Δt), n), "step_async")
+
+# ---- time-averaged output (Oceananigans AveragedTimeInterval) ---------------------------------------------------------
+accumulate!(integ::B200Integrator, name::Symbol, weight) =
+    check(ccall((:trm_accumulate, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble), integ.handle, Cint(getproperty(TerrariumB200, name)), weight), "accumulate")
+function get_accumulated(integ::B200Integrator{NF}, name::Symbol; scale = 1.0, reset = true) where {NF}
+    rows = field_rows(integ, name)
+    out = Array{NF}(undef, integ.ncol, rows)
+    check(ccall((:trm_get_accumulated, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64, Cdouble, Int32), integ.handle,
+                Cint(getproperty(TerrariumB200, name)), out, length(out), scale, reset ? 1 : 0), "get_accumulated")
+    return rows == 1 ? vec(out) : permutedims(out)
+end
+
+function __init__()
+    v = ccall((:trm_abi_version, LIB), Cint, ())
+    v == TRM_ABI_VERSION || error("libterrarium_b200 has ABI version $v, this module was written for $TRM_ABI_VERSION")
 end
 
 end # module

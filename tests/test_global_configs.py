@@ -1,0 +1,107 @@
+"""BASELINE configs 2 and 3 on the reference's own grids: ``ColumnRingGrid`` over the ERA5-Land N72 / N145 land masks
+(``tests/golden/era5_land_masks.npz``, frozen from ``/root/reference/inputs`` by ``tests/golden/make_land_masks.py``),
+set up as ``examples/simulations/soil_heat_global.jl`` does (latitude climatology, 0.05 K/m profile, daily surface
+temperature cycle shifted by longitude)."""
+import datetime
+import os
+
+import numpy as np
+import pytest
+
+from common import ENGINES, make, max_scaled_err, richards_soil, trm
+
+FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "era5_land_masks.npz")
+COLUMNS = {"N72": 14017, "N145": 56951}
+
+
+def era5_land_grid(name, nf, spacing):
+    d = np.load(FIXTURE)
+    lat, lon = d[f"{name}_lat"], d[f"{name}_lon"]
+    mask = np.unpackbits(d[f"{name}_bits"])[:lat.size * lon.size].astype(bool)
+    # ring order of a full grid: rings north to south, longitude fastest; radians as RingGrids.get_lonlats (:39)
+    return trm.ColumnRingGrid(trm.B200(), nf, spacing, mask, lon=np.deg2rad(np.tile(lon, lat.size)), lat=np.deg2rad(np.repeat(lat, lon.size)))
+
+
+def soil_heat_global(engine, name, nf, soil=None, stepper=trm.ForwardEuler, math="faithful", saturation=None):
+    grid = era5_land_grid(name, nf, trm.ExponentialSpacing(N=30))
+    lon, lat = grid.masked_lonlat()
+    T0 = 20.0 - np.abs(40.0 * np.sin(lat))                        # mean_annual_temperature, soil_heat_global.jl:51
+    bc = trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0))   # :72-93
+    inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z}  # :59-64
+    if saturation is not None:
+        inits["saturation_water_ice"] = saturation
+    model = trm.SoilModel(grid, soil=soil) if soil is not None else trm.SoilModel(grid)
+    return grid, T0, make(engine, model, stepper(), boundary_conditions=bc, initializers=inits, math=math)
+
+
+def test_mask_fixture_geometry():
+    for name, ncol in COLUMNS.items():
+        grid = era5_land_grid(name, np.float32, trm.ExponentialSpacing(N=30))
+        n = int(name[1:])
+        assert grid.Nc == ncol and grid.npoints == (2 * n) * (4 * n) and grid.Nz == 30
+        lon, lat = grid.masked_lonlat()
+        assert np.all(np.diff(lat) <= 0) and lat[0] > 1.4 and lat[-1] < -1.1     # Greenland ... Antarctica
+        # Antarctica: every point of the southernmost ring is land; the northernmost ring is ocean
+        assert grid.mask[-4 * n:].all() and not grid.mask[:4 * n].any()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_soil_heat_global_n72(engine):
+    """Config 2 as the example runs it: Float32, two default time steps, then 12 h at 600 s (:108-113)."""
+    grid, T0, integ = soil_heat_global(engine, "N72", np.float32)
+    assert grid.Nc == COLUMNS["N72"]
+    Tg0 = integ.state.ground_temperature.numpy().copy()
+    assert np.allclose(Tg0.reshape(-1), T0 + 0.05 * 0.025, atol=1e-4)    # top cell centre at z = -0.025 m
+    trm.timestep(integ)
+    trm.timestep(integ)
+    trm.run(integ, period=datetime.timedelta(hours=12), dt=600.0)
+    assert integ.clock.time == 2 * 300.0 + 43200.0 and integ.clock.iteration == 74
+    T = integ.state.temperature.numpy()
+    Tg = integ.state.ground_temperature.numpy().reshape(-1)
+    assert T.dtype == np.float32 and np.isfinite(T).all()
+    assert Tg.min() > -30.5 and Tg.max() < 30.5 and np.abs(Tg - Tg0.reshape(-1)).max() > 1.0
+    assert np.array_equal(T[-1].reshape(-1), Tg)                           # ground_temperature is the top layer
+    deep = T[0].reshape(-1)                                               # the bottom cell (z ~ -180 m) has not moved
+    assert np.allclose(deep, (T0 - 0.05 * grid.znodes_center()[0]).astype(np.float32), atol=1e-3)
+    # surface map on the full ring grid (RingGrids.Field(..., grid), :104, :116): ocean points stay NaN
+    ring = grid.to_ring(Tg)
+    assert ring.shape == (41472,) and np.isnan(ring).sum() == 41472 - grid.Nc and np.array_equal(grid.from_ring(ring), Tg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+def test_soil_heat_global_n72_parity(math):
+    """Config 2, Float64: library against the oracle after the example's 74 steps (north_star tolerance 1e-9)."""
+    runs = []
+    for engine in ("oracle", "cuda"):
+        _, _, integ = soil_heat_global(engine, "N72", np.float64, math=math)
+        trm.timestep(integ)
+        trm.timestep(integ)
+        trm.run(integ, period=43200.0, dt=600.0)
+        runs.append(integ)
+    o, c = runs
+    for name in ("temperature", "internal_energy", "liquid_water_fraction"):
+        assert max_scaled_err(getattr(c.state, name).numpy(), getattr(o.state, name).numpy()) <= 1e-9, name
+    assert np.array_equal(c.state.saturation_water_ice.numpy(), o.state.saturation_water_ice.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stepper", [trm.ForwardEuler, trm.Heun], ids=["euler", "heun"])
+def test_soil_energy_richards_n145_parity(stepper):
+    """Config 3: coupled soil energy + Richards hydrology on the N145 land columns, Float64, 60 steps of 60 s."""
+    runs = []
+    for engine in ("oracle", "cuda"):
+        grid, _, integ = soil_heat_global(engine, "N145", np.float64, soil=richards_soil(), stepper=stepper,
+                                          saturation=lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x)
+        assert grid.Nc == COLUMNS["N145"]
+        integ.step(60.0, 60)
+        integ.compute_auxiliary()
+        runs.append(integ)
+    o, c = runs
+    for name in ("temperature", "internal_energy", "saturation_water_ice", "pressure_head", "water_table"):
+        assert max_scaled_err(getattr(c.state, name).numpy(), getattr(o.state, name).numpy()) <= 1e-9, name
+    # column water is conserved (no-flux boundaries): thickness-weighted saturation, test/soil/soil_hydrology_tests.jl:171-188
+    dz = grid.dz()[:, None]
+    sat = c.state.saturation_water_ice.numpy().reshape(grid.Nz, -1)
+    want = (np.minimum(1.0, 0.5 - 0.1 * grid.znodes_center())[:, None] * dz).sum(axis=0)
+    assert np.allclose((sat * dz).sum(axis=0) + c.state.surface_excess_water.numpy().reshape(-1) / 0.49, want, rtol=1e-12)
