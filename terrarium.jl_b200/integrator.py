@@ -186,7 +186,9 @@ class ModelIntegrator:
                 if next_user >= abi.TRM_IN_USER0 + abi.TRM_NUM_USER_INPUTS:
                     raise ValueError("too many boundary condition inputs")
                 cfg.bc[bc.slot].input = next_user
-                pending.append((next_user, bc.value))
+                # no value: the boundary value is the input variable `bc.name` (`var(name, XY())`, soil_model_bcs.jl:17),
+                # zero until an InputSource of that name provides it
+                pending.append((next_user, 0.0 if bc.value is None else bc.value))
                 if bc.name:
                     self._bc_inputs[bc.name] = next_user
                 next_user += 1
@@ -198,6 +200,9 @@ class ModelIntegrator:
             sources = [inputs] if hasattr(inputs, "name") else list(inputs)
             inputs = {src.name: src.value for src in sources}
         for name, value in (inputs or {}).items():
+            if name in self._bc_inputs:       # a boundary condition input, e.g. PrescribedSurfaceTemperature("Tair")
+                self._set_input(self._bc_inputs[name], value)
+                continue
             if name not in abi.INPUT_IDS:
                 raise KeyError(f"unknown input variable {name!r}")
             self._set_input(abi.INPUT_IDS[name], value)

@@ -474,6 +474,8 @@ def InputSource(grid, data, name: Optional[str] = None, times=None, reftime: flo
     ``TimeSeries`` (field sources), or an array on the ring grid of a ``ColumnRingGrid`` (optionally with ``times``)."""
     if name is None:
         raise ValueError("InputSource needs the name of the input variable it provides")
+    if isinstance(data, (RasterInputSource, TimeSeries, Sinusoid)):   # e.g. RasterInputSource.from_netcdf(...)
+        return NamedInput(name, data)
     ring = hasattr(grid, "mask") and isinstance(data, np.ndarray) and data.shape[-1] == grid.npoints and grid.npoints != grid.Nc
     value = RasterInputSource(values=data, times=times, reftime=reftime) if ring else (TimeSeries(times, data) if times is not None else data)
     return NamedInput(name, value)
@@ -506,11 +508,11 @@ def GradientBoundaryCondition(value):
 
 
 # aliases of src/models/soil/soil_model_bcs.jl:6-40 -------------------------------------------
-def PrescribedSurfaceTemperature(name: str, value) -> Dict[str, Dict[str, BoundaryCondition]]:
+def PrescribedSurfaceTemperature(name: str, value=None) -> Dict[str, Dict[str, BoundaryCondition]]:
     return {"temperature": {"top": BoundaryCondition(abi.TRM_BC_VALUE, abi.TRM_BC_TEMPERATURE_TOP, value, name)}}
 
 
-def PrescribedBottomTemperature(name: str, value):
+def PrescribedBottomTemperature(name: str, value=None):
     return {"temperature": {"bottom": BoundaryCondition(abi.TRM_BC_VALUE, abi.TRM_BC_TEMPERATURE_BOTTOM, value, name)}}
 
 

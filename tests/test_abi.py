@@ -139,3 +139,61 @@ def test_enum_values_match_header():
     # the field-id table is dense and in header order for the vegetation block
     veg = [a.FIELD_IDS[n] for n in a.VEGETATION_FIELDS]
     assert veg == list(range(21, 43))
+
+
+def test_julia_glue_matches_the_abi():
+    """``julia/TerrariumB200.jl`` cannot be executed here (no Julia), so its tables are checked statically against the ctypes
+    mirror (itself pinned to the compiled header above): field ids, input ids, boundary slots, the size of ``TrmParams`` /
+    ``TrmConfig`` / ``TrmDiag`` counted from the Julia field declarations, and that every ``ccall`` names an exported
+    symbol with the argument count the header declares."""
+    import re
+    a = trm.abi
+    text = open(os.path.join(ROOT, "terrarium.jl_b200", "julia", "TerrariumB200.jl")).read()
+    # @enum FieldId
+    enum = re.search(r"@enum FieldId::Cint (.*)", text).group(1)
+    ids = {k: int(v) for k, v in re.findall(r"(\w+)=(\d+)", enum)}
+    assert ids and all(a.FIELD_IDS[k] == v for k, v in ids.items())
+    assert set(a.VEGETATION_FIELDS) <= set(ids)
+    # input ids and BC slots
+    inputs = dict(re.findall(r":(\w+) => (\d+)", re.search(r"const INPUT_ID = Dict\((.*?)\)\n", text, re.S).group(1)))
+    assert inputs and all(a.INPUT_IDS[k] == int(v) for k, v in inputs.items())
+    slots = re.findall(r"\(:(\w+), :(\w+)\) => (\d+)", re.search(r"const BC_SLOT = Dict\((.*?)\)\n", text, re.S).group(1))
+    want = {("temperature", "top"): a.TRM_BC_TEMPERATURE_TOP, ("temperature", "bottom"): a.TRM_BC_TEMPERATURE_BOTTOM,
+            ("internal_energy", "top"): a.TRM_BC_ENERGY_TOP, ("internal_energy", "bottom"): a.TRM_BC_ENERGY_BOTTOM,
+            ("saturation_water_ice", "top"): a.TRM_BC_SATURATION_TOP, ("saturation_water_ice", "bottom"): a.TRM_BC_SATURATION_BOTTOM,
+            ("pressure_head", "top"): a.TRM_BC_PRESSURE_TOP, ("pressure_head", "bottom"): a.TRM_BC_PRESSURE_BOTTOM}
+    assert {(f, s): int(v) for f, s, v in slots} == want
+    assert int(re.search(r"const TRM_ABI_VERSION = Int32\((\d+)\)", text).group(1)) == a.TRM_ABI_VERSION
+
+    # struct sizes from the Julia declarations (all members are naturally aligned: 4-byte members come in pairs)
+    def struct_bytes(name):
+        body = re.search(rf"struct {name}\b(.*?)\nend", text, re.S).group(1)
+        body = re.sub(r"#.*", "", body)
+        size = 0
+        for typ in re.findall(r"::\s*([\w{}, ]+?)\s*(?:;|\n|$)", body):
+            m = re.match(r"NTuple\{(\w+), (\w+)\}", typ)
+            n, base = (m.group(1), m.group(2)) if m else (1, typ)
+            n = a.TRM_BC_NSLOTS if n == "TRM_BC_NSLOTS" else int(n)
+            size += n * {"Cdouble": 8, "Int64": 8, "Int32": 4, "Ptr{Cdouble}": 8, "TrmBC": 8, "TrmParams": C.sizeof(a.trm_params)}[base]
+        return size
+    assert struct_bytes("TrmParams") == C.sizeof(a.trm_params)
+    assert struct_bytes("TrmConfig") == C.sizeof(a.trm_config)
+    assert struct_bytes("TrmDiag") == C.sizeof(a.trm_diag)
+
+    # every ccall: exported symbol, argument tuple as long as the header's parameter list
+    header = open(os.path.join(ROOT, "include", "terrarium_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    nargs = {}
+    for name, params in re.findall(r"\b(trm_\w+)\s*\(([^;{]*?)\)\s*;", header):
+        params = params.strip()
+        nargs[name] = 0 if params in ("", "void") else params.count(",") + 1
+    calls = re.findall(r"ccall\(\(:(trm_\w+), LIB\), \w+,\s*\(([^()]*(?:\{[^{}]*\}[^()]*)*)\)", text)
+    assert len(calls) >= 25
+    for name, argtypes in calls:
+        assert name in nargs, name
+        depth, n = 0, (1 if argtypes.strip() else 0)
+        for ch in argtypes.strip().rstrip(","):
+            depth += ch == "{"
+            depth -= ch == "}"
+            n += (ch == "," and depth == 0)
+        assert n == nargs[name], (name, argtypes, nargs[name])

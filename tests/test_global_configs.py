@@ -105,3 +105,52 @@ def test_soil_energy_richards_n145_parity(stepper):
     sat = c.state.saturation_water_ice.numpy().reshape(grid.Nz, -1)
     want = (np.minimum(1.0, 0.5 - 0.1 * grid.znodes_center())[:, None] * dz).sum(axis=0)
     assert np.allclose((sat * dz).sum(axis=0) + c.state.surface_excess_water.numpy().reshape(-1) / 0.49, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_soil_heat_global_era5_flow(engine, tmp_path):
+    """``examples/simulations/soil_heat_global_era5.jl:13-48`` end to end: land mask and a 2 m temperature raster read from
+    NetCDF-4 files, ``InputSource(grid, raster; name = :Tair)`` passed to ``initialize``, ``PrescribedSurfaceTemperature(:Tair)``
+    without a value, the first raster slice as initial surface temperature. (The ERA5 raster is not part of the reference
+    checkout: a packed, deflated stand-in on the N72 grid is written here.)"""
+    from hdf5_writer import Writer
+    d = np.load(FIXTURE)
+    lat, lon = d["N72_lat"], d["N72_lon"]
+    land = np.unpackbits(d["N72_bits"])[:lat.size * lon.size].astype(bool).reshape(lat.size, lon.size)
+    hours = np.arange(0, 25, 6)
+    truth = (288.0 - 30.0 * np.abs(np.sin(np.deg2rad(lat)))[None, :, None]
+             + 8.0 * np.sin(2 * np.pi * hours[:, None, None] / 24.0 - np.deg2rad(lon)[None, None, :]))
+    scale, offset = 80.0 / 65000.0, 270.0
+    packed = np.round((truth - offset) / scale).astype("<i2")
+    packed[:, ~land] = -32767                                    # ERA5-Land: missing over the ocean
+    mask_path, t2m_path = str(tmp_path / "lsm.nc"), str(tmp_path / "t2m.nc")
+    w = Writer(2)
+    w.add("time", np.array([998520], dtype="<i4"), layout="contiguous", attrs={"units": "hours since 1900-01-01 00:00:0.0"})
+    w.add("lat", lat, layout="contiguous")
+    w.add("lon", lon, layout="contiguous")
+    w.add("lsm", land[None].astype("<f8"), chunks=(1, 144, 288), dims=("time", "lat", "lon"), attrs={"_FillValue": np.float64(-32767.0)})
+    w.save(mask_path)
+    w = Writer(1)
+    w.add("valid_time", (hours * 3600 + 1672531200).astype("<i8"), layout="contiguous", attrs={"units": "seconds since 1970-01-01"})
+    w.add("latitude", lat, layout="contiguous")
+    w.add("longitude", lon, layout="contiguous")
+    w.add("t2m", packed, chunks=(1, 72, 144), shuffle=True, deflate=5, dims=("valid_time", "latitude", "longitude"),
+          attrs={"scale_factor": np.float64(scale), "add_offset": np.float64(offset), "_FillValue": np.int16(-32767), "units": "K"})
+    w.save(t2m_path)
+
+    grid = trm.ColumnRingGrid.from_land_sea_mask(np.float64, trm.ExponentialSpacing(N=30), path=mask_path)
+    assert grid.Nc == COLUMNS["N72"]
+    raster = trm.RasterInputSource.from_netcdf(t2m_path, "t2m", time="valid_time", decode_times=True, reftime=None)
+    assert raster.values.shape == (5, 41472) and np.isnan(raster.values[:, ~grid.mask]).all() and np.isfinite(raster.values[:, grid.mask]).all()
+    raster.values = raster.values - 273.15
+    forcing = trm.InputSource(grid, raster, name="Tair")
+    Tsurf0 = raster.values[0][grid.mask]
+    inits = {"temperature": lambda x, z: Tsurf0[None, :] - 0.02 * z, "saturation_water_ice": 1.0}
+    integ = make(engine, trm.SoilModel(grid), trm.ForwardEuler(), forcing, initializers=inits,
+                 boundary_conditions=trm.PrescribedSurfaceTemperature("Tair"))
+    trm.timestep(integ, 120.0)
+    trm.run(integ, period=3 * 3600.0, dt=120.0)    # last update_inputs! at t = 3 h: halfway between two slices
+    want = (0.5 * (packed[0].astype(np.float64) + packed[1]) * scale + offset - 273.15)[land]
+    np.testing.assert_allclose(integ.state.Tair.numpy().reshape(-1), want, rtol=1e-12, atol=1e-12)
+    T = integ.state.temperature.numpy()
+    assert np.isfinite(T).all() and np.abs(T[-1].reshape(-1) - Tsurf0).max() > 0.5
