@@ -55,6 +55,54 @@ def test_two_ranks_match_one(tmp_path):
     assert got["slowest"] == 2.0
 
 
+def _ring_case(partition):
+    """ColumnRingGrid over the N72 land mask (every 7th land point) with a time-varying raster as surface temperature:
+    each rank gathers its own columns of the ring raster (idxmap = findall(mask)[col0:col1])."""
+    from common import make, trm
+    from test_global_configs import FIXTURE
+    d = np.load(FIXTURE)
+    land = np.flatnonzero(np.unpackbits(d["N72_bits"])[:41472])
+    mask = np.zeros(41472, dtype=bool)
+    mask[land[::7]] = True
+    grid = trm.ColumnRingGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_max=1.0, N=8), mask)
+    rng = np.random.default_rng(11)
+    times = np.arange(5) * 600.0
+    raster = trm.RasterInputSource(values=5.0 + rng.normal(0.0, 3.0, (5, 41472)), times=times)
+    bcs = trm.PrescribedSurfaceTemperature("T_ub", raster)
+    integ = make("oracle", trm.SoilModel(grid), trm.ForwardEuler(dt=100.0), boundary_conditions=bcs, partition=partition,
+                 initializers={"temperature": 1.0, "saturation_water_ice": 0.5})
+    return grid, integ
+
+
+def _ring_worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from terrarium_jl_b200 import distributed as td
+    grid, integ = _ring_case((rank, world))
+    assert integ.ncol == (1002 if rank == 0 else 1001) and integ.col0 == (0 if rank == 0 else 1002)   # 2003 = ceil(14017 / 7)
+    integ.step(100.0, 15)
+    T = td.gather_field(integ, "temperature")
+    if rank == 0:
+        np.savez(out, T=T, ring=grid.to_ring(T[-1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_on_a_ring_grid_with_raster_forcing(tmp_path):
+    out = str(tmp_path / "ring0.npz")
+    mp.spawn(_ring_worker, args=(2, 31500 + os.getpid() % 2000, out), nprocs=2, join=True)
+    got = np.load(out)
+    grid, single = _ring_case(None)
+    assert grid.Nc == 2003
+    single.step(100.0, 15)
+    T = single.state.temperature.numpy()
+    assert np.array_equal(got["T"], T)
+    ring = got["ring"]
+    assert ring.shape == (41472,) and np.isnan(ring).sum() == 41472 - 2003 and np.array_equal(ring[grid.mask], T[-1].reshape(-1))
+
+
 # ---------------------------------------------------------------------------------------------
 # device side: zero-copy views of the library's buffers and the NCCL output gather
 def _cuda_case(partition, ncol=NCOL):
