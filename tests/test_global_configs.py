@@ -154,3 +154,65 @@ def test_soil_heat_global_era5_flow(engine, tmp_path):
     np.testing.assert_allclose(integ.state.Tair.numpy().reshape(-1), want, rtol=1e-12, atol=1e-12)
     T = integ.state.temperature.numpy()
     assert np.isfinite(T).all() and np.abs(T[-1].reshape(-1) - Tsurf0).max() > 0.5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config 1: the quick-start column (README.md:85-95) and its freeze-thaw variant
+# (examples/simulations/soil_heat_column.jl:13-43), Float32 as written, Float64 for the parity leg
+# ---------------------------------------------------------------------------------------------------------------
+def quick_start(engine, nf, freeze_thaw, math="faithful"):
+    grid = trm.ColumnGrid(trm.B200(), nf, trm.ExponentialSpacing(N=10), 1)
+    if freeze_thaw:
+        init = trm.SoilInitializer(energy=trm.QuasiThermalSteadyState(T0=-1.0), hydrology=trm.ConstantSaturation(sat=1.0))
+        model = trm.SoilModel(grid, initializer=init)
+    else:
+        model = trm.SoilModel(grid)       # DefaultInitializer: T = 0 and the saturation auxiliary left at zero (dry conduction)
+    integ = make(engine, model, trm.ForwardEuler(), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", 1.0), math=math)
+    if freeze_thaw:
+        trm.timestep(integ)
+        trm.timestep(integ)
+        trm.run(integ, period=datetime.timedelta(days=3))
+    else:
+        trm.run(integ, period=datetime.timedelta(days=10))
+    return grid, integ
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_quick_start_column(engine):
+    grid, integ = quick_start(engine, np.float32, freeze_thaw=False)
+    assert integ.clock.time == 864000.0 and integ.clock.iteration == 2880          # default dt = 300 s (forward_euler.jl:8)
+    T = integ.state.temperature.numpy().reshape(-1)
+    assert T.dtype == np.float32 and T.shape == (10,)
+    assert np.all(integ.state.saturation_water_ice.numpy() == 0) and np.all(integ.state.liquid_water_fraction.numpy() == 1)
+    assert np.all(np.diff(T) > 0) and 0.0 < T[0] and 0.97 < T[-1] < 1.0            # warming from the top, bottom cell first in memory
+    assert np.all(integ.state.internal_energy.numpy() > 0)
+    assert np.allclose(integ.state.T_ub.numpy(), 1.0)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_freeze_thaw_column(engine):
+    grid, integ = quick_start(engine, np.float32, freeze_thaw=True)
+    assert integ.clock.time == 600.0 + 3 * 86400.0
+    T = integ.state.temperature.numpy().reshape(-1)
+    liq = integ.state.liquid_water_fraction.numpy().reshape(-1)
+    U = integ.state.internal_energy.numpy().reshape(-1)
+    # T0 - Qgeo / k * z with z < 0: the deepest cells start above 0 degC (thawed), the middle of the column is frozen,
+    # and three days of +1 degC at the surface thaw the top cell and move the front into the second
+    assert liq[-1] == 1.0 and T[-1] > 0 and liq[0] == 1.0 and T[0] > 0
+    frozen = liq == 0
+    assert frozen.any() and np.all(T[frozen] < 0)
+    front = (liq > 0) & (liq < 1)
+    assert front.any() and np.all(T[front] == 0.0)                                 # a cell holding a thaw front sits at 0 degC
+    Lvol = 1000.0 * 3.34e5 * 0.49                                                  # rho_w * Lsl * porosity (saturated)
+    assert np.all(U[liq == 0] < -Lvol * 0.999) and np.all(U[liq == 1] >= 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("freeze_thaw", [False, True], ids=["readme", "freeze-thaw"])
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+def test_quick_start_parity(freeze_thaw, math):
+    (_, o), (_, c) = quick_start("oracle", np.float64, freeze_thaw), quick_start("cuda", np.float64, freeze_thaw, math=math)
+    for name in ("temperature", "internal_energy", "liquid_water_fraction"):
+        assert max_scaled_err(getattr(c.state, name).numpy(), getattr(o.state, name).numpy()) <= 1e-9, name
+    (_, o), (_, c) = quick_start("oracle", np.float32, freeze_thaw), quick_start("cuda", np.float32, freeze_thaw, math=math)
+    assert max_scaled_err(c.state.temperature.numpy(), o.state.temperature.numpy()) <= 2e-4    # Float32 as the README runs it
