@@ -420,20 +420,23 @@ class RasterInputSource:
     reftime: float = 0.0
 
     @classmethod
-    def from_netcdf(cls, path: str, variable: str, time: str = "time", reftime: Optional[float] = 0.0, decode_times: bool = False):
+    def from_netcdf(cls, path: str, variable: str, time: str = "time", reftime: Optional[float] = 0.0, decode_times: bool = False,
+                    time_range: Optional[tuple] = None):
         """Read ``variable[time, ...]`` from a NetCDF file; the trailing dimensions are flattened in storage order to the
         ring-grid points (a full Gaussian / lon-lat raster stored ``[lat, lon]`` north to south is in RingGrids order).
         NetCDF-3 (classic / 64-bit offset) goes through ``scipy.io.netcdf_file``, NetCDF-4 / HDF5 through the decoder in
         ``netcdf4.py``. ``_FillValue`` / ``missing_value`` become NaN, ``scale_factor`` / ``add_offset`` are applied.
         ``decode_times`` converts the time axis to seconds with the CF ``units`` attribute (``"hours since ..."``);
-        ``reftime = None`` takes the first time of the axis (``default_reftime``, TerrariumRastersExt.jl:130-133)."""
+        ``reftime = None`` takes the first time of the axis (``default_reftime``, TerrariumRastersExt.jl:130-133).
+        ``time_range = (i0, i1)`` reads only the snapshots ``i0:i1`` (NetCDF-4: only the chunks they cover are decoded)."""
         from . import netcdf4
         if netcdf4.is_hdf5(path):
             with netcdf4.File(path) as f:
                 var = f.variables[variable]
-                data = var.scaled(np.float64)
                 has_time = bool(var.dimensions) and var.dimensions[0] == time and time in f.variables
-                times = np.array(f.variables[time].read(), dtype=np.float64) if has_time else None
+                i0, i1 = time_range if (has_time and time_range is not None) else (0, None)
+                data = var.scaled(np.float64, i0, i1)
+                times = np.array(f.variables[time].read(i0, i1), dtype=np.float64) if has_time else None
                 units = f.variables[time].attrs.get("units") if has_time else None
         else:
             from scipy.io import netcdf_file
@@ -448,6 +451,8 @@ class RasterInputSource:
                 data = data * scale + offset
                 has_time = time in f.variables and var.dimensions and var.dimensions[0] == time
                 times = np.array(f.variables[time][:], dtype=np.float64) if has_time else None
+                if has_time and time_range is not None:
+                    data, times = data[time_range[0]:time_range[1]], times[time_range[0]:time_range[1]]
                 units = getattr(f.variables[time], "units", None) if has_time else None
                 units = units.decode() if isinstance(units, bytes) else units
         if has_time and decode_times:

@@ -13,12 +13,14 @@ of the HDF5 file format that the netCDF-4 library writes is decoded here with ``
   global heap).
 
 ``File(path).variables[name]`` gives ``Variable`` objects with ``shape``, ``dtype``, ``dimensions`` (from the
-``DIMENSION_LIST`` object references; ``phony_dim_k`` without them), ``attrs`` and ``[...]`` (whole-array read);
+``DIMENSION_LIST`` object references; ``phony_dim_k`` without them), ``attrs`` and ``[...]``. The file is memory-mapped;
+``var[i]`` / ``var[i0:i1]`` / ``var.read(first, last)`` decode only the chunks (or byte range) those rows cover;
 ``Variable.scaled()`` applies ``_FillValue`` / ``missing_value`` → NaN, ``scale_factor`` and ``add_offset`` (CF rules).
 Anything outside the subset raises ``NotImplementedError`` naming the feature — nothing is guessed.
 """
 from __future__ import annotations
 
+import mmap
 import struct
 import zlib
 from typing import Any, Dict, List, Optional, Tuple
@@ -66,9 +68,13 @@ MSG_LAYOUT, MSG_FILTERS, MSG_ATTRIBUTE, MSG_CONTINUE, MSG_SYMTAB, MSG_ATTRINFO =
 
 class File:
     def __init__(self, path: str):
-        with open(path, "rb") as f:
-            self.buf = f.read()
+        self._fh = open(path, "rb")
+        try:     # the file is mapped, not read: a year of hourly ERA5-Land is several GB, of which a run touches slabs
+            self.buf = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+        except ValueError:
+            self.buf = b""
         if self.buf[:8] != SIGNATURE:
+            self.close()
             raise ValueError(f"{path}: not an HDF5 / NetCDF-4 file")
         r = _Reader(self.buf, 8)
         version = r.u(1)
@@ -269,10 +275,18 @@ class File:
     def attrs(self) -> Dict[str, Any]:
         return self.root.attrs
 
+    def close(self):
+        """Unmap the file. Arrays handed out earlier are copies and stay valid."""
+        if isinstance(self.buf, mmap.mmap):
+            self.buf.close()
+        self.buf = b""
+        self._fh.close()
+
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
+        self.close()
         return False
 
 
@@ -473,7 +487,7 @@ def _symbol_table(f: File, btree: int, heap: int) -> Dict[str, int]:
             for _ in range(r.u(2)):
                 name_off, obj = r.u(8), r.u(8)
                 r.skip(24)
-                end = buf.index(b"\0", data + name_off)
+                end = buf.find(b"\0", data + name_off)
                 out[buf[data + name_off:end].decode("utf-8", "replace")] = obj
         else:
             raise ValueError("HDF5: bad group B-tree node")
@@ -547,45 +561,67 @@ class Variable:
 
     # -- data ---------------------------------------------------------------------------------------
     def __getitem__(self, key):
+        """``var[...]`` / ``var[i]`` / ``var[i0:i1]`` / ``var[i0:i1, ...]``: an index or unit-stride slice on the first
+        axis decodes only the chunks (or the contiguous byte range) it covers; anything else reads the whole array."""
+        first, rest = (key[0], key[1:]) if isinstance(key, tuple) and key else (key, ())
+        if self.shape and first is not Ellipsis:
+            n0 = self.shape[0]
+            if isinstance(first, (int, np.integer)):
+                i = int(first) + (n0 if first < 0 else 0)
+                if not 0 <= i < n0:
+                    raise IndexError(f"index {first} out of range for axis 0 of {self.name} with size {n0}")
+                return self.read(i, i + 1)[(0,) + tuple(rest)]
+            if isinstance(first, slice) and first.step in (None, 1):
+                i0, i1, _ = first.indices(n0)
+                return self.read(i0, max(i0, i1))[(slice(None),) + tuple(rest)]
         return self.read()[key]
 
-    def read(self) -> np.ndarray:
+    def read(self, first: int = 0, last: Optional[int] = None) -> np.ndarray:
+        """The rows ``first:last`` of the first axis (default: everything) in native byte order, as a new array."""
         f, body = self.file, self._layout
         dt = self._type.dtype
         if dt is None:
             raise NotImplementedError(f"HDF5: variable {self.name} has a variable-length type")
-        n = int(np.prod(self.shape)) if self.shape else 1
+        if not self.shape:
+            first, last, shape = 0, 1, ()
+        else:
+            last = self.shape[0] if last is None else last
+            if not 0 <= first <= last <= self.shape[0]:
+                raise IndexError(f"rows {first}:{last} outside axis 0 of {self.name} with size {self.shape[0]}")
+            shape = (last - first,) + tuple(self.shape[1:])
+        row = int(np.prod(self.shape[1:])) if self.shape else 1
+        n = (last - first) * row
         ver, cls = body[0], body[1]
         if ver != 3:
             raise NotImplementedError(f"HDF5: data layout message version {ver}")
         if cls == 0:       # compact
             size = int.from_bytes(body[2:4], "little")
             raw = body[4:4 + size]
-            a = np.frombuffer(raw, dtype=dt, count=n)
+            a = np.frombuffer(raw, dtype=dt, count=n, offset=first * row * dt.itemsize)
         elif cls == 1:     # contiguous
             addr, size = struct.unpack("<QQ", body[2:18])
             if addr == UNDEF:
                 a = self._filled(n, dt)
             else:
-                a = np.frombuffer(f.buf, dtype=dt, count=n, offset=addr)
+                a = np.frombuffer(f.buf, dtype=dt, count=n, offset=addr + first * row * dt.itemsize)
         elif cls == 2:     # chunked, version-1 B-tree index
             rank = body[2] - 1
             addr = int.from_bytes(body[3:11], "little")
             chunk = tuple(int.from_bytes(body[11 + 4 * i: 15 + 4 * i], "little") for i in range(rank))
-            a = self._read_chunked(addr, chunk, dt)
+            a = self._read_chunked(addr, chunk, dt, first, last)
         else:
             raise NotImplementedError(f"HDF5: data layout class {cls}")
-        return a.astype(dt.newbyteorder("=")).reshape(self.shape)
+        return a.astype(dt.newbyteorder("="), copy=True).reshape(shape)
 
     def _filled(self, n: int, dt: np.dtype) -> np.ndarray:
         if self._fill is not None and len(self._fill) == dt.itemsize:
             return np.full(n, np.frombuffer(self._fill, dtype=dt)[0], dtype=dt)
         return np.zeros(n, dtype=dt)
 
-    def _read_chunked(self, btree: int, chunk: Tuple[int, ...], dt: np.dtype) -> np.ndarray:
+    def _read_chunked(self, btree: int, chunk: Tuple[int, ...], dt: np.dtype, first: int, last: int) -> np.ndarray:
         f, buf, shape = self.file, self.file.buf, self.shape
         rank = len(shape)
-        out = self._filled(int(np.prod(shape)), dt).reshape(shape)
+        out = self._filled((last - first) * int(np.prod(shape[1:])), dt).reshape((last - first,) + tuple(shape[1:]))
         if btree == UNDEF:
             return out
         chunk_bytes = int(np.prod(chunk)) * dt.itemsize
@@ -603,8 +639,10 @@ class Variable:
                 offs = [r.u(8) for _ in range(rank + 1)][:rank]
                 child = r.u(8)
                 if level > 0:
-                    node(child)
+                    node(child)     # (keys of an internal node are the first chunk of each child: no pruning on them)
                     continue
+                if offs[0] >= last or offs[0] + chunk[0] <= first:
+                    continue        # chunk outside the requested rows: not decompressed
                 raw = buf[child:child + size]
                 for i in range(len(self._filters) - 1, -1, -1):
                     if mask & (1 << i):
@@ -622,18 +660,19 @@ class Variable:
                 if len(raw) != chunk_bytes:
                     raise ValueError(f"HDF5: chunk of {self.name} decodes to {len(raw)} bytes, expected {chunk_bytes}")
                 block = np.frombuffer(raw, dtype=dt).reshape(chunk)
-                sel_out = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, chunk, shape))
-                sel_in = tuple(slice(0, s.stop - s.start) for s in sel_out)
+                lo, hi = max(offs[0], first), min(offs[0] + chunk[0], last)
+                sel_out = (slice(lo - first, hi - first),) + tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs[1:], chunk[1:], shape[1:]))
+                sel_in = (slice(lo - offs[0], hi - offs[0]),) + tuple(slice(0, s.stop - s.start) for s in sel_out[1:])
                 out[sel_out] = block[sel_in]
 
         node(btree)
         return out
 
     # -- CF conventions --------------------------------------------------------------------------------
-    def scaled(self, dtype=np.float64) -> np.ndarray:
-        """Values as floating point with ``_FillValue`` / ``missing_value`` → NaN and ``scale_factor`` / ``add_offset``
-        applied (what Rasters.jl / NCDatasets hand to the reference)."""
-        raw = self.read()
+    def scaled(self, dtype=np.float64, first: int = 0, last: Optional[int] = None) -> np.ndarray:
+        """Values (rows ``first:last`` of the first axis) as floating point with ``_FillValue`` / ``missing_value`` → NaN
+        and ``scale_factor`` / ``add_offset`` applied (what Rasters.jl / NCDatasets hand to the reference)."""
+        raw = self.read(first, last)
         a = raw.astype(dtype)
         for key in ("_FillValue", "missing_value"):
             fv = self.attrs.get(key)

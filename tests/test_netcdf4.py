@@ -125,3 +125,33 @@ def test_reference_land_sea_masks(name, shape, ncol):
     assert lon.shape == (ncol,) and 0.0 <= lon.min() and lon.max() < 2 * np.pi and np.abs(lat).max() < np.pi / 2
     # ring order: latitude rings north to south, longitude fastest
     assert np.all(np.diff(grid.lat) <= 0) and grid.lon[1] > grid.lon[0]
+
+
+@pytest.mark.parametrize("header_version", [1, 2])
+def test_partial_reads_decode_only_the_covered_chunks(tmp_path, header_version, monkeypatch):
+    """``var[i]`` / ``var[i0:i1]`` / ``from_netcdf(time_range=...)``: rows of the first axis without decoding the rest."""
+    import zlib
+    path = str(tmp_path / "era5.nc")
+    packed, want = _era5_like(path, header_version, nt=7)
+    calls = []
+    real = zlib.decompress
+    monkeypatch.setattr(netcdf4.zlib, "decompress", lambda raw: (calls.append(len(raw)), real(raw))[1])
+    with netcdf4.File(path) as f:
+        v = f.variables["t2m"]          # chunks (2, 4, 4) over (7, 6, 9): 4 x 2 x 3 chunks
+        full = v[:]
+        assert len(calls) == 24 and np.array_equal(full, packed.astype(full.dtype))
+        del calls[:]
+        assert np.array_equal(v[3], full[3]) and len(calls) == 6
+        del calls[:]
+        assert np.array_equal(v[2:5, 1:3], full[2:5, 1:3]) and len(calls) == 12     # rows 2..4 touch chunk rows 1 and 2
+        assert np.array_equal(v[-1], full[-1]) and np.array_equal(v[5:5], full[5:5]) and np.array_equal(v[::2], full[::2])
+        np.testing.assert_array_equal(v.scaled(first=1, last=3), want[1:3])
+        assert np.array_equal(f.variables["time"][1:3], (np.arange(7) * 6 + 876576)[1:3])        # contiguous
+        assert np.array_equal(f.variables["latitude"][2:], np.linspace(75.0, -75.0, 6).astype("f4")[2:])   # compact
+        with pytest.raises(IndexError):
+            v[7]
+    src = trm.RasterInputSource.from_netcdf(path, "t2m", decode_times=True, reftime=None, time_range=(2, 6))
+    assert src.values.shape == (4, 54) and src.reftime == (876576 + 12) * 3600.0
+    np.testing.assert_array_equal(src.values, want[2:6].reshape(4, -1))
+    with pytest.raises(ValueError):      # closed with the context manager
+        f.variables["t2m"].read()
