@@ -216,3 +216,38 @@ def test_quick_start_parity(freeze_thaw, math):
         assert max_scaled_err(getattr(c.state, name).numpy(), getattr(o.state, name).numpy()) <= 1e-9, name
     (_, o), (_, c) = quick_start("oracle", np.float32, freeze_thaw), quick_start("cuda", np.float32, freeze_thaw, math=math)
     assert max_scaled_err(c.state.temperature.numpy(), o.state.temperature.numpy()) <= 2e-4    # Float32 as the README runs it
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_speedy_dry_land_coupling_flow(engine):
+    """``examples/simulations/speedy_dry_land.jl:45-86`` from the land side: a SoilModel on a full ring grid whose surface
+    temperature is the input variable ``air_temperature`` (``PrescribedSurfaceTemperature(:air_temperature)`` without a value,
+    ``InputSource(grid, field)``), overwritten by the atmosphere before every coupling interval
+    (``set!(state.inputs.air_temperature, Tair)``), the land advanced with ``run!(period = dt_atm, dt = 300)`` and the top
+    layer handed back; checked against the same integrator stepped by hand with ``timestep!``."""
+    nring = 48 * 96                                              # FullGaussianGrid(24)
+    grid = trm.ColumnRingGrid(trm.B200(), np.float32, trm.ExponentialSpacing(N=30, dz_min=0.05), np.ones(nring, dtype=bool))
+    assert grid.Nc == nring
+    rng = np.random.default_rng(5)
+
+    def build():
+        model = trm.SoilModel(grid, initializer=trm.SoilInitializer())
+        forcing = trm.InputSource(grid, np.zeros(nring, dtype=np.float32), name="air_temperature")
+        return make(engine, model, trm.ForwardEuler(), forcing, boundary_conditions=trm.PrescribedSurfaceTemperature("air_temperature"))
+
+    coupled, manual = build(), build()
+    Tsoil = coupled.state.temperature.numpy()[-1].reshape(-1) + np.float32(273.15)     # Speedy.initialize!, :39-41
+    assert Tsoil.shape == (nring,) and np.all(Tsoil > 273.0)
+    dt_atm = 1800.0
+    for k in range(4):
+        Tair_kelvin = (285.0 + 5.0 * rng.standard_normal(nring)).astype(np.float32)
+        coupled.state.inputs.air_temperature.set(Tair_kelvin - np.float32(273.15))     # :56-57
+        trm.run(coupled, period=dt_atm, dt=300.0)                                       # :60
+        Tsurf = coupled.state.temperature.numpy()[-1].reshape(-1)                       # :65
+        manual.state.air_temperature.set(Tair_kelvin - np.float32(273.15))
+        for _ in range(6):
+            trm.timestep(manual, 300.0)
+        np.testing.assert_allclose(Tsurf, manual.state.ground_temperature.numpy().reshape(-1), rtol=0, atol=1e-5)
+        assert np.array_equal(coupled.state.inputs.air_temperature.numpy(), Tair_kelvin - np.float32(273.15))
+    assert coupled.clock.time == 4 * dt_atm and np.isfinite(coupled.state.temperature.numpy()).all()
+    assert np.abs(coupled.state.temperature.numpy()[-1].reshape(-1) + 273.15 - Tsoil).max() > 0.5
