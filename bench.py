@@ -178,7 +178,13 @@ def cpu_reference(ncol_sample, steps, warmup, nf, budget_s=None):
     import oracle_integrator as oi
     import terrarium_jl_b200 as trm
     integ, _, _ = build_case(trm, oi.oracle_initialize, ncol_sample, 0, 1, 0, nf, "faithful")
-    cores = int(oi.oracle_library().cdll.orc_num_threads())
+    cdll = oi.oracle_library().cdll
+    if os.environ.get("TORCHELASTIC_RUN_ID") and "TERRARIUM_CPU_THREADS" not in os.environ:
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and may use the whole host
+        cdll.orc_set_num_threads(len(os.sched_getaffinity(0)))
+    elif "TERRARIUM_CPU_THREADS" in os.environ:
+        cdll.orc_set_num_threads(int(os.environ["TERRARIUM_CPU_THREADS"]))
+    cores = int(cdll.orc_num_threads())
     integ.step(DT, max(warmup, 1))
     if budget_s is not None:
         t0 = time.perf_counter()

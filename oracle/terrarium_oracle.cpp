@@ -1084,5 +1084,14 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+// bench.py --impl reference under torchrun: the launcher exports OMP_NUM_THREADS=1 to every rank, the reference arm
+// (rank 0 alone) is asked to use all host threads
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 }  // extern "C"
