@@ -57,9 +57,6 @@ class _Reader:
     def skip(self, n: int):
         self.pos += n
 
-    def align(self, base: int, to: int = 8):
-        self.pos = base + -(-(self.pos - base) // to) * to
-
 
 # message types (HDF5 file format specification, section IV.A.2)
 MSG_DATASPACE, MSG_LINKINFO, MSG_DATATYPE, MSG_FILL_OLD, MSG_FILL, MSG_LINK = 0x01, 0x02, 0x03, 0x04, 0x05, 0x06
@@ -325,7 +322,7 @@ class _Type:
 
 
 def _dataspace(body: bytes) -> Tuple[int, ...]:
-    ver, rank, flags = body[0], body[1], body[2]
+    ver, rank = body[0], body[1]      # (flags: maximum sizes / permutation follow the sizes and are not needed)
     if ver == 1:
         pos = 8
     elif ver == 2:
@@ -334,7 +331,6 @@ def _dataspace(body: bytes) -> Tuple[int, ...]:
         pos = 4
     else:
         raise NotImplementedError(f"HDF5: dataspace version {ver}")
-    del flags
     return tuple(int.from_bytes(body[pos + 8 * i: pos + 8 * i + 8], "little") for i in range(rank))
 
 
@@ -476,8 +472,8 @@ def _symbol_table(f: File, btree: int, heap: int) -> Dict[str, int]:
         if buf[addr:addr + 4] == b"TREE":
             r = _Reader(buf, addr + 4)
             r.skip(1)
-            level, used = r.u(1), r.u(2)
-            del level
+            r.skip(1)      # level: children are told apart by their signature
+            used = r.u(2)
             r.skip(16)
             for _ in range(used):
                 r.skip(8)

@@ -130,8 +130,6 @@ class Writer:
                         raw = raw + b"\xde\xad\xbe\xef"
                 entries.append((o, len(raw), put(raw)))
             # one leaf node per 4 chunks under one internal node: exercises the level-1 descent
-            rank = a.ndim
-
             def node(level, items):
                 out = b"TREE" + bytes([1, level]) + struct.pack("<HQQ", len(items), UNDEF, UNDEF)
                 for o, size, child in items:
@@ -146,7 +144,6 @@ class Writer:
             else:
                 tops = [(leaf[0][0], 0, put(node(0, leaf))) for leaf in leaves]
                 v["btree"] = put(node(1, tops))
-            del rank
 
         # global heap for DIMENSION_LIST references is written once the dimension datasets have addresses:
         # dimension scales (variables named as dimensions) get their object headers first
