@@ -118,7 +118,8 @@ class NetCDFWriter:
 
     ``outputs``: mapping ``name -> Field`` (or field names). Every record appends along the unlimited ``time`` dimension;
     3-D fields are ``(time, z, column)`` with layer 0 = bottom cell, z-face fields ``(time, zf, column)``, 2-D fields
-    ``(time, column)``. ``including=("grid",)`` stores the vertical coordinates."""
+    ``(time, column)``. ``including=("grid",)`` stores the vertical coordinates and, on a ``ColumnRingGrid``, the ring position
+    (and longitude / latitude) of every column, so that ``FieldTimeSeries.ring(i)`` can rebuild the global map."""
 
     def __init__(self, integrator: ModelIntegrator, outputs, filename: str, schedule, overwrite_existing: bool = False,
                  including: Sequence[str] = ("grid",)):
@@ -139,6 +140,16 @@ class NetCDFWriter:
         if "grid" in including:
             zc = f.createVariable("z", "f8", ("z",)); zc[:] = integrator.grid.znodes_center().astype(np.float64)
             zf = f.createVariable("zf", "f8", ("zf",)); zf[:] = integrator.grid.znodes_face().astype(np.float64)
+            grid = integrator.grid
+            if hasattr(grid, "mask"):   # ColumnRingGrid: where each column sits on the ring grid (column_ring_grid.jl:46-54)
+                idx = np.flatnonzero(grid.mask)[integrator.col0:integrator.col1]
+                ri = f.createVariable("ring_index", "i4", ("column",)); ri[:] = idx.astype(np.int32)
+                ri.long_name = "0-based position of the column in the ring grid"
+                f.ring_points = np.int32(grid.npoints)
+                for cname, coord in (("lon", grid.lon), ("lat", grid.lat)):
+                    if coord is not None:
+                        cv = f.createVariable(cname, "f8", ("column",)); cv[:] = coord[idx]
+                        cv.units = "radians"
         code = "f8" if np.dtype(integrator.nf) == np.float64 else "f4"
         self._vars = {}
         for name, fld in self.fields.items():
@@ -216,6 +227,8 @@ class FieldTimeSeries:
             self.times = np.array(f.variables["time"][:], dtype=np.float64)
             self.data = np.array(f.variables[name][:])
             self.z = np.array(f.variables["z"][:]) if "z" in f.variables else None
+            self.ring_index = np.array(f.variables["ring_index"][:], dtype=np.int64) if "ring_index" in f.variables else None
+            self.ring_points = int(getattr(f, "ring_points", 0))
         self.name = name
 
     def __len__(self):
@@ -223,6 +236,16 @@ class FieldTimeSeries:
 
     def __getitem__(self, i):
         return self.data[i]
+
+    def ring(self, i, fill_value=np.nan) -> np.ndarray:
+        """Record ``i`` on the full ring grid (``RingGrids.Field(field, grid; fill_value)``, column_ring_grid.jl:102-125):
+        ``[..., ring point]`` with ``fill_value`` at the points without a column."""
+        if self.ring_index is None:
+            raise ValueError("the file was not written from a ColumnRingGrid (no ring_index)")
+        rec = np.asarray(self.data[i])
+        out = np.full(rec.shape[:-1] + (self.ring_points,), fill_value, dtype=rec.dtype)
+        out[..., self.ring_index] = rec
+        return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -251,3 +251,27 @@ def test_speedy_dry_land_coupling_flow(engine):
         assert np.array_equal(coupled.state.inputs.air_temperature.numpy(), Tair_kelvin - np.float32(273.15))
     assert coupled.clock.time == 4 * dt_atm and np.isfinite(coupled.state.temperature.numpy()).all()
     assert np.abs(coupled.state.temperature.numpy()[-1].reshape(-1) + 273.15 - Tsoil).max() > 0.5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_soil_heat_global_simulation_output_on_the_ring_grid(engine, tmp_path):
+    """``soil_heat_global.jl:117-123``: the integrator wrapped in a ``Simulation`` (dt = 600 s) with a scheduled writer; the
+    saved surface temperature is put back on the full Gaussian grid (``RingGrids.Field(..., grid)``, :113)."""
+    grid, T0, integ = soil_heat_global(engine, "N72", np.float32)
+    sim = trm.Simulation(integ, dt=600.0, stop_time=datetime.timedelta(hours=6))
+    path = str(tmp_path / "global.nc")
+    sim.output_writers["surface"] = trm.NetCDFWriter(integ, ["ground_temperature", "temperature"], filename=path, schedule=trm.TimeInterval(7200.0))
+    sim.run(); sim.close()
+    Tg = trm.FieldTimeSeries(path, "ground_temperature")
+    assert list(Tg.times) == [0.0, 7200.0, 14400.0, 21600.0] and Tg.ring_points == 41472
+    assert np.array_equal(Tg[-1].reshape(-1), integ.state.ground_temperature.numpy().reshape(-1))
+    ring = Tg.ring(-1)
+    assert ring.shape[-1] == 41472 and np.isnan(ring).sum() == 41472 - grid.Nc
+    assert np.array_equal(ring.reshape(-1)[grid.mask], Tg[-1].reshape(-1)) and np.array_equal(ring.reshape(-1), grid.to_ring(Tg[-1].reshape(-1)), equal_nan=True)
+    T = trm.FieldTimeSeries(path, "temperature")
+    assert T.ring(1).shape == (30, 41472) and np.array_equal(T.ring(1, fill_value=-999.0)[:, grid.mask], T[1])
+    from scipy.io import netcdf_file
+    with netcdf_file(path, "r", mmap=False) as f:
+        lon, lat = grid.masked_lonlat()
+        assert np.array_equal(f.variables["lon"][:], lon) and np.array_equal(f.variables["lat"][:], lat)
+        assert np.array_equal(f.variables["ring_index"][:], np.flatnonzero(grid.mask))
