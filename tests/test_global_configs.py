@@ -260,7 +260,7 @@ def test_soil_heat_global_simulation_output_on_the_ring_grid(engine, tmp_path):
     grid, T0, integ = soil_heat_global(engine, "N72", np.float32)
     sim = trm.Simulation(integ, dt=600.0, stop_time=datetime.timedelta(hours=6))
     path = str(tmp_path / "global.nc")
-    sim.output_writers["surface"] = trm.NetCDFWriter(integ, ["ground_temperature", "temperature"], filename=path, schedule=trm.TimeInterval(7200.0))
+    sim.output_writers["surface"] = trm.NetCDFWriter(integ, ["temperature", "ground_temperature"], filename=path, schedule=trm.TimeInterval(7200.0))
     sim.run(); sim.close()
     Tg = trm.FieldTimeSeries(path, "ground_temperature")
     assert list(Tg.times) == [0.0, 7200.0, 14400.0, 21600.0] and Tg.ring_points == 41472
