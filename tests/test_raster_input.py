@@ -110,3 +110,26 @@ def test_input_source_constructor(engine):
     np.testing.assert_allclose(integ.state.air_temperature.numpy(), 0.5 * (Ta_ring[0] + Ta_ring[1])[mask], rtol=1e-14)
     assert np.all(integ.state.windspeed.numpy() == 2.5)
     assert np.all(np.isfinite(integ.state.ground_heat_flux.numpy()))
+
+
+def test_netcdf3_packed_fill_value_time_units_and_range(tmp_path):
+    """The NetCDF-3 leg of ``from_netcdf`` treats packing, missing values, CF time units and ``time_range`` like the
+    NetCDF-4 leg (tests/test_netcdf4.py)."""
+    from scipy.io import netcdf_file
+    nt, nlat, nlon = 6, 3, 4
+    packed = (np.arange(nt * nlat * nlon, dtype=np.int16).reshape(nt, nlat, nlon) - 30).astype(np.int16)
+    packed[2, 1, 1] = -32767
+    path = str(tmp_path / "era5_classic.nc")
+    with netcdf_file(path, "w") as f:
+        f.createDimension("time", nt); f.createDimension("latitude", nlat); f.createDimension("longitude", nlon)
+        tv = f.createVariable("time", "i4", ("time",)); tv[:] = 1000 + np.arange(nt); tv.units = "hours since 1900-01-01 00:00:00.0"
+        v = f.createVariable("t2m", "i2", ("time", "latitude", "longitude")); v[:] = packed
+        v.scale_factor = 0.5; v.add_offset = 280.0; v._FillValue = np.int16(-32767); v.missing_value = np.int16(-32767)
+    src = trm.RasterInputSource.from_netcdf(path, "t2m", decode_times=True, reftime=None, time_range=(1, 5))
+    want = packed[1:5].astype(np.float64) * 0.5 + 280.0
+    want[1, 1, 1] = np.nan
+    np.testing.assert_array_equal(src.values, want.reshape(4, -1))
+    assert np.array_equal(src.times, (1001 + np.arange(4)) * 3600.0) and src.reftime == 1001 * 3600.0
+    with pytest.raises(ValueError, match="unsupported CF time unit"):
+        trm.cf_time_unit_seconds("fortnights since 1900-01-01")
+    assert trm.cf_time_unit_seconds("days since 1970-01-01") == 86400.0 and trm.cf_time_unit_seconds(None) == 1.0
