@@ -11,6 +11,7 @@
 #   timestep!(integrator, ::ForwardEuler | ::Heun, dt)   src/timesteppers/forward_euler.jl:19-31, heun.jl:37-71
 #   run!(integrator; steps, period, dt)                  src/timesteppers/model_integrator.jl:72-88
 #   interior(field) / set!(field, value)                 src/state_variables.jl:476-489, src/initializers.jl:23-27
+# Drop-in use: wrap the host grid in `B200Grid(...)`; the reference's `initialize` / `timestep!` / `run!` then dispatch here.
 module TerrariumB200
 
 using Terrarium
@@ -342,6 +343,82 @@ function get_accumulated(integ::B200Integrator{NF}, name::Symbol; scale = 1.0, r
                 Cint(getproperty(TerrariumB200, name)), out, length(out), scale, reset ? 1 : 0), "get_accumulated")
     return rows == 1 ? vec(out) : permutedims(out)
 end
+
+# ---- drop-in dispatch: the reference's own calls, selected by the grid type ----------------------------------------------------
+# `grid = B200Grid(ColumnGrid(CPU(), Float64, ExponentialSpacing(N = 30), 10_000_000); device = 0)` is the only line a
+# user script changes: `SoilModel(grid)` / `LandModel(grid; ...)`, `initialize(model, timestepper, inputs...; boundary_conditions,
+# initializers)`, `timestep!`, `run!`, `integrator.state.<name>` and `interior(...)` then go to the library. The wrapped
+# host grid (a CPU `ColumnGrid` / `ColumnRingGrid`) supplies coordinates, the mask and the reference's initializer code path.
+
+struct B200Arch
+    device::Int
+end
+
+struct B200Grid{NF, G <: Terrarium.AbstractLandGrid{NF}} <: Terrarium.AbstractLandGrid{NF, B200Arch}
+    host::G
+    device::Int
+    math::Symbol
+end
+B200Grid(host::Terrarium.AbstractLandGrid{NF}; device = 0, math = :faithful) where {NF} = B200Grid{NF, typeof(host)}(host, device, math)
+Terrarium.get_field_grid(grid::B200Grid) = Terrarium.get_field_grid(grid.host)
+Terrarium.Oceananigans.Architectures.architecture(grid::B200Grid) = B200Arch(grid.device)
+Base.eltype(::B200Grid{NF}) where {NF} = NF
+Base.show(io::IO, grid::B200Grid) = print(io, "B200Grid(device = $(grid.device), math = $(grid.math)) over ", grid.host)
+
+# the same model on the wrapped host grid (all reference model structs are @kwdef with a `grid` field)
+function host_model(model::M) where {M <: Terrarium.AbstractModel}
+    fields = (; (f => getfield(model, f) for f in fieldnames(M))...)
+    return M.name.wrapper(; fields..., grid = model.grid.host)
+end
+
+"""State access of a `B200Integrator`: `integ.state.temperature` is the host copy `[column, 1, layer]` of the device
+field (the shape `interior(field)` has in the reference); inputs are read as of the last `update_inputs!`."""
+struct B200State{I}
+    integrator::I
+end
+function Base.getproperty(state::B200State, name::Symbol)
+    name === :integrator && return getfield(state, :integrator)
+    integ = getfield(state, :integrator)
+    if name === :inputs
+        return state
+    elseif haskey(INPUT_ID, name) && !isdefined(TerrariumB200, name)
+        return get_input(integ, name)
+    end
+    a = get_field(integ, name)                        # [layer, column] or [column]
+    return a isa AbstractVector ? reshape(a, :, 1, 1) : reshape(permutedims(a), size(a, 2), 1, size(a, 1))
+end
+Terrarium.Oceananigans.interior(a::Array) = a          # `interior(integ.state.temperature)` as in the examples
+
+function Base.getproperty(integ::B200Integrator, name::Symbol)
+    name === :state && return B200State(integ)
+    name === :clock && return (; time = Terrarium.current_time(integ))
+    return getfield(integ, name)
+end
+
+function Terrarium.initialize(model::Terrarium.AbstractModel{NF, <:B200Grid}, timestepper::Terrarium.AbstractTimeStepper,
+                              inputs::Terrarium.InputSource...; boundary_conditions = (;), initializers = (;), kwargs...) where {NF}
+    grid = model.grid
+    integ = initialize_b200(host_model(model), timestepper; device = grid.device, math = grid.math, boundary_conditions, initializers)
+    for source in inputs
+        upload_input!(integ, source)
+    end
+    if grid.host isa Terrarium.ColumnRingGrid
+        set_ring_mask!(integ, vec(Array(grid.host.mask)))
+    end
+    return integ
+end
+
+# InputSource{NF, name}: static fields are copied once, FieldTimeSeries become device tables (input_sources.jl:81-171)
+function upload_input!(integ::B200Integrator, source::Terrarium.FieldInputSource{NF, name}) where {NF, name}
+    set_input!(integ, name, vec(Array(Terrarium.interior(source.field))))
+end
+function upload_input!(integ::B200Integrator, source::Terrarium.FieldTimeSeriesInputSource{NF, name}) where {NF, name}
+    fts = source.fts
+    values = reduce(hcat, [vec(Array(Terrarium.interior(fts[i]))) for i in 1:length(fts.times)])   # [column, time]
+    set_input!(integ, name, TimeSeries(fts.times, values))
+end
+upload_input!(::B200Integrator, source) =
+    throw(ArgumentError("$(typeof(source)) has no device-resident form; pass the raster as TerrariumB200.TimeSeries(times, values; raster = true)"))
 
 function __init__()
     v = ccall((:trm_abi_version, LIB), Cint, ())
