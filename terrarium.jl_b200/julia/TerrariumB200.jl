@@ -110,7 +110,9 @@ model (the reference's own initializer code path) and uploaded with `trm_set_fie
 """
 function initialize_b200(model::Union{SoilModel{NF}, LandModel{NF}}, timestepper; device = 0, math = :faithful,
                          boundary_conditions = (;), initializers = (;)) where {NF}
-    ref = Terrarium.initialize(model, timestepper; boundary_conditions, initializers)   # CPU reference state at t0
+    # CPU reference state at t0 (initial interior values only: boundary conditions act from the first step on and may hold
+    # device-resident sources the CPU path does not know)
+    ref = Terrarium.initialize(model, timestepper; initializers)
     grid = Terrarium.get_field_grid(Terrarium.get_grid(model))
     zf = collect(Float64, Terrarium.znodes(grid, Terrarium.Face()))
     nz, ncol = length(zf) - 1, size(grid, 1)
