@@ -463,6 +463,20 @@ class RasterInputSource:
         return cls(values=data, times=times, reftime=0.0 if reftime is None else reftime)
 
 
+def raster_from_netcdf_files(paths: Sequence[str], variable: str, time: str = "time", reftime: Optional[float] = None) -> "RasterInputSource":
+    """One time-varying raster from several files that continue each other in time (one file per month or year, as
+    ERA5-Land is distributed): the time axes are decoded to seconds with each file's own CF units — they must share
+    the epoch — concatenated and checked to be strictly increasing."""
+    parts = [RasterInputSource.from_netcdf(p, variable, time=time, decode_times=True, reftime=0.0) for p in paths]
+    if not parts or any(p.times is None for p in parts):
+        raise ValueError("raster_from_netcdf_files needs files with a time axis")
+    times = np.concatenate([np.asarray(p.times, dtype=np.float64) for p in parts])
+    if np.any(np.diff(times) <= 0):
+        raise ValueError("the time axes of the files do not continue each other (different epochs or overlapping files?)")
+    values = np.concatenate([p.values for p in parts], axis=0)
+    return RasterInputSource(values=values, times=times, reftime=float(times[0]) if reftime is None else reftime)
+
+
 def cf_time_unit_seconds(units: Optional[str]) -> float:
     """Seconds per unit of a CF time axis (``"<unit> since <epoch>"``)."""
     unit = (units or "seconds").split()[0].lower()

@@ -186,3 +186,26 @@ def test_decoder_round_trips_random_layouts(tmp_path):
         os.remove(path)
 
     check()
+
+
+def test_raster_from_several_files(tmp_path):
+    """Monthly / yearly files concatenated along time (NetCDF-4 and NetCDF-3 mixed), epochs checked."""
+    from scipy.io import netcdf_file
+    a = np.arange(2 * 3 * 4, dtype="<f4").reshape(2, 3, 4)
+    b = 100 + np.arange(3 * 3 * 4, dtype="<f4").reshape(3, 3, 4)
+    p1, p2 = str(tmp_path / "m1.nc"), str(tmp_path / "m2.nc")
+    w = Writer(2)
+    w.add("time", np.array([0, 12], dtype="<i4"), layout="contiguous", attrs={"units": "hours since 2000-01-01"})
+    w.add("y", np.arange(3.0), layout="contiguous")
+    w.add("x", np.arange(4.0), layout="contiguous")
+    w.add("t2m", a, chunks=(1, 3, 4), deflate=3, dims=("time", "y", "x"))
+    w.save(p1)
+    with netcdf_file(p2, "w") as f:
+        f.createDimension("time", 3); f.createDimension("y", 3); f.createDimension("x", 4)
+        tv = f.createVariable("time", "f8", ("time",)); tv[:] = [1440.0, 2160.0, 2880.0]; tv.units = "minutes since 2000-01-01"
+        v = f.createVariable("t2m", "f4", ("time", "y", "x")); v[:] = b
+    src = trm.raster_from_netcdf_files([p1, p2], "t2m")
+    assert np.array_equal(src.times, np.array([0, 12, 24, 36, 48]) * 3600.0) and src.reftime == 0.0
+    assert np.array_equal(src.values, np.concatenate([a, b]).reshape(5, 12))
+    with pytest.raises(ValueError, match="continue each other"):
+        trm.raster_from_netcdf_files([p2, p1], "t2m")
