@@ -1,0 +1,54 @@
+"""Cross-check of the C++ oracle against an independently written numpy restatement (tests/numpy_column.py) of the
+coupled soil energy + Richards ForwardEuler step, on the BASELINE synthetic columns (CPU only: it pins the checker)."""
+import numpy as np
+import pytest
+
+from common import make, max_scaled_err, richards_soil, synthetic_columns, trm
+from numpy_column import Column
+
+
+def _run_both(ncol, nz, steps, dt, richards, unsat="vg", n=2.0, alpha=2.0, frozen=False):
+    lat, lon, T0 = synthetic_columns(ncol)
+    if frozen:
+        T0 = T0 - 12.0                       # a good part of the columns starts below 0 degC
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=nz), ncol)
+    zc = grid.znodes_center()
+    T_init = T0[None, :] - 0.05 * zc[:, None]
+    sat_init = (np.minimum(1.0, 0.5 - 0.1 * zc)[:, None] + 0 * T0[None, :]) if richards else np.full((nz, ncol), 0.8)
+    soil = richards_soil(alpha=alpha, n=n, unsat=unsat) if richards else trm.SoilEnergyWaterCarbon()
+    bcs = trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0))
+    integ = make("oracle", trm.SoilModel(grid, soil=soil), trm.ForwardEuler(dt=dt), boundary_conditions=bcs,
+                 initializers={"temperature": lambda x, z: T0[None, :] - 0.05 * z,
+                               "saturation_water_ice": (lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x) if richards else 0.8})
+    col = Column(grid.z_faces, T_init, sat_init, richards=richards, alpha=alpha, n=n, unsat=unsat)
+    assert max_scaled_err(integ.state.internal_energy.numpy(), col.U) <= 1e-14
+    for _ in range(steps):
+        col.step(dt, T0 + 10.0 * np.sin(2 * np.pi * col.t / 86400.0 - lon))
+    integ.step(dt, steps)
+    integ.compute_auxiliary()
+    return integ, col
+
+
+@pytest.mark.parametrize("unsat, n, alpha", [("vg", 2.0, 2.0), ("vg", 1.6, 1.2), ("linear", 2.0, 2.0)])
+def test_oracle_agrees_with_numpy_restatement_richards(unsat, n, alpha):
+    integ, col = _run_both(ncol=48, nz=30, steps=300, dt=60.0, richards=True, unsat=unsat, n=n, alpha=alpha)
+    s = integ.state
+    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-10
+    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-10
+    assert max_scaled_err(s.saturation_water_ice.numpy(), col.sat) <= 1e-10
+    assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-10
+    assert max_scaled_err(s.liquid_water_fraction.numpy(), col.liq) <= 1e-10
+    assert np.array_equal(s.water_table.numpy().reshape(-1), col.water_table)
+    assert np.allclose(s.surface_excess_water.numpy().reshape(-1), col.S_excess, rtol=1e-10, atol=1e-18)
+    assert np.abs(s.saturation_water_ice.numpy() - np.minimum(1.0, 0.5 - 0.1 * integ.grid.znodes_center())[:, None]).max() > 1e-4   # water moved
+
+
+def test_oracle_agrees_with_numpy_restatement_freeze_thaw():
+    """Heat-only (NoFlow) with phase change: columns start frozen, the daily cycle crosses 0 degC at the surface."""
+    integ, col = _run_both(ncol=48, nz=30, steps=400, dt=300.0, richards=False, frozen=True)
+    s = integ.state
+    liq = s.liquid_water_fraction.numpy()
+    assert (liq == 0).any() and (liq == 1).any() and ((liq > 0) & (liq < 1)).any()
+    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-10
+    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-10
+    assert max_scaled_err(liq, col.liq) <= 1e-10
