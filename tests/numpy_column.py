@@ -93,9 +93,9 @@ class Column:
             psi_m = np.where(sat < 1.0, -(1.0 / self.alpha) * (sat ** (-1.0 / m) - 1.0) ** (1.0 / self.n), 0.0)
         self.psi = np.maximum(0.0, self.water_table[None, :] - self.zc) + psi_m + (self.zc - self.zf[-1])
 
-    # -- one ForwardEuler step (forward_euler.jl:19-31; order of SURVEY A.10) ----------------------------------------------
-    def step(self, dt, T_top):
-        sat, liq, T, U, dz, dzf = self.sat, self.liq, self.T, self.U, self.dz, self.dzf
+    # -- tendencies at the current state (compute_tendencies!) ----------------------------------------------
+    def tendencies(self, T_top):
+        sat, liq, T, dz, dzf = self.sat, self.liq, self.T, self.dz, self.dzf
         nz = sat.shape[0]
         dsat = np.zeros_like(sat)
         if self.richards:
@@ -116,11 +116,14 @@ class Column:
         kf = 0.5 * (kc[1:] + kc[:-1])
         qh = -kf * (T_h[1:] - T_h[:-1]) / dzf
         dU = -(qh[1:] - qh[:-1]) / dz
-        # explicit step, closures
+        return dsat, dU
+
+    # -- explicit_step! + closures (abstract_timestepper.jl:65-141, soil closures) --------------------------------------------
+    def advance(self, dt, dsat, dU):
         if self.richards:
-            self.sat = sat + dt * dsat
+            self.sat = self.sat + dt * dsat
             self.hydrology_closure()
-        self.U = U + dt * dU
+        self.U = self.U + dt * dU
         Lt = self.L * self.sat * self.por
         with np.errstate(divide="ignore", invalid="ignore"):
             frac = np.where(Lt == 0, np.inf, self.U / (-Lt + EPS))            # safediv (utils.jl:25)
@@ -128,3 +131,18 @@ class Column:
         C = self.heat_capacity(self.sat, self.liq)
         self.T = np.where(self.U < -Lt, (self.U + Lt) / C, np.where(self.U >= 0, self.U / C, 0.0))
         self.t += dt
+
+    def step(self, dt, T_top):
+        """ForwardEuler (forward_euler.jl:19-31; order of SURVEY A.10)."""
+        self.advance(dt, *self.tendencies(T_top))
+
+    def heun_step(self, dt, T_top_now, T_top_next):
+        """Heun (heun.jl:37-71): tendencies at the state, an Euler stage with its closures, tendencies of the stage at
+        t + dt (its own inputs), the state advanced with the averaged tendencies."""
+        import copy
+        k1 = self.tendencies(T_top_now)
+        stage = copy.copy(self)
+        stage.sat, stage.U, stage.S_excess = self.sat.copy(), self.U.copy(), self.S_excess.copy()
+        stage.advance(dt, *k1)
+        k2 = stage.tendencies(T_top_next)
+        self.advance(dt, (k1[0] + k2[0]) / 2, (k1[1] + k2[1]) / 2)

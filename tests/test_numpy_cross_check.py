@@ -7,7 +7,7 @@ from common import make, max_scaled_err, richards_soil, synthetic_columns, trm
 from numpy_column import Column
 
 
-def _run_both(ncol, nz, steps, dt, richards, unsat="vg", n=2.0, alpha=2.0, frozen=False):
+def _run_both(ncol, nz, steps, dt, richards, unsat="vg", n=2.0, alpha=2.0, frozen=False, heun=False):
     lat, lon, T0 = synthetic_columns(ncol)
     if frozen:
         T0 = T0 - 12.0                       # a good part of the columns starts below 0 degC
@@ -17,13 +17,17 @@ def _run_both(ncol, nz, steps, dt, richards, unsat="vg", n=2.0, alpha=2.0, froze
     sat_init = (np.minimum(1.0, 0.5 - 0.1 * zc)[:, None] + 0 * T0[None, :]) if richards else np.full((nz, ncol), 0.8)
     soil = richards_soil(alpha=alpha, n=n, unsat=unsat) if richards else trm.SoilEnergyWaterCarbon()
     bcs = trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=86400.0))
-    integ = make("oracle", trm.SoilModel(grid, soil=soil), trm.ForwardEuler(dt=dt), boundary_conditions=bcs,
+    integ = make("oracle", trm.SoilModel(grid, soil=soil), (trm.Heun if heun else trm.ForwardEuler)(dt=dt), boundary_conditions=bcs,
                  initializers={"temperature": lambda x, z: T0[None, :] - 0.05 * z,
                                "saturation_water_ice": (lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x) if richards else 0.8})
     col = Column(grid.z_faces, T_init, sat_init, richards=richards, alpha=alpha, n=n, unsat=unsat)
     assert max_scaled_err(integ.state.internal_energy.numpy(), col.U) <= 1e-14
+    surface = lambda t: T0 + 10.0 * np.sin(2 * np.pi * t / 86400.0 - lon)
     for _ in range(steps):
-        col.step(dt, T0 + 10.0 * np.sin(2 * np.pi * col.t / 86400.0 - lon))
+        if heun:
+            col.heun_step(dt, surface(col.t), surface(col.t + dt))
+        else:
+            col.step(dt, surface(col.t))
     integ.step(dt, steps)
     integ.compute_auxiliary()
     return integ, col
@@ -52,3 +56,15 @@ def test_oracle_agrees_with_numpy_restatement_freeze_thaw():
     assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-10
     assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-10
     assert max_scaled_err(liq, col.liq) <= 1e-10
+
+
+@pytest.mark.parametrize("richards", [True, False], ids=["richards", "noflow"])
+def test_oracle_agrees_with_numpy_restatement_heun(richards):
+    integ, col = _run_both(ncol=32, nz=30, steps=200, dt=60.0 if richards else 300.0, richards=richards, frozen=not richards, heun=True)
+    s = integ.state
+    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-10
+    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-10
+    assert max_scaled_err(s.saturation_water_ice.numpy(), col.sat) <= 1e-10
+    assert max_scaled_err(s.liquid_water_fraction.numpy(), col.liq) <= 1e-10
+    if richards:
+        assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-10
