@@ -274,10 +274,20 @@ class File:
 
     def close(self):
         """Unmap the file. Arrays handed out earlier are copies and stay valid."""
-        if isinstance(self.buf, mmap.mmap):
-            self.buf.close()
-        self.buf = b""
-        self._fh.close()
+        buf, self.buf = getattr(self, "buf", b""), b""
+        if isinstance(buf, mmap.mmap):
+            try:
+                buf.close()
+            except BufferError:      # a zero-copy view handed out by numpy is still alive: left to the garbage collector
+                pass
+        if getattr(self, "_fh", None) is not None:
+            self._fh.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self
