@@ -370,7 +370,7 @@ def main():
                                    "UnsatKVanGenuchten, K_sat=1e-5), ForwardEuler dt=60 s, Nz=30 exponential grid, sinusoidal surface "
                                    "temperature evaluated on the device",
                        "columns": args.columns, "nz": NZ, "columns_per_gpu": ncol_local, "math": args.math,
-                       "model": args.model, "timestepper": args.timestepper,
+                       "processes": {"soil": "soil energy + Richards", "land": "bare-ground LandModel", "land-veg": "vegetated LandModel"}[args.model], "timestepper": args.timestepper,
                        "partition": "contiguous column ranges, no halo, no data-path collective",
                        "cache": "inputs larger than L2 (state read per step = %.1f GB per GPU)" % (2 * ncol_local * NZ * itemsize / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
