@@ -11,8 +11,8 @@
 // paths relative to /root/reference) and is pinned against every known-answer test the reference
 // holds for the path (tests/test_golden.py; vegetation / canopy: test/vegetation/*.jl,
 // test/surface_hydrology/canopy_*_tests.jl, tests/test_vegetation.py, which also holds an independent numpy
-// restatement of the per-column vegetation formulas; the soil energy + Richards step, ForwardEuler and Heun, is
-// cross-checked against a second, separately written numpy restatement in tests/test_numpy_cross_check.py).  Semantics that live
+// restatement of the per-column vegetation formulas; the soil energy + Richards step, ForwardEuler and Heun, and the
+// bare-ground LandModel step are cross-checked against a second, separately written numpy restatement in tests/test_numpy_cross_check.py).  Semantics that live
 // in the absent dependencies are restated from their published behaviour and are marked [OCN]
 // (Oceananigans) or [FC] (FreezeCurves); each is listed in DESIGN.md as "unpinned at rounding
 // level".

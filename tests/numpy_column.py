@@ -146,3 +146,59 @@ class Column:
         stage.advance(dt, *k1)
         k2 = stage.tendencies(T_top_next)
         self.advance(dt, (k1[0] + k2[0]) / 2, (k1[1] + k2[1]) / 2)
+
+
+class LandColumn(Column):
+    """Bare-ground ``LandModel`` (land_model.jl:45-108): the soil column above with the surface energy balance
+    (surface_energy_balance.jl:60-144, radiative_fluxes.jl, turbulent_fluxes.jl, skin_temperature.jl:62-80), bare-ground
+    evaporation (bare_ground_evaporation.jl:49-62) and direct runoff / infiltration (direct_surface_runoff.jl:87-117),
+    coupled to the soil through Flux boundary conditions on ``internal_energy`` (G) and ``saturation_water_ice``
+    (-infiltration), land_model.jl:56-62. Reference default parameters."""
+    rho_a, c_a, Llg, sigma, eps_mw, Tref = 1.293, 1005.7, 2.257e6, 5.6704e-8, 0.622, 273.15
+    albedo, emissivity, kappa_skin, C_h, V_min, tau_r, beta = 0.3, 0.97, 2.0, 1.2e-3, 0.01, 3600.0, 1.0
+
+    def __init__(self, z_faces, T, sat, Ts, **kw):
+        super().__init__(z_faces, T, sat, richards=True, **kw)
+        self.Ts = np.array(Ts, dtype=np.float64)
+
+    @staticmethod
+    def e_sat(T):
+        return np.where(T <= 0, 611.0 * np.exp(22.46 * T / (T + 272.62)), 611.0 * np.exp(17.62 * T / (T + 243.12)))
+
+    def humidity_deficit(self, Ts, q, p):
+        e_air = q * p / (self.eps_mw + (1 - self.eps_mw) * q)
+        vpd = np.maximum(self.e_sat(Ts) - e_air, 0.1)
+        return self.eps_mw * vpd / p
+
+    def surface(self, f):
+        """compute_auxiliary!(state, LandModel) after the soil hydraulics: surface hydrology, then the energy balance twice."""
+        r_a = 1.0 / (self.C_h * np.maximum(np.maximum(f["V"], self.V_min), 1.0e-6))
+        Kf = self.face_conductivity()
+        nz = self.sat.shape[0]
+        K_top, sat_top = Kf[nz], self.sat[-1]
+        self.E = self.beta * self.humidity_deficit(self.Ts, f["q"], f["p"]) / r_a
+        wet = self.S_excess > 0
+        drain = np.where(wet, np.maximum(self.S_excess, 0.0) / self.tau_r, 0.0)
+        influx = np.where(wet, drain, f["rain"])
+        self.infiltration = np.minimum(influx, K_top) * (sat_top < 1.0)
+        self.runoff = f["rain"] + drain - self.infiltration
+        Tg = self.T[-1]
+        for _ in range(2):                                 # land_model.jl:85-86
+            for update_skin in (True, False):              # fluxes, skin temperature, fluxes again (implicit skin temperature)
+                SW_up = self.albedo * f["SW"]
+                LW_up = self.emissivity * self.sigma * (self.Ts + self.Tref) ** 4 + (1 - self.emissivity) * f["LW"]
+                R_net = SW_up - f["SW"] + LW_up - f["LW"]
+                H_s = self.c_a * self.rho_a * ((self.Ts - f["Ta"]) / r_a)
+                H_l = self.Llg * self.rho_a * self.E
+                self.G = R_net - H_s - H_l
+                if update_skin:
+                    self.Ts = Tg - self.G * self.dz[-1, 0] / (2 * self.kappa_skin)
+        self.R_net, self.H_s, self.H_l = R_net, H_s, H_l
+
+    def land_step(self, dt, f):
+        """ForwardEuler: update_state! (auxiliaries, tendencies) and explicit_step! with the coupling Flux BCs."""
+        self.surface(f)
+        dsat, dU = self.tendencies(self.T[-1])             # default (zero-flux) temperature halo: 2 T_top - T_top
+        dU[-1] -= self.G / self.dz[-1, 0]
+        dsat[-1] -= (-self.infiltration) / self.dz[-1, 0]
+        self.advance(dt, dsat, dU)

@@ -68,3 +68,34 @@ def test_oracle_agrees_with_numpy_restatement_heun(richards):
     assert max_scaled_err(s.liquid_water_fraction.numpy(), col.liq) <= 1e-10
     if richards:
         assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-10
+
+
+def test_oracle_agrees_with_numpy_restatement_bare_ground_land_model():
+    """Bare-ground LandModel, ForwardEuler: surface energy balance, evaporation, runoff / infiltration and their Flux-BC
+    coupling to the soil, under the synthetic atmosphere of BASELINE.md section 5 (calm wind)."""
+    from common import synthetic_land_case
+    from numpy_column import LandColumn
+    ncol, nz, dt, steps = 24, 30, 60.0, 400
+    lat, lon, T0 = synthetic_columns(ncol)
+    integ = synthetic_land_case("oracle", ncol, windspeed=0.5, dt=dt)
+    zc = integ.grid.znodes_center()
+    col = LandColumn(integ.grid.z_faces, T0[None, :] - 0.05 * zc[:, None], np.minimum(1.0, 0.5 - 0.1 * zc)[:, None] + 0 * T0[None, :], T0)
+    day, wettest = 86400.0, 0.0
+    for _ in range(steps):
+        t = col.t
+        hour = t / 3600.0
+        h0 = int(np.floor(hour))
+        r0, r1 = (2.0e-8 if (h0 % 24) < 6 else 0.0), (2.0e-8 if ((h0 + 1) % 24) < 6 else 0.0)
+        rain = r0 + (r1 - r0) * (hour - h0)                # hourly table, linear in time (FieldTimeSeries[Time(t)])
+        col.land_step(dt, dict(Ta=T0 + 8.0 * np.sin(2 * np.pi * t / day - lon), SW=np.maximum(600.0 * np.sin(2 * np.pi * t / day - lon), 0.0),
+                               LW=300.0, q=0.005, p=101325.0, V=0.5, rain=rain + 0 * T0))
+        wettest = max(wettest, float(col.infiltration.max()))
+    integ.step(dt, steps)
+    s = integ.state
+    for name, mine in (("temperature", col.T), ("internal_energy", col.U), ("saturation_water_ice", col.sat), ("pressure_head", col.psi)):
+        assert max_scaled_err(getattr(s, name).numpy(), mine) <= 1e-10, name
+    assert max_scaled_err(s.skin_temperature.numpy().reshape(-1), col.Ts) <= 1e-10
+    for name, mine in (("ground_heat_flux", col.G), ("latent_heat_flux", col.H_l), ("sensible_heat_flux", col.H_s), ("surface_net_radiation", col.R_net),
+                       ("infiltration", col.infiltration), ("evaporation_ground", col.E), ("surface_runoff", col.runoff)):
+        assert np.allclose(getattr(s, name).numpy().reshape(-1), mine, rtol=1e-9, atol=1e-9 * max(np.abs(mine).max(), 1e-30)), name
+    assert wettest > 1e-8 and np.abs(col.Ts - T0).max() > 1.0      # it rained into the soil; the skin temperature moved
