@@ -202,3 +202,24 @@ class LandColumn(Column):
         dU[-1] -= self.G / self.dz[-1, 0]
         dsat[-1] -= (-self.infiltration) / self.dz[-1, 0]
         self.advance(dt, dsat, dU)
+
+    def _coupled(self, dsat, dU):
+        """compute_z_bcs! at explicit_step! time: the Flux BCs take the current ground heat flux / infiltration fields."""
+        dsat, dU = dsat.copy(), dU.copy()
+        dU[-1] -= self.G / self.dz[-1, 0]
+        dsat[-1] -= (-self.infiltration) / self.dz[-1, 0]
+        return dsat, dU
+
+    def land_heun_step(self, dt, f_now, f_next):
+        """Heun (heun.jl:37-71): the boundary fluxes are added when a state is stepped, from that state's own fields, so the
+        final step uses the fluxes evaluated at time t (they are not averaged); the skin temperature of the state is the one
+        of its own ``compute_auxiliary!`` at time t."""
+        import copy
+        self.surface(f_now)
+        k1 = self.tendencies(self.T[-1])
+        stage = copy.copy(self)
+        stage.sat, stage.U, stage.S_excess, stage.Ts = self.sat.copy(), self.U.copy(), self.S_excess.copy(), self.Ts.copy()
+        stage.advance(dt, *stage._coupled(*k1))
+        stage.surface(f_next)
+        k2 = stage.tendencies(stage.T[-1])
+        self.advance(dt, *self._coupled((k1[0] + k2[0]) / 2, (k1[1] + k2[1]) / 2))

@@ -70,25 +70,32 @@ def test_oracle_agrees_with_numpy_restatement_heun(richards):
         assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-10
 
 
-def test_oracle_agrees_with_numpy_restatement_bare_ground_land_model():
-    """Bare-ground LandModel, ForwardEuler: surface energy balance, evaporation, runoff / infiltration and their Flux-BC
+@pytest.mark.parametrize("heun", [False, True], ids=["euler", "heun"])
+def test_oracle_agrees_with_numpy_restatement_bare_ground_land_model(heun):
+    """Bare-ground LandModel, ForwardEuler and Heun: surface energy balance, evaporation, runoff / infiltration and their Flux-BC
     coupling to the soil, under the synthetic atmosphere of BASELINE.md section 5 (calm wind)."""
     from common import synthetic_land_case
     from numpy_column import LandColumn
     ncol, nz, dt, steps = 24, 30, 60.0, 400
     lat, lon, T0 = synthetic_columns(ncol)
-    integ = synthetic_land_case("oracle", ncol, windspeed=0.5, dt=dt)
+    integ = synthetic_land_case("oracle", ncol, windspeed=0.5, dt=dt, heun=heun)
     zc = integ.grid.znodes_center()
     col = LandColumn(integ.grid.z_faces, T0[None, :] - 0.05 * zc[:, None], np.minimum(1.0, 0.5 - 0.1 * zc)[:, None] + 0 * T0[None, :], T0)
     day, wettest = 86400.0, 0.0
-    for _ in range(steps):
-        t = col.t
+
+    def forcing(t):
         hour = t / 3600.0
         h0 = int(np.floor(hour))
         r0, r1 = (2.0e-8 if (h0 % 24) < 6 else 0.0), (2.0e-8 if ((h0 + 1) % 24) < 6 else 0.0)
         rain = r0 + (r1 - r0) * (hour - h0)                # hourly table, linear in time (FieldTimeSeries[Time(t)])
-        col.land_step(dt, dict(Ta=T0 + 8.0 * np.sin(2 * np.pi * t / day - lon), SW=np.maximum(600.0 * np.sin(2 * np.pi * t / day - lon), 0.0),
-                               LW=300.0, q=0.005, p=101325.0, V=0.5, rain=rain + 0 * T0))
+        return dict(Ta=T0 + 8.0 * np.sin(2 * np.pi * t / day - lon), SW=np.maximum(600.0 * np.sin(2 * np.pi * t / day - lon), 0.0),
+                    LW=300.0, q=0.005, p=101325.0, V=0.5, rain=rain + 0 * T0)
+
+    for _ in range(steps):
+        if heun:
+            col.land_heun_step(dt, forcing(col.t), forcing(col.t + dt))
+        else:
+            col.land_step(dt, forcing(col.t))
         wettest = max(wettest, float(col.infiltration.max()))
     integ.step(dt, steps)
     s = integ.state
