@@ -37,13 +37,13 @@ def _run_both(ncol, nz, steps, dt, richards, unsat="vg", n=2.0, alpha=2.0, froze
 def test_oracle_agrees_with_numpy_restatement_richards(unsat, n, alpha):
     integ, col = _run_both(ncol=48, nz=30, steps=300, dt=60.0, richards=True, unsat=unsat, n=n, alpha=alpha)
     s = integ.state
-    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-10
-    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-10
-    assert max_scaled_err(s.saturation_water_ice.numpy(), col.sat) <= 1e-10
-    assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-10
-    assert max_scaled_err(s.liquid_water_fraction.numpy(), col.liq) <= 1e-10
+    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-12
+    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-12
+    assert max_scaled_err(s.saturation_water_ice.numpy(), col.sat) <= 1e-12
+    assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-12
+    assert max_scaled_err(s.liquid_water_fraction.numpy(), col.liq) <= 1e-12
     assert np.array_equal(s.water_table.numpy().reshape(-1), col.water_table)
-    assert np.allclose(s.surface_excess_water.numpy().reshape(-1), col.S_excess, rtol=1e-10, atol=1e-18)
+    assert np.allclose(s.surface_excess_water.numpy().reshape(-1), col.S_excess, rtol=1e-12, atol=1e-18)
     assert np.abs(s.saturation_water_ice.numpy() - np.minimum(1.0, 0.5 - 0.1 * integ.grid.znodes_center())[:, None]).max() > 1e-4   # water moved
 
 
@@ -53,21 +53,21 @@ def test_oracle_agrees_with_numpy_restatement_freeze_thaw():
     s = integ.state
     liq = s.liquid_water_fraction.numpy()
     assert (liq == 0).any() and (liq == 1).any() and ((liq > 0) & (liq < 1)).any()
-    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-10
-    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-10
-    assert max_scaled_err(liq, col.liq) <= 1e-10
+    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-12
+    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-12
+    assert max_scaled_err(liq, col.liq) <= 1e-12
 
 
 @pytest.mark.parametrize("richards", [True, False], ids=["richards", "noflow"])
 def test_oracle_agrees_with_numpy_restatement_heun(richards):
     integ, col = _run_both(ncol=32, nz=30, steps=200, dt=60.0 if richards else 300.0, richards=richards, frozen=not richards, heun=True)
     s = integ.state
-    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-10
-    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-10
-    assert max_scaled_err(s.saturation_water_ice.numpy(), col.sat) <= 1e-10
-    assert max_scaled_err(s.liquid_water_fraction.numpy(), col.liq) <= 1e-10
+    assert max_scaled_err(s.temperature.numpy(), col.T) <= 1e-12
+    assert max_scaled_err(s.internal_energy.numpy(), col.U) <= 1e-12
+    assert max_scaled_err(s.saturation_water_ice.numpy(), col.sat) <= 1e-12
+    assert max_scaled_err(s.liquid_water_fraction.numpy(), col.liq) <= 1e-12
     if richards:
-        assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-10
+        assert max_scaled_err(s.pressure_head.numpy(), col.psi) <= 1e-12
 
 
 @pytest.mark.parametrize("heun", [False, True], ids=["euler", "heun"])
@@ -100,8 +100,8 @@ def test_oracle_agrees_with_numpy_restatement_bare_ground_land_model(heun):
     integ.step(dt, steps)
     s = integ.state
     for name, mine in (("temperature", col.T), ("internal_energy", col.U), ("saturation_water_ice", col.sat), ("pressure_head", col.psi)):
-        assert max_scaled_err(getattr(s, name).numpy(), mine) <= 1e-10, name
-    assert max_scaled_err(s.skin_temperature.numpy().reshape(-1), col.Ts) <= 1e-10
+        assert max_scaled_err(getattr(s, name).numpy(), mine) <= 1e-12, name
+    assert max_scaled_err(s.skin_temperature.numpy().reshape(-1), col.Ts) <= 1e-12
     for name, mine in (("ground_heat_flux", col.G), ("latent_heat_flux", col.H_l), ("sensible_heat_flux", col.H_s), ("surface_net_radiation", col.R_net),
                        ("infiltration", col.infiltration), ("evaporation_ground", col.E), ("surface_runoff", col.runoff)):
         assert np.allclose(getattr(s, name).numpy().reshape(-1), mine, rtol=1e-9, atol=1e-9 * max(np.abs(mine).max(), 1e-30)), name
