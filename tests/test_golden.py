@@ -519,3 +519,26 @@ def test_land_model_default_soil_is_immobile_water(engine, stepper):
     assert np.all(np.isfinite(G)) and np.all(G != 0)
     dU = integ.state.internal_energy.numpy() - U0
     assert np.all(np.sign(dU[-1]) == -np.sign(G))                                # G > 0 (upward) cools the top layer
+
+
+# ---------------------------------------------------------------------------------------------
+# 13. volumetric fractions -- test/soil/soil_composition_tests.jl:30-46 (por 0.3, sat 0.5, organic 0.5):
+#     water = por sat liq, ice = por sat (1 - liq), air = por (1 - sat), organic = (1 - por) org, mineral = (1 - por)(1 - org).
+#     Each fraction is read off the initial energy U = T C - L sat por (1 - liq) with a unit heat capacity for one constituent
+#     (the CPU restatement only: this pins the checker's composition; the CUDA path shares the parity tests with it)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("constituent, T0, expect", [
+    ("water", 2.0, 0.3 * 0.5), ("ice", -2.0, 0.3 * 0.5), ("air", 2.0, 0.3 * 0.5), ("organic", 2.0, 0.7 * 0.5), ("mineral", 2.0, 0.7 * 0.5)])
+def test_volumetric_fractions(constituent, T0, expect):
+    por, sat, org = 0.3, 0.5, 0.5
+    caps = trm.SoilHeatCapacities(water=0.0, ice=0.0, air=0.0, mineral=0.0, organic=0.0)
+    setattr(caps, constituent, 1.0)
+    soil = trm.SoilEnergyWaterCarbon(
+        energy=trm.SoilEnergyBalance(thermal_properties=trm.SoilThermalProperties(heat_capacities=caps)),
+        strat=trm.HomogeneousStratigraphy(porosity=trm.ConstantSoilPorosity(mineral_porosity=por, organic_porosity=por)),
+        biogeochem=trm.ConstantSoilCarbonDensity(rho_soc=org * (1 - por) * 1300.0))   # org = rho_soc / ((1 - por_o) rho_org)
+    integ = make("oracle", trm.SoilModel(column(trm.UniformSpacing(dz=0.1, N=4)), soil=soil), trm.ForwardEuler(),
+                 initializers={"temperature": T0, "saturation_water_ice": sat})
+    U = integ.state.internal_energy.numpy()[:, 0]
+    latent = 1000.0 * 3.34e5 * sat * por if T0 < 0 else 0.0
+    assert np.allclose((U + latent) / T0, expect, rtol=1e-12)
