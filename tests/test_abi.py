@@ -176,6 +176,13 @@ def test_julia_glue_matches_the_abi():
             n = a.TRM_BC_NSLOTS if n == "TRM_BC_NSLOTS" else int(n)
             size += n * {"Cdouble": 8, "Int64": 8, "Int32": 4, "Ptr{Cdouble}": 8, "TrmBC": 8, "TrmParams": C.sizeof(a.trm_params)}[base]
         return size
+    def field_names(name):
+        body = re.sub(r"#.*", "", re.search(rf"struct {name}\b(.*?)\nend", text, re.S).group(1))
+        return re.findall(r"(\w+)::", body)
+    assert field_names("TrmConfig") == [f[0] for f in a.trm_config._fields_]
+    julia_params, c_params = field_names("TrmParams"), [f[0] for f in a.trm_params._fields_]
+    assert julia_params[-1] == "vegetation" and julia_params[:-1] == c_params[:len(julia_params) - 1]
+    assert len(c_params) - (len(julia_params) - 1) == 40          # the NTuple{40} block = the vegetation / canopy parameters
     assert struct_bytes("TrmParams") == C.sizeof(a.trm_params)
     assert struct_bytes("TrmConfig") == C.sizeof(a.trm_config)
     assert struct_bytes("TrmDiag") == C.sizeof(a.trm_diag)
