@@ -42,3 +42,13 @@ def test_b200_arm_needs_a_gpu():
         pytest.skip("a GPU is present")
     r = _run(["--steps", "1", "--warmup", "1"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_reference_benchmark_design_script_runs_on_the_cpu_arm(tmp_path):
+    out = str(tmp_path / "design.csv")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "reference_benchmark_design.py"), "--engine", "oracle",
+                        "--max-i", "2", "--samples", "2", "--out", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = open(out).read().strip().splitlines()
+    assert rows[0].split(",")[:4] == ["nrings", "npoints", "min_time_ms", "mid_time_ms"] and len(rows) == 3
+    assert [int(x.split(",")[1]) for x in rows[1:]] == [32, 128]          # FullGaussianGrid(2), (4): 8 n^2 points
