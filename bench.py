@@ -210,6 +210,10 @@ def main():
     ap.add_argument("--cpu-columns", type=int, default=1048576, help="columns of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="mapped", choices=["mapped", "copy"],
+                    help="end-to-end leg: `mapped` = trm_bind_host_io (the stage kernel reads the forcing from / writes the ground "
+                         "temperature to page-locked host memory, one trm_step_async per step); `copy` = trm_set_input_field_async + "
+                         "trm_step_async + trm_get_field_async (copy engines, three calls per step)")
     ap.add_argument("--model", default="soil", choices=["soil", "land", "land-veg"],
                     help="secondary workloads (not the headline): bare-ground LandModel, LandModel with PALADYN vegetation")
     ap.add_argument("--timestepper", default="euler", choices=["euler", "heun"], help="secondary workloads: Heun (two stage launches per step)")
@@ -299,21 +303,46 @@ def main():
     #      overlap the stage kernel of the neighbouring steps; the timed region ends with trm_sync.
     e2e = None
     if not args.no_e2e:
-        tdtype = torch.float64 if nf == np.float64 else torch.float32
         k2 = max(3, args.steps)   # same step count as the kernel-only measurement
-        NBUF = 4                  # pinned host buffers are reused round robin (a fresh upload / download every step)
+        NBUF = 4                  # host buffers are reused round robin (fresh forcing in / ground temperature out every step)
         in_id = integ._bc_inputs["T_ub"]
         gt_id = trm.abi.FIELD_IDS["ground_temperature"]
         t = integ.clock.time
-        forc = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(NBUF)]
-        outs = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(NBUF)]
-        for i, f in enumerate(forc):   # the host-side "atmosphere": this step's surface temperature per column
-            f.copy_(torch.from_numpy((T0 + 10.0 * np.sin(2 * np.pi * (t + i * DT) / 86400.0 - lon)).astype(nf)))
 
-        def e2e_step(i):
-            lib.check(lib.set_input_field_async(h, in_id, C.c_void_p(forc[i % NBUF].data_ptr())), "set_input_field_async")
-            lib.check(lib.step_async(h, DT, 1), "step_async")
-            lib.check(lib.get_field_async(h, gt_id, C.c_void_p(outs[i % NBUF].data_ptr()), ncol_local), "get_field_async")
+        def forcing(i):   # the host-side "atmosphere": this step's surface temperature per column
+            return (T0 + 10.0 * np.sin(2 * np.pi * (t + i * DT) / 86400.0 - lon)).astype(nf)
+
+        if args.e2e_mode == "mapped":
+            ring_in, ring_out = integ.bind_host_io("T_ub", "ground_temperature", nslots=NBUF)
+            it0 = integ.clock.iteration
+            for i in range(NBUF):
+                ring_in[(it0 + i) % NBUF, :] = forcing(i)
+
+            def e2e_step(i):
+                # the coupler owns slot (it0 + i) % NBUF again once the step that used it last has completed: that is
+                # where it would read that step's ground temperature and write this step's forcing
+                if i >= NBUF:
+                    integ.host_io_wait(it0 + i - NBUF + 1)
+                lib.check(lib.step_async(h, DT, 1), "step_async")
+            what = ("per step: ONE call, trm_step_async; the stage kernel reads that step's surface temperature forcing from, and "
+                    "writes the ground temperature to, page-locked mapped host memory (trm_bind_host_io, %d-slot rings; the host "
+                    "waits for the step that last used a slot before reusing it); wall clock around the loop incl. final trm_sync, "
+                    "max over ranks" % NBUF)
+            outs = ring_out
+        else:
+            tdtype = torch.float64 if nf == np.float64 else torch.float32
+            forc = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(NBUF)]
+            outs = [torch.empty(ncol_local, dtype=tdtype).pin_memory() for _ in range(NBUF)]
+            for i, f in enumerate(forc):
+                f.copy_(torch.from_numpy(forcing(i)))
+
+            def e2e_step(i):
+                lib.check(lib.set_input_field_async(h, in_id, C.c_void_p(forc[i % NBUF].data_ptr())), "set_input_field_async")
+                lib.check(lib.step_async(h, DT, 1), "step_async")
+                lib.check(lib.get_field_async(h, gt_id, C.c_void_p(outs[i % NBUF].data_ptr()), ncol_local), "get_field_async")
+            what = ("per step: trm_set_input_field_async(surface temperature forcing, pinned host) + trm_step_async + "
+                    "trm_get_field_async(ground_temperature -> pinned host); copies overlap the stage kernel on copy "
+                    "streams; wall clock around the loop incl. final trm_sync, max over ranks")
 
         for i in range(3):
             e2e_step(i)
@@ -327,11 +356,17 @@ def main():
         el = td.max_over_ranks(time.perf_counter() - w0)
         e2e = {"value": total_cells * k2 / el, "unit": UNIT, "h2d_bytes_per_step": args.columns * itemsize,
                "d2h_bytes_per_step": args.columns * itemsize, "steps": k2, "ms_per_step": 1e3 * el / k2,
-               "what": "per step: trm_set_input_field_async(surface temperature forcing, pinned host) + trm_step_async + "
-                       "trm_get_field_async(ground_temperature -> pinned host); copies overlap the stage kernel on copy "
-                       "streams; wall clock around the loop incl. final trm_sync, max over ranks",
+               "mode": args.e2e_mode, "what": what,
                "host_cpus_of_rank0": len(numa_cpus) if numa_cpus else None}
-        assert all(bool(torch.isfinite(o).all()) for o in outs[3:3 + k2])
+        if args.e2e_mode == "mapped":
+            # the last step's slot holds the ground temperature the library reports for the final state
+            last = (it0 + 3 + k2 - 1) % NBUF
+            gt = integ.state.ground_temperature.numpy()
+            assert np.array_equal(np.asarray(ring_out[last]), gt), "mapped host output differs from ground_temperature"
+            assert bool(np.isfinite(np.asarray(ring_out)).all())
+            lib.check(lib.bind_host_io(h, -1, None, -1, None, 0), "unbind_host_io")
+        else:
+            assert all(bool(torch.isfinite(o).all()) for o in outs)
 
     peak, peak_src = peaks()
     bpc = algorithmic_bytes_per_cell(itemsize, NZ, args.model, args.timestepper == "heun")

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TRM_ABI_VERSION 2
+#define TRM_ABI_VERSION 3
 #define TRM_MAX_NZ 128       /* per-column layers supported by the fused kernels            */
 #define TRM_NUM_USER_INPUTS 8
 
@@ -336,6 +336,10 @@ int trm_get_input(trm_handle* h, int input_id, void* host, int64_t count);
 /* initialize!(state, model) after the user initializers ran: hydrology closure + hydraulics,
  * then the inverse energy closure T -> U (src/processes/soil/soil_coupled.jl:45-54). */
 int trm_initialize(trm_handle* h);
+/* reset!(integrator.state) at the top of initialize!(integrator) (model_integrator.jl:98): zeroes every state, auxiliary,
+ * stage and accumulator field and the clock. Call it BEFORE writing the initial conditions of a re-initialisation
+ * (a fresh handle is already zero). Inputs / boundary sources and the grid are kept. */
+int trm_reset(trm_handle* h);
 /* nsteps x timestep!(integrator, dt; finalize = false) (forward_euler.jl:19-31, heun.jl:37-71):
  * one fused kernel launch per timestepper stage (ForwardEuler: one per step, Heun: two per step). */
 int trm_step(trm_handle* h, double dt, int64_t nsteps);
@@ -347,6 +351,8 @@ int trm_compute_auxiliary(trm_handle* h);
 int trm_compute_tendencies(trm_handle* h);
 
 int trm_get_clock(trm_handle* h, double* time, int64_t* iteration);
+/* (restart from a snapshot: set the fields, then the clock; the time is rounded to NF like the reference's clock and
+ * also becomes the time of the last update_inputs!, so that diagnostics before the first step see the restart time) */
 int trm_set_clock(trm_handle* h, double time, int64_t iteration);
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
@@ -381,6 +387,25 @@ int trm_get_accumulated(trm_handle* h, int field_id, void* host, int64_t count, 
  * a CUDA binding of its own (the Julia / Python host side) can own pinned buffers. */
 int trm_host_alloc(int64_t bytes, void** host);
 int trm_host_free(void* host);
+/* Same with flags: TRM_HOST_WRITE_COMBINED for buffers the host only writes and the GPU only reads (forcing rings). */
+enum trm_host_flags { TRM_HOST_DEFAULT = 0, TRM_HOST_WRITE_COMBINED = 1 };
+int trm_host_alloc_ex(int64_t bytes, int32_t flags, void** host);
+
+/* ---- per-step exchange with a host-side coupler through mapped host memory -------------------------------
+ * Coupled-model usage (examples/simulations/speedy_dry_land.jl:45-68: every coupling step the atmosphere hands the land
+ * model its forcing and reads the surface state back) without a copy per step: the stage kernel itself reads the
+ * per-column input from, and writes the 2-D result field to, page-locked host memory that is mapped into the device's
+ * address space (trm_host_alloc / trm_host_alloc_ex). No copy engine, no staging buffer, no event chain: a coupled
+ * step is ONE call, trm_step_async(h, dt, 1).
+ *   host_in  : nslots x ncol values (NF); the step that advances the clock from iteration k to k+1 reads the values of
+ *              input `input_id` from slot k % nslots (a TRM_SRC_FIELD input: constant over the step, both Heun stages);
+ *   host_out : nslots x ncol values (NF); the same step stores field `field_id` (any 2-D field of the model) of the
+ *              NEW state in slot k % nslots. TRM_F_GROUND_TEMPERATURE is written by the stage kernel itself.
+ * Either pointer may be NULL (one direction only); both NULL removes the binding. trm_host_io_wait(h, k) returns once
+ * the step that produced iteration k has completed: its output slot may be read and its input slot refilled. The
+ * binding starts at the handle's current iteration (trm_get_clock). */
+int trm_bind_host_io(trm_handle* h, int input_id, const void* host_in, int field_id, void* host_out, int32_t nslots);
+int trm_host_io_wait(trm_handle* h, int64_t iteration);
 
 /* ---- ColumnRingGrid conversions (src/grids/column_ring_grid.jl:102-149) --------------------------------
  * The columns of a ColumnRingGrid are the `true` points of a mask over a ring grid of `nring` points, in ring

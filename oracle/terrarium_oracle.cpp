@@ -830,6 +830,15 @@ struct Oracle {
         return TRM_OK;
     }
     int aux() { compute_auxiliary(st); return TRM_OK; }
+    // reset!(integrator.state), model_integrator.jl:98: fields and clock back to zero (inputs are re-read by update_inputs!)
+    int reset() {
+        auto in_keep = st.in;
+        st = State<NF>(); st.alloc(nz, nc, land, veg); st.in = in_keep;
+        stage = State<NF>();   // (Heun copies the whole state into its stage at every step, heun.jl:45)
+        for (auto& a : acc) std::fill(a.begin(), a.end(), 0.0);
+        initialized = false;
+        return TRM_OK;
+    }
     int tendencies() {
         update_state(st);
         // show what explicit_step! would integrate: add the flux BCs on a scratch copy
@@ -1077,6 +1086,7 @@ int orc_set_clock(trm_handle* h_, double t, int64_t it) {
     return TRM_OK;
 }
 int orc_diagnostics(trm_handle* h, trm_diag* d) { return DISPATCH((Handle*)h, diagnostics(d)); }
+int orc_reset(trm_handle* h) { return DISPATCH((Handle*)h, reset()); }
 int64_t orc_array_passes(trm_handle* h_) { Handle* h = (Handle*)h_; return h->dtype == TRM_F32 ? h->f32->passes : h->f64->passes; }
 int orc_num_threads(void) {
 #ifdef _OPENMP

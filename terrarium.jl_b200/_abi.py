@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-TRM_ABI_VERSION = 2
+TRM_ABI_VERSION = 3
 TRM_MAX_NZ = 128
 TRM_NUM_USER_INPUTS = 8
 
@@ -152,12 +152,16 @@ SIGNATURES = {
     "get_accumulated": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int32]),
     "host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "host_free": (C.c_int, [C.c_void_p]),
+    "host_alloc_ex": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bind_host_io": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int32]),
+    "host_io_wait": (C.c_int, [_H, C.c_int64]),
+    "reset": (C.c_int, [_H]),
     "set_ring_index": (C.c_int, [_H, C.POINTER(C.c_int64), C.c_int64]),
     "get_field_ring": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.c_double]),
     "set_field_ring": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
 }
 # entry points that only make sense on a device and that the CPU oracle does not export
-DEVICE_ONLY = ("field_ptr", "field_view", "host_alloc", "host_free", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size",
+DEVICE_ONLY = ("field_ptr", "field_view", "host_alloc", "host_free", "host_alloc_ex", "bind_host_io", "host_io_wait", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size",
                "set_input_field_async", "step_async", "get_field_async", "set_ring_index", "get_field_ring",
                "set_field_ring")
 

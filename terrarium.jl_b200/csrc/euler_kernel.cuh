@@ -78,7 +78,7 @@ __device__ __forceinline__ bool below_one(float v)  { return __float_as_int(v) <
 // EF_KF + 1) and, for the vegetated LandModel, the running soil moisture limiting factor of the state being written
 // (EF_BETA). The LandModel variants do not evaluate the surface block: surface_kernel (stage_kernel.cuh) has run before
 // and left the ground heat flux and the infiltration in their 2-D fields.
-enum EulerField { EF_KF = 0, EF_T = 2, EF_P, EF_KAP, EF_KC, EF_QH, EF_G, EF_DQH, EF_QD, EF_BETA, EF_COUNT };
+enum EulerField { EF_KF = 0, EF_T = 2, EF_P, EF_KAP, EF_KC, EF_QH, EF_G, EF_DQH, EF_QD, EF_BETA, EF_BCT /* prefetched TEMPERATURE_TOP boundary value */, EF_COUNT };
 #ifndef TRM_EULER_DIST
 #define TRM_EULER_DIST 4   // measured on the 10 M-column step: 3 layers ahead 3.675 ms, 4: 3.638, 5: 3.646
 #endif
@@ -156,6 +156,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         return eval_input(A.in[A.bc[slot].input], c, kind == TRM_BC_FLUX ? A.t_b : A.t_x, kind == TRM_BC_FLUX ? 1 : 0);
     };
     const NF wtx = (RICH && !LOAD) ? A.xWt[c] : NF(0);
+    // per-column surface temperature vector (device memory, or mapped host memory bound with trm_bind_host_io): fetched
+    // now, together with the first layer, and consumed ~nz iterations later when the halo above the surface is formed
+    const bool bct_pre = A.bct_pre != 0;
+    if (bct_pre) cp_async<ES>(strip0 + (uint32_t)(EF_BCT * B * ES), A.in[A.bc[TRM_BC_TEMPERATURE_TOP].input].a + c);
 
     // ---- raw prefetch ring: layer k lives in ring slot (k & 3); one cp.async group per layer ----
     // element offsets fit 32 bits (the launcher checks nz * ld < 2^32): one IMAD.WIDE.U32 per address
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 wr(EF_KC, Kcn);
             }
         } else if (!inner && m == nz + 1) {   // halo above the surface, built from layer nz (prv)
-            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(EF_T), bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
+            Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(EF_T), bct_pre ? rd(EF_BCT) : bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
             // conductivity of the halo cell: same (sat, liq) as layer nz when the saturation halo is a copy, else
             // sat = 0, for which the liquid fraction drops out of the constituent sum
             const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                                                         : plant_available_water(A.vp, p, sn, lc) * met.root(j) / met.dzc(j) * met.dzc(j)));
                     if (CLOSE) {
                         stg(A.yT + o, Tc); stg(A.yL + o, lc);
+                        if (!inner && j == nz && A.hio_out) A.hio_out[c] = Tc;   // ground temperature -> mapped host memory
                         // layers below the water table wait for it (written after the sweep)
                         if (RICH && idx != 0) stg(A.yP + o, pressure_head<NF, FAST, VG2>(p, sn, wt_new, met.zC(j), met.psiz(j)));
                     }
@@ -441,6 +446,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 beta += FAST ? plant_available_water_fast(A.vp, p, s, lc) * met.root(k) : plant_available_water(A.vp, p, s, lc) * met.root(k) / met.dzc(k) * met.dzc(k);
             if (H1) continue;   // the stage state keeps no closure fields
             A.yT[o] = Tc; A.yL[o] = lc;
+            if (k == nz && A.hio_out) A.hio_out[c] = Tc;
             A.yP[o] = pressure_head<NF, FAST, VG2>(p, s, wt_new, met.zC(k), met.psiz(k));
         }
         if (LAND && has_veg(A)) A.ybeta[c] = beta;

@@ -25,11 +25,15 @@ cudaError_t launch_phys(int variant, const StageArgs<NF>& a, int block, cudaStre
 template <class NF, int PHYS, int LOAD, int MS, int MODE, bool VG2 = false>
 cudaError_t launch_euler_variant(const StageArgs<NF>& a, cudaStream_t st) {
     constexpr size_t smem = EulerSmem<NF, LOAD, MS, MODE>::BYTES;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to more than 48 KB of dynamic shared memory is a per-device attribute of the function: one flag per
+    // device ordinal (handles on several GPUs may live in one process, e.g. two Julia integrators)
+    static bool configured[64] = {false};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE, VG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t nblk = (a.ncol + TRM_EULER_BLOCK - 1) / TRM_EULER_BLOCK;
     euler_kernel<NF, PHYS, LOAD, kFast, MS, MODE, VG2><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);

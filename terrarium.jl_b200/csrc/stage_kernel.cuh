@@ -122,6 +122,13 @@ struct StageArgs {
     // state a stage kernel writes (accumulated there while the closure fields of the new state are formed)
     const NF* xbeta;
     NF* ybeta;
+    // per-step exchange with a host-side coupler (trm_bind_host_io): when non-null, the temperature of the top layer of
+    // the state this launch writes (ground_temperature) is also stored here -- a device pointer to page-locked, mapped
+    // host memory, written straight from the stage kernel (no copy engine, no staging buffer)
+    NF* hio_out;
+    // the TEMPERATURE_TOP boundary value is a per-column vector (TRM_SRC_FIELD, possibly mapped host memory): the staged
+    // kernel fetches it with cp.async at kernel start instead of a synchronous load at the top of the column
+    int32_t bct_pre, pad3_;
     VegParams<NF> vp;
     const NF* metrics;   // [MET_COUNT][MET_STRIDE], see enum Metric
     DevParams<NF> p;
@@ -648,6 +655,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                         NF Tc, lc;
                         energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
                         A.yT[o] = Tc; A.yL[o] = lc;
+                        if (j == nz && A.hio_out) A.hio_out[c] = Tc;
                         // layers below the water table wait for it (written after the sweep)
                         if (RICH && idx != 0) A.yP[o] = pressure_head<NF, FAST>(p, sn, wt_new, met.zC(j), met.psiz(j));
                     }
@@ -719,6 +727,7 @@ __global__ void __launch_bounds__(TRM_MAX_BLOCK, TRM_MIN_BLOCKS) stage_kernel(co
                 NF s = A.yS[o], U = A.yU[o], Tc, lc;
                 energy_to_temperature<NF, FAST>(p, U, s, Tc, lc);
                 A.yT[o] = Tc; A.yL[o] = lc;
+                if (k == nz && A.hio_out) A.hio_out[c] = Tc;
                 A.yP[o] = pressure_head<NF, FAST>(p, s, wt_new, met.zC(k), met.psiz(k));
             }
         }

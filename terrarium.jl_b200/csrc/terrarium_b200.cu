@@ -31,6 +31,12 @@ int fail(int code, const std::string& m) { g_err = m; return code; }
             return fail(TRM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));               \
     } while (0)
 
+template <class NF>
+__global__ void copy_row_kernel(int64_t n, const NF* __restrict__ x, NF* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i];
+}
+
 struct HandleBase {
     virtual ~HandleBase() {}
     virtual int set_field(int id, const void* host, int64_t count) = 0;
@@ -58,6 +64,10 @@ struct HandleBase {
     virtual int set_ring_index(const int64_t* idx, int64_t nring) = 0;
     virtual int get_field_ring(int id, void* host, int64_t count, double fill) = 0;
     virtual int set_field_ring(int id, const void* host, int64_t count) = 0;
+    virtual int bind_host_io(int in_id, const void* host_in, int field_id, void* host_out, int nslots) = 0;
+    virtual int host_io_wait(int64_t iteration) = 0;
+    virtual int reset_state() = 0;
+    virtual void set_clock(double t, int64_t it) = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     double time = 0.0;   // holds an NF value
@@ -114,6 +124,11 @@ struct Handle : HandleBase {
     int64_t* ring_index = nullptr; int64_t nring = 0;   // ring-grid position of every owned column (ColumnRingGrid mask)
     NF* ring_buf = nullptr; size_t ring_count = 0;
     bool timing_open = false;
+    // per-step exchange through mapped host memory (trm_bind_host_io): step k -> k+1 reads input `in_id` from slot
+    // k % nslots of `in_dev` and writes field `out_id` of the new state to the same slot of `out_dev`; ev[slot] fires when
+    // that step has completed
+    struct HostIO { int in_id = -1, out_id = -1, nslots = 0; const NF* in_dev = nullptr; NF* out_dev = nullptr;
+                    std::vector<cudaEvent_t> ev; int64_t first_iter = 0; } hio;
     double* diag_partial = nullptr; double* diag_out = nullptr; int diag_blocks = 0;
 
     ~Handle() override {
@@ -124,6 +139,7 @@ struct Handle : HandleBase {
         if (s_out) cudaStreamSynchronize(s_out);
         for (cudaEvent_t e : {ev0, ev1, ev_staged, ev_out_done}) if (e) cudaEventDestroy(e);
         for (Input& s : in) for (cudaEvent_t e : {s.ev_free[0], s.ev_free[1], s.ev_ready}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : hio.ev) if (e) cudaEventDestroy(e);
         for (cudaStream_t s : {stream, s_in, s_out}) if (s) cudaStreamDestroy(s);
     }
 
@@ -470,6 +486,20 @@ struct Handle : HandleBase {
     int get_field_ring(int id, void* host, int64_t count, double fill) override;
     int set_field_ring(int id, const void* host, int64_t count) override;
     int ring_buffer(size_t need);
+    int bind_host_io(int in_id, const void* host_in, int field_id, void* host_out, int nslots) override;
+    int host_io_wait(int64_t it) override;
+    int reset_state() override;
+    void set_clock(double t, int64_t it) override { time = (double)(NF)t; t_inputs = time; iteration = it; }
+    // host exchange of the step that starts at `iteration`: input pointer of this step's slot, prefetch flag
+    void apply_host_io(StageArgs<NF>& a, bool writes_final_state) {
+        if (hio.nslots) {
+            const int64_t slot = iteration % hio.nslots;
+            if (hio.in_id >= 0) { a.in[hio.in_id].kind = TRM_SRC_FIELD; a.in[hio.in_id].a = hio.in_dev + slot * nc; }
+            if (writes_final_state && hio.out_id == TRM_F_GROUND_TEMPERATURE) a.hio_out = hio.out_dev + slot * nc;
+        }
+        const trm_bc& b = a.bc[TRM_BC_TEMPERATURE_TOP];
+        a.bct_pre = (b.kind == TRM_BC_VALUE || b.kind == TRM_BC_GRADIENT) && a.in[b.input].kind == TRM_SRC_FIELD && a.in[b.input].a ? 1 : 0;
+    }
 };
 
 template <> int Handle<float>::launch(int variant, const StageArgs<float>& a) {
@@ -559,6 +589,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             const bool load = aux_stale || force_load;
             a.load_aux = load ? 1 : 0;
             set_times(a);
+            apply_host_io(a, true);
             if (split) { if (int rc = launch_surface(0, a)) return rc; }
             if (int rc = launch_euler(a, load ? 1 : 0)) return rc;
         } else {       // heun.jl:37-71
@@ -567,6 +598,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             for (int i = 0; i < 3; ++i) { a.vy[i] = gveg[i]; a.vok1[i] = tveg[i]; }
             a.ybeta = gbeta;
             set_times(a);
+            apply_host_io(a, false);
             if (split) { if (int rc = launch_surface(0, a)) return rc; }
             if (int rc = launch_euler(a, a.load_aux)) return rc;
             StageArgs<NF> b; base_args(b);
@@ -576,10 +608,19 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             b.xbeta = gbeta;
             y_state(b);
             set_times(b);
+            apply_host_io(b, true);
             // stage 2 only re-evaluates the vegetation block (k2 of canopy water, vegetation carbon and area fraction);
             // the bare-ground surface block of the stage state has no effect on the step (heun.jl:63-66)
             if (split && veg) { if (int rc = launch_surface(0, b)) return rc; }
             if (int rc = launch_euler(b, 0)) return rc;
+        }
+        if (hio.nslots) {
+            const int64_t slot = iteration % hio.nslots;
+            if (hio.out_id >= 0 && hio.out_id != TRM_F_GROUND_TEMPERATURE) {   // any other 2-D field: one small copy kernel
+                copy_row_kernel<NF><<<(unsigned)((nc + 255) / 256), 256, 0, stream>>>(nc, field(hio.out_id).ptr, hio.out_dev + slot * nc);
+                ++launches;
+            }
+            CU(cudaEventRecord(hio.ev[slot], stream));
         }
         beta_stale = !split;   // the staged kernels leave the factor of the new state behind; the generic kernel does not
         aux_stale = false;
@@ -612,6 +653,68 @@ template <class NF> int Handle<NF>::step(double dt_, int64_t n) {
 }
 
 template <class NF> int Handle<NF>::step_async(double dt_, int64_t n) { return enqueue_steps(dt_, n); }
+
+// ---- per-step exchange with a host-side coupler through mapped, page-locked host memory ----
+template <class NF> int Handle<NF>::bind_host_io(int in_id, const void* host_in, int field_id, void* host_out, int nslots) {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamSynchronize(stream));
+    for (cudaEvent_t e : hio.ev) if (e) cudaEventDestroy(e);
+    hio = HostIO{};
+    if (!host_in && !host_out) return TRM_OK;   // unbind
+    if (nslots < 1 || nslots > 64) return fail(TRM_ERR_INVALID, "bind_host_io: nslots must be in [1, 64]");
+    if (host_in) {
+        if (in_id < 0 || in_id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bind_host_io: bad input id");
+        if (in[in_id].kind == TRM_SRC_TABLE || in[in_id].kind == TRM_SRC_RASTER) return fail(TRM_ERR_STATE, "bind_host_io: input is a time series table");
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, const_cast<void*>(host_in), 0) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TRM_ERR_INVALID, "bind_host_io: host_in is not page-locked, mapped host memory (allocate it with trm_host_alloc / trm_host_alloc_ex)");
+        }
+        hio.in_id = in_id; hio.in_dev = (const NF*)d;
+    }
+    if (host_out) {
+        FieldRef f = field(field_id);
+        if (!f.ptr || f.nrows != 1) return fail(TRM_ERR_INVALID, "bind_host_io: the output must be a 2-D field of this model (e.g. ground_temperature, skin_temperature)");
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, host_out, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TRM_ERR_INVALID, "bind_host_io: host_out is not page-locked, mapped host memory (allocate it with trm_host_alloc / trm_host_alloc_ex)");
+        }
+        hio.out_id = field_id; hio.out_dev = (NF*)d;
+    }
+    hio.nslots = nslots; hio.first_iter = iteration;
+    hio.ev.assign((size_t)nslots, nullptr);
+    for (int i = 0; i < nslots; ++i) CU(cudaEventCreateWithFlags(&hio.ev[i], cudaEventDisableTiming));
+    return TRM_OK;
+}
+template <class NF> int Handle<NF>::host_io_wait(int64_t it) {
+    if (!hio.nslots) return fail(TRM_ERR_STATE, "host_io_wait without trm_bind_host_io");
+    if (it > iteration) return fail(TRM_ERR_INVALID, "host_io_wait: that step has not been enqueued yet");
+    if (it <= hio.first_iter) return TRM_OK;   // produced before the binding
+    CU(cudaSetDevice(device));
+    // the step (it-1) -> it recorded ev[(it-1) % nslots]; if a later step has reused the slot, waiting for that one is
+    // still correct (steps complete in order)
+    CU(cudaEventSynchronize(hio.ev[(size_t)((it - 1) % hio.nslots)]));
+    return TRM_OK;
+}
+
+// reset!(integrator.state) of initialize!(integrator) (model_integrator.jl:98): every field of the state goes back to
+// zero before the initializers run (metrics and input sources are not state)
+template <class NF> int Handle<NF>::reset_state() {
+    CU(cudaSetDevice(device));
+    const size_t n3 = (size_t)nz * ld;
+    for (NF* f : {U, T, Lq, S, P, tU, tS, gU, gS, paw}) if (f) CU(cudaMemsetAsync(f, 0, n3 * sizeof(NF), stream));
+    if (Kf) CU(cudaMemsetAsync(Kf, 0, (size_t)(nz + 1) * ld * sizeof(NF), stream));
+    for (NF* f : {Sx, Wt, gWt, beta, gbeta}) if (f) CU(cudaMemsetAsync(f, 0, (size_t)ld * sizeof(NF), stream));
+    for (NF* f : land2d) if (f) CU(cudaMemsetAsync(f, 0, (size_t)ld * sizeof(NF), stream));
+    for (NF* f : veg2d) if (f) CU(cudaMemsetAsync(f, 0, (size_t)ld * sizeof(NF), stream));
+    for (int i = 0; i < 3; ++i) for (NF* f : {gveg[i], tveg[i]}) if (f) CU(cudaMemsetAsync(f, 0, (size_t)ld * sizeof(NF), stream));
+    for (int id = 0; id < TRM_F_COUNT; ++id) if (acc[id]) CU(cudaMemsetAsync(acc[id], 0, (size_t)field(id).nrows * ld * sizeof(NF), stream));
+    CU(cudaStreamSynchronize(stream));
+    time = 0.0; iteration = 0; t_inputs = 0.0;
+    initialized = false; aux_stale = true; beta_stale = true;
+    return TRM_OK;
+}
 
 template <class NF> int Handle<NF>::sync_all() {
     CU(cudaSetDevice(device));
@@ -721,10 +824,11 @@ template <class NF> int Handle<NF>::get_field_async(int id, void* host, int64_t 
         staging_count = need;
     }
     CU(cudaStreamWaitEvent(stream, ev_out_done, 0));   // the previous download is done with the staging buffer
-    CU(cudaMemcpyAsync(staging, f.ptr, need * sizeof(NF), cudaMemcpyDeviceToDevice, stream));
+    CU(cudaMemcpyAsync(staging, f.ptr, (f.nrows == 1 ? (size_t)nc : need) * sizeof(NF), cudaMemcpyDeviceToDevice, stream));
     CU(cudaEventRecord(ev_staged, stream));
     CU(cudaStreamWaitEvent(s_out, ev_staged, 0));
-    CU(cudaMemcpy2DAsync(host, nc * sizeof(NF), staging, ld * sizeof(NF), nc * sizeof(NF), f.nrows, cudaMemcpyDeviceToHost, s_out));
+    if (f.nrows == 1) CU(cudaMemcpyAsync(host, staging, nc * sizeof(NF), cudaMemcpyDeviceToHost, s_out));
+    else CU(cudaMemcpy2DAsync(host, nc * sizeof(NF), staging, ld * sizeof(NF), nc * sizeof(NF), f.nrows, cudaMemcpyDeviceToHost, s_out));
     CU(cudaEventRecord(ev_out_done, s_out));
     return TRM_OK;
 }
@@ -915,7 +1019,13 @@ int trm_step(trm_handle* h, double dt, int64_t n) { if (!h) return fail(TRM_ERR_
 int trm_compute_auxiliary(trm_handle* h) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->aux(); }
 int trm_compute_tendencies(trm_handle* h) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->tendencies(); }
 int trm_get_clock(trm_handle* h, double* t, int64_t* it) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); if (t) *t = H(h)->time; if (it) *it = H(h)->iteration; return TRM_OK; }
-int trm_set_clock(trm_handle* h, double t, int64_t it) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); H(h)->time = t; H(h)->iteration = it; return TRM_OK; }
+int trm_set_clock(trm_handle* h, double t, int64_t it) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); H(h)->set_clock(t, it); return TRM_OK; }
+int trm_reset(trm_handle* h) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->reset_state(); }
+int trm_bind_host_io(trm_handle* h, int input_id, const void* host_in, int field_id, void* host_out, int32_t nslots) {
+    if (!h) return fail(TRM_ERR_INVALID, "null handle");
+    return H(h)->bind_host_io(input_id, host_in, field_id, host_out, nslots);
+}
+int trm_host_io_wait(trm_handle* h, int64_t iteration) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->host_io_wait(iteration); }
 int trm_diagnostics(trm_handle* h, trm_diag* out) { if (!h || !out) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics(out, nullptr); }
 int trm_diagnostics_device(trm_handle* h, double** dev) { if (!h || !dev) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics(nullptr, dev); }
 int64_t trm_launch_count(trm_handle* h) { return h ? H(h)->launches : 0; }
@@ -929,7 +1039,15 @@ int trm_get_accumulated(trm_handle* h, int id, void* host, int64_t count, double
 }
 int trm_host_alloc(int64_t bytes, void** host) {
     if (!host || bytes <= 0) return fail(TRM_ERR_INVALID, "trm_host_alloc: bad arguments");
-    cudaError_t e = cudaHostAlloc(host, (size_t)bytes, cudaHostAllocPortable);
+    cudaError_t e = cudaHostAlloc(host, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TRM_ERR_NO_DEVICE : TRM_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    return TRM_OK;
+}
+int trm_host_alloc_ex(int64_t bytes, int32_t flags, void** host) {
+    if (!host || bytes <= 0 || (flags & ~TRM_HOST_WRITE_COMBINED)) return fail(TRM_ERR_INVALID, "trm_host_alloc_ex: bad arguments");
+    unsigned f = cudaHostAllocPortable | cudaHostAllocMapped;
+    if (flags & TRM_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    cudaError_t e = cudaHostAlloc(host, (size_t)bytes, f);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TRM_ERR_NO_DEVICE : TRM_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
     return TRM_OK;
 }

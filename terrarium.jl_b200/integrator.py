@@ -215,6 +215,8 @@ class ModelIntegrator:
     def initialize_state(self):
         """``initialize!(integrator)`` (model_integrator.jl:96-109): user/model initializers, then the
         process initialisation inside the library (closures at t0)."""
+        # reset!(integrator.state) (model_integrator.jl:98): a re-initialisation starts from zeroed fields and clock
+        self._lib.check(self._lib.reset(self._h), "reset")
         fields = dict(self.model.initializer.fields(self.grid))
         # model initializer first, then user field initializers? The reference evaluates the user
         # initializers (:105) *before* the model initializer (:107), so the model initializer wins.
@@ -334,6 +336,41 @@ class ModelIntegrator:
     def compute_auxiliary(self):
         self._lib.check(self._lib.compute_auxiliary(self._h), "compute_auxiliary")
 
+    # -- coupled-model exchange through mapped host memory (trm_bind_host_io) --------------------------------------
+    def bind_host_io(self, input_name: Optional[str], field_name: Optional[str], nslots: int = 4, write_combined: bool = True):
+        """Bind page-locked host rings for a per-step exchange with a host-side coupler (the coupling flow of
+        examples/simulations/speedy_dry_land.jl:45-68): the step from iteration ``k`` reads input ``input_name`` from
+        ``ring_in[k % nslots]`` and stores field ``field_name`` of the new state in ``ring_out[k % nslots]``; the stage
+        kernel accesses the host memory directly. Returns ``(ring_in, ring_out)`` as numpy views ``[nslots, ncol]``."""
+        lib, h = self._lib, self._h
+        nbytes = int(nslots) * self.ncol * np.dtype(self.nf).itemsize
+
+        def ring(flags):
+            q = C.c_void_p()
+            lib.check(lib.host_alloc_ex(nbytes, flags, C.byref(q)), "host_alloc_ex")
+            self._pinned = getattr(self, "_pinned", []) + [q]
+            buf = (C.c_char * nbytes).from_address(q.value)
+            return q, np.frombuffer(buf, dtype=self.nf).reshape(int(nslots), self.ncol)
+
+        in_id, p_in, a_in = -1, C.c_void_p(), None
+        if input_name is not None:
+            in_id = self._bc_inputs[input_name] if input_name in self._bc_inputs else abi.INPUT_IDS[input_name]
+            self._host_callbacks.pop(in_id, None)
+            p_in, a_in = ring(1 if write_combined else 0)
+        out_id, p_out, a_out = -1, C.c_void_p(), None
+        if field_name is not None:
+            out_id = abi.FIELD_IDS[field_name]
+            p_out, a_out = ring(0)
+            a_out[...] = 0
+        lib.check(lib.bind_host_io(h, in_id, p_in, out_id, p_out, int(nslots)), "bind_host_io")
+        return a_in, a_out
+
+    def host_io_wait(self, iteration: int):
+        self._lib.check(self._lib.host_io_wait(self._h, int(iteration)), "host_io_wait")
+
+    def step_async(self, dt: float, nsteps: int = 1):
+        self._lib.check(self._lib.step_async(self._h, float(dt), int(nsteps)), "step_async")
+
     def compute_tendencies(self):
         self._lib.check(self._lib.compute_tendencies(self._h), "compute_tendencies")
 
@@ -349,6 +386,9 @@ class ModelIntegrator:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.destroy(self._h)
             self._h = abi._H()
+            for q in getattr(self, "_pinned", []):
+                self._lib.host_free(q)
+            self._pinned = []
 
     def __del__(self):
         try:

@@ -4,7 +4,7 @@
 # STATUS: UNTESTED SOURCE.  Neither `julia` nor Terrarium's dependencies exist in the build image or
 # on the GPU boxes, so this file has never been executed; the tested caller of the same C ABI is
 # the Python ctypes mirror (terrarium.jl_b200/integrator.py).  The struct layouts below must match
-# include/terrarium_b200.h field for field (TRM_ABI_VERSION = 2).
+# include/terrarium_b200.h field for field (TRM_ABI_VERSION = 3).
 #
 # What it replaces in the reference (paths relative to the Terrarium.jl root):
 #   initialize(model, timestepper, inputs...)            src/timesteppers/model_integrator.jl:145-161
@@ -21,7 +21,7 @@ import FreezeCurves: VanGenuchten, BrooksCorey
 
 const LIB = get(ENV, "TERRARIUM_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libterrarium_b200.so"))
 
-const TRM_ABI_VERSION = Int32(2)
+const TRM_ABI_VERSION = Int32(3)
 const TRM_BC_NSLOTS = 8
 @enum FieldId::Cint internal_energy=0 temperature=1 liquid_water_fraction=2 saturation_water_ice=3 pressure_head=4 hydraulic_conductivity=5 surface_excess_water=6 water_table=7 ground_temperature=8 skin_temperature=9 ground_heat_flux=10 surface_shortwave_up=11 surface_longwave_up=12 surface_net_radiation=13 sensible_heat_flux=14 latent_heat_flux=15 evaporation_ground=16 infiltration=17 surface_runoff=18 carbon_vegetation=21 vegetation_area_fraction=22 canopy_water=23 balanced_leaf_area_index=24 leaf_area_index=25 phenology_factor=26 canopy_water_conductance=27 leaf_to_air_co2_ratio=28 net_assimilation=29 leaf_respiration=30 gross_primary_production=31 autotrophic_respiration=32 net_primary_production=33 soil_moisture_limiting_factor=34 canopy_water_interception=35 canopy_water_removal=36 saturation_canopy_water=37 rainfall_ground=38 evaporation_canopy=39 transpiration=40 plant_available_water=41 root_fraction=42
 
@@ -65,6 +65,19 @@ Base.eltype(::B200Integrator{NF}) where {NF} = NF
 dtype_code(::Type{Float32}) = Int32(0)
 dtype_code(::Type{Float64}) = Int32(1)
 
+# residual water content of a FreezeCurves SWRC (`swrc.vol.θres`, FreezeCurves.jl SoilWaterVolume); 0 when the type has none
+swrc_theta_res(swrc) = hasproperty(swrc, :vol) && hasproperty(swrc.vol, :θres) ? Float64(ustrip(swrc.vol.θres)) : 0.0
+# user VWC forcing (src/processes/soil/hydrology/soil_hydrology.jl:38-48): the library evaluates a constant source / sink in
+# every cell. `nothing` -> 0; a discrete-form Forcing whose parameters carry a `.value` (the form of
+# test/soil/soil_hydrology_tests.jl:191-233) or a plain number -> that value; anything else cannot run inside the kernel.
+function vwc_forcing_value(f)
+    isnothing(f) && return 0.0
+    p = hasproperty(f, :parameters) ? f.parameters : f
+    p isa Number && return Float64(p)
+    hasproperty(p, :value) && return Float64(p.value)
+    error("TerrariumB200: only constant VWC forcings (a number, or Forcing(parameters = (value = ...), discrete_form = true)) are supported on the B200 path")
+end
+
 function params_of(model)
     soil, c = model.soil, model.constants
     k, h = soil.energy.thermal_properties.conductivities, soil.energy.thermal_properties.heat_capacities
@@ -77,8 +90,8 @@ function params_of(model)
         soil.strat.porosity.mineral_porosity, soil.strat.porosity.organic_porosity, soil.biogeochem.ρ_soc, soil.biogeochem.ρ_org,
         (k.water, k.ice, k.air, k.mineral, k.organic), (h.water, h.ice, h.air, h.mineral, h.organic),
         c.ρw, c.Lsl, c.Llg, c.ρₐ, c.cₐ, c.Tref, c.σ, c.ε,
-        hp.sat_hydraulic_cond, ustrip(vg.α), vg.n, ustrip(bc.ψₛ), bc.λ, 0.0,
-        hp.unsat_hydraulic_cond isa UnsatKVanGenuchten ? hp.unsat_hydraulic_cond.impedance : 7.0, 0.0,
+        hp.sat_hydraulic_cond, ustrip(vg.α), vg.n, ustrip(bc.ψₛ), bc.λ, swrc_theta_res(hp.swrc),
+        hp.unsat_hydraulic_cond isa UnsatKVanGenuchten ? hp.unsat_hydraulic_cond.impedance : 7.0, vwc_forcing_value(soil.hydrology.vwc_forcing),
         land ? seb.albedo.albedo : 0.3, land ? seb.albedo.emissivity : 0.97, land ? seb.skin_temperature.κₛ : 2.0,
         land ? model.atmosphere.aerodynamics.C_h : 1.2e-3, land ? model.atmosphere.min_windspeed : 0.01,
         land ? model.surface_hydrology.surface_runoff.τ_r : 3600.0, 1.0,
@@ -131,6 +144,7 @@ function initialize_b200(model::Union{SoilModel{NF}, LandModel{NF}}, timestepper
     for (input, source) in bc_sources                       # device-resident boundary values (user input slots 0..7)
         set_input!(integ, input, source)
     end
+    check(ccall((:trm_reset, LIB), Cint, (Ptr{Cvoid},), integ.handle), "reset")   # reset!(integrator.state), model_integrator.jl:98
     names = (model isa LandModel && !isnothing(model.vegetation)) ?
         (:temperature, :saturation_water_ice, :carbon_vegetation, :vegetation_area_fraction, :canopy_water) : (:temperature, :saturation_water_ice)
     for name in names
@@ -164,6 +178,28 @@ function field_ptr(integ::B200Integrator, name::Symbol)
                 Cint(getproperty(TerrariumB200, name)), p, ld, rows), "field_ptr")
     return p[], ld[], rows[]
 end
+
+"""
+    bind_host_io!(integ, input, field; nslots = 4) -> (ring_in, ring_out)
+
+Per-step exchange with a host-side coupler (the flow of examples/simulations/speedy_dry_land.jl:45-68) through page-locked
+host memory that the stage kernel reads and writes directly (`trm_bind_host_io`): the step from iteration `k` reads input
+`input` from `ring_in[:, k % nslots + 1]` and stores the 2-D field `field` of the new state in `ring_out[:, k % nslots + 1]`.
+`wait_step(integ, k)` blocks until the step that produced iteration `k` has completed.
+"""
+function bind_host_io!(integ::B200Integrator{NF}, input::Integer, field::Symbol; nslots = 4) where {NF}
+    nbytes = nslots * integ.ncol * sizeof(NF)
+    pin, pout = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:trm_host_alloc_ex, LIB), Cint, (Int64, Int32, Ref{Ptr{Cvoid}}), nbytes, 1, pin), "host_alloc_ex")   # write-combined
+    check(ccall((:trm_host_alloc_ex, LIB), Cint, (Int64, Int32, Ref{Ptr{Cvoid}}), nbytes, 0, pout), "host_alloc_ex")
+    check(ccall((:trm_bind_host_io, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int32), integ.handle,
+                Cint(input), pin[], Cint(getproperty(TerrariumB200, field)), pout[], Int32(nslots)), "bind_host_io")
+    return unsafe_wrap(Array, Ptr{NF}(pin[]), (integ.ncol, nslots)), unsafe_wrap(Array, Ptr{NF}(pout[]), (integ.ncol, nslots))
+end
+wait_step(integ::B200Integrator, iteration::Integer) =
+    check(ccall((:trm_host_io_wait, LIB), Cint, (Ptr{Cvoid}, Int64), integ.handle, Int64(iteration)), "host_io_wait")
+step_async!(integ::B200Integrator, Δt, nsteps = 1) =
+    check(ccall((:trm_step_async, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, convert_dt(Δt), Int64(nsteps)), "step_async")
 
 function Terrarium.timestep!(integ::B200Integrator, Δt = default_dt(integ.timestepper); finalize = true)
     check(ccall((:trm_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, convert_dt(Δt), 1), "step")
