@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--model", default="soil", choices=["soil", "land", "land-veg"],
                     help="secondary workloads (not the headline): bare-ground LandModel, LandModel with PALADYN vegetation")
     ap.add_argument("--timestepper", default="euler", choices=["euler", "heun"], help="secondary workloads: Heun (two stage launches per step)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` array (Float32, Heun, LandModel workloads, 20 steps each)")
+    ap.add_argument("--secondary-steps", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     nf = np.float64 if args.dtype == "f64" else np.float32
@@ -379,11 +381,52 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_column_layer_step": bpc,
-                "kernel": ("trm::stage_kernel" if os.environ.get("TRM_KERNEL") == "stream" else "trm::euler_kernel")
+                "kernel": ("trm::stage_kernel" if os.environ.get("TRM_KERNEL") == "stream" else
+                           ("trm::euler2_kernel (two columns per thread, packed f32x2)" if args.dtype == "f32" and args.math == "fast"
+                            and os.environ.get("TRM_F32X2", "1") != "0" else "trm::euler_kernel"))
                           + f"<{args.dtype}, {'RICHARDS' if args.model == 'soil' else 'LAND'}, recompute, {args.math}>"
                           + (" (two stage launches per step)" if args.timestepper == "heun" else "")
                           + (" + trm::surface_kernel" if args.model != "soil" else ""),
                 "launch_ms": per_launch_ms}
+
+    # ---- secondary workloads on the same domain (not the headline; each with its own roofline and clock record) ----
+    secondary_lines = []
+    if not secondary and not args.no_secondary:
+        integ.close()
+        del integ
+        cases = [("f32", "soil", "euler"), ("f64", "soil", "heun"), ("f32", "soil", "heun"), ("f64", "land", "euler"),
+                 ("f64", "land-veg", "euler"), ("f64", "land-veg", "heun"), ("f32", "land-veg", "euler")]
+        for dt_name, model_kind, stepper in cases:
+            nf2 = np.float64 if dt_name == "f64" else np.float32
+            it2, _, _ = build_case(trm, trm.initialize, args.columns, rank, world, local_rank, nf2, args.math,
+                                   model_kind=model_kind, heun=stepper == "heun")
+            it2.step(DT, max(args.warmup, 3))
+            smp = ClockSampler(local_rank)
+            if rank == 0:
+                smp.start()
+            barrier()
+            la = it2._lib.launch_count(it2._h)
+            it2.step(DT, args.secondary_steps)
+            barrier()
+            nl = it2._lib.launch_count(it2._h) - la
+            m2 = C.c_float()
+            it2._lib.check(it2._lib.last_step_ms(it2._h, C.byref(m2)), "last_step_ms")
+            ck = smp.stop() if rank == 0 else None
+            ms2 = td.max_over_ranks(m2.value) / args.secondary_steps
+            d2 = it2.diagnostics()
+            nan2 = td.reduce_diagnostics(d2)["nan_count"]
+            isz = np.dtype(nf2).itemsize
+            bpc2 = algorithmic_bytes_per_cell(isz, NZ, model_kind, stepper == "heun")
+            ach2 = bpc2 * (it2.ncol * NZ) / (ms2 * 1e-3) / 1e9
+            secondary_lines.append({
+                "workload": {"soil": "soil energy + Richards", "land": "bare-ground LandModel", "land-veg": "vegetated LandModel"}[model_kind]
+                            + f", {stepper}, {dt_name}", "dtype": dt_name, "timestepper": stepper, "steps": args.secondary_steps,
+                "ms_per_step": ms2, "value": total_cells / (ms2 * 1e-3), "unit": UNIT, "gpu_launches": int(nl), "nan_count": nan2,
+                "roofline": {"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
+                             "algorithmic_bytes_per_column_layer_step": bpc2},
+                "clocks": ck})
+            it2.close()
+            del it2
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,6 +452,7 @@ def main():
                        "partition": "contiguous column ranges, no halo, no data-path collective",
                        "cache": "inputs larger than L2 (state read per step = %.1f GB per GPU)" % (2 * ncol_local * NZ * itemsize / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "secondary": secondary_lines,
             "wall_s_timed_region": wall,
             "budgets": {"water_before": bud[0], "water_after": bud[1], "nan_count": bud[2], "energy_after": bud[3]},
         }

@@ -414,8 +414,9 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler2_min_blocks<PHYS, MODE
                 if (CLOSE) {
                     stg2(A.yT + o, Tc); stg2(A.yL + o, lc);
                     if (!inner && j == nz && A.hio_out) { A.hio_out[c] = Tc.x; if (vy) A.hio_out[c + 1] = Tc.y; }
-                    // (layers below a water table that is not known yet are overwritten after the sweep)
-                    if (RICH) stg2(A.yP + o, pressure_head2(p, sn, wt_new, met.zC(j), met.psiz(j)));
+                    // layers below the water table wait for it (written after the sweep); in a pair with only one column
+                    // still below its water table that column's value is overwritten there
+                    if (RICH && (idxx | idxy) != 0) stg2(A.yP + o, pressure_head2(p, sn, wt_new, met.zC(j), met.psiz(j)));
                 }
             }
         }
