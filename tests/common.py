@@ -100,3 +100,11 @@ def max_scaled_err(a, b):
     """max |a-b| / max|b| : relative error against the field's scale (robust where the field crosses 0)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), np.finfo(np.float64).tiny))
+
+
+def pointwise_relerr(a, b, floor_frac=1.0e-6):
+    """max |a-b| / max(|b|, floor_frac * max|b|): pointwise relative error with an explicit floor, so that a cell whose
+    value is small against the field's scale is still held to (1 / floor_frac) x the scaled tolerance."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(float(np.max(np.abs(b))), np.finfo(np.float64).tiny)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor_frac * scale)))

@@ -1,15 +1,18 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle on the BASELINE configurations.
 
 Tolerance (BASELINE.json north_star): Float64, max relative error 1e-9 on temperature, internal energy
-and saturation after 1000 steps, plus conservation of the column energy and water budgets.  Relative
-errors are measured against each field's scale (max |field|): temperature crosses zero (degC), where a
-pointwise relative error is meaningless.  Heat-only runs with a constant surface temperature involve no
+and saturation after 1000 steps, plus conservation of the column energy and water budgets.  Two measures
+are asserted, both at that tolerance: the error against each field's scale, max|a-b| / max|b|, and the
+POINTWISE relative error |a-b| / max(|b|, 1e-6 max|b|) -- temperature crosses zero (degC) and the internal
+energy changes sign at the freezing point, so the pointwise measure needs a floor; with this one a cell whose
+value is a millionth of the field's scale is still held to 1e-9 of its own value (observed: <= 4e-12 after 1000
+steps in every configuration).  Heat-only runs with a constant surface temperature involve no
 transcendental function and must be BIT-EXACT in the faithful math mode.
 """
 import numpy as np
 import pytest
 
-from common import (make, max_scaled_err, richards_soil, synthetic_columns, synthetic_land_case,
+from common import (make, max_scaled_err, pointwise_relerr, richards_soil, synthetic_columns, synthetic_land_case,
                     synthetic_soil_case, trm)
 
 pytestmark = pytest.mark.gpu
@@ -18,13 +21,21 @@ FIELDS = ("temperature", "internal_energy", "saturation_water_ice", "liquid_wate
 TOL = 1.0e-9
 
 
-def compare(gpu, cpu, fields, tol):
+def compare(gpu, cpu, fields, tol, columns=None, pw_tol=None):
+    """Both error measures of the module docstring, per field; `columns` restricts the GPU side to a column subset.
+    The pointwise measure is asserted for the Float64 tolerances (at max(tol, 1e-9)); a Float32 field has only ~16 ulp
+    between the floor of 1e-6 of its scale and the rounding of its largest values, so Float32 runs assert the scaled one."""
     worst = {}
+    if pw_tol is None:
+        pw_tol = max(tol, TOL) if tol <= 1.0e-8 else None
     for name in fields:
         a, b = getattr(gpu.state, name).numpy(), getattr(cpu.state, name).numpy()
+        if columns is not None:
+            a = a[..., columns]
         assert np.all(np.isfinite(a)), name
-        worst[name] = max_scaled_err(a, b)
-    assert all(v <= tol for v in worst.values()), worst
+        worst[name] = (max_scaled_err(a, b), pointwise_relerr(a, b) if pw_tol is not None else 0.0)
+    bad = {k: v for k, v in worst.items() if not (v[0] <= tol and (pw_tol is None or v[1] <= pw_tol))}
+    assert not bad, (bad, tol, pw_tol)
     return worst
 
 
@@ -121,6 +132,38 @@ def test_land_model_baseline_forcing_60_steps(math):
     compare(gpu, cpu, LAND_FIELDS, TOL)
 
 
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+@pytest.mark.parametrize("stepper", ["euler", "heun"])
+def test_land_model_baseline_forcing_until_blow_up(math, stepper):
+    """BASELINE config 4 with its own forcing (V = 3 m/s) for as long as the as-coded model stays finite. The explicit
+    skin / top-layer coupling is unstable at this wind speed (G = Rnet - Hs - Hl used as an upward Flux BC on a 5 cm layer,
+    SURVEY.md Appendix C): the oracle's state stops being finite after ~100 steps of 60 s. Both engines are run to the
+    last step at which the oracle is finite everywhere; the instability amplifies rounding differences by the same factor
+    that it amplifies the state (max |T_skin| grows from 23 to ~800 degC in the last 20 steps), so equality is asserted at
+    1e-9 up to ten steps before that point and at 1e-6 at the last finite step; the CUDA path must stay finite as long as
+    the oracle does."""
+    n = 600
+    cpu = synthetic_land_case("oracle", n, heun=stepper == "heun")
+    last = 0
+    snap = {}
+    for i in range(1, 400):
+        cpu.step(60.0, 1)
+        fin = all(np.isfinite(getattr(cpu.state, f).numpy()).all() for f in ("temperature", "skin_temperature", "internal_energy", "saturation_water_ice"))
+        if not fin:
+            break
+        last = i
+    assert 60 < last < 399, last
+    cpu = synthetic_land_case("oracle", n, heun=stepper == "heun")
+    gpu = synthetic_land_case("cuda", n, heun=stepper == "heun", math=math)
+    cpu.step(60.0, last - 10)
+    gpu.step(60.0, last - 10)
+    compare(gpu, cpu, LAND_FIELDS, TOL)
+    cpu.step(60.0, 10)
+    gpu.step(60.0, 10)
+    assert gpu.clock.iteration == cpu.clock.iteration == last
+    compare(gpu, cpu, LAND_FIELDS, 1.0e-6)
+
+
 def test_float32_soil_energy_richards():
     """Float32 (the reference's default for global grids): rounding differences in powf/cbrtf are amplified
     by the number format; tolerance is a few hundred ulps of the field scale after 200 steps."""
@@ -200,6 +243,30 @@ def test_full_size_properties():
     for name in FIELDS:
         a = getattr(gpu.state, name).numpy()[:, :sub]
         assert max_scaled_err(a, getattr(cpu.state, name).numpy()) <= TOL, name
+
+
+def test_full_size_strided_parity_1000_steps():
+    """BASELINE config 5 at its full size, 1000 steps: eight slabs of 512 columns, one inside each column range of the
+    8-GPU partition (unaligned offsets, the last one ending at the last column), against oracle runs of exactly those
+    columns -- columns are independent, so the slabs must agree to the tolerance of the small-case tests."""
+    n, slab, nranks = 10_000_000, 512, 8
+    starts = [r * (n // nranks) + 777 * (r + 1) for r in range(nranks - 1)] + [n - slab]
+    cols = np.concatenate([np.arange(s0, s0 + slab) for s0 in starts])
+    gpu = synthetic_soil_case("cuda", n, math="fast")
+    w0 = gpu.diagnostics()["water"]
+    gpu.step(60.0, 1000)
+    d1 = gpu.diagnostics()
+    assert d1["nan_count"] == 0 and d1["water"] == pytest.approx(w0, rel=1e-10)
+    lat, lon, T0 = synthetic_columns(n)
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(dz_min=0.05, dz_max=100.0, N=30), cols.size)
+    model = trm.SoilModel(grid, soil=richards_soil())
+    bcs = trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0[cols], amp=10.0, phase=lon[cols], period=86400.0))
+    inits = {"temperature": lambda x, z: T0[None, cols] - 0.05 * z,
+             "saturation_water_ice": lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x}
+    cpu = make("oracle", model, trm.ForwardEuler(dt=60.0), boundary_conditions=bcs, initializers=inits)
+    cpu.step(60.0, 1000)
+    compare(gpu, cpu, FIELDS + ("pressure_head",), TOL, columns=cols)
+    compare(gpu, cpu, ("water_table", "surface_excess_water"), TOL, columns=cols)
 
 
 def test_async_pipeline_matches_blocking_calls():
@@ -393,7 +460,11 @@ def test_fast_math_regimes_randomised(seed):
         pair.append(integ)
     for integ in pair:
         integ.step(20.0, 150)
-    compare(pair[0], pair[1], FIELDS + ("pressure_head", "water_table"), TOL)
+    compare(pair[0], pair[1], FIELDS + ("water_table",), TOL)
+    # the matric head psi_m = -(1/alpha) sqrt(se^-2 - 1) loses digits to the cancellation in 1 - se^2 as se -> 1 in ANY
+    # implementation: with se = 1 - d one ulp of se moves psi_m by 1.1e-16 / (2 d) of its value (5e-7 at d = 1e-10, which
+    # these random profiles contain). Against the field's scale that is invisible; pointwise it is bounded at 1e-6 here.
+    compare(pair[0], pair[1], ("pressure_head",), TOL, pw_tol=1.0e-6)
     # (the surface excess is zero or rounding noise of a top layer sitting at saturation here: absolute comparison)
     assert np.max(np.abs(pair[0].state.surface_excess_water.numpy() - pair[1].state.surface_excess_water.numpy())) <= 1.0e-13
     pair[0].compute_auxiliary(); pair[1].compute_auxiliary()
