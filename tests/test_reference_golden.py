@@ -1,0 +1,251 @@
+"""Golden vectors of the UNMODIFIED reference (tests/golden/make_reference_golden.jl -> tests/golden/reference/*.npy), replayed
+through the C ABI on both engines.
+
+The reference is pure Julia and cannot run in the build image or on the GPU boxes, so the vectors are not committed: a
+maintainer with a Terrarium.jl install generates them once (`julia --project=<Terrarium> tests/golden/make_reference_golden.jl`).
+Until then every comparison here SKIPS -- loudly, naming what is missing -- and the oracle stays "partially pinned" (DESIGN.md
+section 2). What always runs is the replay plumbing itself (short runs of every case on the oracle / the CUDA path), so that the
+day the files appear the tests compare instead of failing on a typo.
+
+Tolerance: BASELINE.json north_star -- Float64, 1e-9 of the field scale (and pointwise with the 1e-6 floor) after 1000 steps.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import ENGINES, make, max_scaled_err, pointwise_relerr, richards_soil, trm
+
+REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference")
+TOL = 1.0e-9
+
+SOIL_OUT = ("temperature", "internal_energy", "saturation_water_ice", "liquid_water_fraction")
+RICH_OUT = SOIL_OUT + ("pressure_head", "water_table", "surface_excess_water", "hydraulic_conductivity")
+LAND_OUT = RICH_OUT + ("skin_temperature", "ground_heat_flux", "sensible_heat_flux", "latent_heat_flux", "surface_net_radiation",
+                       "evaporation_ground", "infiltration", "surface_runoff")
+VEG_OUT = LAND_OUT + ("carbon_vegetation", "vegetation_area_fraction", "canopy_water", "net_assimilation", "transpiration")
+
+
+def ref(name):
+    """A golden array as `[layer, column]` / `[column]`; skips the calling test when the reference has not been run."""
+    path = os.path.join(REF, name + ".npy")
+    if not os.path.exists(path):
+        pytest.skip(f"REFERENCE GOLDEN VECTORS MISSING: {path} -- run tests/golden/make_reference_golden.jl with a Terrarium.jl "
+                    "install (no julia in this image); parity with the reference itself stays unpinned until then")
+    a = np.load(path)
+    return a.T if a.ndim == 2 else a
+
+
+def have(name):
+    return os.path.exists(os.path.join(REF, name + ".npy"))
+
+
+def grid_from(zfaces, nf, ncol):
+    dz = np.diff(np.asarray(zfaces, dtype=np.float64))[::-1]          # thicknesses top -> bottom
+    return trm.ColumnGrid(trm.B200(), nf, trm.PrescribedSpacing(list(dz)), ncol)
+
+
+def percol(ncol):
+    lat = np.linspace(-1.5, 1.5, ncol)
+    lon = np.mod(2.399963229728653 * np.arange(1, ncol + 1), 2 * np.pi)
+    return lat, lon, 20.0 - np.abs(40.0 * np.sin(lat))
+
+
+def exponential_grid(nz, ncol, **kw):
+    return trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(N=nz, **kw), ncol)
+
+
+# ---- the replays (same sequence of API calls as the Julia script) ---------------------------------------------------
+def replay_cfg1(engine, variant, nsteps=1000, math="faithful"):
+    grid = exponential_grid(10, 1)
+    if variant == "a":
+        model = trm.SoilModel(grid)
+    else:
+        model = trm.SoilModel(grid, initializer=trm.SoilInitializer(energy=trm.QuasiThermalSteadyState(T0=-1.0), hydrology=trm.ConstantSaturation(sat=1.0)))
+    integ = make(engine, model, trm.ForwardEuler(), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", 1.0), math=math)
+    trm.run(integ, steps=nsteps, dt=300.0)
+    return integ
+
+
+def replay_soil(engine, richards, heun, dt, nsteps=1000, ncol=24, math="faithful"):
+    grid = exponential_grid(30, ncol, dz_min=0.05, dz_max=100.0)
+    lat, lon, T0 = percol(ncol)
+    model = trm.SoilModel(grid, soil=richards_soil()) if richards else trm.SoilModel(grid)
+    inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z,
+             "saturation_water_ice": (lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x) if richards else (lambda x, z: 1.0 + 0 * x + 0 * z)}
+    integ = make(engine, model, (trm.Heun if heun else trm.ForwardEuler)(), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub"),
+                 initializers=inits, math=math)
+    for i in range(nsteps):
+        integ.state.T_ub.set(T0 + 10.0 * np.sin(2 * np.pi * (i * dt) / 86400.0 - lon))
+        integ.step(dt, 1)
+    integ.compute_auxiliary()
+    return integ
+
+
+def replay_land(engine, vegetated, windspeed, nsteps, ncol=16, dt=60.0, math="faithful"):
+    grid = exponential_grid(30, ncol, dz_min=0.05, dz_max=100.0)
+    lat, lon, T0 = percol(ncol)
+    veg = None
+    if vegetated:
+        veg = trm.VegetationCarbon(carbon_dynamics=trm.PALADYNCarbonDynamics(gamma_L=1e-9, gamma_R=1e-9, gamma_S=1e-10),
+                                   vegetation_dynamics=trm.PALADYNVegetationDynamics(gamma_v_min=1e-8))
+    land = trm.LandModel(grid, soil=richards_soil(), vegetation=veg)
+    inits = {"temperature": lambda x, z: T0[None, :] - 0.05 * z, "saturation_water_ice": lambda x, z: np.minimum(1.0, 0.5 - 0.1 * z) + 0 * x,
+             "skin_temperature": T0}
+    inputs = {"surface_longwave_down": 300.0, "specific_humidity": 0.005, "air_pressure": 101325.0, "windspeed": windspeed}
+    if vegetated:
+        inits.update(carbon_vegetation=10.0, vegetation_area_fraction=0.5)
+        inputs.update(CO2=400.0, SAI=0.5)
+    integ = make(engine, land, trm.Heun(), inputs, initializers=inits, math=math)
+    for i in range(nsteps):
+        t = i * dt
+        integ.state.inputs.air_temperature.set(T0 + 8.0 * np.sin(2 * np.pi * t / 86400.0 - lon))
+        integ.state.inputs.surface_shortwave_down.set(np.maximum(0.0, 600.0 * np.sin(2 * np.pi * t / 86400.0 - lon)))
+        integ.state.inputs.rainfall.set(2.0e-8 if (t % 86400.0) < 6 * 3600.0 else 0.0)
+        integ.step(dt, 1)
+    integ.compute_auxiliary()
+    return integ
+
+
+def check(integ, prefix, names, tol=TOL):
+    bad = {}
+    for n in names:
+        want = ref(f"{prefix}_{n}")
+        got = getattr(integ.state, n).numpy()
+        fin = np.isfinite(want)
+        assert np.array_equal(fin, np.isfinite(got)), n
+        e = (max_scaled_err(got[fin], want[fin]), pointwise_relerr(got[fin], want[fin]))
+        if not (e[0] <= tol and e[1] <= tol):
+            bad[n] = e
+    assert not bad, bad
+
+
+# ---- comparisons (skip without the golden files) -------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("variant", ["a", "b"])
+def test_reference_cfg1_quick_start(engine, variant):
+    ref(f"cfg1{variant}_temperature")
+    assert np.allclose(replay_cfg1(engine, variant, 0).grid.znodes_face(), ref("cfg1_zfaces"), rtol=0, atol=1e-12)
+    check(replay_cfg1(engine, variant), f"cfg1{variant}", SOIL_OUT)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case", ["cfg2", "cfg3e", "cfg3h"])
+def test_reference_soil_configs(engine, case):
+    ref(f"{case}_temperature")
+    richards, heun, dt = case != "cfg2", case == "cfg3h", 300.0 if case == "cfg2" else 60.0
+    integ = replay_soil(engine, richards, heun, dt)
+    assert np.allclose(percol(24)[1], ref(f"{case}_lon")) and np.allclose(percol(24)[2], ref(f"{case}_T0"))
+    assert integ.clock.time == pytest.approx(float(ref(f"{case}_time")[0]))
+    check(integ, case, RICH_OUT if richards else SOIL_OUT)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case", ["cfg4b", "cfg4b_v3", "cfg4v"])
+def test_reference_land_configs(engine, case):
+    ref(f"{case}_temperature")
+    integ = replay_land(engine, case == "cfg4v", 3.0 if case == "cfg4b_v3" else 0.5, 60 if case == "cfg4b_v3" else 1000)
+    check(integ, case, VEG_OUT if case == "cfg4v" else LAND_OUT)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reference_value_bc_halo(engine):
+    """Value-BC halo: interior 0.5, value 1.0 -> halo 1.5 (Oceananigans; test/boundary_conditions.jl:16-19). The C ABI never
+    materialises halos; the rule is observable through the first-step tendency of the top layer, so the check is arithmetic:
+    the golden halo must equal 2 v - c, the rule halo_value() / the oracle implement."""
+    for tag in ("uniform", "stretched"):
+        top, halo_top, halo_bottom, bottom = ref(f"sem_value_bc_halo_{tag}")
+        assert halo_top == pytest.approx(2 * 1.0 - top, abs=1e-14)
+        assert halo_bottom == pytest.approx(bottom, abs=0)          # default (no-flux) bottom: copy of the edge value
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("tag", ["constant", "function"])
+def test_reference_noflow_saturation_halo(engine, tag):
+    """The unpinned switch `sat_halo = {zero, copy}`, decided by the reference itself: which value
+    the never-filled z-halo of the auxiliary saturation field holds, and the state after one step of the heat-only model."""
+    halo_top, halo_bottom, tend_top, tend_bottom = ref(f"sem_noflow_sat_halo_{tag}")
+    halo = "copy" if halo_top == 1.0 else "zero"
+    assert halo_top in (0.0, 1.0) and halo_bottom == halo_top
+    grid = exponential_grid(10, 1)
+    model = trm.SoilModel(grid, soil=trm.SoilEnergyWaterCarbon(sat_halo=halo))
+    integ = make(engine, model, trm.ForwardEuler(), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", 1.0),
+                 initializers={"temperature": -1.0, "saturation_water_ice": 1.0})
+    integ.compute_tendencies()
+    tU = integ.state.tendencies_internal_energy.numpy() if hasattr(integ.state, "tendencies_internal_energy") else None
+    if tU is not None:
+        assert tU[-1, 0] == pytest.approx(tend_top, rel=1e-12) and tU[0, 0] == pytest.approx(tend_bottom, rel=1e-12, abs=1e-300)
+    trm.timestep(integ, 300.0)
+    check(integ, f"sem_noflow_sat_halo_{tag}_step1", SOIL_OUT, tol=1e-12)
+
+
+def test_reference_swrc_values():
+    """FreezeCurves' inverse retention curves at 20 water contents against the formulas the oracle restates
+    (soil_hydraulic_closures.jl:95-118)."""
+    def vg(theta, alpha, n, thsat=0.49, thres=0.0):
+        se = (theta - thres) / (thsat - thres)
+        m = 1 - 1 / n
+        return np.where(theta < thsat, -(1 / alpha) * (se ** (-1 / m) - 1) ** (1 / n), 0.0)
+
+    def bc(theta, psis=0.01, lam=0.2, thsat=0.49, thres=0.0):
+        se = (theta - thres) / (thsat - thres)
+        return np.where(theta < thsat, -psis * se ** (-1 / lam), -psis)
+
+    for tag, f in (("vangenuchten_a2_n2", lambda th: vg(th, 2.0, 2.0)), ("vangenuchten_default", lambda th: vg(th, 1.0, 2.0)),
+                   ("brookscorey_default", bc)):
+        tab = ref(f"sem_swrc_inverse_{tag}")          # rows: theta, psi (transposed on load)
+        theta, psi = tab[0], tab[1]
+        assert np.allclose(f(theta), psi, rtol=1e-12, atol=1e-14), tag
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reference_flux_bc_magnitude(engine):
+    """One ForwardEuler step under a top Flux BC: dU_top = -F dt / dz (compute_z_bcs!, abstract_timestepper.jl:69)."""
+    tab = ref("sem_flux_bc_energy_top")
+    U0, U1 = tab[0], tab[1]
+    grid = trm.ColumnGrid(trm.B200(), np.float64, trm.UniformSpacing(dz=0.1, N=10), 1)
+    integ = make(engine, trm.SoilModel(grid), trm.ForwardEuler(), boundary_conditions=trm.GroundHeatFlux(10.0),
+                 initializers={"temperature": 5.0, "saturation_water_ice": lambda x, z: 1.0 + 0 * x + 0 * z})
+    assert np.allclose(integ.state.internal_energy.numpy()[:, 0], U0, rtol=1e-14)
+    integ.step(60.0, 1)
+    assert max_scaled_err(integ.state.internal_energy.numpy()[:, 0], U1) <= 1e-14
+    tab = ref("sem_flux_bc_saturation_top")
+    s0, s1 = tab[0], tab[1]
+    integ = make(engine, trm.SoilModel(grid, soil=richards_soil()), trm.ForwardEuler(), boundary_conditions=trm.InfiltrationFlux(-1.0e-8),
+                 initializers={"temperature": 5.0, "saturation_water_ice": lambda x, z: 0.5 + 0 * x + 0 * z})
+    integ.step(60.0, 1)
+    assert max_scaled_err(integ.state.saturation_water_ice.numpy()[:, 0], s1) <= 1e-13
+
+
+# ---- always: the replay plumbing runs (short) -----------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+def test_replay_plumbing(engine):
+    for integ, names in ((replay_cfg1(engine, "a", 3), SOIL_OUT), (replay_cfg1(engine, "b", 3), SOIL_OUT),
+                         (replay_soil(engine, False, False, 300.0, 3), SOIL_OUT), (replay_soil(engine, True, True, 60.0, 3), RICH_OUT),
+                         (replay_land(engine, False, 0.5, 3), LAND_OUT), (replay_land(engine, True, 0.5, 3), VEG_OUT)):
+        for n in names:
+            assert np.isfinite(getattr(integ.state, n).numpy()).all(), n
+
+
+def test_generator_script_uses_exported_reference_names():
+    """Static check of the Julia script against the reference checkout, when that is present (this container only)."""
+    root = "/root/reference/src"
+    if not os.path.isdir(root):
+        pytest.skip("reference checkout not present")
+    import re
+    text = open(os.path.join(os.path.dirname(REF), "make_reference_golden.jl")).read()
+    exported = set()
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".jl"):
+                cont = False
+                for line in open(os.path.join(dirpath, f)):
+                    if line.strip().startswith("export") or cont:     # (export lists continue after a trailing comma)
+                        exported.update(re.findall(r"[\w!]+", line.replace("export", "")))
+                        cont = line.rstrip().endswith(",")
+    for name in ("ColumnGrid", "ExponentialSpacing", "UniformSpacing", "SoilModel", "LandModel", "ForwardEuler", "Heun", "initialize",
+                 "PrescribedSurfaceTemperature", "GroundHeatFlux", "InfiltrationFlux", "SoilInitializer", "QuasiThermalSteadyState",
+                 "ConstantSaturation", "ConstantSoilHydraulics", "UnsatKVanGenuchten", "SoilHydrology", "RichardsEq",
+                 "SoilEnergyWaterCarbon", "VegetationCarbon", "PALADYNCarbonDynamics", "PALADYNVegetationDynamics", "InputSource",
+                 "VanGenuchten", "BrooksCorey", "XY", "interior", "znodes", "set!", "run!", "timestep!", "compute_auxiliary!", "Field", "Face"):
+        assert name in text and name in exported, name
