@@ -168,13 +168,12 @@ def test_reference_noflow_saturation_halo(engine, tag):
     halo = "copy" if halo_top == 1.0 else "zero"
     assert halo_top in (0.0, 1.0) and halo_bottom == halo_top
     grid = exponential_grid(10, 1)
-    model = trm.SoilModel(grid, soil=trm.SoilEnergyWaterCarbon(sat_halo=halo))
+    model = trm.SoilModel(grid, sat_halo=halo)
     integ = make(engine, model, trm.ForwardEuler(), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", 1.0),
                  initializers={"temperature": -1.0, "saturation_water_ice": 1.0})
     integ.compute_tendencies()
-    tU = integ.state.tendencies_internal_energy.numpy() if hasattr(integ.state, "tendencies_internal_energy") else None
-    if tU is not None:
-        assert tU[-1, 0] == pytest.approx(tend_top, rel=1e-12) and tU[0, 0] == pytest.approx(tend_bottom, rel=1e-12, abs=1e-300)
+    tU = integ.state.tendency_internal_energy.numpy()
+    assert tU[-1, 0] == pytest.approx(tend_top, rel=1e-12) and tU[0, 0] == pytest.approx(tend_bottom, rel=1e-12, abs=1e-300)
     trm.timestep(integ, 300.0)
     check(integ, f"sem_noflow_sat_halo_{tag}_step1", SOIL_OUT, tol=1e-12)
 
@@ -225,6 +224,11 @@ def test_replay_plumbing(engine):
                          (replay_land(engine, False, 0.5, 3), LAND_OUT), (replay_land(engine, True, 0.5, 3), VEG_OUT)):
         for n in names:
             assert np.isfinite(getattr(integ.state, n).numpy()).all(), n
+    for halo in ("zero", "copy"):
+        integ = make(engine, trm.SoilModel(exponential_grid(10, 1), sat_halo=halo), trm.ForwardEuler(),
+                     boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", 1.0), initializers={"temperature": -1.0, "saturation_water_ice": 1.0})
+        integ.compute_tendencies()
+        assert np.isfinite(integ.state.tendency_internal_energy.numpy()).all()
 
 
 def test_generator_script_uses_exported_reference_names():
