@@ -130,9 +130,15 @@ enum trm_source {
     TRM_SRC_SINUSOID = 2,  /* clamp(mean[c] + amp[c]*sin(2*pi*t/period - phase[c]), lo, hi)      */
     TRM_SRC_TABLE = 3,     /* snapshots values[nt][ncol] at times[nt]; linear in time, flat outside
                               (Oceananigans FieldTimeSeries[Time(t)]: v2*n + v1*(1-n))                  */
-    TRM_SRC_RASTER = 4     /* same data, update rule of RasterInputSource (ext/TerrariumRastersExt/
+    TRM_SRC_RASTER = 4,    /* same data, update rule of RasterInputSource (ext/TerrariumRastersExt/
                               TerrariumRastersExt.jl:96-121): x1 + eps*(x2-x1)/dt in Float64, the node value
                               on a node, flat outside the time axis                                      */
+    TRM_SRC_FIELD_PAIR = 5 /* two per-column vectors for ONE step: the values at the step's start time t and at
+                              t + dt (trm_set_input_field_pair). A function valued boundary condition f(x, t)
+                              evaluated on the host: ForwardEuler and Heun stage 1 read the first vector, Heun stage
+                              2 reads the second one where the reference re-evaluates the function at the stage
+                              clock t + dt (Value / Gradient halos, heun.jl:53) and the first one for Flux BCs
+                              (added with the time-n state, heun.jl:63-66)                               */
 };
 
 /* Fields that can be read / written / borrowed. 3-D fields are [nz][ld]; the hydraulic
@@ -316,6 +322,9 @@ int trm_get_field(trm_handle* h, int field_id, void* host, int64_t count);
  *      src/input_output/input_sources.jl:81-171, and function valued BCs) ----------------- */
 int trm_set_input_const(trm_handle* h, int input_id, double value);
 int trm_set_input_field(trm_handle* h, int input_id, const void* host_values /* [ncol] NF */);
+/* Function valued boundary conditions (examples/simulations/soil_heat_global.jl:72-93) cannot run inside a CUDA kernel: the
+ * host evaluates f(x, t) and f(x, t + dt) before each step and hands both over (TRM_SRC_FIELD_PAIR). */
+int trm_set_input_field_pair(trm_handle* h, int input_id, const void* values_t /* [ncol] NF */, const void* values_t_plus_dt /* [ncol] NF */);
 int trm_set_input_sinusoid(trm_handle* h, int input_id, const void* mean, const void* amp,
                            const void* phase /* each [ncol] NF */, double period,
                            double lo, double hi /* clamp; use -INFINITY/INFINITY for none */);

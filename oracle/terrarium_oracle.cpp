@@ -73,6 +73,7 @@ struct InputSource {
     double period = 1.0, lo = -INFINITY, hi = INFINITY;
     int nt = 0;
     std::vector<double> times;
+    double pair_t0 = 0.0;   // TRM_SRC_FIELD_PAIR: start time of the step the pair was handed over for
 };
 
 template <class NF>
@@ -182,6 +183,9 @@ struct Oracle {
         switch (s.kind) {
             case TRM_SRC_CONST: return (NF)s.cval;
             case TRM_SRC_FIELD: return src_field[id][c];
+            // host-evaluated function of time handed over for one step: values at the step's start time `pair_t0` and at
+            // t + dt (the stage clock of Heun, heun.jl:53)
+            case TRM_SRC_FIELD_PAIR: return (double)t > s.pair_t0 ? src_amp[id][c] : src_field[id][c];
             case TRM_SRC_SINUSOID: {
                 // examples/simulations/soil_heat_global.jl:79-88: `2pi * t / period - lon` promotes to
                 // Float64 in Julia whatever NF is; the result is rounded when stored in the NF field.
@@ -993,6 +997,13 @@ int set_infield(Oracle<NF>* o, int id, const void* v) {
 
 }  // namespace
 
+template <class NF> int set_infield_pair(Oracle<NF>* o, int id, const void* v0, const void* v1) {
+    o->src[id].kind = TRM_SRC_FIELD_PAIR; o->src[id].pair_t0 = (double)o->st.time;
+    o->src_field[id].assign((const NF*)v0, (const NF*)v0 + o->nc);
+    o->src_amp[id].assign((const NF*)v1, (const NF*)v1 + o->nc);
+    return TRM_OK;
+}
+
 extern "C" {
 
 void orc_default_params(trm_params* p) {
@@ -1049,6 +1060,10 @@ int orc_set_input_const(trm_handle* h_, int id, double v) {
 int orc_set_input_field(trm_handle* h_, int id, const void* v) {
     Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bad input id");
     return h->dtype == TRM_F32 ? set_infield(h->f32, id, v) : set_infield(h->f64, id, v);
+}
+int orc_set_input_field_pair(trm_handle* h_, int id, const void* v0, const void* v1) {
+    Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bad input id");
+    return h->dtype == TRM_F32 ? set_infield_pair(h->f32, id, v0, v1) : set_infield_pair(h->f64, id, v0, v1);
 }
 int orc_set_input_sinusoid(trm_handle* h_, int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) {
     Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bad input id");

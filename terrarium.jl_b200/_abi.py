@@ -129,6 +129,7 @@ SIGNATURES = {
     "get_field": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "set_input_const": (C.c_int, [_H, C.c_int, C.c_double]),
     "set_input_field": (C.c_int, [_H, C.c_int, C.c_void_p]),
+    "set_input_field_pair": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p]),
     "set_input_sinusoid": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "set_input_table": (C.c_int, [_H, C.c_int, C.c_int32, C.POINTER(C.c_double), C.c_void_p]),
     "set_input_raster": (C.c_int, [_H, C.c_int, C.c_int32, C.POINTER(C.c_double), C.c_void_p]),

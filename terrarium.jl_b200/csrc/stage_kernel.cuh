@@ -153,6 +153,9 @@ __device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t 
     switch (s.kind) {
         case TRM_SRC_CONST: return s.cval;
         case TRM_SRC_FIELD: return s.a[c];
+        // host-evaluated function of time: the launcher points `a` at the values of the time the tendencies are evaluated
+        // at (t_x) and `b` at those of the base state's time (t_b)
+        case TRM_SRC_FIELD_PAIR: return which == 0 ? s.a[c] : s.b[c];
         case TRM_SRC_SINUSOID: {
             // `2pi * t / period - lon` is Float64 arithmetic in Julia whatever NF is
             // (examples/simulations/soil_heat_global.jl:79-88); rounded when stored in the NF field.

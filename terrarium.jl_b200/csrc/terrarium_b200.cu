@@ -45,6 +45,7 @@ struct HandleBase {
     virtual int field_view(int id, const void** p, int64_t* ld, int32_t* nrows) = 0;
     virtual int set_input_const(int id, double v) = 0;
     virtual int set_input_field(int id, const void* v) = 0;
+    virtual int set_input_field_pair(int id, const void* v0, const void* v1) = 0;
     virtual int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) = 0;
     virtual int get_input(int id, void* host, int64_t count) = 0;
     virtual int accumulate(int id, double w) = 0;
@@ -352,6 +353,18 @@ struct Handle : HandleBase {
         in[id].kind = TRM_SRC_FIELD;
         return TRM_OK;
     }
+    int set_input_field_pair(int id, const void* v0, const void* v1) override {
+        CU(cudaSetDevice(device));
+        Input& s = in[id];
+        if ((s.kind == TRM_SRC_TABLE || s.kind == TRM_SRC_RASTER) && s.a) { dfree(s.a); s.a = nullptr; }
+        if (int rc = ensure(&s.a, ld)) return rc;
+        if (int rc = ensure(&s.b, ld)) return rc;
+        CU(cudaMemcpyAsync(s.a, v0, nc * sizeof(NF), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(s.b, v1, nc * sizeof(NF), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        s.kind = TRM_SRC_FIELD_PAIR;
+        return TRM_OK;
+    }
     int set_input_sinusoid(int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) override {
         CU(cudaSetDevice(device));
         Input& s = in[id];
@@ -405,6 +418,7 @@ struct Handle : HandleBase {
             InputDesc<NF>& d = a.in[i]; const Input& s = in[i];
             d.kind = s.kind; d.nt = s.nt; d.cval = (NF)s.cval; d.period = s.period; d.lo = s.lo; d.hi = s.hi;
             d.a = s.a; d.b = s.b; d.c = s.c; d.ld = ld;
+            if (s.kind == TRM_SRC_FIELD_PAIR) d.b = s.a;   // every evaluation at the step's start time; Heun stage 2: pair_stage2()
         }
         a.Kf = Kf;
         a.Ts = land2d[0]; a.G = land2d[1]; a.SWup = land2d[2]; a.LWup = land2d[3]; a.Rnet = land2d[4];
@@ -448,6 +462,10 @@ struct Handle : HandleBase {
             bracket(in[i], (double)a.t_x, a.in[i].br[0]);
             bracket(in[i], (double)a.t_b, a.in[i].br[1]);
         }
+    }
+    // Heun stage 2: host-evaluated functions of time are read at t + dt where the tendencies are evaluated, at t for Flux BCs
+    void pair_stage2(StageArgs<NF>& a) {
+        for (int i = 0; i < TRM_IN_COUNT; ++i) if (in[i].kind == TRM_SRC_FIELD_PAIR) { a.in[i].a = in[i].b; a.in[i].b = in[i].a; }
     }
     void x_state(StageArgs<NF>& a) { a.xU = U; a.xS = S; a.xT = T; a.xL = Lq; a.xP = P; a.xWt = Wt; a.bU = U; a.bS = S; a.bSx = Sx; }
     void y_state(StageArgs<NF>& a) { a.yU = U; a.yS = S; a.yT = T; a.yL = Lq; a.yP = P; a.yWt = Wt; a.ySx = Sx; }
@@ -608,6 +626,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             b.xbeta = gbeta;
             y_state(b);
             set_times(b);
+            pair_stage2(b);
             apply_host_io(b, true);
             // stage 2 only re-evaluates the vegetation block (k2 of canopy water, vegetation carbon and area fraction);
             // the bare-ground surface block of the stage state has no effect on the step (heun.jl:63-66)
@@ -999,6 +1018,10 @@ int trm_set_field(trm_handle* h, int id, const void* host, int64_t count) { if (
 int trm_get_field(trm_handle* h, int id, void* host, int64_t count) { if (!h || !host) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->get_field(id, host, count); }
 int trm_set_input_const(trm_handle* h, int id, double v) { if (!h || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_const(id, v); }
 int trm_set_input_field(trm_handle* h, int id, const void* v) { if (!h || !v || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_field(id, v); }
+int trm_set_input_field_pair(trm_handle* h, int id, const void* v0, const void* v1) {
+    if (!h || !v0 || !v1 || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id");
+    return H(h)->set_input_field_pair(id, v0, v1);
+}
 int trm_set_input_sinusoid(trm_handle* h, int id, const void* mean, const void* amp, const void* phase, double period, double lo, double hi) {
     if (!h || !mean || !amp || !phase || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id");
     return H(h)->set_input_sinusoid(id, mean, amp, phase, period, lo, hi);

@@ -163,6 +163,7 @@ class ModelIntegrator:
         grid = model.grid
         self.grid, self.nf, self.nz = grid, grid.nf, grid.Nz
         rank, world = partition if partition is not None else (0, 1)
+        self.partition = (int(rank), int(world))
         self.col0, self.col1 = grid.partition(rank, world)
         self.ncol = self.col1 - self.col0
         self.ncol_global = grid.Nc
@@ -307,28 +308,36 @@ class ModelIntegrator:
             v = self._percol(value)
             lib.check(lib.set_input_field(h, input_id, v.ctypes.data_as(C.c_void_p)), "set_input_field")
 
-    def _push_callback(self, input_id, t):
+    def _evaluate_callback(self, input_id, t):
         f = self._host_callbacks[input_id]
         x = self.grid.xnodes()[self.col0:self.col1].astype(self.nf)
         try:
             v = np.broadcast_to(np.asarray(f(x, self.nf(t)), dtype=np.float64), (self.ncol,))
         except Exception:
             v = np.array([f(xi, self.nf(t)) for xi in x], dtype=np.float64)
-        v = np.ascontiguousarray(v, dtype=self.nf)
-        self._lib.check(self._lib.set_input_field(self._h, input_id, v.ctypes.data_as(C.c_void_p)), "set_input_field")
+        return np.ascontiguousarray(v, dtype=self.nf)
+
+    def _push_callback(self, input_id, t, dt=None):
+        """Hand a function valued boundary condition f(x, t) to the library for the step starting at `t`: its values at t,
+        and -- for Heun, whose second stage re-evaluates the function at the stage clock (heun.jl:53) -- at t + dt."""
+        v = self._evaluate_callback(input_id, t)
+        if dt is None:
+            self._lib.check(self._lib.set_input_field(self._h, input_id, v.ctypes.data_as(C.c_void_p)), "set_input_field")
+            return
+        v1 = self._evaluate_callback(input_id, self.nf(t) + self.nf(dt))   # tick!(clock, dt) in the clock's number format
+        self._lib.check(self._lib.set_input_field_pair(self._h, input_id, v.ctypes.data_as(C.c_void_p), v1.ctypes.data_as(C.c_void_p)),
+                        "set_input_field_pair")
 
     # ------------------------------------------------------------------------------------------
     def step(self, dt: float, nsteps: int = 1):
         """``nsteps`` x ``timestep!(integrator, dt; finalize=false)``."""
         lib = self._lib
         if self._host_callbacks:
-            if isinstance(self.timestepper, Heun):
-                raise NotImplementedError("function valued boundary conditions evaluated on the host are only supported "
-                                          "with ForwardEuler; use Sinusoid/TimeSeries (device resident) with Heun")
+            heun = isinstance(self.timestepper, Heun)
             for _ in range(int(nsteps)):
                 t = self.clock.time
                 for input_id in self._host_callbacks:
-                    self._push_callback(input_id, t)
+                    self._push_callback(input_id, t, float(dt) if heun else None)
                 lib.check(lib.step(self._h, float(dt), 1), "step")
         else:
             lib.check(lib.step(self._h, float(dt), int(nsteps)), "step")

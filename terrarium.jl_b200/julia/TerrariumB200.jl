@@ -59,7 +59,12 @@ mutable struct B200Integrator{NF, Model, TS}
     timestepper::TS
     ncol::Int
     nz::Int
+    # function valued boundary conditions f(x, t) (examples/simulations/soil_heat_global.jl:72-93): evaluated on the host before
+    # every step at the x-nodes of the columns (input slot => function)
+    callbacks::Vector{Pair{Int, Any}}
+    xnodes::Vector{NF}
 end
+B200Integrator{NF, M, TS}(handle, model, ts, ncol, nz) where {NF, M, TS} = B200Integrator{NF, M, TS}(handle, model, ts, ncol, nz, Pair{Int, Any}[], NF[])
 Base.eltype(::B200Integrator{NF}) where {NF} = NF
 
 dtype_code(::Type{Float32}) = Int32(0)
@@ -202,6 +207,7 @@ step_async!(integ::B200Integrator, Δt, nsteps = 1) =
     check(ccall((:trm_step_async, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, convert_dt(Δt), Int64(nsteps)), "step_async")
 
 function Terrarium.timestep!(integ::B200Integrator, Δt = default_dt(integ.timestepper); finalize = true)
+    isempty(integ.callbacks) || push_callbacks!(integ, current_time(integ), convert_dt(Δt))
     check(ccall((:trm_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, convert_dt(Δt), 1), "step")
     finalize && check(ccall((:trm_compute_auxiliary, LIB), Cint, (Ptr{Cvoid},), integ.handle), "compute_auxiliary")
     return nothing
@@ -210,7 +216,14 @@ end
 function Terrarium.run!(integ::B200Integrator; steps = nothing, period = nothing, Δt = default_dt(integ.timestepper))
     Δt = convert_dt(Δt)
     n = get_steps(steps, period, Δt)
-    check(ccall((:trm_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, Δt, n), "step")          # n fused stage launches
+    if isempty(integ.callbacks)
+        check(ccall((:trm_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, Δt, n), "step")      # n fused stage launches
+    else
+        for _ in 1:n                                                                                        # host functions: step by step
+            push_callbacks!(integ, current_time(integ), Δt)
+            check(ccall((:trm_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, Δt, 1), "step")
+        end
+    end
     check(ccall((:trm_compute_auxiliary, LIB), Cint, (Ptr{Cvoid},), integ.handle), "compute_auxiliary")
     return integ
 end
@@ -264,9 +277,8 @@ function translate_bcs(boundary_conditions)
             throw(ArgumentError("no boundary condition slot for $field / $side in the B200 library"))
         end
         isnothing(bc.condition) && continue                  # NoFluxBoundaryCondition: the default
-        bc.condition isa Function && throw(ArgumentError(
-            "function valued boundary conditions cannot run inside the CUDA kernels: pass a number, a per-column vector, " *
-            "a TerrariumB200.Sinusoid or a TerrariumB200.TimeSeries for $field / $side"))
+        # (a Julia function cannot run inside the library's kernels: it is evaluated on the host before every step, see
+        #  set_input!(integ, id, ::Function); device-resident forms -- Sinusoid, TimeSeries, vectors -- avoid that round trip)
         input = length(sources)                              # TRM_IN_USER0 + k
         input < 8 || throw(ArgumentError("at most 8 user boundary inputs"))
         slots[slot + 1] = TrmBC(bc_kind(bc), Int32(input))
@@ -293,6 +305,29 @@ end
 function set_input!(integ::B200Integrator{NF}, id, v::AbstractVector) where {NF}
     a = percolumn(NF, v, integ.ncol)
     GC.@preserve a check(ccall((:trm_set_input_field, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), integ.handle, input_id(id), pointer(a)), "set_input_field")
+end
+function set_input!(integ::B200Integrator{NF}, id, f::Function) where {NF}
+    filter!(p -> first(p) != Int(input_id(id)), integ.callbacks)
+    push!(integ.callbacks, Int(input_id(id)) => f)
+    if isempty(integ.xnodes)   # x-nodes of the columns (SURVEY.md Appendix B.7): ColumnRingGrid 1 + (i - 1/2)(Nc - 1)/Nc, ColumnGrid (i - 1/2)/Nc
+        grid = Terrarium.get_field_grid(Terrarium.get_grid(integ.model))
+        integ.xnodes = collect(NF, Terrarium.Oceananigans.Grids.xnodes(grid, Center()))
+    end
+    push_callbacks!(integ, current_time(integ), nothing)
+end
+# values of every function valued boundary condition for the step that starts at `t`: f(x, t), and under Heun also
+# f(x, t + Δt), which the second stage reads where the reference re-evaluates the function at the stage clock (heun.jl:53)
+function push_callbacks!(integ::B200Integrator{NF}, t, Δt) where {NF}
+    for (id, f) in integ.callbacks
+        v0 = NF[f(x, NF(t)) for x in integ.xnodes]
+        if isnothing(Δt) || !(integ.timestepper isa Heun)
+            GC.@preserve v0 check(ccall((:trm_set_input_field, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), integ.handle, Cint(id), pointer(v0)), "set_input_field")
+        else
+            v1 = NF[f(x, NF(t) + NF(Δt)) for x in integ.xnodes]
+            GC.@preserve v0 v1 check(ccall((:trm_set_input_field_pair, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), integ.handle,
+                                           Cint(id), pointer(v0), pointer(v1)), "set_input_field_pair")
+        end
+    end
 end
 function set_input!(integ::B200Integrator{NF}, id, s::Sinusoid) where {NF}
     m, a, p = percolumn(NF, s.mean, integ.ncol), percolumn(NF, s.amp, integ.ncol), percolumn(NF, s.phase, integ.ncol)

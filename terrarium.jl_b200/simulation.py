@@ -128,6 +128,11 @@ class NetCDFWriter:
             outputs = {n: n for n in outputs}
         self.integrator = integrator
         self.fields: Dict[str, Field] = {k: (v if isinstance(v, Field) else Field(integrator, v)) for k, v in outputs.items()}
+        # one file per rank of a partitioned run (each rank holds its own column range): <name>_rank<r>.<ext>
+        rank_world = getattr(integrator, "partition", None)
+        if rank_world is not None and rank_world[1] > 1:
+            stem, ext = os.path.splitext(filename)
+            filename = f"{stem}_rank{rank_world[0]}{ext}"
         self.filename, self.schedule = filename, schedule
         if os.path.exists(filename) and not overwrite_existing:
             raise FileExistsError(f"{filename} exists (pass overwrite_existing=True)")
@@ -137,6 +142,9 @@ class NetCDFWriter:
         f.createDimension("z", nz); f.createDimension("zf", nz + 1); f.createDimension("column", nc)
         self._time = f.createVariable("time", "f8", ("time",))
         self._time.units = "s"
+        f.column_range_start = np.int32(integrator.col0)     # [col0, col1) of the global column axis held by this file
+        f.column_range_stop = np.int32(integrator.col1)
+        f.columns_global = np.int32(integrator.ncol_global)
         if "grid" in including:
             zc = f.createVariable("z", "f8", ("z",)); zc[:] = integrator.grid.znodes_center().astype(np.float64)
             zf = f.createVariable("zf", "f8", ("zf",)); zf[:] = integrator.grid.znodes_face().astype(np.float64)
@@ -263,8 +271,14 @@ class Simulation:
         if self.stop_time is None and stop_iteration is None:
             raise ValueError("Simulation needs stop_time or stop_iteration")
         self.align_time_step = align_time_step
-        if finalize_every_step is None:   # needed for exact equivalence only where an auxiliary feeds the next evaluation
-            finalize_every_step = getattr(integrator.model, "vegetation", None) is not None
+        if finalize_every_step is None:
+            # the reference's Simulation calls timestep!(...; finalize = true) every step (model_integrator.jl:64,125-131).
+            # compute_auxiliary! is not idempotent for ANY LandModel: the surface block reads the stored skin temperature and
+            # writes a new one (ImplicitSkinTemperature, skin_temperature.jl:62-80); the vegetated model additionally reads the
+            # net assimilation of the previous evaluation. Only a SoilModel, whose auxiliaries are never read back, may batch
+            # steps without changing the trajectory.
+            from .models import LandModel
+            finalize_every_step = isinstance(integrator.model, LandModel)
         self.finalize_every_step = finalize_every_step
         self.output_writers: Dict[str, NetCDFWriter] = {}
         self.callbacks: Dict[str, Callback] = {}

@@ -485,10 +485,24 @@ def test_function_valued_boundary_condition(engine):
     Ta, Tb = a.state.temperature.numpy(), b.state.temperature.numpy()
     assert np.max(np.abs(Ta - Tb)) <= 1e-11 * np.max(np.abs(Tb))
     assert a.clock.time == b.clock.time == 30000.0
-    # with Heun the stage at t + dt would need a second host evaluation inside the step: refused, not silently wrong
+    # Heun re-evaluates the function at the stage clock t + dt (heun.jl:53): the host hands over f(x, t) and f(x, t + dt)
     h = make(engine, trm.SoilModel(grid), trm.Heun(dt=300.0), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", surface_temperature), initializers=inits)
-    with pytest.raises(NotImplementedError):
-        h.step(300.0, 1)
+    s = make(engine, trm.SoilModel(grid), trm.Heun(dt=300.0), initializers=inits,
+             boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", trm.Sinusoid(mean=T0, amp=10.0, phase=lon, period=P)))
+    h.step(300.0, 100)
+    s.step(300.0, 100)
+    Th, Ts = h.state.temperature.numpy(), s.state.temperature.numpy()
+    assert np.max(np.abs(Th - Ts)) <= 1e-11 * np.max(np.abs(Ts))
+    assert np.max(np.abs(Th - Ta)) > 1e-6          # (and Heun is not ForwardEuler)
+    # a function valued FLUX boundary condition is added with the time-n state in both stages (heun.jl:63-66)
+    def heat_flux(x, t):
+        return -5.0 + 3.0 * np.sin(2 * np.pi * t / P) + 0 * x
+    hf = make(engine, trm.SoilModel(grid), trm.Heun(dt=300.0), boundary_conditions=trm.GroundHeatFlux(heat_flux), initializers=inits)
+    sf = make(engine, trm.SoilModel(grid), trm.Heun(dt=300.0), initializers=inits,
+              boundary_conditions=trm.GroundHeatFlux(trm.Sinusoid(mean=-5.0 + 0 * T0, amp=3.0, phase=0.0 * lon, period=P)))
+    hf.step(300.0, 50)
+    sf.step(300.0, 50)
+    assert np.max(np.abs(hf.state.temperature.numpy() - sf.state.temperature.numpy())) <= 1e-11 * np.max(np.abs(Ts))
 
 
 # ---------------------------------------------------------------------------------------------

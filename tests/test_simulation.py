@@ -108,3 +108,56 @@ def test_averaged_time_interval(engine, tmp_path):
         np.testing.assert_allclose(Tg[rec], accG / 1800.0, rtol=1e-13, atol=1e-13)
         np.testing.assert_allclose(K[rec], accK / 1800.0, rtol=1e-13)
     assert np.array_equal(integ.state.temperature.numpy(), ref.state.temperature.numpy())
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_bare_ground_land_trajectory_does_not_depend_on_the_output_interval(engine, tmp_path):
+    """compute_auxiliary! is not idempotent for the bare-ground LandModel either (the surface block reads the stored skin
+    temperature and writes a new one), and the reference's Simulation finalizes every step (model_integrator.jl:64,125-131):
+    the state after 12 steps must not depend on how often something observes it, and must equal a timestep! loop."""
+    from common import synthetic_land_case
+    runs = []
+    for every in (1, 4, 12):
+        integ = synthetic_land_case(engine, 9, windspeed=0.5)
+        sim = trm.Simulation(integ, stop_iteration=12, dt=60.0)
+        assert sim.finalize_every_step
+        sim.output_writers["o"] = trm.NetCDFWriter(integ, ["skin_temperature", "temperature"], filename=str(tmp_path / f"o{every}.nc"),
+                                                   schedule=trm.IterationInterval(every))
+        sim.run(); sim.close()
+        runs.append(integ)
+    loop = synthetic_land_case(engine, 9, windspeed=0.5)
+    loop.compute_auxiliary()
+    for _ in range(12):
+        trm.timestep(loop, 60.0)
+    for name in ("skin_temperature", "temperature", "ground_heat_flux", "internal_energy"):
+        want = getattr(loop.state, name).numpy()
+        for integ in runs:
+            assert np.array_equal(getattr(integ.state, name).numpy(), want), name
+    # a SoilModel has no auxiliary that is read back: it may batch steps
+    from common import synthetic_soil_case
+    assert not trm.Simulation(synthetic_soil_case(engine, 3), stop_iteration=1, dt=60.0).finalize_every_step
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_partitioned_run_writes_one_file_per_rank(engine, tmp_path):
+    """Every rank of a partitioned run holds its own column range: the writer must not share one file between ranks."""
+    from common import make, synthetic_columns
+    n = 10
+    lat, lon, T0 = synthetic_columns(n)
+    files = []
+    for rank in range(2):
+        grid = trm.ColumnGrid(trm.B200(), np.float64, trm.ExponentialSpacing(N=8), n)
+        integ = make(engine, trm.SoilModel(grid), trm.ForwardEuler(dt=300.0), boundary_conditions=trm.PrescribedSurfaceTemperature("T_ub", T0),
+                     initializers={"temperature": lambda x, z: T0[None, :] - 0.05 * z, "saturation_water_ice": 1.0}, partition=(rank, 2))
+        sim = trm.Simulation(integ, stop_iteration=3, dt=300.0)
+        w = trm.NetCDFWriter(integ, ["temperature"], filename=str(tmp_path / "part.nc"), schedule=trm.IterationInterval(1))
+        sim.output_writers["t"] = w
+        sim.run(); sim.close()
+        files.append((w.filename, integ.col0, integ.col1, integ.state.temperature.numpy()))
+    assert files[0][0].endswith("part_rank0.nc") and files[1][0].endswith("part_rank1.nc")
+    from scipy.io import netcdf_file
+    for name, c0, c1, T in files:
+        with netcdf_file(name, "r", mmap=False) as f:
+            assert int(f.column_range_start) == c0 and int(f.column_range_stop) == c1 and int(f.columns_global) == n
+            assert np.array_equal(f.variables["temperature"][-1], T)
+    assert files[0][2] == files[1][1] and files[1][2] == n
