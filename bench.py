@@ -38,6 +38,7 @@ UNIT = "column-layer-steps/s"
 NZ = 30
 DT = 60.0
 SEED = 20260101
+CPU_BUILD = ""
 
 
 def algorithmic_bytes_per_cell(itemsize: int, nz: int, model: str = "soil", heun: bool = False) -> float:
@@ -177,6 +178,8 @@ def cpu_reference(ncol_sample, steps, warmup, nf, budget_s=None):
     With `budget_s` the step count is chosen from a 2-step probe so that the timed sample takes about that long."""
     import oracle_integrator as oi
     import terrarium_jl_b200 as trm
+    if "TERRARIUM_ORACLE_LIB" not in os.environ:   # the CPU arm uses the instruction set of the host it is timed on
+        os.environ["TERRARIUM_ORACLE_LIB"] = oi.build_native_oracle()
     integ, _, _ = build_case(trm, oi.oracle_initialize, ncol_sample, 0, 1, 0, nf, "faithful")
     cdll = oi.oracle_library().cdll
     if os.environ.get("TORCHELASTIC_RUN_ID") and "TERRARIUM_CPU_THREADS" not in os.environ:
@@ -194,6 +197,8 @@ def cpu_reference(ncol_sample, steps, warmup, nf, budget_s=None):
     t0 = time.perf_counter()
     integ.step(DT, steps)
     el = time.perf_counter() - t0
+    global CPU_BUILD
+    CPU_BUILD = "-O3 -march=native" if os.environ.get("TERRARIUM_ORACLE_LIB", "").endswith("_native.so") else "-O3 -march=x86-64-v3 (AVX2)"
     return ncol_sample * NZ * steps / el, el, cores, steps
 
 
@@ -241,7 +246,7 @@ def main():
                                    "Julia reference cannot run here (no julia in the image)",
                        "columns_per_step": ncs, "nz": NZ},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{ncs} columns x {NZ} layers x {args.steps} steps of the same workload"},
+                             "sample": f"{ncs} columns x {NZ} layers x {args.steps} steps of the same workload; g++ {CPU_BUILD}, OpenMP"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -435,7 +440,7 @@ def main():
             v, el, cores, nst = cpu_reference(args.cpu_columns, 10, 1, nf, budget_s=12.0)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{args.cpu_columns} columns x {NZ} layers x {nst} steps of the same workload ({el:.1f} s); restated "
-                                      "reference CPU path (C++/OpenMP oracle, one loop nest per reference kernel), all host cores"}
+                                      f"reference CPU path (C++/OpenMP oracle, one loop nest per reference kernel, g++ {CPU_BUILD}), all host cores"}
         except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU number
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
 

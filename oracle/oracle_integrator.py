@@ -33,10 +33,21 @@ def build_oracle(force: bool = False) -> str:
     return ORACLE_PATH
 
 
+def build_native_oracle() -> str:
+    """The oracle compiled with -march=native ON THIS HOST (bench.py's CPU baseline); falls back to the portable build."""
+    try:
+        subprocess.run(["make", "-C", HERE, "-s", "native"], check=True, capture_output=True, timeout=300)
+        path = os.path.join(HERE, "libterrarium_oracle_native.so")
+        C.CDLL(path)
+        return path
+    except Exception:
+        return build_oracle()
+
+
 @lru_cache(maxsize=1)
 def oracle_library() -> abi.BoundLibrary:
-    build_oracle()
-    lib = abi.BoundLibrary(C.CDLL(ORACLE_PATH), "orc_", skip=abi.DEVICE_ONLY)
+    path = os.environ.get("TERRARIUM_ORACLE_LIB") or build_oracle()
+    lib = abi.BoundLibrary(C.CDLL(path), "orc_", skip=abi.DEVICE_ONLY)
     lib.cdll.orc_array_passes.restype = C.c_int64
     lib.cdll.orc_array_passes.argtypes = [C.c_void_p]
     lib.cdll.orc_num_threads.restype = C.c_int

@@ -845,15 +845,35 @@ __global__ void __launch_bounds__(256) diag_kernel(int64_t ncol, int64_t ld, int
         for (int i = 0; i < 7; ++i) partial[(int64_t)blockIdx.x * 8 + i] = red[i][0];
 }
 
-static __global__ void finish_diag(int nblocks, const double* __restrict__ partial, double ncol, double* __restrict__ out) {
-    // single thread, fixed order: deterministic sums
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// second level of the reduction: one block, every thread folds the partials b = t, t + 256, ... in that fixed order, then a
+// fixed tree over the 256 threads -- parallel and still deterministic (the summation order does not depend on timing)
+static __global__ void __launch_bounds__(256) finish_diag(int nblocks, const double* __restrict__ partial, double ncol, double* __restrict__ out) {
     double e = 0, w = 0, tmin = CUDART_INF, tmax = -CUDART_INF, smin = CUDART_INF, smax = -CUDART_INF, nan = 0;
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = threadIdx.x; b < nblocks; b += 256) {
         const double* q = partial + (int64_t)b * 8;
         e += q[0]; w += q[1]; tmin = fmin(tmin, q[2]); tmax = fmax(tmax, q[3]); smin = fmin(smin, q[4]); smax = fmax(smax, q[5]); nan += q[6];
     }
-    out[0] = e; out[1] = w; out[2] = tmin; out[3] = tmax; out[4] = smin; out[5] = smax; out[6] = nan; out[7] = ncol;
+    __shared__ double red[7][256];
+    const double v[7] = {e, w, tmin, tmax, smin, smax, nan};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) red[i][threadIdx.x] = v[i];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + s];
+            red[1][threadIdx.x] += red[1][threadIdx.x + s];
+            red[2][threadIdx.x] = fmin(red[2][threadIdx.x], red[2][threadIdx.x + s]);
+            red[3][threadIdx.x] = fmax(red[3][threadIdx.x], red[3][threadIdx.x + s]);
+            red[4][threadIdx.x] = fmin(red[4][threadIdx.x], red[4][threadIdx.x + s]);
+            red[5][threadIdx.x] = fmax(red[5][threadIdx.x], red[5][threadIdx.x + s]);
+            red[6][threadIdx.x] += red[6][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 7; ++i) out[i] = red[i][0];
+        out[7] = ncol;
+    }
 }
 
 }  // namespace trm

@@ -125,6 +125,14 @@ struct Handle : HandleBase {
     int64_t* ring_index = nullptr; int64_t nring = 0;   // ring-grid position of every owned column (ColumnRingGrid mask)
     NF* ring_buf = nullptr; size_t ring_count = 0;
     bool timing_open = false;
+    bool fallback_logged = false;   // the staged kernels do not apply (fields of 2^32 elements or more): said once on stderr
+    void log_fallback() {
+        if (fallback_logged) return;
+        fallback_logged = true;
+        std::fprintf(stderr, "terrarium_b200: nz * ld = %llu >= 2^32 elements per field: the shared-memory staged kernels use 32-bit element "
+                             "offsets, running the register-streaming stage kernel instead (about 1.4x slower per step)\n",
+                     (unsigned long long)nz * (unsigned long long)ld);
+    }
     // per-step exchange through mapped host memory (trm_bind_host_io): step k -> k+1 reads input `in_id` from slot
     // k % nslots of `in_dev` and writes field `out_id` of the new state to the same slot of `out_dev`; ev[slot] fires when
     // that step has completed
@@ -548,7 +556,7 @@ template <> int Handle<float>::launch_euler(const StageArgs<float>& a, int load_
     const int generic = a.mode == MODE_EULER ? (load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE) : VAR_GENERIC;
     if (euler_impl != 1) return launch(generic, a);
     cudaError_t e = ks->euler_f32(phys, a.mode, load_aux, a, stream);
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(generic, a); }
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); log_fallback(); return launch(generic, a); }
     ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
@@ -557,7 +565,7 @@ template <> int Handle<double>::launch_euler(const StageArgs<double>& a, int loa
     const int generic = a.mode == MODE_EULER ? (load_aux ? VAR_EULER_LOAD : VAR_EULER_RECOMPUTE) : VAR_GENERIC;
     if (euler_impl != 1) return launch(generic, a);
     cudaError_t e = ks->euler_f64(phys, a.mode, load_aux, a, stream);
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return launch(generic, a); }
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); log_fallback(); return launch(generic, a); }
     ++launches;
     if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("euler kernel launch: ") + cudaGetErrorString(e));
     return TRM_OK;
@@ -940,7 +948,7 @@ template <class NF> int Handle<NF>::tendencies() {
 template <class NF> int Handle<NF>::diagnostics(trm_diag* out, double** dev) {
     CU(cudaSetDevice(device));
     diag_kernel<NF><<<diag_blocks, 256, 0, stream>>>(nc, ld, nz, metrics, p.por, U, T, S, richards ? Sx : nullptr, diag_partial);
-    finish_diag<<<1, 32, 0, stream>>>(diag_blocks, diag_partial, (double)nc, diag_out);
+    finish_diag<<<1, 256, 0, stream>>>(diag_blocks, diag_partial, (double)nc, diag_out);
     launches += 2;
     CU(cudaGetLastError());
     if (dev) *dev = diag_out;
