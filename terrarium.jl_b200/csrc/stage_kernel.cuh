@@ -236,9 +236,12 @@ __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface
 // function: the bare-ground LandModel must not pay for the registers this block needs around the call. Scalars come
 // in by value; the results land_surface needs (ground / canopy evaporation, transpiration, rain reaching the ground)
 // are read back from the auxiliary fields this function writes.
+// results of the vegetation block that the rest of the surface block needs (kept in registers by the inlined variant)
+template <class NF> struct VegOut { NF Egnd, rain_ground, E_can, transp; };
+
 template <class NF, bool FAST>
-__device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t c, NF Ta, NF SWd, NF pres, NF ea, NF rain, NF Vc, double ra,
-                                                NF dq, NF T_top, NF beta_sm, NF beta_g, bool stage2) {
+__device__ __forceinline__ void vegetation_surface_impl(const StageArgs<NF>& A, int64_t c, NF Ta, NF SWd, NF pres, NF ea, NF rain, NF Vc, double ra,
+                                                        NF dq, NF T_top, NF beta_sm, NF beta_g, bool stage2, VegOut<NF>& out) {
     const DevParams<NF>& p = A.p;
     const VegParams<NF>& v = A.vp;
     const NF co2 = surface_input(A.in[TRM_IN_CO2], c, A.t_x);
@@ -304,12 +307,19 @@ __device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t 
             A.vy[i][c] = A.vb[i][c] + ki * A.dt;
         }
     }
+    out.Egnd = Egnd; out.rain_ground = rain_ground; out.E_can = E_can; out.transp = transp;
     if (stage2) return;   // the auxiliaries of a stage-2 evaluation belong to the stage copy (heun.jl:45-58)
     NF* const* o = A.veg2d;
     o[VF_LAIB][c] = LAIb; o[VF_LAI][c] = LAI; o[VF_PHEN][c] = phen; o[VF_GWCAN][c] = gw; o[VF_LAMC][c] = lamc;
     o[VF_AN][c] = An; o[VF_RD][c] = Rd; o[VF_GPP][c] = GPP; o[VF_RA][c] = Ra; o[VF_NPP][c] = NPP; o[VF_BETASM][c] = beta_sm;
     o[VF_ICAN][c] = I_can; o[VF_RCAN][c] = R_can; o[VF_FCAN][c] = f_can; o[VF_RAING][c] = rain_ground;
-    o[VF_ECAN][c] = E_can; o[VF_TRANSP][c] = transp; A.Egnd[c] = Egnd;
+    o[VF_ECAN][c] = E_can; o[VF_TRANSP][c] = transp;
+}
+// out-of-line copy for the generic stage kernel, which must not pay for the registers of this block around the call
+template <class NF, bool FAST>
+__device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t c, NF Ta, NF SWd, NF pres, NF ea, NF rain, NF Vc, double ra,
+                                                NF dq, NF T_top, NF beta_sm, NF beta_g, bool stage2, VegOut<NF>& out) {
+    vegetation_surface_impl<NF, FAST>(A, c, Ta, SWd, pres, ea, rain, Vc, ra, dq, T_top, beta_sm, beta_g, stage2, out);
 }
 
 // LandModel per-column surface processes for one update_state! (land_model.jl:79-88): bare-ground evaporation,
@@ -322,9 +332,9 @@ __device__ __noinline__ void vegetation_surface(const StageArgs<NF>& A, int64_t 
 // evapotranspiration (surface_hydrology.jl:36-50) and advances canopy water, vegetation carbon and area fraction.
 // `stage2` (Heun stage 2): only what feeds the k2 tendencies of those three variables is evaluated -- on the stage
 // state, at t + dt -- and no auxiliary field is written (they belong to the stage copy in the reference, heun.jl:45-58).
-template <class NF, bool FAST>
-__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF liq_top, NF K_top, NF dz_top,
-                                          NF beta_sm, bool stage2, NF& G_out, NF& inf_out) {
+template <class NF, bool FAST, bool INLINE_VEG>
+__device__ __forceinline__ void land_surface_impl(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF liq_top, NF K_top, NF dz_top,
+                                                  NF beta_sm, bool stage2, NF& G_out, NF& inf_out) {
     const DevParams<NF>& p = A.p;
     const bool veg = has_veg(A);
     // (inputs: see surface_input)
@@ -364,11 +374,13 @@ __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, boo
     NF rain_ground = a.rain;   // NoCanopyInterception: rainfall_ground aliases rainfall (canopy_interception.jl:11-15)
     NF Qh = Egnd;              // surface_humidity_flux of the evapotranspiration scheme
     if (veg) {
-        vegetation_surface<NF, FAST>(A, c, a.Ta, a.SWd, a.pres, ea, a.rain, Vc, a.ra, dq, T_top, beta_sm, beta_g, stage2);
+        VegOut<NF> vo;
+        if (INLINE_VEG) vegetation_surface_impl<NF, FAST>(A, c, a.Ta, a.SWd, a.pres, ea, a.rain, Vc, a.ra, dq, T_top, beta_sm, beta_g, stage2, vo);
+        else vegetation_surface<NF, FAST>(A, c, a.Ta, a.SWd, a.pres, ea, a.rain, Vc, a.ra, dq, T_top, beta_sm, beta_g, stage2, vo);
         if (stage2) { G_out = A.G[c]; inf_out = A.infil[c]; return; }   // Flux BCs use the time-n fluxes of stage 1 (heun.jl:63-66)
-        Egnd = A.Egnd[c];
-        rain_ground = A.veg2d[VF_RAING][c];
-        Qh = Egnd + A.veg2d[VF_ECAN][c] + A.veg2d[VF_TRANSP][c];   // surface_humidity_flux, canopy_evapotranspiration.jl:75-80
+        Egnd = vo.Egnd;
+        rain_ground = vo.rain_ground;
+        Qh = Egnd + vo.E_can + vo.transp;   // surface_humidity_flux, canopy_evapotranspiration.jl:75-80
     }
     // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 ; K_top = Kf[Nz]
     NF drain, inf;
@@ -391,6 +403,13 @@ __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, boo
     if (!prescribed) A.Ts[c] = Ts;
     G_out = G; inf_out = inf;
 }
+// out of line for the generic stage kernel: it runs once per column and step, and inlined it would set the register
+// budget of the whole layer loop
+template <class NF, bool FAST>
+__device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, bool richards, NF T_top, NF sat_top, NF liq_top, NF K_top, NF dz_top,
+                                          NF beta_sm, bool stage2, NF& G_out, NF& inf_out) {
+    land_surface_impl<NF, FAST, false>(A, c, richards, T_top, sat_top, liq_top, K_top, dz_top, beta_sm, stage2, G_out, inf_out);
+}
 
 // ---- surface block as its own launch (staged ForwardEuler / Heun kernels, euler_kernel.cuh) ----------------------
 // The surface processes of one update_state! only need the top soil layer of the state they are evaluated on, the
@@ -398,12 +417,16 @@ __device__ __noinline__ void land_surface(const StageArgs<NF>& A, int64_t c, boo
 // that state has left in `xbeta`. Running them as a separate one-thread-per-column launch keeps the layer loop of
 // the stage kernel free of the call (and of its register demand); the stage kernel then reads G and the infiltration
 // like any other Flux boundary condition.
+// resident blocks of 128 threads the register allocator must allow. The block is one inlined flow (input loads up front, the
+// vegetation results in registers): Float64 wants ~116 registers to be spill free; measured per 10 M vegetated columns with
+// 8 / 6 / 5 / 4 blocks: 4.92 / 4.85 / 4.84 / 4.97 ms per step (bare ground 4.01 / - / 4.08 / 4.18), Float32 2.44 (8) / 2.51 (4);
+// the out-of-line form of round 1 (results handed over through global memory, 328-byte stack frame): 5.22 / 4.07 / 2.65 ms
 #ifndef TRM_SURFACE_BLOCKS
-#define TRM_SURFACE_BLOCKS 8   // resident blocks of 128 threads the register allocator must allow (64 registers: measured 4 blocks
-                               // 2.19 ms, 8 blocks 1.60 ms per 10 M vegetated columns -- the block is a long FP64 dependency chain)
+#define TRM_SURFACE_BLOCKS 0
 #endif
+template <class NF> constexpr int surface_blocks() { return TRM_SURFACE_BLOCKS ? TRM_SURFACE_BLOCKS : (sizeof(NF) == 8 ? 6 : 8); }
 template <class NF, bool FAST>
-__global__ void __launch_bounds__(128, TRM_SURFACE_BLOCKS) surface_kernel(const __grid_constant__ StageArgs<NF> A) {
+__global__ void __launch_bounds__(128, (surface_blocks<NF>())) surface_kernel(const __grid_constant__ StageArgs<NF> A) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= A.ncol) return;
     const DevParams<NF>& p = A.p;
@@ -416,7 +439,13 @@ __global__ void __launch_bounds__(128, TRM_SURFACE_BLOCKS) surface_kernel(const 
     const NF K_top = cell_conductivity<NF, FAST>(p, sat_top, liq_top);   // Kf[Nz] = Kc[Nz], soil_hydrology.jl:249-276
     const NF dz_top = A.metrics[MET_DZC * MET_STRIDE + nz];
     NF G, inf;
+#ifdef TRM_SURFACE_OUTLINE
     land_surface<NF, FAST>(A, c, A.richards != 0, T_top, sat_top, liq_top, K_top, dz_top, has_veg(A) ? A.xbeta[c] : NF(0), A.mode == MODE_HEUN2, G, inf);
+#else
+    // one inlined flow: every input load can be issued before the first dependent instruction, the results of the vegetation
+    // block stay in registers, no stack frame
+    land_surface_impl<NF, FAST, true>(A, c, A.richards != 0, T_top, sat_top, liq_top, K_top, dz_top, has_veg(A) ? A.xbeta[c] : NF(0), A.mode == MODE_HEUN2, G, inf);
+#endif
 }
 
 // soil moisture limiting factor from the stored saturation / liquid fraction (first step after initialize or after the
