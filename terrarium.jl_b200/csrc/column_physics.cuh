@@ -400,6 +400,10 @@ __device__ __forceinline__ float pow4(float x) { double d = (double)x; double d2
 // saturation vapour pressure (August-Roche-Magnus), physics_utils.jl:54-73
 template <class NF, bool FAST = false>
 __device__ __forceinline__ NF saturation_vapor_pressure(NF T) {
+    if (FAST) {   // the same two formulas with the constants selected first: one division and one exponential per call
+        const NF a = T <= 0 ? NF(22.46) : NF(17.62), b = T <= 0 ? NF(272.62) : NF(243.12);
+        return NF(611.0) * xexp<NF, FAST>(dv<NF, FAST>(a * T, T + b));
+    }
     return T <= 0 ? NF(611.0) * xexp<NF, FAST>(dv<NF, FAST>(NF(22.46) * T, T + NF(272.62))) : NF(611.0) * xexp<NF, FAST>(dv<NF, FAST>(NF(17.62) * T, T + NF(243.12)));
 }
 

@@ -150,12 +150,15 @@ __device__ __forceinline__ bool has_veg(const StageArgs<NF>& A) {
 // `which`: 0 when t is the time the tendencies are evaluated at (t_x), 1 for the time of the base state (t_b, Flux BCs)
 template <class NF>
 __device__ __forceinline__ NF eval_input_inline(const InputDesc<NF>& s, int64_t c, NF t, int which = 0) {
-    switch (s.kind) {
-        case TRM_SRC_CONST: return s.cval;
-        case TRM_SRC_FIELD: return s.a[c];
-        // host-evaluated function of time: the launcher points `a` at the values of the time the tendencies are evaluated
-        // at (t_x) and `b` at those of the base state's time (t_b)
-        case TRM_SRC_FIELD_PAIR: return which == 0 ? s.a[c] : s.b[c];
+    // (an if-chain on the launch-uniform kind, cheapest kinds first: the jump table of a `switch` costs an indirect branch
+    //  per input, and the surface block evaluates a dozen inputs per column)
+    const int kind = s.kind;
+    if (kind == TRM_SRC_CONST) return s.cval;
+    if (kind == TRM_SRC_FIELD) return s.a[c];
+    // host-evaluated function of time: the launcher points `a` at the values of the time the tendencies are evaluated
+    // at (t_x) and `b` at those of the base state's time (t_b)
+    if (kind == TRM_SRC_FIELD_PAIR) return which == 0 ? s.a[c] : s.b[c];
+    switch (kind) {
         case TRM_SRC_SINUSOID: {
             // `2pi * t / period - lon` is Float64 arithmetic in Julia whatever NF is
             // (examples/simulations/soil_heat_global.jl:79-88); rounded when stored in the NF field.
@@ -258,8 +261,8 @@ __device__ __forceinline__ void vegetation_surface_impl(const StageArgs<NF>& A, 
     const NF vpd_air = jmax(saturation_vapor_pressure<NF, FAST>(Ta) - ea, NF(0.1));
     const NF fapar = 1 - xexp<NF, FAST>(-v.k_ext * LAI);   // also the absorbed fraction of PAR (photosynthesis.jl:124-128)
     const NF g0 = (v.g_min / 1000) * fapar * beta_sm;
-    const NF gw = g0 + dv<NF, FAST>(NF(1.6) * (1 + dv<NF, FAST>(v.g1, tsqrt(vpd_air))) * An_prev, co2) * NF(1.0e6);
-    const NF lamc = NF(1.0) - dv<NF, FAST>(NF(1.0), NF(1.0) + dv<NF, FAST>(v.g1, tsqrt(vpd_air * NF(1.0e-3))));
+    const NF gw = g0 + dv<NF, FAST>(NF(1.6) * (1 + dv<NF, FAST>(v.g1, M<NF, FAST>::sqrt_(vpd_air))) * An_prev, co2) * NF(1.0e6);
+    const NF lamc = NF(1.0) - dv<NF, FAST>(NF(1.0), NF(1.0) + dv<NF, FAST>(v.g1, M<NF, FAST>::sqrt_(vpd_air * NF(1.0e-3))));
     // LUEPhotosynthesis (photosynthesis.jl:284-344)
     NF Rd, An;
     photosynthesis<NF, FAST>(v, Ta, SWd, pres, co2, LAI, fapar, lamc, beta_sm, Rd, An);
@@ -390,10 +393,13 @@ __device__ __forceinline__ void land_surface_impl(const StageArgs<NF>& A, int64_
     // surface energy balance kernel, executed twice (land_model.jl:85-86) ; the latent heat flux follows the humidity
     // flux of the evapotranspiration scheme (turbulent_fluxes.jl:137-150)
     NF swu, lwu, rnet, hs, hl, G;
+    // Each call of the fused SEB kernel is: fluxes(Ts) -> Ts = Tg - G dz / (2 kappa_s) -> fluxes(Ts). The first evaluation of
+    // the second call sees exactly the inputs of the last evaluation of the first call and reproduces its results bit for
+    // bit, so it is not repeated: three flux evaluations instead of four.
+    seb_fluxes<NF, FAST>(p, a, prescribed ? a.Tskin_in : Ts, Qh, swu, lwu, rnet, hs, hl, G);
+    if (!prescribed) {
 #pragma unroll 1
-    for (int rep = 0; rep < 2; ++rep) {
-        seb_fluxes<NF, FAST>(p, a, prescribed ? a.Tskin_in : Ts, Qh, swu, lwu, rnet, hs, hl, G);
-        if (!prescribed) {
+        for (int rep = 0; rep < 2; ++rep) {
             Ts = T_top - dv<NF, FAST>(G * dz_top, 2 * p.kappa_skin);   // ImplicitSkinTemperature, skin_temperature.jl:62-68,138-150
             seb_fluxes<NF, FAST>(p, a, Ts, Qh, swu, lwu, rnet, hs, hl, G);
         }

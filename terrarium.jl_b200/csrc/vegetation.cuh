@@ -82,7 +82,7 @@ __device__ __forceinline__ void photosynthesis(const VegParams<NF>& v, NF T_air,
     Rd = v.alpha_C3 * Vc_max * beta_sm;
     const NF JE = c_1 * APAR, JC = c_2 * Vc_max;
     const NF sJ = JE + JC;
-    const NF Ag = dv<NF, FAST>(sJ - tsqrt(sJ * sJ - NF(4) * v.theta_r * JE * JC), NF(2) * v.theta_r) * beta_sm;
+    const NF Ag = dv<NF, FAST>(sJ - M<NF, FAST>::sqrt_(sJ * sJ - NF(4) * v.theta_r * JE * JC), NF(2) * v.theta_r) * beta_sm;
     An = Ag - Rd;
 }
 
