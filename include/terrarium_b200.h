@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TRM_ABI_VERSION 3
+#define TRM_ABI_VERSION 4
 #define TRM_MAX_NZ 128       /* per-column layers supported by the fused kernels            */
 #define TRM_NUM_USER_INPUTS 8
 
@@ -82,6 +82,15 @@ enum trm_vegetation  { TRM_VEG_NONE = 0, TRM_VEG_CARBON = 1 };
  * ConstantEvaporationResistanceFactor (params.evap_beta, :6-11) or SoilMoistureResistanceFactor (Lee & Pielke 1992, :32-57:
  * (1 - cos(pi theta_w / theta_fc))^2 / 4 below field capacity, 1 above; theta_w of the top soil layer). */
 enum trm_ground_resistance { TRM_GROUND_RES_CONSTANT = 0, TRM_GROUND_RES_SOIL_MOISTURE = 1 };
+/* Schemes of the surface energy balance (src/processes/surface_energy/): ConstantAlbedo (params.albedo / emissivity) or
+ * PrescribedAlbedo (inputs TRM_IN_ALBEDO / TRM_IN_EMISSIVITY, albedo.jl:7-44); DiagnosedRadiativeFluxes (radiative_fluxes.jl:
+ * 72-209) or PrescribedRadiativeFluxes (outgoing short / longwave radiation are inputs, :13-67); DiagnosedTurbulentFluxes
+ * (turbulent_fluxes.jl:20-150) or PrescribedTurbulentFluxes (sensible / latent heat flux are inputs, :9-16). With a prescribed
+ * scheme the fields of the same name hold the input values; net radiation and ground heat flux are still diagnosed
+ * (R_net = SW_up - SW_down + LW_up - LW_down, G = R_net - H_s - H_l). */
+enum trm_albedo_kind    { TRM_ALBEDO_CONSTANT = 0, TRM_ALBEDO_PRESCRIBED = 1 };
+enum trm_radiative_kind { TRM_RADIATIVE_DIAGNOSED = 0, TRM_RADIATIVE_PRESCRIBED = 1 };
+enum trm_turbulent_kind { TRM_TURBULENT_DIAGNOSED = 0, TRM_TURBULENT_PRESCRIBED = 1 };
 /* Arithmetic contract of the CUDA kernels.
  *  FAITHFUL: same operations in the same order as the reference/oracle (true divisions,
  *            pow where the reference calls ^), no FMA contraction.
@@ -121,7 +130,14 @@ enum trm_input_id {
     TRM_IN_SKIN_TEMPERATURE = 18, /* only read with TRM_SKIN_PRESCRIBED */
     TRM_IN_SAI = 19,                    /* stem area index, canopy_interception.jl:54 (no default: 0)          */
     TRM_IN_DAILY_LEAF_RESPIRATION = 20, /* autotrophic_respiration.jl:33 (no default: 0)                       */
-    TRM_IN_COUNT = 21
+    /* prescribed variants of the surface energy balance (read only when the corresponding scheme is selected) */
+    TRM_IN_ALBEDO = 21,                 /* PrescribedAlbedo, src/processes/surface_energy/albedo.jl:7-14        */
+    TRM_IN_EMISSIVITY = 22,
+    TRM_IN_SHORTWAVE_UP = 23,           /* PrescribedRadiativeFluxes, radiative_fluxes.jl:13-23                 */
+    TRM_IN_LONGWAVE_UP = 24,
+    TRM_IN_SENSIBLE_HEAT_FLUX = 25,     /* PrescribedTurbulentFluxes, turbulent_fluxes.jl:9-16                  */
+    TRM_IN_LATENT_HEAT_FLUX = 26,
+    TRM_IN_COUNT = 27
 };
 /* How an input is produced at clock time t (device resident, evaluated inside the stage kernel). */
 enum trm_source {
@@ -278,6 +294,10 @@ typedef struct trm_config {
     int32_t math;             /* trm_math */
     int32_t vegetation;       /* trm_vegetation (LandModel only) */
     int32_t ground_resistance;/* trm_ground_resistance (LandModel only) */
+    int32_t albedo_kind;      /* trm_albedo_kind (LandModel only) */
+    int32_t radiative;        /* trm_radiative_kind (LandModel only) */
+    int32_t turbulent;        /* trm_turbulent_kind (LandModel only) */
+    int32_t reserved0;        /* must be 0 */
     const double* z_faces;    /* nz+1 face elevations, bottom .. 0 (column_grid.jl:30-31); copied */
     trm_params params;
     trm_bc bc[TRM_BC_NSLOTS];

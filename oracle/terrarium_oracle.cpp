@@ -436,9 +436,17 @@ struct Oracle {
     inline void seb_fluxes(State<NF>& s, int64_t c) const {
         NF SWd = s.in[TRM_IN_SHORTWAVE_DOWN][c], LWd = s.in[TRM_IN_LONGWAVE_DOWN][c];
         NF Tsurf = cfg.skin == TRM_SKIN_PRESCRIBED ? s.in[TRM_IN_SKIN_TEMPERATURE][c] : s.Ts[c];
-        NF swu = albedo * SWd;                                   // radiative_fluxes.jl:85-88
-        NF TK = Tsurf + Tref;
-        NF lwu = emis * sigma * jl_pow4(TK) + (1 - emis) * LWd;  // radiative_fluxes.jl:95-100, physical_constants.jl:67
+        // albedo / emissivity: ConstantAlbedo parameters or the PrescribedAlbedo inputs (albedo.jl:7-44, abstract_types.jl:120-131)
+        const bool alb_in = cfg.albedo_kind == TRM_ALBEDO_PRESCRIBED;
+        NF alb = alb_in ? s.in[TRM_IN_ALBEDO][c] : albedo, emi = alb_in ? s.in[TRM_IN_EMISSIVITY][c] : emis;
+        NF swu, lwu;
+        if (cfg.radiative == TRM_RADIATIVE_PRESCRIBED) {        // radiative_fluxes.jl:46-50
+            swu = s.in[TRM_IN_SHORTWAVE_UP][c]; lwu = s.in[TRM_IN_LONGWAVE_UP][c];
+        } else {
+            swu = alb * SWd;                                     // radiative_fluxes.jl:85-88
+            NF TK = Tsurf + Tref;
+            lwu = emi * sigma * jl_pow4(TK) + (1 - emi) * LWd;   // radiative_fluxes.jl:95-100, physical_constants.jl:67
+        }
         s.SWup[c] = swu; s.LWup[c] = lwu;
         NF rnet = swu - SWd + lwu - LWd;                         // radiative_fluxes.jl:196-209
         s.Rnet[c] = rnet;
@@ -448,6 +456,7 @@ struct Oracle {
         // turbulent_fluxes.jl:137-150 (coupled to ET): surface_humidity_flux = E_gnd (+ E_can + T_can, canopy_evapotranspiration.jl:75-80)
         NF Qh = veg ? s.Egnd[c] + s.Ecan[c] + s.transp[c] : s.Egnd[c];
         NF hl = Llg * rho_a * Qh;
+        if (cfg.turbulent == TRM_TURBULENT_PRESCRIBED) { hs = s.in[TRM_IN_SENSIBLE_HEAT_FLUX][c]; hl = s.in[TRM_IN_LATENT_HEAT_FLUX][c]; }   // turbulent_fluxes.jl:9-16
         s.Hs[c] = hs; s.Hl[c] = hl;
         s.G[c] = rnet - hs - hl;                                  // skin_temperature.jl:76-80
     }
@@ -992,6 +1001,8 @@ int set_raster(Oracle<NF>* o, int id, int nt, const double* times, const void* v
 template <class NF>
 int set_infield(Oracle<NF>* o, int id, const void* v) {
     o->src[id].kind = TRM_SRC_FIELD; o->src_field[id].assign((const NF*)v, (const NF*)v + o->nc);
+    // set!(state.inputs.<name>, values) writes the input Field itself: a following compute_auxiliary! sees it without update_inputs!
+    if ((int64_t)o->st.in[id].size() == o->nc) o->st.in[id] = o->src_field[id];
     return TRM_OK;
 }
 
@@ -1054,7 +1065,8 @@ int orc_set_field(trm_handle* h, int id, const void* host, int64_t count) { retu
 int orc_get_field(trm_handle* h, int id, void* host, int64_t count) { return DISPATCH((Handle*)h, get_field(id, host, count)); }
 int orc_set_input_const(trm_handle* h_, int id, double v) {
     Handle* h = (Handle*)h_; if (id < 0 || id >= TRM_IN_COUNT) return fail(TRM_ERR_INVALID, "bad input id");
-    if (h->dtype == TRM_F32) { h->f32->src[id].kind = TRM_SRC_CONST; h->f32->src[id].cval = v; } else { h->f64->src[id].kind = TRM_SRC_CONST; h->f64->src[id].cval = v; }
+    if (h->dtype == TRM_F32) { h->f32->src[id].kind = TRM_SRC_CONST; h->f32->src[id].cval = v; std::fill(h->f32->st.in[id].begin(), h->f32->st.in[id].end(), (float)v); }
+    else { h->f64->src[id].kind = TRM_SRC_CONST; h->f64->src[id].cval = v; std::fill(h->f64->st.in[id].begin(), h->f64->st.in[id].end(), v); }
     return TRM_OK;
 }
 int orc_set_input_field(trm_handle* h_, int id, const void* v) {

@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-TRM_ABI_VERSION = 3
+TRM_ABI_VERSION = 4
 TRM_MAX_NZ = 128
 TRM_NUM_USER_INPUTS = 8
 
@@ -37,7 +37,8 @@ TRM_IN_USER0 = 0
 (TRM_IN_AIR_TEMPERATURE, TRM_IN_AIR_PRESSURE, TRM_IN_WINDSPEED, TRM_IN_SPECIFIC_HUMIDITY, TRM_IN_RAINFALL,
  TRM_IN_SNOWFALL, TRM_IN_SHORTWAVE_DOWN, TRM_IN_LONGWAVE_DOWN, TRM_IN_DAYTIME_LENGTH, TRM_IN_CO2,
  TRM_IN_SKIN_TEMPERATURE, TRM_IN_SAI, TRM_IN_DAILY_LEAF_RESPIRATION) = range(8, 21)
-TRM_IN_COUNT = 21
+TRM_IN_ALBEDO, TRM_IN_EMISSIVITY, TRM_IN_SHORTWAVE_UP, TRM_IN_LONGWAVE_UP, TRM_IN_SENSIBLE_HEAT_FLUX, TRM_IN_LATENT_HEAT_FLUX = 21, 22, 23, 24, 25, 26
+TRM_IN_COUNT = 27
 TRM_SRC_CONST, TRM_SRC_FIELD, TRM_SRC_SINUSOID, TRM_SRC_TABLE, TRM_SRC_RASTER = 0, 1, 2, 3, 4
 
 FIELD_IDS = {
@@ -65,7 +66,14 @@ INPUT_IDS = {
     "surface_shortwave_down": TRM_IN_SHORTWAVE_DOWN, "surface_longwave_down": TRM_IN_LONGWAVE_DOWN,
     "daytime_length": TRM_IN_DAYTIME_LENGTH, "CO2": TRM_IN_CO2, "skin_temperature": TRM_IN_SKIN_TEMPERATURE,
     "SAI": TRM_IN_SAI, "daily_leaf_respiration": TRM_IN_DAILY_LEAF_RESPIRATION,
+    "albedo": TRM_IN_ALBEDO, "emissivity": TRM_IN_EMISSIVITY,
 }
+# inputs of the prescribed flux schemes: they share their names with the fields the diagnosed schemes write
+PRESCRIBED_FLUX_INPUTS = {"surface_shortwave_up": TRM_IN_SHORTWAVE_UP, "surface_longwave_up": TRM_IN_LONGWAVE_UP,
+                          "sensible_heat_flux": TRM_IN_SENSIBLE_HEAT_FLUX, "latent_heat_flux": TRM_IN_LATENT_HEAT_FLUX}
+TRM_ALBEDO_CONSTANT, TRM_ALBEDO_PRESCRIBED = 0, 1
+TRM_RADIATIVE_DIAGNOSED, TRM_RADIATIVE_PRESCRIBED = 0, 1
+TRM_TURBULENT_DIAGNOSED, TRM_TURBULENT_PRESCRIBED = 0, 1
 
 
 # vegetated LandModel parameters, in header order
@@ -103,6 +111,7 @@ class trm_config(C.Structure):
         ("nz", C.c_int32), ("device", C.c_int32), ("model", C.c_int32), ("timestepper", C.c_int32),
         ("hydrology", C.c_int32), ("swrc", C.c_int32), ("unsat_k", C.c_int32), ("sat_halo", C.c_int32),
         ("skin", C.c_int32), ("math", C.c_int32), ("vegetation", C.c_int32), ("ground_resistance", C.c_int32),
+        ("albedo_kind", C.c_int32), ("radiative", C.c_int32), ("turbulent", C.c_int32), ("reserved0", C.c_int32),
         ("z_faces", C.POINTER(C.c_double)),
         ("params", trm_params),
         ("bc", trm_bc * TRM_BC_NSLOTS),

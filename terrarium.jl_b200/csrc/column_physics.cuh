@@ -27,6 +27,7 @@ struct DevParams {
     NF rpor, neg_inv_alpha, vg_k_exp1, vg_k_exp2, vg_inv_m_neg, vg_inv_n, r_thspan, se_off;
     NF hc_wi, hc_ia, hc_base, sqk_wi, sqk_ia, sqk_base;   // regrouped constituent sums (see energy_to_temperature)
     int32_t swrc, unsat_k, sat_halo, skin, ground_res;
+    int32_t albedo_kind, rad_kind, turb_kind;   // trm_albedo_kind / trm_radiative_kind / trm_turbulent_kind
     NF th_fc;                  // field capacity (ground evaporation resistance, plant available water)
     int32_t vg_n_is_2;
 };

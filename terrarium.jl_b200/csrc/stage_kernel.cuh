@@ -218,6 +218,8 @@ __device__ __forceinline__ NF halo_value(int kind, NF edge, NF v, NF D, bool top
 template <class NF>
 struct Surface {
     NF SWd, LWd, Ta, pres, q, V, rain, Tskin_in;
+    NF alb, emi;                     // ConstantAlbedo parameters or the PrescribedAlbedo inputs (albedo.jl:7-44)
+    NF swu_in, lwu_in, hs_in, hl_in; // inputs of PrescribedRadiativeFluxes / PrescribedTurbulentFluxes
     double ra;
 };
 
@@ -226,12 +228,20 @@ struct Surface {
 template <class NF, bool FAST>
 __device__ __forceinline__ void seb_fluxes(const DevParams<NF>& p, const Surface<NF>& a, NF Tsurf, NF Egnd,
                                            NF& swu, NF& lwu, NF& rnet, NF& hs, NF& hl, NF& G) {
-    swu = p.albedo * a.SWd;
-    NF TK = Tsurf + p.Tref;
-    lwu = p.emis * p.sigma * pow4(TK) + (1 - p.emis) * a.LWd;
+    if (p.rad_kind == TRM_RADIATIVE_PRESCRIBED) {   // radiative_fluxes.jl:46-50
+        swu = a.swu_in; lwu = a.lwu_in;
+    } else {
+        swu = a.alb * a.SWd;
+        NF TK = Tsurf + p.Tref;
+        lwu = a.emi * p.sigma * pow4(TK) + (1 - a.emi) * a.LWd;
+    }
     rnet = swu - a.SWd + lwu - a.LWd;
-    hs = (NF)((double)(p.c_a * p.rho_a) * dv<double, FAST>((double)(Tsurf - a.Ta), a.ra));
-    hl = p.Llg * p.rho_a * Egnd;
+    if (p.turb_kind == TRM_TURBULENT_PRESCRIBED) {  // turbulent_fluxes.jl:9-16
+        hs = a.hs_in; hl = a.hl_in;
+    } else {
+        hs = (NF)((double)(p.c_a * p.rho_a) * dv<double, FAST>((double)(Tsurf - a.Ta), a.ra));
+        hl = p.Llg * p.rho_a * Egnd;
+    }
     G = rnet - hs - hl;
 }
 
@@ -354,6 +364,11 @@ __device__ __forceinline__ void land_surface_impl(const StageArgs<NF>& A, int64_
     a.rain = surface_input(A.in[TRM_IN_RAINFALL], c, A.t_x);
     const bool prescribed = p.skin == TRM_SKIN_PRESCRIBED;
     a.Tskin_in = prescribed ? surface_input(A.in[TRM_IN_SKIN_TEMPERATURE], c, A.t_x) : NF(0);
+    a.alb = p.albedo; a.emi = p.emis;
+    if (p.albedo_kind == TRM_ALBEDO_PRESCRIBED) { a.alb = surface_input(A.in[TRM_IN_ALBEDO], c, A.t_x); a.emi = surface_input(A.in[TRM_IN_EMISSIVITY], c, A.t_x); }
+    a.swu_in = a.lwu_in = a.hs_in = a.hl_in = NF(0);
+    if (p.rad_kind == TRM_RADIATIVE_PRESCRIBED) { a.swu_in = surface_input(A.in[TRM_IN_SHORTWAVE_UP], c, A.t_x); a.lwu_in = surface_input(A.in[TRM_IN_LONGWAVE_UP], c, A.t_x); }
+    if (p.turb_kind == TRM_TURBULENT_PRESCRIBED) { a.hs_in = surface_input(A.in[TRM_IN_SENSIBLE_HEAT_FLUX], c, A.t_x); a.hl_in = surface_input(A.in[TRM_IN_LATENT_HEAT_FLUX], c, A.t_x); }
     // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
     NF Vc = jmax(a.V, p.Vmin);
     double Va = fmax((double)Vc, 1.0e-6);

@@ -239,6 +239,8 @@ struct Handle : HandleBase {
         p.swrc = c.swrc; p.unsat_k = c.unsat_k; p.sat_halo = c.sat_halo; p.skin = c.skin;
         if (c.ground_resistance != TRM_GROUND_RES_CONSTANT && c.ground_resistance != TRM_GROUND_RES_SOIL_MOISTURE) return fail(TRM_ERR_INVALID, "bad ground_resistance code");
         p.ground_res = c.ground_resistance; p.th_fc = (NF)q.field_capacity;
+        if ((c.albedo_kind | c.radiative | c.turbulent) & ~1 || c.reserved0 != 0) return fail(TRM_ERR_INVALID, "bad albedo_kind / radiative / turbulent code (or reserved0 != 0)");
+        p.albedo_kind = c.albedo_kind; p.rad_kind = c.radiative; p.turb_kind = c.turbulent;
         p.vg_n_is_2 = (p.vg_n == NF(2)) ? 1 : 0;
         vp.th_fc = (NF)q.field_capacity; vp.th_wp = (NF)q.wilting_point; vp.C_mass = (NF)q.C_mass;
         vp.tau25 = (NF)q.tau25; vp.Kc25 = (NF)q.Kc25; vp.Ko25 = (NF)q.Ko25; vp.q10_tau = (NF)q.q10_tau; vp.q10_Kc = (NF)q.q10_Kc; vp.q10_Ko = (NF)q.q10_Ko;

@@ -114,13 +114,14 @@ class StateVariables:
     def __getattr__(self, name):
         if name == "inputs":   # state.inputs.<name> (state_variables.jl:38-41)
             return _Inputs(self._i)
+        if name in abi.PRESCRIBED_FLUX_INPUTS and self._i._prescribed_flux_input(name):
+            return InputField(self._i, abi.PRESCRIBED_FLUX_INPUTS[name])   # an input variable under the prescribed scheme
         if name in abi.FIELD_IDS:
             return Field(self._i, name)
-        if name in self._i._bc_inputs:
-            return InputField(self._i, self._i._bc_inputs[name])
-        if name in abi.INPUT_IDS:
-            return InputField(self._i, abi.INPUT_IDS[name])
-        raise AttributeError(name)
+        try:
+            return InputField(self._i, self._i._input_id(name))
+        except KeyError:
+            raise AttributeError(name) from None
 
 
 class _Inputs:
@@ -128,11 +129,10 @@ class _Inputs:
         self._i = integ
 
     def __getattr__(self, name):
-        if name in self._i._bc_inputs:
-            return InputField(self._i, self._i._bc_inputs[name])
-        if name in abi.INPUT_IDS:
-            return InputField(self._i, abi.INPUT_IDS[name])
-        raise AttributeError(name)
+        try:
+            return InputField(self._i, self._i._input_id(name))
+        except KeyError:
+            raise AttributeError(name) from None
 
 
 class InputField:
@@ -204,13 +204,28 @@ class ModelIntegrator:
             if name in self._bc_inputs:       # a boundary condition input, e.g. PrescribedSurfaceTemperature("Tair")
                 self._set_input(self._bc_inputs[name], value)
                 continue
-            if name not in abi.INPUT_IDS:
-                raise KeyError(f"unknown input variable {name!r}")
-            self._set_input(abi.INPUT_IDS[name], value)
+            self._set_input(self._input_id(name), value)
         self.state = StateVariables(self)
         self.clock = self.state.clock
         self.initializers = dict(initializers or {})
         self.initialize_state()
+
+    def _input_id(self, name: str) -> int:
+        """Input slot of a named input variable. With a prescribed flux scheme (PrescribedRadiativeFluxes /
+        PrescribedTurbulentFluxes) the fluxes are INPUT variables that carry the names the diagnosed schemes give their
+        auxiliary fields (radiative_fluxes.jl:19-23, turbulent_fluxes.jl:13-16)."""
+        if name in self._bc_inputs:
+            return self._bc_inputs[name]
+        if name in abi.INPUT_IDS:
+            return abi.INPUT_IDS[name]
+        if name in abi.PRESCRIBED_FLUX_INPUTS and self._prescribed_flux_input(name):
+            return abi.PRESCRIBED_FLUX_INPUTS[name]
+        raise KeyError(f"unknown input variable {name!r}")
+
+    def _prescribed_flux_input(self, name: str) -> bool:
+        cfg = self._cfg
+        radiative = name in ("surface_shortwave_up", "surface_longwave_up")
+        return bool(cfg.radiative if radiative else cfg.turbulent) and cfg.model == abi.TRM_MODEL_LAND
 
     # ------------------------------------------------------------------------------------------
     def initialize_state(self):

@@ -4,7 +4,7 @@
 # STATUS: UNTESTED SOURCE.  Neither `julia` nor Terrarium's dependencies exist in the build image or
 # on the GPU boxes, so this file has never been executed; the tested caller of the same C ABI is
 # the Python ctypes mirror (terrarium.jl_b200/integrator.py).  The struct layouts below must match
-# include/terrarium_b200.h field for field (TRM_ABI_VERSION = 3).
+# include/terrarium_b200.h field for field (TRM_ABI_VERSION = 4).
 #
 # What it replaces in the reference (paths relative to the Terrarium.jl root):
 #   initialize(model, timestepper, inputs...)            src/timesteppers/model_integrator.jl:145-161
@@ -21,7 +21,7 @@ import FreezeCurves: VanGenuchten, BrooksCorey
 
 const LIB = get(ENV, "TERRARIUM_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libterrarium_b200.so"))
 
-const TRM_ABI_VERSION = Int32(3)
+const TRM_ABI_VERSION = Int32(4)
 const TRM_BC_NSLOTS = 8
 @enum FieldId::Cint internal_energy=0 temperature=1 liquid_water_fraction=2 saturation_water_ice=3 pressure_head=4 hydraulic_conductivity=5 surface_excess_water=6 water_table=7 ground_temperature=8 skin_temperature=9 ground_heat_flux=10 surface_shortwave_up=11 surface_longwave_up=12 surface_net_radiation=13 sensible_heat_flux=14 latent_heat_flux=15 evaporation_ground=16 infiltration=17 surface_runoff=18 carbon_vegetation=21 vegetation_area_fraction=22 canopy_water=23 balanced_leaf_area_index=24 leaf_area_index=25 phenology_factor=26 canopy_water_conductance=27 leaf_to_air_co2_ratio=28 net_assimilation=29 leaf_respiration=30 gross_primary_production=31 autotrophic_respiration=32 net_primary_production=33 soil_moisture_limiting_factor=34 canopy_water_interception=35 canopy_water_removal=36 saturation_canopy_water=37 rainfall_ground=38 evaporation_canopy=39 transpiration=40 plant_available_water=41 root_fraction=42
 
@@ -41,6 +41,10 @@ struct TrmConfig                      # trm_config
     model::Int32; timestepper::Int32; hydrology::Int32; swrc::Int32; unsat_k::Int32; sat_halo::Int32; skin::Int32; math::Int32
     vegetation::Int32                 # trm_vegetation: 0 = nothing (bare ground), 1 = VegetationCarbon
     ground_resistance::Int32          # trm_ground_resistance: 0 = constant factor, 1 = SoilMoistureResistanceFactor
+    albedo_kind::Int32                # 0 = ConstantAlbedo, 1 = PrescribedAlbedo (inputs :albedo, :emissivity)
+    radiative::Int32                  # 0 = DiagnosedRadiativeFluxes, 1 = PrescribedRadiativeFluxes
+    turbulent::Int32                  # 0 = DiagnosedTurbulentFluxes, 1 = PrescribedTurbulentFluxes
+    reserved0::Int32
     z_faces::Ptr{Cdouble}
     params::TrmParams
     bc::NTuple{TRM_BC_NSLOTS, TrmBC}
@@ -97,7 +101,7 @@ function params_of(model)
         c.ρw, c.Lsl, c.Llg, c.ρₐ, c.cₐ, c.Tref, c.σ, c.ε,
         hp.sat_hydraulic_cond, ustrip(vg.α), vg.n, ustrip(bc.ψₛ), bc.λ, swrc_theta_res(hp.swrc),
         hp.unsat_hydraulic_cond isa UnsatKVanGenuchten ? hp.unsat_hydraulic_cond.impedance : 7.0, vwc_forcing_value(soil.hydrology.vwc_forcing),
-        land ? seb.albedo.albedo : 0.3, land ? seb.albedo.emissivity : 0.97, land ? seb.skin_temperature.κₛ : 2.0,
+        (land && seb.albedo isa Terrarium.ConstantAlbedo) ? seb.albedo.albedo : 0.3, (land && seb.albedo isa Terrarium.ConstantAlbedo) ? seb.albedo.emissivity : 0.97, land ? seb.skin_temperature.κₛ : 2.0,
         land ? model.atmosphere.aerodynamics.C_h : 1.2e-3, land ? model.atmosphere.min_windspeed : 0.01,
         land ? model.surface_hydrology.surface_runoff.τ_r : 3600.0, 1.0,
         vegetation_params(model, hp, c))
@@ -141,6 +145,9 @@ function initialize_b200(model::Union{SoilModel{NF}, LandModel{NF}}, timestepper
         hyd.hydraulic_properties.swrc isa VanGenuchten ? 0 : 1, hyd.hydraulic_properties.unsat_hydraulic_cond isa UnsatKVanGenuchten ? 1 : 0,
         0, 0, math === :fast ? 1 : 0, (model isa LandModel && !isnothing(model.vegetation)) ? 1 : 0,
         (model isa LandModel && model.surface_hydrology.evapotranspiration.ground_resistance isa Terrarium.SoilMoistureResistanceFactor) ? 1 : 0,
+        (model isa LandModel && model.surface_energy_balance.albedo isa Terrarium.PrescribedAlbedo) ? 1 : 0,
+        (model isa LandModel && model.surface_energy_balance.radiative_fluxes isa Terrarium.PrescribedRadiativeFluxes) ? 1 : 0,
+        (model isa LandModel && model.surface_energy_balance.turbulent_fluxes isa Terrarium.PrescribedTurbulentFluxes) ? 1 : 0, 0,
         pointer(zf), params_of(model), bcs))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve zf check(ccall((:trm_create, LIB), Cint, (Ref{TrmConfig}, Ref{Ptr{Cvoid}}), cfg, h), "create")
@@ -290,7 +297,10 @@ end
 # ---- inputs / forcing -----------------------------------------------------------------------------------------------
 const INPUT_ID = Dict(:air_temperature => 8, :air_pressure => 9, :windspeed => 10, :specific_humidity => 11, :rainfall => 12,
                       :snowfall => 13, :surface_shortwave_down => 14, :surface_longwave_down => 15, :daytime_length => 16,
-                      :CO2 => 17, :skin_temperature => 18, :SAI => 19, :daily_leaf_respiration => 20)
+                      :CO2 => 17, :skin_temperature => 18, :SAI => 19, :daily_leaf_respiration => 20,
+                      :albedo => 21, :emissivity => 22)
+# inputs of the prescribed flux schemes (they carry the names of the fields the diagnosed schemes write): set_input!(integ, PRESCRIBED_INPUT_ID[name], v)
+const PRESCRIBED_INPUT_ID = Dict(:surface_shortwave_up => 23, :surface_longwave_up => 24, :sensible_heat_flux => 25, :latent_heat_flux => 26)
 input_id(id::Integer) = Cint(id)
 input_id(name::Symbol) = Cint(INPUT_ID[name])
 

@@ -194,10 +194,32 @@ class PrescribedSkinTemperature:  # skin_temperature.jl:12-15
     kappa_s: float = 2.0
 
 
+class PrescribedAlbedo:  # albedo.jl:7-14: albedo and emissivity are the input variables `albedo` / `emissivity`
+    pass
+
+
+class DiagnosedRadiativeFluxes:  # radiative_fluxes.jl:72-76
+    pass
+
+
+class PrescribedRadiativeFluxes:  # radiative_fluxes.jl:13-23: inputs `surface_shortwave_up` / `surface_longwave_up`
+    pass
+
+
+class DiagnosedTurbulentFluxes:  # turbulent_fluxes.jl:20-28
+    pass
+
+
+class PrescribedTurbulentFluxes:  # turbulent_fluxes.jl:9-16: inputs `sensible_heat_flux` / `latent_heat_flux`
+    pass
+
+
 @dataclass
-class SurfaceEnergyBalance:  # surface_energy_balance.jl:9-38 (diagnosed radiative + turbulent fluxes)
+class SurfaceEnergyBalance:  # surface_energy_balance.jl:9-38
     skin_temperature: Any = field(default_factory=ImplicitSkinTemperature)
-    albedo: ConstantAlbedo = field(default_factory=ConstantAlbedo)
+    albedo: Any = field(default_factory=ConstantAlbedo)
+    radiative_fluxes: Any = field(default_factory=DiagnosedRadiativeFluxes)
+    turbulent_fluxes: Any = field(default_factory=DiagnosedTurbulentFluxes)
 
 
 @dataclass
@@ -682,7 +704,8 @@ def build_params(model) -> abi.trm_params:
     p.albedo, p.emissivity, p.kappa_skin, p.C_h, p.min_windspeed, p.tau_r, p.evap_beta = 0.3, 0.97, 2.0, 1.2e-3, 0.01, 3600.0, 1.0
     if isinstance(model, LandModel):
         seb, sh, atm = model.surface_energy_balance, model.surface_hydrology, model.atmosphere
-        p.albedo, p.emissivity = seb.albedo.albedo, seb.albedo.emissivity
+        if isinstance(seb.albedo, ConstantAlbedo):   # (PrescribedAlbedo: per-column inputs instead)
+            p.albedo, p.emissivity = seb.albedo.albedo, seb.albedo.emissivity
         p.kappa_skin = seb.skin_temperature.kappa_s
         p.C_h, p.min_windspeed = atm.C_h, atm.min_windspeed
         p.tau_r = sh.surface_runoff.tau_r
@@ -745,6 +768,11 @@ def build_config(model, timestepper, ncol: int, col0: int = 0, device: int = 0, 
     if isinstance(model, LandModel) and isinstance(model.surface_hydrology.evapotranspiration.ground_resistance_factor, SoilMoistureResistanceFactor):
         cfg.ground_resistance = abi.TRM_GROUND_RES_SOIL_MOISTURE
     cfg.vegetation = abi.TRM_VEG_CARBON if isinstance(model, LandModel) and model.vegetation is not None else abi.TRM_VEG_NONE
+    if isinstance(model, LandModel):
+        seb = model.surface_energy_balance
+        cfg.albedo_kind = abi.TRM_ALBEDO_PRESCRIBED if isinstance(seb.albedo, PrescribedAlbedo) else abi.TRM_ALBEDO_CONSTANT
+        cfg.radiative = abi.TRM_RADIATIVE_PRESCRIBED if isinstance(seb.radiative_fluxes, PrescribedRadiativeFluxes) else abi.TRM_RADIATIVE_DIAGNOSED
+        cfg.turbulent = abi.TRM_TURBULENT_PRESCRIBED if isinstance(seb.turbulent_fluxes, PrescribedTurbulentFluxes) else abi.TRM_TURBULENT_DIAGNOSED
     zbuf = np.ascontiguousarray(grid.z_faces, dtype=np.float64)
     import ctypes as C
     cfg.z_faces = zbuf.ctypes.data_as(C.POINTER(C.c_double))

@@ -556,3 +556,86 @@ def test_volumetric_fractions(constituent, T0, expect):
     U = integ.state.internal_energy.numpy()[:, 0]
     latent = 1000.0 * 3.34e5 * sat * por if T0 < 0 else 0.0
     assert np.allclose((U + latent) / T0, expect, rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# prescribed schemes of the surface energy balance (albedo.jl:7-14, radiative_fluxes.jl:13-67, turbulent_fluxes.jl:9-16);
+# known answers of test/surface_energy/{albedo,radiative_fluxes,turbulent_fluxes}.jl
+# ---------------------------------------------------------------------------------------------
+def _prescribed_seb_case(engine, seb, inputs, n=3):
+    grid = column(trm.ExponentialSpacing(N=10), n=n)
+    land = trm.LandModel(grid, vegetation=None, surface_energy_balance=seb)
+    return make(engine, land, trm.ForwardEuler(dt=60.0), inputs,
+                initializers={"temperature": 0.0, "saturation_water_ice": 0.5, "skin_temperature": 0.0})
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_prescribed_radiative_fluxes(engine):
+    """test/surface_energy/radiative_fluxes.jl:4-19: R_net = 50 - 100 + 5 - 20 with all four fluxes given."""
+    seb = trm.SurfaceEnergyBalance(radiative_fluxes=trm.PrescribedRadiativeFluxes())
+    integ = _prescribed_seb_case(engine, seb, {"surface_shortwave_down": 100.0, "surface_longwave_down": 20.0,
+                                               "surface_shortwave_up": 50.0, "surface_longwave_up": 5.0})
+    integ.compute_auxiliary()
+    assert np.allclose(integ.state.surface_net_radiation.numpy(), 50.0 - 100.0 + 5.0 - 20.0, rtol=1e-14)
+    assert np.array_equal(integ.state.inputs.surface_shortwave_up.numpy(), np.full(3, 50.0))
+    # an input variable under this scheme: set!(state.surface_shortwave_up, ...) changes the flux (radiative_fluxes.jl:19-23)
+    integ.state.surface_shortwave_up.set(np.array([50.0, 60.0, 70.0]))
+    integ.compute_auxiliary()
+    assert np.allclose(integ.state.surface_net_radiation.numpy(), np.array([50.0, 60.0, 70.0]) - 100.0 + 5.0 - 20.0, rtol=1e-14)
+    # G = R_net - H_s - H_l still closes the budget (skin_temperature.jl:76-80)
+    s = integ.state
+    assert np.allclose(s.ground_heat_flux.numpy(), s.surface_net_radiation.numpy() - s.sensible_heat_flux.numpy() - s.latent_heat_flux.numpy(), rtol=1e-12)
+    with pytest.raises(KeyError):   # not an input under the diagnosed scheme
+        _prescribed_seb_case(engine, trm.SurfaceEnergyBalance(), {"surface_shortwave_up": 50.0})
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_prescribed_turbulent_fluxes(engine):
+    """test/surface_energy/turbulent_fluxes.jl:4-16: the sensible / latent heat fluxes are the inputs (10, 5)."""
+    seb = trm.SurfaceEnergyBalance(turbulent_fluxes=trm.PrescribedTurbulentFluxes())
+    integ = _prescribed_seb_case(engine, seb, {"sensible_heat_flux": 10.0, "latent_heat_flux": 5.0, "surface_shortwave_down": 100.0})
+    integ.compute_auxiliary()
+    s = integ.state
+    assert np.array_equal(s.inputs.sensible_heat_flux.numpy(), np.full(3, 10.0)) and np.array_equal(s.inputs.latent_heat_flux.numpy(), np.full(3, 5.0))
+    assert np.allclose(s.ground_heat_flux.numpy(), s.surface_net_radiation.numpy() - 15.0, rtol=1e-12)
+    integ.step(60.0, 5)
+    assert np.isfinite(s.temperature.numpy()).all()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_prescribed_albedo(engine):
+    """test/surface_energy/albedo.jl:14-25 (inputs albedo = 0.4, emissivity = 0.8) through the diagnosed radiative fluxes of
+    test/surface_energy/radiative_fluxes.jl:21-39: SW_up = albedo SW_down, LW_up = (1 - eps) LW_down + eps sigma (Ts + 273.15)^4."""
+    seb = trm.SurfaceEnergyBalance(albedo=trm.PrescribedAlbedo(), skin_temperature=trm.PrescribedSkinTemperature())
+    alb = np.array([0.4, 0.5, 0.1])
+    integ = _prescribed_seb_case(engine, seb, {"albedo": alb, "emissivity": 0.8, "surface_shortwave_down": 100.0, "surface_longwave_down": 20.0,
+                                               "skin_temperature": 0.0})
+    integ.compute_auxiliary()
+    s = integ.state
+    assert np.allclose(s.surface_shortwave_up.numpy(), alb * 100.0, rtol=1e-14)
+    assert np.allclose(s.surface_longwave_up.numpy(), (1 - 0.8) * 20.0 + 0.8 * 5.6704e-8 * 273.15 ** 4, rtol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+def test_prescribed_seb_schemes_parity(math):
+    """All three prescribed schemes together, 300 steps, both math modes against the oracle."""
+    n = 129
+    rng = np.random.default_rng(3)
+    inputs = {"albedo": rng.uniform(0.1, 0.5, n), "emissivity": rng.uniform(0.8, 1.0, n), "surface_shortwave_down": rng.uniform(0, 500, n),
+              "surface_longwave_down": 300.0, "surface_shortwave_up": rng.uniform(0, 150, n), "surface_longwave_up": rng.uniform(250, 400, n),
+              "sensible_heat_flux": rng.uniform(-20, 40, n), "latent_heat_flux": rng.uniform(0, 30, n), "rainfall": 1.0e-8, "windspeed": 0.5}
+    seb = trm.SurfaceEnergyBalance(albedo=trm.PrescribedAlbedo(), radiative_fluxes=trm.PrescribedRadiativeFluxes(), turbulent_fluxes=trm.PrescribedTurbulentFluxes())
+
+    def build(engine):
+        from common import richards_soil
+        grid = column(trm.ExponentialSpacing(dz_min=0.05, dz_max=10.0, N=20), n=n)
+        land = trm.LandModel(grid, soil=richards_soil(), vegetation=None, surface_energy_balance=seb)
+        return make(engine, land, trm.ForwardEuler(dt=60.0), inputs, math=math,
+                    initializers={"temperature": lambda x, z: 4.0 - 0.02 * z, "saturation_water_ice": lambda x, z: np.minimum(1.0, 0.6 - 0.1 * z) + 0 * x,
+                                  "skin_temperature": 4.0})
+    gpu, cpu = build("cuda"), build("oracle")
+    gpu.step(60.0, 300); cpu.step(60.0, 300)
+    from common import max_scaled_err
+    for name in ("temperature", "internal_energy", "saturation_water_ice", "skin_temperature", "ground_heat_flux", "surface_net_radiation"):
+        assert max_scaled_err(getattr(gpu.state, name).numpy(), getattr(cpu.state, name).numpy()) <= 1e-9, name
