@@ -389,6 +389,24 @@ int trm_diagnostics(trm_handle* h, trm_diag* out);
 /* Same numbers left in device memory as 8 doubles in trm_diag order (for ncclAllReduce). */
 int trm_diagnostics_device(trm_handle* h, double** dev_out);
 
+/* ---- global diagnostics over NCCL (one process per GPU, one handle per process) ----------------------------------
+ * The columns never exchange data; NCCL only serves the global diagnostic reductions (and output gathers, for which
+ * trm_field_view hands the device buffers to the caller's own ncclAllGather / NCCL.jl). The library binds to the NCCL
+ * the host process already has loaded (NCCL.jl's or torch's libnccl.so.2; dlsym first, dlopen("libnccl.so.2") otherwise),
+ * so a communicator created by the host's own NCCL binding can be adopted, and a host without a binding can create one here:
+ *   trm_nccl_get_unique_id  rank 0 fills 128 bytes (ncclUniqueId); the caller distributes them to the other ranks
+ *                           (a file, MPI, Julia's Distributed, torch.distributed ...)
+ *   trm_nccl_comm_init      ncclCommInitRank on the handle's device; the handle owns (and destroys) the communicator
+ *   trm_nccl_comm_adopt     use an ncclComm_t the caller owns (must come from the same libnccl instance)
+ *   trm_diagnostics_allreduce  local reduction (as trm_diagnostics) + two ncclAllReduce calls on the handle's stream:
+ *                           energy, water, nan_count, ncol are summed, minima / maxima are combined; every rank gets the
+ *                           global trm_diag. TRM_ERR_UNSUPPORTED when no NCCL library can be found. */
+#define TRM_NCCL_UNIQUE_ID_BYTES 128
+int trm_nccl_get_unique_id(void* id_bytes);
+int trm_nccl_comm_init(trm_handle* h, int32_t nranks, int32_t rank, const void* id_bytes);
+int trm_nccl_comm_adopt(trm_handle* h, void* nccl_comm);
+int trm_diagnostics_allreduce(trm_handle* h, trm_diag* out);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t trm_launch_count(trm_handle* h);
 /* Elapsed device time [ms] of the most recent trm_step call measured with CUDA events on the

@@ -152,6 +152,10 @@ SIGNATURES = {
     "set_clock": (C.c_int, [_H, C.c_double, C.c_int64]),
     "diagnostics": (C.c_int, [_H, C.POINTER(trm_diag)]),
     "diagnostics_device": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "nccl_get_unique_id": (C.c_int, [C.c_void_p]),
+    "nccl_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
+    "nccl_comm_adopt": (C.c_int, [_H, C.c_void_p]),
+    "diagnostics_allreduce": (C.c_int, [_H, C.POINTER(trm_diag)]),
     "launch_count": (C.c_int64, [_H]),
     "last_step_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "set_block_size": (C.c_int, [_H, C.c_int]),
@@ -171,7 +175,7 @@ SIGNATURES = {
     "set_field_ring": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
 }
 # entry points that only make sense on a device and that the CPU oracle does not export
-DEVICE_ONLY = ("field_ptr", "field_view", "host_alloc", "host_free", "host_alloc_ex", "bind_host_io", "host_io_wait", "input_ptr", "diagnostics_device", "launch_count", "last_step_ms", "set_block_size",
+DEVICE_ONLY = ("field_ptr", "field_view", "host_alloc", "host_free", "host_alloc_ex", "bind_host_io", "host_io_wait", "input_ptr", "diagnostics_device", "nccl_get_unique_id", "nccl_comm_init", "nccl_comm_adopt", "diagnostics_allreduce", "launch_count", "last_step_ms", "set_block_size",
                "set_input_field_async", "step_async", "get_field_async", "set_ring_index", "get_field_ring",
                "set_field_ring")
 

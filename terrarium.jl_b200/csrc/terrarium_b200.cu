@@ -6,6 +6,7 @@
 // There is NO CPU implementation behind these entry points: without a CUDA device trm_create
 // fails with TRM_ERR_NO_DEVICE.
 #include <nvtx3/nvToolsExt.h>
+#include <dlfcn.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +36,49 @@ template <class NF>
 __global__ void copy_row_kernel(int64_t n, const NF* __restrict__ x, NF* __restrict__ y) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = x[i];
+}
+
+// ---- NCCL, bound at run time to the library the host process uses (no link-time dependency) ----
+struct NcclApi {
+    struct Id { char b[128]; };   // ncclUniqueId, passed by value
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+const NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* lib = RTLD_DEFAULT;
+        if (!dlsym(RTLD_DEFAULT, "ncclAllReduce")) {
+            lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) return a;
+        }
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(lib, "ncclAllReduce");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy;
+        return a;
+    }();
+    return api;
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMin = 3;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+int nccl_fail(int rc, const char* what) {
+    const NcclApi& n = nccl_api();
+    return fail(TRM_ERR_CUDA, std::string(what) + ": " + (n.GetErrorString ? n.GetErrorString(rc) : "NCCL error " + std::to_string(rc)));
+}
+
+// diag_out = [energy, water, tmin, tmax, smin, smax, nan, ncol]  <->  sums [energy, water, nan, ncol], minima [tmin, smin, -tmax, -smax]
+static __global__ void diag_pack_kernel(const double* __restrict__ d, double* __restrict__ q) {
+    if (threadIdx.x == 0) { q[0] = d[0]; q[1] = d[1]; q[2] = d[6]; q[3] = d[7]; q[4] = d[2]; q[5] = d[4]; q[6] = -d[3]; q[7] = -d[5]; }
+}
+static __global__ void diag_unpack_kernel(const double* __restrict__ q, double* __restrict__ d) {
+    if (threadIdx.x == 0) { d[0] = q[0]; d[1] = q[1]; d[6] = q[2]; d[7] = q[3]; d[2] = q[4]; d[4] = q[5]; d[3] = -q[6]; d[5] = -q[7]; }
 }
 
 struct HandleBase {
@@ -68,6 +112,8 @@ struct HandleBase {
     virtual int bind_host_io(int in_id, const void* host_in, int field_id, void* host_out, int nslots) = 0;
     virtual int host_io_wait(int64_t iteration) = 0;
     virtual int reset_state() = 0;
+    virtual int diagnostics_allreduce(trm_diag* out) = 0;
+    void* nccl_comm = nullptr; bool nccl_owned = false;
     virtual void set_clock(double t, int64_t it) = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -149,6 +195,7 @@ struct Handle : HandleBase {
         for (cudaEvent_t e : {ev0, ev1, ev_staged, ev_out_done}) if (e) cudaEventDestroy(e);
         for (Input& s : in) for (cudaEvent_t e : {s.ev_free[0], s.ev_free[1], s.ev_ready}) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : hio.ev) if (e) cudaEventDestroy(e);
+        if (nccl_comm && nccl_owned && nccl_api().ok) nccl_api().CommDestroy(nccl_comm);
         for (cudaStream_t s : {stream, s_in, s_out}) if (s) cudaStreamDestroy(s);
     }
 
@@ -495,6 +542,8 @@ struct Handle : HandleBase {
     int aux() override;
     int tendencies() override;
     int diagnostics(trm_diag* out, double** dev) override;
+    int diagnostics_allreduce(trm_diag* out) override;
+    double* diag_pack = nullptr;
     int set_block(int b) override {
         if (b < 32 || b > TRM_MAX_BLOCK || b % 32) return fail(TRM_ERR_INVALID, "block must be a multiple of 32 in [32, 128]");
         block = b;
@@ -964,6 +1013,26 @@ template <class NF> int Handle<NF>::diagnostics(trm_diag* out, double** dev) {
     return TRM_OK;
 }
 
+template <class NF> int Handle<NF>::diagnostics_allreduce(trm_diag* out) {
+    const NcclApi& n = nccl_api();
+    if (!n.ok) return fail(TRM_ERR_UNSUPPORTED, "no NCCL library found (libnccl.so.2)");
+    if (!nccl_comm) return fail(TRM_ERR_STATE, "trm_diagnostics_allreduce before trm_nccl_comm_init / trm_nccl_comm_adopt");
+    if (int rc = diagnostics(nullptr, nullptr)) return rc;   // local partials -> diag_out (device)
+    if (!diag_pack) { if (int rc = dalloc(&diag_pack, 8)) return rc; }
+    diag_pack_kernel<<<1, 32, 0, stream>>>(diag_out, diag_pack);
+    if (int rc = n.AllReduce(diag_pack, diag_pack, 4, kNcclFloat64, kNcclSum, nccl_comm, stream)) return nccl_fail(rc, "ncclAllReduce(sum)");
+    if (int rc = n.AllReduce(diag_pack + 4, diag_pack + 4, 4, kNcclFloat64, kNcclMin, nccl_comm, stream)) return nccl_fail(rc, "ncclAllReduce(min)");
+    diag_unpack_kernel<<<1, 32, 0, stream>>>(diag_pack, diag_out);
+    launches += 2;
+    CU(cudaGetLastError());
+    double v[8];
+    CU(cudaMemcpyAsync(v, diag_out, sizeof(v), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    out->energy = v[0]; out->water = v[1]; out->t_min = v[2]; out->t_max = v[3];
+    out->sat_min = v[4]; out->sat_max = v[5]; out->nan_count = v[6]; out->ncol = v[7];
+    return TRM_OK;
+}
+
 HandleBase* H(trm_handle* h) { return reinterpret_cast<HandleBase*>(h); }
 bool bad_input(int id) { return id < 0 || id >= TRM_IN_COUNT; }
 
@@ -1061,6 +1130,35 @@ int trm_bind_host_io(trm_handle* h, int input_id, const void* host_in, int field
 int trm_host_io_wait(trm_handle* h, int64_t iteration) { if (!h) return fail(TRM_ERR_INVALID, "null handle"); return H(h)->host_io_wait(iteration); }
 int trm_diagnostics(trm_handle* h, trm_diag* out) { if (!h || !out) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics(out, nullptr); }
 int trm_diagnostics_device(trm_handle* h, double** dev) { if (!h || !dev) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics(nullptr, dev); }
+int trm_nccl_get_unique_id(void* id) {
+    if (!id) return fail(TRM_ERR_INVALID, "null argument");
+    const NcclApi& n = nccl_api();
+    if (!n.ok) return fail(TRM_ERR_UNSUPPORTED, "no NCCL library found (libnccl.so.2)");
+    if (int rc = n.GetUniqueId(id)) return nccl_fail(rc, "ncclGetUniqueId");
+    return TRM_OK;
+}
+int trm_nccl_comm_init(trm_handle* h, int32_t nranks, int32_t rank, const void* id) {
+    if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(TRM_ERR_INVALID, "bad handle / rank / id");
+    const NcclApi& n = nccl_api();
+    if (!n.ok) return fail(TRM_ERR_UNSUPPORTED, "no NCCL library found (libnccl.so.2)");
+    HandleBase* b = H(h);
+    if (b->nccl_comm) return fail(TRM_ERR_STATE, "the handle already has a communicator");
+    if (cudaSetDevice(b->device) != cudaSuccess) return fail(TRM_ERR_CUDA, "cudaSetDevice");
+    NcclApi::Id uid; std::memcpy(uid.b, id, sizeof(uid.b));
+    void* comm = nullptr;
+    if (int rc = n.CommInitRank(&comm, nranks, uid, rank)) return nccl_fail(rc, "ncclCommInitRank");
+    b->nccl_comm = comm; b->nccl_owned = true;
+    return TRM_OK;
+}
+int trm_nccl_comm_adopt(trm_handle* h, void* comm) {
+    if (!h || !comm) return fail(TRM_ERR_INVALID, "null argument");
+    if (!nccl_api().ok) return fail(TRM_ERR_UNSUPPORTED, "no NCCL library found (libnccl.so.2)");
+    HandleBase* b = H(h);
+    if (b->nccl_comm && b->nccl_owned) nccl_api().CommDestroy(b->nccl_comm);
+    b->nccl_comm = comm; b->nccl_owned = false;
+    return TRM_OK;
+}
+int trm_diagnostics_allreduce(trm_handle* h, trm_diag* out) { if (!h || !out) return fail(TRM_ERR_INVALID, "null argument"); return H(h)->diagnostics_allreduce(out); }
 int64_t trm_launch_count(trm_handle* h) { return h ? H(h)->launches : 0; }
 int trm_last_step_ms(trm_handle* h, float* ms) { if (!h || !ms) return fail(TRM_ERR_INVALID, "null argument"); *ms = H(h)->last_ms; return TRM_OK; }
 int trm_set_input_field_async(trm_handle* h, int id, const void* v) { if (!h || !v || bad_input(id)) return fail(TRM_ERR_INVALID, "bad handle / input id"); return H(h)->set_input_field_async(id, v); }

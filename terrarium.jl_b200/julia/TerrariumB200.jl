@@ -235,6 +235,27 @@ function Terrarium.run!(integ::B200Integrator; steps = nothing, period = nothing
     return integ
 end
 
+# ---- multi-GPU: one Julia process per GPU (Distributed / MPI.jl), one integrator per process over its column range; the
+# columns never exchange data, NCCL only reduces the global diagnostics (SURVEY.md 8e) ------------------------------------
+"""128-byte NCCL unique id created by rank 0; distribute it to the other ranks (e.g. `MPI.Bcast!`, `Distributed.remotecall`)."""
+function nccl_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:trm_nccl_get_unique_id, LIB), Cint, (Ptr{Cvoid},), id), "nccl_get_unique_id")
+    return id
+end
+"""Create the handle's NCCL communicator (`ncclCommInitRank`); collective over all ranks."""
+init_comm!(integ::B200Integrator, nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ccall((:trm_nccl_comm_init, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}), integ.handle, nranks, rank, id), "nccl_comm_init")
+"""Use a communicator NCCL.jl already owns: `adopt_comm!(integ, comm.handle)`."""
+adopt_comm!(integ::B200Integrator, comm::Ptr{Cvoid}) =
+    check(ccall((:trm_nccl_comm_adopt, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), integ.handle, comm), "nccl_comm_adopt")
+"""Global diagnostics (energy, water, extrema, NaN count over ALL ranks' columns); collective."""
+function global_diagnostics(integ::B200Integrator)
+    d = Ref(TrmDiag(0, 0, 0, 0, 0, 0, 0, 0))
+    check(ccall((:trm_diagnostics_allreduce, LIB), Cint, (Ptr{Cvoid}, Ref{TrmDiag}), integ.handle, d), "diagnostics_allreduce")
+    return d[]
+end
+
 function Terrarium.current_time(integ::B200Integrator)
     t, it = Ref{Cdouble}(0), Ref{Int64}(0)
     check(ccall((:trm_get_clock, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Int64}), integ.handle, t, it), "get_clock")

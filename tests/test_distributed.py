@@ -167,6 +167,27 @@ def nccl_gather_worker():
         assert np.array_equal(got.reshape(want.shape), want), name
     d = td.reduce_diagnostics(part.diagnostics())
     assert d["ncol"] == ncol and d["nan_count"] == 0
+    # the same reduction inside the library (trm_diagnostics_allreduce): rank 0 creates the NCCL unique id through the C ABI,
+    # the bytes travel over the process group the host already has, every rank initialises its handle's communicator
+    import ctypes as C
+    from terrarium_jl_b200 import _abi as abi
+    lib, h = part._lib, part._h
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_char * 128)()
+        lib.check(lib.nccl_get_unique_id(buf), "nccl_get_unique_id")
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    uid = uid.cuda()
+    dist.broadcast(uid, src=0)
+    raw = bytes(uid.cpu().numpy().tobytes())
+    lib.check(lib.nccl_comm_init(h, world, rank, C.c_char_p(raw)), "nccl_comm_init")
+    g = abi.trm_diag()
+    lib.check(lib.diagnostics_allreduce(h, C.byref(g)), "diagnostics_allreduce")
+    w = whole.diagnostics()
+    assert g.ncol == ncol and g.nan_count == 0
+    assert g.t_min == w["t_min"] and g.t_max == w["t_max"] and g.sat_min == w["sat_min"] and g.sat_max == w["sat_max"]
+    assert abs(g.energy - d["energy"]) <= 1e-12 * abs(d["energy"]) and abs(g.water - d["water"]) <= 1e-12 * abs(d["water"])
+    assert abs(g.water - w["water"]) <= 1e-11 * abs(w["water"])
     dist.barrier()
     if rank == 0:
         print(f"nccl gather over {world} ranks: OK")
