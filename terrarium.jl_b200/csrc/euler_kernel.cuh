@@ -102,9 +102,81 @@ struct EulerSmem {
     static constexpr int METRICS = MET_COUNT * MS;                                    // elements (the root fraction row is only filled by LandModel kernels)
     static constexpr int STRIP = EF_COUNT * TRM_EULER_BLOCK;
     static constexpr int RING = (2 * EULER_RD + (LOAD ? 3 : 0) * PF_) * TRM_EULER_BLOCK;   // U, sat (, T, liq, psi)
-    static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * PF_ * TRM_EULER_BLOCK;   // k1U, k1S, bU, bS
+    // Heun stage 2: k1U, k1S, bU, bS of the layer to be updated (stored protocol) / k1U, k1S next to U, sat (recompute protocol)
+    static constexpr int XRING = (MODE != MODE_HEUN2 ? 0 : (heun_recompute<NF>() ? 2 * EULER_RD : 4 * PF_)) * TRM_EULER_BLOCK;
     static constexpr size_t BYTES = sizeof(NF) * (size_t)(METRICS + STRIP + RING + XRING);
 };
+
+// Heun stage 1, recompute protocol, slow path of one column (Richards): a layer of the stage state went negative, so the
+// stage copy needs the downward sweep of adjust_saturation_profile! (soil_hydrology.jl:201-216), which stage 2 cannot rebuild
+// layer by layer. The column's stage state is formed here in full from the base state and the k1 this thread has just stored
+// (explicit_step! with the time-n Flux BCs, upward sweep, downward sweep), written to yU / yS, and the column is flagged.
+template <class NF, bool FAST, int MS, bool LAND>
+__device__ __noinline__ void heun1_slow_column(const StageArgs<NF>& A, Metrics<NF, MS> met, int64_t c) {
+    const DevParams<NF>& p = A.p;
+    const int nz = A.nz;
+    const int64_t ld = A.ld;
+    const NF dt = A.dt;
+    auto bc_input = [&](int slot) -> NF { return eval_input(A.in[A.bc[slot].input], c, A.t_b, 1); };   // Flux BCs: time of the base state
+    NF carry = NF(0);
+#pragma unroll 1
+    for (int k = 1; k <= nz; ++k) {
+        const int64_t o = (int64_t)(k - 1) * ld + c;
+        NF tU = A.oTU[o], tS = A.oTS[o];
+        if (k == nz) {
+            if (LAND) { tU -= A.G[c] / met.dzc(nz); tS -= (-A.infil[c]) / met.dzc(nz); }
+            else {
+                if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / met.dzc(nz);
+                if (A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / met.dzc(nz);
+            }
+        }
+        if (k == 1) {
+            if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / met.dzc(1);
+            if (A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
+        }
+        A.yU[o] = A.bU[o] + tU * dt;
+        NF s = A.bS[o] + tS * dt;
+        s = s + carry;
+        if (k < nz) {
+            const NF e = M<NF, FAST>::pos(s - 1);
+            s -= e;
+            carry = FAST ? e * met.dzc(k) * met.rdzc(k + 1) : e * met.dzc(k) / met.dzc(k + 1);
+        }
+        A.yS[o] = s;
+    }
+    NF carry_dn = NF(0);
+#pragma unroll 1
+    for (int k = nz; k >= 1; --k) {
+        const int64_t o = (int64_t)(k - 1) * ld + c;
+        NF s = A.yS[o];
+        if (k < nz) s -= carry_dn;
+        if (k >= 2) {
+            const NF d = jmax(-s, NF(0));
+            s += d;
+            carry_dn = d * met.dzc(k) / met.dzc(k - 1);
+        }
+        if (k == nz) s -= jmax(s - 1, NF(0));   // (the surface excess water of the stage copy is not used)
+        if (k == 1) s = jmax(s, NF(0));
+        A.yS[o] = s;
+    }
+    int idx = 0;
+#pragma unroll 1
+    for (int k = 1; k <= nz; ++k) if (idx == 0 && A.yS[(int64_t)(k - 1) * ld + c] < 1) idx = k;
+    if (idx == 0) idx = nz + 1;
+    A.yWt[c] = met.zF(idx);
+    A.hflag_out[c] = NF(1);
+    if (LAND && has_veg(A)) {   // soil moisture limiting factor of the stage state, for the vegetation block of stage 2
+        NF beta = NF(0);
+#pragma unroll 1
+        for (int k = 1; k <= nz; ++k) {
+            const int64_t o = (int64_t)(k - 1) * ld + c;
+            NF Tc, lc;
+            energy_to_temperature<NF, FAST>(p, A.yU[o], A.yS[o], Tc, lc);
+            beta += FAST ? plant_available_water_fast(A.vp, p, A.yS[o], lc) * met.root(k) : plant_available_water(A.vp, p, A.yS[o], lc) * met.root(k) / met.dzc(k) * met.dzc(k);
+        }
+        A.ybeta[c] = beta;
+    }
+}
 
 // VG2: van Genuchten n = 2 for retention curve and conductivity, checked on the host (see cell_conductivity)
 template <class NF, int PHYS, int LOAD_CT, bool FAST, int MS, int MODE = MODE_EULER, bool VG2 = false>
@@ -119,6 +191,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     constexpr bool H1 = MODE == MODE_HEUN1, H2 = MODE == MODE_HEUN2;
     constexpr int DIST_ = euler_dist(MODE), PF_ = euler_pf(MODE);
     constexpr bool CLOSE = !H1;    // Heun stage 1 leaves the closure fields of the stage state to stage 2 (recomputed there)
+    constexpr bool RC = heun_recompute<NF>() && (H1 || H2);   // Heun "recompute" protocol (see heun_recompute)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nz = A.nz;
@@ -166,6 +239,9 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     uint32_t oin = (uint32_t)c;
     const uint32_t xring0 = ring0 + (uint32_t)(SM::RING * ES);
     uint32_t oext = (uint32_t)c;   // (Heun stage 2) element offset of the next layer of the extra ring
+    // (recompute protocol, stage 2) k1 of layer k lives next to U / sat of layer k, from its prefetch until its update
+    auto k1U_slot = [&](int k) { return xring0 + (uint32_t)((k & (EULER_RD - 1)) * B * ES); };
+    auto k1S_slot = [&](int k) { return xring0 + (uint32_t)(((k & (EULER_RD - 1)) + EULER_RD) * B * ES); };
     auto prefetch = [&](int k, bool always = false) {
         if (always || k <= nz) {
             cp_async<ES>(ringU(k), A.xU + oin);
@@ -176,9 +252,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 cp_async<ES>(dst + PF_ * B * ES, A.xL + oin);
                 if (RICH) cp_async<ES>(dst + 2 * PF_ * B * ES, A.xP + oin);
             }
+            if (H2 && RC) { cp_async<ES>(k1U_slot(k), A.k1U + oin); if (RICH) cp_async<ES>(k1S_slot(k), A.k1S + oin); }
             oin += (uint32_t)ld;
         }
-        if (H2) {
+        if (H2 && !RC) {
             // Heun stage 2: k1 and the base state of layer k-2, needed when that layer is updated (iteration k)
             const int kk = k - 2;
             if (kk >= 1 && kk <= nz) {
@@ -205,6 +282,23 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     if (RICH && !H1) Sx_new = A.bSx[c] + NF(0) * dt;   // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
     uint32_t oout = (uint32_t)c;   // element offset of layer m-2
     if (LAND && has_veg(A)) wr(EF_BETA, NF(0));   // vegetated LandModel: soil moisture limiting factor (plant_available_water.jl:31-35)
+    // recompute protocol, stage 2: upward-sweep carry of the stage state being rebuilt ; columns whose stage state was stored
+    NF carry1 = NF(0);
+    const bool flagged = (H2 && RC && RICH) ? (A.hflag_in[c] != NF(0)) : false;
+    uint32_t oent = (uint32_t)c;   // element offset of the entering layer (stored stage state of a flagged column)
+    // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 ): the fluxes of the time-n state.
+    // LandModel: ground heat flux and infiltration left by surface_kernel (land_model.jl:56-62)
+    auto apply_top_flux = [&](NF& tU, NF& tS) {
+        if (LAND) { const NF G_top = A.G[c]; tU -= G_top / met.dzc(nz); if (RICH) { const NF infil_top = A.infil[c]; tS -= (-infil_top) / met.dzc(nz); } }
+        else {
+            if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / met.dzc(nz);
+            if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / met.dzc(nz);
+        }
+    };
+    auto apply_bottom_flux = [&](NF& tU, NF& tS) {
+        if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / met.dzc(1);
+        if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
+    };
 
     // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-DIST, for which every
     // layer-index special case below is statically false / true: no halo, no boundary face, no Flux BC, the
@@ -217,8 +311,32 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         const NF Kf1 = RICH ? ldsv(kf_prv, (NF*)nullptr) : NF(0);   // Kf[m-1]
         if (inner || m <= nz) {
             cp_async_wait<DIST_>();   // all but the DIST most recent groups have landed: layer m is in the ring
-            const NF Ur = ldsv(ringU(m), (NF*)nullptr);
-            const NF sr = ldsv(ringS(m), (NF*)nullptr);
+            NF Ur = ldsv(ringU(m), (NF*)nullptr);
+            NF sr = ldsv(ringS(m), (NF*)nullptr);
+            if (H2 && RC) {
+                // stage state of layer m: what stage 1 computed from the same base state and k1, and did not store
+                // (explicit_step! + upward sweep of adjust_saturation_profile! of the stage copy, heun.jl:45-49)
+                if (flagged) { Ur = A.sU[oent]; sr = A.sS[oent]; }
+                else {
+                    NF t1U = ldsv(k1U_slot(m), (NF*)nullptr), t1S = RICH ? ldsv(k1S_slot(m), (NF*)nullptr) : NF(0);
+                    if (!inner && m == nz) apply_top_flux(t1U, t1S);
+                    if (!inner && m == 1) apply_bottom_flux(t1U, t1S);
+                    Ur = Ur + t1U * dt;
+                    if (RICH) {
+                        sr = sr + t1S * dt;
+                        sr = sr + carry1;
+                        if (inner || m < nz) {
+                            const NF e = Mx::pos(sr - 1);
+                            sr -= e;
+                            carry1 = FAST ? e * met.dzc(m) * met.rdzc(m + 1) : e * met.dzc(m) / met.dzc(m + 1);
+                        }
+                        if (!FAST && m >= 2) sr = sr + jmax(-sr, NF(0));
+                        if (!inner && m == nz) sr -= Mx::pos(sr - 1);       // top excess of the stage copy (its surface excess water is not used)
+                        if (!FAST && !inner && m == 1) sr = jmax(sr, NF(0));
+                    }
+                }
+                oent += (uint32_t)ld;
+            }
             NF ln;
             if (LOAD) {
                 const uint32_t src = ring0 + (uint32_t)((2 * EULER_RD + (m & (PF_ - 1))) * B * ES);
@@ -277,9 +395,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
 
         // ---- LandModel surface processes, once the top layer is the one about to be updated ----
-        NF G_top = NF(0), infil_top = NF(0);   // fluxes coupling the surface to the top soil layer (same iteration)
-        // (evaluated by surface_kernel on the time-n state; Heun stage 2 applies the same time-n fluxes, heun.jl:63-66)
-        if (LAND && !inner && m == nz + 2) { G_top = A.G[c]; infil_top = A.infil[c]; }
+        // (LandModel: the fluxes coupling the surface to the top soil layer were evaluated by surface_kernel on the time-n
+        //  state; Heun stage 2 applies the same time-n fluxes, heun.jl:63-66 -- see apply_top_flux)
 
         if (inner || m >= 3) {
             // ---- tendencies of layer j = m-2 ----
@@ -293,7 +410,11 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 tS = FAST ? dth * p.rpor : dth / p.por;                          // soil_hydrology.jl:222-237
             }
             NF Ub, sb;   // base state the update is applied to
-            if (H2) {   // average_tendencies! (heun.jl:27-35) with k1 of stage 1 ; the base is the state at time n
+            if (H2 && RC) {   // average_tendencies! (heun.jl:27-35) ; k1 and the base state sit in the 8-deep rings
+                tU = (ldsv(k1U_slot(j), (NF*)nullptr) + tU) / 2;
+                Ub = ldsv(ringU(j), (NF*)nullptr); sb = ldsv(ringS(j), (NF*)nullptr);
+                if (RICH) tS = (ldsv(k1S_slot(j), (NF*)nullptr) + tS) / 2;
+            } else if (H2) {   // average_tendencies! (heun.jl:27-35) with k1 of stage 1 ; the base is the state at time n
                 const uint32_t x = xring0 + (uint32_t)((j & (PF_ - 1)) * B * ES);
                 tU = (ldsv(x, (NF*)nullptr) + tU) / 2;
                 Ub = ldsv(x + 2 * PF_ * B * ES, (NF*)nullptr);
@@ -303,18 +424,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (H1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }   // k1, before the Flux BCs
                 Ub = ldsv(ringU(j), (NF*)nullptr); sb = ldsv(ringS(j), (NF*)nullptr);
             }
-            // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69 )
-            if (!inner && j == nz) {
-                if (LAND) { tU -= G_top / met.dzc(nz); if (RICH) tS -= (-infil_top) / met.dzc(nz); }   // land_model.jl:56-62
-                else {
-                    if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) tU -= bc_input(TRM_BC_ENERGY_TOP) / met.dzc(nz);
-                    if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) tS -= bc_input(TRM_BC_SATURATION_TOP) / met.dzc(nz);
-                }
-            }
-            if (!inner && j == 1) {
-                if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) tU += bc_input(TRM_BC_ENERGY_BOTTOM) / met.dzc(1);
-                if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
-            }
+            if (!inner && j == nz) apply_top_flux(tU, tS);
+            if (!inner && j == 1) apply_bottom_flux(tU, tS);
             // ---- explicit step, abstract_timestepper.jl:113-141 ----
             const NF Un = Ub + tU * dt;
             NF sn = sb;
@@ -331,9 +442,13 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             }
             // (fast math, inner layers: the regular stores below ARE the raw values the slow path re-reads -- no
             //  surface excess, no clamp -- so the flag needs no branch here; the closure stores are overwritten later)
+            // (recompute protocol, Heun stage 1: the stage state is not stored -- except its top layer, which the vegetation
+            //  block of stage 2 reads through surface_kernel -- and a column that goes negative rebuilds it in its slow path)
+            constexpr bool STORE = !(H1 && RC);
+            if (!STORE && !inner && j == nz) A.yU[o] = Un;
             if (RICH && !(inner && FAST) && any_neg()) {
                 // raw values for the slow path below (the downward sweep needs the whole profile)
-                A.yU[o] = Un; A.yS[o] = sn;
+                if (STORE) { A.yU[o] = Un; A.yS[o] = sn; }
             } else {
                 if (RICH) {
                     // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
@@ -344,10 +459,11 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                         Sx_new += e * met.dzc(nz);
                     }
                     if (!FAST && !inner && j == 1) sn = jmax(sn, NF(0));       // :216
-                    stg(A.yS + o, sn);
+                    if (STORE) stg(A.yS + o, sn);
+                    else if (!inner && j == nz) A.yS[o] = sn;                  // (top layer, after the top excess went to the surface)
                     if (idx == 0 && (FAST ? below_one(sn) : sn < 1)) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                 }
-                stg(A.yU + o, Un);
+                if (STORE) stg(A.yU + o, Un);
                 if (CLOSE || (LAND && has_veg(A))) {
                     NF Tc, lc;
                     energy_to_temperature<NF, FAST>(p, Un, sn, Tc, lc);
@@ -389,6 +505,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     if (!any_neg()) {
         if (idx == 0) { idx = nz + 1; wt_new = met.zF(nz + 1); }   // all saturated: z of the surface (halo cell / fallback give the same)
         A.yWt[c] = wt_new;
+        if (H1 && RC) A.hflag_out[c] = NF(0);   // stage 2 rebuilds the stage state of this column from the base state and k1
         if (H1) return;            // the stage state needs no surface excess water and no closure fields
         A.ySx[c] = Sx_new;
         // pressure head of the saturated zone below the water table: psi_m(sat >= 1) is a constant
@@ -406,6 +523,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
         return;
     }
+    if (H1 && RC) { heun1_slow_column<NF, FAST, MS, LAND>(A, met, c); return; }
     // ---- slow path: a layer went negative. Downward sweep (soil_hydrology.jl:201-216) top -> bottom on the raw
     //      profile this thread just stored, then water table and closures bottom -> top. ----
     {

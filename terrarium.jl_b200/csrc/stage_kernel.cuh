@@ -107,6 +107,11 @@ struct StageArgs {
     // tendencies: read in Heun stage 2, written in Heun stage 1 (without Flux BCs) and TEND (with)
     const NF *k1U, *k1S;
     NF *oTU, *oTS;
+    // Heun, "recompute" protocol of the Float64 staged kernels (euler_kernel.cuh): stage 1 stores k1 and the stage water table
+    // but not the stage state, which stage 2 rebuilds from the base state and k1. A column whose stage state needs the downward
+    // sweep (negative saturation) is flagged by stage 1, which then stores its stage state in full (sU / sS, read by stage 2).
+    const NF *sU, *sS, *hflag_in;
+    NF* hflag_out;
     NF* Kf;   // z-face hydraulic conductivity [nz+1][ld], written in AUX / TEND
     // LandModel 2-D fields
     NF *Ts, *G, *SWup, *LWup, *Rnet, *Hs, *Hl, *Egnd, *infil, *runoff;
@@ -135,6 +140,19 @@ struct StageArgs {
     trm_bc bc[TRM_BC_NSLOTS];
     InputDesc<NF> in[TRM_IN_COUNT];
 };
+
+// Heun traffic: with the stage state stored (stage 1: read U, sat; write U*, sat*, k1U, k1S -- stage 2: read U*, sat*, k1U, k1S,
+// U, sat; write U, sat, T, liq, psi) a step moves 17 values per cell. The "recompute" protocol drops the stage state from
+// memory: stage 2 rebuilds U* = U + dt (k1U + Flux BCs), sat* = adjust(sat + dt (k1S + Flux BCs)) of the entering layer from
+// the base state and k1, which it needs anyway for the update two iterations later (one 8-deep ring serves both uses):
+// 13 values per cell. Float64 only (the Float32 kernels keep the stored form); TRM_HEUN_STORE_STAGE switches it off.
+template <class NF> __host__ __device__ constexpr bool heun_recompute() {
+#ifdef TRM_HEUN_STORE_STAGE
+    return false;
+#else
+    return sizeof(NF) == 8;
+#endif
+}
 
 // vegetated LandModel? (TRM_NO_VEG: tuning builds that compile the vegetation code out)
 template <class NF>

@@ -144,6 +144,7 @@ struct Handle : HandleBase {
     NF *tU = nullptr, *tS = nullptr, *gU = nullptr, *gS = nullptr;   // tendencies, Heun stage state
     // 2-D [ld]
     NF *Sx = nullptr, *Wt = nullptr, *gWt = nullptr;
+    NF* hflag = nullptr;   // Heun recompute protocol: columns whose stage state was stored by stage 1 (negative saturation)
     NF* land2d[10] = {nullptr};   // Ts, G, SWup, LWup, Rnet, Hs, Hl, Egnd, infil, runoff
     // vegetated LandModel: 2-D fields in VegField order (first three prognostic), Heun stage values and k1 of the
     // prognostic triple, plant available water [nz][ld], host copy of the static root fraction per layer
@@ -312,7 +313,7 @@ struct Handle : HandleBase {
         if (int rc = dalloc(&Wt, ld)) return rc;
         if (heun) {
             for (NF** f : {&tU, &gU}) if (int rc = dalloc(f, n3)) return rc;
-            if (richards) { for (NF** f : {&tS, &gS}) if (int rc = dalloc(f, n3)) return rc; if (int rc = dalloc(&gWt, ld)) return rc; }
+            if (richards) { for (NF** f : {&tS, &gS}) if (int rc = dalloc(f, n3)) return rc; if (int rc = dalloc(&gWt, ld)) return rc; if (int rc = dalloc(&hflag, ld)) return rc; }
         }
         if (land) for (int i = 0; i < 10; ++i) if (int rc = dalloc(&land2d[i], ld)) return rc;
         if (veg) {
@@ -553,6 +554,8 @@ struct Handle : HandleBase {
     int launch_surface(int what, const StageArgs<NF>& a);
     // the staged kernels (euler_kernel.cuh) leave the LandModel surface block to surface_kernel; the generic streaming
     // kernel evaluates it inline
+    // Heun recompute protocol (stage_kernel.cuh: heun_recompute): the Float64 staged kernels, both stages of a step alike
+    bool heun_rc() const { return heun_recompute<NF>() && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     bool split_surface() const { return land && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     int enqueue_steps(double dt, int64_t n);
     int set_input_field_async(int id, const void* v) override;
@@ -674,6 +677,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
             for (int i = 0; i < 3; ++i) { a.vy[i] = gveg[i]; a.vok1[i] = tveg[i]; }
             a.ybeta = gbeta;
+            a.hflag_out = hflag;
             set_times(a);
             apply_host_io(a, false);
             if (split) { if (int rc = launch_surface(0, a)) return rc; }
@@ -681,6 +685,10 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             StageArgs<NF> b; base_args(b);
             b.dt = dt; b.mode = MODE_HEUN2; b.load_aux = 0; b.t_x = t1; b.t_b = t;
             b.xU = gU; b.xS = richards ? gS : S; b.xWt = gWt; b.bU = U; b.bS = S; b.bSx = Sx; b.k1U = tU; b.k1S = tS;
+            const bool rc = heun_rc();
+            // recompute protocol: the stage kernel streams the base state and k1 and rebuilds the stage state; only flagged
+            // columns (and the top layer, for the surface block) read what stage 1 stored
+            if (rc) { b.xU = U; b.xS = S; b.sU = gU; b.sS = gS; b.hflag_in = hflag; }
             for (int i = 0; i < 3; ++i) { b.vx[i] = gveg[i]; b.vk1[i] = tveg[i]; }
             b.xbeta = gbeta;
             y_state(b);
@@ -689,7 +697,11 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
             apply_host_io(b, true);
             // stage 2 only re-evaluates the vegetation block (k2 of canopy water, vegetation carbon and area fraction);
             // the bare-ground surface block of the stage state has no effect on the step (heun.jl:63-66)
-            if (split && veg) { if (int rc = launch_surface(0, b)) return rc; }
+            if (split && veg) {
+                StageArgs<NF> bs = b;   // the surface block is evaluated on the stage state (its top layer is always stored)
+                bs.xU = gU; bs.xS = richards ? gS : S;
+                if (int rc2 = launch_surface(0, bs)) return rc2;
+            }
             if (int rc = launch_euler(b, 0)) return rc;
         }
         if (hio.nslots) {

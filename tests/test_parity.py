@@ -491,3 +491,34 @@ def test_debug_nancheck(monkeypatch):
     integ.state.internal_energy.set(U)
     with pytest.raises(trm.TerrariumError, match="TERRARIUM_DEBUG"):
         integ.step(60.0, 1)
+
+
+@pytest.mark.parametrize("math", ["faithful", "fast"])
+def test_heun_negative_saturation_stage_state(math):
+    """Heun with a strong sink: the STAGE state of two thirds of the columns goes negative and needs the downward sweep of
+    adjust_saturation_profile! (soil_hydrology.jl:201-216). Under the recompute protocol of the Float64 kernels stage 1 then
+    stores the stage state of exactly those columns and flags them; every other column is rebuilt by stage 2 from the base
+    state and k1. The sweep leaves the deficient layer at exactly zero saturation, whose matric head is -Inf in the reference
+    formulation, so the stage-2 Darcy fluxes -- and with them the new saturation -- of such a column are NaN in the
+    reference (and in the oracle); its internal energy stays finite and depends on the swept stage saturation through the
+    thermal conductivity and the heat capacity. Asserted: identical finite / non-finite pattern, finite values to 1e-12."""
+    n = 96
+
+    def build(engine):
+        rng = np.random.default_rng(7)
+        grid = trm.ColumnGrid(trm.B200(), np.float64, trm.UniformSpacing(dz=0.1, N=20), n)
+        model = trm.SoilModel(grid, soil=richards_soil(vwc_forcing=-1.0e-4))
+        sat0 = rng.uniform(0.004, 0.02, (20, n))
+        sat0[:, ::3] = 0.9   # every third column stays on the fast path
+        return make(engine, model, trm.Heun(dt=60.0), initializers={"temperature": 5.0, "saturation_water_ice": sat0}, math=math)
+
+    cpu, gpu = build("oracle"), build("cuda")
+    cpu.step(60.0, 1); gpu.step(60.0, 1)
+    sat_c = cpu.state.saturation_water_ice.numpy()
+    assert (~np.isfinite(sat_c)).any(axis=0).sum() == 64 and np.isfinite(sat_c[:, ::3]).all()
+    for name in ("saturation_water_ice", "internal_energy", "water_table", "surface_excess_water"):
+        a, b = getattr(gpu.state, name).numpy(), getattr(cpu.state, name).numpy()
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin), name
+        assert max_scaled_err(a[fin], b[fin]) <= 1e-12, name
+    assert np.isfinite(cpu.state.internal_energy.numpy()).all()
