@@ -41,19 +41,22 @@ SEED = 20260101
 CPU_BUILD = ""
 
 
-def algorithmic_bytes_per_cell(itemsize: int, nz: int, model: str = "soil", heun: bool = False) -> float:
+def algorithmic_bytes_per_cell(itemsize: int, nz: int, model: str = "soil", heun: bool = False, moved: bool = False) -> float:
     """read U, sat; write U, sat, T, liq, psi (7 values per cell) + per column: surface_excess_water
-    R/W, water_table R/W, sinusoid forcing parameters (mean, amp, phase) R = 7 values per column.
+    R/W, water_table R/W, sinusoid forcing parameters (mean, amp, phase) R = 7 values per column. The same figure is the
+    algorithmic one for Heun ("Euler or fused Heun: 7 s"): a step reads the state once and writes the new state once.
 
-    Secondary workloads: Heun = stage 1 (read U, sat; write stage U, sat and k1 of both) + stage 2 (read
-    stage U, sat, both k1, base U, sat; write U, sat, T, liq, psi) = 17 values per cell. Per column, the bare-ground
-    LandModel moves 22 values (skin temperature and surface excess water, 8 forcing parameters / table rows in; 10 surface
-    fields out; G and infiltration read back by the stage kernel), the vegetated one 49 (adds 3 prognostic variables R/W,
-    the previous net assimilation, the soil moisture factor R/W, SAI, 17 auxiliaries out); a Heun step re-reads G and the
-    infiltration in stage 2 (+2) and, vegetated, evaluates the vegetation block again on the stage state (+27)."""
-    per_cell = 17.0 if heun else 7.0
+    `moved = True`: what the TWO stage launches of a Heun step actually move. Float64 (recompute protocol):
+    stage 1 reads U, sat and writes k1 of both; stage 2 reads U, sat, both k1 and writes U, sat, T, liq, psi = 13 values per
+    cell; Float32 keeps the stage state in memory: 17 values. Per column, the bare-ground LandModel moves 22 values (skin
+    temperature and surface excess water, 8 forcing parameters / table rows in; 10 surface fields out; G and infiltration read
+    back by the stage kernel), the vegetated one 49 (adds 3 prognostic variables R/W, the previous net assimilation, the soil
+    moisture factor R/W, SAI, 17 auxiliaries out); a Heun step re-reads G and the infiltration in stage 2 (+2) and, vegetated,
+    evaluates the vegetation block again on the stage state (+27)."""
+    per_cell = 7.0
     per_col = {"soil": 7.0, "land": 22.0, "land-veg": 49.0}[model]
-    if heun:
+    if heun and moved:
+        per_cell = 13.0 if itemsize == 8 else 17.0
         per_col += {"soil": 4.0, "land": 2.0, "land-veg": 27.0}[model]
     return per_cell * itemsize + per_col * itemsize / nz
 
@@ -392,7 +395,8 @@ def main():
                           + f"<{args.dtype}, {'RICHARDS' if args.model == 'soil' else 'LAND'}, recompute, {args.math}>"
                           + (" (two stage launches per step)" if args.timestepper == "heun" else "")
                           + (" + trm::surface_kernel" if args.model != "soil" else ""),
-                "launch_ms": per_launch_ms}
+                "launch_ms": per_launch_ms,
+                "moved_bytes_per_column_layer_step": algorithmic_bytes_per_cell(itemsize, NZ, args.model, args.timestepper == "heun", moved=True)}
 
     # ---- secondary workloads on the same domain (not the headline; each with its own roofline and clock record) ----
     secondary_lines = []
@@ -423,12 +427,15 @@ def main():
             isz = np.dtype(nf2).itemsize
             bpc2 = algorithmic_bytes_per_cell(isz, NZ, model_kind, stepper == "heun")
             ach2 = bpc2 * (it2.ncol * NZ) / (ms2 * 1e-3) / 1e9
+            moved2 = algorithmic_bytes_per_cell(isz, NZ, model_kind, stepper == "heun", moved=True)
             secondary_lines.append({
                 "workload": {"soil": "soil energy + Richards", "land": "bare-ground LandModel", "land-veg": "vegetated LandModel"}[model_kind]
                             + f", {stepper}, {dt_name}", "dtype": dt_name, "timestepper": stepper, "steps": args.secondary_steps,
                 "ms_per_step": ms2, "value": total_cells / (ms2 * 1e-3), "unit": UNIT, "gpu_launches": int(nl), "nan_count": nan2,
                 "roofline": {"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
-                             "algorithmic_bytes_per_column_layer_step": bpc2},
+                             "algorithmic_bytes_per_column_layer_step": bpc2,
+                             # what the launches of one step move (Heun: two stage launches) and the same fraction on that basis
+                             "moved_bytes_per_column_layer_step": moved2, "frac_of_moved_bytes": ach2 / peak * moved2 / bpc2},
                 "clocks": ck})
             it2.close()
             del it2
