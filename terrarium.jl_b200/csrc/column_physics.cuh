@@ -30,6 +30,7 @@ struct DevParams {
     int32_t albedo_kind, rad_kind, turb_kind;   // trm_albedo_kind / trm_radiative_kind / trm_turbulent_kind
     NF th_fc;                  // field capacity (ground evaporation resistance, plant available water)
     int32_t vg_n_is_2;
+    int32_t bc_k;              // Brooks-Corey: 1 / lambda when that is a small integer (the default lambda = 0.2 -> 5), else 0
 };
 
 template <class NF> struct Lim;

@@ -12,8 +12,10 @@
 //   * two independent dependency chains per thread hide the fixed-latency stalls that dominate the scalar kernel.
 // Same algorithm, same pipeline and the same shared-memory layout idea as euler_kernel (see its header); the per-cell
 // formulas are the FAST (reciprocal / rsqrt based, van Genuchten n = 2) forms of column_physics.cuh restated on pairs.
-// Columns whose saturation goes negative take the per-column slow path of the scalar kernel. Fast math, recomputed closure
-// fields and a van Genuchten n = 2 soil only: every other case runs euler_kernel.
+// Columns whose saturation goes negative take the per-column slow path of the scalar kernel. Fast math and recomputed closure
+// fields only, for two soils (template parameter SOIL): van Genuchten n = 2 retention curve + conductivity (the configuration
+// of BASELINE.json) and the reference's DEFAULT hydraulics, Brooks-Corey with an integer 1 / lambda + linear conductivity
+// (ConstantSoilHydraulics(), the soil of test/benchmarks/gpu/soil_heat_hydrology_global.jl). Every other case runs euler_kernel.
 #pragma once
 
 #include "euler_kernel.cuh"
@@ -111,10 +113,36 @@ __device__ __forceinline__ F2 cell_conductivity2(const DevParams<float>& p, F2 s
     K = sel(one, KI, K);
     return sel(zero, 0.0f, K);
 }
+// UnsatKLinear (soil_hydraulic_properties.jl:170-198): K = K_sat water / (water + ice + air), the three fractions formed as
+// in volumetric_fractions (soil_volume.jl:52-67)
+__device__ __forceinline__ F2 cell_conductivity2_linear(const DevParams<float>& p, F2 sat, F2 liq) {
+    const F2 wi = sat * p.por;
+    const F2 water = wi * liq;
+    const F2 ice = wi * (bc2(1.0f) - liq);
+    const F2 air = (bc2(1.0f) - sat) * p.por;
+    return (water * p.Ksat) * rcp2((water + ice) + air);
+}
+enum Soil2 { SOIL2_VG2 = 0, SOIL2_BC_LINEAR = 1 };
+template <int SOIL>
+__device__ __forceinline__ F2 cell_conductivity2s(const DevParams<float>& p, F2 sat, F2 liq) {
+    return SOIL == SOIL2_VG2 ? cell_conductivity2(p, sat, liq) : cell_conductivity2_linear(p, sat, liq);
+}
+// Brooks-Corey matric head with an integer exponent k = 1 / lambda: psi_m = -psi_s se^-k below saturation, -psi_s at
+// saturation (FreezeCurves BrooksCorey); se^k by repeated multiplication (k is launch-uniform, <= 8)
+__device__ __forceinline__ F2 brooks_corey_psim2(const DevParams<float>& p, F2 theta) {
+    const F2 se = fma2(theta, p.r_thspan, p.se_off);
+    F2 pw = se;
+#pragma unroll 1
+    for (int i = 1; i < p.bc_k; ++i) pw = pw * se;
+    const F2 r = rcp2(pw) * -p.bc_psis;          // se = 0 (dry layer): rcp(0) = +Inf -> -Inf as in the reference
+    return F2{theta.x < p.por ? r.x : -p.bc_psis, theta.y < p.por ? r.y : -p.bc_psis};
+}
 // total pressure head, saturation_to_pressure! (soil_hydraulic_closures.jl:102-129) with the van Genuchten n = 2 retention
 // curve: psi_m = -(1/alpha) sqrt(se^-2 - 1) = -(1/alpha) a / sqrt(a t), a = 1 - se^2, t = se^2 (see swrc_inverse)
+template <int SOIL = SOIL2_VG2>
 __device__ __forceinline__ F2 pressure_head2(const DevParams<float>& p, F2 sat, F2 wt, float zc, float psiz) {
     const F2 theta = sat * p.por;
+    if (SOIL == SOIL2_BC_LINEAR) return (pos2(wt + (-zc)) + brooks_corey_psim2(p, theta)) + psiz;
     const F2 se = fma2(theta, p.r_thspan, p.se_off);
     const F2 t = se * se;
     const F2 a = abs2(fma2(se * -1.0f, se, 1.0f));
@@ -149,7 +177,7 @@ constexpr int euler2_min_blocks() { return MODE == MODE_HEUN2 ? 4 : (phys_land(P
 
 // slow path of one column: a layer went negative. Downward sweep (soil_hydrology.jl:201-216) top -> bottom on the raw
 // profile the thread has just stored, then water table and closures bottom -> top (same code as the scalar kernel).
-template <int MS, int MODE, bool LAND>
+template <int MS, int MODE, bool LAND, bool VG2>
 __device__ __noinline__ void euler2_slow_column(const StageArgs<float>& A, Metrics<float, MS> met, int64_t c, float Sx_new) {
     constexpr bool H1 = MODE == MODE_HEUN1;
     using NF = float;
@@ -193,12 +221,12 @@ __device__ __noinline__ void euler2_slow_column(const StageArgs<float>& A, Metri
         if (H1) continue;   // the stage state keeps no closure fields
         A.yT[o] = Tc; A.yL[o] = lc;
         if (k == nz && A.hio_out) A.hio_out[c] = Tc;
-        A.yP[o] = pressure_head<NF, true, true>(p, s, wt_new, met.zC(k), met.psiz(k));
+        A.yP[o] = pressure_head<NF, true, VG2>(p, s, wt_new, met.zC(k), met.psiz(k));
     }
     if (LAND && has_veg(A)) A.ybeta[c] = beta;
 }
 
-template <int PHYS, int MS, int MODE>
+template <int PHYS, int MS, int MODE, int SOIL = SOIL2_VG2>
 __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler2_min_blocks<PHYS, MODE>())) euler2_kernel(const __grid_constant__ StageArgs<float> A) {
     constexpr bool RICH = phys_richards(PHYS);
     constexpr bool LAND = phys_land(PHYS);
@@ -300,10 +328,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler2_min_blocks<PHYS, MODE
             const F2 sr = lds2(ringS(m));
             F2 ln, wi;
             energy_to_temperature2(p, Ur, sr, Tn, ln, wi);
-            if (RICH) Pn = pressure_head2(p, sr, wtx, met.zC(m), met.psiz(m));
+            if (RICH) Pn = pressure_head2<SOIL>(p, sr, wtx, met.zC(m), met.psiz(m));
             kapn = thermal_conductivity2(p, wi, ln);
             if (RICH) {
-                const F2 Kcn = cell_conductivity2(p, sr, ln);
+                const F2 Kcn = cell_conductivity2s<SOIL>(p, sr, ln);
                 Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : min2(Kcn, rd(EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
                 wr(EF_KC, Kcn);
             }
@@ -416,7 +444,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler2_min_blocks<PHYS, MODE
                     if (!inner && j == nz && A.hio_out) { A.hio_out[c] = Tc.x; if (vy) A.hio_out[c + 1] = Tc.y; }
                     // layers below the water table wait for it (written after the sweep); in a pair with only one column
                     // still below its water table that column's value is overwritten there
-                    if (RICH && (idxx | idxy) != 0) stg2(A.yP + o, pressure_head2(p, sn, wt_new, met.zC(j), met.psiz(j)));
+                    if (RICH && (idxx | idxy) != 0) stg2(A.yP + o, pressure_head2<SOIL>(p, sn, wt_new, met.zC(j), met.psiz(j)));
                 }
             }
         }
@@ -454,7 +482,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler2_min_blocks<PHYS, MODE
         if (!nx) A.ySx[c] = Sx_new.x;
         if (vy && !ny) A.ySx[c + 1] = Sx_new.y;
         // psi_m(sat >= 1) is a constant: (wt - zC) + psat + (zC - zref) is one value for the whole saturated zone
-        const float psat = swrc_inverse<float, true, true>(p, p.por, p.por);
+        const float psat = swrc_inverse<float, true, SOIL == SOIL2_VG2>(p, p.por, p.por);
         const float zref = met.zF(nz + 1);
         const float px = (wt_new.x - zref) + psat, py = (wt_new.y - zref) + psat;
         const int kx = nx ? 0 : (idxx <= nz ? idxx : nz + 1), ky = (ny || !vy) ? 0 : (idxy <= nz ? idxy : nz + 1);   // layers 1 .. k-1 are rewritten
@@ -468,8 +496,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler2_min_blocks<PHYS, MODE
 #pragma unroll 1
         for (; k < kmax; ++k, o += ld) rest[o] = pr;
     }
-    if (nx) euler2_slow_column<MS, MODE, LAND>(A, met, c, Sx_new.x);
-    if (ny && vy) euler2_slow_column<MS, MODE, LAND>(A, met, c + 1, Sx_new.y);
+    if (nx) euler2_slow_column<MS, MODE, LAND, SOIL == SOIL2_VG2>(A, met, c, Sx_new.x);
+    if (ny && vy) euler2_slow_column<MS, MODE, LAND, SOIL == SOIL2_VG2>(A, met, c + 1, Sx_new.y);
 }
 
 }  // namespace trm

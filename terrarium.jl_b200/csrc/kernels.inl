@@ -67,43 +67,46 @@ cudaError_t launch_euler_mode(int mode, const StageArgs<NF>& a, cudaStream_t st)
 }
 #if TRM_FAST
 // Float32, fast math: two columns per thread with packed f32x2 arithmetic (euler2_kernel.cuh)
-template <int PHYS, int MS, int MODE>
+template <int PHYS, int MS, int MODE, int SOIL>
 cudaError_t launch_euler2_variant(const StageArgs<float>& a, cudaStream_t st) {
     constexpr size_t smem = Euler2Smem<MS, MODE>::BYTES;
     static bool configured[64] = {false};
     int dev = 0;
     if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(euler2_kernel<PHYS, MS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(euler2_kernel<PHYS, MS, MODE, SOIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t npairs = (a.ncol + 1) / 2;
     const int64_t nblk = (npairs + TRM_EULER_BLOCK - 1) / TRM_EULER_BLOCK;
-    euler2_kernel<PHYS, MS, MODE><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
+    euler2_kernel<PHYS, MS, MODE, SOIL><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int PHYS>
+template <int PHYS, int SOIL>
 cudaError_t launch_euler2_mode(int mode, const StageArgs<float>& a, cudaStream_t st) {
     const bool compact = a.nz + 3 <= EULER_MS_SMALL;
-    if (mode == MODE_HEUN1) return compact ? launch_euler2_variant<PHYS, EULER_MS_SMALL, MODE_HEUN1>(a, st) : launch_euler2_variant<PHYS, MET_STRIDE, MODE_HEUN1>(a, st);
-    if (mode == MODE_HEUN2) return launch_euler2_variant<PHYS, MET_STRIDE, MODE_HEUN2>(a, st);
-    return compact ? launch_euler2_variant<PHYS, EULER_MS_SMALL, MODE_EULER>(a, st) : launch_euler2_variant<PHYS, MET_STRIDE, MODE_EULER>(a, st);
+    if (mode == MODE_HEUN1) return compact ? launch_euler2_variant<PHYS, EULER_MS_SMALL, MODE_HEUN1, SOIL>(a, st) : launch_euler2_variant<PHYS, MET_STRIDE, MODE_HEUN1, SOIL>(a, st);
+    if (mode == MODE_HEUN2) return launch_euler2_variant<PHYS, MET_STRIDE, MODE_HEUN2, SOIL>(a, st);
+    return compact ? launch_euler2_variant<PHYS, EULER_MS_SMALL, MODE_EULER, SOIL>(a, st) : launch_euler2_variant<PHYS, MET_STRIDE, MODE_EULER, SOIL>(a, st);
 }
-// does the packed kernel cover this launch? (closure fields recomputed; Richards soils: van Genuchten n = 2 for retention
-// curve and conductivity, the compile-time specialisation the packed formulas are written for). TRM_F32X2=0 switches it off.
-inline bool euler2_applies(int phys, int load_aux, const StageArgs<float>& a) {
+// Which packed instantiation covers this launch, -1 for none (closure fields recomputed; Richards soils: van Genuchten n = 2
+// for retention curve and conductivity, or Brooks-Corey with an integer 1 / lambda + linear conductivity -- the reference's
+// default hydraulics). TRM_F32X2=0 switches the packed kernels off.
+inline int euler2_soil(int phys, int load_aux, const StageArgs<float>& a) {
     const char* e = std::getenv("TRM_F32X2");   // (read per launch: tests compare both kernels within one process)
-    if ((e && e[0] == '0') || load_aux) return false;
-    if (!phys_richards(phys)) return true;
-    return a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN;
+    if ((e && e[0] == '0') || load_aux) return -1;
+    if (!phys_richards(phys)) return SOIL2_VG2;
+    if (a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN) return SOIL2_VG2;
+    if (a.p.swrc == TRM_SWRC_BROOKSCOREY && a.p.bc_k > 0 && a.p.unsat_k == TRM_UNSATK_LINEAR) return SOIL2_BC_LINEAR;
+    return -1;
 }
-inline cudaError_t launch_euler2(int phys, int mode, const StageArgs<float>& a, cudaStream_t st) {
+inline cudaError_t launch_euler2(int phys, int mode, int soil, const StageArgs<float>& a, cudaStream_t st) {
     switch (phys) {
-        case PHYS_NOFLOW:   return launch_euler2_mode<PHYS_NOFLOW>(mode, a, st);
-        case PHYS_RICHARDS: return launch_euler2_mode<PHYS_RICHARDS>(mode, a, st);
-        case PHYS_LAND:     return launch_euler2_mode<PHYS_LAND>(mode, a, st);
-        default:            return launch_euler2_mode<PHYS_LAND_NOFLOW>(mode, a, st);
+        case PHYS_NOFLOW:   return launch_euler2_mode<PHYS_NOFLOW, SOIL2_VG2>(mode, a, st);
+        case PHYS_RICHARDS: return soil == SOIL2_VG2 ? launch_euler2_mode<PHYS_RICHARDS, SOIL2_VG2>(mode, a, st) : launch_euler2_mode<PHYS_RICHARDS, SOIL2_BC_LINEAR>(mode, a, st);
+        case PHYS_LAND:     return soil == SOIL2_VG2 ? launch_euler2_mode<PHYS_LAND, SOIL2_VG2>(mode, a, st) : launch_euler2_mode<PHYS_LAND, SOIL2_BC_LINEAR>(mode, a, st);
+        default:            return launch_euler2_mode<PHYS_LAND_NOFLOW, SOIL2_VG2>(mode, a, st);
     }
 }
 #endif
@@ -114,7 +117,8 @@ cudaError_t launch_euler(int phys, int mode, int load_aux, const StageArgs<NF>& 
     if ((uint64_t)a.nz * (uint64_t)a.ld >= (1ull << 32)) return cudaErrorInvalidConfiguration;
 #if TRM_FAST
     if constexpr (std::is_same<NF, float>::value) {
-        if (euler2_applies(phys, load_aux, a)) return launch_euler2(phys, mode, a, st);
+        const int soil = euler2_soil(phys, load_aux, a);
+        if (soil >= 0) return launch_euler2(phys, mode, soil, a, st);
     }
 #endif
     switch (phys * 2 + (load_aux ? 1 : 0)) {

@@ -290,6 +290,7 @@ struct Handle : HandleBase {
         if ((c.albedo_kind | c.radiative | c.turbulent) & ~1 || c.reserved0 != 0) return fail(TRM_ERR_INVALID, "bad albedo_kind / radiative / turbulent code (or reserved0 != 0)");
         p.albedo_kind = c.albedo_kind; p.rad_kind = c.radiative; p.turb_kind = c.turbulent;
         p.vg_n_is_2 = (p.vg_n == NF(2)) ? 1 : 0;
+        { const NF k = 1 / p.bc_lambda; const int ki = (int)std::lround((double)k); p.bc_k = (ki >= 1 && ki <= 8 && NF(ki) == k) ? ki : 0; }
         vp.th_fc = (NF)q.field_capacity; vp.th_wp = (NF)q.wilting_point; vp.C_mass = (NF)q.C_mass;
         vp.tau25 = (NF)q.tau25; vp.Kc25 = (NF)q.Kc25; vp.Ko25 = (NF)q.Ko25; vp.q10_tau = (NF)q.q10_tau; vp.q10_Kc = (NF)q.q10_Kc; vp.q10_Ko = (NF)q.q10_Ko;
         vp.alpha_leaf = (NF)q.alpha_leaf; vp.alpha_a = (NF)q.alpha_a; vp.alpha_C3 = (NF)q.alpha_C3; vp.cq = (NF)q.cq; vp.k_ext = (NF)q.k_ext;
