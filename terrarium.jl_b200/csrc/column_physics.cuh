@@ -182,11 +182,12 @@ struct M<float, true> {
 
 // exp for the fast build (per-column surface / vegetation block: thirteen of them per column). Argument reduction
 // x = n ln2 + r with the round-to-nearest magic constant, degree-13 Taylor polynomial on |r| <= ln2 / 2 (truncation
-// 4e-18), scaling through the exponent field; arguments are clamped to +-700 (no overflow / denormal handling).
+// 4e-18), scaling through the exponent field. The result is clamped to [2^-1000, 2^1000] on the INTEGER exponent n (two
+// integer instructions instead of a NaN-aware Float64 min / max pair: |x| up to 2^31 ln2 still reduces correctly); no overflow
+// to Inf, no denormal handling, NaN / Inf arguments give an unspecified finite or NaN value.
 __device__ __forceinline__ double exp_fast(double x) {
-    x = fmin(fmax(x, -700.0), 700.0);
     const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
-    const int n = __double2loint(t);
+    const int n = max(min(__double2loint(t), 1000), -1000);
     const double nf = t - 6755399441055744.0;
     double r = fma(nf, -6.93147180369123816490e-01, x);
     r = fma(nf, -1.90821492927058770002e-10, r);
@@ -206,6 +207,9 @@ __device__ __forceinline__ double exp_fast(double x) {
     p = fma(p, r, 1.0);
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
+// Julia's NaN-propagating max / min in the faithful build, compare + select in the fast build
+template <class NF, bool FAST> __device__ __forceinline__ NF xmax(NF a, NF b) { return FAST ? M<NF, FAST>::mx(a, b) : jmax(a, b); }
+template <class NF, bool FAST> __device__ __forceinline__ NF xmin(NF a, NF b) { return FAST ? M<NF, FAST>::mn(a, b) : jmin(a, b); }
 template <class NF, bool FAST> __device__ __forceinline__ NF xexp(NF a) { return texp(a); }
 template <> __device__ __forceinline__ double xexp<double, true>(double a) { return exp_fast(a); }
 

@@ -286,7 +286,7 @@ __device__ __forceinline__ void vegetation_surface_impl(const StageArgs<NF>& A, 
     const NF LAI = (fdec * phen + (NF(1.0) - fdec)) * LAIb;
     // MedlynStomatalConductance (stomatal_conductance.jl:45-82): vapour pressure deficit at the air temperature,
     // net assimilation of the PREVIOUS evaluation (vegetation_carbon.jl:89-91)
-    const NF vpd_air = jmax(saturation_vapor_pressure<NF, FAST>(Ta) - ea, NF(0.1));
+    const NF vpd_air = xmax<NF, FAST>(saturation_vapor_pressure<NF, FAST>(Ta) - ea, NF(0.1));
     const NF fapar = 1 - xexp<NF, FAST>(-v.k_ext * LAI);   // also the absorbed fraction of PAR (photosynthesis.jl:124-128)
     const NF g0 = (v.g_min / 1000) * fapar * beta_sm;
     const NF gw = g0 + dv<NF, FAST>(NF(1.6) * (1 + dv<NF, FAST>(v.g1, M<NF, FAST>::sqrt_(vpd_air))) * An_prev, co2) * NF(1.0e6);
@@ -310,14 +310,14 @@ __device__ __forceinline__ void vegetation_surface_impl(const StageArgs<NF>& A, 
     const NF wmax = v.w_can_max * (LAI + SAI);
     const NF f_can = wmax > 0 ? dv<NF, FAST>(wcan, wmax) : NF(0);
     const NF I_can = v.alpha_int * rain * (NF(1) - xexp<NF, FAST>(-v.k_ext_can * (LAI + SAI)));
-    const NF R_can = jmax(wcan, NF(0)) / v.tau_w;
+    const NF R_can = xmax<NF, FAST>(wcan, NF(0)) / v.tau_w;
     const NF rain_ground = rain - I_can + R_can;
     // PALADYNCanopyEvapotranspiration (canopy_evapotranspiration.jl:51-177): humidity gradients at the skin and at
     // the ground temperature, resistance between ground and canopy, stomatal resistance
     const NF esg = saturation_vapor_pressure<NF, FAST>(T_top);
-    const NF dqg = dv<NF, FAST>(p.eps_mw * jmax(esg - ea, NF(0.1)), pres);
+    const NF dqg = dv<NF, FAST>(p.eps_mw * xmax<NF, FAST>(esg - ea, NF(0.1)), pres);
     const NF re = dv<NF, FAST>(1 - xexp<NF, FAST>(-LAI - SAI), v.C_can * Vc);
-    const NF rs = dv<NF, FAST>(NF(1), jmax(gw, tsqrt(Lim<NF>::eps())));
+    const NF rs = dv<NF, FAST>(NF(1), xmax<NF, FAST>(gw, tsqrt(Lim<NF>::eps())));
     const NF transp = (NF)dv<double, FAST>((double)dq, ra + (double)rs);
     const NF Egnd = (NF)dv<double, FAST>((double)(beta_g * dqg), ra + (double)re);
     const NF E_can = (NF)dv<double, FAST>((double)(f_can * dq), ra);
@@ -327,7 +327,7 @@ __device__ __forceinline__ void vegetation_surface_impl(const StageArgs<NF>& A, 
     NF k[3];
     k[2] = I_can - E_can - R_can;
     k[0] = (NF(1.0) - lam) * NPP - (v.gamma_L / v.SLA + v.gamma_R / v.SLA + v.gamma_S * v.awl) * LAIb;
-    const NF nus = jmax(nu, v.nu_seed);
+    const NF nus = xmax<NF, FAST>(nu, v.nu_seed);
     k[1] = dv<NF, FAST>(lam * NPP, Cv) * nus * (NF(1.0) - nu) - v.gamma_v * nus;
     if (A.mode == MODE_EULER || A.mode == MODE_HEUN1 || A.mode == MODE_HEUN2) {
 #pragma unroll
@@ -388,7 +388,7 @@ __device__ __forceinline__ void land_surface_impl(const StageArgs<NF>& A, int64_
     if (p.rad_kind == TRM_RADIATIVE_PRESCRIBED) { a.swu_in = surface_input(A.in[TRM_IN_SHORTWAVE_UP], c, A.t_x); a.lwu_in = surface_input(A.in[TRM_IN_LONGWAVE_UP], c, A.t_x); }
     if (p.turb_kind == TRM_TURBULENT_PRESCRIBED) { a.hs_in = surface_input(A.in[TRM_IN_SENSIBLE_HEAT_FLUX], c, A.t_x); a.hl_in = surface_input(A.in[TRM_IN_LATENT_HEAT_FLUX], c, A.t_x); }
     // aerodynamic_resistance, prescribed_atmosphere.jl:110-116,137 (Float64 literal 1.0e-6 promotes)
-    NF Vc = jmax(a.V, p.Vmin);
+    NF Vc = xmax<NF, FAST>(a.V, p.Vmin);
     double Va = fmax((double)Vc, 1.0e-6);
     a.ra = dv<double, FAST>(1.0, (double)p.C_h * Va);
     NF Ts = Ts0;
@@ -397,7 +397,7 @@ __device__ __forceinline__ void land_surface_impl(const StageArgs<NF>& A, int64_
     NF Tsurf = prescribed ? a.Tskin_in : Ts;
     NF es = saturation_vapor_pressure<NF, FAST>(Tsurf);
     NF ea = dv<NF, FAST>(a.q * a.pres, p.eps_mw + (1 - p.eps_mw) * a.q);
-    NF vpd = jmax(es - ea, NF(0.1));
+    NF vpd = xmax<NF, FAST>(es - ea, NF(0.1));
     NF dq = dv<NF, FAST>(p.eps_mw * vpd, a.pres);
     // ground evaporation resistance factor, ground_resistance_factor.jl:6-11 (constant) / :32-57 (soil moisture limited)
     NF beta_g = p.beta;
@@ -420,8 +420,8 @@ __device__ __forceinline__ void land_surface_impl(const StageArgs<NF>& A, int64_
     }
     // DirectSurfaceRunoff, direct_surface_runoff.jl:87-117 ; K_top = Kf[Nz]
     NF drain, inf;
-    if (S > 0) { drain = dv<NF, FAST>(jmax(S, NF(0)), p.tau_r); inf = (sat_top < 1) ? jmin(drain, K_top) : NF(0); }
-    else { drain = 0; inf = (sat_top < 1) ? jmin(rain_ground, K_top) : NF(0); }
+    if (S > 0) { drain = dv<NF, FAST>(xmax<NF, FAST>(S, NF(0)), p.tau_r); inf = (sat_top < 1) ? xmin<NF, FAST>(drain, K_top) : NF(0); }
+    else { drain = 0; inf = (sat_top < 1) ? xmin<NF, FAST>(rain_ground, K_top) : NF(0); }
     NF runoff = rain_ground + drain - inf;
     // surface energy balance kernel, executed twice (land_model.jl:85-86) ; the latent heat flux follows the humidity
     // flux of the evapotranspiration scheme (turbulent_fluxes.jl:137-150)
