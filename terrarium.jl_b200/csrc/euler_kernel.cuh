@@ -91,6 +91,15 @@ static_assert(TRM_EULER_DIST >= 1 && TRM_EULER_DIST <= 5, "the U / sat ring hold
 constexpr int EULER_RD = 8;   // depth of the U / sat ring: layer k stays in slot (k & 7) from its prefetch (iteration
                               // k-3) until it is updated (iteration k+2), so the raw values are never copied
 
+// position of a pipeline iteration in the column (see `iterate`): IP_GEN = layer-index tests at run time ; the others make
+// them compile-time constants: m = 1, 2, 3 ; 4 <= m <= nz-DIST (the layer DIST ahead exists: prefetch) ; nz-DIST < m < nz ;
+// m = nz (top layer enters) ; m = nz+1 (halo above the surface) ; m = nz+2 (top layer is updated). Needs nz >= 4.
+enum IterPos { IP_GEN = 0, IP_M1, IP_M2, IP_M3, IP_INNER, IP_INNER_NP, IP_NZ, IP_HALO, IP_LAST };
+template <int P> using IterTag = std::integral_constant<int, P>;
+#ifndef TRM_EULER_SPEC
+#define TRM_EULER_SPEC 1
+#endif
+
 constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 6 blocks per SM resident)
 
 // MODE: which timestepper stage the launch is (subset of StageMode): MODE_EULER, MODE_HEUN1 (stage state and k1 out,
@@ -192,6 +201,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     constexpr int DIST_ = euler_dist(MODE), PF_ = euler_pf(MODE);
     constexpr bool CLOSE = !H1;    // Heun stage 1 leaves the closure fields of the stage state to stage 2 (recomputed there)
     constexpr bool RC = heun_recompute<NF>() && (H1 || H2);   // Heun "recompute" protocol (see heun_recompute)
+    // one instantiation of the loop body per position in the column (hot configurations only: code size / build time)
+    constexpr bool SPEC = TRM_EULER_SPEC && FAST && !LOAD && (MS == EULER_MS_SMALL || H2);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nz = A.nz;
@@ -300,16 +311,30 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) tS += bc_input(TRM_BC_SATURATION_BOTTOM) / met.dzc(1);
     };
 
-    // One pipeline iteration. `inner` (compile time) marks the iterations 4 <= m <= nz-DIST, for which every
-    // layer-index special case below is statically false / true: no halo, no boundary face, no Flux BC, the
-    // prefetched layer exists. The two instantiations share the source; the loop picks the cheap one whenever it can.
-    auto iterate = [&](const int m, auto inner_tag) {
-        constexpr bool inner = decltype(inner_tag)::value;
-        prefetch(m + DIST_, inner);
+    // One pipeline iteration. The position tag (compile time, enum IterPos) says where in the column the iteration sits,
+    // so that every layer-index special case below (halo, boundary face, Flux BC, does the prefetched layer exist) is
+    // statically false / true; IP_GEN keeps them as run-time tests on m (columns of fewer than four layers, faithful
+    // math). All instantiations share this source.
+    auto iterate = [&](const int m, auto pos_tag) {
+        constexpr int POS = decltype(pos_tag)::value;
+        constexpr bool GEN = POS == IP_GEN;
+        const bool m_is_1 = GEN ? m == 1 : POS == IP_M1;
+        const bool m_is_nz = GEN ? m == nz : POS == IP_NZ;
+        const bool enters = GEN ? m <= nz : POS <= IP_NZ;             // layer m exists and enters the pipeline
+        const bool is_halo = GEN ? m == nz + 1 : POS == IP_HALO;      // the halo cell above the surface enters
+        const bool has_face = GEN ? m <= nz + 1 : POS != IP_LAST;     // face m carries a heat flux / head gradient
+        const bool has_darcy = GEN ? m >= 2 : POS != IP_M1;           // face m-1 carries a Darcy flux
+        const bool updates = GEN ? m >= 3 : POS >= IP_M3;             // layer j = m-2 is updated
+        const bool j_is_1 = GEN ? m == 3 : POS == IP_M3;
+        const bool j_is_nz = GEN ? m == nz + 2 : POS == IP_LAST;
+        const bool j_ge_2 = GEN ? m >= 4 : POS > IP_M3;
+        if (POS == IP_INNER) prefetch(m + DIST_, true);
+        else if (POS >= IP_INNER_NP && !(H2 && !RC)) cp_async_commit();   // nothing left to prefetch: the (empty) group keeps the count in step
+        else prefetch(m + DIST_, false);
         // ---- layer m (or the halo above the surface) enters the pipeline ----
         NF Tn, Pn = NF(0), kapn, Kfn = NF(0);     // T, psi, kappa of layer m ; Kf[m]
         const NF Kf1 = RICH ? ldsv(kf_prv, (NF*)nullptr) : NF(0);   // Kf[m-1]
-        if (inner || m <= nz) {
+        if (enters) {
             cp_async_wait<DIST_>();   // all but the DIST most recent groups have landed: layer m is in the ring
             NF Ur = ldsv(ringU(m), (NF*)nullptr);
             NF sr = ldsv(ringS(m), (NF*)nullptr);
@@ -319,20 +344,20 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (flagged) { Ur = A.sU[oent]; sr = A.sS[oent]; }
                 else {
                     NF t1U = ldsv(k1U_slot(m), (NF*)nullptr), t1S = RICH ? ldsv(k1S_slot(m), (NF*)nullptr) : NF(0);
-                    if (!inner && m == nz) apply_top_flux(t1U, t1S);
-                    if (!inner && m == 1) apply_bottom_flux(t1U, t1S);
+                    if (m_is_nz) apply_top_flux(t1U, t1S);
+                    if (m_is_1) apply_bottom_flux(t1U, t1S);
                     Ur = Ur + t1U * dt;
                     if (RICH) {
                         sr = sr + t1S * dt;
                         sr = sr + carry1;
-                        if (inner || m < nz) {
+                        if (!m_is_nz) {
                             const NF e = Mx::pos(sr - 1);
                             sr -= e;
                             carry1 = FAST ? e * met.dzc(m) * met.rdzc(m + 1) : e * met.dzc(m) / met.dzc(m + 1);
                         }
-                        if (!FAST && m >= 2) sr = sr + jmax(-sr, NF(0));
-                        if (!inner && m == nz) sr -= Mx::pos(sr - 1);       // top excess of the stage copy (its surface excess water is not used)
-                        if (!FAST && !inner && m == 1) sr = jmax(sr, NF(0));
+                        if (!FAST && !m_is_1) sr = sr + jmax(-sr, NF(0));
+                        if (m_is_nz) sr -= Mx::pos(sr - 1);       // top excess of the stage copy (its surface excess water is not used)
+                        if (!FAST && m_is_1) sr = jmax(sr, NF(0));
                     }
                 }
                 oent += (uint32_t)ld;
@@ -351,10 +376,10 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
             if (RICH) {
                 // cell conductivity and face conductivity Kf[m], soil_hydrology.jl:249-276
                 const NF Kcn = cell_conductivity<NF, FAST, VG2>(p, sr, ln);
-                Kfn = (!inner && (m == 1 || m == nz)) ? Kcn : Mx::mn(Kcn, rd(EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
+                Kfn = (m_is_1 || m_is_nz) ? Kcn : Mx::mn(Kcn, rd(EF_KC));   // Kf[1] = Kc[1], Kf[Nz] = Kc[Nz]
                 wr(EF_KC, Kcn);
             }
-        } else if (!inner && m == nz + 1) {   // halo above the surface, built from layer nz (prv)
+        } else if (is_halo) {   // halo above the surface, built from layer nz (prv)
             Tn = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(EF_T), bct_pre ? rd(EF_BCT) : bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
             // conductivity of the halo cell: same (sat, liq) as layer nz when the saturation halo is a copy, else
             // sat = 0, for which the liquid fraction drops out of the constituent sum
@@ -367,7 +392,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
         // ---- lower neighbour of layer m: layer m-1, or the halo below the bottom layer for m = 1 ----
         NF Tp, kapp, Pp = NF(0);
-        if (!inner && m == 1) {
+        if (m_is_1) {
             Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, Tn, bc_input(TRM_BC_TEMPERATURE_BOTTOM), met.dzf(1), false);
             const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
             kapp = copy ? kapn : (FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)));
@@ -378,14 +403,14 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
         // ---- heat flux and head gradient at face m (diffusive_heat_flux, soil_energy.jl:134-149) ----
         NF qhn = NF(0), gn = NF(0);
-        if (inner || m <= nz + 1) {
+        if (has_face) {
             qhn = -((kapn + kapp) / 2) * ((Tn - Tp) * met.rdzf(m));
             if (RICH) gn = (Pn - Pp) * met.rdzf(m);
         }
         const NF dqhn = qhn - rd(EF_QH);
         // ---- Darcy flux at face m-1 (darcy_flux, soil_hydrology_rre.jl:119-131) ----
         NF qdn = NF(0);
-        if (RICH && (inner || m >= 2)) {
+        if (RICH && has_darcy) {
             const NF g = rd(EF_G);
             const NF Kf2 = ldsv(kf_cur, (NF*)nullptr);   // Kf[m-2] (0 for m = 2: Kf[0] is never written by the reference)
             NF Kk;
@@ -398,7 +423,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         // (LandModel: the fluxes coupling the surface to the top soil layer were evaluated by surface_kernel on the time-n
         //  state; Heun stage 2 applies the same time-n fluxes, heun.jl:63-66 -- see apply_top_flux)
 
-        if (inner || m >= 3) {
+        if (updates) {
             // ---- tendencies of layer j = m-2 ----
             const int j = m - 2;
             const uint32_t o = oout;
@@ -424,8 +449,8 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 if (H1) { A.oTU[o] = tU; if (RICH) A.oTS[o] = tS; }   // k1, before the Flux BCs
                 Ub = ldsv(ringU(j), (NF*)nullptr); sb = ldsv(ringS(j), (NF*)nullptr);
             }
-            if (!inner && j == nz) apply_top_flux(tU, tS);
-            if (!inner && j == 1) apply_bottom_flux(tU, tS);
+            if (j_is_nz) apply_top_flux(tU, tS);
+            if (j_is_1) apply_bottom_flux(tU, tS);
             // ---- explicit step, abstract_timestepper.jl:113-141 ----
             const NF Un = Ub + tU * dt;
             NF sn = sb;
@@ -433,34 +458,35 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                 sn = sn + tS * dt;
                 // ---- adjust_saturation_profile!, upward sweep (soil_hydrology.jl:192-199) ----
                 sn = sn + carry;
-                if (inner || j < nz) {
+                if (!j_is_nz) {
                     const NF e = Mx::pos(sn - 1);
                     sn -= e;
                     carry = FAST ? e * met.dzc(j) * met.rdzc(j + 1) : e * met.dzc(j) / met.dzc(j + 1);
                 }
                 if (FAST) neg_acc |= sign_word(sn); else if (sn < 0) neg_acc = -1;
             }
-            // (fast math, inner layers: the regular stores below ARE the raw values the slow path re-reads -- no
+            // (fast math, every layer but the top one: the regular stores below ARE the raw values the slow path re-reads -- no
             //  surface excess, no clamp -- so the flag needs no branch here; the closure stores are overwritten later)
             // (recompute protocol, Heun stage 1: the stage state is not stored -- except its top layer, which the vegetation
             //  block of stage 2 reads through surface_kernel -- and a column that goes negative rebuilds it in its slow path)
             constexpr bool STORE = !(H1 && RC);
-            if (!STORE && !inner && j == nz) A.yU[o] = Un;
-            if (RICH && !(inner && FAST) && any_neg()) {
+            if (!STORE && j_is_nz) A.yU[o] = Un;
+            const bool raw_is_regular = FAST && (GEN ? false : !j_is_nz);
+            if (RICH && !raw_is_regular && any_neg()) {
                 // raw values for the slow path below (the downward sweep needs the whole profile)
                 if (STORE) { A.yU[o] = Un; A.yS[o] = sn; }
             } else {
                 if (RICH) {
                     // downward sweep with no deficit anywhere: sat += max(-sat, 0) (:201-208) is the identity
-                    if (!FAST && j >= 2) sn = sn + jmax(-sn, NF(0));
-                    if (!inner && j == nz) {                         // top excess -> surface_excess_water (:210-214)
+                    if (!FAST && j_ge_2) sn = sn + jmax(-sn, NF(0));
+                    if (j_is_nz) {                         // top excess -> surface_excess_water (:210-214)
                         const NF e = Mx::pos(sn - 1);
                         sn -= e;
                         Sx_new += e * met.dzc(nz);
                     }
-                    if (!FAST && !inner && j == 1) sn = jmax(sn, NF(0));       // :216
+                    if (!FAST && j_is_1) sn = jmax(sn, NF(0));       // :216
                     if (STORE) stg(A.yS + o, sn);
-                    else if (!inner && j == nz) A.yS[o] = sn;                  // (top layer, after the top excess went to the surface)
+                    else if (j_is_nz) A.yS[o] = sn;                  // (top layer, after the top excess went to the surface)
                     if (idx == 0 && (FAST ? below_one(sn) : sn < 1)) { idx = j; wt_new = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                 }
                 if (STORE) stg(A.yU + o, Un);
@@ -474,7 +500,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
                                                         : plant_available_water(A.vp, p, sn, lc) * met.root(j) / met.dzc(j) * met.dzc(j)));
                     if (CLOSE) {
                         stg(A.yT + o, Tc); stg(A.yL + o, lc);
-                        if (!inner && j == nz && A.hio_out) A.hio_out[c] = Tc;   // ground temperature -> mapped host memory
+                        if (j_is_nz && A.hio_out) A.hio_out[c] = Tc;   // ground temperature -> mapped host memory
                         // layers below the water table wait for it (written after the sweep)
                         if (RICH && idx != 0) stg(A.yP + o, pressure_head<NF, FAST, VG2>(p, sn, wt_new, met.zC(j), met.psiz(j)));
                     }
@@ -486,15 +512,23 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         if (RICH) { wr(EF_P, Pn); sts(kf_cur, Kfn); wr(EF_G, gn); wr(EF_QD, qdn); }
         const uint32_t t = kf_cur; kf_cur = kf_prv; kf_prv = t;
     };
-    {
+    if (SPEC && nz >= 4) {
+        iterate(1, IterTag<IP_M1>{}); iterate(2, IterTag<IP_M2>{}); iterate(3, IterTag<IP_M3>{});
+        int m = 4;
+#pragma unroll 1
+        for (; m <= nz - DIST_; ++m) iterate(m, IterTag<IP_INNER>{});
+#pragma unroll 1
+        for (; m < nz; ++m) iterate(m, IterTag<IP_INNER_NP>{});
+        iterate(nz, IterTag<IP_NZ>{}); iterate(nz + 1, IterTag<IP_HALO>{}); iterate(nz + 2, IterTag<IP_LAST>{});
+    } else {
         int m = 1;
 #pragma unroll 1
         while (m <= nz + 2) {
             if (m >= 4 && m <= nz - DIST_) {
 #pragma unroll 1
-                do { iterate(m, std::true_type{}); ++m; } while (m <= nz - DIST_);
+                do { iterate(m, IterTag<IP_INNER>{}); ++m; } while (m <= nz - DIST_);
             } else {
-                iterate(m, std::false_type{});
+                iterate(m, IterTag<IP_GEN>{});
                 ++m;
             }
         }
