@@ -100,7 +100,8 @@ template <int P> using IterTag = std::integral_constant<int, P>;
 #define TRM_EULER_SPEC 1
 #endif
 
-constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 6 blocks per SM resident)
+constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37: read from the kernel parameters, no shared-memory copy
+static_assert(EULER_MS_SMALL == CMET_STRIDE, "the compact variants read StageArgs::cmet");
 
 // MODE: which timestepper stage the launch is (subset of StageMode): MODE_EULER, MODE_HEUN1 (stage state and k1 out,
 // no closure fields), MODE_HEUN2 (tendencies evaluated on the stage state, averaged with k1, applied to the base state:
@@ -108,7 +109,8 @@ constexpr int EULER_MS_SMALL = 40;   // compact metric rows for nz <= 37 (keeps 
 template <class NF, int LOAD, int MS, int MODE = MODE_EULER>
 struct EulerSmem {
     static constexpr int PF_ = euler_pf(MODE);
-    static constexpr int METRICS = MET_COUNT * MS;                                    // elements (the root fraction row is only filled by LandModel kernels)
+    static constexpr bool CMET = MS == EULER_MS_SMALL;                                // compact rows: read from the kernel parameters (MetricsC)
+    static constexpr int METRICS = CMET ? 0 : MET_COUNT * MS;                         // elements (the root fraction row is only filled by LandModel kernels)
     static constexpr int STRIP = EF_COUNT * TRM_EULER_BLOCK;
     static constexpr int RING = (2 * EULER_RD + (LOAD ? 3 : 0) * PF_) * TRM_EULER_BLOCK;   // U, sat (, T, liq, psi)
     // Heun stage 2: k1U, k1S, bU, bS of the layer to be updated (stored protocol) / k1U, k1S next to U, sat (recompute protocol)
@@ -120,8 +122,8 @@ struct EulerSmem {
 // stage copy needs the downward sweep of adjust_saturation_profile! (soil_hydrology.jl:201-216), which stage 2 cannot rebuild
 // layer by layer. The column's stage state is formed here in full from the base state and the k1 this thread has just stored
 // (explicit_step! with the time-n Flux BCs, upward sweep, downward sweep), written to yU / yS, and the column is flagged.
-template <class NF, bool FAST, int MS, bool LAND>
-__device__ __noinline__ void heun1_slow_column(const StageArgs<NF>& A, Metrics<NF, MS> met, int64_t c) {
+template <class NF, bool FAST, class Met, bool LAND>
+__device__ __noinline__ void heun1_slow_column(const StageArgs<NF>& A, Met met, int64_t c) {
     const DevParams<NF>& p = A.p;
     const int nz = A.nz;
     const int64_t ld = A.ld;
@@ -206,14 +208,17 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nz = A.nz;
-    {
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    using Met = std::conditional_t<SM::CMET, MetricsC<NF>, Metrics<NF, MS>>;
+    Met met;
+    if constexpr (SM::CMET) met.A = &A;
+    else {
         NF* sm = reinterpret_cast<NF*>(smem_raw);
         for (int q = 0; q < met_rows(LAND); ++q)
             for (int i = threadIdx.x; i < nz + 3; i += B) sm[q * MS + i] = A.metrics[q * MET_STRIDE + i];
+        __syncthreads();
+        met.base = smem_base;
     }
-    __syncthreads();
-    Metrics<NF, MS> met;
-    met.base = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
     const int64_t c = (int64_t)blockIdx.x * B + threadIdx.x;
     if (c >= A.ncol) return;
@@ -222,9 +227,9 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
     const NF dt = A.dt;
 
     // shared addresses of this thread's strip: field f is  strip0 + f * B * ES ; the two Kf slots alternate
-    const uint32_t strip0 = met.base + (uint32_t)((SM::METRICS + threadIdx.x) * ES);
+    const uint32_t strip0 = smem_base + (uint32_t)((SM::METRICS + threadIdx.x) * ES);
     uint32_t kf_cur = strip0 + B * ES, kf_prv = strip0;   // Kf[m] is written to kf_cur, which still holds Kf[m-2] ; kf_prv holds Kf[m-1]
-    const uint32_t ring0 = met.base + (uint32_t)((SM::METRICS + SM::STRIP + threadIdx.x) * ES);
+    const uint32_t ring0 = smem_base + (uint32_t)((SM::METRICS + SM::STRIP + threadIdx.x) * ES);
     auto rd = [&](int f) { return ldsv(strip0 + (uint32_t)(f * B * ES), (NF*)nullptr); };
     auto wr = [&](int f, NF v) { sts(strip0 + (uint32_t)(f * B * ES), v); };
     // U and sat of layer k while it is in flight (iterations k-3 .. k+2)
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(TRM_EULER_BLOCK, (euler_min_blocks<NF, PHYS, F
         }
         return;
     }
-    if (H1 && RC) { heun1_slow_column<NF, FAST, MS, LAND>(A, met, c); return; }
+    if (H1 && RC) { heun1_slow_column<NF, FAST, Met, LAND>(A, met, c); return; }
     // ---- slow path: a layer went negative. Downward sweep (soil_hydrology.jl:201-216) top -> bottom on the raw
     //      profile this thread just stored, then water table and closures bottom -> top. ----
     {

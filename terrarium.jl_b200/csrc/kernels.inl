@@ -66,48 +66,59 @@ cudaError_t launch_euler_mode(int mode, const StageArgs<NF>& a, cudaStream_t st)
                    : launch_euler_variant<NF, PHYS, LOAD, MET_STRIDE, MODE_EULER>(a, st);
 }
 #if TRM_FAST
-// Float32, fast math: two columns per thread with packed f32x2 arithmetic (euler2_kernel.cuh)
-template <int PHYS, int MS, int MODE, int SOIL>
-cudaError_t launch_euler2_variant(const StageArgs<float>& a, cudaStream_t st) {
-    constexpr size_t smem = Euler2Smem<MS, MODE>::BYTES;
+// fast math: two columns per thread (euler2_kernel.cuh) -- Float32 with packed f32x2 arithmetic, every timestepper stage ;
+// Float64 with 16-byte accesses, ForwardEuler stage (the Heun stages of Float64 run the recompute protocol of euler_kernel)
+template <class T, int PHYS, int MS, int MODE, int SOIL>
+cudaError_t launch_euler2_variant(const StageArgs<T>& a, cudaStream_t st) {
+    constexpr size_t smem = Euler2Smem<T, MS, MODE, phys_land(PHYS)>::BYTES;
     static bool configured[64] = {false};
     int dev = 0;
     if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(euler2_kernel<PHYS, MS, MODE, SOIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(euler2_kernel<T, PHYS, MS, MODE, SOIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t npairs = (a.ncol + 1) / 2;
-    const int64_t nblk = (npairs + TRM_EULER_BLOCK - 1) / TRM_EULER_BLOCK;
-    euler2_kernel<PHYS, MS, MODE, SOIL><<<(unsigned)nblk, TRM_EULER_BLOCK, smem, st>>>(a);
+    const int64_t nblk = (npairs + euler2_block<T>() - 1) / euler2_block<T>();
+    euler2_kernel<T, PHYS, MS, MODE, SOIL><<<(unsigned)nblk, euler2_block<T>(), smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int PHYS, int SOIL>
-cudaError_t launch_euler2_mode(int mode, const StageArgs<float>& a, cudaStream_t st) {
+template <class T, int PHYS, int SOIL>
+cudaError_t launch_euler2_mode(int mode, const StageArgs<T>& a, cudaStream_t st) {
     const bool compact = a.nz + 3 <= EULER_MS_SMALL;
-    if (mode == MODE_HEUN1) return compact ? launch_euler2_variant<PHYS, EULER_MS_SMALL, MODE_HEUN1, SOIL>(a, st) : launch_euler2_variant<PHYS, MET_STRIDE, MODE_HEUN1, SOIL>(a, st);
-    if (mode == MODE_HEUN2) return launch_euler2_variant<PHYS, MET_STRIDE, MODE_HEUN2, SOIL>(a, st);
-    return compact ? launch_euler2_variant<PHYS, EULER_MS_SMALL, MODE_EULER, SOIL>(a, st) : launch_euler2_variant<PHYS, MET_STRIDE, MODE_EULER, SOIL>(a, st);
+    if constexpr (sizeof(T) == 4) {
+        if (mode == MODE_HEUN1) return compact ? launch_euler2_variant<T, PHYS, EULER_MS_SMALL, MODE_HEUN1, SOIL>(a, st) : launch_euler2_variant<T, PHYS, MET_STRIDE, MODE_HEUN1, SOIL>(a, st);
+        if (mode == MODE_HEUN2) return launch_euler2_variant<T, PHYS, MET_STRIDE, MODE_HEUN2, SOIL>(a, st);
+    }
+    return compact ? launch_euler2_variant<T, PHYS, EULER_MS_SMALL, MODE_EULER, SOIL>(a, st) : launch_euler2_variant<T, PHYS, MET_STRIDE, MODE_EULER, SOIL>(a, st);
 }
-// Which packed instantiation covers this launch, -1 for none (closure fields recomputed; Richards soils: van Genuchten n = 2
+// Which pair instantiation covers this launch, -1 for none (closure fields recomputed; Richards soils: van Genuchten n = 2
 // for retention curve and conductivity, or Brooks-Corey with an integer 1 / lambda + linear conductivity -- the reference's
-// default hydraulics). TRM_F32X2=0 switches the packed kernels off.
-inline int euler2_soil(int phys, int load_aux, const StageArgs<float>& a) {
-    const char* e = std::getenv("TRM_F32X2");   // (read per launch: tests compare both kernels within one process)
+// default hydraulics). TRM_F32X2=0 / TRM_F64X2=0 switch the pair kernels of a number format off.
+template <class T>
+inline int euler2_soil(int phys, int mode, int load_aux, const StageArgs<T>& a) {
+    const char* e = std::getenv(sizeof(T) == 4 ? "TRM_F32X2" : "TRM_F64X2");   // (read per launch: tests compare both kernels within one process)
     if ((e && e[0] == '0') || load_aux) return -1;
+    if (sizeof(T) == 8 && mode != MODE_EULER) return -1;
     if (!phys_richards(phys)) return SOIL2_VG2;
     if (a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN) return SOIL2_VG2;
     if (a.p.swrc == TRM_SWRC_BROOKSCOREY && a.p.bc_k > 0 && a.p.unsat_k == TRM_UNSATK_LINEAR) return SOIL2_BC_LINEAR;
     return -1;
 }
-inline cudaError_t launch_euler2(int phys, int mode, int soil, const StageArgs<float>& a, cudaStream_t st) {
+template <class T>
+inline cudaError_t launch_euler2(int phys, int mode, int soil, const StageArgs<T>& a, cudaStream_t st) {
+#ifdef TRM_DEV_MIN   // (kernel tuning builds, profiles/build_variant.sh: only the instantiations of the soil benchmark)
+    if (phys != PHYS_RICHARDS || soil != SOIL2_VG2) return cudaErrorInvalidConfiguration;
+    return launch_euler2_mode<T, PHYS_RICHARDS, SOIL2_VG2>(mode, a, st);
+#else
     switch (phys) {
-        case PHYS_NOFLOW:   return launch_euler2_mode<PHYS_NOFLOW, SOIL2_VG2>(mode, a, st);
-        case PHYS_RICHARDS: return soil == SOIL2_VG2 ? launch_euler2_mode<PHYS_RICHARDS, SOIL2_VG2>(mode, a, st) : launch_euler2_mode<PHYS_RICHARDS, SOIL2_BC_LINEAR>(mode, a, st);
-        case PHYS_LAND:     return soil == SOIL2_VG2 ? launch_euler2_mode<PHYS_LAND, SOIL2_VG2>(mode, a, st) : launch_euler2_mode<PHYS_LAND, SOIL2_BC_LINEAR>(mode, a, st);
-        default:            return launch_euler2_mode<PHYS_LAND_NOFLOW, SOIL2_VG2>(mode, a, st);
+        case PHYS_NOFLOW:   return launch_euler2_mode<T, PHYS_NOFLOW, SOIL2_VG2>(mode, a, st);
+        case PHYS_RICHARDS: return soil == SOIL2_VG2 ? launch_euler2_mode<T, PHYS_RICHARDS, SOIL2_VG2>(mode, a, st) : launch_euler2_mode<T, PHYS_RICHARDS, SOIL2_BC_LINEAR>(mode, a, st);
+        case PHYS_LAND:     return soil == SOIL2_VG2 ? launch_euler2_mode<T, PHYS_LAND, SOIL2_VG2>(mode, a, st) : launch_euler2_mode<T, PHYS_LAND, SOIL2_BC_LINEAR>(mode, a, st);
+        default:            return launch_euler2_mode<T, PHYS_LAND_NOFLOW, SOIL2_VG2>(mode, a, st);
     }
+#endif
 }
 #endif
 
@@ -116,10 +127,14 @@ cudaError_t launch_euler(int phys, int mode, int load_aux, const StageArgs<NF>& 
     // the kernel addresses layers with 32-bit element offsets; larger fields run the generic streaming kernel
     if ((uint64_t)a.nz * (uint64_t)a.ld >= (1ull << 32)) return cudaErrorInvalidConfiguration;
 #if TRM_FAST
-    if constexpr (std::is_same<NF, float>::value) {
-        const int soil = euler2_soil(phys, load_aux, a);
-        if (soil >= 0) return launch_euler2(phys, mode, soil, a, st);
+    {
+        const int soil = euler2_soil<NF>(phys, mode, load_aux, a);
+        if (soil >= 0) return launch_euler2<NF>(phys, mode, soil, a, st);
     }
+#endif
+#ifdef TRM_DEV_MIN
+    if (phys != PHYS_RICHARDS) return cudaErrorInvalidConfiguration;
+    return load_aux ? launch_euler_mode<NF, PHYS_RICHARDS, 1>(mode, a, st) : launch_euler_mode<NF, PHYS_RICHARDS, 0>(mode, a, st);
 #endif
     switch (phys * 2 + (load_aux ? 1 : 0)) {
         case 0: return launch_euler_mode<NF, PHYS_NOFLOW, 0>(mode, a, st);

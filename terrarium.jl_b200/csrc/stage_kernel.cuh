@@ -53,18 +53,31 @@ __host__ __device__ constexpr int met_rows(bool land) { return land ? MET_COUNT 
 // rebuild the shared window base (S2R SR_CgaCtaId + LEA) in front of every access when registers are tight.
 __device__ __forceinline__ float  lds(uint32_t a, float*)  { float v;  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double lds(uint32_t a, double*) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+#define TRM_METRIC_ACCESSORS \
+    __device__ __forceinline__ NF zF(int k) const { return get(MET_ZF, k); } \
+    __device__ __forceinline__ NF zC(int k) const { return get(MET_ZC, k); } \
+    __device__ __forceinline__ NF dzc(int k) const { return get(MET_DZC, k); } \
+    __device__ __forceinline__ NF rdzc(int k) const { return get(MET_RDZC, k); } \
+    __device__ __forceinline__ NF dzf(int k) const { return get(MET_DZF, k); } \
+    __device__ __forceinline__ NF rdzf(int k) const { return get(MET_RDZF, k); } \
+    __device__ __forceinline__ NF psiz(int k) const { return get(MET_PSIZ, k); } \
+    __device__ __forceinline__ NF root(int k) const { return get(MET_ROOT, k); }
 template <class NF, int STRIDE = MET_STRIDE>
 struct Metrics {
     uint32_t base;   // shared address of the metric table (rows of STRIDE values)
     __device__ __forceinline__ NF get(int q, int k) const { return lds(base + (uint32_t)((q * STRIDE + k) * (int)sizeof(NF)), (NF*)nullptr); }
-    __device__ __forceinline__ NF zF(int k) const { return get(MET_ZF, k); }
-    __device__ __forceinline__ NF zC(int k) const { return get(MET_ZC, k); }
-    __device__ __forceinline__ NF dzc(int k) const { return get(MET_DZC, k); }
-    __device__ __forceinline__ NF rdzc(int k) const { return get(MET_RDZC, k); }
-    __device__ __forceinline__ NF dzf(int k) const { return get(MET_DZF, k); }
-    __device__ __forceinline__ NF rdzf(int k) const { return get(MET_RDZF, k); }
-    __device__ __forceinline__ NF psiz(int k) const { return get(MET_PSIZ, k); }
-    __device__ __forceinline__ NF root(int k) const { return get(MET_ROOT, k); }
+    TRM_METRIC_ACCESSORS
+};
+// Compact metric rows (nz + 3 <= CMET_STRIDE) inside the kernel parameters: the staged kernels read `quantity[k]` with a
+// launch-uniform k straight from the constant bank (uniform loads: no shared-memory staging, no traffic on the LSU data
+// pipe, which is what bounds those kernels -- profiles/r02_summary.md).
+constexpr int CMET_STRIDE = 40;
+template <class NF> struct StageArgs;
+template <class NF>
+struct MetricsC {
+    const StageArgs<NF>* A;
+    __device__ __forceinline__ NF get(int q, int k) const { return A->cmet[q * CMET_STRIDE + k]; }
+    TRM_METRIC_ACCESSORS
 };
 
 #ifndef TRM_MAX_BLOCK
@@ -136,6 +149,7 @@ struct StageArgs {
     int32_t bct_pre, pad3_;
     VegParams<NF> vp;
     const NF* metrics;   // [MET_COUNT][MET_STRIDE], see enum Metric
+    NF cmet[MET_COUNT * CMET_STRIDE];   // the same rows with stride CMET_STRIDE when nz + 3 <= CMET_STRIDE (see MetricsC)
     DevParams<NF> p;
     trm_bc bc[TRM_BC_NSLOTS];
     InputDesc<NF> in[TRM_IN_COUNT];

@@ -139,6 +139,7 @@ struct Handle : HandleBase {
     DevParams<NF> p{};
     std::vector<void*> allocs;
     NF* metrics = nullptr;
+    NF cmet[MET_COUNT * CMET_STRIDE] = {};   // compact rows handed to the staged kernels inside their parameters
     // 3-D [nz][ld]
     NF *U = nullptr, *T = nullptr, *Lq = nullptr, *S = nullptr, *P = nullptr, *Kf = nullptr;
     NF *tU = nullptr, *tS = nullptr, *gU = nullptr, *gS = nullptr;   // tendencies, Heun stage state
@@ -261,6 +262,8 @@ struct Handle : HandleBase {
             for (int k = 1; k <= nz; ++k) root[k] = root[k] / sum;
             rootf.assign(root + 1, root + nz + 1);
         }
+        if (nz + 3 <= CMET_STRIDE)   // compact copy for the kernel parameters (MetricsC)
+            for (int q = 0; q < MET_COUNT; ++q) std::copy_n(m.data() + (size_t)q * MET_STRIDE, nz + 3, cmet + (size_t)q * CMET_STRIDE);
         if (int rc = dalloc(&metrics, m.size())) return rc;
         CU(cudaMemcpyAsync(metrics, m.data(), m.size() * sizeof(NF), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
@@ -472,6 +475,7 @@ struct Handle : HandleBase {
         std::memset(&a, 0, sizeof(a));
         a.ncol = nc; a.ld = ld; a.nz = nz; a.richards = richards ? 1 : 0;
         a.metrics = metrics; a.p = p;
+        std::memcpy(a.cmet, cmet, sizeof(cmet));
         for (int s = 0; s < TRM_BC_NSLOTS; ++s) a.bc[s] = cfg.bc[s];
         for (int i = 0; i < TRM_IN_COUNT; ++i) {
             InputDesc<NF>& d = a.in[i]; const Input& s = in[i];
