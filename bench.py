@@ -311,8 +311,7 @@ def main():
     #      forcing (pinned memory -> trm_set_input_field_async), advances one step (trm_step_async) and receives the
     #      ground temperature (trm_get_field_async -> pinned memory).  Uploads / downloads run on copy streams and
     #      overlap the stage kernel of the neighbouring steps; the timed region ends with trm_sync.
-    e2e = None
-    if not args.no_e2e:
+    def run_e2e(mode):
         k2 = max(3, args.steps)   # same step count as the kernel-only measurement
         NBUF = 4                  # host buffers are reused round robin (fresh forcing in / ground temperature out every step)
         in_id = integ._bc_inputs["T_ub"]
@@ -322,7 +321,7 @@ def main():
         def forcing(i):   # the host-side "atmosphere": this step's surface temperature per column
             return (T0 + 10.0 * np.sin(2 * np.pi * (t + i * DT) / 86400.0 - lon)).astype(nf)
 
-        if args.e2e_mode == "mapped":
+        if mode == "mapped":
             ring_in, ring_out = integ.bind_host_io("T_ub", "ground_temperature", nslots=NBUF)
             it0 = integ.clock.iteration
             for i in range(NBUF):
@@ -364,11 +363,11 @@ def main():
         lib.check(lib.sync(h), "sync")
         barrier()
         el = td.max_over_ranks(time.perf_counter() - w0)
-        e2e = {"value": total_cells * k2 / el, "unit": UNIT, "h2d_bytes_per_step": args.columns * itemsize,
+        res = {"value": total_cells * k2 / el, "unit": UNIT, "h2d_bytes_per_step": args.columns * itemsize,
                "d2h_bytes_per_step": args.columns * itemsize, "steps": k2, "ms_per_step": 1e3 * el / k2,
-               "mode": args.e2e_mode, "what": what,
+               "mode": mode, "what": what,
                "host_cpus_of_rank0": len(numa_cpus) if numa_cpus else None}
-        if args.e2e_mode == "mapped":
+        if mode == "mapped":
             # the last step's slot holds the ground temperature the library reports for the final state
             last = (it0 + 3 + k2 - 1) % NBUF
             gt = integ.state.ground_temperature.numpy()
@@ -377,6 +376,17 @@ def main():
             lib.check(lib.bind_host_io(h, -1, None, -1, None, 0), "unbind_host_io")
         else:
             assert all(bool(torch.isfinite(o).all()) for o in outs)
+        return res
+
+    e2e = None
+    if not args.no_e2e:
+        # both public end-to-end paths are timed (the host side of these boxes decides which one is faster: the mapped path
+        # depends on the latency of PCIe reads issued by the kernel, the copy path on the copy engines); `--e2e-mode` names
+        # the preferred one, the line reports the faster as `e2e` and the other one next to it
+        first = run_e2e(args.e2e_mode)
+        second = run_e2e("copy" if args.e2e_mode == "mapped" else "mapped")
+        e2e, other = (first, second) if first["ms_per_step"] <= second["ms_per_step"] else (second, first)
+        e2e["other_mode"] = {k: other[k] for k in ("mode", "value", "ms_per_step", "steps")}
 
     peak, peak_src = peaks()
     bpc = algorithmic_bytes_per_cell(itemsize, NZ, args.model, args.timestepper == "heun")

@@ -219,14 +219,15 @@ __device__ __forceinline__ P2<T> halo_value2(int kind, P2<T> edge, P2<T> v, T D,
 #endif
 template <class T> __host__ __device__ constexpr int euler2_block() { return sizeof(T) == 8 ? TRM_EULER2_F64_BLOCK : TRM_EULER_BLOCK; }
 
-// The pair kernels keep the prefetched top boundary temperature in the U-ring slot of the (non-existent) layer nz+1 instead
-// of a strip slot of its own, and the soil moisture limiting factor slot exists only in the LandModel variants.
+// Strip slots of the pair kernels: the soil moisture limiting factor slot exists only in the LandModel variants; the prefetched
+// top boundary temperature follows in a slot of its own (BCT_SLOT).
 template <class T, int MS, int MODE, bool LAND>
 struct Euler2Smem {
     static constexpr int PF_ = euler_pf(MODE);
     static constexpr bool CMET = MS == EULER_MS_SMALL;                                 // compact rows: read from the kernel parameters (MetricsC)
     static constexpr int METRICS = CMET ? 0 : (met_rows(LAND) * MS + 1) / 2 * 2;        // scalars (the strips start pair-aligned)
-    static constexpr int NSTRIP = LAND ? EF_BETA + 1 : EF_BETA;
+    static constexpr int BCT_SLOT = LAND ? EF_BETA + 1 : EF_BETA;                      // prefetched TEMPERATURE_TOP boundary value
+    static constexpr int NSTRIP = BCT_SLOT + 1;
     static constexpr int STRIP = NSTRIP * euler2_block<T>();                          // pair slots
     static constexpr int RING = 2 * EULER_RD * euler2_block<T>();                     // U, sat
     static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * PF_ * euler2_block<T>();   // k1U, k1S, bU, bS
@@ -348,14 +349,16 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
     };
     const F2 wtx = RICH ? ldg2(A.xWt + c) : zero2;
     const bool bct_pre = A.bct_pre != 0;
-    // per-column surface temperature vector (device memory, or mapped host memory bound with trm_bind_host_io): it travels
-    // like a layer nz+1 of the U ring -- fetched DIST iterations before the halo above the surface is formed, into the ring
-    // slot that layer would use (a mapped host ring is not padded: one scalar copy per column)
-    auto prefetch_bct = [&](int k) {
+    // per-column surface temperature vector (device memory, or mapped host memory bound with trm_bind_host_io): fetched now,
+    // with the first layer, into a strip slot of its own and consumed ~nz iterations later when the halo above the surface
+    // is formed -- a read of host memory needs that lead (fetched DIST layers ahead it cost 13.4 instead of 3.4 ms per
+    // 10 M-column step). A mapped host ring is not padded: one scalar copy per column.
+    const uint32_t bct_slot = strip0 + (uint32_t)(SM::BCT_SLOT * B * ES);
+    if (bct_pre) {
         const T* a = A.in[A.bc[TRM_BC_TEMPERATURE_TOP].input].a;
-        cp_async<(int)sizeof(T)>(ringU(k), a + c);
-        cp_async<(int)sizeof(T)>(ringU(k) + (uint32_t)sizeof(T), a + c1);
-    };
+        cp_async<(int)sizeof(T)>(bct_slot, a + c);
+        cp_async<(int)sizeof(T)>(bct_slot + (uint32_t)sizeof(T), a + c1);
+    }
 
     uint32_t oin = (uint32_t)c;
     const uint32_t xring0 = ring0 + (uint32_t)(SM::RING * ES);
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
             cp_async<ES>(ringU(k), A.xU + oin);
             cp_async<ES>(ringS(k), A.xS + oin);
             oin += (uint32_t)ld;
-        } else if (bct_pre && k == nz + 1) prefetch_bct(k);
+        }
         if (H2) {
             const int kk = k - 2;
             if (kk >= 1 && kk <= nz) {
@@ -407,7 +410,6 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
         const bool j_is_nz = GEN ? m == nz + 2 : POS == IP_LAST;
         if (POS == IP_INNER) prefetch(m + DIST_, true);
         else if (POS >= IP_INNER_NP && !H2) {   // no layer left to prefetch (Heun stage 2 still fetches k1 / the base state of layer m+DIST-2)
-            if (bct_pre && m + DIST_ == nz + 1) prefetch_bct(nz + 1);
             cp_async_commit();
         }
         else prefetch(m + DIST_, false);
@@ -428,8 +430,8 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
                 wr(EF_KC, Kcn);
             }
         } else if (is_halo) {   // halo above the surface
-            if (bct_pre) cp_async_wait<DIST_>();   // (the group of layer nz+1 is DIST groups old, like that of every entering layer)
-            Tn = halo_value2(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(EF_T), bct_pre ? ld2(ringU(nz + 1)) : bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
+            if (bct_pre) cp_async_wait<DIST_>();   // (its group is the first one: long complete unless the column has fewer layers than the prefetch distance)
+            Tn = halo_value2(A.bc[TRM_BC_TEMPERATURE_TOP].kind, rd(EF_T), bct_pre ? ld2(bct_slot) : bc_input(TRM_BC_TEMPERATURE_TOP), met.dzf(nz + 1), true);
             const bool copy = RICH || p.sat_halo == TRM_HALO_COPY;
             kapn = copy ? rd(EF_KAP) : bc2<T>(thermal_conductivity_fast(p, T(0), T(1)));
             if (RICH) Pn = halo_value2(A.bc[TRM_BC_PRESSURE_TOP].kind, rd(EF_P), bc_input(TRM_BC_PRESSURE_TOP), met.dzf(nz + 1), true);

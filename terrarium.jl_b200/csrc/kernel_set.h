@@ -21,6 +21,10 @@ struct KernelSet {
     // LandModel surface block as its own launch (what = 0) / soil moisture limiting factor from stored fields (what = 1)
     cudaError_t (*surface_f32)(int what, const StageArgs<float>& a, cudaStream_t st);
     cudaError_t (*surface_f64)(int what, const StageArgs<double>& a, cudaStream_t st);
+    // small domains: one warp per column, `nsteps` ForwardEuler (heun = 0) or Heun steps inside one launch
+    // (warp_kernel.cuh); cudaErrorInvalidConfiguration = not applicable (LandModel, nz > 31)
+    cudaError_t (*warp_f32)(int phys, int heun, int nsteps, const StageArgs<float>& a, cudaStream_t st);
+    cudaError_t (*warp_f64)(int phys, int heun, int nsteps, const StageArgs<double>& a, cudaStream_t st);
 };
 
 const KernelSet& kernels_faithful();   // compiled with -fmad=false, reference operation order

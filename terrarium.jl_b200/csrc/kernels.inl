@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "euler_kernel.cuh"
 #include "euler2_kernel.cuh"
+#include "warp_kernel.cuh"
 
 namespace trm {
 namespace {
@@ -95,12 +96,14 @@ cudaError_t launch_euler2_mode(int mode, const StageArgs<T>& a, cudaStream_t st)
 }
 // Which pair instantiation covers this launch, -1 for none (closure fields recomputed; Richards soils: van Genuchten n = 2
 // for retention curve and conductivity, or Brooks-Corey with an integer 1 / lambda + linear conductivity -- the reference's
-// default hydraulics). TRM_F32X2=0 / TRM_F64X2=0 switch the pair kernels of a number format off.
+// default hydraulics). TRM_F32X2=0 switches the Float32 pair kernels off, TRM_F64X2=1 the Float64 pair kernel on.
 template <class T>
 inline int euler2_soil(int phys, int mode, int load_aux, const StageArgs<T>& a) {
     const char* e = std::getenv(sizeof(T) == 4 ? "TRM_F32X2" : "TRM_F64X2");   // (read per launch: tests compare both kernels within one process)
     if ((e && e[0] == '0') || load_aux) return -1;
-    if (sizeof(T) == 8 && mode != MODE_EULER) return -1;
+    // Float64: the one-column kernel is the faster one on the 10 M-column step (3.17 ms against 3.24 - 3.34 ms of the pair
+    // instantiations, profiles/r02_sweep_compact_metrics.txt): the Float64 pair kernel runs on request only (TRM_F64X2=1)
+    if (sizeof(T) == 8 && (mode != MODE_EULER || !(e && e[0] == '1'))) return -1;
     if (!phys_richards(phys)) return SOIL2_VG2;
     if (a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN) return SOIL2_VG2;
     if (a.p.swrc == TRM_SWRC_BROOKSCOREY && a.p.bc_k > 0 && a.p.unsat_k == TRM_UNSATK_LINEAR) return SOIL2_BC_LINEAR;
@@ -148,6 +151,24 @@ cudaError_t launch_euler(int phys, int mode, int load_aux, const StageArgs<NF>& 
     }
 }
 
+// one warp per column, nsteps steps per launch (warp_kernel.cuh): SoilModel, nz <= 31
+template <class NF>
+cudaError_t launch_warp(int phys, int heun, int nsteps, const StageArgs<NF>& a, cudaStream_t st) {
+    if (phys_land(phys) || a.nz > WARP_MAX_NZ || a.nz < 1) return cudaErrorInvalidConfiguration;
+    constexpr int cols = TRM_WARP_BLOCK / 32;
+    const unsigned nblk = (unsigned)((a.ncol + cols - 1) / cols);
+    if (phys == PHYS_NOFLOW) { column_warp_kernel<NF, false, kFast, WSOIL_GENERIC><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun); return cudaGetLastError(); }
+#if TRM_FAST
+    if (a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN)
+        column_warp_kernel<NF, true, true, WSOIL_VG2><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
+    else if (a.p.swrc == TRM_SWRC_BROOKSCOREY && a.p.bc_k > 0 && a.p.unsat_k == TRM_UNSATK_LINEAR)
+        column_warp_kernel<NF, true, true, WSOIL_BC_LINEAR><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
+    else
+#endif
+        column_warp_kernel<NF, true, kFast, WSOIL_GENERIC><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
+    return cudaGetLastError();
+}
+
 template <class NF>
 cudaError_t launch_stage(int phys, int variant, const StageArgs<NF>& a, int block, cudaStream_t st) {
     switch (phys) {
@@ -182,7 +203,8 @@ const KernelSet& kernels_fast() {
 const KernelSet& kernels_faithful() {
 #endif
     static const KernelSet ks = {&launch_stage<float>, &launch_stage<double>, &launch_init<float>, &launch_init<double>,
-                                 &launch_euler<float>, &launch_euler<double>, &launch_surface<float>, &launch_surface<double>};
+                                 &launch_euler<float>, &launch_euler<double>, &launch_surface<float>, &launch_surface<double>,
+                                 &launch_warp<float>, &launch_warp<double>};
     return ks;
 }
 

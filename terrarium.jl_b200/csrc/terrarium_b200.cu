@@ -563,6 +563,22 @@ struct Handle : HandleBase {
     bool heun_rc() const { return heun_recompute<NF>() && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     bool split_surface() const { return land && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     int enqueue_steps(double dt, int64_t n);
+    // small domains (warp_kernel.cuh): one warp per column, several steps per launch. Applies to the SoilModel with
+    // nz <= 31 while the column count leaves the one-thread-per-column kernels latency bound (less than about one wave of
+    // warps). Measured crossover with the streaming kernels (profiles/r02_small_domains.csv): ~72 k columns in Float32,
+    // ~30 k in Float64 (lanes = layers of one column diverge where adjacent columns of one layer do not, and the Float64
+    // fast-math sequences are longer): default limit 65536 / 24576 columns (TRM_WARP_COLS overrides it ; TRM_WARP=0
+    // switches the kernel off ; tests compare both within a process).
+    bool use_warp() const {
+        if (land || euler_impl != 1 || nz > 31) return false;
+        const char* e = std::getenv("TRM_WARP");
+        if (e && e[0] == '0') return false;
+        const char* m = std::getenv("TRM_WARP_COLS");
+        const int64_t max_cols = m ? std::atoll(m) : (sizeof(NF) == 4 ? 65536 : 24576);
+        return nc <= max_cols;
+    }
+    int enqueue_steps_warp(NF dt, int64_t n);
+    cudaError_t call_warp(int nsteps, const StageArgs<NF>& a);
     int set_input_field_async(int id, const void* v) override;
     int get_field_async(int id, void* host, int64_t count) override;
     int step_async(double dt, int64_t n) override;
@@ -653,12 +669,65 @@ template <class NF> int Handle<NF>::initialize() {
     return TRM_OK;
 }
 
+template <> cudaError_t Handle<float>::call_warp(int nsteps, const StageArgs<float>& a) { return ks->warp_f32(phys, heun ? 1 : 0, nsteps, a, stream); }
+template <> cudaError_t Handle<double>::call_warp(int nsteps, const StageArgs<double>& a) { return ks->warp_f64(phys, heun ? 1 : 0, nsteps, a, stream); }
+
+// timestep! x n on a small domain: the warp-per-column kernel advances every column `chunk` steps per launch, both Heun stages
+// included. Inputs whose descriptor changes from step to step on the host side (tables / rasters: time bracket ; host
+// evaluated functions: value pair ; a mapped host exchange: ring slot) limit a launch to one step.
+template <class NF> int Handle<NF>::enqueue_steps_warp(NF dt, int64_t n) {
+    bool per_step = hio.nslots != 0;
+    for (int i = 0; i < TRM_IN_COUNT; ++i)
+        if (in[i].kind == TRM_SRC_TABLE || in[i].kind == TRM_SRC_RASTER || in[i].kind == TRM_SRC_FIELD_PAIR) per_step = true;
+    int64_t done = 0;
+    while (done < n) {
+        const int64_t chunk = per_step ? 1 : std::min<int64_t>(n - done, 1 << 30);
+        StageArgs<NF> a; base_args(a);
+        const NF t = (NF)time;
+        a.dt = dt; a.mode = heun ? MODE_HEUN1 : MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
+        a.load_aux = (aux_stale || force_load) ? 1 : 0;
+        // time index of the descriptors inside this kernel: 0 = start of the step, 1 = start + dt (Heun stage 2)
+        for (int i = 0; i < TRM_IN_COUNT; ++i) {
+            if (in[i].kind == TRM_SRC_TABLE || in[i].kind == TRM_SRC_RASTER) {
+                bracket(in[i], (double)t, a.in[i].br[0]);
+                bracket(in[i], (double)(NF)(t + dt), a.in[i].br[1]);
+            }
+            if (in[i].kind == TRM_SRC_FIELD_PAIR) { a.in[i].a = in[i].a; a.in[i].b = in[i].b; }
+        }
+        apply_host_io(a, true);
+        cudaError_t e = call_warp((int)chunk, a); ++launches;
+        if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("warp kernel launch: ") + cudaGetErrorString(e));
+        if (hio.nslots) {
+            const int64_t slot = iteration % hio.nslots;
+            if (hio.out_id >= 0 && hio.out_id != TRM_F_GROUND_TEMPERATURE) {
+                copy_row_kernel<NF><<<(unsigned)((nc + 255) / 256), 256, 0, stream>>>(nc, field(hio.out_id).ptr, hio.out_dev + slot * nc);
+                ++launches;
+            }
+            CU(cudaEventRecord(hio.ev[slot], stream));
+        }
+        aux_stale = false; beta_stale = true;
+        for (int64_t i = 0; i < chunk; ++i) {   // tick!(clock, dt) in the clock's number format, like the kernel
+            const NF ts = (NF)time;
+            t_inputs = (double)ts;
+            time = (double)(NF)(ts + dt); iteration += 1;
+        }
+        done += chunk;
+    }
+    return TRM_OK;
+}
+
 template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
     if (!initialized) return fail(TRM_ERR_STATE, "trm_step before trm_initialize");
     if (n < 0) return fail(TRM_ERR_INVALID, "nsteps < 0");
     CU(cudaSetDevice(device));
     const NF dt = (NF)dt_;
     CU(cudaEventRecord(ev0, stream));
+    if (use_warp()) {
+        if (int rc = enqueue_steps_warp(dt, n)) return rc;
+        CU(cudaEventRecord(ev1, stream));
+        timing_open = true;
+        return TRM_OK;
+    }
     for (int64_t i = 0; i < n; ++i) {
         StageArgs<NF> a; base_args(a);
         const NF t = (NF)time;

@@ -1,0 +1,319 @@
+// warp_kernel.cuh -- small domains: one WARP per column, one lane per layer, `nsteps` time steps inside one launch.
+//
+// The streaming kernels (euler_kernel.cuh) give a column to one thread: on the reference's real grids (N72: 14 017
+// columns, N145: 56 951) the GPU then holds less than one wave of warps and a step costs the latency of one thread's
+// sweep over the nz layers (23 us Float32, 33 us Float64), whatever the column count. The explicit scheme is parallel
+// over the layers of a column, so here the 32 lanes of a warp hold the layers of ONE column (lane l = layer l + 1, lane nz
+// = the halo cell above the surface, nz <= 31): the vertical stencil is five warp shuffles per evaluation, the water
+// table is a ballot, the (rare) saturation sweeps run through shuffles, and because columns never interact the warp
+// advances its column `nsteps` steps with U, sat, the water table and the surface excess water in registers -- global
+// memory is touched at the start and at the end of the launch only. Heun runs both stages back to back in the same
+// registers (no stage state, no k1 in memory). Per-cell arithmetic: the functions of column_physics.cuh in the order of
+// the streaming kernels (same reference citations), so both kernels agree to rounding and, where no transcendental and no
+// contraction is involved (faithful math, heat only), bit for bit.
+//
+// SoilModel only (energy + Richards or immobile water); the LandModel variants keep the streaming kernels.
+#pragma once
+
+#include "stage_kernel.cuh"
+
+namespace trm {
+
+#ifndef TRM_WARP_BLOCK
+#define TRM_WARP_BLOCK 128   // four columns per block
+#endif
+constexpr int WARP_MAX_NZ = 31;   // lane nz is the halo cell above the surface
+
+enum WarpSoil { WSOIL_GENERIC = 0 /* run-time tests, general formulas out of line */, WSOIL_VG2 = 1 /* van Genuchten n = 2 */,
+                WSOIL_BC_LINEAR = 2 /* Brooks-Corey with integer 1 / lambda + linear conductivity: the reference's defaults */ };
+
+__device__ __forceinline__ bool sign_set(double v) { return __double2hiint(v) < 0; }
+__device__ __forceinline__ bool sign_set(float v)  { return __float_as_int(v) < 0; }
+__device__ __forceinline__ bool lt_one(double v) { return __double2hiint(v) < 0x3FF00000; }
+__device__ __forceinline__ bool lt_one(float v)  { return __float_as_int(v) < 0x3F800000; }
+
+// Brooks-Corey matric head with an integer exponent k = 1 / lambda (fast math): psi_m = -psi_s se^-k below saturation,
+// -psi_s at saturation (FreezeCurves BrooksCorey, SURVEY.md A.9 ; soil_hydraulic_closures.jl:115-118)
+template <class NF>
+__device__ __forceinline__ NF brooks_corey_psim_fast(const DevParams<NF>& p, NF theta) {
+    const NF se = fma_(theta, p.r_thspan, p.se_off);
+    NF pw = se;
+#pragma unroll 1
+    for (int i = 1; i < p.bc_k; ++i) pw = pw * se;
+    NF r = M<NF, true>::rcp(pw) * -p.bc_psis;
+    r = pw == NF(0) ? -Lim<NF>::inf() : r;   // dry layer: -Inf as in the reference
+    return theta < p.por ? r : -p.bc_psis;
+}
+// UnsatKLinear (soil_hydraulic_properties.jl:170-198) with the reciprocal of fast math
+template <class NF>
+__device__ __forceinline__ NF cell_conductivity_linear_fast(const DevParams<NF>& p, NF sat, NF liq) {
+    const NF wi = sat * p.por;
+    const NF water = wi * liq, ice = wi * (1 - liq), air = (1 - sat) * p.por;
+    return (water * p.Ksat) * M<NF, true>::rcp((water + ice) + air);
+}
+
+template <class NF, bool RICH, bool FAST, int SOIL>
+__global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, const int heun) {
+    using Mx = M<NF, FAST>;
+    constexpr bool VG2 = SOIL == WSOIL_VG2;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * (TRM_WARP_BLOCK / 32) + (threadIdx.x >> 5);
+    if (c >= A.ncol) return;   // (a whole warp leaves together)
+    const DevParams<NF>& p = A.p;
+    const int nz = A.nz;
+    const int k = lane + 1;                               // 1-based layer (lanes < nz) / face index (lanes <= nz)
+    const bool isL = lane < nz, isH = lane == nz, isTop = lane == nz - 1, isBot = lane == 0;
+    const NF dt = A.dt;
+    const int64_t o = (int64_t)lane * A.ld + c;           // this lane's cell in a [layer][column] field
+
+    // grid metrics of this lane's layer / lower face, read once (rows of MET_STRIDE values, 1-based + halos)
+    const NF* met = A.metrics;
+    const int kc = min(k, nz), kf = min(k, nz + 1);
+    const NF zC_k = met[MET_ZC * MET_STRIDE + kc], psiz_k = met[MET_PSIZ * MET_STRIDE + kc];
+    const NF dzc_k = met[MET_DZC * MET_STRIDE + kc], rdzc_k = met[MET_RDZC * MET_STRIDE + kc];
+    const NF zF_k = met[MET_ZF * MET_STRIDE + kf];
+    const NF dzf_k = met[MET_DZF * MET_STRIDE + kf], rdzf_k = met[MET_RDZF * MET_STRIDE + kf];
+    const NF dzc_up = __shfl_down_sync(FULL, dzc_k, 1), rdzc_up = __shfl_down_sync(FULL, rdzc_k, 1);   // layer k + 1
+    const NF dzc_dn = __shfl_up_sync(FULL, dzc_k, 1);                                                    // layer k - 1
+    const NF zsurf = met[MET_ZF * MET_STRIDE + nz + 1];
+
+    // Boundary values. Evaluating an input is per-column scalar work (a Float64 `sin` for the sinusoid form) that one lane would
+    // do while 31 wait, every step: instead, every 31 steps lane i evaluates every boundary input at the clock time of step
+    // i of the block (t advanced i times by dt in the clock's number format, exactly as the step loop does) and a step reads
+    // its values with a shuffle: slot value at the step's start time from lane `si`, at start + dt (what Heun stage 2 needs
+    // for Value / Gradient BCs; Flux BCs always belong to the time-n state, abstract_timestepper.jl:69, heun.jl:63-66) from
+    // lane `si + 1`. Inputs whose descriptor is per step on the host side (tables / rasters: time bracket ; host evaluated
+    // functions: value pair) run one step per launch, with descriptor index 0 = step start (lane 0), 1 = start + dt (lane 1).
+    constexpr int BC_BLOCK = 31;
+    NF t = A.t_x;
+    NF bcv[TRM_BC_NSLOTS];
+#pragma unroll
+    for (int q = 0; q < TRM_BC_NSLOTS; ++q) bcv[q] = NF(0);
+    int si = 0;   // step index inside the current block of BC_BLOCK steps
+    auto refresh_bcs = [&]() {
+        NF tl = t;
+#pragma unroll 1
+        for (int i = 0; i < lane; ++i) tl = tl + dt;
+#pragma unroll
+        for (int q = 0; q < TRM_BC_NSLOTS; ++q)
+            if (A.bc[q].kind != TRM_BC_DEFAULT) bcv[q] = eval_input(A.in[A.bc[q].input], c, tl, lane == 0 ? 0 : 1);
+    };
+    auto bc_val = [&](int slot, bool stage2) -> NF {   // (call from converged code only)
+        const int kind = A.bc[slot].kind;
+        if (kind == TRM_BC_DEFAULT) return NF(0);
+        const bool late = stage2 && kind != TRM_BC_FLUX;
+        return __shfl_sync(FULL, bcv[slot], si + (late ? 1 : 0));
+    };
+    auto pressure = [&](NF s, NF wt) -> NF {
+        if (FAST && SOIL == WSOIL_BC_LINEAR) return (Mx::pos(wt + (-zC_k)) + brooks_corey_psim_fast(p, s * p.por)) + psiz_k;
+        return pressure_head<NF, FAST, VG2>(p, s, wt, zC_k, psiz_k);
+    };
+    const bool halo_copy = RICH || p.sat_halo == TRM_HALO_COPY;
+    auto kappa_dry = [&]() -> NF { return FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)); };
+
+    // compute_auxiliary! + compute_tendencies! on the state (Ux, sx, wtx): tendencies of this lane's layer, before Flux BCs
+    auto evaluate = [&](NF Ux, NF sx, NF wtx, bool stage2, bool loaded, NF& tU, NF& tS) {
+        const NF bT_top = bc_val(TRM_BC_TEMPERATURE_TOP, stage2), bT_bot = bc_val(TRM_BC_TEMPERATURE_BOTTOM, stage2);
+        const NF bP_top = RICH ? bc_val(TRM_BC_PRESSURE_TOP, stage2) : NF(0), bP_bot = RICH ? bc_val(TRM_BC_PRESSURE_BOTTOM, stage2) : NF(0);
+        NF T = NF(0), liq = NF(1), P = NF(0), kap = NF(0), Kc = NF(0);
+        if (isL) {
+            if (loaded) { T = A.xT[o]; liq = A.xL[o]; if (RICH) P = A.xP[o]; }
+            else {
+                energy_to_temperature<NF, FAST>(p, Ux, sx, T, liq);
+                if (RICH) P = pressure(sx, wtx);
+            }
+            kap = FAST ? thermal_conductivity_fast(p, sx, liq) : thermal_conductivity(p, sx, liq);
+            if (RICH) Kc = (FAST && SOIL == WSOIL_BC_LINEAR) ? cell_conductivity_linear_fast(p, sx, liq) : cell_conductivity<NF, FAST, VG2>(p, sx, liq);
+        }
+        const NF T_dn = __shfl_up_sync(FULL, T, 1), kap_dn = __shfl_up_sync(FULL, kap, 1);
+        NF P_dn = NF(0), Kf = NF(0);
+        if (RICH) {
+            P_dn = __shfl_up_sync(FULL, P, 1);
+            const NF Kc_dn = __shfl_up_sync(FULL, Kc, 1);
+            // face conductivity Kf[k] (soil_hydrology.jl:249-276): Kf[1] = Kc[1], Kf[Nz] = Kc[Nz], Kf[Nz+1] = Kf[Nz]
+            if (isL) Kf = (isBot || isTop) ? Kc : Mx::mn(Kc, Kc_dn);
+            const NF Kf_dn = __shfl_up_sync(FULL, Kf, 1);
+            if (isH) Kf = Kf_dn;
+        }
+        if (isH) {   // halo cell above the surface, from layer nz (fill_halo_regions!)
+            T = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, T_dn, bT_top, dzf_k, true);
+            kap = halo_copy ? kap_dn : kappa_dry();
+            if (RICH) P = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, P_dn, bP_top, dzf_k, true);
+        }
+        NF Tp = T_dn, kapp = kap_dn, Pp = P_dn;
+        if (isBot) {  // halo cell below the bottom layer
+            Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, T, bT_bot, dzf_k, false);
+            kapp = halo_copy ? kap : kappa_dry();
+            if (RICH) Pp = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, P, bP_bot, dzf_k, false);
+        }
+        // heat flux and head gradient at face k (diffusive_heat_flux, soil_energy.jl:134-149), faces 1 .. nz + 1
+        NF qh = NF(0), g = NF(0);
+        if (lane <= nz) {
+            qh = -((kap + kapp) / 2) * ((T - Tp) * rdzf_k);
+            if (RICH) g = (P - Pp) * rdzf_k;
+        }
+        const NF qh_up = __shfl_down_sync(FULL, qh, 1);
+        tU = -((qh_up - qh) * rdzc_k);                                   // soil_energy.jl:112-131
+        tS = NF(0);
+        if (RICH) {
+            // Darcy flux at face k (darcy_flux, soil_hydrology_rre.jl:119-131): upwinded face conductivity, Kf[0] = Kf[Nz+2] = 0
+            NF Kf_lo = __shfl_up_sync(FULL, Kf, 1), Kf_hi = __shfl_down_sync(FULL, Kf, 1);
+            if (isBot) Kf_lo = NF(0);
+            if (isH) Kf_hi = NF(0);
+            NF Kk;
+            if (FAST) Kk = Mx::mn(Kf, g < 0 ? Kf_lo : Kf_hi);
+            else Kk = (g < 0 ? jmin(Kf_lo, Kf) : NF(0)) + (g >= 0 ? jmin(Kf, Kf_hi) : NF(0));
+            const NF qd = lane <= nz ? -Kk * g : NF(0);
+            const NF qd_up = __shfl_down_sync(FULL, qd, 1);
+            const NF dth = -((qd_up - qd) * rdzc_k) + NF(0) + p.vwcf;     // soil_hydrology_rre.jl:95-117
+            tS = FAST ? dth * p.rpor : dth / p.por;                       // soil_hydrology.jl:222-237
+        }
+    };
+    // Flux boundary conditions of the time-n state on the tendencies of the top / bottom layer (compute_z_bcs!)
+    auto apply_flux_bcs = [&](NF& tU, NF& tS) {
+        const bool fE_top = A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX, fE_bot = A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX;
+        const bool fS_top = RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX, fS_bot = RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX;
+        const NF vE_top = fE_top ? bc_val(TRM_BC_ENERGY_TOP, false) : NF(0), vS_top = fS_top ? bc_val(TRM_BC_SATURATION_TOP, false) : NF(0);
+        const NF vE_bot = fE_bot ? bc_val(TRM_BC_ENERGY_BOTTOM, false) : NF(0), vS_bot = fS_bot ? bc_val(TRM_BC_SATURATION_BOTTOM, false) : NF(0);
+        if (isTop) {
+            if (fE_top) tU -= vE_top / dzc_k;
+            if (fS_top) tS -= vS_top / dzc_k;
+        }
+        if (isBot) {
+            if (fE_bot) tU += vE_bot / dzc_k;
+            if (fS_bot) tS += vS_bot / dzc_k;
+        }
+    };
+    // adjust_saturation_profile! (soil_hydrology.jl:185-219) + compute_water_table! (:170-175) on the updated saturations of
+    // the column. Returns this lane's saturation; `Sx` receives the top excess (surface_excess_water), `wt` the water table,
+    // `idx` the lowest unsaturated layer (0: none), `slow` whether the downward sweep ran.
+    auto adjust = [&](NF sn, NF& Sx, NF& wt, int& idx, bool& slow) -> NF {
+        // upward sweep (:192-199): excess of a layer is handed to the layer above, scaled by the thickness ratio
+        const bool over = isL && !isTop && sn > NF(1);
+        if (__any_sync(FULL, over)) {
+            NF carry = NF(0);
+#pragma unroll 1
+            for (int l = 0; l < nz; ++l) {
+                const NF cin = __shfl_sync(FULL, carry, (l + 31) & 31);   // (lane 31 is never a layer: 0 for the bottom layer)
+                if (lane == l) {
+                    sn = sn + cin;
+                    if (!isTop) {
+                        const NF e = Mx::pos(sn - 1);
+                        sn -= e;
+                        carry = FAST ? e * dzc_k * rdzc_up : e * dzc_k / dzc_up;
+                    }
+                }
+            }
+        } else {
+            sn = sn + NF(0);   // (the carry every layer adds in the sequential form)
+        }
+        const bool neg = isL && (FAST ? sign_set(sn) : sn < 0);
+        slow = __any_sync(FULL, neg) != 0;
+        unsigned unsat;
+        if (!slow) {
+            // downward sweep with no deficit anywhere: sat += max(-sat, 0) is the identity (:201-208)
+            if (!FAST && isL && k >= 2) sn = sn + jmax(-sn, NF(0));
+            if (isTop) {                                   // top excess -> surface_excess_water (:210-214)
+                const NF e = Mx::pos(sn - 1);
+                sn -= e;
+                Sx += e * dzc_k;
+            }
+            if (!FAST && isBot) sn = jmax(sn, NF(0));      // :216
+            unsat = __ballot_sync(FULL, isL && (FAST ? lt_one(sn) : sn < 1));
+        } else {
+            // a layer went negative: downward sweep top -> bottom (:201-216), deficits are taken from the layer below
+            NF carry_dn = NF(0);
+#pragma unroll 1
+            for (int l = nz - 1; l >= 0; --l) {
+                const NF cin = __shfl_sync(FULL, carry_dn, (l + 1) & 31);
+                if (lane == l) {
+                    NF s = sn;
+                    if (k < nz) s -= cin;
+                    if (k >= 2) {
+                        const NF d = jmax(-s, NF(0));
+                        s += d;
+                        carry_dn = d * dzc_k / dzc_dn;
+                    }
+                    if (k == nz) {
+                        const NF e = jmax(s - 1, NF(0));
+                        s -= e;
+                        Sx += e * dzc_k;
+                    }
+                    if (k == 1) s = jmax(s, NF(0));
+                    sn = s;
+                }
+            }
+            unsat = __ballot_sync(FULL, isL && sn < 1);
+        }
+        Sx = __shfl_sync(FULL, Sx, nz - 1);
+        idx = __ffs((int)unsat);                          // compute_water_table!, kernel_utils.jl:7-16 ; 0 = all saturated
+        wt = __shfl_sync(FULL, zF_k, idx ? idx - 1 : nz);  // zF(idx), or z of the surface
+        return sn;
+    };
+
+    // ---- state of the column: registers for the whole launch ----
+    NF U = NF(0), s = NF(0);
+    if (isL) { U = A.xU[o]; s = A.xS[o]; }
+    NF wt = RICH ? A.xWt[c] : NF(0);
+    NF Sx = RICH ? A.bSx[c] : NF(0);
+    int idx = 0;
+    bool slow = false;
+    bool loaded = A.load_aux != 0;   // first evaluation after initialize / a user write: stored closure fields (see stage_kernel.cuh)
+
+#pragma unroll 1
+    for (int step = 0; step < nsteps; ++step) {
+        if (si == BC_BLOCK) si = 0;
+        if (si == 0) refresh_bcs();
+        NF tU, tS;
+        evaluate(U, s, wt, false, loaded, tU, tS);
+        loaded = false;
+        if (heun) {
+            // heun.jl:37-71: stage state = explicit step with k1 (+ Flux BCs) and its closure, k2 on the stage state at t + dt,
+            // averaged tendencies (+ the Flux BCs of the time-n state) applied to the base state
+            NF t1U = tU, t1S = tS;
+            apply_flux_bcs(t1U, t1S);
+            const NF Us = U + t1U * dt;
+            NF ss = s, wts = wt;
+            if (RICH) {
+                NF Sx_stage = NF(0); int idx_s; bool slow_s;
+                ss = adjust(s + t1S * dt, Sx_stage, wts, idx_s, slow_s);   // (the stage copy's surface excess water is not used)
+            }
+            NF k2U, k2S;
+            evaluate(Us, ss, wts, true, false, k2U, k2S);
+            tU = (tU + k2U) / 2;                                          // average_tendencies!, heun.jl:27-35
+            if (RICH) tS = (tS + k2S) / 2;
+        }
+        apply_flux_bcs(tU, tS);
+        U = U + tU * dt;                                                  // explicit_step!, abstract_timestepper.jl:113-141
+        if (RICH) {
+            Sx = Sx + NF(0) * dt;                                         // surface_excess_water tendency is zero (soil_hydrology.jl:260-267)
+            s = adjust(s + tS * dt, Sx, wt, idx, slow);
+        }
+        t = t + dt;                                                       // tick!(clock, dt) in the clock's number format
+        ++si;
+    }
+    if (nsteps <= 0) return;
+
+    // ---- closure! of the final state and stores ----
+    if (isL) {
+        NF Tc, lc;
+        energy_to_temperature<NF, FAST>(p, U, s, Tc, lc);
+        A.yU[o] = U; A.yT[o] = Tc; A.yL[o] = lc;
+        if (isTop && A.hio_out) A.hio_out[c] = Tc;                        // ground temperature -> mapped host memory
+        if (RICH) {
+            A.yS[o] = s;
+            NF Pc;
+            if (slow || (idx != 0 && k >= idx)) Pc = pressure(s, wt);
+            else {
+                // saturated zone below the water table: psi_m(sat >= 1) is a constant (see euler_kernel.cuh)
+                const NF psat = (FAST && SOIL == WSOIL_BC_LINEAR) ? brooks_corey_psim_fast(p, p.por) : swrc_inverse<NF, FAST, VG2>(p, p.por, p.por);
+                Pc = FAST ? (wt - zsurf) + psat : Mx::mx(NF(0), wt - zC_k) + psat + psiz_k;
+            }
+            A.yP[o] = Pc;
+        }
+    }
+    if (RICH && lane == 0) { A.yWt[c] = wt; A.ySx[c] = Sx; }
+}
+
+}  // namespace trm

@@ -139,6 +139,8 @@ def test_packed_over_saturation_to_surface_excess():
 
 def test_packed_kernel_is_the_one_that_runs():
     """The Float32 fast-math step launches euler2_kernel (one launch per step, half as many blocks)."""
+    if os.environ.get("TRM_WARP") == "1":
+        pytest.skip("TRM_TEST_WARP=1: small domains run the warp-per-column kernel")
     gpu = synthetic_soil_case("cuda", 4096, nf=np.float32, math="fast")
     gpu.step(60.0, 2)          # first step reads the stored closure fields (one-column kernel), then the packed kernel
     l0 = gpu._lib.launch_count(gpu._h)
@@ -169,7 +171,8 @@ def test_packed_default_hydraulics_brooks_corey_linear(stepper):
     cpu.step(60.0, 40)
     l0 = a._lib.launch_count(a._h)
     a.step(60.0, 1)
-    assert a._lib.launch_count(a._h) - l0 == (2 if stepper == "heun" else 1)
+    if os.environ.get("TRM_WARP") != "1":
+        assert a._lib.launch_count(a._h) - l0 == (2 if stepper == "heun" else 1)
     cpu.step(60.0, 1)
     with scalar_kernel():
         b.step(60.0, 1)
