@@ -450,6 +450,33 @@ def main():
             it2.close()
             del it2
 
+    # ---- small domains (one GPU): the same soil workload at the column counts of the reference's own configurations, 600
+    #      steps per trm_step call. Below 114 688 (Float32) / 49 152 (Float64) columns the library runs them on the
+    #      warp-per-column kernel (csrc/warp_kernel.cuh: all steps of a call in one launch, state in registers -- no HBM
+    #      roofline applies, the figure is time per step); TRM_WARP=0 gives the streaming kernels' time next to it. ----
+    small_lines = []
+    if not secondary and not args.no_secondary and world == 1:
+        for label, ncs, dt_name, stepper in (("single column", 1, "f64", "euler"), ("N72 land mask", 14017, "f32", "euler"),
+                                             ("N72 land mask", 14017, "f64", "heun"), ("N145 land mask", 56951, "f32", "euler")):
+            nf2 = np.float64 if dt_name == "f64" else np.float32
+            row = {"workload": f"soil energy + Richards, {label}, {stepper}, {dt_name}", "columns": ncs, "steps_per_call": 600}
+            for warp in ("1", "0"):
+                os.environ["TRM_WARP"] = warp
+                it2, _, _ = build_case(trm, trm.initialize, ncs, 0, 1, local_rank, nf2, args.math, heun=stepper == "heun")
+                it2.step(DT, 20)
+                la = it2._lib.launch_count(it2._h)
+                it2.step(DT, 600)
+                nl = it2._lib.launch_count(it2._h) - la
+                m2 = C.c_float()
+                it2._lib.check(it2._lib.last_step_ms(it2._h, C.byref(m2)), "last_step_ms")
+                key = "warp_per_column" if warp == "1" else "streaming"
+                row[key] = {"us_per_step": 1e3 * m2.value / 600, "gpu_launches": int(nl),
+                            "value": ncs * NZ * 600 / (m2.value * 1e-3), "unit": UNIT, "nan_count": it2.diagnostics()["nan_count"]}
+                it2.close()
+                del it2
+            os.environ.pop("TRM_WARP", None)
+            small_lines.append(row)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -474,7 +501,7 @@ def main():
                        "partition": "contiguous column ranges, no halo, no data-path collective",
                        "cache": "inputs larger than L2 (state read per step = %.1f GB per GPU)" % (2 * ncol_local * NZ * itemsize / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "secondary": secondary_lines,
+            "secondary": secondary_lines, "small_domains": small_lines,
             "wall_s_timed_region": wall,
             "budgets": {"water_before": bud[0], "water_after": bud[1], "nan_count": bud[2], "energy_after": bud[3]},
         }

@@ -565,16 +565,16 @@ struct Handle : HandleBase {
     int enqueue_steps(double dt, int64_t n);
     // small domains (warp_kernel.cuh): one warp per column, several steps per launch. Applies to the SoilModel with
     // nz <= 31 while the column count leaves the one-thread-per-column kernels latency bound (less than about one wave of
-    // warps). Measured crossover with the streaming kernels (profiles/r02_small_domains.csv): ~72 k columns in Float32,
-    // ~30 k in Float64 (lanes = layers of one column diverge where adjacent columns of one layer do not, and the Float64
-    // fast-math sequences are longer): default limit 65536 / 24576 columns (TRM_WARP_COLS overrides it ; TRM_WARP=0
-    // switches the kernel off ; tests compare both within a process).
+    // warps). Measured crossover with the streaming kernels (profiles/r02_warp_crossover.txt): ~115 k columns in Float32
+    // (Heun: ~200 k), ~55 k in Float64 (lanes = layers of one column diverge where adjacent columns of one layer do not, and
+    // the Float64 fast-math sequences are longer): default limit 114688 / 49152 columns (TRM_WARP_COLS overrides it ;
+    // TRM_WARP=0 switches the kernel off ; tests compare both within a process).
     bool use_warp() const {
         if (land || euler_impl != 1 || nz > 31) return false;
         const char* e = std::getenv("TRM_WARP");
         if (e && e[0] == '0') return false;
         const char* m = std::getenv("TRM_WARP_COLS");
-        const int64_t max_cols = m ? std::atoll(m) : (sizeof(NF) == 4 ? 65536 : 24576);
+        const int64_t max_cols = m ? std::atoll(m) : (sizeof(NF) == 4 ? 114688 : 49152);
         return nc <= max_cols;
     }
     int enqueue_steps_warp(NF dt, int64_t n);

@@ -5,7 +5,8 @@
 // sweep over the nz layers (23 us Float32, 33 us Float64), whatever the column count. The explicit scheme is parallel
 // over the layers of a column, so here the 32 lanes of a warp hold the layers of ONE column (lane l = layer l + 1, lane nz
 // = the halo cell above the surface, nz <= 31): the vertical stencil is five warp shuffles per evaluation, the water
-// table is a ballot, the (rare) saturation sweeps run through shuffles, and because columns never interact the warp
+// table is a ballot, the upward saturation sweep is a five-round scan (fast math; the reference's sequential chain in faithful
+// math and for the rare downward sweep), and because columns never interact the warp
 // advances its column `nsteps` steps with U, sat, the water table and the surface excess water in registers -- global
 // memory is touched at the start and at the end of the launch only. Heun runs both stages back to back in the same
 // registers (no stage state, no k1 in memory). Per-cell arithmetic: the functions of column_physics.cuh in the order of
@@ -110,12 +111,27 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
         return pressure_head<NF, FAST, VG2>(p, s, wt, zC_k, psiz_k);
     };
     const bool halo_copy = RICH || p.sat_halo == TRM_HALO_COPY;
+    // boundary condition kinds are launch uniform: read once, not once per step
+    const int kT_top = A.bc[TRM_BC_TEMPERATURE_TOP].kind, kT_bot = A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind;
+    const int kP_top = A.bc[TRM_BC_PRESSURE_TOP].kind, kP_bot = A.bc[TRM_BC_PRESSURE_BOTTOM].kind;
+    const bool fE_top = A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX, fE_bot = A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX;
+    const bool fS_top = RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX, fS_bot = RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX;
+    // Oceananigans halo fill (halo_value, stage_kernel.cuh). Fast math: a Value BC is edge + (v - edge) / (D / 2) * D =
+    // edge + 2 (v - edge) without the division, evaluated with selects (every lane computes, the halo lanes keep the result)
+    auto halo = [&](int kind, NF edge, NF v, NF D, bool top) -> NF {
+        if (!FAST) return halo_value(kind, edge, v, D, top);
+        const NF val = fma_(NF(2), v - edge, edge);
+        const NF grad = top ? fma_(v, D, edge) : fma_(-v, D, edge);
+        return kind == TRM_BC_VALUE ? val : (kind == TRM_BC_GRADIENT ? grad : edge);
+    };
     auto kappa_dry = [&]() -> NF { return FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)); };
 
     // compute_auxiliary! + compute_tendencies! on the state (Ux, sx, wtx): tendencies of this lane's layer, before Flux BCs
     auto evaluate = [&](NF Ux, NF sx, NF wtx, bool stage2, bool loaded, NF& tU, NF& tS) {
-        const NF bT_top = bc_val(TRM_BC_TEMPERATURE_TOP, stage2), bT_bot = bc_val(TRM_BC_TEMPERATURE_BOTTOM, stage2);
-        const NF bP_top = RICH ? bc_val(TRM_BC_PRESSURE_TOP, stage2) : NF(0), bP_bot = RICH ? bc_val(TRM_BC_PRESSURE_BOTTOM, stage2) : NF(0);
+        const NF bT_top = kT_top != TRM_BC_DEFAULT ? bc_val(TRM_BC_TEMPERATURE_TOP, stage2) : NF(0);
+        const NF bT_bot = kT_bot != TRM_BC_DEFAULT ? bc_val(TRM_BC_TEMPERATURE_BOTTOM, stage2) : NF(0);
+        const NF bP_top = (RICH && kP_top != TRM_BC_DEFAULT) ? bc_val(TRM_BC_PRESSURE_TOP, stage2) : NF(0);
+        const NF bP_bot = (RICH && kP_bot != TRM_BC_DEFAULT) ? bc_val(TRM_BC_PRESSURE_BOTTOM, stage2) : NF(0);
         NF T = NF(0), liq = NF(1), P = NF(0), kap = NF(0), Kc = NF(0);
         if (isL) {
             if (loaded) { T = A.xT[o]; liq = A.xL[o]; if (RICH) P = A.xP[o]; }
@@ -136,16 +152,32 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
             const NF Kf_dn = __shfl_up_sync(FULL, Kf, 1);
             if (isH) Kf = Kf_dn;
         }
-        if (isH) {   // halo cell above the surface, from layer nz (fill_halo_regions!)
-            T = halo_value(A.bc[TRM_BC_TEMPERATURE_TOP].kind, T_dn, bT_top, dzf_k, true);
-            kap = halo_copy ? kap_dn : kappa_dry();
-            if (RICH) P = halo_value(A.bc[TRM_BC_PRESSURE_TOP].kind, P_dn, bP_top, dzf_k, true);
-        }
         NF Tp = T_dn, kapp = kap_dn, Pp = P_dn;
-        if (isBot) {  // halo cell below the bottom layer
-            Tp = halo_value(A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind, T, bT_bot, dzf_k, false);
-            kapp = halo_copy ? kap : kappa_dry();
-            if (RICH) Pp = halo_value(A.bc[TRM_BC_PRESSURE_BOTTOM].kind, P, bP_bot, dzf_k, false);
+        if (FAST) {
+            // halo cell above the surface (lane nz, from layer nz) and below the bottom layer (lower neighbour of lane 0)
+            // (fill_halo_regions!), branch free
+            const NF Th = halo(kT_top, T_dn, bT_top, dzf_k, true), Tb = halo(kT_bot, T, bT_bot, dzf_k, false);
+            const NF kd = halo_copy ? NF(0) : kappa_dry();
+            T = isH ? Th : T;
+            kap = isH ? (halo_copy ? kap_dn : kd) : kap;
+            Tp = isBot ? Tb : Tp;
+            kapp = isBot ? (halo_copy ? kap : kd) : kapp;
+            if (RICH) {
+                const NF Ph = halo(kP_top, P_dn, bP_top, dzf_k, true), Pb = halo(kP_bot, P, bP_bot, dzf_k, false);
+                P = isH ? Ph : P;
+                Pp = isBot ? Pb : Pp;
+            }
+        } else {
+            if (isH) {
+                T = halo(kT_top, T_dn, bT_top, dzf_k, true);
+                kap = halo_copy ? kap_dn : kappa_dry();
+                if (RICH) P = halo(kP_top, P_dn, bP_top, dzf_k, true);
+            }
+            if (isBot) {
+                Tp = halo(kT_bot, T, bT_bot, dzf_k, false);
+                kapp = halo_copy ? kap : kappa_dry();
+                if (RICH) Pp = halo(kP_bot, P, bP_bot, dzf_k, false);
+            }
         }
         // heat flux and head gradient at face k (diffusive_heat_flux, soil_energy.jl:134-149), faces 1 .. nz + 1
         NF qh = NF(0), g = NF(0);
@@ -172,8 +204,7 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     };
     // Flux boundary conditions of the time-n state on the tendencies of the top / bottom layer (compute_z_bcs!)
     auto apply_flux_bcs = [&](NF& tU, NF& tS) {
-        const bool fE_top = A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX, fE_bot = A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX;
-        const bool fS_top = RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX, fS_bot = RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX;
+        if (!(fE_top || fE_bot || fS_top || fS_bot)) return;
         const NF vE_top = fE_top ? bc_val(TRM_BC_ENERGY_TOP, false) : NF(0), vS_top = fS_top ? bc_val(TRM_BC_SATURATION_TOP, false) : NF(0);
         const NF vE_bot = fE_bot ? bc_val(TRM_BC_ENERGY_BOTTOM, false) : NF(0), vS_bot = fS_bot ? bc_val(TRM_BC_SATURATION_BOTTOM, false) : NF(0);
         if (isTop) {
@@ -191,7 +222,25 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     auto adjust = [&](NF sn, NF& Sx, NF& wt, int& idx, bool& slow) -> NF {
         // upward sweep (:192-199): excess of a layer is handed to the layer above, scaled by the thickness ratio
         const bool over = isL && !isTop && sn > NF(1);
-        if (__any_sync(FULL, over)) {
+        if (FAST && __any_sync(FULL, over)) {
+            // The carry out of a layer as a function of the carry in is h(c) = max(r (s + c - 1), 0) = max(alpha c + beta, gamma)
+            // with alpha = r (thickness ratio), beta = r (s - 1), gamma = 0 -- a family closed under composition,
+            // (a2, b2, g2) o (a1, b1, g1) = (a2 a1, a2 b1 + b2, max(a2 g1 + b2, g2)) -- so the carries of the whole column are
+            // an inclusive scan over the lanes (five shuffle rounds) evaluated at c = 0 instead of a chain through nz layers.
+            // Same recurrence, different association: the carries agree with the sequential form to rounding.
+            const bool mid = isL && !isTop;
+            const NF r = dzc_k * rdzc_up;
+            NF al = mid ? r : NF(0), be = mid ? r * (sn - 1) : NF(0), ga = NF(0);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const NF a1 = __shfl_up_sync(FULL, al, d), b1 = __shfl_up_sync(FULL, be, d), g1 = __shfl_up_sync(FULL, ga, d);
+                if (lane >= d) { ga = Mx::mx(fma_(al, g1, be), ga); be = fma_(al, b1, be); al = al * a1; }
+            }
+            NF cin = __shfl_up_sync(FULL, Mx::mx(be, ga), 1);
+            cin = isBot ? NF(0) : cin;
+            sn = sn + cin;
+            if (mid) { const NF e = Mx::pos(sn - 1); sn -= e; }
+        } else if (__any_sync(FULL, over)) {
             NF carry = NF(0);
 #pragma unroll 1
             for (int l = 0; l < nz; ++l) {
