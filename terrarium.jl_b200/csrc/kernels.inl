@@ -101,13 +101,18 @@ template <class T>
 inline int euler2_soil(int phys, int mode, int load_aux, const StageArgs<T>& a) {
     const char* e = std::getenv(sizeof(T) == 4 ? "TRM_F32X2" : "TRM_F64X2");   // (read per launch: tests compare both kernels within one process)
     if ((e && e[0] == '0') || load_aux) return -1;
-    // Float64: the one-column kernel is the faster one on the 10 M-column step (3.17 ms against 3.24 - 3.34 ms of the pair
-    // instantiations, profiles/r02_sweep_compact_metrics.txt): the Float64 pair kernel runs on request only (TRM_F64X2=1)
-    if (sizeof(T) == 8 && (mode != MODE_EULER || !(e && e[0] == '1'))) return -1;
-    if (!phys_richards(phys)) return SOIL2_VG2;
-    if (a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN) return SOIL2_VG2;
-    if (a.p.swrc == TRM_SWRC_BROOKSCOREY && a.p.bc_k > 0 && a.p.unsat_k == TRM_UNSATK_LINEAR) return SOIL2_BC_LINEAR;
-    return -1;
+    if (sizeof(T) == 8 && mode != MODE_EULER) return -1;   // (the Float64 Heun stages run the recompute protocol of euler_kernel)
+    int soil = -1;
+    if (!phys_richards(phys)) soil = SOIL2_VG2;
+    else if (a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN) soil = SOIL2_VG2;
+    else if (a.p.swrc == TRM_SWRC_BROOKSCOREY && a.p.bc_k > 0 && a.p.unsat_k == TRM_UNSATK_LINEAR) soil = SOIL2_BC_LINEAR;
+    // Float64, van Genuchten n = 2 / immobile water: the one-column kernel has its own compile-time instantiation and is the
+    // faster one on the 10 M-column step (3.17 ms against 3.24 - 3.34 ms, profiles/r02_sweep_compact_metrics.txt): the pair
+    // kernel runs on request only (TRM_F64X2=1). The default Brooks-Corey + linear soil has a compile-time instantiation
+    // only here (the one-column kernel takes the general out-of-line formulas: 4.9 against 3.1 ms per 60 steps on 131 072
+    // columns of the reference's benchmark design), so it stays on the pair kernel.
+    if (sizeof(T) == 8 && soil == SOIL2_VG2 && !(e && e[0] == '1')) return -1;
+    return soil;
 }
 template <class T>
 inline cudaError_t launch_euler2(int phys, int mode, int soil, const StageArgs<T>& a, cudaStream_t st) {
@@ -151,22 +156,27 @@ cudaError_t launch_euler(int phys, int mode, int load_aux, const StageArgs<NF>& 
     }
 }
 
-// one warp per column, nsteps steps per launch (warp_kernel.cuh): SoilModel, nz <= 31
-template <class NF>
-cudaError_t launch_warp(int phys, int heun, int nsteps, const StageArgs<NF>& a, cudaStream_t st) {
-    if (phys_land(phys) || a.nz > WARP_MAX_NZ || a.nz < 1) return cudaErrorInvalidConfiguration;
+// one warp per column, nsteps steps per launch (warp_kernel.cuh): nz <= 31 ; LandModel: one step per launch, after surface_kernel
+template <class NF, bool LAND>
+cudaError_t launch_warp_land(bool rich, int heun, int nsteps, const StageArgs<NF>& a, cudaStream_t st) {
     constexpr int cols = TRM_WARP_BLOCK / 32;
     const unsigned nblk = (unsigned)((a.ncol + cols - 1) / cols);
-    if (phys == PHYS_NOFLOW) { column_warp_kernel<NF, false, kFast, WSOIL_GENERIC><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun); return cudaGetLastError(); }
+    if (!rich) { column_warp_kernel<NF, false, kFast, WSOIL_GENERIC, LAND><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun); return cudaGetLastError(); }
 #if TRM_FAST
     if (a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN)
-        column_warp_kernel<NF, true, true, WSOIL_VG2><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
+        column_warp_kernel<NF, true, true, WSOIL_VG2, LAND><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
     else if (a.p.swrc == TRM_SWRC_BROOKSCOREY && a.p.bc_k > 0 && a.p.unsat_k == TRM_UNSATK_LINEAR)
-        column_warp_kernel<NF, true, true, WSOIL_BC_LINEAR><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
+        column_warp_kernel<NF, true, true, WSOIL_BC_LINEAR, LAND><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
     else
 #endif
-        column_warp_kernel<NF, true, kFast, WSOIL_GENERIC><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
+        column_warp_kernel<NF, true, kFast, WSOIL_GENERIC, LAND><<<nblk, TRM_WARP_BLOCK, 0, st>>>(a, nsteps, heun);
     return cudaGetLastError();
+}
+template <class NF>
+cudaError_t launch_warp(int phys, int heun, int nsteps, const StageArgs<NF>& a, cudaStream_t st) {
+    if (a.nz > WARP_MAX_NZ || a.nz < 1 || (phys_land(phys) && nsteps != 1)) return cudaErrorInvalidConfiguration;
+    return phys_land(phys) ? launch_warp_land<NF, true>(phys_richards(phys), heun, nsteps, a, st)
+                           : launch_warp_land<NF, false>(phys_richards(phys), heun, nsteps, a, st);
 }
 
 template <class NF>

@@ -140,6 +140,9 @@ struct StageArgs {
     // state a stage kernel writes (accumulated there while the closure fields of the new state are formed)
     const NF* xbeta;
     NF* ybeta;
+    // (warp-per-column kernel, vegetated LandModel under Heun) what the stage-2 surface launch reads: top layer of the stage
+    // state (stored into the stage fields) and the factor of the stage state
+    NF *stU, *stS, *sbeta;
     // per-step exchange with a host-side coupler (trm_bind_host_io): when non-null, the temperature of the top layer of
     // the state this launch writes (ground_temperature) is also stored here -- a device pointer to page-locked, mapped
     // host memory, written straight from the stage kernel (no copy engine, no staging buffer)

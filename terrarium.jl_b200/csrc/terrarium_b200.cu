@@ -563,18 +563,21 @@ struct Handle : HandleBase {
     bool heun_rc() const { return heun_recompute<NF>() && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     bool split_surface() const { return land && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     int enqueue_steps(double dt, int64_t n);
-    // small domains (warp_kernel.cuh): one warp per column, several steps per launch. Applies to the SoilModel with
-    // nz <= 31 while the column count leaves the one-thread-per-column kernels latency bound (less than about one wave of
+    // small domains (warp_kernel.cuh): one warp per column, several steps per launch (LandModel: surface_kernel + one
+    // launch per step, both Heun stages in it). Applies with nz <= 31 while the column count leaves the one-thread-per-column kernels latency bound (less than about one wave of
     // warps). Measured crossover with the streaming kernels (profiles/r02_warp_crossover.txt): ~115 k columns in Float32
     // (Heun: ~200 k), ~55 k in Float64 (lanes = layers of one column diverge where adjacent columns of one layer do not, and
     // the Float64 fast-math sequences are longer): default limit 114688 / 49152 columns (TRM_WARP_COLS overrides it ;
     // TRM_WARP=0 switches the kernel off ; tests compare both within a process).
     bool use_warp() const {
-        if (land || euler_impl != 1 || nz > 31) return false;
+        if (euler_impl != 1 || nz > 31) return false;
         const char* e = std::getenv("TRM_WARP");
         if (e && e[0] == '0') return false;
         const char* m = std::getenv("TRM_WARP_COLS");
-        const int64_t max_cols = m ? std::atoll(m) : (sizeof(NF) == 4 ? 114688 : 49152);
+        // LandModel: one step per launch (the surface block runs in between), so the copies of the column tile between global
+        // memory and the registers are paid every step: the streaming kernels win earlier (N145, vegetated, Float32: 73 against
+        // 53 us per ForwardEuler step ; N72: 46 against 101 us per Heun step)
+        const int64_t max_cols = m ? std::atoll(m) : (land ? (sizeof(NF) == 4 ? 32768 : 16384) : (sizeof(NF) == 4 ? 114688 : 49152));
         return nc <= max_cols;
     }
     int enqueue_steps_warp(NF dt, int64_t n);
@@ -676,27 +679,63 @@ template <> cudaError_t Handle<double>::call_warp(int nsteps, const StageArgs<do
 // included. Inputs whose descriptor changes from step to step on the host side (tables / rasters: time bracket ; host
 // evaluated functions: value pair ; a mapped host exchange: ring slot) limit a launch to one step.
 template <class NF> int Handle<NF>::enqueue_steps_warp(NF dt, int64_t n) {
-    bool per_step = hio.nslots != 0;
+    bool per_step = hio.nslots != 0 || land;   // LandModel: the surface block is a launch of its own before every step
     for (int i = 0; i < TRM_IN_COUNT; ++i)
         if (in[i].kind == TRM_SRC_TABLE || in[i].kind == TRM_SRC_RASTER || in[i].kind == TRM_SRC_FIELD_PAIR) per_step = true;
     int64_t done = 0;
     while (done < n) {
         const int64_t chunk = per_step ? 1 : std::min<int64_t>(n - done, 1 << 30);
-        StageArgs<NF> a; base_args(a);
         const NF t = (NF)time;
+        const NF t1 = t + dt;
+        if (land) {
+            // surface block on the time-n state (land_model.jl:79-88): leaves the ground heat flux / infiltration that the warp
+            // kernel applies as top Flux BCs; same arguments as the stage-1 / ForwardEuler surface launch of enqueue_steps
+            if (veg && beta_stale) {
+                StageArgs<NF> g; base_args(g); x_state(g);
+                if (int rc = launch_surface(1, g)) return rc;
+            }
+            StageArgs<NF> a; base_args(a);
+            a.dt = dt; a.mode = heun ? MODE_HEUN1 : MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
+            a.load_aux = (aux_stale || force_load) ? 1 : 0;
+            if (heun) {
+                a.yU = gU; a.yS = gS; a.yWt = gWt; a.ySx = nullptr; a.oTU = tU; a.oTS = tS;
+                for (int i = 0; i < 3; ++i) { a.vy[i] = gveg[i]; a.vok1[i] = tveg[i]; }
+                a.ybeta = gbeta;
+            }
+            set_times(a);
+            apply_host_io(a, !heun);
+            if (int rc = launch_surface(0, a)) return rc;
+        }
+        StageArgs<NF> a; base_args(a);
         a.dt = dt; a.mode = heun ? MODE_HEUN1 : MODE_EULER; a.t_x = t; a.t_b = t; x_state(a); y_state(a);
         a.load_aux = (aux_stale || force_load) ? 1 : 0;
+        a.stU = gU; a.stS = gS; a.sbeta = gbeta;   // (vegetated LandModel, Heun) top layer and factor of the stage state
         // time index of the descriptors inside this kernel: 0 = start of the step, 1 = start + dt (Heun stage 2)
         for (int i = 0; i < TRM_IN_COUNT; ++i) {
             if (in[i].kind == TRM_SRC_TABLE || in[i].kind == TRM_SRC_RASTER) {
                 bracket(in[i], (double)t, a.in[i].br[0]);
-                bracket(in[i], (double)(NF)(t + dt), a.in[i].br[1]);
+                bracket(in[i], (double)t1, a.in[i].br[1]);
             }
             if (in[i].kind == TRM_SRC_FIELD_PAIR) { a.in[i].a = in[i].a; a.in[i].b = in[i].b; }
         }
         apply_host_io(a, true);
         cudaError_t e = call_warp((int)chunk, a); ++launches;
         if (e != cudaSuccess) return fail(TRM_ERR_CUDA, std::string("warp kernel launch: ") + cudaGetErrorString(e));
+        if (land && veg && heun) {
+            // Heun stage 2 of the vegetated model: the vegetation block on the stage state at t + dt, for k2 of canopy water,
+            // vegetation carbon and area fraction only (heun.jl:45-58) -- it feeds nothing back into the soil step, so it runs
+            // after the kernel that formed the stage state; same arguments as the stage-2 surface launch of enqueue_steps
+            StageArgs<NF> b; base_args(b);
+            b.dt = dt; b.mode = MODE_HEUN2; b.load_aux = 0; b.t_x = t1; b.t_b = t;
+            b.xU = gU; b.xS = richards ? gS : S; b.xWt = gWt; b.bU = U; b.bS = S; b.bSx = Sx; b.k1U = tU; b.k1S = tS;
+            for (int i = 0; i < 3; ++i) { b.vx[i] = gveg[i]; b.vk1[i] = tveg[i]; }
+            b.xbeta = gbeta;
+            y_state(b);
+            set_times(b);
+            pair_stage2(b);
+            apply_host_io(b, true);
+            if (int rc = launch_surface(0, b)) return rc;
+        }
         if (hio.nslots) {
             const int64_t slot = iteration % hio.nslots;
             if (hio.out_id >= 0 && hio.out_id != TRM_F_GROUND_TEMPERATURE) {
@@ -705,7 +744,7 @@ template <class NF> int Handle<NF>::enqueue_steps_warp(NF dt, int64_t n) {
             }
             CU(cudaEventRecord(hio.ev[slot], stream));
         }
-        aux_stale = false; beta_stale = true;
+        aux_stale = false; beta_stale = !(land && veg);   // (the LandModel variant leaves the factor of the new state behind)
         for (int64_t i = 0; i < chunk; ++i) {   // tick!(clock, dt) in the clock's number format, like the kernel
             const NF ts = (NF)time;
             t_inputs = (double)ts;

@@ -13,7 +13,12 @@
 // the streaming kernels (same reference citations), so both kernels agree to rounding and, where no transcendental and no
 // contraction is involved (faithful math, heat only), bit for bit.
 //
-// SoilModel only (energy + Richards or immobile water); the LandModel variants keep the streaming kernels.
+// LandModel (LAND): the per-column surface block stays a launch of its own (surface_kernel, stage_kernel.cuh: per-column scalar
+// work that a lane-per-layer layout cannot spread), so a LandModel step is surface_kernel + ONE launch of this kernel with
+// nsteps = 1: the ground heat flux and the infiltration it left behind are the top Flux BCs, both Heun stages run here (stage 2
+// applies the same time-n fluxes, heun.jl:63-66), and for the vegetated model the kernel leaves what the surface launches need:
+// the soil moisture limiting factor of the new state and -- Heun -- of the stage state, plus the stage state's top layer, on
+// which the stage-2 surface launch (k2 of the vegetation prognostics only) runs AFTER this kernel.
 #pragma once
 
 #include "stage_kernel.cuh"
@@ -21,7 +26,7 @@
 namespace trm {
 
 #ifndef TRM_WARP_BLOCK
-#define TRM_WARP_BLOCK 128   // four columns per block
+#define TRM_WARP_BLOCK 128   // four adjacent columns per block (measured equal to eight: profiles/r02_summary.md)
 #endif
 constexpr int WARP_MAX_NZ = 31;   // lane nz is the halo cell above the surface
 
@@ -53,20 +58,36 @@ __device__ __forceinline__ NF cell_conductivity_linear_fast(const DevParams<NF>&
     return (water * p.Ksat) * M<NF, true>::rcp((water + ice) + air);
 }
 
-template <class NF, bool RICH, bool FAST, int SOIL>
-__global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, const int heun) {
+template <class NF, bool RICH, bool FAST, int SOIL, bool LAND = false>
+__global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512) / TRM_WARP_BLOCK) /* <= 64 / 128 registers: 32 / 16 warps per SM */ column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, const int heun) {
     using Mx = M<NF, FAST>;
     constexpr bool VG2 = SOIL == WSOIL_VG2;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * (TRM_WARP_BLOCK / 32) + (threadIdx.x >> 5);
-    if (c >= A.ncol) return;   // (a whole warp leaves together)
+    // A block owns CW adjacent columns. Fields are [layer][column]: a lane of a column's warp would touch one 4-byte element
+    // of a sector per access, so the block moves its nz x CW tile of every field between global and shared memory with all
+    // threads (CW consecutive threads = one contiguous row segment: 16 / 32 bytes of a 32-byte sector in Float32 / Float64
+    // instead of 4 / 8) and the warps pick their column out of the tile. That matters when a launch advances one step only (LandModel, per-step callers): loads and stores are
+    // then the larger part of the launch.
+    constexpr int CW = TRM_WARP_BLOCK / 32, TS = CW + 1;   // (odd row stride: the column reads are bank-conflict free)
+    __shared__ NF tile[5][32 * TS];
+    const int wi = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * CW;
+    // Warps past the last column of a ragged last block repeat the work of the last column and store nothing: every warp runs
+    // the same code, so the compiler keeps the shuffles free of re-convergence code (a loop that depends on `active`, which it
+    // cannot prove warp-uniform, cost a WARPSYNC sequence per shuffle and 15-20 % of the step time).
+    const bool active = c0 + wi < A.ncol;
+    const int wc = active ? wi : (int)(A.ncol - 1 - c0);   // column of the tile this warp computes
+    const int64_t c = c0 + wc;
+    const int tr = threadIdx.x / CW, tc = threadIdx.x % CW;   // this thread's element of the tile in the cooperative copies
+    const int64_t tg = (int64_t)tr * A.ld + c0 + tc;          // (rows are padded to a multiple of 64 columns: reads stay in bounds)
     const DevParams<NF>& p = A.p;
     const int nz = A.nz;
     const int k = lane + 1;                               // 1-based layer (lanes < nz) / face index (lanes <= nz)
     const bool isL = lane < nz, isH = lane == nz, isTop = lane == nz - 1, isBot = lane == 0;
     const NF dt = A.dt;
     const int64_t o = (int64_t)lane * A.ld + c;           // this lane's cell in a [layer][column] field
+    const int to = lane * TS + wc;                        // ... and in the shared-memory tile
 
     // grid metrics of this lane's layer / lower face, read once (rows of MET_STRIDE values, 1-based + halos)
     const NF* met = A.metrics;
@@ -114,8 +135,20 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     // boundary condition kinds are launch uniform: read once, not once per step
     const int kT_top = A.bc[TRM_BC_TEMPERATURE_TOP].kind, kT_bot = A.bc[TRM_BC_TEMPERATURE_BOTTOM].kind;
     const int kP_top = A.bc[TRM_BC_PRESSURE_TOP].kind, kP_bot = A.bc[TRM_BC_PRESSURE_BOTTOM].kind;
-    const bool fE_top = A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX, fE_bot = A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX;
-    const bool fS_top = RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX, fS_bot = RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX;
+    const bool fE_top = !LAND && A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX, fE_bot = A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX;
+    const bool fS_top = !LAND && RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX, fS_bot = RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX;
+    const NF G_top = LAND ? A.G[c] : NF(0), infil_top = (LAND && RICH) ? A.infil[c] : NF(0);   // (LandModel launches advance one step)
+    const bool veg = LAND && has_veg(A);
+    const NF root_k = veg ? met[MET_ROOT * MET_STRIDE + kc] : NF(0);
+    // soil moisture limiting factor of a state: Integral(PAW * root_fraction / dz, dims = 3) (plant_available_water.jl:31-35),
+    // a warp sum here (the streaming kernels and the oracle add bottom -> top: equal to rounding)
+    auto beta_of = [&](NF sat, NF liq) -> NF {
+        NF b = NF(0);
+        if (isL) b = FAST ? plant_available_water_fast(A.vp, p, sat, liq) * root_k : plant_available_water(A.vp, p, sat, liq) * root_k / dzc_k * dzc_k;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) b += __shfl_xor_sync(FULL, b, d);
+        return b;
+    };
     // Oceananigans halo fill (halo_value, stage_kernel.cuh). Fast math: a Value BC is edge + (v - edge) / (D / 2) * D =
     // edge + 2 (v - edge) without the division, evaluated with selects (every lane computes, the halo lanes keep the result)
     auto halo = [&](int kind, NF edge, NF v, NF D, bool top) -> NF {
@@ -127,14 +160,14 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     auto kappa_dry = [&]() -> NF { return FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)); };
 
     // compute_auxiliary! + compute_tendencies! on the state (Ux, sx, wtx): tendencies of this lane's layer, before Flux BCs
-    auto evaluate = [&](NF Ux, NF sx, NF wtx, bool stage2, bool loaded, NF& tU, NF& tS) {
+    auto evaluate = [&](NF Ux, NF sx, NF wtx, bool stage2, bool loaded, NF& tU, NF& tS, NF& liq_out) {
         const NF bT_top = kT_top != TRM_BC_DEFAULT ? bc_val(TRM_BC_TEMPERATURE_TOP, stage2) : NF(0);
         const NF bT_bot = kT_bot != TRM_BC_DEFAULT ? bc_val(TRM_BC_TEMPERATURE_BOTTOM, stage2) : NF(0);
         const NF bP_top = (RICH && kP_top != TRM_BC_DEFAULT) ? bc_val(TRM_BC_PRESSURE_TOP, stage2) : NF(0);
         const NF bP_bot = (RICH && kP_bot != TRM_BC_DEFAULT) ? bc_val(TRM_BC_PRESSURE_BOTTOM, stage2) : NF(0);
         NF T = NF(0), liq = NF(1), P = NF(0), kap = NF(0), Kc = NF(0);
         if (isL) {
-            if (loaded) { T = A.xT[o]; liq = A.xL[o]; if (RICH) P = A.xP[o]; }
+            if (loaded) { T = tile[2][to]; liq = tile[3][to]; if (RICH) P = tile[4][to]; }   // (the tile holds the inputs until the end)
             else {
                 energy_to_temperature<NF, FAST>(p, Ux, sx, T, liq);
                 if (RICH) P = pressure(sx, wtx);
@@ -142,6 +175,7 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
             kap = FAST ? thermal_conductivity_fast(p, sx, liq) : thermal_conductivity(p, sx, liq);
             if (RICH) Kc = (FAST && SOIL == WSOIL_BC_LINEAR) ? cell_conductivity_linear_fast(p, sx, liq) : cell_conductivity<NF, FAST, VG2>(p, sx, liq);
         }
+        liq_out = liq;
         const NF T_dn = __shfl_up_sync(FULL, T, 1), kap_dn = __shfl_up_sync(FULL, kap, 1);
         NF P_dn = NF(0), Kf = NF(0);
         if (RICH) {
@@ -204,6 +238,10 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     };
     // Flux boundary conditions of the time-n state on the tendencies of the top / bottom layer (compute_z_bcs!)
     auto apply_flux_bcs = [&](NF& tU, NF& tS) {
+        if (LAND && isTop) {   // ground heat flux and infiltration left by surface_kernel (land_model.jl:56-62)
+            tU -= G_top / dzc_k;
+            if (RICH) tS -= (-infil_top) / dzc_k;
+        }
         if (!(fE_top || fE_bot || fS_top || fS_bot)) return;
         const NF vE_top = fE_top ? bc_val(TRM_BC_ENERGY_TOP, false) : NF(0), vS_top = fS_top ? bc_val(TRM_BC_SATURATION_TOP, false) : NF(0);
         const NF vE_bot = fE_bot ? bc_val(TRM_BC_ENERGY_BOTTOM, false) : NF(0), vS_bot = fS_bot ? bc_val(TRM_BC_SATURATION_BOTTOM, false) : NF(0);
@@ -302,8 +340,13 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     };
 
     // ---- state of the column: registers for the whole launch ----
+    if (tr < A.nz) {
+        tile[0][tr * TS + tc] = A.xU[tg]; tile[1][tr * TS + tc] = A.xS[tg];
+        if (A.load_aux) { tile[2][tr * TS + tc] = A.xT[tg]; tile[3][tr * TS + tc] = A.xL[tg]; if (RICH) tile[4][tr * TS + tc] = A.xP[tg]; }
+    }
+    __syncthreads();
     NF U = NF(0), s = NF(0);
-    if (isL) { U = A.xU[o]; s = A.xS[o]; }
+    if (isL) { U = tile[0][to]; s = tile[1][to]; }
     NF wt = RICH ? A.xWt[c] : NF(0);
     NF Sx = RICH ? A.bSx[c] : NF(0);
     int idx = 0;
@@ -314,8 +357,8 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     for (int step = 0; step < nsteps; ++step) {
         if (si == BC_BLOCK) si = 0;
         if (si == 0) refresh_bcs();
-        NF tU, tS;
-        evaluate(U, s, wt, false, loaded, tU, tS);
+        NF tU, tS, liq_x;
+        evaluate(U, s, wt, false, loaded, tU, tS, liq_x);
         loaded = false;
         if (heun) {
             // heun.jl:37-71: stage state = explicit step with k1 (+ Flux BCs) and its closure, k2 on the stage state at t + dt,
@@ -328,8 +371,15 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
                 NF Sx_stage = NF(0); int idx_s; bool slow_s;
                 ss = adjust(s + t1S * dt, Sx_stage, wts, idx_s, slow_s);   // (the stage copy's surface excess water is not used)
             }
-            NF k2U, k2S;
-            evaluate(Us, ss, wts, true, false, k2U, k2S);
+            NF k2U, k2S, liq_s;
+            evaluate(Us, ss, wts, true, false, k2U, k2S, liq_s);
+            if (veg) {
+                // for the stage-2 surface launch (vegetation block on the stage state, heun.jl:45-58): top layer of the stage
+                // state and its soil moisture limiting factor
+                const NF bs = beta_of(ss, liq_s);
+                if (active && isTop) { A.stU[o] = Us; if (RICH) A.stS[o] = ss; }
+                if (active && lane == 0) A.sbeta[c] = bs;
+            }
             tU = (tU + k2U) / 2;                                          // average_tendencies!, heun.jl:27-35
             if (RICH) tS = (tS + k2S) / 2;
         }
@@ -344,14 +394,17 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
     }
     if (nsteps <= 0) return;
 
-    // ---- closure! of the final state and stores ----
-    if (isL) {
+    // ---- closure! of the final state, results into the tile, cooperative stores ----
+    __syncthreads();   // (every warp is through with the inputs in the tile: it now takes the results)
+    NF lc_new = NF(1);
+    if (isL) {   // (a repeating warp writes the same values to the same tile column)
         NF Tc, lc;
         energy_to_temperature<NF, FAST>(p, U, s, Tc, lc);
-        A.yU[o] = U; A.yT[o] = Tc; A.yL[o] = lc;
-        if (isTop && A.hio_out) A.hio_out[c] = Tc;                        // ground temperature -> mapped host memory
+        tile[0][to] = U; tile[2][to] = Tc; tile[3][to] = lc;
+        if (active && isTop && A.hio_out) A.hio_out[c] = Tc;              // ground temperature -> mapped host memory
+        lc_new = lc;
         if (RICH) {
-            A.yS[o] = s;
+            tile[1][to] = s;
             NF Pc;
             if (slow || (idx != 0 && k >= idx)) Pc = pressure(s, wt);
             else {
@@ -359,10 +412,19 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK) column_warp_kernel(const __gri
                 const NF psat = (FAST && SOIL == WSOIL_BC_LINEAR) ? brooks_corey_psim_fast(p, p.por) : swrc_inverse<NF, FAST, VG2>(p, p.por, p.por);
                 Pc = FAST ? (wt - zsurf) + psat : Mx::mx(NF(0), wt - zC_k) + psat + psiz_k;
             }
-            A.yP[o] = Pc;
+            tile[4][to] = Pc;
         }
     }
-    if (RICH && lane == 0) { A.yWt[c] = wt; A.ySx[c] = Sx; }
+    __syncthreads();
+    if (tr < A.nz && c0 + tc < A.ncol) {
+        A.yU[tg] = tile[0][tr * TS + tc]; A.yT[tg] = tile[2][tr * TS + tc]; A.yL[tg] = tile[3][tr * TS + tc];
+        if (RICH) { A.yS[tg] = tile[1][tr * TS + tc]; A.yP[tg] = tile[4][tr * TS + tc]; }
+    }
+    if (RICH && active && lane == 0) { A.yWt[c] = wt; A.ySx[c] = Sx; }
+    if (veg) {   // soil moisture limiting factor of the NEW state, for the surface launch of the next step
+        const NF b = beta_of(s, lc_new);
+        if (active && lane == 0) A.ybeta[c] = b;
+    }
 }
 
 }  // namespace trm

@@ -14,6 +14,8 @@ import test_golden
 import test_host_io
 import test_parity
 import test_raster_input
+import test_simulation
+import test_vegetation
 from common import make, max_scaled_err, pointwise_relerr, richards_soil, synthetic_columns, synthetic_soil_case, trm
 
 pytestmark = pytest.mark.gpu
@@ -199,6 +201,28 @@ REPLAYS = [
     (test_raster_input.test_raster_forcing_parity_with_oracle, {}),
     (test_host_io.test_mapped_host_exchange_equals_copies, dict(heun=False, math="fast", nf=np.float64)),
     (test_host_io.test_mapped_host_exchange_equals_copies, dict(heun=True, math="faithful", nf=np.float32)),
+    # LandModel: surface_kernel + one warp launch per step (both Heun stages in it; vegetated: stage-2 surface launch after it)
+    (test_parity.test_land_model_1000_steps, dict(math="faithful", stepper="euler")),
+    (test_parity.test_land_model_1000_steps, dict(math="fast", stepper="heun")),
+    (test_parity.test_land_model_immobile_water_1000_steps, dict(math="fast", stepper="heun")),
+    (test_parity.test_land_model_immobile_water_1000_steps, dict(math="faithful", stepper="euler")),
+    (test_parity.test_land_model_baseline_forcing_until_blow_up, dict(math="fast", stepper="heun")),
+    (test_golden.test_land_model_coupling_signs, dict(engine="cuda")),
+    (test_golden.test_runoff_and_infiltration, dict(engine="cuda")),
+    (test_golden.test_land_model_default_soil_is_immobile_water, dict(engine="cuda", stepper="heun")),
+    (test_golden.test_prescribed_seb_schemes_parity, dict(math="fast")),
+    (test_vegetation.test_vegetated_land_parity_1000_steps, dict(math="fast", heun=False)),
+    (test_vegetation.test_vegetated_land_parity_1000_steps, dict(math="fast", heun=True)),
+    (test_vegetation.test_vegetated_land_parity_1000_steps, dict(math="faithful", heun=True)),
+    (test_vegetation.test_vegetated_land_default_parameters_parity, dict(heun=True)),
+    (test_vegetation.test_vegetated_land_f32_and_noflow_soil, {}),
+    (test_vegetation.test_vegetated_land_layer_counts_and_ragged_columns, dict(nz=7, ncol=129)),
+    (test_vegetation.test_vegetated_land_layer_counts_and_ragged_columns, dict(nz=2, ncol=1)),
+    (test_vegetation.test_user_write_between_steps_refreshes_the_soil_moisture_factor, {}),
+    (test_vegetation.test_coupled_vegetation_soil_step, dict(engine="cuda", stepper="heun")),
+    (test_vegetation.test_land_model_energy_and_water_budgets_close, dict(engine="cuda", vegetated=True)),
+    (test_vegetation.test_land_model_energy_and_water_budgets_close, dict(engine="cuda", vegetated=False)),
+    (test_host_io.test_mapped_host_exchange_land_model, {}),
 ]
 
 
@@ -206,6 +230,35 @@ REPLAYS = [
 def test_replay_through_the_warp_kernel(fn, kw):
     with warp_kernel():
         fn(**kw)
+
+
+@pytest.mark.parametrize("vegetated", [False, True], ids=["bare", "vegetated"])
+@pytest.mark.parametrize("heun", [False, True], ids=["euler", "heun"])
+def test_land_model_warp_equals_streaming(heun, vegetated):
+    """LandModel: surface_kernel + ONE warp launch per step (Heun: both stages in it, the stage-2 surface launch of the vegetated
+    model after it) against the streaming kernels (two stage launches per Heun step)."""
+    from common import synthetic_land_case
+    n = 130
+
+    def build():
+        if vegetated:
+            return test_vegetation.synthetic_vegetated_case("cuda", n, heun=heun, math="fast")
+        return synthetic_land_case("cuda", n, heun=heun, math="fast", windspeed=0.5)
+
+    a, b = build(), build()
+    l0 = launches(a)
+    with warp_kernel():
+        a.step(60.0, 150)
+    # per step: surface launch + warp launch (+ the stage-2 surface launch of the vegetated model under Heun)
+    assert launches(a) - l0 == 150 * (2 + (1 if heun and vegetated else 0)) + (1 if vegetated else 0)
+    b.step(60.0, 150)
+    names = RFIELDS + ("skin_temperature", "ground_heat_flux", "infiltration")
+    if vegetated:
+        names += ("carbon_vegetation", "canopy_water", "vegetation_area_fraction", "soil_moisture_limiting_factor", "transpiration")
+    for name in names:
+        x, y = getattr(a.state, name).numpy(), getattr(b.state, name).numpy()
+        assert np.all(np.isfinite(x)), name
+        assert max_scaled_err(x, y) <= 1.0e-10, (name, max_scaled_err(x, y))
 
 
 def _variant_cases():
