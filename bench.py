@@ -46,9 +46,9 @@ def algorithmic_bytes_per_cell(itemsize: int, nz: int, model: str = "soil", heun
     R/W, water_table R/W, sinusoid forcing parameters (mean, amp, phase) R = 7 values per column. The same figure is the
     algorithmic one for Heun ("Euler or fused Heun: 7 s"): a step reads the state once and writes the new state once.
 
-    `moved = True`: what the TWO stage launches of a Heun step actually move. Float64 (recompute protocol):
-    stage 1 reads U, sat and writes k1 of both; stage 2 reads U, sat, both k1 and writes U, sat, T, liq, psi = 13 values per
-    cell; Float32 keeps the stage state in memory: 17 values. Per column, the bare-ground LandModel moves 22 values (skin
+    `moved = True`: what the TWO stage launches of a Heun step actually move (recompute protocol, both number
+    formats): stage 1 reads U, sat and writes k1 of both; stage 2 reads U, sat, both k1 and writes U, sat, T, liq, psi = 13
+    values per cell. Per column, the bare-ground LandModel moves 22 values (skin
     temperature and surface excess water, 8 forcing parameters / table rows in; 10 surface fields out; G and infiltration read
     back by the stage kernel), the vegetated one 49 (adds 3 prognostic variables R/W, the previous net assimilation, the soil
     moisture factor R/W, SAI, 17 auxiliaries out); a Heun step re-reads G and the infiltration in stage 2 (+2) and, vegetated,
@@ -56,7 +56,7 @@ def algorithmic_bytes_per_cell(itemsize: int, nz: int, model: str = "soil", heun
     per_cell = 7.0
     per_col = {"soil": 7.0, "land": 22.0, "land-veg": 49.0}[model]
     if heun and moved:
-        per_cell = 13.0 if itemsize == 8 else 17.0
+        per_cell = 13.0
         per_col += {"soil": 4.0, "land": 2.0, "land-veg": 27.0}[model]
     return per_cell * itemsize + per_col * itemsize / nz
 

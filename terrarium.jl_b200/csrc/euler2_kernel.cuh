@@ -230,7 +230,8 @@ struct Euler2Smem {
     static constexpr int NSTRIP = BCT_SLOT + 1;
     static constexpr int STRIP = NSTRIP * euler2_block<T>();                          // pair slots
     static constexpr int RING = 2 * EULER_RD * euler2_block<T>();                     // U, sat
-    static constexpr int XRING = (MODE == MODE_HEUN2 ? 4 : 0) * PF_ * euler2_block<T>();   // k1U, k1S, bU, bS
+    // Heun stage 2: k1U, k1S, bU, bS of the layer to be updated (stored protocol) / k1U, k1S next to U, sat (recompute protocol)
+    static constexpr int XRING = (MODE != MODE_HEUN2 ? 0 : (heun_recompute<T>() ? 2 * EULER_RD : 4 * PF_)) * euler2_block<T>();
     static constexpr size_t BYTES = sizeof(T) * (size_t)METRICS + 2 * sizeof(T) * (size_t)(STRIP + RING + XRING);
 };
 
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
     constexpr bool H1 = MODE == MODE_HEUN1, H2 = MODE == MODE_HEUN2;
     constexpr int DIST_ = euler_dist(MODE), PF_ = euler_pf(MODE);
     constexpr bool CLOSE = !H1;
+    constexpr bool RC = heun_recompute<T>() && (H1 || H2);   // Heun "recompute" protocol (stage_kernel.cuh: heun_recompute)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nz = A.nz;
@@ -363,13 +365,17 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
     uint32_t oin = (uint32_t)c;
     const uint32_t xring0 = ring0 + (uint32_t)(SM::RING * ES);
     uint32_t oext = (uint32_t)c;
+    auto k1U_slot = [&](int k) { return xring0 + (uint32_t)((k & (EULER_RD - 1)) * B * ES); };
+    auto k1S_slot = [&](int k) { return xring0 + (uint32_t)(((k & (EULER_RD - 1)) + EULER_RD) * B * ES); };
     auto prefetch = [&](int k, bool always = false) {
         if (always || k <= nz) {
             cp_async<ES>(ringU(k), A.xU + oin);
             cp_async<ES>(ringS(k), A.xS + oin);
+            // (recompute protocol, stage 2) k1 of layer k lives next to U / sat of layer k, from its prefetch until its update
+            if (H2 && RC) { cp_async<ES>(k1U_slot(k), A.k1U + oin); if (RICH) cp_async<ES>(k1S_slot(k), A.k1S + oin); }
             oin += (uint32_t)ld;
         }
-        if (H2) {
+        if (H2 && !RC) {
             const int kk = k - 2;
             if (kk >= 1 && kk <= nz) {
                 const uint32_t dst = xring0 + (uint32_t)((kk & (PF_ - 1)) * B * ES);
@@ -393,6 +399,30 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
     uint32_t oout = (uint32_t)c;
     if (LAND && has_veg(A)) wr(EF_BETA, zero2);
 
+    // Flux boundary conditions of the time-n state (compute_z_bcs!, abstract_timestepper.jl:69) on the tendencies of the top /
+    // bottom layer. LandModel: ground heat flux and infiltration left by surface_kernel (land_model.jl:56-62)
+    auto apply_top_flux = [&](F2& tU, F2& tS) {
+        const T dz = met.dzc(nz);
+        if (LAND) {
+            const F2 G_top = ldg2(A.G + c);
+            tU = F2{tU.x - G_top.x / dz, tU.y - G_top.y / dz};
+            if (RICH) { const F2 infil_top = ldg2(A.infil + c); tS = F2{tS.x - (-infil_top.x) / dz, tS.y - (-infil_top.y) / dz}; }
+        } else {
+            if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_ENERGY_TOP); tU = F2{tU.x - f.x / dz, tU.y - f.y / dz}; }
+            if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_SATURATION_TOP); tS = F2{tS.x - f.x / dz, tS.y - f.y / dz}; }
+        }
+    };
+    auto apply_bottom_flux = [&](F2& tU, F2& tS) {
+        const T dz = met.dzc(1);
+        if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_ENERGY_BOTTOM); tU = F2{tU.x + f.x / dz, tU.y + f.y / dz}; }
+        if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_SATURATION_BOTTOM); tS = F2{tS.x + f.x / dz, tS.y + f.y / dz}; }
+    };
+    // recompute protocol, stage 2: upward-sweep carry of the stage state being rebuilt ; columns whose stage state was stored
+    F2 carry1 = zero2;
+    const bool flagx = (H2 && RC && RICH) ? (A.hflag_in[c] != T(0)) : false;
+    const bool flagy = (H2 && RC && RICH) ? (A.hflag_in[c1] != T(0)) : false;
+    uint32_t oent = (uint32_t)c;       // element offset of the entering layer (stored stage state of a flagged column)
+
     F2 Ur_nx = zero2, sr_nx = zero2;   // raw U / sat of the layer that enters next
     // One pipeline iteration (see euler_kernel). The flux slots hold the NEGATED fluxes: EF_QH = kappa_f dT/dz,
     // EF_QD = K* dpsi/dz, so that the tendencies come out of one packed FFMA each without sign flips.
@@ -409,7 +439,7 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
         const bool j_is_1 = GEN ? m == 3 : POS == IP_M3;
         const bool j_is_nz = GEN ? m == nz + 2 : POS == IP_LAST;
         if (POS == IP_INNER) prefetch(m + DIST_, true);
-        else if (POS >= IP_INNER_NP && !H2) {   // no layer left to prefetch (Heun stage 2 still fetches k1 / the base state of layer m+DIST-2)
+        else if (POS >= IP_INNER_NP && !(H2 && !RC)) {   // no layer left to prefetch (stored protocol: Heun stage 2 still fetches k1 / the base state of layer m+DIST-2)
             cp_async_commit();
         }
         else prefetch(m + DIST_, false);
@@ -418,8 +448,31 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
         if (enters) {
             // (the raw values of the entering layer were read from the ring at the end of the previous iteration: the
             //  shared-memory latency overlaps the update / closure arithmetic of that iteration instead of heading this one)
-            const F2 Ur = Ur_nx;
-            const F2 sr = sr_nx;
+            F2 Ur = Ur_nx;
+            F2 sr = sr_nx;
+            if (H2 && RC) {
+                // stage state of layer m: what stage 1 computed from the same base state and k1, and did not store
+                // (explicit_step! + upward sweep of adjust_saturation_profile! of the stage copy, heun.jl:45-49) -- the same
+                // operations in the same order as the update section of stage 1
+                F2 t1U = ld2(k1U_slot(m)), t1S = RICH ? ld2(k1S_slot(m)) : zero2;
+                if (m_is_nz) apply_top_flux(t1U, t1S);
+                if (m_is_1) apply_bottom_flux(t1U, t1S);
+                F2 Us = fma2<T>(t1U, dt, Ur), ss = sr;
+                if (RICH) {
+                    ss = fma2<T>(t1S, dt, ss) + carry1;
+                    if (!m_is_nz) {
+                        const F2 e = pos2(ss + T(-1));
+                        ss = ss - e;
+                        carry1 = e * (met.dzc(m) * met.rdzc(m + 1));
+                    } else {
+                        ss = ss - pos2(ss + T(-1));   // top excess of the stage copy (its surface excess water is not used)
+                    }
+                    if (flagx) { Us.x = A.sU[oent]; ss.x = A.sS[oent]; }
+                    if (flagy) { Us.y = A.sU[oent + 1]; ss.y = A.sS[oent + 1]; }
+                }
+                oent += (uint32_t)ld;
+                Ur = Us; sr = ss;
+            }
             F2 ln, wi;
             energy_to_temperature2(p, Ur, sr, Tn, ln, wi);
             if (RICH) Pn = pressure_head2<SOIL, T>(p, sr, wtx, met.zC(m), met.psiz(m));
@@ -465,8 +518,6 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
             const F2 Kk = min2(Kf1, sel<T>(B2{g.x < T(0), g.y < T(0)}, Kf2, Kfn));
             nqd = Kk * g;
         }
-        F2 G_top = zero2, infil_top = zero2;
-        if (LAND && j_is_nz) { G_top = ldg2(A.G + c); infil_top = ldg2(A.infil + c); }
 
         if (updates) {
             const int j = m - 2;
@@ -477,7 +528,11 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
             F2 tS = zero2;
             if (RICH) tS = fma2<T>(nqd - rd(EF_QD), rzc, p.vwcf) * p.rpor;
             F2 Ub, sb;
-            if (H2) {   // average_tendencies! (heun.jl:27-35) ; the base is the state at time n
+            if (H2 && RC) {   // average_tendencies! (heun.jl:27-35) ; k1 and the base state sit in the 8-deep rings
+                tU = (ld2(k1U_slot(j)) + tU) * T(0.5);
+                Ub = ld2(ringU(j)); sb = ld2(ringS(j));
+                if (RICH) tS = (ld2(k1S_slot(j)) + tS) * T(0.5);
+            } else if (H2) {   // average_tendencies! (heun.jl:27-35) ; the base is the state at time n
                 const uint32_t x = xring0 + (uint32_t)((j & (PF_ - 1)) * B * ES);
                 tU = (ld2(x) + tU) * T(0.5);
                 Ub = ld2(x + 2 * PF_ * B * ES);
@@ -487,19 +542,8 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
                 if (H1) { stg2(A.oTU + o, tU); if (RICH) stg2(A.oTS + o, tS); }   // k1, before the Flux BCs
                 Ub = ld2(ringU(j)); sb = ld2(ringS(j));
             }
-            if (j_is_nz) {   // Flux boundary conditions (compute_z_bcs!, abstract_timestepper.jl:69)
-                const T dz = met.dzc(nz);
-                if (LAND) { tU = F2{tU.x - G_top.x / dz, tU.y - G_top.y / dz}; if (RICH) tS = F2{tS.x - (-infil_top.x) / dz, tS.y - (-infil_top.y) / dz}; }
-                else {
-                    if (A.bc[TRM_BC_ENERGY_TOP].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_ENERGY_TOP); tU = F2{tU.x - f.x / dz, tU.y - f.y / dz}; }
-                    if (RICH && A.bc[TRM_BC_SATURATION_TOP].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_SATURATION_TOP); tS = F2{tS.x - f.x / dz, tS.y - f.y / dz}; }
-                }
-            }
-            if (j_is_1) {
-                const T dz = met.dzc(1);
-                if (A.bc[TRM_BC_ENERGY_BOTTOM].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_ENERGY_BOTTOM); tU = F2{tU.x + f.x / dz, tU.y + f.y / dz}; }
-                if (RICH && A.bc[TRM_BC_SATURATION_BOTTOM].kind == TRM_BC_FLUX) { const F2 f = bc_input(TRM_BC_SATURATION_BOTTOM); tS = F2{tS.x + f.x / dz, tS.y + f.y / dz}; }
-            }
+            if (j_is_nz) apply_top_flux(tU, tS);
+            if (j_is_1) apply_bottom_flux(tU, tS);
             // ---- explicit step ----
             const F2 Un = fma2<T>(tU, dt, Ub);
             F2 sn = sb;
@@ -521,11 +565,13 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
                     sn = sn - e;
                     Sx_new = fma2<T>(e, met.dzc(nz), Sx_new);
                 }
-                stg2(A.yS + o, sn);
+                // (recompute protocol, Heun stage 1: the stage state is not stored -- except its top layer, which the vegetation
+                //  block of stage 2 reads through surface_kernel -- and a column that goes negative rebuilds it in its slow path)
+                if (!(H1 && RC) || j_is_nz) stg2(A.yS + o, sn);
                 if (idxx == 0 && below_one(sn.x)) { idxx = j; wt_new.x = met.zF(j); }   // compute_water_table!, kernel_utils.jl:7-16
                 if (idxy == 0 && below_one(sn.y)) { idxy = j; wt_new.y = met.zF(j); }
             }
-            stg2(A.yU + o, Un);
+            if (!(H1 && RC) || j_is_nz) stg2(A.yU + o, Un);
             if (CLOSE || (LAND && has_veg(A))) {
                 F2 Tc, lc, wi;
                 energy_to_temperature2(p, Un, sn, Tc, lc, wi);
@@ -606,6 +652,13 @@ __global__ void __launch_bounds__(euler2_block<T>(), (euler2_min_blocks<T, PHYS,
         const T pr = kx < ky ? py : px;
 #pragma unroll 1
         for (; k < kmax; ++k, o += ld) rest[o] = pr;
+    }
+    if (H1 && RC) {
+        // stage 2 rebuilds the stage state of a column from the base state and k1 -- unless a layer went negative: the stage
+        // copy then needs the downward sweep, is formed here in full, stored, and the column is flagged (euler_kernel.cuh)
+        if (nx) heun1_slow_column<T, true, Met, LAND>(A, met, c); else A.hflag_out[c] = T(0);
+        if (vy) { if (ny) heun1_slow_column<T, true, Met, LAND>(A, met, c + 1); else A.hflag_out[c + 1] = T(0); }
+        return;
     }
     if (nx) euler2_slow_column<T, Met, MODE, LAND, SOIL == SOIL2_VG2>(A, met, c, Sx_new.x);
     if (ny && vy) euler2_slow_column<T, Met, MODE, LAND, SOIL == SOIL2_VG2>(A, met, c + 1, Sx_new.y);

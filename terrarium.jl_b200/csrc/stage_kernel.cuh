@@ -162,12 +162,13 @@ struct StageArgs {
 // U, sat; write U, sat, T, liq, psi) a step moves 17 values per cell. The "recompute" protocol drops the stage state from
 // memory: stage 2 rebuilds U* = U + dt (k1U + Flux BCs), sat* = adjust(sat + dt (k1S + Flux BCs)) of the entering layer from
 // the base state and k1, which it needs anyway for the update two iterations later (one 8-deep ring serves both uses):
-// 13 values per cell. Float64 only (the Float32 kernels keep the stored form); TRM_HEUN_STORE_STAGE switches it off.
+// 13 values per cell. Staged kernels of both number formats (the generic streaming kernel keeps the stored form);
+// TRM_HEUN_STORE_STAGE switches it off.
 template <class NF> __host__ __device__ constexpr bool heun_recompute() {
 #ifdef TRM_HEUN_STORE_STAGE
     return false;
 #else
-    return sizeof(NF) == 8;
+    return true;
 #endif
 }
 

@@ -181,3 +181,29 @@ def test_packed_default_hydraulics_brooks_corey_linear(stepper):
         assert np.all(np.isfinite(x)), name
         assert max_scaled_err(x, y) <= 5.0e-6, (name, max_scaled_err(x, y))
         assert max_scaled_err(x, z) <= 5.0e-5, (name, max_scaled_err(x, z))
+
+
+def test_packed_heun_negative_saturation_stage_state():
+    """Heun, recompute protocol in the pair kernels: in the SECOND step (the first one reads the stored closure fields on the
+    one-column kernel) the stage state of two thirds of the columns goes negative; the pair kernel's stage 1 then forms and
+    stores the stage state of exactly those columns and flags them -- a pair may hold one flagged and one rebuilt column --
+    and its stage 2 reads them back. Same outcome as on the one-column kernel: the same columns end with a NaN saturation
+    (tests/test_parity.py::test_heun_negative_saturation_stage_state), everything finite agrees."""
+    n = 97
+
+    def build():
+        rng = np.random.default_rng(7)
+        grid = trm.ColumnGrid(trm.B200(), np.float32, trm.UniformSpacing(dz=0.1, N=20), n)
+        model = trm.SoilModel(grid, soil=richards_soil(vwc_forcing=-1.0e-4))
+        sat0 = rng.uniform(0.014, 0.022, (20, n))
+        sat0[:, ::3] = 0.9   # every third column stays on the fast path
+        return make("cuda", model, trm.Heun(dt=60.0), initializers={"temperature": 5.0, "saturation_water_ice": sat0}, math="fast")
+
+    a, b = both(build, 1, chunks=2)
+    sa, sb = a.state.saturation_water_ice.numpy(), b.state.saturation_water_ice.numpy()
+    broken = (~np.isfinite(sb)).any(axis=0)
+    assert broken.sum() >= n // 2 and np.isfinite(sb[:, ::3]).all()
+    assert np.array_equal((~np.isfinite(sa)).any(axis=0), broken)
+    assert max_scaled_err(sa[:, ~broken], sb[:, ~broken]) <= 2.0e-6
+    Ua, Ub = a.state.internal_energy.numpy(), b.state.internal_energy.numpy()
+    assert np.isfinite(Ub).all() and max_scaled_err(Ua, Ub) <= 2.0e-6
