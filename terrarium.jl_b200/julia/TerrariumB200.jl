@@ -224,7 +224,7 @@ function Terrarium.run!(integ::B200Integrator; steps = nothing, period = nothing
     Δt = convert_dt(Δt)
     n = get_steps(steps, period, Δt)
     if isempty(integ.callbacks)
-        check(ccall((:trm_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, Δt, n), "step")      # n fused stage launches
+        check(ccall((:trm_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Int64), integ.handle, Δt, n), "step")      # n fused stage launches (small domains: one launch)
     else
         for _ in 1:n                                                                                        # host functions: step by step
             push_callbacks!(integ, current_time(integ), Δt)
@@ -495,9 +495,30 @@ Terrarium.Oceananigans.interior(a::Array) = a          # `interior(integ.state.t
 
 function Base.getproperty(integ::B200Integrator, name::Symbol)
     name === :state && return B200State(integ)
-    name === :clock && return (; time = Terrarium.current_time(integ))
+    name === :clock && return Terrarium.Oceananigans.TimeSteppers.Clock(; time = Terrarium.current_time(integ), iteration = iteration(integ))
+    name === :grid && return Terrarium.get_field_grid(getfield(integ, :model).grid)   # (as ModelIntegrator does for the output writers)
     return getfield(integ, name)
 end
+
+# ---- Oceananigans model interface (src/timesteppers/model_integrator.jl:39-66): `Simulation(integ; Δt, stop_time)`, its
+# callbacks and its output writers drive a B200Integrator like a ModelIntegrator. Output writers take functions of the
+# model next to Fields: `output_functions(integ, names)` hands them the host copy of the named fields, shaped like
+# `interior(field)`, fetched from the library when the writer's schedule fires --------------------------------------------
+function iteration(integ::B200Integrator)
+    it = Ref{Int64}(0)
+    check(ccall((:trm_get_clock, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Int64}), integ.handle, C_NULL, it), "get_clock")
+    return Int(it[])
+end
+Base.time(integ::B200Integrator) = Terrarium.current_time(integ)
+Base.eltype(::B200Integrator{NF}) where {NF} = NF
+Terrarium.Oceananigans.Solvers.iteration(integ::B200Integrator) = iteration(integ)
+Terrarium.Oceananigans.Architectures.architecture(integ::B200Integrator) = Terrarium.Oceananigans.Architectures.architecture(getfield(integ, :model).grid)
+Terrarium.Oceananigans.TimeSteppers.update_state!(integ::B200Integrator; compute_tendencies = true) =
+    check(ccall((:trm_compute_auxiliary, LIB), Cint, (Ptr{Cvoid},), integ.handle), "compute_auxiliary")
+Terrarium.Oceananigans.TimeSteppers.time_step!(integ::B200Integrator, Δt; kwargs...) = Terrarium.timestep!(integ, Δt)
+Terrarium.Oceananigans.Simulations.timestepper(integ::B200Integrator) = getfield(integ, :timestepper)
+"""`JLD2Writer(integ, output_functions(integ, (:temperature, :saturation_water_ice)); filename, schedule)`."""
+output_functions(integ::B200Integrator, names) = NamedTuple{Tuple(names)}(Tuple((m -> getproperty(m.state, n)) for n in names))
 
 function Terrarium.initialize(model::Terrarium.AbstractModel{NF, <:B200Grid}, timestepper::Terrarium.AbstractTimeStepper,
                               inputs::Terrarium.InputSource...; boundary_conditions = (;), initializers = (;), kwargs...) where {NF}
