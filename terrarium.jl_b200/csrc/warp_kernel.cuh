@@ -149,14 +149,18 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512)
         for (int d = 16; d >= 1; d >>= 1) b += __shfl_xor_sync(FULL, b, d);
         return b;
     };
-    // Oceananigans halo fill (halo_value, stage_kernel.cuh). Fast math: a Value BC is edge + (v - edge) / (D / 2) * D =
-    // edge + 2 (v - edge) without the division, evaluated with selects (every lane computes, the halo lanes keep the result)
-    auto halo = [&](int kind, NF edge, NF v, NF D, bool top) -> NF {
-        if (!FAST) return halo_value(kind, edge, v, D, top);
-        const NF val = fma_(NF(2), v - edge, edge);
-        const NF grad = top ? fma_(v, D, edge) : fma_(-v, D, edge);
-        return kind == TRM_BC_VALUE ? val : (kind == TRM_BC_GRADIENT ? grad : edge);
+    // Oceananigans halo fill (halo_value, stage_kernel.cuh). Fast math: every form is linear in the edge cell and the boundary
+    // value -- Value: edge + (v - edge) / (D / 2) * D = 2 v - edge ; Gradient: edge +- v D ; none: edge -- so the lane that forms a
+    // halo (lane nz: above the surface ; lane 0: below the bottom layer) keeps its two coefficients per field and a halo is one
+    // multiply + one FMA, selected into place (no division, no branch)
+    auto halo = [&](int kind, NF edge, NF v, NF D, bool top) -> NF { return halo_value(kind, edge, v, D, top); };
+    auto halo_coef = [&](int kind, bool top, NF& ce, NF& cv) {
+        ce = kind == TRM_BC_VALUE ? NF(-1) : NF(1);
+        cv = kind == TRM_BC_VALUE ? NF(2) : (kind == TRM_BC_GRADIENT ? (top ? dzf_k : -dzf_k) : NF(0));
     };
+    NF ceT, cvT, ceP, cvP;
+    halo_coef(isH ? kT_top : kT_bot, isH, ceT, cvT);
+    halo_coef(isH ? kP_top : kP_bot, isH, ceP, cvP);
     auto kappa_dry = [&]() -> NF { return FAST ? thermal_conductivity_fast(p, NF(0), NF(1)) : thermal_conductivity(p, NF(0), NF(1)); };
 
     // compute_auxiliary! + compute_tendencies! on the state (Ux, sx, wtx): tendencies of this lane's layer, before Flux BCs
@@ -190,16 +194,16 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512)
         if (FAST) {
             // halo cell above the surface (lane nz, from layer nz) and below the bottom layer (lower neighbour of lane 0)
             // (fill_halo_regions!), branch free
-            const NF Th = halo(kT_top, T_dn, bT_top, dzf_k, true), Tb = halo(kT_bot, T, bT_bot, dzf_k, false);
+            const NF hT = fma_(cvT, isH ? bT_top : bT_bot, ceT * (isH ? T_dn : T));
             const NF kd = halo_copy ? NF(0) : kappa_dry();
-            T = isH ? Th : T;
+            T = isH ? hT : T;
             kap = isH ? (halo_copy ? kap_dn : kd) : kap;
-            Tp = isBot ? Tb : Tp;
+            Tp = isBot ? hT : Tp;
             kapp = isBot ? (halo_copy ? kap : kd) : kapp;
             if (RICH) {
-                const NF Ph = halo(kP_top, P_dn, bP_top, dzf_k, true), Pb = halo(kP_bot, P, bP_bot, dzf_k, false);
-                P = isH ? Ph : P;
-                Pp = isBot ? Pb : Pp;
+                const NF hP = fma_(cvP, isH ? bP_top : bP_bot, ceP * (isH ? P_dn : P));
+                P = isH ? hP : P;
+                Pp = isBot ? hP : Pp;
             }
         } else {
             if (isH) {
