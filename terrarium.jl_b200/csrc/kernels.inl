@@ -58,7 +58,8 @@ cudaError_t launch_euler_mode(int mode, const StageArgs<NF>& a, cudaStream_t st)
     if (mode == MODE_HEUN2) {   // stage state: always recomputed
         constexpr bool H2_VG2 = kFast && phys_richards(PHYS);
         if (H2_VG2 && a.p.vg_n_is_2 && a.p.swrc == TRM_SWRC_VANGENUCHTEN && a.p.unsat_k == TRM_UNSATK_VANGENUCHTEN)
-            return launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2, H2_VG2>(a, st);
+            return compact ? launch_euler_variant<NF, PHYS, 0, EULER_MS_SMALL, MODE_HEUN2, H2_VG2>(a, st)
+                           : launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2, H2_VG2>(a, st);
         return launch_euler_variant<NF, PHYS, 0, MET_STRIDE, MODE_HEUN2>(a, st);
     }
     if (vg2) return compact ? launch_euler_variant<NF, PHYS, LOAD, EULER_MS_SMALL, MODE_EULER, CAN_VG2>(a, st)
@@ -90,7 +91,7 @@ cudaError_t launch_euler2_mode(int mode, const StageArgs<T>& a, cudaStream_t st)
     const bool compact = a.nz + 3 <= EULER_MS_SMALL;
     if constexpr (sizeof(T) == 4) {
         if (mode == MODE_HEUN1) return compact ? launch_euler2_variant<T, PHYS, EULER_MS_SMALL, MODE_HEUN1, SOIL>(a, st) : launch_euler2_variant<T, PHYS, MET_STRIDE, MODE_HEUN1, SOIL>(a, st);
-        if (mode == MODE_HEUN2) return launch_euler2_variant<T, PHYS, MET_STRIDE, MODE_HEUN2, SOIL>(a, st);
+        if (mode == MODE_HEUN2) return compact ? launch_euler2_variant<T, PHYS, EULER_MS_SMALL, MODE_HEUN2, SOIL>(a, st) : launch_euler2_variant<T, PHYS, MET_STRIDE, MODE_HEUN2, SOIL>(a, st);
     }
     return compact ? launch_euler2_variant<T, PHYS, EULER_MS_SMALL, MODE_EULER, SOIL>(a, st) : launch_euler2_variant<T, PHYS, MET_STRIDE, MODE_EULER, SOIL>(a, st);
 }
