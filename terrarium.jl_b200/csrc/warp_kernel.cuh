@@ -59,7 +59,8 @@ __device__ __forceinline__ NF cell_conductivity_linear_fast(const DevParams<NF>&
 }
 
 template <class NF, bool RICH, bool FAST, int SOIL, bool LAND = false>
-__global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512) / TRM_WARP_BLOCK) /* <= 64 / 128 registers: 32 / 16 warps per SM */ column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, const int heun) {
+__global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512) / TRM_WARP_BLOCK)   // <= 64 / 128 registers: 32 / 16 warps per SM
+column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, const int heun) {
     using Mx = M<NF, FAST>;
     constexpr bool VG2 = SOIL == WSOIL_VG2;
     constexpr unsigned FULL = 0xffffffffu;
@@ -67,8 +68,8 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512)
     // A block owns CW adjacent columns. Fields are [layer][column]: a lane of a column's warp would touch one 4-byte element
     // of a sector per access, so the block moves its nz x CW tile of every field between global and shared memory with all
     // threads (CW consecutive threads = one contiguous row segment: 16 / 32 bytes of a 32-byte sector in Float32 / Float64
-    // instead of 4 / 8) and the warps pick their column out of the tile. That matters when a launch advances one step only (LandModel, per-step callers): loads and stores are
-    // then the larger part of the launch.
+    // instead of 4 / 8) and the warps pick their column out of the tile. That matters when a launch advances one step only
+    // (LandModel, per-step callers): loads and stores are then the larger part of the launch.
     constexpr int CW = TRM_WARP_BLOCK / 32, TS = CW + 1;   // (odd row stride: the column reads are bank-conflict free)
     __shared__ NF tile[5][32 * TS];
     const int wi = threadIdx.x >> 5;
@@ -153,7 +154,6 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512)
     // value -- Value: edge + (v - edge) / (D / 2) * D = 2 v - edge ; Gradient: edge +- v D ; none: edge -- so the lane that forms a
     // halo (lane nz: above the surface ; lane 0: below the bottom layer) keeps its two coefficients per field and a halo is one
     // multiply + one FMA, selected into place (no division, no branch)
-    auto halo = [&](int kind, NF edge, NF v, NF D, bool top) -> NF { return halo_value(kind, edge, v, D, top); };
     auto halo_coef = [&](int kind, bool top, NF& ce, NF& cv) {
         ce = kind == TRM_BC_VALUE ? NF(-1) : NF(1);
         cv = kind == TRM_BC_VALUE ? NF(2) : (kind == TRM_BC_GRADIENT ? (top ? dzf_k : -dzf_k) : NF(0));
@@ -207,14 +207,14 @@ __global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512)
             }
         } else {
             if (isH) {
-                T = halo(kT_top, T_dn, bT_top, dzf_k, true);
+                T = halo_value(kT_top, T_dn, bT_top, dzf_k, true);
                 kap = halo_copy ? kap_dn : kappa_dry();
-                if (RICH) P = halo(kP_top, P_dn, bP_top, dzf_k, true);
+                if (RICH) P = halo_value(kP_top, P_dn, bP_top, dzf_k, true);
             }
             if (isBot) {
-                Tp = halo(kT_bot, T, bT_bot, dzf_k, false);
+                Tp = halo_value(kT_bot, T, bT_bot, dzf_k, false);
                 kapp = halo_copy ? kap : kappa_dry();
-                if (RICH) Pp = halo(kP_bot, P, bP_bot, dzf_k, false);
+                if (RICH) Pp = halo_value(kP_bot, P, bP_bot, dzf_k, false);
             }
         }
         // heat flux and head gradient at face k (diffusive_heat_flux, soil_energy.jl:134-149), faces 1 .. nz + 1
