@@ -238,11 +238,14 @@ struct Euler2Smem {
 #ifndef TRM_EULER2_BLOCKS
 #define TRM_EULER2_BLOCKS 6
 #endif
+#ifndef TRM_EULER2_H2_BLOCKS
+#define TRM_EULER2_H2_BLOCKS 4   // Float32 Heun stage 2
+#endif
 #ifndef TRM_EULER2_F64_BLOCKS
 #define TRM_EULER2_F64_BLOCKS 4   // 16-byte slots: 52 KB of shared memory per 128-thread block (10 strip slots + the rings)
 #endif
 template <class T, int PHYS, int MODE, int MS>
-constexpr int euler2_min_blocks() { return sizeof(T) == 8 ? ((phys_land(PHYS) || MS != EULER_MS_SMALL) ? 3 : TRM_EULER2_F64_BLOCKS) : (MODE == MODE_HEUN2 ? 4 : (phys_land(PHYS) ? 5 : TRM_EULER2_BLOCKS)); }
+constexpr int euler2_min_blocks() { return sizeof(T) == 8 ? ((phys_land(PHYS) || MS != EULER_MS_SMALL) ? 3 : TRM_EULER2_F64_BLOCKS) : (MODE == MODE_HEUN2 ? TRM_EULER2_H2_BLOCKS : (phys_land(PHYS) ? 5 : TRM_EULER2_BLOCKS)); }
 
 // slow path of one column: a layer went negative. Downward sweep (soil_hydrology.jl:201-216) top -> bottom on the raw
 // profile the thread has just stored, then water table and closures bottom -> top (same code as the scalar kernel).

@@ -34,6 +34,9 @@ namespace trm {
 #ifndef TRM_EULER_F32_BLOCKS
 #define TRM_EULER_F32_BLOCKS 8
 #endif
+#ifndef TRM_EULER_H2_BLOCKS
+#define TRM_EULER_H2_BLOCKS 4    // Heun stage 2 (second ring: 44 - 52 KB of shared memory per block)
+#endif
 #ifndef TRM_EULER_LAND_BLOCKS
 #define TRM_EULER_LAND_BLOCKS 6   // the LandModel variants no longer contain the surface block (surface_kernel): same budget as the soil kernel
 #endif
@@ -42,7 +45,7 @@ namespace trm {
 // gets a looser bound.
 template <class NF, int PHYS, bool FAST, int MODE = MODE_EULER>
 constexpr int euler_min_blocks() {
-    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? 4 : (phys_land(PHYS) ? TRM_EULER_LAND_BLOCKS : (sizeof(NF) == 4 ? TRM_EULER_F32_BLOCKS : TRM_EULER_MIN_BLOCKS)));
+    return !FAST ? (sizeof(NF) == 8 ? 3 : 4) : (MODE == MODE_HEUN2 ? TRM_EULER_H2_BLOCKS : (phys_land(PHYS) ? TRM_EULER_LAND_BLOCKS : (sizeof(NF) == 4 ? TRM_EULER_F32_BLOCKS : TRM_EULER_MIN_BLOCKS)));
 }
 
 // volatile without a "memory" clobber: the shared-memory accesses of a thread keep their program order among
