@@ -223,6 +223,13 @@ REPLAYS = [
     (test_vegetation.test_land_model_energy_and_water_budgets_close, dict(engine="cuda", vegetated=True)),
     (test_vegetation.test_land_model_energy_and_water_budgets_close, dict(engine="cuda", vegetated=False)),
     (test_host_io.test_mapped_host_exchange_land_model, {}),
+    # randomised regimes (frozen / thawing / saturated / dry layers next to each other in one column = in one warp)
+    (test_parity.test_fast_math_regimes_randomised, dict(seed=0)),
+    (test_parity.test_fast_math_regimes_randomised, dict(seed=1)),
+    (test_parity.test_fast_math_regimes_randomised, dict(seed=2)),
+    (test_parity.test_fast_math_regimes_randomised, dict(seed=3)),
+    (test_parity.test_fast_math_regimes_randomised, dict(seed=4)),
+    (test_parity.test_fast_math_regimes_randomised, dict(seed=5)),
 ]
 
 
