@@ -29,3 +29,23 @@ for nf, name in ((np.float32, "f32"), (np.float64, "f64")):
                 row.append(1e3 * best / 300)
                 g.close()
             print(f"{name} {'heun ' if heun else 'euler'} {ncol:7d} columns: streaming {row[0]:8.2f} us/step   warp-per-column {row[1]:8.2f} us/step", flush=True)
+
+# ---- one step per call (per-step callers, host-evaluated boundary conditions): the tile copies are paid every step ----
+print("one step per trm_step call:")
+for nf, name in ((np.float32, "f32"), (np.float64, "f64")):
+    for heun in (False, True):
+        for ncol in (8192, 16384, 32768, 57344):
+            row = []
+            for warp in ("0", "1"):
+                os.environ["TRM_WARP"] = warp
+                g = synthetic_soil_case("cuda", ncol, nf=nf, heun=heun, math="fast")
+                g.step(60.0, 5)
+                tot = 0.0
+                for _ in range(100):
+                    g.step(60.0, 1)
+                    ms = C.c_float()
+                    g._lib.check(g._lib.last_step_ms(g._h, C.byref(ms)), "last_step_ms")
+                    tot += ms.value
+                row.append(1e3 * tot / 100)
+                g.close()
+            print(f"{name} {'heun ' if heun else 'euler'} {ncol:7d} columns: streaming {row[0]:8.2f} us/step   warp-per-column {row[1]:8.2f} us/step", flush=True)

@@ -563,21 +563,36 @@ struct Handle : HandleBase {
     bool heun_rc() const { return heun_recompute<NF>() && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     bool split_surface() const { return land && euler_impl == 1 && (uint64_t)nz * (uint64_t)ld < (1ull << 32); }
     int enqueue_steps(double dt, int64_t n);
-    // small domains (warp_kernel.cuh): one warp per column, several steps per launch (LandModel: surface_kernel + one
-    // launch per step, both Heun stages in it). Applies with nz <= 31 while the column count leaves the one-thread-per-column kernels latency bound (less than about one wave of
-    // warps). Measured crossover with the streaming kernels (profiles/r02_warp_crossover.txt): ~115 k columns in Float32
-    // (Heun: ~200 k), ~55 k in Float64 (lanes = layers of one column diverge where adjacent columns of one layer do not, and
-    // the Float64 fast-math sequences are longer): default limit 114688 / 49152 columns (TRM_WARP_COLS overrides it ;
-    // TRM_WARP=0 switches the kernel off ; tests compare both within a process).
-    bool use_warp() const {
+    // Small domains (warp_kernel.cuh): one warp per column, several steps per launch (LandModel: surface_kernel + one launch
+    // per step, both Heun stages in it). Applies with nz <= 31 while the column count leaves the one-thread-per-column
+    // kernels latency bound (less than about one wave of warps). Measured crossover with the streaming kernels
+    // (profiles/r02_warp_crossover.txt): ~115 k columns in Float32 (Heun: ~200 k), ~55 k in Float64 (lanes = layers of one
+    // column diverge where adjacent columns of one layer do not, and the Float64 fast-math sequences are longer): default
+    // limit 114688 / 49152 columns. A launch that advances ONE step only -- LandModel (the surface block runs in between),
+    // inputs whose descriptor changes per step, a bound host exchange, a caller that asks for one step per call -- has much
+    // lower limits (see use_warp). TRM_WARP_COLS overrides the limit, TRM_WARP=0 switches the kernel off (tests compare
+    // both within a process).
+    bool steps_one_by_one() const {
+        if (land || hio.nslots != 0) return true;
+        for (int i = 0; i < TRM_IN_COUNT; ++i)
+            if (in[i].kind == TRM_SRC_TABLE || in[i].kind == TRM_SRC_RASTER || in[i].kind == TRM_SRC_FIELD_PAIR) return true;
+        return false;
+    }
+    bool use_warp(int64_t n) const {
         if (euler_impl != 1 || nz > 31) return false;
         const char* e = std::getenv("TRM_WARP");
         if (e && e[0] == '0') return false;
         const char* m = std::getenv("TRM_WARP_COLS");
-        // LandModel: one step per launch (the surface block runs in between), so the copies of the column tile between global
-        // memory and the registers are paid every step: the streaming kernels win earlier (N145, vegetated, Float32: 73 against
-        // 53 us per ForwardEuler step ; N72: 46 against 101 us per Heun step)
-        const int64_t max_cols = m ? std::atoll(m) : (land ? (sizeof(NF) == 4 ? 32768 : 16384) : (sizeof(NF) == 4 ? 114688 : 49152));
+        const bool single = n <= 1 || steps_one_by_one(), f32 = sizeof(NF) == 4;
+        int64_t max_cols = f32 ? 114688 : 49152;
+        if (single) {
+            // measured (profiles/r02_warp_crossover.txt, r02_small_domains.csv): a one-step launch pays its fixed latencies
+            // (metrics, tile, boundary inputs, closure) in every step -- ~23 us on 8192 columns against 2.6 us per step of a
+            // 600-step launch -- and only wins where it replaces several streaming launches: Heun, and the LandModel under Heun
+            if (heun) max_cols = land ? (f32 ? 32768 : 16384) : (f32 ? 16384 : 8192);
+            else max_cols = f32 ? 8192 : 4096;
+        }
+        if (m) max_cols = std::atoll(m);
         return nc <= max_cols;
     }
     int enqueue_steps_warp(NF dt, int64_t n);
@@ -679,9 +694,7 @@ template <> cudaError_t Handle<double>::call_warp(int nsteps, const StageArgs<do
 // included. Inputs whose descriptor changes from step to step on the host side (tables / rasters: time bracket ; host
 // evaluated functions: value pair ; a mapped host exchange: ring slot) limit a launch to one step.
 template <class NF> int Handle<NF>::enqueue_steps_warp(NF dt, int64_t n) {
-    bool per_step = hio.nslots != 0 || land;   // LandModel: the surface block is a launch of its own before every step
-    for (int i = 0; i < TRM_IN_COUNT; ++i)
-        if (in[i].kind == TRM_SRC_TABLE || in[i].kind == TRM_SRC_RASTER || in[i].kind == TRM_SRC_FIELD_PAIR) per_step = true;
+    const bool per_step = steps_one_by_one();   // (LandModel: the surface block is a launch of its own before every step)
     int64_t done = 0;
     while (done < n) {
         const int64_t chunk = per_step ? 1 : std::min<int64_t>(n - done, 1 << 30);
@@ -761,7 +774,7 @@ template <class NF> int Handle<NF>::enqueue_steps(double dt_, int64_t n) {
     CU(cudaSetDevice(device));
     const NF dt = (NF)dt_;
     CU(cudaEventRecord(ev0, stream));
-    if (use_warp()) {
+    if (use_warp(n)) {
         if (int rc = enqueue_steps_warp(dt, n)) return rc;
         CU(cudaEventRecord(ev1, stream));
         timing_open = true;
