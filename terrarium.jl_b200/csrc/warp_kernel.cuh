@@ -114,10 +114,11 @@ column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, co
 #pragma unroll
     for (int q = 0; q < TRM_BC_NSLOTS; ++q) bcv[q] = NF(0);
     int si = 0;   // step index inside the current block of BC_BLOCK steps
-    auto refresh_bcs = [&]() {
+    auto refresh_bcs = [&](int remaining) {   // `remaining` steps of the launch: lanes beyond it hold values nobody reads
         NF tl = t;
+        const int adds = min(lane, remaining);
 #pragma unroll 1
-        for (int i = 0; i < lane; ++i) tl = tl + dt;
+        for (int i = 0; i < adds; ++i) tl = tl + dt;
 #pragma unroll
         for (int q = 0; q < TRM_BC_NSLOTS; ++q)
             if (A.bc[q].kind != TRM_BC_DEFAULT) bcv[q] = eval_input(A.in[A.bc[q].input], c, tl, lane == 0 ? 0 : 1);
@@ -360,7 +361,7 @@ column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, co
 #pragma unroll 1
     for (int step = 0; step < nsteps; ++step) {
         if (si == BC_BLOCK) si = 0;
-        if (si == 0) refresh_bcs();
+        if (si == 0) refresh_bcs(nsteps - step);
         NF tU, tS, liq_x;
         evaluate(U, s, wt, false, loaded, tU, tS, liq_x);
         loaded = false;
