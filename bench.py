@@ -451,7 +451,7 @@ def main():
             del it2
 
     # ---- small domains (one GPU): the same soil workload at the column counts of the reference's own configurations, 600
-    #      steps per trm_step call. Below 114 688 (Float32) / 49 152 (Float64) columns the library runs them on the
+    #      steps per trm_step call. Below 114 688 (Float32) / 65 536 (Float64) columns the library runs them on the
     #      warp-per-column kernel (csrc/warp_kernel.cuh: all steps of a call in one launch, state in registers -- no HBM
     #      roofline applies, the figure is time per step); TRM_WARP=0 gives the streaming kernels' time next to it. ----
     small_lines = []

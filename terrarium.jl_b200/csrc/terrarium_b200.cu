@@ -566,9 +566,9 @@ struct Handle : HandleBase {
     // Small domains (warp_kernel.cuh): one warp per column, several steps per launch (LandModel: surface_kernel + one launch
     // per step, both Heun stages in it). Applies with nz <= 31 while the column count leaves the one-thread-per-column
     // kernels latency bound (less than about one wave of warps). Measured crossover with the streaming kernels
-    // (profiles/r02_warp_crossover.txt): ~115 k columns in Float32 (Heun: ~200 k), ~55 k in Float64 (lanes = layers of one
+    // (profiles/r02_warp_crossover.txt): ~115 k columns in Float32 (Heun: ~200 k), ~80 k in Float64 (lanes = layers of one
     // column diverge where adjacent columns of one layer do not, and the Float64 fast-math sequences are longer): default
-    // limit 114688 / 49152 columns. A launch that advances ONE step only -- LandModel (the surface block runs in between),
+    // limit 114688 / 65536 columns. A launch that advances ONE step only -- LandModel (the surface block runs in between),
     // inputs whose descriptor changes per step, a bound host exchange, a caller that asks for one step per call -- has much
     // lower limits (see use_warp). TRM_WARP_COLS overrides the limit, TRM_WARP=0 switches the kernel off (tests compare
     // both within a process).
@@ -584,7 +584,7 @@ struct Handle : HandleBase {
         if (e && e[0] == '0') return false;
         const char* m = std::getenv("TRM_WARP_COLS");
         const bool single = n <= 1 || steps_one_by_one(), f32 = sizeof(NF) == 4;
-        int64_t max_cols = f32 ? 114688 : 49152;
+        int64_t max_cols = f32 ? 114688 : 65536;
         if (single) {
             // measured (profiles/r02_warp_crossover.txt, r02_small_domains.csv): a one-step launch pays its fixed latencies
             // (metrics, tile, boundary inputs, closure) in every step -- ~23 us on 8192 columns against 2.6 us per step of a

@@ -28,6 +28,11 @@ namespace trm {
 #ifndef TRM_WARP_BLOCK
 #define TRM_WARP_BLOCK 128   // four adjacent columns per block (measured equal to eight: profiles/r02_summary.md)
 #endif
+#ifndef TRM_WARP_F64_THREADS
+// resident threads per SM the Float64 fast-math instantiations must allow. Measured on 14 017 / 49 152 columns (us per step,
+// ForwardEuler): 512 threads (<= 128 registers) 8.51 / 27.9 ; 640 (96) 7.65 / 24.6 ; 768 (80, 48-96 bytes of spills) 7.28 / 22.9
+#define TRM_WARP_F64_THREADS 768
+#endif
 constexpr int WARP_MAX_NZ = 31;   // lane nz is the halo cell above the surface
 
 enum WarpSoil { WSOIL_GENERIC = 0 /* run-time tests, general formulas out of line */, WSOIL_VG2 = 1 /* van Genuchten n = 2 */,
@@ -59,7 +64,7 @@ __device__ __forceinline__ NF cell_conductivity_linear_fast(const DevParams<NF>&
 }
 
 template <class NF, bool RICH, bool FAST, int SOIL, bool LAND = false>
-__global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : 512) / TRM_WARP_BLOCK)   // <= 64 / 128 registers: 32 / 16 warps per SM
+__global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : (FAST ? TRM_WARP_F64_THREADS : 512)) / TRM_WARP_BLOCK)   // <= 64 / 80 (faithful: 128) registers
 column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, const int heun) {
     using Mx = M<NF, FAST>;
     constexpr bool VG2 = SOIL == WSOIL_VG2;

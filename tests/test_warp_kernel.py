@@ -1,7 +1,7 @@
 """Small domains: the warp-per-column kernel (csrc/warp_kernel.cuh; lane = layer, several steps per launch, both Heun stages in
 one launch) against the one-thread-per-column streaming kernels of the same math mode and against the oracle.
 
-The library picks this kernel by itself for the SoilModel on up to 114 688 (Float32) / 49 152 (Float64) columns (TRM_WARP_COLS) with at most 31 layers; the
+The library picks this kernel by itself for the SoilModel on up to 114 688 (Float32) / 65 536 (Float64) columns (TRM_WARP_COLS) with at most 31 layers; the
 rest of the suite pins the streaming kernels (tests/conftest.py), this module switches the warp path on around its runs and
 replays the parity / known-answer tests of the other modules through it."""
 import os
