@@ -33,6 +33,9 @@ namespace trm {
 // ForwardEuler): 512 threads (<= 128 registers) 8.51 / 27.9 ; 640 (96) 7.65 / 24.6 ; 768 (80, 48-96 bytes of spills) 7.28 / 22.9
 #define TRM_WARP_F64_THREADS 768
 #endif
+#ifndef TRM_WARP_F32_THREADS
+#define TRM_WARP_F32_THREADS 1024   // Float32: <= 64 registers (1280 threads / 48 registers measured 2-5 % slower; Float64 with 1024 / 64: +5 % on full domains, -12 % on a single column)
+#endif
 constexpr int WARP_MAX_NZ = 31;   // lane nz is the halo cell above the surface
 
 enum WarpSoil { WSOIL_GENERIC = 0 /* run-time tests, general formulas out of line */, WSOIL_VG2 = 1 /* van Genuchten n = 2 */,
@@ -64,7 +67,7 @@ __device__ __forceinline__ NF cell_conductivity_linear_fast(const DevParams<NF>&
 }
 
 template <class NF, bool RICH, bool FAST, int SOIL, bool LAND = false>
-__global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? 1024 : (FAST ? TRM_WARP_F64_THREADS : 512)) / TRM_WARP_BLOCK)   // <= 64 / 80 (faithful: 128) registers
+__global__ void __launch_bounds__(TRM_WARP_BLOCK, (sizeof(NF) == 4 ? TRM_WARP_F32_THREADS : (FAST ? TRM_WARP_F64_THREADS : 512)) / TRM_WARP_BLOCK)   // <= 64 / 80 (faithful: 128) registers
 column_warp_kernel(const __grid_constant__ StageArgs<NF> A, const int nsteps, const int heun) {
     using Mx = M<NF, FAST>;
     constexpr bool VG2 = SOIL == WSOIL_VG2;
